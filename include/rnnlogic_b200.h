@@ -1,0 +1,197 @@
+/*
+ * rnnlogic_b200 -- C-ABI of the B200-native (sm_100a) reasoning-predictor hot path.
+ *
+ * Drop-in boundary.  The reference (DeepGraphLearning/RNNLogic) has no FFI: its boundary for
+ * this path is Python (src/data.py, src/predictors.py, src/trainer.py).  Each entry point
+ * below names the reference interface it replaces (file:line relative to /root/reference);
+ * the Python classes of the same names in rnnlogic_b200/ (re-exported by compat/) bind these
+ * symbols with ctypes (rnnlogic_b200/_lib.py).  INTEGRATION.md shows the binding a reference
+ * maintainer would add.
+ *
+ * Conventions
+ *  - plain C: pointers + sizes only, no torch types.  All `const T*` inside the structs are
+ *    DEVICE pointers (cudaMalloc / torch caching allocator); the structs themselves are host
+ *    memory and are passed by pointer.  `stream` is a cudaStream_t cast to void*.
+ *  - every function returns 0 on success, a negative rl_status otherwise; the message of the
+ *    last failure on the calling thread is rl_last_error().  Nothing here synchronises the
+ *    device or allocates device memory; kernels are enqueued on `stream`.
+ *  - queries are processed in SLOTS of RL_LANES = 32 queries that share one head relation
+ *    (the reference's single-relation batch, predictors.py:55,212).  All per-slot matrices
+ *    are ENTITY-MAJOR: X[row][lane], one 128-byte line per row for 32-bit counts.
+ */
+#ifndef RNNLOGIC_B200_H
+#define RNNLOGIC_B200_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define RL_LANES 32
+#define RL_ABI_VERSION 1
+
+enum rl_status {
+    RL_OK = 0,
+    RL_ERR_ARG = -1,      /* bad argument (null pointer, size, level out of range) */
+    RL_ERR_CUDA = -2,     /* a CUDA runtime call / launch failed */
+    RL_ERR_NO_DEVICE = -3 /* no CUDA device visible: there is NO CPU fallback */
+};
+
+/* Knowledge graph, replaces KnowledgeGraph.relation2adjacency / relation2ht2index
+ * (src/data.py:39-40,63-69,101-104).  Relation-sorted DCSR *by destination*: for relation rho
+ * the distinct tails are rows [dst_ptr[rho], dst_ptr[rho+1]); row k has tail row_dst[k] and
+ * in-edges edge_src[row_start[k] .. row_start[k+1]).  rank_tab answers "which row of relation
+ * rho is entity e" with one 8-byte load: word w = e>>5 holds {bits, rows before this word}.
+ * ord_* keep the reference's per-relation edge order (train.txt order) so that an
+ * `edges_to_remove` index (data.py:164-170) maps to its (head, tail). ent_* is the transpose:
+ * for entity e the (relation, row-within-relation) pairs where e is a tail. */
+typedef struct rl_graph {
+    int32_t num_entities, num_relations, rank_words, total_rows, num_edges;
+    const int32_t *dst_ptr;    /* [R+1]            */
+    const int32_t *row_dst;    /* [total_rows]     */
+    const int32_t *row_start;  /* [total_rows+1]   */
+    const int32_t *edge_src;   /* [E]              */
+    const uint32_t *rank_tab;  /* [R*rank_words*2] */
+    const int32_t *ord_ptr;    /* [R+1]            */
+    const int32_t *ord_h;      /* [E] head of the k-th train edge of the relation */
+    const int32_t *ord_t;      /* [E] tail ...                                    */
+    const int32_t *ent_ptr;    /* [N+1]            */
+    const int32_t *ent_rel;    /* [total_rows]     */
+    const int32_t *ent_row;    /* [total_rows] row index local to the relation */
+} rl_graph;
+
+/* Compiled rule set, replaces Predictor.relation2rules (src/predictors.py:46-49, 186-189).
+ * Per head relation the rule bodies form a prefix trie (one node per distinct non-empty body
+ * prefix); nodes of one head are contiguous and ordered by depth.  A node's frontier is a
+ * [rows(node_rel) x 32] block at row offset node_row_off inside the slot's arena.  Work is cut
+ * into chunks of <= 32 consecutive rows of one node; lvl_ptr[q*(max_len+1)+d] .. [..+d+1] is
+ * the chunk range of depth d+1 of head q.  term_* lists, per (head, last relation), the
+ * (node, rule id) pairs of rules ending at a node; zr_* the rules with an empty body. */
+typedef struct rl_rules {
+    int32_t num_nodes, num_rules, max_len, num_chunks, num_terms;
+    const int32_t *node_rel;      /* [num_nodes] */
+    const int32_t *node_parent;   /* [num_nodes] global node id, -1 = the one-hot root */
+    const int64_t *node_row_off;  /* [num_nodes] */
+    const int32_t *head_node_ptr; /* [R+1] */
+    const int32_t *lvl_ptr;       /* [R*(max_len+1)] */
+    const int32_t *chunk_node;    /* [num_chunks] */
+    const int32_t *chunk_row0;    /* [num_chunks] first row, local to the node */
+    const int32_t *term_ptr;      /* [R*R+1] key = head*R + last relation */
+    const int32_t *term_node;     /* [num_terms] */
+    const int32_t *term_rule;     /* [num_terms] */
+    const int32_t *zr_ptr;        /* [R+1] */
+    const int32_t *zr_rule;       /* [#empty-body rules] */
+} rl_rules;
+
+/* One call's queries, cut into slots (<= 32 queries of one head relation each). */
+typedef struct rl_slots {
+    int32_t num_slots;
+    const int32_t *slot_head;  /* [S] head relation */
+    const int32_t *lane_h;     /* [S*32] query entity, -1 = padding lane */
+    const int32_t *lane_t;     /* [S*32] answer entity (train / eval), -1 = none */
+    const int32_t *lane_eh;    /* [S*32] head of the removed edge, -1 = no removal */
+    const int32_t *lane_et;    /* [S*32] tail of the removed edge */
+    const int64_t *arena_off;  /* [S] first arena row of the slot */
+    const int32_t *nz_off;     /* [S] first node_nz entry of the slot */
+} rl_slots;
+
+/* Known-answer lists, replaces KnowledgeGraph.hr2o / hr2oo / hr2ooo (src/data.py:36-38,49-61,
+ * 79-99): sorted keys r*N+h, CSR of de-duplicated tails.  Used for the smoothed multi-hot
+ * target (data.py:207-212) and the eval filter (data.py:250-254, 287-291). */
+typedef struct rl_answers {
+    int64_t num_keys;
+    const int64_t *keys;  /* [num_keys] ascending */
+    const int32_t *ptr;   /* [num_keys+1] */
+    const int32_t *ent;   /* [ptr[num_keys]] */
+} rl_answers;
+
+int rl_abi_version(void);
+const char *rl_last_error(void);
+/* Number of visible CUDA devices (>= 1) or RL_ERR_NO_DEVICE. */
+int rl_device_count(void);
+
+/* Fill lane_h / lane_t / lane_eh / lane_et from the reference's batch tensors
+ * (all_h, all_t, edges_to_remove int64[Q] on the device; trainer.py:69-82).  Query i of slot s
+ * is q_off[s] + lane (q_off is a DEVICE int32[S+1]).  all_t / edges_to_remove may be NULL. */
+int rl_prepare_slots(const rl_graph *g, int32_t num_slots, const int32_t *slot_head,
+                     const int32_t *q_off, const int64_t *all_h, const int64_t *all_t,
+                     const int64_t *edges_to_remove, int32_t *lane_h, int32_t *lane_t,
+                     int32_t *lane_eh, int32_t *lane_et, void *stream);
+
+/* Kernel (1): frontier expansion of one trie depth for every slot, replaces
+ * KnowledgeGraph.propagate (src/data.py:149-173) for all rules of the head at once.
+ * count_bits = 32 (uint32 rows, *overflow set to 1 when a count does not fit) or 64 (wraps
+ * like the reference's int64).  grid_chunks = max over the call's slots of the number of
+ * chunks at this depth.  node_nz[nz_off[s] + local node] is set to 1 when a node has a
+ * non-zero count; with skip_empty != 0 the children of an all-zero node are not computed
+ * (their rows are then undefined and every consumer honours node_nz). */
+int rl_expand_level(const rl_graph *g, const rl_rules *r, const rl_slots *s, int32_t depth,
+                    int32_t grid_chunks, int32_t count_bits, void *arena, int32_t *node_nz,
+                    int32_t *overflow, int32_t skip_empty, void *stream);
+
+/* Debug / API parity: dense int64[32][N] (lane-major, like the reference's [B,N]) counts of
+ * one trie node of one slot; node < 0 selects the one-hot root (empty body).  Replaces the
+ * return value of KnowledgeGraph.grounding (src/data.py:147). */
+int rl_node_counts_dense(const rl_graph *g, const rl_rules *r, const rl_slots *s, int32_t slot,
+                         int32_t node, int32_t count_bits, const void *arena,
+                         const int32_t *node_nz, int32_t skip_empty, int64_t *out, void *stream);
+
+/* Kernel (2a): rule-weight aggregation, replaces the loop of Predictor.forward
+ * (src/predictors.py:58-65,73-78).  Z[S][N][32] fp32 = sum_rule w_rule * fp32(count) (+ bias[e]
+ * when bias != NULL).  nzmask[S][N]: bit b set <=> sum_rule count[e][b] != 0.  With
+ * fill_neg_inf != 0 cells with a clear bit get -inf (entity_feature != 'bias'). */
+int rl_predictor_scores(const rl_graph *g, const rl_rules *r, const rl_slots *s,
+                        int32_t count_bits, const void *arena, const int32_t *node_nz,
+                        int32_t skip_empty, const float *rule_weights, const float *bias,
+                        int32_t fill_neg_inf, float *Z, uint32_t *nzmask, void *stream);
+
+/* Kernel (2b): log(softmax + 1e-8) cross-entropy against the smoothed target, replaces
+ * src/trainer.py:84,88-89, fused with its backward.  target = smoothing * multi_hot(train
+ * answers of (h, head)) + (1 - smoothing) * one_hot(t).  Outputs, per slot:
+ * loss[S] (already divided by max(sum target, 1)), tsum[S]; G[S][N][32] = dloss_s/dZ.
+ * use_mask != 0 <=> entity_feature != 'bias' (only cells with their nzmask bit take part).
+ * partial is scratch of S * nblk * 64 floats with nblk = rl_softmax_blocks(N). */
+int rl_softmax_blocks(int32_t num_entities);
+int rl_softmax_ce(const rl_graph *g, const rl_slots *s, const rl_answers *train_answers,
+                  float smoothing, int32_t use_mask, const float *Z, const uint32_t *nzmask,
+                  float *partial, float *stats, float *loss, float *tsum, float *G,
+                  void *stream);
+
+/* Kernel (2c): backward into rule weights and bias, replaces autograd through
+ * src/predictors.py:64,74.  grad_w[num_rules] and grad_bias[N] (may be NULL) are ACCUMULATED
+ * into (zero them first): grad_w[i] += sum_s slot_scale[s] * <G_s, fp32(count_i)>. */
+int rl_predictor_backward(const rl_graph *g, const rl_rules *r, const rl_slots *s,
+                          int32_t count_bits, const void *arena, const int32_t *node_nz,
+                          int32_t skip_empty, const float *G, const float *slot_scale,
+                          int32_t max_terms, float *grad_w, float *grad_bias, void *stream);
+
+/* Kernel (3): filtered rank bounds, replaces src/trainer.py:189-201.  LH[S*32][2] int64:
+ * L = #{e not known: z_e > z_t} + 1, H = #{e not known: z_e >= z_t} + 2; (1, N+1) when the
+ * answer's nzmask bit is clear and use_mask != 0.  `known` = hr2oo (valid) / hr2ooo (test).
+ * counters is scratch int32[S*64], zeroed by the call. */
+int rl_filtered_rank(const rl_graph *g, const rl_slots *s, const rl_answers *known,
+                     int32_t use_mask, const float *Z, const uint32_t *nzmask,
+                     int32_t *counters, int64_t *LH, void *stream);
+
+/* Same bounds from the reference's dense tensors (logits fp32[Q][N], flag u8[Q][N],
+ * mask u8[Q][N], t int64[Q]) -- what TrainerPredictor.evaluate holds (trainer.py:182-187). */
+int rl_filtered_rank_dense(int64_t Q, int64_t N, const float *logits, const uint8_t *flag,
+                           const uint8_t *mask, const int64_t *t, int64_t *LH, void *stream);
+
+/* Hits@1/3/10, MR, MRR partial sums over rows (L,H) with weight[] (0 drops a duplicate),
+ * replaces src/trainer.py:211-232.  harmonic is fp64[N+2] with harmonic[k] = sum_{i<=k} 1/i.
+ * sums[5] fp64 are ACCUMULATED (zero them first). */
+int rl_rank_metrics(int64_t Q, const int64_t *LH, const double *weight, int32_t expectation,
+                    const double *harmonic, double *sums, void *stream);
+
+/* Entity-major <-> reference layout: out[b][e] = Z[slot][e][b] for b < nq (fp32 [nq][N]). */
+int rl_slot_to_dense(int32_t N, int32_t nq, const float *Z_slot, float *out, int64_t out_stride,
+                     void *stream);
+int rl_mask_to_dense(int32_t N, int32_t nq, const uint32_t *nzmask_slot, uint8_t *out,
+                     int64_t out_stride, void *stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* RNNLOGIC_B200_H */

@@ -1,0 +1,132 @@
+"""ctypes binding of librnnlogic_b200.so (include/rnnlogic_b200.h).
+
+The shared library is built in-tree by ``__graft_entry__.build()`` (nvcc, sm_100a).  There is no
+CPU fallback: importing this module without the library, or calling into it without a CUDA
+device, raises."""
+from __future__ import annotations
+
+import ctypes as C
+import os
+import subprocess
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+ROOT = os.path.dirname(_HERE)
+LIB_PATH = os.path.join(_HERE, "lib", "librnnlogic_b200.so")
+SOURCES = [os.path.join(_HERE, "csrc", f) for f in ("rl_kernels.cu", "rl_plus.cu")]
+HEADER = os.path.join(ROOT, "include", "rnnlogic_b200.h")
+
+LANES = 32
+i32p = C.POINTER(C.c_int32)
+i64p = C.POINTER(C.c_int64)
+u32p = C.POINTER(C.c_uint32)
+f32p = C.POINTER(C.c_float)
+f64p = C.POINTER(C.c_double)
+u8p = C.POINTER(C.c_uint8)
+vp = C.c_void_p
+
+
+class RlGraph(C.Structure):
+    _fields_ = [("num_entities", C.c_int32), ("num_relations", C.c_int32), ("rank_words", C.c_int32),
+                ("total_rows", C.c_int32), ("num_edges", C.c_int32),
+                ("dst_ptr", vp), ("row_dst", vp), ("row_start", vp), ("edge_src", vp), ("rank_tab", vp),
+                ("ord_ptr", vp), ("ord_h", vp), ("ord_t", vp), ("ent_ptr", vp), ("ent_rel", vp), ("ent_row", vp)]
+
+
+class RlRules(C.Structure):
+    _fields_ = [("num_nodes", C.c_int32), ("num_rules", C.c_int32), ("max_len", C.c_int32),
+                ("num_chunks", C.c_int32), ("num_terms", C.c_int32),
+                ("node_rel", vp), ("node_parent", vp), ("node_row_off", vp), ("head_node_ptr", vp),
+                ("lvl_ptr", vp), ("chunk_node", vp), ("chunk_row0", vp), ("term_ptr", vp),
+                ("term_node", vp), ("term_rule", vp), ("zr_ptr", vp), ("zr_rule", vp)]
+
+
+class RlSlots(C.Structure):
+    _fields_ = [("num_slots", C.c_int32), ("slot_head", vp), ("lane_h", vp), ("lane_t", vp),
+                ("lane_eh", vp), ("lane_et", vp), ("arena_off", vp), ("nz_off", vp)]
+
+
+class RlAnswers(C.Structure):
+    _fields_ = [("num_keys", C.c_int64), ("keys", vp), ("ptr", vp), ("ent", vp)]
+
+
+def nvcc_command(out=LIB_PATH):
+    srcs = [s for s in SOURCES if os.path.exists(s)]
+    return ["nvcc", "-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17",
+            "-shared", "-Xcompiler", "-fPIC", "-I", os.path.join(ROOT, "include"), "-o", out] + srcs
+
+
+def build(force: bool = False) -> str:
+    """Compile csrc/*.cu for sm_100a into rnnlogic_b200/lib/ (cross-compiles without a GPU)."""
+    os.makedirs(os.path.dirname(LIB_PATH), exist_ok=True)
+    deps = [s for s in SOURCES if os.path.exists(s)] + [HEADER]
+    stale = force or not os.path.exists(LIB_PATH) or any(
+        os.path.getmtime(d) > os.path.getmtime(LIB_PATH) for d in deps)
+    if stale:
+        subprocess.check_call(nvcc_command())
+    return LIB_PATH
+
+
+_lib = None
+
+_PROTOS = {
+    "rl_abi_version": (C.c_int, []),
+    "rl_last_error": (C.c_char_p, []),
+    "rl_device_count": (C.c_int, []),
+    "rl_prepare_slots": (C.c_int, [C.POINTER(RlGraph), C.c_int32, vp, vp, vp, vp, vp, vp, vp, vp, vp, vp]),
+    "rl_expand_level": (C.c_int, [C.POINTER(RlGraph), C.POINTER(RlRules), C.POINTER(RlSlots), C.c_int32,
+                                  C.c_int32, C.c_int32, vp, vp, vp, C.c_int32, vp]),
+    "rl_node_counts_dense": (C.c_int, [C.POINTER(RlGraph), C.POINTER(RlRules), C.POINTER(RlSlots), C.c_int32,
+                                       C.c_int32, C.c_int32, vp, vp, C.c_int32, vp, vp]),
+    "rl_predictor_scores": (C.c_int, [C.POINTER(RlGraph), C.POINTER(RlRules), C.POINTER(RlSlots), C.c_int32,
+                                      vp, vp, C.c_int32, vp, vp, C.c_int32, vp, vp, vp]),
+    "rl_softmax_blocks": (C.c_int, [C.c_int32]),
+    "rl_softmax_ce": (C.c_int, [C.POINTER(RlGraph), C.POINTER(RlSlots), C.POINTER(RlAnswers), C.c_float,
+                                C.c_int32, vp, vp, vp, vp, vp, vp, vp, vp]),
+    "rl_predictor_backward": (C.c_int, [C.POINTER(RlGraph), C.POINTER(RlRules), C.POINTER(RlSlots), C.c_int32,
+                                        vp, vp, C.c_int32, vp, vp, C.c_int32, vp, vp, vp]),
+    "rl_filtered_rank": (C.c_int, [C.POINTER(RlGraph), C.POINTER(RlSlots), C.POINTER(RlAnswers), C.c_int32,
+                                   vp, vp, vp, vp, vp]),
+    "rl_filtered_rank_dense": (C.c_int, [C.c_int64, C.c_int64, vp, vp, vp, vp, vp, vp]),
+    "rl_rank_metrics": (C.c_int, [C.c_int64, vp, vp, C.c_int32, vp, vp, vp]),
+    "rl_slot_to_dense": (C.c_int, [C.c_int32, C.c_int32, vp, vp, C.c_int64, vp]),
+    "rl_mask_to_dense": (C.c_int, [C.c_int32, C.c_int32, vp, vp, C.c_int64, vp]),
+}
+
+
+def exported_symbols():
+    """Names every entry point declared in include/rnnlogic_b200.h must resolve to."""
+    return sorted(_PROTOS)
+
+
+def lib():
+    """The loaded shared library (raises if it was not built -- no fallback)."""
+    global _lib
+    if _lib is None:
+        if not os.path.exists(LIB_PATH):
+            raise RuntimeError(
+                "rnnlogic_b200: %s is missing. Build it with `python -c 'import __graft_entry__ as g; g.build()'` "
+                "(nvcc, sm_100a). There is no CPU / PyTorch fallback for the hot path." % LIB_PATH)
+        L = C.CDLL(LIB_PATH)
+        for name, (res, args) in _PROTOS.items():
+            fn = getattr(L, name)
+            fn.restype = res
+            fn.argtypes = args
+        _lib = L
+    return _lib
+
+
+class RlError(RuntimeError):
+    pass
+
+
+def check(rc: int, what: str = ""):
+    if rc < 0:
+        msg = lib().rl_last_error().decode(errors="replace")
+        raise RlError("%s failed (%d): %s" % (what or "rnnlogic_b200 call", rc, msg))
+    return rc
+
+
+def require_cuda(t, what="tensor"):
+    if t.device.type != "cuda":
+        raise RlError("rnnlogic_b200 is CUDA-only (sm_100a): %s lives on %s. There is no CPU fallback; "
+                      "move the model / batch to a CUDA device." % (what, t.device))

@@ -1,0 +1,857 @@
+// rnnlogic_b200 -- hand-written sm_100a kernels + C-ABI (include/rnnlogic_b200.h).
+//
+// Hot path of RNNLogic's reasoning predictor (reference: src/data.py:136-173 grounding,
+// src/predictors.py:53-80 aggregation, src/trainer.py:84-89 loss, :189-238 rank/metrics).
+// All per-slot matrices are entity-major [row][32 lanes]: a warp owns rows, lane b owns query b,
+// so every frontier / logit access is one coalesced 128-byte line.  This is HBM/L2-bound
+// integer work: no tensor cores, the levers are coalescing, loads in flight and grid sizing.
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include <stdio.h>
+#include <math.h>
+
+#include "rnnlogic_b200.h"
+
+#define FULL 0xffffffffu
+#define WARPS_PER_BLOCK 8
+#define SM_ROWS_PER_BLOCK 512   // entity rows per block in the softmax / rank sweeps
+
+static thread_local char g_err[512] = "";
+
+static int fail(int code, const char *what, cudaError_t e = cudaSuccess)
+{
+    if (e != cudaSuccess) snprintf(g_err, sizeof(g_err), "%s: %s", what, cudaGetErrorString(e));
+    else snprintf(g_err, sizeof(g_err), "%s", what);
+    return code;
+}
+
+#define CHECK_LAUNCH(name)                                             \
+    do {                                                               \
+        cudaError_t e_ = cudaGetLastError();                           \
+        if (e_ != cudaSuccess) return fail(RL_ERR_CUDA, name, e_);     \
+    } while (0)
+
+// ------------------------------------------------------------------------------------------
+// device helpers
+// ------------------------------------------------------------------------------------------
+__device__ __forceinline__ int rank_row(const rl_graph &g, int rel, int e)
+{
+    const uint2 w = __ldg(reinterpret_cast<const uint2 *>(g.rank_tab) + (size_t)rel * g.rank_words + (e >> 5));
+    const uint32_t bit = 1u << (e & 31);
+    return (w.x & bit) ? (int)(w.y + __popc(w.x & (bit - 1))) : -1;
+}
+
+__device__ __forceinline__ double warp_sum(double v)
+{
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(FULL, v, o);
+    return v;
+}
+__device__ __forceinline__ float warp_sumf(float v)
+{
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(FULL, v, o);
+    return v;
+}
+__device__ __forceinline__ int warp_sumi(int v)
+{
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(FULL, v, o);
+    return v;
+}
+
+// lower_bound over sorted keys; returns index or -1
+__device__ __forceinline__ int find_key(const rl_answers &a, long long key)
+{
+    long long lo = 0, hi = a.num_keys;
+    while (lo < hi) {
+        long long mid = (lo + hi) >> 1;
+        if (a.keys[mid] < key) lo = mid + 1; else hi = mid;
+    }
+    return (lo < a.num_keys && a.keys[lo] == key) ? (int)lo : -1;
+}
+
+// ------------------------------------------------------------------------------------------
+// slot preparation (trainer.py:69-82 batch tensors -> lane arrays)
+// ------------------------------------------------------------------------------------------
+__global__ void k_prepare_slots(rl_graph g, int S, const int32_t *__restrict__ slot_head,
+                                const int32_t *__restrict__ q_off, const int64_t *__restrict__ all_h,
+                                const int64_t *__restrict__ all_t, const int64_t *__restrict__ etr,
+                                int32_t *lane_h, int32_t *lane_t, int32_t *lane_eh, int32_t *lane_et)
+{
+    int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= S * RL_LANES) return;
+    int s = i >> 5, lane = i & 31;
+    int qi = q_off[s] + lane;
+    bool valid = qi < q_off[s + 1];
+    lane_h[i] = valid ? (int32_t)all_h[qi] : -1;
+    lane_t[i] = (valid && all_t) ? (int32_t)all_t[qi] : -1;
+    int eh = -1, et = -1;
+    if (valid && etr) {
+        int rel = slot_head[s];
+        int64_t k = etr[qi];
+        int64_t n = g.ord_ptr[rel + 1] - g.ord_ptr[rel];
+        if (k >= 0 && k < n) {
+            eh = g.ord_h[g.ord_ptr[rel] + k];
+            et = g.ord_t[g.ord_ptr[rel] + k];
+        }
+    }
+    lane_eh[i] = eh;
+    lane_et[i] = et;
+}
+
+// ------------------------------------------------------------------------------------------
+// kernel (1): frontier expansion.  One warp = one chunk of <= 32 consecutive destination rows
+// of one trie node of one slot.  The chunk's in-edges are contiguous in edge_src, so they are
+// fetched 32 at a time with one coalesced load; each lane resolves the parent-frontier row of
+// "its" edge (8-byte rank-table load), then the warp pulls the 32 parent rows (128 B each,
+// all 32 loads in flight before the first add) and reduces them segment by segment.
+// ------------------------------------------------------------------------------------------
+template <typename CT, bool ROOT>
+__global__ void __launch_bounds__(WARPS_PER_BLOCK * 32)
+k_expand(rl_graph g, rl_rules r, rl_slots s, int depth, CT *__restrict__ arena,
+         int32_t *__restrict__ node_nz, int32_t *__restrict__ overflow, int skip_empty)
+{
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int slot = blockIdx.y;
+    const int q = s.slot_head[slot];
+    const int32_t *lp = r.lvl_ptr + (size_t)q * (r.max_len + 1);
+    const int chunk = lp[depth - 1] + blockIdx.x * WARPS_PER_BLOCK + warp;
+    if (chunk >= lp[depth]) return;
+    const int v = r.chunk_node[chunk], row0 = r.chunk_row0[chunk];
+    const int rho = r.node_rel[v];
+    const int nzb = s.nz_off[slot] - r.head_node_ptr[q];
+    const size_t abase = (size_t)s.arena_off[slot];
+    const CT *__restrict__ X = nullptr;
+    int prel = -1;
+    if (!ROOT) {
+        const int p = r.node_parent[v];
+        if (skip_empty && node_nz[nzb + p] == 0) return;
+        prel = r.node_rel[p];
+        X = arena + (abase + (size_t)r.node_row_off[p]) * RL_LANES;
+    }
+    CT *__restrict__ Y = arena + (abase + (size_t)r.node_row_off[v] + row0) * RL_LANES;
+    const int rbase = g.dst_ptr[rho] + row0;
+    const int nr = min(32, g.dst_ptr[rho + 1] - rbase);
+    const int my_rs = g.row_start[rbase + min(lane, nr)];
+    const int e_end = g.row_start[rbase + nr];
+    const int my_dst = lane < nr ? g.row_dst[rbase + lane] : -1;
+    const int h = s.lane_h[slot * RL_LANES + lane];
+    const bool masked = (rho == q);
+    const int eh = masked ? s.lane_eh[slot * RL_LANES + lane] : -1;
+    const int et = masked ? s.lane_et[slot * RL_LANES + lane] : -1;
+
+    int cur = 0;                                         // row being accumulated
+    int row_end = (nr > 1) ? __shfl_sync(FULL, my_rs, 1) : e_end;
+    unsigned long long acc = 0;
+    bool any = false, ovf = false;
+
+    auto flush = [&](int j) {
+        const int d = __shfl_sync(FULL, my_dst, j);
+        if (eh >= 0 && et == d) {                        // data.py:164-170: drop the query's own edge
+            unsigned long long sub;
+            if (ROOT) sub = (eh == h) ? 1ull : 0ull;
+            else {
+                const int pr = rank_row(g, prel, eh);
+                sub = pr >= 0 ? (unsigned long long)X[(size_t)pr * RL_LANES + lane] : 0ull;
+            }
+            acc -= sub;
+        }
+        if (sizeof(CT) == 4 && (acc >> 32)) ovf = true;
+        Y[(size_t)j * RL_LANES + lane] = (CT)acc;
+        any |= (acc != 0);
+        acc = 0;
+    };
+
+    for (int base = __shfl_sync(FULL, my_rs, 0); base < e_end; base += 32) {
+        const int n = min(32, e_end - base);
+        const int src = lane < n ? __ldg(g.edge_src + base + lane) : -1;
+        CT vals[32];
+        if (ROOT) {
+#pragma unroll
+            for (int k = 0; k < 32; ++k) vals[k] = (CT)((k < n) && (__shfl_sync(FULL, src, k) == h));
+        } else {
+            const int pr = src >= 0 ? rank_row(g, prel, src) : -1;
+#pragma unroll
+            for (int k = 0; k < 32; ++k) {
+                const int p = __shfl_sync(FULL, pr, k);
+                vals[k] = p >= 0 ? X[(size_t)p * RL_LANES + lane] : (CT)0;
+            }
+        }
+#pragma unroll
+        for (int k = 0; k < 32; ++k) {
+            if (k < n) {
+                while (base + k >= row_end) {
+                    flush(cur);
+                    ++cur;
+                    row_end = (cur + 1 < nr) ? __shfl_sync(FULL, my_rs, cur + 1) : e_end;
+                }
+                acc += (unsigned long long)vals[k];
+            }
+        }
+    }
+    while (cur < nr) {
+        flush(cur);
+        ++cur;
+    }
+    if (__any_sync(FULL, any) && lane == 0) node_nz[nzb + v] = 1;
+    if (__any_sync(FULL, ovf) && lane == 0) *overflow = 1;
+}
+
+// dense int64 [32][N] view of one node (debug / KnowledgeGraph.grounding return value)
+template <typename CT>
+__global__ void k_node_dense(rl_graph g, rl_rules r, rl_slots s, int slot, int node, const CT *__restrict__ arena,
+                             const int32_t *__restrict__ node_nz, int skip_empty, int64_t *__restrict__ out)
+{
+    __shared__ long long tile[32][33];
+    const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;     // 32 warps
+    const int N = g.num_entities;
+    const int e = blockIdx.x * 32 + w;
+    long long c = 0;
+    if (e < N) {
+        if (node < 0) c = (s.lane_h[slot * RL_LANES + lane] == e);
+        else {
+            const int q = s.slot_head[slot];
+            const bool live = !(skip_empty && node_nz[s.nz_off[slot] - r.head_node_ptr[q] + node] == 0);
+            const int row = live ? rank_row(g, r.node_rel[node], e) : -1;
+            if (row >= 0) c = (long long)arena[((size_t)s.arena_off[slot] + r.node_row_off[node] + row) * RL_LANES + lane];
+        }
+    }
+    tile[w][lane] = c;                                            // [entity][lane]
+    __syncthreads();
+    const int eo = blockIdx.x * 32 + lane;
+    if (eo < N) out[(size_t)w * N + eo] = tile[lane][w];          // lane-major row w
+}
+
+// ------------------------------------------------------------------------------------------
+// kernel (2a): pull aggregation of the rule weights.  Warp = one entity row of one slot; it
+// walks the (relation, row) pairs in which the entity is a tail and, per pair, the rules of the
+// slot's head that end in that relation.
+// ------------------------------------------------------------------------------------------
+template <typename CT>
+__global__ void __launch_bounds__(WARPS_PER_BLOCK * 32)
+k_predictor_scores(rl_graph g, rl_rules r, rl_slots s, const CT *__restrict__ arena,
+                   const int32_t *__restrict__ node_nz, int skip_empty, const float *__restrict__ w,
+                   const float *__restrict__ bias, int fill_neg_inf, float *__restrict__ Z,
+                   uint32_t *__restrict__ nzmask)
+{
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int slot = blockIdx.y;
+    const int e = blockIdx.x * WARPS_PER_BLOCK + warp;
+    const int N = g.num_entities, R = g.num_relations;
+    if (e >= N) return;
+    const int q = s.slot_head[slot];
+    const int nzb = s.nz_off[slot] - r.head_node_ptr[q];
+    const size_t abase = (size_t)s.arena_off[slot];
+    const int32_t *tp = r.term_ptr + (size_t)q * R;
+    double acc = 0.0;
+    bool any = false;
+    const int p0 = g.ent_ptr[e], p1 = g.ent_ptr[e + 1];
+    for (int pb = p0; pb < p1; pb += 32) {
+        // lane-parallel fetch of up to 32 (relation,row) pairs and their rule ranges
+        const int pi = pb + lane;
+        int rel = -1, row = 0, t0 = 0, t1 = 0;
+        if (pi < p1) {
+            rel = g.ent_rel[pi];
+            row = g.ent_row[pi];
+            t0 = tp[rel];
+            t1 = tp[rel + 1];
+        }
+        const int npair = min(32, p1 - pb);
+        for (int k = 0; k < npair; ++k) {
+            const int a0 = __shfl_sync(FULL, t0, k), a1 = __shfl_sync(FULL, t1, k);
+            const int rw = __shfl_sync(FULL, row, k);
+            for (int t = a0; t < a1; ++t) {
+                const int v = __ldg(r.term_node + t);
+                if (skip_empty && node_nz[nzb + v] == 0) continue;
+                const CT c = arena[(abase + (size_t)r.node_row_off[v] + rw) * RL_LANES + lane];
+                if (c != 0) {
+                    acc += (double)(float)c * (double)__ldg(w + r.term_rule[t]);   // x.float() * w  (predictors.py:64)
+                    any = true;
+                }
+            }
+        }
+    }
+    if (s.lane_h[slot * RL_LANES + lane] == e) {                  // empty-body rules: count = one_hot(h)
+        for (int t = r.zr_ptr[q]; t < r.zr_ptr[q + 1]; ++t) {
+            acc += (double)__ldg(w + r.zr_rule[t]);
+            any = true;
+        }
+    }
+    float z = (float)acc;
+    if (bias) z += bias[e];
+    if (fill_neg_inf && !any) z = -INFINITY;
+    Z[((size_t)slot * N + e) * RL_LANES + lane] = z;
+    const uint32_t bits = __ballot_sync(FULL, any);
+    if (lane == 0) nzmask[(size_t)slot * N + e] = bits;
+}
+
+// ------------------------------------------------------------------------------------------
+// kernel (2b): log(softmax + 1e-8) CE + backward (trainer.py:84,88-89)
+// ------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(WARPS_PER_BLOCK * 32)
+k_softmax_partial(int N, const float *__restrict__ Z, float *__restrict__ partial, int nblk)
+{
+    __shared__ float sm_m[WARPS_PER_BLOCK][32], sm_s[WARPS_PER_BLOCK][32];
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int slot = blockIdx.y;
+    const float *Zs = Z + (size_t)slot * N * RL_LANES;
+    const int e0 = blockIdx.x * SM_ROWS_PER_BLOCK;
+    const int e1 = min(N, e0 + SM_ROWS_PER_BLOCK);
+    float m = -INFINITY, sum = 0.f;
+    for (int e = e0 + warp; e < e1; e += WARPS_PER_BLOCK) {
+        const float z = Zs[(size_t)e * RL_LANES + lane];
+        if (z > m) { sum = sum * expf(m - z) + 1.f; m = z; }
+        else if (z != -INFINITY) sum += expf(z - m);
+    }
+    sm_m[warp][lane] = m;
+    sm_s[warp][lane] = sum;
+    __syncthreads();
+    if (warp == 0) {
+        float M = -INFINITY;
+        for (int k = 0; k < WARPS_PER_BLOCK; ++k) M = fmaxf(M, sm_m[k][lane]);
+        float S = 0.f;
+        for (int k = 0; k < WARPS_PER_BLOCK; ++k)
+            if (sm_m[k][lane] != -INFINITY) S += sm_s[k][lane] * expf(sm_m[k][lane] - M);
+        float *p = partial + ((size_t)slot * nblk + blockIdx.x) * 64;
+        p[lane] = M;
+        p[32 + lane] = S;
+    }
+}
+
+// one block per slot: combine the partials, then walk the sparse targets
+// stats[slot][lane][4] = (max, sumexp, S_b, valid)
+__global__ void __launch_bounds__(WARPS_PER_BLOCK * 32)
+k_ce_finalize(rl_graph g, rl_slots s, rl_answers ans, float smoothing, int use_mask,
+              const float *__restrict__ Z, const uint32_t *__restrict__ nzmask,
+              const float *__restrict__ partial, int nblk, float *__restrict__ stats,
+              float *__restrict__ loss, float *__restrict__ tsum)
+{
+    __shared__ float sm_m[32], sm_s[32];
+    __shared__ double red_l[WARPS_PER_BLOCK], red_t[WARPS_PER_BLOCK];
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int slot = blockIdx.x;
+    const int N = g.num_entities;
+    const int q = s.slot_head[slot];
+    if (warp == 0) {
+        float M = -INFINITY;
+        const float *p = partial + (size_t)slot * nblk * 64;
+        for (int k = 0; k < nblk; ++k) M = fmaxf(M, p[k * 64 + lane]);
+        float S = 0.f;
+        for (int k = 0; k < nblk; ++k) {
+            const float mk = p[k * 64 + lane];
+            if (mk != -INFINITY) S += p[k * 64 + 32 + lane] * expf(mk - M);
+        }
+        sm_m[lane] = M;
+        sm_s[lane] = S;
+    }
+    __syncthreads();
+    const float *Zs = Z + (size_t)slot * N * RL_LANES;
+    const uint32_t *ms = nzmask + (size_t)slot * N;
+    double wl = 0.0, wt = 0.0;
+    for (int b = warp; b < 32; b += WARPS_PER_BLOCK) {
+        const int h = s.lane_h[slot * RL_LANES + b];
+        const int t = s.lane_t[slot * RL_LANES + b];
+        const float M = sm_m[b], S = sm_s[b];
+        float lsum = 0.f, tacc = 0.f, sb = 0.f;
+        bool saw_t = false;
+        if (h >= 0 && M != -INFINITY) {
+            const int ki = find_key(ans, (long long)q * N + h);
+            const int a0 = ki >= 0 ? ans.ptr[ki] : 0, a1 = ki >= 0 ? ans.ptr[ki + 1] : 0;
+            for (int a = a0 + lane; a < a1; a += 32) {
+                const int e = ans.ent[a];
+                float tg = smoothing;
+                if (e == t) { tg += 1.f - smoothing; saw_t = true; }
+                if (use_mask && !((ms[e] >> b) & 1u)) continue;
+                const float p = expf(Zs[(size_t)e * RL_LANES + b] - M) / S;
+                lsum += logf(p + 1e-8f) * tg;
+                tacc += tg;
+                sb += tg / (p + 1e-8f) * p;
+            }
+            saw_t = __any_sync(FULL, saw_t);
+            if (!saw_t && t >= 0 && lane == 0 && !(use_mask && !((ms[t] >> b) & 1u))) {
+                const float tg = 1.f - smoothing;
+                const float p = expf(Zs[(size_t)t * RL_LANES + b] - M) / S;
+                lsum += logf(p + 1e-8f) * tg;
+                tacc += tg;
+                sb += tg / (p + 1e-8f) * p;
+            }
+        }
+        lsum = warp_sumf(lsum);
+        tacc = warp_sumf(tacc);
+        sb = warp_sumf(sb);
+        if (lane == 0) {
+            float *st = stats + ((size_t)slot * 32 + b) * 4;
+            st[0] = M; st[1] = S; st[2] = sb; st[3] = (h >= 0 && M != -INFINITY) ? 1.f : 0.f;
+        }
+        wl += (double)lsum;
+        wt += (double)tacc;
+    }
+    if (lane == 0) { red_l[warp] = wl; red_t[warp] = wt; }
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        double L = 0.0, T = 0.0;
+        for (int k = 0; k < WARPS_PER_BLOCK; ++k) { L += red_l[k]; T += red_t[k]; }
+        const float Tf = (float)T;
+        tsum[slot] = Tf;
+        loss[slot] = (float)(-L) / fmaxf(Tf, 1.f);
+    }
+}
+
+// G[e][b] = softmax * S_b / T'   (dense part of dloss/dZ)
+__global__ void __launch_bounds__(256)
+k_grad_dense(int N, const float *__restrict__ Z, const float *__restrict__ stats,
+             const float *__restrict__ tsum, float *__restrict__ G)
+{
+    const int slot = blockIdx.y;
+    const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= (size_t)N * RL_LANES) return;
+    const int b = (int)(i & 31);
+    const float *st = stats + ((size_t)slot * 32 + b) * 4;
+    const float T = fmaxf(tsum[slot], 1.f);
+    float gval = 0.f;
+    if (st[3] != 0.f) {
+        const float z = Z[(size_t)slot * N * RL_LANES + i];
+        if (z != -INFINITY) gval = expf(z - st[0]) / st[1] * st[2] / T;
+    }
+    G[(size_t)slot * N * RL_LANES + i] = gval;
+}
+
+// sparse part: G[e][b] -= p * tgt / (p + eps) / T' at the target entries
+__global__ void __launch_bounds__(WARPS_PER_BLOCK * 32)
+k_grad_sparse(rl_graph g, rl_slots s, rl_answers ans, float smoothing, int use_mask,
+              const float *__restrict__ Z, const uint32_t *__restrict__ nzmask,
+              const float *__restrict__ stats, const float *__restrict__ tsum, float *__restrict__ G)
+{
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int slot = blockIdx.x;
+    const int N = g.num_entities;
+    const int q = s.slot_head[slot];
+    const float *Zs = Z + (size_t)slot * N * RL_LANES;
+    float *Gs = G + (size_t)slot * N * RL_LANES;
+    const uint32_t *ms = nzmask + (size_t)slot * N;
+    const float T = fmaxf(tsum[slot], 1.f);
+    for (int b = warp; b < 32; b += WARPS_PER_BLOCK) {
+        const float *st = stats + ((size_t)slot * 32 + b) * 4;
+        if (st[3] == 0.f) continue;
+        const int h = s.lane_h[slot * RL_LANES + b];
+        const int t = s.lane_t[slot * RL_LANES + b];
+        const float M = st[0], S = st[1];
+        const int ki = find_key(ans, (long long)q * N + h);
+        const int a0 = ki >= 0 ? ans.ptr[ki] : 0, a1 = ki >= 0 ? ans.ptr[ki + 1] : 0;
+        bool saw_t = false;
+        for (int a = a0 + lane; a < a1; a += 32) {
+            const int e = ans.ent[a];
+            float tg = smoothing;
+            if (e == t) { tg += 1.f - smoothing; saw_t = true; }
+            if (use_mask && !((ms[e] >> b) & 1u)) continue;
+            const float p = expf(Zs[(size_t)e * RL_LANES + b] - M) / S;
+            Gs[(size_t)e * RL_LANES + b] -= p * (tg / (p + 1e-8f)) / T;
+        }
+        saw_t = __any_sync(FULL, saw_t);
+        if (!saw_t && t >= 0 && lane == 0 && !(use_mask && !((ms[t] >> b) & 1u))) {
+            const float tg = 1.f - smoothing;
+            const float p = expf(Zs[(size_t)t * RL_LANES + b] - M) / S;
+            Gs[(size_t)t * RL_LANES + b] -= p * (tg / (p + 1e-8f)) / T;
+        }
+    }
+}
+
+// ------------------------------------------------------------------------------------------
+// kernel (2c): backward into rule weights / bias
+// ------------------------------------------------------------------------------------------
+template <typename CT>
+__global__ void __launch_bounds__(128)
+k_predictor_bwd_w(rl_graph g, rl_rules r, rl_slots s, const CT *__restrict__ arena,
+                  const int32_t *__restrict__ node_nz, int skip_empty, const float *__restrict__ G,
+                  const float *__restrict__ slot_scale, float *__restrict__ grad_w)
+{
+    __shared__ double red[4];
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int slot = blockIdx.y;
+    const int N = g.num_entities, R = g.num_relations;
+    const int q = s.slot_head[slot];
+    const float scale = slot_scale ? slot_scale[slot] : 1.f;
+    const float *Gs = G + (size_t)slot * N * RL_LANES;
+    if (blockIdx.x == 0 && warp == 0 && r.zr_ptr[q + 1] > r.zr_ptr[q]) {   // empty-body rules
+        const int h = s.lane_h[slot * RL_LANES + lane];
+        double v = h >= 0 ? (double)Gs[(size_t)h * RL_LANES + lane] : 0.0;
+        v = warp_sum(v);
+        if (lane == 0)
+            for (int t = r.zr_ptr[q]; t < r.zr_ptr[q + 1]; ++t) atomicAdd(grad_w + r.zr_rule[t], (float)v * scale);
+    }
+    const int t = r.term_ptr[(size_t)q * R] + blockIdx.x;
+    if (t >= r.term_ptr[(size_t)(q + 1) * R]) return;
+    const int v = r.term_node[t];
+    if (skip_empty && node_nz[s.nz_off[slot] - r.head_node_ptr[q] + v] == 0) return;
+    const int rho = r.node_rel[v];
+    const int rb = g.dst_ptr[rho], nrows = g.dst_ptr[rho + 1] - rb;
+    const CT *Xv = arena + ((size_t)s.arena_off[slot] + r.node_row_off[v]) * RL_LANES;
+    double acc = 0.0;
+    for (int j = warp; j < nrows; j += 4) {
+        const CT c = Xv[(size_t)j * RL_LANES + lane];
+        if (c != 0) acc += (double)(float)c * (double)Gs[(size_t)g.row_dst[rb + j] * RL_LANES + lane];
+    }
+    acc = warp_sum(acc);
+    if (lane == 0) red[warp] = acc;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        const double tot = red[0] + red[1] + red[2] + red[3];
+        if (tot != 0.0) atomicAdd(grad_w + r.term_rule[t], (float)tot * scale);
+    }
+}
+
+__global__ void __launch_bounds__(WARPS_PER_BLOCK * 32)
+k_bias_grad(int N, int S, const float *__restrict__ G, const float *__restrict__ slot_scale,
+            float *__restrict__ grad_bias)
+{
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int e = blockIdx.x * WARPS_PER_BLOCK + warp;
+    if (e >= N) return;
+    double acc = 0.0;
+    for (int sl = 0; sl < S; ++sl)
+        acc += (double)G[((size_t)sl * N + e) * RL_LANES + lane] * (double)(slot_scale ? slot_scale[sl] : 1.f);
+    acc = warp_sum(acc);
+    if (lane == 0) grad_bias[e] += (float)acc;
+}
+
+// ------------------------------------------------------------------------------------------
+// kernel (3): filtered rank (trainer.py:189-201) + metrics (trainer.py:211-232)
+// ------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(WARPS_PER_BLOCK * 32)
+k_rank_count(int N, rl_slots s, const float *__restrict__ Z, int32_t *__restrict__ counters)
+{
+    __shared__ int sm_gt[WARPS_PER_BLOCK][32], sm_ge[WARPS_PER_BLOCK][32];
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int slot = blockIdx.y;
+    const float *Zs = Z + (size_t)slot * N * RL_LANES;
+    const int t = s.lane_t[slot * RL_LANES + lane];
+    const float val = t >= 0 ? Zs[(size_t)t * RL_LANES + lane] : INFINITY;
+    const int e0 = blockIdx.x * SM_ROWS_PER_BLOCK, e1 = min(N, e0 + SM_ROWS_PER_BLOCK);
+    int gt = 0, ge = 0;
+    for (int e = e0 + warp; e < e1; e += WARPS_PER_BLOCK) {
+        const float z = Zs[(size_t)e * RL_LANES + lane];
+        gt += z > val;
+        ge += z >= val;
+    }
+    sm_gt[warp][lane] = gt;
+    sm_ge[warp][lane] = ge;
+    __syncthreads();
+    if (warp == 0) {
+        int a = 0, b = 0;
+        for (int k = 0; k < WARPS_PER_BLOCK; ++k) { a += sm_gt[k][lane]; b += sm_ge[k][lane]; }
+        atomicAdd(counters + ((size_t)slot * 32 + lane) * 2, a);
+        atomicAdd(counters + ((size_t)slot * 32 + lane) * 2 + 1, b);
+    }
+}
+
+__global__ void __launch_bounds__(WARPS_PER_BLOCK * 32)
+k_rank_finalize(rl_graph g, rl_slots s, rl_answers known, int use_mask, const float *__restrict__ Z,
+                const uint32_t *__restrict__ nzmask, const int32_t *__restrict__ counters,
+                int64_t *__restrict__ LH)
+{
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int slot = blockIdx.x;
+    const int N = g.num_entities;
+    const int q = s.slot_head[slot];
+    const float *Zs = Z + (size_t)slot * N * RL_LANES;
+    for (int b = warp; b < 32; b += WARPS_PER_BLOCK) {
+        const int h = s.lane_h[slot * RL_LANES + b];
+        const int t = s.lane_t[slot * RL_LANES + b];
+        long long L = 0, H = 0;
+        if (h >= 0 && t >= 0) {
+            if (use_mask && !((nzmask[(size_t)slot * N + t] >> b) & 1u)) { L = 1; H = (long long)N + 1; }
+            else {
+                const float val = Zs[(size_t)t * RL_LANES + b];
+                const int ki = find_key(known, (long long)q * N + h);
+                const int a0 = ki >= 0 ? known.ptr[ki] : 0, a1 = ki >= 0 ? known.ptr[ki + 1] : 0;
+                int gt = 0, ge = 0;
+                for (int a = a0 + lane; a < a1; a += 32) {
+                    const float z = Zs[(size_t)known.ent[a] * RL_LANES + b];
+                    gt += z > val;
+                    ge += z >= val;
+                }
+                gt = warp_sumi(gt);
+                ge = warp_sumi(ge);
+                L = (long long)(counters[((size_t)slot * 32 + b) * 2] - gt) + 1;
+                H = (long long)(counters[((size_t)slot * 32 + b) * 2 + 1] - ge) + 2;
+            }
+        }
+        if (lane == 0) {
+            LH[((size_t)slot * 32 + b) * 2] = L;
+            LH[((size_t)slot * 32 + b) * 2 + 1] = H;
+        }
+    }
+}
+
+__global__ void __launch_bounds__(256)
+k_rank_dense(long long N, const float *__restrict__ logits, const uint8_t *__restrict__ flag,
+             const uint8_t *__restrict__ mask, const int64_t *__restrict__ t, int64_t *__restrict__ LH)
+{
+    __shared__ int red[2][8];
+    const long long k = blockIdx.x;
+    const float *row = logits + k * N;
+    const uint8_t *fl = flag + k * N;
+    const long long tk = t[k];
+    if (!mask[k * N + tk]) {
+        if (threadIdx.x == 0) { LH[2 * k] = 1; LH[2 * k + 1] = N + 1; }
+        return;
+    }
+    const float val = row[tk];
+    int gt = 0, ge = 0;
+    for (long long e = threadIdx.x; e < N; e += blockDim.x) {
+        if (fl[e]) { gt += row[e] > val; ge += row[e] >= val; }
+    }
+    gt = warp_sumi(gt);
+    ge = warp_sumi(ge);
+    if ((threadIdx.x & 31) == 0) { red[0][threadIdx.x >> 5] = gt; red[1][threadIdx.x >> 5] = ge; }
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        int a = 0, b = 0;
+        for (int i = 0; i < 8; ++i) { a += red[0][i]; b += red[1][i]; }
+        LH[2 * k] = a + 1;
+        LH[2 * k + 1] = b + 2;
+    }
+}
+
+__global__ void __launch_bounds__(256)
+k_rank_metrics(long long Q, const int64_t *__restrict__ LH, const double *__restrict__ weight, int expectation,
+               const double *__restrict__ harmonic, double *__restrict__ sums)
+{
+    __shared__ double red[5][8];
+    double v[5] = {0, 0, 0, 0, 0};
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < Q; i += (long long)gridDim.x * blockDim.x) {
+        const double wgt = weight ? weight[i] : 1.0;
+        const long long L = LH[2 * i], H = LH[2 * i + 1];
+        if (wgt == 0.0 || H <= L) continue;
+        if (expectation) {
+            const double n = (double)(H - L);
+            const long long hi = H - 1;
+            v[0] += wgt * (double)max(0ll, min(hi, 1ll) - L + 1) / n;
+            v[1] += wgt * (double)max(0ll, min(hi, 3ll) - L + 1) / n;
+            v[2] += wgt * (double)max(0ll, min(hi, 10ll) - L + 1) / n;
+            v[3] += wgt * 0.5 * (double)(L + hi);
+            v[4] += wgt * (harmonic[hi] - harmonic[L - 1]) / n;
+        } else {
+            const long long rank = H - 1;
+            v[0] += wgt * (rank <= 1);
+            v[1] += wgt * (rank <= 3);
+            v[2] += wgt * (rank <= 10);
+            v[3] += wgt * (double)rank;
+            v[4] += wgt / (double)rank;
+        }
+    }
+    for (int m = 0; m < 5; ++m) {
+        const double x = warp_sum(v[m]);
+        if ((threadIdx.x & 31) == 0) red[m][threadIdx.x >> 5] = x;
+    }
+    __syncthreads();
+    if (threadIdx.x < 5) {
+        double x = 0;
+        for (int i = 0; i < 8; ++i) x += red[threadIdx.x][i];
+        atomicAdd(sums + threadIdx.x, x);
+    }
+}
+
+// entity-major slot -> reference layout
+__global__ void k_slot_to_dense(int N, int nq, const float *__restrict__ Zs, float *__restrict__ out, long long stride)
+{
+    __shared__ float tile[32][33];
+    const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+    const int e = blockIdx.x * 32 + w;
+    tile[w][lane] = e < N ? Zs[(size_t)e * RL_LANES + lane] : 0.f;
+    __syncthreads();
+    const int eo = blockIdx.x * 32 + lane;
+    if (eo < N && w < nq) out[(size_t)w * stride + eo] = tile[lane][w];
+}
+
+__global__ void k_mask_to_dense(int N, int nq, const uint32_t *__restrict__ ms, uint8_t *__restrict__ out, long long stride)
+{
+    const int e = blockIdx.x * blockDim.x + threadIdx.x;
+    if (e >= N) return;
+    const uint32_t bits = ms[e];
+    for (int b = 0; b < nq; ++b) out[(size_t)b * stride + e] = (bits >> b) & 1u;
+}
+
+// ------------------------------------------------------------------------------------------
+// C-ABI
+// ------------------------------------------------------------------------------------------
+extern "C" {
+
+int rl_abi_version(void) { return RL_ABI_VERSION; }
+const char *rl_last_error(void) { return g_err; }
+
+int rl_device_count(void)
+{
+    int n = 0;
+    cudaError_t e = cudaGetDeviceCount(&n);
+    if (e != cudaSuccess || n <= 0) {
+        cudaGetLastError();
+        return fail(RL_ERR_NO_DEVICE, "no CUDA device visible (rnnlogic_b200 has no CPU fallback)");
+    }
+    return n;
+}
+
+int rl_prepare_slots(const rl_graph *g, int32_t S, const int32_t *slot_head, const int32_t *q_off,
+                     const int64_t *all_h, const int64_t *all_t, const int64_t *etr, int32_t *lane_h,
+                     int32_t *lane_t, int32_t *lane_eh, int32_t *lane_et, void *stream)
+{
+    if (!g || !slot_head || !q_off || !all_h || !lane_h || !lane_t || !lane_eh || !lane_et || S <= 0)
+        return fail(RL_ERR_ARG, "rl_prepare_slots: bad argument");
+    const int n = S * RL_LANES;
+    k_prepare_slots<<<(n + 255) / 256, 256, 0, (cudaStream_t)stream>>>(*g, S, slot_head, q_off, all_h, all_t, etr,
+                                                                        lane_h, lane_t, lane_eh, lane_et);
+    CHECK_LAUNCH("k_prepare_slots");
+    return RL_OK;
+}
+
+int rl_expand_level(const rl_graph *g, const rl_rules *r, const rl_slots *s, int32_t depth, int32_t grid_chunks,
+                    int32_t count_bits, void *arena, int32_t *node_nz, int32_t *overflow, int32_t skip_empty,
+                    void *stream)
+{
+    if (!g || !r || !s || !arena || !node_nz || !overflow) return fail(RL_ERR_ARG, "rl_expand_level: null argument");
+    if (depth < 1 || depth > r->max_len) return fail(RL_ERR_ARG, "rl_expand_level: depth out of range");
+    if (count_bits != 32 && count_bits != 64) return fail(RL_ERR_ARG, "rl_expand_level: count_bits must be 32 or 64");
+    if (grid_chunks <= 0 || s->num_slots <= 0) return RL_OK;
+    dim3 grid((grid_chunks + WARPS_PER_BLOCK - 1) / WARPS_PER_BLOCK, s->num_slots);
+    cudaStream_t st = (cudaStream_t)stream;
+    if (count_bits == 32) {
+        if (depth == 1) k_expand<uint32_t, true><<<grid, WARPS_PER_BLOCK * 32, 0, st>>>(*g, *r, *s, depth, (uint32_t *)arena, node_nz, overflow, skip_empty);
+        else k_expand<uint32_t, false><<<grid, WARPS_PER_BLOCK * 32, 0, st>>>(*g, *r, *s, depth, (uint32_t *)arena, node_nz, overflow, skip_empty);
+    } else {
+        if (depth == 1) k_expand<unsigned long long, true><<<grid, WARPS_PER_BLOCK * 32, 0, st>>>(*g, *r, *s, depth, (unsigned long long *)arena, node_nz, overflow, skip_empty);
+        else k_expand<unsigned long long, false><<<grid, WARPS_PER_BLOCK * 32, 0, st>>>(*g, *r, *s, depth, (unsigned long long *)arena, node_nz, overflow, skip_empty);
+    }
+    CHECK_LAUNCH("k_expand");
+    return RL_OK;
+}
+
+int rl_node_counts_dense(const rl_graph *g, const rl_rules *r, const rl_slots *s, int32_t slot, int32_t node,
+                         int32_t count_bits, const void *arena, const int32_t *node_nz, int32_t skip_empty,
+                         int64_t *out, void *stream)
+{
+    if (!g || !r || !s || !out || (node >= 0 && (!arena || !node_nz))) return fail(RL_ERR_ARG, "rl_node_counts_dense: null argument");
+    if (slot < 0 || slot >= s->num_slots || node >= r->num_nodes) return fail(RL_ERR_ARG, "rl_node_counts_dense: index out of range");
+    const int grid = (g->num_entities + 31) / 32;
+    if (count_bits == 32) k_node_dense<uint32_t><<<grid, 1024, 0, (cudaStream_t)stream>>>(*g, *r, *s, slot, node, (const uint32_t *)arena, node_nz, skip_empty, out);
+    else if (count_bits == 64) k_node_dense<unsigned long long><<<grid, 1024, 0, (cudaStream_t)stream>>>(*g, *r, *s, slot, node, (const unsigned long long *)arena, node_nz, skip_empty, out);
+    else return fail(RL_ERR_ARG, "rl_node_counts_dense: count_bits must be 32 or 64");
+    CHECK_LAUNCH("k_node_dense");
+    return RL_OK;
+}
+
+int rl_predictor_scores(const rl_graph *g, const rl_rules *r, const rl_slots *s, int32_t count_bits,
+                        const void *arena, const int32_t *node_nz, int32_t skip_empty, const float *w,
+                        const float *bias, int32_t fill_neg_inf, float *Z, uint32_t *nzmask, void *stream)
+{
+    if (!g || !r || !s || !arena || !node_nz || !w || !Z || !nzmask) return fail(RL_ERR_ARG, "rl_predictor_scores: null argument");
+    if (s->num_slots <= 0) return RL_OK;
+    dim3 grid((g->num_entities + WARPS_PER_BLOCK - 1) / WARPS_PER_BLOCK, s->num_slots);
+    cudaStream_t st = (cudaStream_t)stream;
+    if (count_bits == 32) k_predictor_scores<uint32_t><<<grid, WARPS_PER_BLOCK * 32, 0, st>>>(*g, *r, *s, (const uint32_t *)arena, node_nz, skip_empty, w, bias, fill_neg_inf, Z, nzmask);
+    else if (count_bits == 64) k_predictor_scores<unsigned long long><<<grid, WARPS_PER_BLOCK * 32, 0, st>>>(*g, *r, *s, (const unsigned long long *)arena, node_nz, skip_empty, w, bias, fill_neg_inf, Z, nzmask);
+    else return fail(RL_ERR_ARG, "rl_predictor_scores: count_bits must be 32 or 64");
+    CHECK_LAUNCH("k_predictor_scores");
+    return RL_OK;
+}
+
+int rl_softmax_blocks(int32_t N) { return (N + SM_ROWS_PER_BLOCK - 1) / SM_ROWS_PER_BLOCK; }
+
+int rl_softmax_ce(const rl_graph *g, const rl_slots *s, const rl_answers *ans, float smoothing, int32_t use_mask,
+                  const float *Z, const uint32_t *nzmask, float *partial, float *stats, float *loss, float *tsum,
+                  float *G, void *stream)
+{
+    if (!g || !s || !ans || !Z || !nzmask || !partial || !stats || !loss || !tsum) return fail(RL_ERR_ARG, "rl_softmax_ce: null argument");
+    const int S = s->num_slots, N = g->num_entities;
+    if (S <= 0) return RL_OK;
+    const int nblk = rl_softmax_blocks(N);
+    cudaStream_t st = (cudaStream_t)stream;
+    k_softmax_partial<<<dim3(nblk, S), WARPS_PER_BLOCK * 32, 0, st>>>(N, Z, partial, nblk);
+    CHECK_LAUNCH("k_softmax_partial");
+    k_ce_finalize<<<S, WARPS_PER_BLOCK * 32, 0, st>>>(*g, *s, *ans, smoothing, use_mask, Z, nzmask, partial, nblk, stats, loss, tsum);
+    CHECK_LAUNCH("k_ce_finalize");
+    if (G) {
+        const size_t n = (size_t)N * RL_LANES;
+        k_grad_dense<<<dim3((unsigned)((n + 255) / 256), S), 256, 0, st>>>(N, Z, stats, tsum, G);
+        CHECK_LAUNCH("k_grad_dense");
+        k_grad_sparse<<<S, WARPS_PER_BLOCK * 32, 0, st>>>(*g, *s, *ans, smoothing, use_mask, Z, nzmask, stats, tsum, G);
+        CHECK_LAUNCH("k_grad_sparse");
+    }
+    return RL_OK;
+}
+
+int rl_predictor_backward(const rl_graph *g, const rl_rules *r, const rl_slots *s, int32_t count_bits,
+                          const void *arena, const int32_t *node_nz, int32_t skip_empty, const float *G,
+                          const float *slot_scale, int32_t max_terms, float *grad_w, float *grad_bias, void *stream)
+{
+    if (!g || !r || !s || !arena || !node_nz || !G || !grad_w) return fail(RL_ERR_ARG, "rl_predictor_backward: null argument");
+    const int S = s->num_slots, N = g->num_entities;
+    if (S <= 0) return RL_OK;
+    cudaStream_t st = (cudaStream_t)stream;
+    dim3 grid(max_terms > 0 ? max_terms : 1, S);
+    if (count_bits == 32) k_predictor_bwd_w<uint32_t><<<grid, 128, 0, st>>>(*g, *r, *s, (const uint32_t *)arena, node_nz, skip_empty, G, slot_scale, grad_w);
+    else if (count_bits == 64) k_predictor_bwd_w<unsigned long long><<<grid, 128, 0, st>>>(*g, *r, *s, (const unsigned long long *)arena, node_nz, skip_empty, G, slot_scale, grad_w);
+    else return fail(RL_ERR_ARG, "rl_predictor_backward: count_bits must be 32 or 64");
+    CHECK_LAUNCH("k_predictor_bwd_w");
+    if (grad_bias) {
+        k_bias_grad<<<(N + WARPS_PER_BLOCK - 1) / WARPS_PER_BLOCK, WARPS_PER_BLOCK * 32, 0, st>>>(N, S, G, slot_scale, grad_bias);
+        CHECK_LAUNCH("k_bias_grad");
+    }
+    return RL_OK;
+}
+
+int rl_filtered_rank(const rl_graph *g, const rl_slots *s, const rl_answers *known, int32_t use_mask,
+                     const float *Z, const uint32_t *nzmask, int32_t *counters, int64_t *LH, void *stream)
+{
+    if (!g || !s || !known || !Z || !nzmask || !counters || !LH) return fail(RL_ERR_ARG, "rl_filtered_rank: null argument");
+    const int S = s->num_slots, N = g->num_entities;
+    if (S <= 0) return RL_OK;
+    cudaStream_t st = (cudaStream_t)stream;
+    cudaError_t e = cudaMemsetAsync(counters, 0, (size_t)S * 64 * sizeof(int32_t), st);
+    if (e != cudaSuccess) return fail(RL_ERR_CUDA, "rl_filtered_rank: memset", e);
+    k_rank_count<<<dim3(rl_softmax_blocks(N), S), WARPS_PER_BLOCK * 32, 0, st>>>(N, *s, Z, counters);
+    CHECK_LAUNCH("k_rank_count");
+    k_rank_finalize<<<S, WARPS_PER_BLOCK * 32, 0, st>>>(*g, *s, *known, use_mask, Z, nzmask, counters, LH);
+    CHECK_LAUNCH("k_rank_finalize");
+    return RL_OK;
+}
+
+int rl_filtered_rank_dense(int64_t Q, int64_t N, const float *logits, const uint8_t *flag, const uint8_t *mask,
+                           const int64_t *t, int64_t *LH, void *stream)
+{
+    if (!logits || !flag || !mask || !t || !LH) return fail(RL_ERR_ARG, "rl_filtered_rank_dense: null argument");
+    if (Q <= 0) return RL_OK;
+    k_rank_dense<<<(unsigned)Q, 256, 0, (cudaStream_t)stream>>>(N, logits, flag, mask, t, LH);
+    CHECK_LAUNCH("k_rank_dense");
+    return RL_OK;
+}
+
+int rl_rank_metrics(int64_t Q, const int64_t *LH, const double *weight, int32_t expectation,
+                    const double *harmonic, double *sums, void *stream)
+{
+    if (!LH || !sums || (expectation && !harmonic)) return fail(RL_ERR_ARG, "rl_rank_metrics: null argument");
+    if (Q <= 0) return RL_OK;
+    int grid = (int)((Q + 255) / 256);
+    if (grid > 592) grid = 592;
+    k_rank_metrics<<<grid, 256, 0, (cudaStream_t)stream>>>(Q, LH, weight, expectation, harmonic, sums);
+    CHECK_LAUNCH("k_rank_metrics");
+    return RL_OK;
+}
+
+int rl_slot_to_dense(int32_t N, int32_t nq, const float *Zs, float *out, int64_t stride, void *stream)
+{
+    if (!Zs || !out || nq < 0 || nq > RL_LANES) return fail(RL_ERR_ARG, "rl_slot_to_dense: bad argument");
+    k_slot_to_dense<<<(N + 31) / 32, 1024, 0, (cudaStream_t)stream>>>(N, nq, Zs, out, stride);
+    CHECK_LAUNCH("k_slot_to_dense");
+    return RL_OK;
+}
+
+int rl_mask_to_dense(int32_t N, int32_t nq, const uint32_t *ms, uint8_t *out, int64_t stride, void *stream)
+{
+    if (!ms || !out || nq < 0 || nq > RL_LANES) return fail(RL_ERR_ARG, "rl_mask_to_dense: bad argument");
+    k_mask_to_dense<<<(N + 255) / 256, 256, 0, (cudaStream_t)stream>>>(N, nq, ms, out, stride);
+    CHECK_LAUNCH("k_mask_to_dense");
+    return RL_OK;
+}
+
+}  // extern "C"

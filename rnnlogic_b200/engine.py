@@ -1,0 +1,166 @@
+"""Host-side driver of the grounding kernels: cuts a call's queries into 32-lane slots, owns the
+frontier arena and runs the per-depth expansion launches (include/rnnlogic_b200.h).
+
+Reference semantics: KnowledgeGraph.grounding / propagate (src/data.py:136-173) for every rule
+of the batch's head relation at once."""
+from __future__ import annotations
+
+import ctypes as C
+from collections import OrderedDict
+from typing import List, Optional, Sequence
+
+import numpy as np
+import torch
+
+from . import _lib
+from .rules import CompiledRules
+
+LANES = _lib.LANES
+
+
+def _stream():
+    return C.c_void_p(torch.cuda.current_stream().cuda_stream)
+
+
+class Slots:
+    """Device-side description of one call (rl_slots) + its frontier arena."""
+
+    def __init__(self, dg, cr: CompiledRules, heads: np.ndarray, q_off: np.ndarray,
+                 all_h: torch.Tensor, all_t: Optional[torch.Tensor], etr: Optional[torch.Tensor]):
+        dev = dg.device
+        S = int(heads.shape[0])
+        self.S, self.heads, self.q_off = S, heads, q_off
+        self.nq = np.diff(q_off)
+        arena_off = np.zeros(S + 1, dtype=np.int64)
+        np.cumsum(cr.head_rows[heads], out=arena_off[1:])
+        nz_off = np.zeros(S + 1, dtype=np.int64)
+        np.cumsum(cr.head_nodes[heads], out=nz_off[1:])
+        self.arena_rows, self.nz_total = int(arena_off[-1]), int(nz_off[-1])
+        # one packed H2D copy for the slot descriptors
+        pack = np.concatenate([heads.astype(np.int64), q_off.astype(np.int64), nz_off[:-1], arena_off[:-1]])
+        d = torch.from_numpy(pack).to(dev, non_blocking=True)
+        self.slot_head = d[:S].to(torch.int32)
+        self.q_off_dev = d[S:2 * S + 1].to(torch.int32)
+        self.nz_off = d[2 * S + 1:3 * S + 1].to(torch.int32)
+        self.arena_off = d[3 * S + 1:4 * S + 1].contiguous()
+        self.lane = torch.empty(4, S * LANES, dtype=torch.int32, device=dev)
+        _lib.check(_lib.lib().rl_prepare_slots(
+            dg.ref(), S, self.slot_head.data_ptr(), self.q_off_dev.data_ptr(), all_h.data_ptr(),
+            all_t.data_ptr() if all_t is not None else None, etr.data_ptr() if etr is not None else None,
+            self.lane[0].data_ptr(), self.lane[1].data_ptr(), self.lane[2].data_ptr(), self.lane[3].data_ptr(),
+            _stream()), "rl_prepare_slots")
+        self.struct = _lib.RlSlots(S, self.slot_head.data_ptr(), self.lane[0].data_ptr(), self.lane[1].data_ptr(),
+                                   self.lane[2].data_ptr(), self.lane[3].data_ptr(), self.arena_off.data_ptr(),
+                                   self.nz_off.data_ptr())
+        self._keep = (all_h, all_t, etr, d)
+        self.arena = None
+        self.node_nz = None
+        self.overflow = None
+        self.count_bits = 32
+
+    def ref(self):
+        return C.byref(self.struct)
+
+
+class Grounder:
+    """Grounds every rule of a compiled rule set for batches of queries on one device."""
+
+    def __init__(self, graph, compiled: CompiledRules, device, skip_empty: bool = True):
+        self.graph, self.cr = graph, compiled
+        self.dg = graph.device_graph(device)
+        self.device = self.dg.device
+        self.dr = compiled.device_rules(self.device)
+        self.skip_empty = bool(skip_empty)
+        self.force_bits: Optional[int] = None
+
+    def make_slots(self, heads: Sequence[int], sizes: Sequence[int], all_h, all_t=None, etr=None) -> Slots:
+        """heads[i] / sizes[i]: head relation and number of queries of the i-th single-relation
+        group; queries are consecutive in all_h / all_t / etr (int64 CUDA tensors).  Groups larger
+        than 32 are split into several slots."""
+        for name, t in (("all_h", all_h), ("all_t", all_t), ("edges_to_remove", etr)):
+            if t is not None:
+                _lib.require_cuda(t, name)
+        sh, qo, pos = [], [0], 0
+        for hd, n in zip(heads, sizes):
+            for k in range(0, int(n), LANES):
+                sh.append(int(hd))
+                qo.append(pos + min(int(n), k + LANES))
+            pos += int(n)
+        if not sh:
+            raise ValueError("empty batch")
+        return Slots(self.dg, self.cr, np.array(sh, dtype=np.int64), np.array(qo, dtype=np.int64),
+                     all_h.contiguous(), None if all_t is None else all_t.contiguous(),
+                     None if etr is None else etr.contiguous())
+
+    def _run(self, sl: Slots, bits: int):
+        dev = self.device
+        sl.count_bits = bits
+        sl.arena = torch.empty(max(1, sl.arena_rows) * LANES, dtype=torch.int32 if bits == 32 else torch.int64,
+                               device=dev)
+        sl.node_nz = torch.zeros(max(1, sl.nz_total) + 1, dtype=torch.int32, device=dev)
+        sl.overflow = sl.node_nz[-1:]
+        L = _lib.lib()
+        lc = self.cr.level_chunks[sl.heads]                               # [S, max_len]
+        for depth in range(1, self.cr.max_len + 1):
+            gc = int(lc[:, depth - 1].max())
+            if gc == 0:
+                continue
+            _lib.check(L.rl_expand_level(self.dg.ref(), self.dr.ref(), sl.ref(), depth, gc, bits,
+                                         sl.arena.data_ptr(), sl.node_nz.data_ptr(), sl.overflow.data_ptr(),
+                                         int(self.skip_empty), _stream()), "rl_expand_level")
+
+    def ground(self, sl: Slots, check_overflow: bool = True) -> Slots:
+        """Run all depths.  Counts are kept in 32-bit rows; if any count does not fit (host sync on
+        one int when check_overflow) the call is repeated with 64-bit rows, which wrap exactly
+        like the reference's int64 tensors."""
+        bits = self.force_bits or 32
+        self._run(sl, bits)
+        if bits == 32 and check_overflow and int(sl.overflow.item()) != 0:
+            self._run(sl, 64)
+        return sl
+
+    def node_counts(self, sl: Slots, slot: int, node: int) -> torch.Tensor:
+        """int64[32, N] dense counts of one trie node (node < 0: the one-hot root)."""
+        out = torch.empty(LANES, self.graph.entity_size, dtype=torch.int64, device=self.device)
+        _lib.check(_lib.lib().rl_node_counts_dense(
+            self.dg.ref(), self.dr.ref(), sl.ref(), slot, node, sl.count_bits,
+            sl.arena.data_ptr() if sl.arena is not None else None,
+            sl.node_nz.data_ptr() if sl.node_nz is not None else None, int(self.skip_empty),
+            out.data_ptr(), _stream()), "rl_node_counts_dense")
+        return out
+
+    def rule_counts(self, sl: Slots, rule_ids: Sequence[int]) -> torch.Tensor:
+        """int64[len(rule_ids), Q, N] counts per rule (debug / parity; the production path never
+        materialises this tensor).  All slots must share the rules' head."""
+        Q = int(sl.q_off[-1])
+        out = torch.empty(len(rule_ids), Q, self.graph.entity_size, dtype=torch.int64, device=self.device)
+        for i, rid in enumerate(rule_ids):
+            node = int(self.cr.rule_node[rid])
+            for s in range(sl.S):
+                dense = self.node_counts(sl, s, node)
+                out[i, sl.q_off[s]:sl.q_off[s + 1]] = dense[:sl.nq[s]]
+        return out
+
+
+_CHAIN_CACHE_MAX = 4096
+
+
+def ground_chain(graph, h: torch.Tensor, r: int, body: List[int], etr: Optional[torch.Tensor]) -> torch.Tensor:
+    """KnowledgeGraph.grounding for one rule body (src/data.py:136-147)."""
+    _lib.require_cuda(h, "h")
+    key = (r, tuple(body))
+    cache = graph._chains
+    if key in cache:
+        cache.move_to_end(key)
+        cr = cache[key]
+    else:
+        cr = CompiledRules(graph, [(r, body)])
+        cache[key] = cr
+        if len(cache) > _CHAIN_CACHE_MAX:
+            cache.popitem(last=False)
+    gr = Grounder(graph, cr, h.device, skip_empty=True)
+    B = int(h.shape[0])
+    sl = gr.make_slots([r], [B], h.to(torch.int64), None, None if etr is None else etr.to(h.device, torch.int64))
+    if len(body):
+        gr.ground(sl)
+    return gr.rule_counts(sl, [0])[0]

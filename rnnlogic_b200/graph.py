@@ -1,0 +1,248 @@
+"""Knowledge-graph storage for the B200 hot path.
+
+Mirrors the interface of the reference ``KnowledgeGraph`` (src/data.py:9-173): same
+constructor, same attributes (``entity_size``, ``relation_size``, ``train_facts``, ``hr2o`` ...,
+``relation2ht2index``, ``encode_hr``, ``encode_ht``) and the same ``grounding(h, r, rule,
+edges_to_remove) -> int64[B,N]`` operator -- but the adjacency lives on the GPU as a
+relation-sorted DCSR by destination (include/rnnlogic_b200.h: rl_graph) and grounding runs the
+hand-written frontier-expansion kernel.  Host-side construction is vectorised numpy.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import os
+from collections import OrderedDict
+from typing import Dict, List, Optional, Sequence
+
+import numpy as np
+import torch
+
+from . import _lib
+
+
+def _answers_csr(N: int, parts: Sequence[np.ndarray]):
+    """(keys, ptr, ent): sorted unique keys r*N+h with their de-duplicated tails."""
+    tri = np.concatenate([p.reshape(-1, 3) for p in parts], axis=0).astype(np.int64)
+    if tri.shape[0] == 0:
+        return np.zeros(0, np.int64), np.zeros(1, np.int32), np.zeros(0, np.int32)
+    key = tri[:, 1] * N + tri[:, 0]
+    pair = np.unique(np.stack([key, tri[:, 2]], axis=1), axis=0)
+    keys, start = np.unique(pair[:, 0], return_index=True)
+    ptr = np.concatenate([start, [pair.shape[0]]]).astype(np.int32)
+    return keys.astype(np.int64), ptr, pair[:, 1].astype(np.int32)
+
+
+class DeviceGraph:
+    """Device-resident copy of the graph arrays + the C struct handed to the kernels."""
+
+    def __init__(self, kg: "KnowledgeGraph", device: torch.device):
+        self.device = device
+        h = kg.host
+        self.t = {k: torch.from_numpy(v).to(device) for k, v in h.items()}
+        t = self.t
+        self.struct = _lib.RlGraph(
+            kg.entity_size, kg.relation_size, kg.rank_words, int(h["row_dst"].shape[0]), int(h["edge_src"].shape[0]),
+            t["dst_ptr"].data_ptr(), t["row_dst"].data_ptr(), t["row_start"].data_ptr(), t["edge_src"].data_ptr(),
+            t["rank_tab"].data_ptr(), t["ord_ptr"].data_ptr(), t["ord_h"].data_ptr(), t["ord_t"].data_ptr(),
+            t["ent_ptr"].data_ptr(), t["ent_rel"].data_ptr(), t["ent_row"].data_ptr())
+        self.answers = {}
+        for which in ("hr2o", "hr2oo", "hr2ooo"):
+            keys, ptr, ent = kg.answers_csr(which)
+            tk, tp, te = (torch.from_numpy(a).to(device) for a in (keys, ptr, ent))
+            self.answers[which] = (_lib.RlAnswers(int(keys.shape[0]), tk.data_ptr(), tp.data_ptr(), te.data_ptr()),
+                                   (tk, tp, te))
+        hs = np.zeros(kg.entity_size + 2, dtype=np.float64)
+        hs[1:] = np.cumsum(1.0 / np.arange(1, kg.entity_size + 2, dtype=np.float64))
+        self.harmonic = torch.from_numpy(hs).to(device)
+
+    def ref(self):
+        return C.byref(self.struct)
+
+
+class KnowledgeGraph(object):
+    def __init__(self, data_path: Optional[str] = None, *, entity_size: Optional[int] = None,
+                 relation_size: Optional[int] = None, train=None, valid=None, test=None):
+        """``KnowledgeGraph(data_path)`` reads entities.dict / relations.dict / {train,valid,test}.txt
+        exactly like src/data.py:10-108.  The keyword form builds the same object from integer
+        id arrays [E,3] of (h, r, t) (synthetic graphs, tests)."""
+        self.data_path = data_path
+        self.entity2id, self.relation2id, self.id2entity, self.id2relation = {}, {}, {}, {}
+        if data_path is not None:
+            with open(os.path.join(data_path, "entities.dict")) as fi:
+                for line in fi:
+                    i, name = line.strip().split("\t")
+                    self.entity2id[name] = int(i)
+                    self.id2entity[int(i)] = name
+            with open(os.path.join(data_path, "relations.dict")) as fi:
+                for line in fi:
+                    i, name = line.strip().split("\t")
+                    self.relation2id[name] = int(i)
+                    self.id2relation[int(i)] = name
+            self.entity_size = len(self.entity2id)
+            self.relation_size = len(self.relation2id)
+            splits = []
+            for name in ("train", "valid", "test"):
+                rows = []
+                with open(os.path.join(data_path, name + ".txt")) as fi:
+                    for line in fi:
+                        h, r, t = line.strip().split("\t")
+                        rows.append((self.entity2id[h], self.relation2id[r], self.entity2id[t]))
+                splits.append(np.array(rows, dtype=np.int64).reshape(-1, 3))
+            train, valid, test = splits
+        else:
+            self.entity_size = int(entity_size)
+            self.relation_size = int(relation_size)
+            train = np.asarray(train, dtype=np.int64).reshape(-1, 3)
+            valid = np.zeros((0, 3), np.int64) if valid is None else np.asarray(valid, dtype=np.int64).reshape(-1, 3)
+            test = np.zeros((0, 3), np.int64) if test is None else np.asarray(test, dtype=np.int64).reshape(-1, 3)
+        self.train_array, self.valid_array, self.test_array = train, valid, test
+        self._lists: Dict[str, list] = {}
+        self._dicts: Dict[str, dict] = {}
+        self._csr: Dict[str, tuple] = {}
+        self._ht2index = None
+        self._devices: Dict[str, DeviceGraph] = {}
+        self._chains: "OrderedDict[tuple, object]" = OrderedDict()
+        self._build_host()
+        if data_path is not None:
+            print("Data loading | DONE!")
+
+    # ---- reference-compatible attributes (lazy: Python lists/dicts are slow at 2e7 edges) ----
+    def _facts(self, name):
+        if name not in self._lists:
+            arr = getattr(self, name + "_array")
+            self._lists[name] = [tuple(row) for row in arr.tolist()]
+        return self._lists[name]
+
+    train_facts = property(lambda self: self._facts("train"))
+    valid_facts = property(lambda self: self._facts("valid"))
+    test_facts = property(lambda self: self._facts("test"))
+
+    def _answer_dict(self, which):
+        """data.py:49-61,79-99 -- insertion order of the reference (train, then valid, then test)."""
+        if which not in self._dicts:
+            parts = {"hr2o": ("train",), "hr2oo": ("train", "valid"), "hr2ooo": ("train", "valid", "test")}[which]
+            d: Dict[int, List[int]] = {}
+            for p in parts:
+                for h, r, t in self._facts(p):
+                    d.setdefault(self.encode_hr(h, r), []).append(t)
+            self._dicts[which] = d
+        return self._dicts[which]
+
+    hr2o = property(lambda self: self._answer_dict("hr2o"))
+    hr2oo = property(lambda self: self._answer_dict("hr2oo"))
+    hr2ooo = property(lambda self: self._answer_dict("hr2ooo"))
+
+    @property
+    def relation2ht2index(self):
+        """data.py:66-69: per relation, (t*N+h) -> position in the relation's train-order edge list."""
+        if self._ht2index is None:
+            out = [dict() for _ in range(self.relation_size)]
+            for (h, r, t), k in zip(self._facts("train"), self.train_edge_index.tolist()):
+                out[r][self.encode_ht(h, t)] = k
+            self._ht2index = out
+        return self._ht2index
+
+    def encode_hr(self, h, r):
+        return r * self.entity_size + h
+
+    def decode_hr(self, index):
+        return index % self.entity_size, index // self.entity_size
+
+    def encode_ht(self, h, t):
+        return t * self.entity_size + h
+
+    def decode_ht(self, index):
+        return index % self.entity_size, index // self.entity_size
+
+    def answers_csr(self, which):
+        if which not in self._csr:
+            parts = {"hr2o": (self.train_array,), "hr2oo": (self.train_array, self.valid_array),
+                     "hr2ooo": (self.train_array, self.valid_array, self.test_array)}[which]
+            self._csr[which] = _answers_csr(self.entity_size, parts)
+        return self._csr[which]
+
+    # ---- host-side DCSR construction ---------------------------------------------------------
+    def _build_host(self):
+        N, R = self.entity_size, self.relation_size
+        tr = self.train_array
+        E = tr.shape[0]
+        if E >= 2 ** 31 or N >= 2 ** 31:
+            raise ValueError("graph too large for 32-bit indices")
+        h, r, t = tr[:, 0], tr[:, 1], tr[:, 2]
+        if E and (h.min() < 0 or h.max() >= N or t.min() < 0 or t.max() >= N or r.min() < 0 or r.max() >= R):
+            raise ValueError("triple id out of range")
+        # reference edge order: per relation, train.txt order (data.py:63-64)
+        order = np.argsort(r, kind="stable")
+        rel_sizes = np.bincount(r, minlength=R).astype(np.int64)
+        ord_ptr = np.zeros(R + 1, dtype=np.int64)
+        np.cumsum(rel_sizes, out=ord_ptr[1:])
+        self.train_edge_index = np.empty(E, dtype=np.int64)       # index of train fact i inside its relation
+        self.train_edge_index[order] = np.arange(E) - ord_ptr[r[order]]
+        # duplicates are an input error in the reference (assert at data.py:67)
+        full_key = (r * N + t) * N + h if N * N * max(R, 1) < 2 ** 62 else None
+        if full_key is not None and np.unique(full_key).shape[0] != E:
+            raise AssertionError("duplicate train triple")
+        # DCSR by destination: sort by (r, t, h)
+        srt = np.lexsort((h, t, r))
+        rs, ts, hs = r[srt], t[srt], h[srt]
+        rowkey = rs * N + ts
+        new_row = np.ones(E, dtype=bool)
+        new_row[1:] = rowkey[1:] != rowkey[:-1]
+        row_first = np.flatnonzero(new_row)
+        TR = row_first.shape[0]
+        row_rel = rs[row_first]
+        row_dst = ts[row_first]
+        row_start = np.concatenate([row_first, [E]])
+        dst_ptr = np.zeros(R + 1, dtype=np.int64)
+        np.cumsum(np.bincount(row_rel, minlength=R), out=dst_ptr[1:])
+        local_row = np.arange(TR) - dst_ptr[row_rel]
+        # rank table {bits, rows-before-word} per (relation, 32-entity word)
+        W = (N + 31) // 32
+        bits = np.zeros(R * W, dtype=np.uint32)
+        np.bitwise_or.at(bits, row_rel * W + (row_dst >> 5), (np.uint32(1) << (row_dst & 31).astype(np.uint32)))
+        pop = np.bitwise_count(bits).astype(np.int64).reshape(R, W) if R * W else np.zeros((R, W), np.int64)
+        prefix = np.cumsum(pop, axis=1) - pop
+        rank_tab = np.empty((R * W, 2), dtype=np.uint32)
+        rank_tab[:, 0] = bits
+        rank_tab[:, 1] = prefix.reshape(-1).astype(np.uint32)
+        # transpose: entity -> (relation, local row) pairs in which it is a tail
+        eo = np.lexsort((row_rel, row_dst))
+        ent_ptr = np.zeros(N + 1, dtype=np.int64)
+        np.cumsum(np.bincount(row_dst, minlength=N), out=ent_ptr[1:])
+        # per-relation statistics (algorithmic-bytes model)
+        self.rel_edges = rel_sizes
+        self.rel_rows = np.diff(dst_ptr)
+        srckey = np.unique(r * N + h)
+        self.rel_sources = np.bincount(srckey // N, minlength=R).astype(np.int64)
+        self.rank_words = W
+        i32 = lambda a: np.ascontiguousarray(a, dtype=np.int32)
+        self.host = {
+            "dst_ptr": i32(dst_ptr), "row_dst": i32(row_dst), "row_start": i32(row_start), "edge_src": i32(hs),
+            "rank_tab": np.ascontiguousarray(rank_tab.reshape(-1)),
+            "ord_ptr": i32(ord_ptr), "ord_h": i32(h[order]), "ord_t": i32(t[order]),
+            "ent_ptr": i32(ent_ptr), "ent_rel": i32(row_rel[eo]), "ent_row": i32(local_row[eo]),
+        }
+
+    def device_graph(self, device) -> DeviceGraph:
+        device = torch.device(device)
+        if device.type != "cuda":
+            raise _lib.RlError("rnnlogic_b200 is CUDA-only (sm_100a): no CPU fallback for grounding (got %s)" % device)
+        if device.index is None:
+            device = torch.device("cuda", torch.cuda.current_device())
+        key = str(device)
+        if key not in self._devices:
+            self._devices[key] = DeviceGraph(self, device)
+        return self._devices[key]
+
+    # ---- a6: grounding operator, API of src/data.py:136-147 ------------------------------------
+    def grounding(self, h, r, rule, edges_to_remove):
+        """int64[B,N] path counts of body ``rule`` from each h[b]; the query's own edge
+        (``edges_to_remove[b]``, an index into relation r's train-order edge list) is cut on the
+        hops whose relation equals r.  Bit-exact with the reference; CUDA tensors only."""
+        from .engine import ground_chain
+        return ground_chain(self, h, int(r), [int(x) for x in rule], edges_to_remove)
+
+    def propagate(self, x, relation, edges_to_remove=None):
+        raise NotImplementedError(
+            "rnnlogic_b200 fuses propagate (src/data.py:149-173) into the frontier-expansion kernel; "
+            "call grounding(h, r, rule, edges_to_remove) instead")

@@ -1,0 +1,174 @@
+"""Rule compiler: rule list -> per-head prefix tries + work tables (include/rnnlogic_b200.h:
+rl_rules).  Replaces the ``relation2rules`` table of the reference predictors
+(src/predictors.py:46-49, 186-189) for the GPU kernels.
+
+Sharing body prefixes is exact: the edge mask of a hop depends only on (head, hop relation)
+(src/data.py:143-146), so two rules of one head with the same prefix have the same frontier.
+"""
+from __future__ import annotations
+
+import ctypes as C
+from typing import Dict, List, Sequence, Tuple
+
+import numpy as np
+import torch
+
+from . import _lib
+
+LANES = _lib.LANES
+
+
+def parse_rules(inp) -> List[Tuple[int, List[int]]]:
+    """list[[head, body...]] or a file of whitespace-separated ints (predictors.py:27-43)."""
+    rules: List[Tuple[int, List[int]]] = []
+    if type(inp) == list:
+        for rule in inp:
+            rules.append((int(rule[0]), [int(v) for v in rule[1:]]))
+    elif type(inp) == str:
+        with open(inp, "r") as fi:
+            for line in fi:
+                toks = [int(v) for v in line.strip().split()]
+                rules.append((toks[0], toks[1:]))
+    else:
+        raise ValueError
+    return rules
+
+
+class CompiledRules:
+    def __init__(self, graph, rules: Sequence[Tuple[int, Sequence[int]]]):
+        self.graph = graph
+        R = graph.relation_size
+        self.num_rules = len(rules)
+        self.max_len = max([len(b) for _, b in rules] + [1])
+        rel_rows = graph.rel_rows
+        # ---- tries -------------------------------------------------------------------------
+        tries: List[Dict[tuple, int]] = [dict() for _ in range(R)]
+        per_head_nodes: List[List[tuple]] = [[] for _ in range(R)]      # (depth, rel, parent_prefix)
+        rule_leaf: List[tuple] = []
+        zero_rules: List[List[int]] = [[] for _ in range(R)]
+        for idx, (head, body) in enumerate(rules):
+            if not (0 <= head < R) or any(not (0 <= b < R) for b in body):
+                raise ValueError("rule %d uses a relation id outside [0, %d)" % (idx, R))
+            body = tuple(body)
+            if len(body) == 0:
+                zero_rules[head].append(idx)
+                rule_leaf.append(None)
+                continue
+            trie = tries[head]
+            for d in range(1, len(body) + 1):
+                pre = body[:d]
+                if pre not in trie:
+                    trie[pre] = len(per_head_nodes[head])
+                    per_head_nodes[head].append((d, pre[-1], pre[:-1]))
+            rule_leaf.append((head, body))
+        # global node numbering: by head, then depth (stable)
+        node_rel, node_parent, node_depth, node_head = [], [], [], []
+        head_node_ptr = np.zeros(R + 1, dtype=np.int64)
+        gid: List[Dict[tuple, int]] = [dict() for _ in range(R)]
+        for q in range(R):
+            nodes = per_head_nodes[q]
+            order = sorted(range(len(nodes)), key=lambda i: nodes[i][0])
+            base = len(node_rel)
+            local_pre = {v: k for k, v in tries[q].items()}
+            for new, old in enumerate(order):
+                gid[q][local_pre[old]] = base + new
+            for old in order:
+                d, rel, ppre = nodes[old]
+                node_rel.append(rel)
+                node_depth.append(d)
+                node_head.append(q)
+                node_parent.append(gid[q][ppre] if len(ppre) else -1)
+            head_node_ptr[q + 1] = len(node_rel)
+        self.num_nodes = len(node_rel)
+        node_rel = np.array(node_rel, dtype=np.int64)
+        node_depth = np.array(node_depth, dtype=np.int64)
+        node_head = np.array(node_head, dtype=np.int64)
+        node_parent = np.array(node_parent, dtype=np.int64)
+        node_rows = rel_rows[node_rel] if self.num_nodes else np.zeros(0, np.int64)
+        # arena rows per head and per-node offset inside the head's arena
+        csum = np.zeros(self.num_nodes + 1, dtype=np.int64)
+        np.cumsum(node_rows, out=csum[1:])
+        head_row_base = csum[head_node_ptr[:-1]]
+        node_row_off = csum[:-1] - (head_row_base[node_head] if self.num_nodes else 0)
+        self.head_rows = csum[head_node_ptr[1:]] - csum[head_node_ptr[:-1]]
+        self.head_nodes = np.diff(head_node_ptr)
+        # chunks of <= 32 rows
+        nch = (node_rows + LANES - 1) // LANES
+        chunk_node = np.repeat(np.arange(self.num_nodes), nch)
+        cstart = np.zeros(self.num_nodes + 1, dtype=np.int64)
+        np.cumsum(nch, out=cstart[1:])
+        chunk_row0 = (np.arange(chunk_node.shape[0]) - cstart[chunk_node]) * LANES
+        self.num_chunks = int(chunk_node.shape[0])
+        L1 = self.max_len + 1
+        # lvl_ptr[q, d] = first chunk of the first node with (head q, depth > d)
+        nkey = node_head * (L1 + 1) + node_depth                     # ascending in node order
+        want = (np.arange(R)[:, None] * (L1 + 1) + np.arange(1, L1 + 1)[None, :]).reshape(-1)
+        first_node = np.searchsorted(nkey, want, side="left")
+        lvl_ptr = cstart[first_node].reshape(R, L1)
+        self.level_chunks = np.diff(lvl_ptr, axis=1)                  # [R, max_len] chunks per (head, depth)
+        # terminal lists keyed by (head, last relation)
+        t_rule = np.array([i for i, lf in enumerate(rule_leaf) if lf is not None], dtype=np.int64)
+        t_node = np.array([gid[lf[0]][lf[1]] for lf in rule_leaf if lf is not None], dtype=np.int64)
+        if t_rule.shape[0]:
+            t_key = node_head[t_node] * R + node_rel[t_node]
+            o = np.lexsort((t_rule, t_key))
+            t_rule, t_node, t_key = t_rule[o], t_node[o], t_key[o]
+        else:
+            t_key = np.zeros(0, np.int64)
+        term_ptr = np.zeros(R * R + 1, dtype=np.int64)
+        np.cumsum(np.bincount(t_key, minlength=R * R), out=term_ptr[1:])
+        self.num_terms = int(t_rule.shape[0])
+        self.head_terms = term_ptr[(np.arange(R) + 1) * R] - term_ptr[np.arange(R) * R]
+        self.rule_node = np.full(self.num_rules, -1, dtype=np.int64)
+        self.rule_node[t_rule] = t_node
+        zr_ptr = np.zeros(R + 1, dtype=np.int64)
+        np.cumsum([len(z) for z in zero_rules], out=zr_ptr[1:])
+        zr_rule = np.array([i for z in zero_rules for i in z], dtype=np.int64)
+        # rule ids per head in rule-file order (reference relation2rules order)
+        self.rules = list(rules)
+        self.head_rules: List[List[int]] = [[] for _ in range(R)]
+        for idx, (head, _) in enumerate(rules):
+            self.head_rules[head].append(idx)
+        # algorithmic bytes per head for a 32-lane slot: c = i = 4 bytes
+        E, D, U = graph.rel_edges, graph.rel_rows, graph.rel_sources
+        per_node = 4 * E[node_rel] + 8 * D[node_rel] + 4 * LANES * ((node_depth > 1) * U[node_rel] + D[node_rel]) \
+            if self.num_nodes else np.zeros(0, np.int64)
+        nb = np.zeros(self.num_nodes + 1, dtype=np.int64)
+        np.cumsum(per_node, out=nb[1:])
+        self.head_ground_bytes = nb[head_node_ptr[1:]] - nb[head_node_ptr[:-1]]
+        self.node_depth, self.node_rel_host, self.node_head = node_depth, node_rel, node_head
+        self.head_node_ptr = head_node_ptr
+        i32 = lambda a: np.ascontiguousarray(a, dtype=np.int32)
+        if self.num_chunks >= 2 ** 31 or self.num_nodes >= 2 ** 31:
+            raise ValueError("rule set too large for 32-bit work tables")
+        self.host = {
+            "node_rel": i32(node_rel), "node_parent": i32(node_parent),
+            "node_row_off": np.ascontiguousarray(node_row_off, dtype=np.int64),
+            "head_node_ptr": i32(head_node_ptr), "lvl_ptr": i32(lvl_ptr.reshape(-1)),
+            "chunk_node": i32(chunk_node), "chunk_row0": i32(chunk_row0), "term_ptr": i32(term_ptr),
+            "term_node": i32(t_node), "term_rule": i32(t_rule), "zr_ptr": i32(zr_ptr), "zr_rule": i32(zr_rule),
+        }
+        self._devices = {}
+
+    def device_rules(self, device) -> "DeviceRules":
+        key = str(device)
+        if key not in self._devices:
+            self._devices[key] = DeviceRules(self, device)
+        return self._devices[key]
+
+
+class DeviceRules:
+    def __init__(self, cr: CompiledRules, device):
+        self.device = device
+        # zero-length arrays still need a valid (non-null) pointer for the arg checks
+        self.t = {k: torch.from_numpy(v if v.shape[0] else np.zeros(1, v.dtype)).to(device) for k, v in cr.host.items()}
+        t = self.t
+        self.struct = _lib.RlRules(
+            cr.num_nodes, cr.num_rules, cr.max_len, cr.num_chunks, cr.num_terms,
+            t["node_rel"].data_ptr(), t["node_parent"].data_ptr(), t["node_row_off"].data_ptr(),
+            t["head_node_ptr"].data_ptr(), t["lvl_ptr"].data_ptr(), t["chunk_node"].data_ptr(),
+            t["chunk_row0"].data_ptr(), t["term_ptr"].data_ptr(), t["term_node"].data_ptr(),
+            t["term_rule"].data_ptr(), t["zr_ptr"].data_ptr(), t["zr_rule"].data_ptr())
+
+    def ref(self):
+        return C.byref(self.struct)
