@@ -148,15 +148,18 @@ int rl_predictor_scores(const rl_graph *g, const rl_rules *r, const rl_slots *s,
 
 /* Kernel (2b): log(softmax + 1e-8) cross-entropy against the smoothed target, replaces
  * src/trainer.py:84,88-89, fused with its backward.  target = smoothing * multi_hot(train
- * answers of (h, head)) + (1 - smoothing) * one_hot(t).  Outputs, per slot:
- * loss[S] (already divided by max(sum target, 1)), tsum[S]; G[S][N][32] = dloss_s/dZ.
+ * answers of (h, head)) + (1 - smoothing) * one_hot(t).  A GROUP is one reference batch: slots
+ * [group_ptr[i], group_ptr[i+1]) (DEVICE int32[n_groups+1]; NULL <=> every slot is its own
+ * group).  Outputs: group_loss[n_groups] = -sum lp*target / max(sum target, 1), group_tsum
+ * [n_groups] = sum target, and (when G != NULL) G[S][N][32] = d group_loss / dZ.
  * use_mask != 0 <=> entity_feature != 'bias' (only cells with their nzmask bit take part).
- * partial is scratch of S * nblk * 64 floats with nblk = rl_softmax_blocks(N). */
+ * Scratch: partial = S * rl_softmax_blocks(N) * 64 floats, stats = S*32*4 floats
+ * (max, sum-exp, S_b, valid per lane), slot_sums = 3*S floats. */
 int rl_softmax_blocks(int32_t num_entities);
 int rl_softmax_ce(const rl_graph *g, const rl_slots *s, const rl_answers *train_answers,
                   float smoothing, int32_t use_mask, const float *Z, const uint32_t *nzmask,
-                  float *partial, float *stats, float *loss, float *tsum, float *G,
-                  void *stream);
+                  int32_t n_groups, const int32_t *group_ptr, float *partial, float *stats,
+                  float *slot_sums, float *group_loss, float *group_tsum, float *G, void *stream);
 
 /* Kernel (2c): backward into rule weights and bias, replaces autograd through
  * src/predictors.py:64,74.  grad_w[num_rules] and grad_bias[N] (may be NULL) are ACCUMULATED

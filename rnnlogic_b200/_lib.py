@@ -81,7 +81,7 @@ _PROTOS = {
                                       vp, vp, C.c_int32, vp, vp, C.c_int32, vp, vp, vp]),
     "rl_softmax_blocks": (C.c_int, [C.c_int32]),
     "rl_softmax_ce": (C.c_int, [C.POINTER(RlGraph), C.POINTER(RlSlots), C.POINTER(RlAnswers), C.c_float,
-                                C.c_int32, vp, vp, vp, vp, vp, vp, vp, vp]),
+                                C.c_int32, vp, vp, C.c_int32, vp, vp, vp, vp, vp, vp, vp, vp]),
     "rl_predictor_backward": (C.c_int, [C.POINTER(RlGraph), C.POINTER(RlRules), C.POINTER(RlSlots), C.c_int32,
                                         vp, vp, C.c_int32, vp, vp, C.c_int32, vp, vp, vp]),
     "rl_filtered_rank": (C.c_int, [C.POINTER(RlGraph), C.POINTER(RlSlots), C.POINTER(RlAnswers), C.c_int32,

@@ -325,7 +325,7 @@ __global__ void __launch_bounds__(WARPS_PER_BLOCK * 32)
 k_ce_finalize(rl_graph g, rl_slots s, rl_answers ans, float smoothing, int use_mask,
               const float *__restrict__ Z, const uint32_t *__restrict__ nzmask,
               const float *__restrict__ partial, int nblk, float *__restrict__ stats,
-              float *__restrict__ loss, float *__restrict__ tsum)
+              float *__restrict__ slot_lsum, float *__restrict__ slot_tsum)
 {
     __shared__ float sm_m[32], sm_s[32];
     __shared__ double red_l[WARPS_PER_BLOCK], red_t[WARPS_PER_BLOCK];
@@ -392,27 +392,43 @@ k_ce_finalize(rl_graph g, rl_slots s, rl_answers ans, float smoothing, int use_m
     if (threadIdx.x == 0) {
         double L = 0.0, T = 0.0;
         for (int k = 0; k < WARPS_PER_BLOCK; ++k) { L += red_l[k]; T += red_t[k]; }
-        const float Tf = (float)T;
-        tsum[slot] = Tf;
-        loss[slot] = (float)(-L) / fmaxf(Tf, 1.f);
+        slot_tsum[slot] = (float)T;
+        slot_lsum[slot] = (float)(-L);
     }
+}
+
+// per group (= one reference batch, possibly several slots): loss = -sum lp*tgt / max(sum tgt, 1)
+// (trainer.py:89); slot_invT[s] = 1 / max(T_group, 1)
+__global__ void k_group_reduce(int n_groups, const int32_t *__restrict__ group_ptr, const float *__restrict__ slot_lsum,
+                               const float *__restrict__ slot_tsum, float *__restrict__ group_loss,
+                               float *__restrict__ group_tsum, float *__restrict__ slot_invT)
+{
+    const int gi = blockIdx.x * blockDim.x + threadIdx.x;
+    if (gi >= n_groups) return;
+    const int s0 = group_ptr ? group_ptr[gi] : gi, s1 = group_ptr ? group_ptr[gi + 1] : gi + 1;
+    double L = 0.0, T = 0.0;
+    for (int k = s0; k < s1; ++k) { L += (double)slot_lsum[k]; T += (double)slot_tsum[k]; }
+    const float Tf = fmaxf((float)T, 1.f);
+    group_tsum[gi] = (float)T;
+    group_loss[gi] = (float)L / Tf;
+    for (int k = s0; k < s1; ++k) slot_invT[k] = 1.f / Tf;
 }
 
 // G[e][b] = softmax * S_b / T'   (dense part of dloss/dZ)
 __global__ void __launch_bounds__(256)
 k_grad_dense(int N, const float *__restrict__ Z, const float *__restrict__ stats,
-             const float *__restrict__ tsum, float *__restrict__ G)
+             const float *__restrict__ slot_invT, float *__restrict__ G)
 {
     const int slot = blockIdx.y;
     const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= (size_t)N * RL_LANES) return;
     const int b = (int)(i & 31);
     const float *st = stats + ((size_t)slot * 32 + b) * 4;
-    const float T = fmaxf(tsum[slot], 1.f);
+    const float iT = slot_invT[slot];
     float gval = 0.f;
     if (st[3] != 0.f) {
         const float z = Z[(size_t)slot * N * RL_LANES + i];
-        if (z != -INFINITY) gval = expf(z - st[0]) / st[1] * st[2] / T;
+        if (z != -INFINITY) gval = expf(z - st[0]) / st[1] * st[2] * iT;
     }
     G[(size_t)slot * N * RL_LANES + i] = gval;
 }
@@ -421,7 +437,7 @@ k_grad_dense(int N, const float *__restrict__ Z, const float *__restrict__ stats
 __global__ void __launch_bounds__(WARPS_PER_BLOCK * 32)
 k_grad_sparse(rl_graph g, rl_slots s, rl_answers ans, float smoothing, int use_mask,
               const float *__restrict__ Z, const uint32_t *__restrict__ nzmask,
-              const float *__restrict__ stats, const float *__restrict__ tsum, float *__restrict__ G)
+              const float *__restrict__ stats, const float *__restrict__ slot_invT, float *__restrict__ G)
 {
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const int slot = blockIdx.x;
@@ -430,7 +446,7 @@ k_grad_sparse(rl_graph g, rl_slots s, rl_answers ans, float smoothing, int use_m
     const float *Zs = Z + (size_t)slot * N * RL_LANES;
     float *Gs = G + (size_t)slot * N * RL_LANES;
     const uint32_t *ms = nzmask + (size_t)slot * N;
-    const float T = fmaxf(tsum[slot], 1.f);
+    const float iT = slot_invT[slot];
     for (int b = warp; b < 32; b += WARPS_PER_BLOCK) {
         const float *st = stats + ((size_t)slot * 32 + b) * 4;
         if (st[3] == 0.f) continue;
@@ -446,13 +462,13 @@ k_grad_sparse(rl_graph g, rl_slots s, rl_answers ans, float smoothing, int use_m
             if (e == t) { tg += 1.f - smoothing; saw_t = true; }
             if (use_mask && !((ms[e] >> b) & 1u)) continue;
             const float p = expf(Zs[(size_t)e * RL_LANES + b] - M) / S;
-            Gs[(size_t)e * RL_LANES + b] -= p * (tg / (p + 1e-8f)) / T;
+            Gs[(size_t)e * RL_LANES + b] -= p * (tg / (p + 1e-8f)) * iT;
         }
         saw_t = __any_sync(FULL, saw_t);
         if (!saw_t && t >= 0 && lane == 0 && !(use_mask && !((ms[t] >> b) & 1u))) {
             const float tg = 1.f - smoothing;
             const float p = expf(Zs[(size_t)t * RL_LANES + b] - M) / S;
-            Gs[(size_t)t * RL_LANES + b] -= p * (tg / (p + 1e-8f)) / T;
+            Gs[(size_t)t * RL_LANES + b] -= p * (tg / (p + 1e-8f)) * iT;
         }
     }
 }
@@ -758,23 +774,29 @@ int rl_predictor_scores(const rl_graph *g, const rl_rules *r, const rl_slots *s,
 int rl_softmax_blocks(int32_t N) { return (N + SM_ROWS_PER_BLOCK - 1) / SM_ROWS_PER_BLOCK; }
 
 int rl_softmax_ce(const rl_graph *g, const rl_slots *s, const rl_answers *ans, float smoothing, int32_t use_mask,
-                  const float *Z, const uint32_t *nzmask, float *partial, float *stats, float *loss, float *tsum,
+                  const float *Z, const uint32_t *nzmask, int32_t n_groups, const int32_t *group_ptr,
+                  float *partial, float *stats, float *slot_sums, float *group_loss, float *group_tsum,
                   float *G, void *stream)
 {
-    if (!g || !s || !ans || !Z || !nzmask || !partial || !stats || !loss || !tsum) return fail(RL_ERR_ARG, "rl_softmax_ce: null argument");
+    if (!g || !s || !ans || !Z || !nzmask || !partial || !stats || !slot_sums || !group_loss || !group_tsum)
+        return fail(RL_ERR_ARG, "rl_softmax_ce: null argument");
     const int S = s->num_slots, N = g->num_entities;
     if (S <= 0) return RL_OK;
+    if (n_groups <= 0 || n_groups > S || (!group_ptr && n_groups != S)) return fail(RL_ERR_ARG, "rl_softmax_ce: bad group table");
     const int nblk = rl_softmax_blocks(N);
     cudaStream_t st = (cudaStream_t)stream;
+    float *slot_lsum = slot_sums, *slot_tsum = slot_sums + S, *slot_invT = slot_sums + 2 * (size_t)S;
     k_softmax_partial<<<dim3(nblk, S), WARPS_PER_BLOCK * 32, 0, st>>>(N, Z, partial, nblk);
     CHECK_LAUNCH("k_softmax_partial");
-    k_ce_finalize<<<S, WARPS_PER_BLOCK * 32, 0, st>>>(*g, *s, *ans, smoothing, use_mask, Z, nzmask, partial, nblk, stats, loss, tsum);
+    k_ce_finalize<<<S, WARPS_PER_BLOCK * 32, 0, st>>>(*g, *s, *ans, smoothing, use_mask, Z, nzmask, partial, nblk, stats, slot_lsum, slot_tsum);
     CHECK_LAUNCH("k_ce_finalize");
+    k_group_reduce<<<(n_groups + 127) / 128, 128, 0, st>>>(n_groups, group_ptr, slot_lsum, slot_tsum, group_loss, group_tsum, slot_invT);
+    CHECK_LAUNCH("k_group_reduce");
     if (G) {
         const size_t n = (size_t)N * RL_LANES;
-        k_grad_dense<<<dim3((unsigned)((n + 255) / 256), S), 256, 0, st>>>(N, Z, stats, tsum, G);
+        k_grad_dense<<<dim3((unsigned)((n + 255) / 256), S), 256, 0, st>>>(N, Z, stats, slot_invT, G);
         CHECK_LAUNCH("k_grad_dense");
-        k_grad_sparse<<<S, WARPS_PER_BLOCK * 32, 0, st>>>(*g, *s, *ans, smoothing, use_mask, Z, nzmask, stats, tsum, G);
+        k_grad_sparse<<<S, WARPS_PER_BLOCK * 32, 0, st>>>(*g, *s, *ans, smoothing, use_mask, Z, nzmask, stats, slot_invT, G);
         CHECK_LAUNCH("k_grad_sparse");
     }
     return RL_OK;

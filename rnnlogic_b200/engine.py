@@ -92,6 +92,25 @@ class Grounder:
                      all_h.contiguous(), None if all_t is None else all_t.contiguous(),
                      None if etr is None else etr.contiguous())
 
+    def make_slots_host(self, batches, with_etr: bool, etr_lists=None) -> Slots:
+        """Slots for a list of single-relation batches given as host lists of (h, r, t) triples
+        (what the datasets hold).  One packed host->device copy carries h, t and the removed-edge
+        indices; with_etr looks the indices up in the graph's train-edge table (data.py:214-216)."""
+        heads = [b[0][1] for b in batches]
+        sizes = [len(b) for b in batches]
+        flat = np.array([x for b in batches for x in b], dtype=np.int64).reshape(-1, 3)
+        rows = [flat[:, 0], flat[:, 2]]
+        if with_etr:
+            if etr_lists is not None:
+                rows.append(np.array([e for l in etr_lists for e in l], dtype=np.int64))
+            else:
+                rows.append(self.graph.edge_index_of(flat))
+        d = torch.from_numpy(np.ascontiguousarray(np.stack(rows))).to(self.device, non_blocking=True)
+        sl = self.make_slots(heads, sizes, d[0], d[1], d[2] if with_etr else None)
+        sl.group_sizes = sizes
+        sl.h2d_bytes = int(d.numel() * 8)
+        return sl
+
     def _run(self, sl: Slots, bits: int):
         dev = self.device
         sl.count_bits = bits

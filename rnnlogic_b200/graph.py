@@ -154,6 +154,24 @@ class KnowledgeGraph(object):
     def decode_ht(self, index):
         return index % self.entity_size, index // self.entity_size
 
+    def edge_index_of(self, triples: np.ndarray) -> np.ndarray:
+        """Position of each (h, r, t) train triple inside relation r's train-order edge list -- the
+        ``edges_to_remove`` value of the reference's TrainDataset (data.py:214-216).  Vectorised
+        binary search over the sorted train keys; raises KeyError for a triple not in train."""
+        N = self.entity_size
+        if getattr(self, "_train_keys", None) is None:
+            tr = self.train_array
+            key = (tr[:, 1] * N + tr[:, 2]) * N + tr[:, 0]
+            o = np.argsort(key, kind="stable")
+            self._train_keys, self._train_keys_idx = key[o], self.train_edge_index[o]
+        tri = np.asarray(triples, dtype=np.int64).reshape(-1, 3)
+        key = (tri[:, 1] * N + tri[:, 2]) * N + tri[:, 0]
+        pos = np.searchsorted(self._train_keys, key)
+        pos = np.minimum(pos, self._train_keys.shape[0] - 1)
+        if not np.array_equal(self._train_keys[pos], key):
+            raise KeyError("triple not in train.txt")
+        return self._train_keys_idx[pos]
+
     def answers_csr(self, which):
         if which not in self._csr:
             parts = {"hr2o": (self.train_array,), "hr2oo": (self.train_array, self.valid_array),

@@ -1,0 +1,161 @@
+"""GPU parity of Predictor (kernels 2a/2b/2c/3) against the reference's golden outputs and the
+oracle: logits / loss / MRR within 1e-5 relative (north_star), (L,H) bounds exact up to fp32
+near-ties, gradients within 1e-4."""
+import numpy as np
+import pytest
+import torch
+
+from tests import _golden as G
+
+pytestmark = pytest.mark.gpu
+DEV = "cuda:0"
+
+
+def make_kg(fx):
+    from rnnlogic_b200 import KnowledgeGraph
+    return KnowledgeGraph(entity_size=int(fx["N"]), relation_size=int(fx["R"]), train=fx["train"],
+                          valid=fx["valid"], test=fx["test"])
+
+
+def make_predictor(fx, kg, ef):
+    from rnnlogic_b200.predictors import Predictor
+    m = Predictor(kg, entity_feature=ef)
+    m.set_rules(G.rules_of(fx))
+    with torch.no_grad():
+        m.rule_weights.copy_(torch.from_numpy(fx["pred_%s_w" % ef]))
+        if ef == "bias":
+            m.bias.copy_(torch.from_numpy(fx["pred_bias_b"]))
+    return m.cuda()
+
+
+@pytest.fixture(scope="module", params=G.DATASETS)
+def ds(request):
+    fx = G.load(request.param)
+    return request.param, fx, make_kg(fx)
+
+
+def ref_loss(score, mask, target, all_t, smoothing=0.2):
+    tgt = target * smoothing + torch.nn.functional.one_hot(all_t, target.shape[1]) * (1 - smoothing)
+    lp = (torch.softmax(score, dim=1) + 1e-8).log()
+    return -(lp[mask] * tgt[mask]).sum() / torch.clamp(tgt[mask].sum(), min=1)
+
+
+@pytest.mark.parametrize("ef", ["bias", "none"])
+def test_forward_api_loss_and_autograd(ds, ef):
+    name, fx, kg = ds
+    m = make_predictor(fx, kg, ef)
+    for j in range(5):
+        if "pred_%s_tb%d_score" % (ef, j) not in fx:
+            continue
+        tri, target, etr = G.train_batch_inputs(fx, j)
+        tri_t = torch.from_numpy(tri).to(DEV)
+        m.zero_grad()
+        score, mask = m(tri_t[:, 0], tri_t[:, 1], etr.to(DEV))
+        assert score.dtype == torch.float32 and mask.dtype == torch.bool
+        assert np.array_equal(mask.cpu().numpy(), fx["pred_%s_tb%d_mask" % (ef, j)])
+        np.testing.assert_allclose(score.detach().cpu().numpy(), fx["pred_%s_tb%d_score" % (ef, j)], rtol=1e-5, atol=2e-6)
+        if "pred_%s_tb%d_loss" % (ef, j) in fx:
+            loss = ref_loss(score, mask, target.to(DEV), tri_t[:, 2])
+            loss.backward()
+            np.testing.assert_allclose(loss.item(), fx["pred_%s_tb%d_loss" % (ef, j)], rtol=1e-5)
+            np.testing.assert_allclose(m.rule_weights.grad.cpu().numpy(), fx["pred_%s_tb%d_gw" % (ef, j)], rtol=1e-4, atol=1e-6)
+            if ef == "bias":
+                np.testing.assert_allclose(m.bias.grad.cpu().numpy(), fx["pred_bias_tb%d_gb" % j], rtol=1e-4, atol=1e-7)
+    for j in range(4):
+        key = "pred_%s_vb%d_score" % (ef, j)
+        if key not in fx:
+            continue
+        tri, flag = G.valid_batch_inputs(fx, j)
+        tri_t = torch.from_numpy(tri).to(DEV)
+        with torch.no_grad():
+            score, mask = m(tri_t[:, 0], tri_t[:, 1], None)
+        assert np.array_equal(mask.cpu().numpy(), fx["pred_%s_vb%d_mask" % (ef, j)])
+        np.testing.assert_allclose(score.cpu().numpy(), fx[key], rtol=1e-5, atol=2e-6)
+
+
+@pytest.mark.parametrize("ef", ["bias", "none"])
+def test_fused_train_step_matches_reference(ds, ef):
+    """Fused ground->aggregate->CE->backward (no dense target) == reference loss and gradients,
+    one batch at a time and several batches in one call (gradient accumulation)."""
+    name, fx, kg = ds
+    m = make_predictor(fx, kg, ef)
+    js = [j for j in range(5) if "pred_%s_tb%d_loss" % (ef, j) in fx]
+    acc_w = 0
+    for j in js:
+        tri, _, _ = G.train_batch_inputs(fx, j)
+        m.zero_grad()
+        loss, tsum = m.fused_train_step([[tuple(x) for x in tri.tolist()]], 0.2)
+        np.testing.assert_allclose(loss[0].item(), fx["pred_%s_tb%d_loss" % (ef, j)], rtol=1e-5)
+        np.testing.assert_allclose(m.rule_weights.grad.cpu().numpy(), fx["pred_%s_tb%d_gw" % (ef, j)], rtol=1e-4, atol=1e-6)
+        if ef == "bias":
+            np.testing.assert_allclose(m.bias.grad.cpu().numpy(), fx["pred_bias_tb%d_gb" % j], rtol=1e-4, atol=1e-7)
+        acc_w = acc_w + fx["pred_%s_tb%d_gw" % (ef, j)]
+    m.zero_grad()
+    batches = [[tuple(x) for x in G.train_batch_inputs(fx, j)[0].tolist()] for j in js]
+    loss, tsum = m.fused_train_step(batches, 0.2)
+    for k, j in enumerate(js):
+        np.testing.assert_allclose(loss[k].item(), fx["pred_%s_tb%d_loss" % (ef, j)], rtol=1e-5)
+    np.testing.assert_allclose(m.rule_weights.grad.cpu().numpy(), acc_w, rtol=1e-4, atol=2e-6)
+
+
+def test_compute_H(ds):
+    name, fx, kg = ds
+    m = make_predictor(fx, kg, "bias")
+    for j in range(5):
+        if "pred_bias_tb%d_H" % j not in fx:
+            continue
+        tri, _, etr = G.train_batch_inputs(fx, j)
+        tri_t = torch.from_numpy(tri).to(DEV)
+        H, idx = m.compute_H(tri_t[:, 0], tri_t[:, 1], tri_t[:, 2], etr.to(DEV))
+        assert np.array_equal(idx.cpu().numpy(), fx["pred_bias_tb%d_Hidx" % j])
+        np.testing.assert_allclose(H.cpu().numpy(), fx["pred_bias_tb%d_H" % j], rtol=1e-4, atol=1e-6)
+
+
+@pytest.mark.parametrize("ef", ["bias", "none"])
+def test_fused_rank_and_metrics_vs_reference_evaluate(ds, ef):
+    """(h,r,t,L,H) rows and Hit@k/MR/MRR of the reference's TrainerPredictor.evaluate('valid')."""
+    from rnnlogic_b200.trainer import summarize_ranks
+    name, fx, kg = ds
+    m = make_predictor(fx, kg, ef)
+    sizes = fx["eval_%s_batches" % ef]
+    triples = fx["eval_%s_triples" % ef].astype(np.int64)
+    batches, off = [], 0
+    for n in sizes:
+        batches.append([tuple(x) for x in triples[off:off + n].tolist()])
+        off += n
+    rows = []
+    for c0 in range(0, len(batches), 16):
+        LH = m.fused_rank(batches[c0:c0 + 16], "valid")
+        tri = torch.tensor([x for b in batches[c0:c0 + 16] for x in b], dtype=torch.long, device=DEV)
+        rows.append(torch.cat([tri, LH], 1))
+    ranks = torch.cat(rows, 0)
+    got = ranks.cpu().numpy()
+    want = fx["eval_%s_rows" % ef]
+    got_s = got[np.lexsort(got.T[::-1])]
+    want_s = want[np.lexsort(want.T[::-1])]
+    assert np.array_equal(got_s[:, :3], want_s[:, :3])
+    frac = (got_s[:, 3:] != want_s[:, 3:]).any(axis=1).mean()
+    assert frac <= 0.002, frac                     # fp32 near-ties may flip a bound by one
+    for expectation in (True, False):
+        res = summarize_ranks(m, ranks, expectation, kg.entity_size)
+        logged = fx["eval_%s_%d_logged" % (ef, expectation)]
+        assert res["data"] == int(logged[0])
+        np.testing.assert_allclose(res["mrr"], fx["eval_%s_%d_mrr" % (ef, expectation)], rtol=1e-5)
+        np.testing.assert_allclose([res["hit1"], res["hit3"], res["hit10"], res["mr"]], logged[1:5], rtol=2e-5, atol=2e-6)
+        # metrics kernel itself: exact rows of the reference in -> the reference's numbers out
+        res2 = summarize_ranks(m, torch.from_numpy(want).to(DEV), expectation, kg.entity_size)
+        np.testing.assert_allclose(res2["mrr"], fx["eval_%s_%d_mrr" % (ef, expectation)], rtol=1e-12)
+
+
+def test_dense_rank_kernel_matches_oracle():
+    from rnnlogic_b200.hotpath import dense_filtered_rank
+    from oracle import rnnlogic_oracle as O
+    g = torch.Generator().manual_seed(0)
+    Q, N = 37, 1000
+    logits = torch.randn(Q, N, generator=g).round(decimals=1)      # many ties
+    flag = torch.rand(Q, N, generator=g) > 0.1
+    mask = torch.rand(Q, N, generator=g) > 0.3
+    t = torch.randint(N, (Q,), generator=g)
+    want = O.filtered_rank(logits, flag, mask, t)
+    got = dense_filtered_rank(logits.cuda(), flag.cuda(), mask.cuda(), t.cuda()).cpu().numpy()
+    assert np.array_equal(got, want)
