@@ -63,7 +63,7 @@ def test_all_rules_of_head_vs_oracle(ds, skip_empty, bits):
 
 
 def test_overflow_falls_back_to_64bit():
-    """Complete bipartite-ish graph: counts exceed 2^32 after 7 hops; int64 result must match the
+    """Complete bipartite-ish graph: counts exceed 2^32 after 8 hops; int64 result must match the
     oracle bit for bit (and wrap like int64 beyond 2^63)."""
     from rnnlogic_b200 import KnowledgeGraph
     from oracle import rnnlogic_oracle as O
@@ -72,12 +72,12 @@ def test_overflow_falls_back_to_64bit():
     kg = KnowledgeGraph(entity_size=N, relation_size=2, train=tri)
     okg = O.OracleKG(N, 2, tri, np.zeros((0, 3), np.int64), np.zeros((0, 3), np.int64))
     h = torch.arange(5)
-    for L in (6, 7, 13):
+    for L in (6, 8, 13):
         body = [0] * L
         got = kg.grounding(h.cuda(), 1, body, None).cpu().numpy()
         want = okg.grounding(h.numpy(), 1, body, None)
         assert np.array_equal(got, want), L
-        if L == 7:
+        if L == 8:
             assert want.max() > 2 ** 32
 
 
