@@ -1,0 +1,346 @@
+#!/usr/bin/env python
+"""bench.py -- rule-grounded queries/sec on the FB15k-237-shaped synthetic workload.
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference]
+    torchrun --nnodes=1 --nproc-per-node N ... bench.py --gpus N ...
+
+A step = one pass of the hot path (ground every rule of the head -> rule-weight aggregation ->
+log(softmax+1e-8) CE -> backward into rule weights/bias -> Adam) over ``--batches`` reference
+batches (single-relation groups of <= 32 train queries, src/data.py:186-196) per GPU.  Batches
+are sharded over ranks (KG + rules replicated, one flat gradient all-reduce per step): weak
+scaling.  ``value`` is timed with the step's queries already in HBM; ``e2e`` goes through the
+public fused API from HOST lists (pack + H2D + kernels + D2H of the losses) every step.
+``--impl reference`` times the CPU oracle port of the reference path (oracle/) on host cores."""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+import torch
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+METRIC = "rule_grounded_train_queries_per_sec"
+UNIT = "queries/s"
+B = 32
+
+
+def build_workload(seed=237, scale=1.0):
+    from rnnlogic_b200 import synth
+    shape = synth.load_shape("fb15k237")
+    N, R, train, valid, test = synth.synthetic_kg(shape, scale=scale)
+    rules = synth.synthetic_rules(shape)
+    return shape, N, R, train, valid, test, rules
+
+
+def make_batches(train, R, seed):
+    """Reference batching (data.py:186-196) with numpy: group by relation, shuffle, cut into <= 32."""
+    rng = np.random.default_rng(seed)
+    batches = []
+    order = np.argsort(train[:, 1], kind="stable")
+    tr = train[order]
+    bounds = np.searchsorted(tr[:, 1], np.arange(R + 1))
+    for r in range(R):
+        grp = tr[bounds[r]:bounds[r + 1]]
+        grp = grp[rng.permutation(grp.shape[0])]
+        for k in range(0, grp.shape[0], B):
+            batches.append(grp[k:k + B])
+    perm = rng.permutation(len(batches))
+    return [batches[i] for i in perm]
+
+
+class ClockSampler:
+    QUERY = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,"
+             "clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+             "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index=0):
+        self.index, self.proc, self.lines = index, None, []
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.index), "--query-gpu=" + self.QUERY,
+                                          "--format=csv,noheader,nounits", "-lms", "100"],
+                                         stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.thread = threading.Thread(target=self._read, daemon=True)
+            self.thread.start()
+        except OSError:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.lines.append(line.strip())
+
+    def stop(self):
+        if self.proc is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=5)
+        except Exception:
+            self.proc.kill()
+        sm, mx, reasons = [], [], set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for ln in self.lines:
+            f = [x.strip() for x in ln.split(",")]
+            if len(f) < 9:
+                continue
+            try:
+                sm.append(float(f[1]))
+                mx.append(float(f[2]))
+            except ValueError:
+                continue
+            for nm, v in zip(names, f[5:9]):
+                if v.lower().startswith("active"):
+                    reasons.add(nm)
+        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": float(max(mx)) if mx else None,
+                "samples": len(sm), "reasons": sorted(reasons)}
+
+
+def cpu_reference_run(N, R, train, valid, test, rules, batches, steps, warmup, budget_s=20.0):
+    """Oracle port of the reference Predictor train step on host cores (bounded sample)."""
+    from oracle import rnnlogic_oracle as O
+    torch.set_num_threads(os.cpu_count() or 1)
+    kg = O.OracleKG(N, R, train, valid, test)
+    table = O.relation2rules(O.parse_rules([[h] + list(b) for h, b in rules]), R)
+    g = torch.Generator().manual_seed(0)
+    w = (torch.randn(len(rules), generator=g) * 0.1).requires_grad_()
+    bias = torch.zeros(N, requires_grad=True)
+    opt = torch.optim.Adam([w, bias], lr=0.005)
+    times, nq = [], 0
+
+    def one(batch):
+        data = [tuple(int(v) for v in row) for row in batch]
+        all_h, all_r, all_t, target, etr = O.train_batch(kg, data)
+        q = int(all_r[0])
+        score, mask = O.predictor_forward(kg, table[q], w, bias, all_h, etr.numpy(), q)
+        loss = O.ce_loss(score, mask, O.smoothed_target(target, all_t, 0.2))
+        opt.zero_grad()
+        loss.backward()
+        opt.step()
+        return len(data)
+
+    i = 0
+    for _ in range(warmup):
+        one(batches[i % len(batches)])
+        i += 1
+    t_all = time.perf_counter()
+    for _ in range(steps):
+        t0 = time.perf_counter()
+        nq += one(batches[i % len(batches)])
+        i += 1
+        times.append(time.perf_counter() - t0)
+        if time.perf_counter() - t_all > budget_s and len(times) >= 1:
+            break
+    total = sum(times)
+    return {"value": nq / total, "unit": UNIT, "cores": torch.get_num_threads(), "kind": "port",
+            "sample": "%d train batches of <=32 queries (%d queries), oracle port: C grounding per rule (1 thread) + "
+                      "torch-CPU aggregation/CE/backward/Adam (%d threads)" % (len(times), nq, torch.get_num_threads()),
+            "steps_done": len(times), "ms_per_step": 1e3 * total / len(times)}
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--warmup", type=int, default=5)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--batches", type=int, default=64, help="reference batches (of <=32 queries) per step per GPU")
+    ap.add_argument("--no-skip-empty", action="store_true", help="compute sub-tries of all-zero frontiers too")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--mode", default="train", choices=["train", "eval"])
+    args = ap.parse_args()
+    if args.warmup < 3:
+        args.warmup = 3
+
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+
+    shape, N, R, train, valid, test, rules = build_workload()
+    batches = make_batches(train, R, seed=1)
+    workload = ("FB15k-237-shape synthetic KG (N=%d, R=%d, E=%d train triples incl. inverses), %d synthetic rules "
+                "of the reference rule file's shape (L<=3), Predictor(bias) train step, B=32 per batch, %d batches/step/GPU"
+                % (N, R, train.shape[0], len(rules), args.batches))
+
+    if args.impl == "reference":
+        if rank != 0:
+            return
+        res = cpu_reference_run(N, R, train, valid, test, rules, batches, args.steps, args.warmup, budget_s=120.0)
+        line = {"impl": "reference", "metric": METRIC, "value": res["value"], "unit": UNIT, "n_gpus": args.gpus,
+                "steps": res["steps_done"], "warmup": args.warmup, "ms_per_step": res["ms_per_step"],
+                "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "int64/f32",
+                "data": "synthetic", "config": {"workload": workload.replace("%d batches/step/GPU" % args.batches, "1 batch/step")},
+                "cpu_baseline": {k: res[k] for k in ("value", "unit", "cores", "kind", "sample")},
+                "e2e": {"value": res["value"], "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+                "gpu_launches": 0}
+        print(json.dumps(line))
+        return
+
+    assert torch.cuda.is_available(), "bench.py needs a CUDA device (no CPU fallback)"
+    from rnnlogic_b200 import KnowledgeGraph, _lib
+    from rnnlogic_b200.predictors import Predictor
+    from rnnlogic_b200 import comm
+    dev = torch.device("cuda", local_rank)
+    torch.cuda.set_device(dev)
+    if world > 1:
+        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        comm.init_process_group("nccl", init_method="env://")
+
+    kg = KnowledgeGraph(entity_size=N, relation_size=R, train=train, valid=valid, test=test)
+    model = Predictor(kg, entity_feature="bias")
+    model.skip_empty = not args.no_skip_empty
+    model.set_rules([[h] + list(b) for h, b in rules])
+    g = torch.Generator().manual_seed(0)
+    with torch.no_grad():
+        model.rule_weights.copy_(torch.randn(model.num_rules, generator=g) * 0.1)
+    model = model.cuda(dev)
+    opt = torch.optim.Adam(model.parameters(), lr=0.005)
+    sk = model._driver(dev)
+    cr = model.compiled
+
+    my = batches[rank::world]
+    per = args.batches
+    n_steps = args.warmup + args.steps
+    step_batches = [[my[(s * per + j) % len(my)] for j in range(per)] for s in range(n_steps)]
+    step_lists = [[[tuple(x) for x in b.tolist()] for b in sb] for sb in step_batches]
+    queries_per_step = [sum(len(b) for b in sb) for sb in step_batches]
+
+    def allreduce_and_step(gw, gb):
+        if world > 1:
+            flat = torch.cat([gw, gb])
+            comm.all_reduce_sum_(flat)
+            flat /= world
+            gw, gb = flat[:gw.numel()], flat[gw.numel():]
+        model.rule_weights.grad, model.bias.grad = gw, gb
+        opt.step()
+
+    # ---------------- device-resident timing (`value`) ----------------
+    slots = [sk.gr.make_slots_host(sl, with_etr=True) for sl in step_lists]       # inputs now in HBM
+    torch.cuda.synchronize()
+    if world > 1:
+        torch.distributed.barrier()
+    for s in range(args.warmup):
+        loss, tsum, _, gw, gb = model.step_on_slots(sk, slots[s], 0.2, 1.0 / per)
+        allreduce_and_step(gw, gb)
+        slots[s].arena = None
+    torch.cuda.synchronize()
+    assert int(sum(int(slots[s].overflow.item()) for s in range(args.warmup))) == 0, "32-bit count overflow in warmup"
+    clocks = ClockSampler(local_rank)
+    if rank == 0:
+        clocks.start()
+    if world > 1:
+        torch.distributed.barrier()
+    torch.cuda.synchronize()
+    launches0 = _lib.lib().rl_launch_count()
+    sk.gr.level_events = []
+    ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    ev0.record()
+    losses = []
+    for s in range(args.warmup, n_steps):
+        loss, tsum, _, gw, gb = model.step_on_slots(sk, slots[s], 0.2, 1.0 / per)
+        allreduce_and_step(gw, gb)
+        slots[s].arena = None          # stream-ordered reuse by the caching allocator
+        losses.append(loss)
+    ev1.record()
+    torch.cuda.synchronize()
+    if world > 1:
+        torch.distributed.barrier()
+    elapsed_ms = ev0.elapsed_time(ev1)
+    launches = _lib.lib().rl_launch_count() - launches0
+    level_events, sk.gr.level_events = sk.gr.level_events, None
+    ovf = sum(int(slots[s].overflow.item()) for s in range(args.warmup, n_steps))
+    assert ovf == 0, "32-bit count overflow inside the timed region (rerun needed in 64-bit)"
+    assert all(torch.isfinite(l).all().item() for l in losses)
+    clk = clocks.stop() if rank == 0 else None
+    t = torch.tensor([elapsed_ms], dtype=torch.float64, device=dev)
+    if world > 1:
+        torch.distributed.all_reduce(t, op=torch.distributed.ReduceOp.MAX)
+    elapsed_ms = float(t.item())
+    q_timed = sum(queries_per_step[args.warmup:])
+    qt = torch.tensor([q_timed], dtype=torch.float64, device=dev)
+    if world > 1:
+        torch.distributed.all_reduce(qt)
+    value = float(qt.item()) / (elapsed_ms / 1e3)
+
+    # roofline of the dominant kernel (k_expand): algorithmic bytes of SURVEY 8d per launch
+    exp_ms = {}
+    for depth, e0, e1 in level_events:
+        exp_ms[depth] = exp_ms.get(depth, 0.0) + e0.elapsed_time(e1)
+    heads_timed = np.concatenate([slots[s].heads for s in range(args.warmup, n_steps)])
+    alg_bytes = float(cr.head_ground_bytes[heads_timed].sum())
+    n_exp_launch = len(level_events)
+    exp_total_ms = sum(exp_ms.values())
+    peaks = {}
+    try:
+        with open(os.path.join(ROOT, "MEASURED_PEAKS.json")) as f:
+            peaks = json.load(f)
+    except OSError:
+        pass
+    peak = float(peaks.get("hbm_gbs", 6650.0))
+    achieved = alg_bytes / (exp_total_ms / 1e3) / 1e9 if exp_total_ms > 0 else 0.0
+    roofline = {"bound": "hbm", "kernel": "k_expand (frontier expansion, all depths)", "achieved": achieved,
+                "peak": peak, "peak_source": "measured" if "hbm_gbs" in peaks else "fallback", "unit": "GB/s",
+                "frac": achieved / peak, "traffic": None,
+                "algorithmic_bytes_per_launch": alg_bytes / max(1, n_exp_launch),
+                "avg_launch_ms": exp_total_ms / max(1, n_exp_launch), "launches": n_exp_launch,
+                "ms_by_depth": {str(k): v for k, v in sorted(exp_ms.items())},
+                "share_of_step": exp_total_ms / (ev0.elapsed_time(ev1)),
+                "skip_empty": bool(model.skip_empty)}
+
+    # ---------------- end-to-end through the public fused API (host lists in, losses out) --------
+    torch.cuda.synchronize()
+    if world > 1:
+        torch.distributed.barrier()
+    h2d = d2h = 0
+    for s in range(args.warmup):
+        opt.zero_grad(set_to_none=True)
+        model.fused_train_step(step_lists[s], 0.2, grad_scale=1.0 / per)
+        allreduce_and_step(model.rule_weights.grad, model.bias.grad)
+    torch.cuda.synchronize()
+    if world > 1:
+        torch.distributed.barrier()
+    t0 = time.perf_counter()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for s in range(args.warmup, n_steps):
+        opt.zero_grad(set_to_none=True)
+        loss, tsum = model.fused_train_step(step_lists[s], 0.2, grad_scale=1.0 / per)
+        h2d += model.last_h2d_bytes + 8 * (4 * len(step_lists[s]) + 1)
+        d2h += model.last_d2h_bytes
+        allreduce_and_step(model.rule_weights.grad, model.bias.grad)
+    e1.record()
+    torch.cuda.synchronize()
+    e2e_ms = e0.elapsed_time(e1)
+    te = torch.tensor([e2e_ms], dtype=torch.float64, device=dev)
+    if world > 1:
+        torch.distributed.all_reduce(te, op=torch.distributed.ReduceOp.MAX)
+    e2e_value = float(qt.item()) / (float(te.item()) / 1e3)
+
+    if rank != 0:
+        return
+    line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
+            "ms_per_step": elapsed_ms / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+            "dtype": "u32/f32", "data": "synthetic",
+            "config": {"workload": workload, "queries_per_step_per_gpu": int(np.mean(queries_per_step)),
+                       "l2_policy": "per-step working set (frontier arena %.1f GB) is larger than the 126 MB L2"
+                                    % (float(cr.head_rows[heads_timed].sum()) * 128 / args.steps / 1e9),
+                       "parallelism": "dp%d (queries sharded, KG replicated)" % world,
+                       "skip_empty": bool(model.skip_empty)},
+            "roofline": roofline,
+            "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d // args.steps,
+                    "d2h_bytes_per_step": d2h // args.steps},
+            "gpu_launches": int(launches), "clocks": clk}
+    if world == 1 and not args.no_cpu_baseline:
+        res = cpu_reference_run(N, R, train, valid, test, rules, batches, 1000, 1, budget_s=15.0)
+        line["cpu_baseline"] = {k: res[k] for k in ("value", "unit", "cores", "kind", "sample")}
+    print(json.dumps(line))
+
+
+if __name__ == "__main__":
+    main()

@@ -108,6 +108,8 @@ typedef struct rl_answers {
 
 int rl_abi_version(void);
 const char *rl_last_error(void);
+/* Kernels enqueued by this library since it was loaded (per process). */
+long long rl_launch_count(void);
 /* Number of visible CUDA devices (>= 1) or RL_ERR_NO_DEVICE. */
 int rl_device_count(void);
 

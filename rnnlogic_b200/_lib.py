@@ -72,6 +72,7 @@ _PROTOS = {
     "rl_abi_version": (C.c_int, []),
     "rl_last_error": (C.c_char_p, []),
     "rl_device_count": (C.c_int, []),
+    "rl_launch_count": (C.c_longlong, []),
     "rl_prepare_slots": (C.c_int, [C.POINTER(RlGraph), C.c_int32, vp, vp, vp, vp, vp, vp, vp, vp, vp, vp]),
     "rl_expand_level": (C.c_int, [C.POINTER(RlGraph), C.POINTER(RlRules), C.POINTER(RlSlots), C.c_int32,
                                   C.c_int32, C.c_int32, vp, vp, vp, C.c_int32, vp]),

@@ -17,6 +17,7 @@
 #define SM_ROWS_PER_BLOCK 512   // entity rows per block in the softmax / rank sweeps
 
 static thread_local char g_err[512] = "";
+static long long g_launches = 0;   // kernels enqueued through this library (bench.py: gpu_launches)
 
 static int fail(int code, const char *what, cudaError_t e = cudaSuccess)
 {
@@ -29,6 +30,7 @@ static int fail(int code, const char *what, cudaError_t e = cudaSuccess)
     do {                                                               \
         cudaError_t e_ = cudaGetLastError();                           \
         if (e_ != cudaSuccess) return fail(RL_ERR_CUDA, name, e_);     \
+        ++g_launches;                                                  \
     } while (0)
 
 // ------------------------------------------------------------------------------------------
@@ -696,6 +698,7 @@ extern "C" {
 
 int rl_abi_version(void) { return RL_ABI_VERSION; }
 const char *rl_last_error(void) { return g_err; }
+long long rl_launch_count(void) { return g_launches; }
 
 int rl_device_count(void)
 {

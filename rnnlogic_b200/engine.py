@@ -72,6 +72,7 @@ class Grounder:
         self.dr = compiled.device_rules(self.device)
         self.skip_empty = bool(skip_empty)
         self.force_bits: Optional[int] = None
+        self.level_events = None      # bench.py: list collecting (depth, start, end) CUDA events
 
     def make_slots(self, heads: Sequence[int], sizes: Sequence[int], all_h, all_t=None, etr=None) -> Slots:
         """heads[i] / sizes[i]: head relation and number of queries of the i-th single-relation
@@ -124,9 +125,15 @@ class Grounder:
             gc = int(lc[:, depth - 1].max())
             if gc == 0:
                 continue
+            if self.level_events is not None:
+                e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                e0.record()
             _lib.check(L.rl_expand_level(self.dg.ref(), self.dr.ref(), sl.ref(), depth, gc, bits,
                                          sl.arena.data_ptr(), sl.node_nz.data_ptr(), sl.overflow.data_ptr(),
                                          int(self.skip_empty), _stream()), "rl_expand_level")
+            if self.level_events is not None:
+                e1.record()
+                self.level_events.append((depth, e0, e1))
 
     def ground(self, sl: Slots, check_overflow: bool = True) -> Slots:
         """Run all depths.  Counts are kept in 32-bit rows; if any count does not fit (host sync on

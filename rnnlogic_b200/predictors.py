@@ -167,37 +167,47 @@ def _group_mask_sum(sl, nzmask, ng):
     return torch.zeros(ng, dtype=torch.float32, device=nzmask.device).index_add_(0, gid, per_slot)
 
 
+def _predictor_step_on_slots(self, sk, sl, smoothing, grad_scale=1.0, bits=32):
+    """Enqueue ground -> aggregate -> CE -> backward for prepared slots (no host sync).
+    Returns the device tensors (loss[ng], tsum[ng], mask_sum[ng] | None, grad_w, grad_b)."""
+    device = sk.device
+    use_bias = self.entity_feature == "bias"
+    gptr, ng = _group_ptr(sl, device)
+    sk.gr._run(sl, bits)
+    Z, nzmask = sk.predictor_scores(sl, self.rule_weights.detach(), self.bias.detach() if use_bias else None,
+                                    not use_bias)
+    loss, tsum, G = sk.softmax_ce(sl, Z, nzmask, smoothing, not use_bias, gptr, ng, want_grad=True)
+    gw = torch.zeros_like(self.rule_weights)
+    gb = torch.zeros_like(self.bias) if use_bias else None
+    scale = None
+    if grad_scale != 1.0:
+        scale = torch.full((sl.S,), float(grad_scale), dtype=torch.float32, device=device)
+    sk.predictor_backward(sl, G, scale, gw, gb)
+    msum = None if use_bias else _group_mask_sum(sl, nzmask, ng)
+    return loss, tsum, msum, gw, gb
+
+
 def _predictor_fused_train(self, batches, smoothing, grad_scale=1.0):
     """One fused step over a list of single-relation train batches (trainer.py:68-93 for each):
     ground -> aggregate -> log(softmax+1e-8) CE -> backward.  Gradients of ``grad_scale * sum of
-    the batch losses`` are ACCUMULATED into .grad.  Returns (loss[n_batches], target_sum[n_batches],
-    candidate flag) as a host float tensor -- one device->host read per step."""
+    the batch losses`` are ACCUMULATED into .grad.  Returns (loss[n_batches], target_sum[n_batches])
+    as host float tensors -- one device->host read per step."""
     device = self.rule_weights.device
     sk = self._driver(device)
     use_bias = self.entity_feature == "bias"
     sl = sk.gr.make_slots_host(batches, with_etr=True)
-    gptr, ng = _group_ptr(sl, device)
-    for attempt in (0, 1):
-        sk.gr._run(sl, sk.gr.force_bits or (32 if attempt == 0 else 64))
-        Z, nzmask = sk.predictor_scores(sl, self.rule_weights.detach(), self.bias.detach() if use_bias else None,
-                                        not use_bias)
-        loss, tsum, G = sk.softmax_ce(sl, Z, nzmask, smoothing, not use_bias, gptr, ng, want_grad=True)
-        gw = torch.zeros_like(self.rule_weights)
-        gb = torch.zeros_like(self.bias) if use_bias else None
-        scale = None
-        if grad_scale != 1.0:
-            scale = torch.full((sl.S,), float(grad_scale), dtype=torch.float32, device=device)
-        sk.predictor_backward(sl, G, scale, gw, gb)
-        parts = [loss, tsum]
-        if not use_bias:
-            parts.append(_group_mask_sum(sl, nzmask, ng))
+    ng = len(batches)
+    for bits in ((sk.gr.force_bits,) if sk.gr.force_bits else (32, 64)):
+        loss, tsum, msum, gw, gb = _predictor_step_on_slots(self, sk, sl, smoothing, grad_scale, bits)
+        parts = [loss, tsum] + ([msum] if msum is not None else [])
         host = torch.cat(parts + [sl.overflow.float()]).cpu()            # the step's one sync
-        if host[-1].item() == 0 or sl.count_bits == 64:
+        if host[-1].item() == 0 or bits == 64:
             break
     for p, g in ((self.rule_weights, gw), (self.bias if use_bias else None, gb)):
         if p is not None:
             p.grad = g if p.grad is None else p.grad.add_(g)
     self.last_h2d_bytes = sl.h2d_bytes
+    self.last_d2h_bytes = int(host.numel() * 4)
     self.last_mask_sum = None if use_bias else host[2 * ng:3 * ng].tolist()
     return host[:ng], host[ng:2 * ng]
 
@@ -226,4 +236,5 @@ def _valid_lanes(sl, LH):
 
 
 Predictor.fused_train_step = _predictor_fused_train
+Predictor.step_on_slots = _predictor_step_on_slots
 Predictor.fused_rank = _predictor_fused_rank

@@ -1,0 +1,139 @@
+"""Synthetic knowledge graphs and rule sets of the shapes BASELINE.json names (there is no
+network and the reference's FB15k-237 / WN18RR train files are missing).
+
+``shapes/*.json`` hold only aggregate statistics of the reference's inputs (sizes, per-relation
+counts, per-head rule-length and trie-depth histograms) made by scripts/make_shapes.py."""
+from __future__ import annotations
+
+import json
+import os
+from typing import List, Tuple
+
+import numpy as np
+
+_SHAPES = os.path.join(os.path.dirname(os.path.abspath(__file__)), "shapes")
+
+
+def load_shape(name: str) -> dict:
+    with open(os.path.join(_SHAPES, name + ".json")) as f:
+        return json.load(f)
+
+
+def _draw_triples(rng, n_target, half, N, rw, ew, perm, taken: set):
+    """i.i.d. (r ~ rw, h,t ~ Zipf popularity), no self loops / duplicates."""
+    out = np.zeros((0, 3), dtype=np.int64)
+    keys = set()
+    cdf_r, cdf_e = np.cumsum(rw), np.cumsum(ew)
+    while out.shape[0] < n_target:
+        k = int((n_target - out.shape[0]) * 1.15) + 16
+        r = np.minimum(np.searchsorted(cdf_r, rng.random(k)), half - 1)
+        h = perm[np.minimum(np.searchsorted(cdf_e, rng.random(k)), N - 1)]
+        t = perm[np.minimum(np.searchsorted(cdf_e, rng.random(k)), N - 1)]
+        key = (r * N + h) * N + t
+        ok = h != t
+        _, first = np.unique(key, return_index=True)
+        uniq = np.zeros(k, dtype=bool)
+        uniq[first] = True
+        ok &= uniq
+        ok &= np.array([kk not in taken and kk not in keys for kk in key.tolist()], dtype=bool)
+        cand = np.stack([h, r, t], 1)[ok][: n_target - out.shape[0]]
+        keys.update(((cand[:, 1] * N + cand[:, 0]) * N + cand[:, 2]).tolist())
+        out = np.concatenate([out, cand], 0)
+    taken |= keys
+    return out
+
+
+def _with_inverses(base: np.ndarray, half: int) -> np.ndarray:
+    inv = np.stack([base[:, 2], base[:, 1] + half, base[:, 0]], 1)
+    return np.stack([base, inv], 1).reshape(-1, 3)
+
+
+def synthetic_kg(shape: dict, seed: int = None, scale: float = 1.0):
+    """(N, R, train, valid, test): calibrated recipe of SURVEY App. C.  Every base triple (h,r,t)
+    is followed by its inverse (t, r+R/2, h).  valid/test are synthetic too (same recipe)."""
+    seed = shape["seed"] if seed is None else seed
+    rng = np.random.default_rng(seed)
+    N, R = shape["num_entities"], shape["num_relations"]
+    half = R // 2
+    rw = np.asarray(shape["eval_count_per_base_relation"], dtype=np.float64) + 1.0
+    rw /= rw.sum()
+    ew = (np.arange(N) + 1.0) ** (-shape["entity_zipf"])
+    ew /= ew.sum()
+    perm = rng.permutation(N)
+    taken: set = set()
+    n_valid, n_test = shape["valid_triples"] // 2, shape["test_triples"] // 2
+    valid = _draw_triples(rng, int(n_valid * scale), half, N, rw, ew, perm, taken)
+    test = _draw_triples(rng, int(n_test * scale), half, N, rw, ew, perm, taken)
+    train = _draw_triples(rng, int(shape["train_base_triples"] * scale), half, N, rw, ew, perm, taken)
+    train = train[np.lexsort((train[:, 2], train[:, 1], train[:, 0]))]
+    return N, R, _with_inverses(train, half), _with_inverses(valid, half), _with_inverses(test, half)
+
+
+def synthetic_rules(shape: dict, seed: int = None) -> List[Tuple[int, List[int]]]:
+    """A rule list with the reference file's shape: per head the same number of rules of each body
+    length and (up to feasibility) the same number of distinct body prefixes per depth, body
+    relations drawn from the file's usage histogram."""
+    seed = shape["seed"] if seed is None else seed
+    rng = np.random.default_rng(seed + 1)
+    R, lmax = shape["num_relations"], shape["max_len"]
+    usage = np.asarray(shape["body_relation_usage"], dtype=np.float64) + 1.0
+    prob = usage / usage.sum()
+    rules: List[Tuple[int, List[int]]] = []
+    for q in range(R):
+        n_len = shape["rules_per_head_by_len"][q]
+        d_dep = shape["trie_nodes_per_head_by_depth"][q]
+        rules += [(q, [])] * n_len[0]
+        levels: List[List[tuple]] = []
+        for depth in range(1, lmax + 1):
+            want = d_dep[depth - 1]
+            nodes: List[tuple] = []
+            if want:
+                if depth == 1:
+                    rels = rng.choice(R, size=min(want, R), replace=False, p=prob)
+                    nodes = [(int(r),) for r in rels]
+                else:
+                    parents = levels[-1]
+                    seen = set()
+                    # parents that are not rule ends themselves need a child first
+                    need = max(0, len(parents) - n_len[depth - 1])
+                    order = list(rng.permutation(len(parents))[:need]) + list(rng.integers(len(parents), size=max(0, want - need)))
+                    for pi in order[:want]:
+                        for _try in range(8):
+                            cand = parents[int(pi)] + (int(rng.choice(R, p=prob)),)
+                            if cand not in seen:
+                                seen.add(cand)
+                                nodes.append(cand)
+                                break
+            levels.append(nodes)
+        for depth in range(1, lmax + 1):
+            nodes = levels[depth - 1]
+            n = n_len[depth]
+            if n == 0 or not nodes:
+                continue
+            has_child = set(c[:-1] for c in levels[depth]) if depth < lmax else set()
+            leaves = [p for p in nodes if p not in has_child]
+            inner = [p for p in nodes if p in has_child]
+            chosen = leaves[:n]
+            if len(chosen) < n:
+                extra = [inner[i] for i in rng.permutation(len(inner))[: n - len(chosen)]]
+                chosen += extra
+            while len(chosen) < n:                      # duplicates, as in the reference file
+                chosen.append(nodes[int(rng.integers(len(nodes)))])
+            rules += [(q, list(p)) for p in chosen]
+    order = rng.permutation(len(rules))
+    return [rules[i] for i in order]
+
+
+def scaled_kg(N=1_000_000, R=1000, E=20_000_000, seed=5):
+    """Config 5: relation sizes Zipf(1.0) over R/2 base relations, entity popularity Zipf(0.7)."""
+    shape = {"num_entities": N, "num_relations": R, "train_base_triples": E // 2, "entity_zipf": 0.7, "seed": seed,
+             "valid_triples": 2000, "test_triples": 2000,
+             "eval_count_per_base_relation": (1e6 / (np.arange(R // 2) + 1.0)).tolist()}
+    return synthetic_kg(shape)
+
+
+def scaled_rules(R=1000, n_rules=10_000, length=3, seed=5):
+    rng = np.random.default_rng(seed)
+    heads = rng.integers(R, size=n_rules)
+    bodies = rng.integers(R, size=(n_rules, length))
+    return [(int(h), [int(b) for b in body]) for h, body in zip(heads, bodies)]
