@@ -151,7 +151,7 @@ def main():
     ap.add_argument("--warmup", type=int, default=5)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--batches", type=int, default=64, help="reference batches (of <=32 queries) per step per GPU")
-    ap.add_argument("--no-skip-empty", action="store_true", help="compute sub-tries of all-zero frontiers too")
+    ap.add_argument("--dense", action="store_true", help="expand every row of every trie node (dense SpMM; roofline mode)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--mode", default="train", choices=["train", "eval"])
     args = ap.parse_args()
@@ -194,7 +194,7 @@ def main():
 
     kg = KnowledgeGraph(entity_size=N, relation_size=R, train=train, valid=valid, test=test)
     model = Predictor(kg, entity_feature="bias")
-    model.skip_empty = not args.no_skip_empty
+    model.force_dense = bool(args.dense)
     model.set_rules([[h] + list(b) for h, b in rules])
     g = torch.Generator().manual_seed(0)
     with torch.no_grad():
@@ -291,7 +291,7 @@ def main():
                 "avg_launch_ms": exp_total_ms / max(1, n_exp_launch), "launches": n_exp_launch,
                 "ms_by_depth": {str(k): v for k, v in sorted(exp_ms.items())},
                 "share_of_step": exp_total_ms / (ev0.elapsed_time(ev1)),
-                "skip_empty": bool(model.skip_empty)}
+                "dense_expansion": bool(model.force_dense)}
 
     # ---------------- end-to-end through the public fused API (host lists in, losses out) --------
     torch.cuda.synchronize()
@@ -331,7 +331,7 @@ def main():
                        "l2_policy": "per-step working set (frontier arena %.1f GB) is larger than the 126 MB L2"
                                     % (float(cr.head_rows[heads_timed].sum()) * 128 / args.steps / 1e9),
                        "parallelism": "dp%d (queries sharded, KG replicated)" % world,
-                       "skip_empty": bool(model.skip_empty)},
+                       "dense_expansion": bool(model.force_dense)},
             "roofline": roofline,
             "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d // args.steps,
                     "d2h_bytes_per_step": d2h // args.steps},

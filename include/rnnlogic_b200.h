@@ -45,7 +45,8 @@ enum rl_status {
  * rho is entity e" with one 8-byte load: word w = e>>5 holds {bits, rows before this word}.
  * ord_* keep the reference's per-relation edge order (train.txt order) so that an
  * `edges_to_remove` index (data.py:164-170) maps to its (head, tail). ent_* is the transpose:
- * for entity e the (relation, row-within-relation) pairs where e is a tail. */
+ * for entity e the (relation, row-within-relation) pairs where e is a tail.  fsrc_ptr/frow_start/
+ * fedge_dstrow/srank_tab are the same edges sorted by (relation, head, tail). */
 typedef struct rl_graph {
     int32_t num_entities, num_relations, rank_words, total_rows, num_edges;
     const int32_t *dst_ptr;    /* [R+1]            */
@@ -59,6 +60,11 @@ typedef struct rl_graph {
     const int32_t *ent_ptr;    /* [N+1]            */
     const int32_t *ent_rel;    /* [total_rows]     */
     const int32_t *ent_row;    /* [total_rows] row index local to the relation */
+    /* forward DCSR (by source), used to find which destination rows a frontier can reach */
+    const int32_t *fsrc_ptr;     /* [R+1] distinct heads per relation */
+    const int32_t *frow_start;   /* [total_srcs+1] out-edge offsets */
+    const int32_t *fedge_dstrow; /* [E] destination row (local to the relation) of each out-edge */
+    const uint32_t *srank_tab;   /* [R*rank_words*2] rank table over heads */
 } rl_graph;
 
 /* Compiled rule set, replaces Predictor.relation2rules (src/predictors.py:46-49, 186-189).
@@ -82,6 +88,9 @@ typedef struct rl_rules {
     const int32_t *term_rule;     /* [num_terms] */
     const int32_t *zr_ptr;        /* [R+1] */
     const int32_t *zr_rule;       /* [#empty-body rules] */
+    const int32_t *lvl_node_ptr;  /* [R*(max_len+1)] node range per (head, depth), like lvl_ptr */
+    const int32_t *node_chunk0;   /* [num_nodes] global id of the node's first chunk */
+    const int32_t *node_nterm;    /* [num_nodes] number of rules ending at the node */
 } rl_rules;
 
 /* One call's queries, cut into slots (<= 32 queries of one head relation each). */
@@ -93,8 +102,21 @@ typedef struct rl_slots {
     const int32_t *lane_eh;    /* [S*32] head of the removed edge, -1 = no removal */
     const int32_t *lane_et;    /* [S*32] tail of the removed edge */
     const int64_t *arena_off;  /* [S] first arena row of the slot */
-    const int32_t *nz_off;     /* [S] first node_nz entry of the slot */
+    const int32_t *nz_off;     /* [S] first node_cnt entry of the slot */
+    const int64_t *mask_off;   /* [S] first row_mask word of the slot (one word per chunk) */
 } rl_slots;
+
+/* Per-call frontier state (all DEVICE memory owned by the caller; row_mask, node_cnt, ent_active
+ * and overflow must be zero before depth 1).  A row of a node is meaningful iff its row_mask bit
+ * is set; rows outside the bitmap are never written nor read (exact: they are all-zero). */
+typedef struct rl_frontier {
+    int32_t count_bits;    /* 32: uint32 counts + overflow flag, 64: wraps like the reference's int64 */
+    void *arena;           /* [rows][32] counts */
+    uint32_t *row_mask;    /* one word per 32-row chunk */
+    int32_t *node_cnt;     /* valid rows per (slot, node) */
+    uint32_t *ent_active;  /* [S][rank_words] entities some rule end may reach */
+    int32_t *overflow;     /* set to 1 when a 32-bit count overflowed */
+} rl_frontier;
 
 /* Known-answer lists, replaces KnowledgeGraph.hr2o / hr2oo / hr2ooo (src/data.py:36-38,49-61,
  * 79-99): sorted keys r*N+h, CSR of de-duplicated tails.  Used for the smoothed multi-hot
@@ -122,30 +144,29 @@ int rl_prepare_slots(const rl_graph *g, int32_t num_slots, const int32_t *slot_h
                      int32_t *lane_eh, int32_t *lane_et, void *stream);
 
 /* Kernel (1): frontier expansion of one trie depth for every slot, replaces
- * KnowledgeGraph.propagate (src/data.py:149-173) for all rules of the head at once.
- * count_bits = 32 (uint32 rows, *overflow set to 1 when a count does not fit) or 64 (wraps
- * like the reference's int64).  grid_chunks = max over the call's slots of the number of
- * chunks at this depth.  node_nz[nz_off[s] + local node] is set to 1 when a node has a
- * non-zero count; with skip_empty != 0 the children of an all-zero node are not computed
- * (their rows are then undefined and every consumer honours node_nz). */
+ * KnowledgeGraph.propagate (src/data.py:149-173) for all rules of the head at once.  Two
+ * launches: k_symbolic (which destination rows can be non-zero -> row_mask) and k_numeric (the
+ * segmented pull SpMM over those rows, query edge removed on hops of the head relation).
+ * grid_nodes / grid_chunks = max over the call's slots of the number of trie nodes / chunks at
+ * this depth.  A node whose parent has more than dense_num/dense_den of its rows valid takes all
+ * its rows; force_dense != 0 does that for every node (plain dense SpMM: every algorithmic byte
+ * of SURVEY.md 8d is moved -- the mode the roofline figure is quoted on). */
 int rl_expand_level(const rl_graph *g, const rl_rules *r, const rl_slots *s, int32_t depth,
-                    int32_t grid_chunks, int32_t count_bits, void *arena, int32_t *node_nz,
-                    int32_t *overflow, int32_t skip_empty, void *stream);
+                    int32_t grid_nodes, int32_t grid_chunks, const rl_frontier *fr,
+                    int32_t dense_num, int32_t dense_den, int32_t force_dense, void *stream);
 
 /* Debug / API parity: dense int64[32][N] (lane-major, like the reference's [B,N]) counts of
  * one trie node of one slot; node < 0 selects the one-hot root (empty body).  Replaces the
  * return value of KnowledgeGraph.grounding (src/data.py:147). */
 int rl_node_counts_dense(const rl_graph *g, const rl_rules *r, const rl_slots *s, int32_t slot,
-                         int32_t node, int32_t count_bits, const void *arena,
-                         const int32_t *node_nz, int32_t skip_empty, int64_t *out, void *stream);
+                         int32_t node, const rl_frontier *fr, int64_t *out, void *stream);
 
 /* Kernel (2a): rule-weight aggregation, replaces the loop of Predictor.forward
  * (src/predictors.py:58-65,73-78).  Z[S][N][32] fp32 = sum_rule w_rule * fp32(count) (+ bias[e]
  * when bias != NULL).  nzmask[S][N]: bit b set <=> sum_rule count[e][b] != 0.  With
  * fill_neg_inf != 0 cells with a clear bit get -inf (entity_feature != 'bias'). */
 int rl_predictor_scores(const rl_graph *g, const rl_rules *r, const rl_slots *s,
-                        int32_t count_bits, const void *arena, const int32_t *node_nz,
-                        int32_t skip_empty, const float *rule_weights, const float *bias,
+                        const rl_frontier *fr, const float *rule_weights, const float *bias,
                         int32_t fill_neg_inf, float *Z, uint32_t *nzmask, void *stream);
 
 /* Kernel (2b): log(softmax + 1e-8) cross-entropy against the smoothed target, replaces
@@ -167,8 +188,7 @@ int rl_softmax_ce(const rl_graph *g, const rl_slots *s, const rl_answers *train_
  * src/predictors.py:64,74.  grad_w[num_rules] and grad_bias[N] (may be NULL) are ACCUMULATED
  * into (zero them first): grad_w[i] += sum_s slot_scale[s] * <G_s, fp32(count_i)>. */
 int rl_predictor_backward(const rl_graph *g, const rl_rules *r, const rl_slots *s,
-                          int32_t count_bits, const void *arena, const int32_t *node_nz,
-                          int32_t skip_empty, const float *G, const float *slot_scale,
+                          const rl_frontier *fr, const float *G, const float *slot_scale,
                           int32_t max_terms, float *grad_w, float *grad_bias, void *stream);
 
 /* Kernel (3): filtered rank bounds, replaces src/trainer.py:189-201.  LH[S*32][2] int64:

@@ -29,7 +29,8 @@ class RlGraph(C.Structure):
     _fields_ = [("num_entities", C.c_int32), ("num_relations", C.c_int32), ("rank_words", C.c_int32),
                 ("total_rows", C.c_int32), ("num_edges", C.c_int32),
                 ("dst_ptr", vp), ("row_dst", vp), ("row_start", vp), ("edge_src", vp), ("rank_tab", vp),
-                ("ord_ptr", vp), ("ord_h", vp), ("ord_t", vp), ("ent_ptr", vp), ("ent_rel", vp), ("ent_row", vp)]
+                ("ord_ptr", vp), ("ord_h", vp), ("ord_t", vp), ("ent_ptr", vp), ("ent_rel", vp), ("ent_row", vp),
+                ("fsrc_ptr", vp), ("frow_start", vp), ("fedge_dstrow", vp), ("srank_tab", vp)]
 
 
 class RlRules(C.Structure):
@@ -37,12 +38,18 @@ class RlRules(C.Structure):
                 ("num_chunks", C.c_int32), ("num_terms", C.c_int32),
                 ("node_rel", vp), ("node_parent", vp), ("node_row_off", vp), ("head_node_ptr", vp),
                 ("lvl_ptr", vp), ("chunk_node", vp), ("chunk_row0", vp), ("term_ptr", vp),
-                ("term_node", vp), ("term_rule", vp), ("zr_ptr", vp), ("zr_rule", vp)]
+                ("term_node", vp), ("term_rule", vp), ("zr_ptr", vp), ("zr_rule", vp),
+                ("lvl_node_ptr", vp), ("node_chunk0", vp), ("node_nterm", vp)]
 
 
 class RlSlots(C.Structure):
     _fields_ = [("num_slots", C.c_int32), ("slot_head", vp), ("lane_h", vp), ("lane_t", vp),
-                ("lane_eh", vp), ("lane_et", vp), ("arena_off", vp), ("nz_off", vp)]
+                ("lane_eh", vp), ("lane_et", vp), ("arena_off", vp), ("nz_off", vp), ("mask_off", vp)]
+
+
+class RlFrontier(C.Structure):
+    _fields_ = [("count_bits", C.c_int32), ("arena", vp), ("row_mask", vp), ("node_cnt", vp),
+                ("ent_active", vp), ("overflow", vp)]
 
 
 class RlAnswers(C.Structure):
@@ -75,16 +82,16 @@ _PROTOS = {
     "rl_launch_count": (C.c_longlong, []),
     "rl_prepare_slots": (C.c_int, [C.POINTER(RlGraph), C.c_int32, vp, vp, vp, vp, vp, vp, vp, vp, vp, vp]),
     "rl_expand_level": (C.c_int, [C.POINTER(RlGraph), C.POINTER(RlRules), C.POINTER(RlSlots), C.c_int32,
-                                  C.c_int32, C.c_int32, vp, vp, vp, C.c_int32, vp]),
+                                  C.c_int32, C.c_int32, C.POINTER(RlFrontier), C.c_int32, C.c_int32, C.c_int32, vp]),
     "rl_node_counts_dense": (C.c_int, [C.POINTER(RlGraph), C.POINTER(RlRules), C.POINTER(RlSlots), C.c_int32,
-                                       C.c_int32, C.c_int32, vp, vp, C.c_int32, vp, vp]),
-    "rl_predictor_scores": (C.c_int, [C.POINTER(RlGraph), C.POINTER(RlRules), C.POINTER(RlSlots), C.c_int32,
-                                      vp, vp, C.c_int32, vp, vp, C.c_int32, vp, vp, vp]),
+                                       C.c_int32, C.POINTER(RlFrontier), vp, vp]),
+    "rl_predictor_scores": (C.c_int, [C.POINTER(RlGraph), C.POINTER(RlRules), C.POINTER(RlSlots),
+                                      C.POINTER(RlFrontier), vp, vp, C.c_int32, vp, vp, vp]),
     "rl_softmax_blocks": (C.c_int, [C.c_int32]),
     "rl_softmax_ce": (C.c_int, [C.POINTER(RlGraph), C.POINTER(RlSlots), C.POINTER(RlAnswers), C.c_float,
                                 C.c_int32, vp, vp, C.c_int32, vp, vp, vp, vp, vp, vp, vp, vp]),
-    "rl_predictor_backward": (C.c_int, [C.POINTER(RlGraph), C.POINTER(RlRules), C.POINTER(RlSlots), C.c_int32,
-                                        vp, vp, C.c_int32, vp, vp, C.c_int32, vp, vp, vp]),
+    "rl_predictor_backward": (C.c_int, [C.POINTER(RlGraph), C.POINTER(RlRules), C.POINTER(RlSlots),
+                                        C.POINTER(RlFrontier), vp, vp, C.c_int32, vp, vp, vp]),
     "rl_filtered_rank": (C.c_int, [C.POINTER(RlGraph), C.POINTER(RlSlots), C.POINTER(RlAnswers), C.c_int32,
                                    vp, vp, vp, vp, vp]),
     "rl_filtered_rank_dense": (C.c_int, [C.c_int64, C.c_int64, vp, vp, vp, vp, vp, vp]),

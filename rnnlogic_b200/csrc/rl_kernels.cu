@@ -103,16 +103,102 @@ __global__ void k_prepare_slots(rl_graph g, int S, const int32_t *__restrict__ s
 }
 
 // ------------------------------------------------------------------------------------------
-// kernel (1): frontier expansion.  One warp = one chunk of <= 32 consecutive destination rows
-// of one trie node of one slot.  The chunk's in-edges are contiguous in edge_src, so they are
-// fetched 32 at a time with one coalesced load; each lane resolves the parent-frontier row of
-// "its" edge (8-byte rank-table load), then the warp pulls the 32 parent rows (128 B each,
-// all 32 loads in flight before the first add) and reduces them segment by segment.
+// kernel (1): frontier expansion, two launches per trie depth.
+//
+//  k_symbolic  one warp per (slot, trie node): decides WHICH destination rows of the node can be
+//              non-zero.  It walks the valid rows of the parent frontier (bitmap), looks each
+//              entity up in the relation's forward DCSR and ORs the reached destination rows into
+//              the node's row bitmap (one 32-bit word per 32-row chunk).  A parent with more than
+//              dense_num/dense_den of its rows valid switches the node to "all rows" (plain SpMM).
+//  k_numeric   one warp per chunk of <= 32 destination rows: builds the compact list of in-edges
+//              of the chunk's valid rows (warp scan), fetches the sources 32 at a time (coalesced),
+//              resolves each source's parent-frontier row with one 8-byte rank-table load + one
+//              bitmap word, then pulls the parent rows (128 B each, lane = query, 8 loads in
+//              flight) and reduces them per destination row.  Rows outside the bitmap are never
+//              written or read.  The query's own edge is cut with an exact integer fix-up.
 // ------------------------------------------------------------------------------------------
+__device__ __forceinline__ int srank_row(const rl_graph &g, int rel, int e)
+{
+    const uint2 w = __ldg(reinterpret_cast<const uint2 *>(g.srank_tab) + (size_t)rel * g.rank_words + (e >> 5));
+    const uint32_t bit = 1u << (e & 31);
+    return (w.x & bit) ? (int)(w.y + __popc(w.x & (bit - 1))) : -1;
+}
+
+__device__ __forceinline__ void mark_out_edges(const rl_graph &g, int rho, int ent, uint32_t *cm)
+{
+    const int sr = srank_row(g, rho, ent);
+    if (sr < 0) return;
+    const int fb = g.fsrc_ptr[rho] + sr;
+    const int k1 = g.frow_start[fb + 1];
+    for (int k = g.frow_start[fb]; k < k1; ++k) {
+        const int dr = __ldg(g.fedge_dstrow + k);
+        atomicOr(cm + (dr >> 5), 1u << (dr & 31));
+    }
+}
+
+template <bool ROOT>
+__global__ void __launch_bounds__(WARPS_PER_BLOCK * 32)
+k_symbolic(rl_graph g, rl_rules r, rl_slots s, int depth, rl_frontier fr, int dense_num, int dense_den, int force_dense)
+{
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int slot = blockIdx.y;
+    const int q = s.slot_head[slot];
+    const int32_t *np = r.lvl_node_ptr + (size_t)q * (r.max_len + 1);
+    const int v = np[depth - 1] + blockIdx.x * WARPS_PER_BLOCK + warp;
+    if (v >= np[depth]) return;
+    const int rho = r.node_rel[v];
+    const int D = g.dst_ptr[rho + 1] - g.dst_ptr[rho];
+    const int nw = (D + 31) >> 5;
+    if (nw == 0) return;
+    const int hc0 = r.lvl_ptr[(size_t)q * (r.max_len + 1)];
+    uint32_t *mbase = fr.row_mask + (size_t)s.mask_off[slot];
+    uint32_t *cm = mbase + (r.node_chunk0[v] - hc0);
+    const int nzb = s.nz_off[slot] - r.head_node_ptr[q];
+    bool dense = force_dense != 0;
+    const uint32_t *pm = nullptr;
+    int rho_p = -1, Dp = 0;
+    if (!ROOT) {
+        const int p = r.node_parent[v];
+        const int cntp = fr.node_cnt[nzb + p];
+        if (!dense && cntp == 0) return;                       // empty parent => empty node
+        rho_p = r.node_rel[p];
+        Dp = g.dst_ptr[rho_p + 1] - g.dst_ptr[rho_p];
+        if ((long long)cntp * dense_den > (long long)Dp * dense_num) dense = true;
+        pm = mbase + (r.node_chunk0[p] - hc0);
+    }
+    if (dense) {
+        for (int w = lane; w < nw; w += 32)
+            cm[w] = (w == nw - 1 && (D & 31)) ? ((1u << (D & 31)) - 1u) : 0xffffffffu;
+        if (lane == 0) fr.node_cnt[nzb + v] = D;
+        return;
+    }
+    if (ROOT) {
+        const int h = s.lane_h[slot * RL_LANES + lane];
+        if (h >= 0) mark_out_edges(g, rho, h, cm);
+    } else {
+        const int nwp = (Dp + 31) >> 5;
+        const int pb = g.dst_ptr[rho_p];
+        for (int w0 = 0; w0 < nwp; w0 += 32) {
+            const int wi = w0 + lane;
+            uint32_t word = wi < nwp ? pm[wi] : 0u;
+            while (word) {
+                const int bit = __ffs(word) - 1;
+                word &= word - 1;
+                mark_out_edges(g, rho, __ldg(g.row_dst + pb + wi * 32 + bit), cm);
+            }
+        }
+    }
+    __syncwarp();
+    int c = 0;
+    for (int w = lane; w < nw; w += 32) c += __popc(__ldcg(cm + w));
+    c = warp_sumi(c);
+    if (lane == 0) fr.node_cnt[nzb + v] = c;
+}
+
+#define EDGE_GROUP 8
 template <typename CT, bool ROOT>
 __global__ void __launch_bounds__(WARPS_PER_BLOCK * 32)
-k_expand(rl_graph g, rl_rules r, rl_slots s, int depth, CT *__restrict__ arena,
-         int32_t *__restrict__ node_nz, int32_t *__restrict__ overflow, int skip_empty)
+k_numeric(rl_graph g, rl_rules r, rl_slots s, int depth, rl_frontier fr)
 {
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const int slot = blockIdx.y;
@@ -120,90 +206,120 @@ k_expand(rl_graph g, rl_rules r, rl_slots s, int depth, CT *__restrict__ arena,
     const int32_t *lp = r.lvl_ptr + (size_t)q * (r.max_len + 1);
     const int chunk = lp[depth - 1] + blockIdx.x * WARPS_PER_BLOCK + warp;
     if (chunk >= lp[depth]) return;
+    const int hc0 = lp[0];
+    const uint32_t *mbase = fr.row_mask + (size_t)s.mask_off[slot];
+    const uint32_t m = mbase[chunk - hc0];
+    if (m == 0u) return;
     const int v = r.chunk_node[chunk], row0 = r.chunk_row0[chunk];
     const int rho = r.node_rel[v];
-    const int nzb = s.nz_off[slot] - r.head_node_ptr[q];
     const size_t abase = (size_t)s.arena_off[slot];
+    CT *arena = reinterpret_cast<CT *>(fr.arena);
     const CT *__restrict__ X = nullptr;
+    const uint32_t *__restrict__ pm = nullptr;
     int prel = -1;
     if (!ROOT) {
         const int p = r.node_parent[v];
-        if (skip_empty && node_nz[nzb + p] == 0) return;
         prel = r.node_rel[p];
         X = arena + (abase + (size_t)r.node_row_off[p]) * RL_LANES;
+        pm = mbase + (r.node_chunk0[p] - hc0);
     }
     CT *__restrict__ Y = arena + (abase + (size_t)r.node_row_off[v] + row0) * RL_LANES;
     const int rbase = g.dst_ptr[rho] + row0;
     const int nr = min(32, g.dst_ptr[rho + 1] - rbase);
     const int my_rs = g.row_start[rbase + min(lane, nr)];
-    const int e_end = g.row_start[rbase + nr];
+    const int my_re = g.row_start[rbase + min(lane + 1, nr)];
     const int my_dst = lane < nr ? g.row_dst[rbase + lane] : -1;
+    const bool active = (m >> lane) & 1u;
+    const int deg = active ? my_re - my_rs : 0;
+    int P = deg;                                            // inclusive scan of deg over lanes
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+        const int t = __shfl_up_sync(FULL, P, o);
+        if (lane >= o) P += t;
+    }
+    const int T = __shfl_sync(FULL, P, 31);
+    const int my_first = P - deg;                            // position of my row's first edge in the list
     const int h = s.lane_h[slot * RL_LANES + lane];
     const bool masked = (rho == q);
     const int eh = masked ? s.lane_eh[slot * RL_LANES + lane] : -1;
     const int et = masked ? s.lane_et[slot * RL_LANES + lane] : -1;
+    if (r.node_nterm[v] > 0 && active)                       // candidate entities for the aggregation
+        atomicOr(fr.ent_active + (size_t)slot * g.rank_words + (my_dst >> 5), 1u << (my_dst & 31));
 
-    int cur = 0;                                         // row being accumulated
-    int row_end = (nr > 1) ? __shfl_sync(FULL, my_rs, 1) : e_end;
+    int cur = -1;
     unsigned long long acc = 0;
-    bool any = false, ovf = false;
-
+    bool ovf = false;
     auto flush = [&](int j) {
         const int d = __shfl_sync(FULL, my_dst, j);
-        if (eh >= 0 && et == d) {                        // data.py:164-170: drop the query's own edge
+        if (eh >= 0 && et == d) {                            // data.py:164-170: drop the query's own edge
             unsigned long long sub;
             if (ROOT) sub = (eh == h) ? 1ull : 0ull;
             else {
-                const int pr = rank_row(g, prel, eh);
+                int pr = rank_row(g, prel, eh);
+                if (pr >= 0 && !((pm[pr >> 5] >> (pr & 31)) & 1u)) pr = -1;
                 sub = pr >= 0 ? (unsigned long long)X[(size_t)pr * RL_LANES + lane] : 0ull;
             }
             acc -= sub;
         }
         if (sizeof(CT) == 4 && (acc >> 32)) ovf = true;
         Y[(size_t)j * RL_LANES + lane] = (CT)acc;
-        any |= (acc != 0);
         acc = 0;
     };
 
-    for (int base = __shfl_sync(FULL, my_rs, 0); base < e_end; base += 32) {
-        const int n = min(32, e_end - base);
-        const int src = lane < n ? __ldg(g.edge_src + base + lane) : -1;
-        CT vals[32];
-        if (ROOT) {
+    for (int base = 0; base < T; base += 32) {
+        const int n = min(32, T - base);
+        const int k = min(base + lane, T - 1);
+        int row = 0;                                         // #lanes with P <= k  (binary search over lanes)
 #pragma unroll
-            for (int k = 0; k < 32; ++k) vals[k] = (CT)((k < n) && (__shfl_sync(FULL, src, k) == h));
-        } else {
-            const int pr = src >= 0 ? rank_row(g, prel, src) : -1;
-#pragma unroll
-            for (int k = 0; k < 32; ++k) {
-                const int p = __shfl_sync(FULL, pr, k);
-                vals[k] = p >= 0 ? X[(size_t)p * RL_LANES + lane] : (CT)0;
-            }
+        for (int step = 16; step > 0; step >>= 1)
+            if (__shfl_sync(FULL, P, row + step - 1) <= k) row += step;
+        const int e = __shfl_sync(FULL, my_rs, row) + (k - __shfl_sync(FULL, my_first, row));
+        const int src = lane < n ? __ldg(g.edge_src + e) : -1;
+        int pr = -1;
+        if (!ROOT && src >= 0) {
+            pr = rank_row(g, prel, src);
+            if (pr >= 0 && !((pm[pr >> 5] >> (pr & 31)) & 1u)) pr = -1;
         }
+        for (int k0 = 0; k0 < n; k0 += EDGE_GROUP) {
+            CT vals[EDGE_GROUP];
+            int rws[EDGE_GROUP];
 #pragma unroll
-        for (int k = 0; k < 32; ++k) {
-            if (k < n) {
-                while (base + k >= row_end) {
-                    flush(cur);
-                    ++cur;
-                    row_end = (cur + 1 < nr) ? __shfl_sync(FULL, my_rs, cur + 1) : e_end;
+            for (int u = 0; u < EDGE_GROUP; ++u) {
+                const int kk = (k0 + u) & 31;
+                rws[u] = __shfl_sync(FULL, row, kk);
+                if (ROOT) {
+                    const int sv = __shfl_sync(FULL, src, kk);
+                    vals[u] = (CT)((k0 + u < n) && (sv == h));
+                } else {
+                    const int p = __shfl_sync(FULL, pr, kk);
+                    vals[u] = (k0 + u < n && p >= 0) ? X[(size_t)p * RL_LANES + lane] : (CT)0;
                 }
-                acc += (unsigned long long)vals[k];
+            }
+#pragma unroll
+            for (int u = 0; u < EDGE_GROUP; ++u) {
+                if (k0 + u < n) {
+                    if (rws[u] != cur) {
+                        if (cur >= 0) flush(cur);
+                        cur = rws[u];
+                    }
+                    acc += (unsigned long long)vals[u];
+                }
             }
         }
     }
-    while (cur < nr) {
-        flush(cur);
-        ++cur;
-    }
-    if (__any_sync(FULL, any) && lane == 0) node_nz[nzb + v] = 1;
-    if (__any_sync(FULL, ovf) && lane == 0) *overflow = 1;
+    if (cur >= 0) flush(cur);
+    if (__any_sync(FULL, ovf) && lane == 0) *fr.overflow = 1;
+}
+
+__device__ __forceinline__ bool row_valid(const rl_rules &r, const uint32_t *mbase, int hc0, int v, int row)
+{
+    return (mbase[r.node_chunk0[v] - hc0 + (row >> 5)] >> (row & 31)) & 1u;
 }
 
 // dense int64 [32][N] view of one node (debug / KnowledgeGraph.grounding return value)
 template <typename CT>
-__global__ void k_node_dense(rl_graph g, rl_rules r, rl_slots s, int slot, int node, const CT *__restrict__ arena,
-                             const int32_t *__restrict__ node_nz, int skip_empty, int64_t *__restrict__ out)
+__global__ void k_node_dense(rl_graph g, rl_rules r, rl_slots s, int slot, int node, rl_frontier fr,
+                             int64_t *__restrict__ out)
 {
     __shared__ long long tile[32][33];
     const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;     // 32 warps
@@ -214,9 +330,11 @@ __global__ void k_node_dense(rl_graph g, rl_rules r, rl_slots s, int slot, int n
         if (node < 0) c = (s.lane_h[slot * RL_LANES + lane] == e);
         else {
             const int q = s.slot_head[slot];
-            const bool live = !(skip_empty && node_nz[s.nz_off[slot] - r.head_node_ptr[q] + node] == 0);
-            const int row = live ? rank_row(g, r.node_rel[node], e) : -1;
-            if (row >= 0) c = (long long)arena[((size_t)s.arena_off[slot] + r.node_row_off[node] + row) * RL_LANES + lane];
+            const int hc0 = r.lvl_ptr[(size_t)q * (r.max_len + 1)];
+            const uint32_t *mbase = fr.row_mask + (size_t)s.mask_off[slot];
+            const int row = rank_row(g, r.node_rel[node], e);
+            if (row >= 0 && row_valid(r, mbase, hc0, node, row))
+                c = (long long)reinterpret_cast<const CT *>(fr.arena)[((size_t)s.arena_off[slot] + r.node_row_off[node] + row) * RL_LANES + lane];
         }
     }
     tile[w][lane] = c;                                            // [entity][lane]
@@ -226,66 +344,76 @@ __global__ void k_node_dense(rl_graph g, rl_rules r, rl_slots s, int slot, int n
 }
 
 // ------------------------------------------------------------------------------------------
-// kernel (2a): pull aggregation of the rule weights.  Warp = one entity row of one slot; it
-// walks the (relation, row) pairs in which the entity is a tail and, per pair, the rules of the
-// slot's head that end in that relation.
+// kernel (2a): pull aggregation of the rule weights.  One warp = 32 consecutive entities of one
+// slot.  Entities no rule end reaches (ent_active bit clear) only get their bias / -inf row; a
+// candidate entity walks the (relation, row) pairs in which it is a tail and, per pair, the rules
+// of the slot's head that end in that relation (deterministic order, fp64 accumulation).
 // ------------------------------------------------------------------------------------------
 template <typename CT>
 __global__ void __launch_bounds__(WARPS_PER_BLOCK * 32)
-k_predictor_scores(rl_graph g, rl_rules r, rl_slots s, const CT *__restrict__ arena,
-                   const int32_t *__restrict__ node_nz, int skip_empty, const float *__restrict__ w,
+k_predictor_scores(rl_graph g, rl_rules r, rl_slots s, rl_frontier fr, const float *__restrict__ w,
                    const float *__restrict__ bias, int fill_neg_inf, float *__restrict__ Z,
                    uint32_t *__restrict__ nzmask)
 {
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const int slot = blockIdx.y;
-    const int e = blockIdx.x * WARPS_PER_BLOCK + warp;
+    const int ew = blockIdx.x * WARPS_PER_BLOCK + warp;           // entity word
     const int N = g.num_entities, R = g.num_relations;
-    if (e >= N) return;
+    if (ew >= g.rank_words) return;
     const int q = s.slot_head[slot];
-    const int nzb = s.nz_off[slot] - r.head_node_ptr[q];
+    const int hc0 = r.lvl_ptr[(size_t)q * (r.max_len + 1)];
+    const uint32_t *mbase = fr.row_mask + (size_t)s.mask_off[slot];
     const size_t abase = (size_t)s.arena_off[slot];
+    const CT *arena = reinterpret_cast<const CT *>(fr.arena);
     const int32_t *tp = r.term_ptr + (size_t)q * R;
-    double acc = 0.0;
-    bool any = false;
-    const int p0 = g.ent_ptr[e], p1 = g.ent_ptr[e + 1];
-    for (int pb = p0; pb < p1; pb += 32) {
-        // lane-parallel fetch of up to 32 (relation,row) pairs and their rule ranges
-        const int pi = pb + lane;
-        int rel = -1, row = 0, t0 = 0, t1 = 0;
-        if (pi < p1) {
-            rel = g.ent_rel[pi];
-            row = g.ent_row[pi];
-            t0 = tp[rel];
-            t1 = tp[rel + 1];
-        }
-        const int npair = min(32, p1 - pb);
-        for (int k = 0; k < npair; ++k) {
-            const int a0 = __shfl_sync(FULL, t0, k), a1 = __shfl_sync(FULL, t1, k);
-            const int rw = __shfl_sync(FULL, row, k);
-            for (int t = a0; t < a1; ++t) {
-                const int v = __ldg(r.term_node + t);
-                if (skip_empty && node_nz[nzb + v] == 0) continue;
-                const CT c = arena[(abase + (size_t)r.node_row_off[v] + rw) * RL_LANES + lane];
-                if (c != 0) {
-                    acc += (double)(float)c * (double)__ldg(w + r.term_rule[t]);   // x.float() * w  (predictors.py:64)
-                    any = true;
+    const int h = s.lane_h[slot * RL_LANES + lane];
+    const int z0 = r.zr_ptr[q], z1 = r.zr_ptr[q + 1];
+    uint32_t act = fr.ent_active[(size_t)slot * g.rank_words + ew];
+    if (z1 > z0) act |= __reduce_or_sync(FULL, (h >= 0 && (h >> 5) == ew) ? (1u << (h & 31)) : 0u);
+    double zsum = 0.0;
+    if (z1 > z0) for (int t = z0; t < z1; ++t) zsum += (double)__ldg(w + r.zr_rule[t]);
+    const int e1 = min(32, N - ew * 32);
+    for (int i = 0; i < e1; ++i) {
+        const int e = ew * 32 + i;
+        double acc = 0.0;
+        bool any = false;
+        if ((act >> i) & 1u) {
+            const int p0 = g.ent_ptr[e], p1 = g.ent_ptr[e + 1];
+            for (int pb = p0; pb < p1; pb += 32) {
+                const int pi = pb + lane;
+                int row = 0, t0 = 0, t1 = 0;
+                if (pi < p1) {
+                    const int rel = g.ent_rel[pi];
+                    row = g.ent_row[pi];
+                    t0 = tp[rel];
+                    t1 = tp[rel + 1];
+                }
+                uint32_t have = __ballot_sync(FULL, t1 > t0);
+                while (have) {
+                    const int k = __ffs(have) - 1;
+                    have &= have - 1;
+                    const int a0 = __shfl_sync(FULL, t0, k), a1 = __shfl_sync(FULL, t1, k);
+                    const int rw = __shfl_sync(FULL, row, k);
+                    for (int t = a0; t < a1; ++t) {
+                        const int v = __ldg(r.term_node + t);
+                        if (!row_valid(r, mbase, hc0, v, rw)) continue;
+                        const CT c = arena[(abase + (size_t)r.node_row_off[v] + rw) * RL_LANES + lane];
+                        if (c != 0) {
+                            acc += (double)(float)c * (double)__ldg(w + r.term_rule[t]);   // x.float() * w (predictors.py:64)
+                            any = true;
+                        }
+                    }
                 }
             }
+            if (h == e && z1 > z0) { acc += zsum; any = true; }   // empty-body rules: count = one_hot(h)
         }
+        float z = (float)acc;
+        if (bias) z += bias[e];
+        if (fill_neg_inf && !any) z = -INFINITY;
+        Z[((size_t)slot * N + e) * RL_LANES + lane] = z;
+        const uint32_t bits = __ballot_sync(FULL, any);
+        if (lane == 0) nzmask[(size_t)slot * N + e] = bits;
     }
-    if (s.lane_h[slot * RL_LANES + lane] == e) {                  // empty-body rules: count = one_hot(h)
-        for (int t = r.zr_ptr[q]; t < r.zr_ptr[q + 1]; ++t) {
-            acc += (double)__ldg(w + r.zr_rule[t]);
-            any = true;
-        }
-    }
-    float z = (float)acc;
-    if (bias) z += bias[e];
-    if (fill_neg_inf && !any) z = -INFINITY;
-    Z[((size_t)slot * N + e) * RL_LANES + lane] = z;
-    const uint32_t bits = __ballot_sync(FULL, any);
-    if (lane == 0) nzmask[(size_t)slot * N + e] = bits;
 }
 
 // ------------------------------------------------------------------------------------------
@@ -480,8 +608,7 @@ k_grad_sparse(rl_graph g, rl_slots s, rl_answers ans, float smoothing, int use_m
 // ------------------------------------------------------------------------------------------
 template <typename CT>
 __global__ void __launch_bounds__(128)
-k_predictor_bwd_w(rl_graph g, rl_rules r, rl_slots s, const CT *__restrict__ arena,
-                  const int32_t *__restrict__ node_nz, int skip_empty, const float *__restrict__ G,
+k_predictor_bwd_w(rl_graph g, rl_rules r, rl_slots s, rl_frontier fr, const float *__restrict__ G,
                   const float *__restrict__ slot_scale, float *__restrict__ grad_w)
 {
     __shared__ double red[4];
@@ -501,14 +628,21 @@ k_predictor_bwd_w(rl_graph g, rl_rules r, rl_slots s, const CT *__restrict__ are
     const int t = r.term_ptr[(size_t)q * R] + blockIdx.x;
     if (t >= r.term_ptr[(size_t)(q + 1) * R]) return;
     const int v = r.term_node[t];
-    if (skip_empty && node_nz[s.nz_off[slot] - r.head_node_ptr[q] + v] == 0) return;
+    if (fr.node_cnt[s.nz_off[slot] - r.head_node_ptr[q] + v] == 0) return;
     const int rho = r.node_rel[v];
     const int rb = g.dst_ptr[rho], nrows = g.dst_ptr[rho + 1] - rb;
-    const CT *Xv = arena + ((size_t)s.arena_off[slot] + r.node_row_off[v]) * RL_LANES;
+    const int nw = (nrows + 31) >> 5;
+    const uint32_t *cm = fr.row_mask + (size_t)s.mask_off[slot] + (r.node_chunk0[v] - r.lvl_ptr[(size_t)q * (r.max_len + 1)]);
+    const CT *Xv = reinterpret_cast<const CT *>(fr.arena) + ((size_t)s.arena_off[slot] + r.node_row_off[v]) * RL_LANES;
     double acc = 0.0;
-    for (int j = warp; j < nrows; j += 4) {
-        const CT c = Xv[(size_t)j * RL_LANES + lane];
-        if (c != 0) acc += (double)(float)c * (double)Gs[(size_t)g.row_dst[rb + j] * RL_LANES + lane];
+    for (int wi = warp; wi < nw; wi += 4) {
+        uint32_t word = cm[wi];
+        while (word) {
+            const int j = wi * 32 + __ffs(word) - 1;
+            word &= word - 1;
+            const CT c = Xv[(size_t)j * RL_LANES + lane];
+            if (c != 0) acc += (double)(float)c * (double)Gs[(size_t)g.row_dst[rb + j] * RL_LANES + lane];
+        }
     }
     acc = warp_sum(acc);
     if (lane == 0) red[warp] = acc;
@@ -724,52 +858,63 @@ int rl_prepare_slots(const rl_graph *g, int32_t S, const int32_t *slot_head, con
     return RL_OK;
 }
 
-int rl_expand_level(const rl_graph *g, const rl_rules *r, const rl_slots *s, int32_t depth, int32_t grid_chunks,
-                    int32_t count_bits, void *arena, int32_t *node_nz, int32_t *overflow, int32_t skip_empty,
-                    void *stream)
+static int check_frontier(const rl_frontier *fr, const char *who)
 {
-    if (!g || !r || !s || !arena || !node_nz || !overflow) return fail(RL_ERR_ARG, "rl_expand_level: null argument");
+    if (!fr || !fr->arena || !fr->row_mask || !fr->node_cnt || !fr->ent_active || !fr->overflow) return fail(RL_ERR_ARG, who);
+    if (fr->count_bits != 32 && fr->count_bits != 64) return fail(RL_ERR_ARG, "count_bits must be 32 or 64");
+    return RL_OK;
+}
+
+int rl_expand_level(const rl_graph *g, const rl_rules *r, const rl_slots *s, int32_t depth, int32_t grid_nodes,
+                    int32_t grid_chunks, const rl_frontier *fr, int32_t dense_num, int32_t dense_den,
+                    int32_t force_dense, void *stream)
+{
+    if (!g || !r || !s) return fail(RL_ERR_ARG, "rl_expand_level: null argument");
+    if (check_frontier(fr, "rl_expand_level: incomplete rl_frontier") != RL_OK) return RL_ERR_ARG;
     if (depth < 1 || depth > r->max_len) return fail(RL_ERR_ARG, "rl_expand_level: depth out of range");
-    if (count_bits != 32 && count_bits != 64) return fail(RL_ERR_ARG, "rl_expand_level: count_bits must be 32 or 64");
-    if (grid_chunks <= 0 || s->num_slots <= 0) return RL_OK;
-    dim3 grid((grid_chunks + WARPS_PER_BLOCK - 1) / WARPS_PER_BLOCK, s->num_slots);
+    if (dense_den <= 0 || dense_num < 0) return fail(RL_ERR_ARG, "rl_expand_level: bad dense threshold");
+    if (grid_chunks <= 0 || grid_nodes <= 0 || s->num_slots <= 0) return RL_OK;
     cudaStream_t st = (cudaStream_t)stream;
-    if (count_bits == 32) {
-        if (depth == 1) k_expand<uint32_t, true><<<grid, WARPS_PER_BLOCK * 32, 0, st>>>(*g, *r, *s, depth, (uint32_t *)arena, node_nz, overflow, skip_empty);
-        else k_expand<uint32_t, false><<<grid, WARPS_PER_BLOCK * 32, 0, st>>>(*g, *r, *s, depth, (uint32_t *)arena, node_nz, overflow, skip_empty);
+    dim3 gs((grid_nodes + WARPS_PER_BLOCK - 1) / WARPS_PER_BLOCK, s->num_slots);
+    if (depth == 1) k_symbolic<true><<<gs, WARPS_PER_BLOCK * 32, 0, st>>>(*g, *r, *s, depth, *fr, dense_num, dense_den, force_dense);
+    else k_symbolic<false><<<gs, WARPS_PER_BLOCK * 32, 0, st>>>(*g, *r, *s, depth, *fr, dense_num, dense_den, force_dense);
+    CHECK_LAUNCH("k_symbolic");
+    dim3 grid((grid_chunks + WARPS_PER_BLOCK - 1) / WARPS_PER_BLOCK, s->num_slots);
+    if (fr->count_bits == 32) {
+        if (depth == 1) k_numeric<uint32_t, true><<<grid, WARPS_PER_BLOCK * 32, 0, st>>>(*g, *r, *s, depth, *fr);
+        else k_numeric<uint32_t, false><<<grid, WARPS_PER_BLOCK * 32, 0, st>>>(*g, *r, *s, depth, *fr);
     } else {
-        if (depth == 1) k_expand<unsigned long long, true><<<grid, WARPS_PER_BLOCK * 32, 0, st>>>(*g, *r, *s, depth, (unsigned long long *)arena, node_nz, overflow, skip_empty);
-        else k_expand<unsigned long long, false><<<grid, WARPS_PER_BLOCK * 32, 0, st>>>(*g, *r, *s, depth, (unsigned long long *)arena, node_nz, overflow, skip_empty);
+        if (depth == 1) k_numeric<unsigned long long, true><<<grid, WARPS_PER_BLOCK * 32, 0, st>>>(*g, *r, *s, depth, *fr);
+        else k_numeric<unsigned long long, false><<<grid, WARPS_PER_BLOCK * 32, 0, st>>>(*g, *r, *s, depth, *fr);
     }
-    CHECK_LAUNCH("k_expand");
+    CHECK_LAUNCH("k_numeric");
     return RL_OK;
 }
 
 int rl_node_counts_dense(const rl_graph *g, const rl_rules *r, const rl_slots *s, int32_t slot, int32_t node,
-                         int32_t count_bits, const void *arena, const int32_t *node_nz, int32_t skip_empty,
-                         int64_t *out, void *stream)
+                         const rl_frontier *fr, int64_t *out, void *stream)
 {
-    if (!g || !r || !s || !out || (node >= 0 && (!arena || !node_nz))) return fail(RL_ERR_ARG, "rl_node_counts_dense: null argument");
+    if (!g || !r || !s || !out) return fail(RL_ERR_ARG, "rl_node_counts_dense: null argument");
+    if (check_frontier(fr, "rl_node_counts_dense: incomplete rl_frontier") != RL_OK) return RL_ERR_ARG;
     if (slot < 0 || slot >= s->num_slots || node >= r->num_nodes) return fail(RL_ERR_ARG, "rl_node_counts_dense: index out of range");
     const int grid = (g->num_entities + 31) / 32;
-    if (count_bits == 32) k_node_dense<uint32_t><<<grid, 1024, 0, (cudaStream_t)stream>>>(*g, *r, *s, slot, node, (const uint32_t *)arena, node_nz, skip_empty, out);
-    else if (count_bits == 64) k_node_dense<unsigned long long><<<grid, 1024, 0, (cudaStream_t)stream>>>(*g, *r, *s, slot, node, (const unsigned long long *)arena, node_nz, skip_empty, out);
-    else return fail(RL_ERR_ARG, "rl_node_counts_dense: count_bits must be 32 or 64");
+    if (fr->count_bits == 32) k_node_dense<uint32_t><<<grid, 1024, 0, (cudaStream_t)stream>>>(*g, *r, *s, slot, node, *fr, out);
+    else k_node_dense<unsigned long long><<<grid, 1024, 0, (cudaStream_t)stream>>>(*g, *r, *s, slot, node, *fr, out);
     CHECK_LAUNCH("k_node_dense");
     return RL_OK;
 }
 
-int rl_predictor_scores(const rl_graph *g, const rl_rules *r, const rl_slots *s, int32_t count_bits,
-                        const void *arena, const int32_t *node_nz, int32_t skip_empty, const float *w,
-                        const float *bias, int32_t fill_neg_inf, float *Z, uint32_t *nzmask, void *stream)
+int rl_predictor_scores(const rl_graph *g, const rl_rules *r, const rl_slots *s, const rl_frontier *fr,
+                        const float *w, const float *bias, int32_t fill_neg_inf, float *Z, uint32_t *nzmask,
+                        void *stream)
 {
-    if (!g || !r || !s || !arena || !node_nz || !w || !Z || !nzmask) return fail(RL_ERR_ARG, "rl_predictor_scores: null argument");
+    if (!g || !r || !s || !w || !Z || !nzmask) return fail(RL_ERR_ARG, "rl_predictor_scores: null argument");
+    if (check_frontier(fr, "rl_predictor_scores: incomplete rl_frontier") != RL_OK) return RL_ERR_ARG;
     if (s->num_slots <= 0) return RL_OK;
-    dim3 grid((g->num_entities + WARPS_PER_BLOCK - 1) / WARPS_PER_BLOCK, s->num_slots);
+    dim3 grid((g->rank_words + WARPS_PER_BLOCK - 1) / WARPS_PER_BLOCK, s->num_slots);
     cudaStream_t st = (cudaStream_t)stream;
-    if (count_bits == 32) k_predictor_scores<uint32_t><<<grid, WARPS_PER_BLOCK * 32, 0, st>>>(*g, *r, *s, (const uint32_t *)arena, node_nz, skip_empty, w, bias, fill_neg_inf, Z, nzmask);
-    else if (count_bits == 64) k_predictor_scores<unsigned long long><<<grid, WARPS_PER_BLOCK * 32, 0, st>>>(*g, *r, *s, (const unsigned long long *)arena, node_nz, skip_empty, w, bias, fill_neg_inf, Z, nzmask);
-    else return fail(RL_ERR_ARG, "rl_predictor_scores: count_bits must be 32 or 64");
+    if (fr->count_bits == 32) k_predictor_scores<uint32_t><<<grid, WARPS_PER_BLOCK * 32, 0, st>>>(*g, *r, *s, *fr, w, bias, fill_neg_inf, Z, nzmask);
+    else k_predictor_scores<unsigned long long><<<grid, WARPS_PER_BLOCK * 32, 0, st>>>(*g, *r, *s, *fr, w, bias, fill_neg_inf, Z, nzmask);
     CHECK_LAUNCH("k_predictor_scores");
     return RL_OK;
 }
@@ -805,18 +950,18 @@ int rl_softmax_ce(const rl_graph *g, const rl_slots *s, const rl_answers *ans, f
     return RL_OK;
 }
 
-int rl_predictor_backward(const rl_graph *g, const rl_rules *r, const rl_slots *s, int32_t count_bits,
-                          const void *arena, const int32_t *node_nz, int32_t skip_empty, const float *G,
-                          const float *slot_scale, int32_t max_terms, float *grad_w, float *grad_bias, void *stream)
+int rl_predictor_backward(const rl_graph *g, const rl_rules *r, const rl_slots *s, const rl_frontier *fr,
+                          const float *G, const float *slot_scale, int32_t max_terms, float *grad_w,
+                          float *grad_bias, void *stream)
 {
-    if (!g || !r || !s || !arena || !node_nz || !G || !grad_w) return fail(RL_ERR_ARG, "rl_predictor_backward: null argument");
+    if (!g || !r || !s || !G || !grad_w) return fail(RL_ERR_ARG, "rl_predictor_backward: null argument");
+    if (check_frontier(fr, "rl_predictor_backward: incomplete rl_frontier") != RL_OK) return RL_ERR_ARG;
     const int S = s->num_slots, N = g->num_entities;
     if (S <= 0) return RL_OK;
     cudaStream_t st = (cudaStream_t)stream;
     dim3 grid(max_terms > 0 ? max_terms : 1, S);
-    if (count_bits == 32) k_predictor_bwd_w<uint32_t><<<grid, 128, 0, st>>>(*g, *r, *s, (const uint32_t *)arena, node_nz, skip_empty, G, slot_scale, grad_w);
-    else if (count_bits == 64) k_predictor_bwd_w<unsigned long long><<<grid, 128, 0, st>>>(*g, *r, *s, (const unsigned long long *)arena, node_nz, skip_empty, G, slot_scale, grad_w);
-    else return fail(RL_ERR_ARG, "rl_predictor_backward: count_bits must be 32 or 64");
+    if (fr->count_bits == 32) k_predictor_bwd_w<uint32_t><<<grid, 128, 0, st>>>(*g, *r, *s, *fr, G, slot_scale, grad_w);
+    else k_predictor_bwd_w<unsigned long long><<<grid, 128, 0, st>>>(*g, *r, *s, *fr, G, slot_scale, grad_w);
     CHECK_LAUNCH("k_predictor_bwd_w");
     if (grad_bias) {
         k_bias_grad<<<(N + WARPS_PER_BLOCK - 1) / WARPS_PER_BLOCK, WARPS_PER_BLOCK * 32, 0, st>>>(N, S, G, slot_scale, grad_bias);

@@ -35,14 +35,18 @@ class Slots:
         np.cumsum(cr.head_rows[heads], out=arena_off[1:])
         nz_off = np.zeros(S + 1, dtype=np.int64)
         np.cumsum(cr.head_nodes[heads], out=nz_off[1:])
-        self.arena_rows, self.nz_total = int(arena_off[-1]), int(nz_off[-1])
+        mask_off = np.zeros(S + 1, dtype=np.int64)
+        np.cumsum(cr.head_chunks[heads], out=mask_off[1:])
+        self.arena_rows, self.nz_total, self.mask_words = int(arena_off[-1]), int(nz_off[-1]), int(mask_off[-1])
         # one packed H2D copy for the slot descriptors
-        pack = np.concatenate([heads.astype(np.int64), q_off.astype(np.int64), nz_off[:-1], arena_off[:-1]])
+        pack = np.concatenate([heads.astype(np.int64), q_off.astype(np.int64), nz_off[:-1], arena_off[:-1],
+                               mask_off[:-1]])
         d = torch.from_numpy(pack).to(dev, non_blocking=True)
         self.slot_head = d[:S].to(torch.int32)
         self.q_off_dev = d[S:2 * S + 1].to(torch.int32)
         self.nz_off = d[2 * S + 1:3 * S + 1].to(torch.int32)
         self.arena_off = d[3 * S + 1:4 * S + 1].contiguous()
+        self.mask_off = d[4 * S + 1:5 * S + 1].contiguous()
         self.lane = torch.empty(4, S * LANES, dtype=torch.int32, device=dev)
         _lib.check(_lib.lib().rl_prepare_slots(
             dg.ref(), S, self.slot_head.data_ptr(), self.q_off_dev.data_ptr(), all_h.data_ptr(),
@@ -51,12 +55,16 @@ class Slots:
             _stream()), "rl_prepare_slots")
         self.struct = _lib.RlSlots(S, self.slot_head.data_ptr(), self.lane[0].data_ptr(), self.lane[1].data_ptr(),
                                    self.lane[2].data_ptr(), self.lane[3].data_ptr(), self.arena_off.data_ptr(),
-                                   self.nz_off.data_ptr())
+                                   self.nz_off.data_ptr(), self.mask_off.data_ptr())
         self._keep = (all_h, all_t, etr, d)
         self.arena = None
-        self.node_nz = None
+        self.state = None         # int32 buffer: row_mask | node_cnt | ent_active | overflow
         self.overflow = None
+        self.frontier = None      # _lib.RlFrontier
         self.count_bits = 32
+
+    def fref(self):
+        return C.byref(self.frontier)
 
     def ref(self):
         return C.byref(self.struct)
@@ -65,12 +73,15 @@ class Slots:
 class Grounder:
     """Grounds every rule of a compiled rule set for batches of queries on one device."""
 
-    def __init__(self, graph, compiled: CompiledRules, device, skip_empty: bool = True):
+    def __init__(self, graph, compiled: CompiledRules, device, force_dense: bool = False):
         self.graph, self.cr = graph, compiled
         self.dg = graph.device_graph(device)
         self.device = self.dg.device
         self.dr = compiled.device_rules(self.device)
-        self.skip_empty = bool(skip_empty)
+        # a node takes ALL its rows (plain dense SpMM) once its parent has > dense_num/dense_den valid
+        # rows; force_dense does so for every node (all algorithmic bytes of SURVEY 8d are moved)
+        self.force_dense = bool(force_dense)
+        self.dense_num, self.dense_den = 1, 4
         self.force_bits: Optional[int] = None
         self.level_events = None      # bench.py: list collecting (depth, start, end) CUDA events
 
@@ -117,23 +128,36 @@ class Grounder:
         sl.count_bits = bits
         sl.arena = torch.empty(max(1, sl.arena_rows) * LANES, dtype=torch.int32 if bits == 32 else torch.int64,
                                device=dev)
-        sl.node_nz = torch.zeros(max(1, sl.nz_total) + 1, dtype=torch.int32, device=dev)
-        sl.overflow = sl.node_nz[-1:]
+        W = self.graph.rank_words
+        n_mask, n_cnt, n_ent = sl.mask_words + 1, sl.nz_total + 1, sl.S * W
+        sl.state = torch.zeros(n_mask + n_cnt + n_ent + 1, dtype=torch.int32, device=dev)   # one memset
+        sl.overflow = sl.state[-1:]
+        base = sl.state.data_ptr()
+        sl.frontier = _lib.RlFrontier(bits, sl.arena.data_ptr(), base, base + 4 * n_mask,
+                                      base + 4 * (n_mask + n_cnt), sl.overflow.data_ptr())
         L = _lib.lib()
         lc = self.cr.level_chunks[sl.heads]                               # [S, max_len]
+        ln = self.cr.level_nodes[sl.heads]
         for depth in range(1, self.cr.max_len + 1):
-            gc = int(lc[:, depth - 1].max())
+            gc, gn = int(lc[:, depth - 1].max()), int(ln[:, depth - 1].max())
             if gc == 0:
                 continue
             if self.level_events is not None:
                 e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
                 e0.record()
-            _lib.check(L.rl_expand_level(self.dg.ref(), self.dr.ref(), sl.ref(), depth, gc, bits,
-                                         sl.arena.data_ptr(), sl.node_nz.data_ptr(), sl.overflow.data_ptr(),
-                                         int(self.skip_empty), _stream()), "rl_expand_level")
+            _lib.check(L.rl_expand_level(self.dg.ref(), self.dr.ref(), sl.ref(), depth, gn, gc, sl.fref(),
+                                         self.dense_num, self.dense_den, int(self.force_dense), _stream()),
+                       "rl_expand_level")
             if self.level_events is not None:
                 e1.record()
                 self.level_events.append((depth, e0, e1))
+
+    def _run_empty(self, sl: Slots):
+        sl.arena = torch.zeros(LANES, dtype=torch.int32, device=self.device)
+        sl.state = torch.zeros(8, dtype=torch.int32, device=self.device)
+        sl.overflow = sl.state[-1:]
+        p = sl.state.data_ptr()
+        sl.frontier = _lib.RlFrontier(32, sl.arena.data_ptr(), p, p + 4, p + 8, sl.overflow.data_ptr())
 
     def ground(self, sl: Slots, check_overflow: bool = True) -> Slots:
         """Run all depths.  Counts are kept in 32-bit rows; if any count does not fit (host sync on
@@ -148,11 +172,11 @@ class Grounder:
     def node_counts(self, sl: Slots, slot: int, node: int) -> torch.Tensor:
         """int64[32, N] dense counts of one trie node (node < 0: the one-hot root)."""
         out = torch.empty(LANES, self.graph.entity_size, dtype=torch.int64, device=self.device)
+        if sl.frontier is None:                       # only the one-hot root is asked for (empty body)
+            self._run_empty(sl)
         _lib.check(_lib.lib().rl_node_counts_dense(
-            self.dg.ref(), self.dr.ref(), sl.ref(), slot, node, sl.count_bits,
-            sl.arena.data_ptr() if sl.arena is not None else None,
-            sl.node_nz.data_ptr() if sl.node_nz is not None else None, int(self.skip_empty),
-            out.data_ptr(), _stream()), "rl_node_counts_dense")
+            self.dg.ref(), self.dr.ref(), sl.ref(), slot, node, sl.fref(), out.data_ptr(), _stream()),
+            "rl_node_counts_dense")
         return out
 
     def rule_counts(self, sl: Slots, rule_ids: Sequence[int]) -> torch.Tensor:
@@ -184,7 +208,7 @@ def ground_chain(graph, h: torch.Tensor, r: int, body: List[int], etr: Optional[
         cache[key] = cr
         if len(cache) > _CHAIN_CACHE_MAX:
             cache.popitem(last=False)
-    gr = Grounder(graph, cr, h.device, skip_empty=True)
+    gr = Grounder(graph, cr, h.device)
     B = int(h.shape[0])
     sl = gr.make_slots([r], [B], h.to(torch.int64), None, None if etr is None else etr.to(h.device, torch.int64))
     if len(body):

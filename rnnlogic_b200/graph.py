@@ -38,13 +38,15 @@ class DeviceGraph:
     def __init__(self, kg: "KnowledgeGraph", device: torch.device):
         self.device = device
         h = kg.host
-        self.t = {k: torch.from_numpy(v).to(device) for k, v in h.items()}
+        self.t = {k: torch.from_numpy(v if v.shape[0] else np.zeros(2, v.dtype)).to(device) for k, v in h.items()}
         t = self.t
         self.struct = _lib.RlGraph(
             kg.entity_size, kg.relation_size, kg.rank_words, int(h["row_dst"].shape[0]), int(h["edge_src"].shape[0]),
             t["dst_ptr"].data_ptr(), t["row_dst"].data_ptr(), t["row_start"].data_ptr(), t["edge_src"].data_ptr(),
             t["rank_tab"].data_ptr(), t["ord_ptr"].data_ptr(), t["ord_h"].data_ptr(), t["ord_t"].data_ptr(),
-            t["ent_ptr"].data_ptr(), t["ent_rel"].data_ptr(), t["ent_row"].data_ptr())
+            t["ent_ptr"].data_ptr(), t["ent_rel"].data_ptr(), t["ent_row"].data_ptr(),
+            t["fsrc_ptr"].data_ptr(), t["frow_start"].data_ptr(), t["fedge_dstrow"].data_ptr(),
+            t["srank_tab"].data_ptr())
         self.answers = {}
         for which in ("hr2o", "hr2oo", "hr2ooo"):
             keys, ptr, ent = kg.answers_csr(which)
@@ -227,6 +229,26 @@ class KnowledgeGraph(object):
         eo = np.lexsort((row_rel, row_dst))
         ent_ptr = np.zeros(N + 1, dtype=np.int64)
         np.cumsum(np.bincount(row_dst, minlength=N), out=ent_ptr[1:])
+        # forward DCSR by source: edges sorted by (r, h, t); each out-edge stores the LOCAL row of its tail
+        fs = np.lexsort((t, h, r))
+        rf, hf, tf = r[fs], h[fs], t[fs]
+        skey = rf * N + hf
+        new_src = np.ones(E, dtype=bool)
+        new_src[1:] = skey[1:] != skey[:-1]
+        src_first = np.flatnonzero(new_src)
+        src_rel, src_ent = rf[src_first], hf[src_first]
+        frow_start = np.concatenate([src_first, [E]])
+        fsrc_ptr = np.zeros(R + 1, dtype=np.int64)
+        np.cumsum(np.bincount(src_rel, minlength=R), out=fsrc_ptr[1:])
+        # local destination row of every edge: position of (r,t) among the relation's rows
+        fedge_dstrow = np.searchsorted(rs[row_first] * N + row_dst, rf * N + tf) - dst_ptr[rf]
+        sbits = np.zeros(R * W, dtype=np.uint32)
+        np.bitwise_or.at(sbits, src_rel * W + (src_ent >> 5), (np.uint32(1) << (src_ent & 31).astype(np.uint32)))
+        spop = np.bitwise_count(sbits).astype(np.int64).reshape(R, W) if R * W else np.zeros((R, W), np.int64)
+        sprefix = np.cumsum(spop, axis=1) - spop
+        srank_tab = np.empty((R * W, 2), dtype=np.uint32)
+        srank_tab[:, 0] = sbits
+        srank_tab[:, 1] = sprefix.reshape(-1).astype(np.uint32)
         # per-relation statistics (algorithmic-bytes model)
         self.rel_edges = rel_sizes
         self.rel_rows = np.diff(dst_ptr)
@@ -239,6 +261,8 @@ class KnowledgeGraph(object):
             "rank_tab": np.ascontiguousarray(rank_tab.reshape(-1)),
             "ord_ptr": i32(ord_ptr), "ord_h": i32(h[order]), "ord_t": i32(t[order]),
             "ent_ptr": i32(ent_ptr), "ent_rel": i32(row_rel[eo]), "ent_row": i32(local_row[eo]),
+            "fsrc_ptr": i32(fsrc_ptr), "frow_start": i32(frow_start), "fedge_dstrow": i32(fedge_dstrow),
+            "srank_tab": np.ascontiguousarray(srank_tab.reshape(-1)),
         }
 
     def device_graph(self, device) -> DeviceGraph:

@@ -30,9 +30,9 @@ class ScoreKernels:
         Z = torch.empty(sl.S, self.N, LANES, dtype=torch.float32, device=self.device)
         nzmask = torch.empty(sl.S, self.N, dtype=torch.int32, device=self.device)
         _lib.check(_lib.lib().rl_predictor_scores(
-            self.dg.ref(), self.dr.ref(), sl.ref(), sl.count_bits, sl.arena.data_ptr(), sl.node_nz.data_ptr(),
-            int(self.gr.skip_empty), w.data_ptr(), bias.data_ptr() if bias is not None else None,
-            int(fill_neg_inf), Z.data_ptr(), nzmask.data_ptr(), _stream()), "rl_predictor_scores")
+            self.dg.ref(), self.dr.ref(), sl.ref(), sl.fref(), w.data_ptr(),
+            bias.data_ptr() if bias is not None else None, int(fill_neg_inf), Z.data_ptr(), nzmask.data_ptr(),
+            _stream()), "rl_predictor_scores")
         return Z, nzmask
 
     # ---- kernel (2b) -------------------------------------------------------------------------
@@ -59,10 +59,9 @@ class ScoreKernels:
                            grad_bias: Optional[torch.Tensor]):
         max_terms = int(self.cr.head_terms[sl.heads].max())
         _lib.check(_lib.lib().rl_predictor_backward(
-            self.dg.ref(), self.dr.ref(), sl.ref(), sl.count_bits, sl.arena.data_ptr(), sl.node_nz.data_ptr(),
-            int(self.gr.skip_empty), G.data_ptr(), slot_scale.data_ptr() if slot_scale is not None else None,
-            max_terms, grad_w.data_ptr(), grad_bias.data_ptr() if grad_bias is not None else None, _stream()),
-            "rl_predictor_backward")
+            self.dg.ref(), self.dr.ref(), sl.ref(), sl.fref(), G.data_ptr(),
+            slot_scale.data_ptr() if slot_scale is not None else None, max_terms, grad_w.data_ptr(),
+            grad_bias.data_ptr() if grad_bias is not None else None, _stream()), "rl_predictor_backward")
 
     # ---- kernel (3) --------------------------------------------------------------------------
     def filtered_rank(self, sl: Slots, Z, nzmask, which: str, use_mask: bool) -> torch.Tensor:

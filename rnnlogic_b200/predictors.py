@@ -26,7 +26,7 @@ LANES = _lib.LANES
 class _RuleModel(nn.Module):
     """Shared plumbing: rule parsing/compilation and per-device kernel drivers."""
 
-    skip_empty = True        # skip sub-tries whose parent frontier is all-zero (exact)
+    force_dense = False      # True: expand every row of every trie node (plain dense SpMM)
 
     def _load_rules(self, input, who):
         rules = parse_rules(input)
@@ -45,7 +45,7 @@ class _RuleModel(nn.Module):
                                "fallback: move the model and the batch to a CUDA device." % device)
         key = str(device)
         if key not in self._drivers:
-            self._drivers[key] = ScoreKernels(Grounder(self.graph, self.compiled, device, self.skip_empty))
+            self._drivers[key] = ScoreKernels(Grounder(self.graph, self.compiled, device, self.force_dense))
         return self._drivers[key]
 
     def _ground(self, all_h, all_r, edges_to_remove):

@@ -106,6 +106,9 @@ class CompiledRules:
         first_node = np.searchsorted(nkey, want, side="left")
         lvl_ptr = cstart[first_node].reshape(R, L1)
         self.level_chunks = np.diff(lvl_ptr, axis=1)                  # [R, max_len] chunks per (head, depth)
+        lvl_node_ptr = first_node.reshape(R, L1)
+        self.level_nodes = np.diff(lvl_node_ptr, axis=1)              # [R, max_len] nodes per (head, depth)
+        self.head_chunks = lvl_ptr[:, -1] - lvl_ptr[:, 0]
         # terminal lists keyed by (head, last relation)
         t_rule = np.array([i for i, lf in enumerate(rule_leaf) if lf is not None], dtype=np.int64)
         t_node = np.array([gid[lf[0]][lf[1]] for lf in rule_leaf if lf is not None], dtype=np.int64)
@@ -121,6 +124,7 @@ class CompiledRules:
         self.head_terms = term_ptr[(np.arange(R) + 1) * R] - term_ptr[np.arange(R) * R]
         self.rule_node = np.full(self.num_rules, -1, dtype=np.int64)
         self.rule_node[t_rule] = t_node
+        node_nterm = np.bincount(t_node, minlength=max(1, self.num_nodes))
         zr_ptr = np.zeros(R + 1, dtype=np.int64)
         np.cumsum([len(z) for z in zero_rules], out=zr_ptr[1:])
         zr_rule = np.array([i for z in zero_rules for i in z], dtype=np.int64)
@@ -147,6 +151,7 @@ class CompiledRules:
             "head_node_ptr": i32(head_node_ptr), "lvl_ptr": i32(lvl_ptr.reshape(-1)),
             "chunk_node": i32(chunk_node), "chunk_row0": i32(chunk_row0), "term_ptr": i32(term_ptr),
             "term_node": i32(t_node), "term_rule": i32(t_rule), "zr_ptr": i32(zr_ptr), "zr_rule": i32(zr_rule),
+            "lvl_node_ptr": i32(lvl_node_ptr.reshape(-1)), "node_chunk0": i32(cstart[:-1]), "node_nterm": i32(node_nterm),
         }
         self._devices = {}
 
@@ -168,7 +173,8 @@ class DeviceRules:
             t["node_rel"].data_ptr(), t["node_parent"].data_ptr(), t["node_row_off"].data_ptr(),
             t["head_node_ptr"].data_ptr(), t["lvl_ptr"].data_ptr(), t["chunk_node"].data_ptr(),
             t["chunk_row0"].data_ptr(), t["term_ptr"].data_ptr(), t["term_node"].data_ptr(),
-            t["term_rule"].data_ptr(), t["zr_ptr"].data_ptr(), t["zr_rule"].data_ptr())
+            t["term_rule"].data_ptr(), t["zr_ptr"].data_ptr(), t["zr_rule"].data_ptr(),
+            t["lvl_node_ptr"].data_ptr(), t["node_chunk0"].data_ptr(), t["node_nterm"].data_ptr())
 
     def ref(self):
         return C.byref(self.struct)

@@ -32,9 +32,9 @@ def test_grounding_api_matches_reference_golden(ds):
         assert np.array_equal(got.cpu().numpy(), fx["gr%d_counts" % c]), (name, c, body)
 
 
-@pytest.mark.parametrize("skip_empty", [True, False])
+@pytest.mark.parametrize("mode", ["auto", "dense", "sparse"])
 @pytest.mark.parametrize("bits", [32, 64])
-def test_all_rules_of_head_vs_oracle(ds, skip_empty, bits):
+def test_all_rules_of_head_vs_oracle(ds, mode, bits):
     """Every rule of the head through the shared trie == per-rule oracle grounding (with the
     query edge removed), for train batches (B up to 50 -> 2 slots)."""
     from rnnlogic_b200 import CompiledRules
@@ -42,7 +42,9 @@ def test_all_rules_of_head_vs_oracle(ds, skip_empty, bits):
     name, fx, kg, okg, rules = ds
     dev = torch.device("cuda:0")
     cr = CompiledRules(kg, rules)
-    gr = Grounder(kg, cr, dev, skip_empty=skip_empty)
+    gr = Grounder(kg, cr, dev, force_dense=(mode == "dense"))
+    if mode == "sparse":
+        gr.dense_num, gr.dense_den = 1 << 20, 1      # never switch a node to all-rows
     gr.force_bits = bits
     for j in range(0, int(fx["tb_n"]), 3):
         tri, _, etr = G.train_batch_inputs(fx, j)
