@@ -38,7 +38,7 @@ static int fail(int code, const char *what, cudaError_t e = cudaSuccess)
 // ------------------------------------------------------------------------------------------
 __device__ __forceinline__ int rank_row(const rl_graph &g, int rel, int e)
 {
-    const uint2 w = __ldg(reinterpret_cast<const uint2 *>(g.rank_tab) + (size_t)rel * g.rank_words + (e >> 5));
+    const uint2 w = __ldg(reinterpret_cast<const uint2 *>(g.rank_tab) + (size_t)rel * g.rank_words + (e >> 5));  // g is a kernel parameter (constant bank), always inlined
     const uint32_t bit = 1u << (e & 31);
     return (w.x & bit) ? (int)(w.y + __popc(w.x & (bit - 1))) : -1;
 }
@@ -169,7 +169,6 @@ k_symbolic(rl_graph g, rl_rules r, rl_slots s, int depth, rl_frontier fr, int de
     if (dense) {
         for (int w = lane; w < nw; w += 32)
             cm[w] = (w == nw - 1 && (D & 31)) ? ((1u << (D & 31)) - 1u) : 0xffffffffu;
-        if (lane == 0) fr.node_cnt[nzb + v] = D;
         return;
     }
     if (ROOT) {
@@ -188,29 +187,17 @@ k_symbolic(rl_graph g, rl_rules r, rl_slots s, int depth, rl_frontier fr, int de
             }
         }
     }
-    __syncwarp();
-    int c = 0;
-    for (int w = lane; w < nw; w += 32) c += __popc(__ldcg(cm + w));
-    c = warp_sumi(c);
-    if (lane == 0) fr.node_cnt[nzb + v] = c;
 }
 
 #define EDGE_GROUP 8
+// One chunk (<= 32 destination rows of node v starting at row0) with valid-row word m.
+// Returns the word of rows that ended up NON-ZERO (exact frontier support).
 template <typename CT, bool ROOT>
-__global__ void __launch_bounds__(WARPS_PER_BLOCK * 32)
-k_numeric(rl_graph g, rl_rules r, rl_slots s, int depth, rl_frontier fr)
+__device__ __forceinline__ uint32_t numeric_chunk(const rl_graph &g, const rl_rules &r, const rl_slots &s, const rl_frontier &fr,
+                                                  int slot, int q, int hc0, const uint32_t *mbase, int v, int row0, uint32_t m,
+                                                  int h, int lane_eh, int lane_et, bool &ovf)
 {
-    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    const int slot = blockIdx.y;
-    const int q = s.slot_head[slot];
-    const int32_t *lp = r.lvl_ptr + (size_t)q * (r.max_len + 1);
-    const int chunk = lp[depth - 1] + blockIdx.x * WARPS_PER_BLOCK + warp;
-    if (chunk >= lp[depth]) return;
-    const int hc0 = lp[0];
-    const uint32_t *mbase = fr.row_mask + (size_t)s.mask_off[slot];
-    const uint32_t m = mbase[chunk - hc0];
-    if (m == 0u) return;
-    const int v = r.chunk_node[chunk], row0 = r.chunk_row0[chunk];
+    const int lane = threadIdx.x & 31;
     const int rho = r.node_rel[v];
     const size_t abase = (size_t)s.arena_off[slot];
     CT *arena = reinterpret_cast<CT *>(fr.arena);
@@ -239,16 +226,13 @@ k_numeric(rl_graph g, rl_rules r, rl_slots s, int depth, rl_frontier fr)
     }
     const int T = __shfl_sync(FULL, P, 31);
     const int my_first = P - deg;                            // position of my row's first edge in the list
-    const int h = s.lane_h[slot * RL_LANES + lane];
     const bool masked = (rho == q);
-    const int eh = masked ? s.lane_eh[slot * RL_LANES + lane] : -1;
-    const int et = masked ? s.lane_et[slot * RL_LANES + lane] : -1;
-    if (r.node_nterm[v] > 0 && active)                       // candidate entities for the aggregation
-        atomicOr(fr.ent_active + (size_t)slot * g.rank_words + (my_dst >> 5), 1u << (my_dst & 31));
+    const int eh = masked ? lane_eh : -1;
+    const int et = masked ? lane_et : -1;
 
     int cur = -1;
     unsigned long long acc = 0;
-    bool ovf = false;
+    uint32_t nzrows = 0;
     auto flush = [&](int j) {
         const int d = __shfl_sync(FULL, my_dst, j);
         if (eh >= 0 && et == d) {                            // data.py:164-170: drop the query's own edge
@@ -262,7 +246,10 @@ k_numeric(rl_graph g, rl_rules r, rl_slots s, int depth, rl_frontier fr)
             acc -= sub;
         }
         if (sizeof(CT) == 4 && (acc >> 32)) ovf = true;
-        Y[(size_t)j * RL_LANES + lane] = (CT)acc;
+        if (__any_sync(FULL, acc != 0)) {                    // all-zero rows are dropped from the bitmap
+            Y[(size_t)j * RL_LANES + lane] = (CT)acc;
+            nzrows |= 1u << j;
+        }
         acc = 0;
     };
 
@@ -308,12 +295,53 @@ k_numeric(rl_graph g, rl_rules r, rl_slots s, int depth, rl_frontier fr)
         }
     }
     if (cur >= 0) flush(cur);
+    if (r.node_nterm[v] > 0 && ((nzrows >> lane) & 1u))      // candidate entities for the aggregation
+        atomicOr(fr.ent_active + (size_t)slot * g.rank_words + (my_dst >> 5), 1u << (my_dst & 31));
+    return nzrows;
+}
+
+// One warp = 32 consecutive chunks of one slot at this depth: the 32 valid-row words are read with
+// one coalesced load and only chunks with a non-zero word are expanded.
+template <typename CT, bool ROOT>
+__global__ void __launch_bounds__(WARPS_PER_BLOCK * 32)
+k_numeric(rl_graph g, rl_rules r, rl_slots s, int depth, rl_frontier fr)
+{
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int slot = blockIdx.y;
+    const int q = s.slot_head[slot];
+    const int32_t *lp = r.lvl_ptr + (size_t)q * (r.max_len + 1);
+    const int c_end = lp[depth];
+    const int c0 = lp[depth - 1] + (blockIdx.x * WARPS_PER_BLOCK + warp) * 32;
+    if (c0 >= c_end) return;
+    const int hc0 = lp[0];
+    uint32_t *mbase = fr.row_mask + (size_t)s.mask_off[slot];
+    const int nzb = s.nz_off[slot] - r.head_node_ptr[q];
+    const int my_chunk = c0 + lane;
+    uint32_t my_m = my_chunk < c_end ? mbase[my_chunk - hc0] : 0u;
+    uint32_t todo = __ballot_sync(FULL, my_m != 0u);
+    if (todo == 0u) return;
+    const int h = s.lane_h[slot * RL_LANES + lane];
+    const int leh = s.lane_eh[slot * RL_LANES + lane];
+    const int let_ = s.lane_et[slot * RL_LANES + lane];
+    bool ovf = false;
+    uint32_t my_out = 0u;
+    while (todo) {
+        const int c = __ffs(todo) - 1;
+        todo &= todo - 1;
+        const int chunk = c0 + c;
+        const uint32_t m = __shfl_sync(FULL, my_m, c);
+        const int v = r.chunk_node[chunk], row0 = r.chunk_row0[chunk];
+        const uint32_t nz = numeric_chunk<CT, ROOT>(g, r, s, fr, slot, q, hc0, mbase, v, row0, m, h, leh, let_, ovf);
+        if (lane == c) my_out = nz;
+        if (lane == 0 && nz) atomicAdd(fr.node_cnt + nzb + v, __popc(nz));
+    }
+    if (my_m != my_out) mbase[my_chunk - hc0] = my_out;      // bitmap now = rows that are non-zero
     if (__any_sync(FULL, ovf) && lane == 0) *fr.overflow = 1;
 }
 
-__device__ __forceinline__ bool row_valid(const rl_rules &r, const uint32_t *mbase, int hc0, int v, int row)
+__device__ __forceinline__ bool row_valid(const int32_t *__restrict__ node_chunk0, const uint32_t *mbase, int hc0, int v, int row)
 {
-    return (mbase[r.node_chunk0[v] - hc0 + (row >> 5)] >> (row & 31)) & 1u;
+    return (mbase[node_chunk0[v] - hc0 + (row >> 5)] >> (row & 31)) & 1u;
 }
 
 // dense int64 [32][N] view of one node (debug / KnowledgeGraph.grounding return value)
@@ -333,7 +361,7 @@ __global__ void k_node_dense(rl_graph g, rl_rules r, rl_slots s, int slot, int n
             const int hc0 = r.lvl_ptr[(size_t)q * (r.max_len + 1)];
             const uint32_t *mbase = fr.row_mask + (size_t)s.mask_off[slot];
             const int row = rank_row(g, r.node_rel[node], e);
-            if (row >= 0 && row_valid(r, mbase, hc0, node, row))
+            if (row >= 0 && row_valid(r.node_chunk0, mbase, hc0, node, row))
                 c = (long long)reinterpret_cast<const CT *>(fr.arena)[((size_t)s.arena_off[slot] + r.node_row_off[node] + row) * RL_LANES + lane];
         }
     }
@@ -396,7 +424,7 @@ k_predictor_scores(rl_graph g, rl_rules r, rl_slots s, rl_frontier fr, const flo
                     const int rw = __shfl_sync(FULL, row, k);
                     for (int t = a0; t < a1; ++t) {
                         const int v = __ldg(r.term_node + t);
-                        if (!row_valid(r, mbase, hc0, v, rw)) continue;
+                        if (!row_valid(r.node_chunk0, mbase, hc0, v, rw)) continue;
                         const CT c = arena[(abase + (size_t)r.node_row_off[v] + rw) * RL_LANES + lane];
                         if (c != 0) {
                             acc += (double)(float)c * (double)__ldg(w + r.term_rule[t]);   // x.float() * w (predictors.py:64)
@@ -638,10 +666,22 @@ k_predictor_bwd_w(rl_graph g, rl_rules r, rl_slots s, rl_frontier fr, const floa
     for (int wi = warp; wi < nw; wi += 4) {
         uint32_t word = cm[wi];
         while (word) {
-            const int j = wi * 32 + __ffs(word) - 1;
-            word &= word - 1;
-            const CT c = Xv[(size_t)j * RL_LANES + lane];
-            if (c != 0) acc += (double)(float)c * (double)Gs[(size_t)g.row_dst[rb + j] * RL_LANES + lane];
+            int j[4];
+            CT c[4];
+            float gv[4];
+#pragma unroll
+            for (int u = 0; u < 4; ++u) {                      // 4 rows in flight
+                j[u] = word ? wi * 32 + __ffs(word) - 1 : -1;
+                word &= word - 1;
+            }
+#pragma unroll
+            for (int u = 0; u < 4; ++u) c[u] = j[u] >= 0 ? Xv[(size_t)j[u] * RL_LANES + lane] : (CT)0;
+#pragma unroll
+            for (int u = 0; u < 4; ++u)
+                gv[u] = j[u] >= 0 ? Gs[(size_t)__ldg(g.row_dst + rb + j[u]) * RL_LANES + lane] : 0.f;
+#pragma unroll
+            for (int u = 0; u < 4; ++u)
+                if (c[u] != 0) acc += (double)(float)c[u] * (double)gv[u];
         }
     }
     acc = warp_sum(acc);
@@ -879,7 +919,7 @@ int rl_expand_level(const rl_graph *g, const rl_rules *r, const rl_slots *s, int
     if (depth == 1) k_symbolic<true><<<gs, WARPS_PER_BLOCK * 32, 0, st>>>(*g, *r, *s, depth, *fr, dense_num, dense_den, force_dense);
     else k_symbolic<false><<<gs, WARPS_PER_BLOCK * 32, 0, st>>>(*g, *r, *s, depth, *fr, dense_num, dense_den, force_dense);
     CHECK_LAUNCH("k_symbolic");
-    dim3 grid((grid_chunks + WARPS_PER_BLOCK - 1) / WARPS_PER_BLOCK, s->num_slots);
+    dim3 grid((grid_chunks + WARPS_PER_BLOCK * 32 - 1) / (WARPS_PER_BLOCK * 32), s->num_slots);
     if (fr->count_bits == 32) {
         if (depth == 1) k_numeric<uint32_t, true><<<grid, WARPS_PER_BLOCK * 32, 0, st>>>(*g, *r, *s, depth, *fr);
         else k_numeric<uint32_t, false><<<grid, WARPS_PER_BLOCK * 32, 0, st>>>(*g, *r, *s, depth, *fr);

@@ -83,6 +83,8 @@ class Grounder:
         self.force_dense = bool(force_dense)
         self.dense_num, self.dense_den = 1, 4
         self.force_bits: Optional[int] = None
+        self._ws_arena = None
+        self._ws_state = None
         self.level_events = None      # bench.py: list collecting (depth, start, end) CUDA events
 
     def make_slots(self, heads: Sequence[int], sizes: Sequence[int], all_h, all_t=None, etr=None) -> Slots:
@@ -119,6 +121,7 @@ class Grounder:
                 rows.append(self.graph.edge_index_of(flat))
         d = torch.from_numpy(np.ascontiguousarray(np.stack(rows))).to(self.device, non_blocking=True)
         sl = self.make_slots(heads, sizes, d[0], d[1], d[2] if with_etr else None)
+        sl.use_workspace = True
         sl.group_sizes = sizes
         sl.h2d_bytes = int(d.numel() * 8)
         return sl
@@ -126,11 +129,24 @@ class Grounder:
     def _run(self, sl: Slots, bits: int):
         dev = self.device
         sl.count_bits = bits
-        sl.arena = torch.empty(max(1, sl.arena_rows) * LANES, dtype=torch.int32 if bits == 32 else torch.int64,
-                               device=dev)
         W = self.graph.rank_words
         n_mask, n_cnt, n_ent = sl.mask_words + 1, sl.nz_total + 1, sl.S * W
-        sl.state = torch.zeros(n_mask + n_cnt + n_ent + 1, dtype=torch.int32, device=dev)   # one memset
+        n_arena = max(1, sl.arena_rows) * LANES * (1 if bits == 32 else 2)
+        n_state = n_mask + n_cnt + n_ent + 1
+        if getattr(sl, "use_workspace", False):
+            # fused paths consume the frontier inside the call: reuse one grow-only buffer (no
+            # cudaMalloc in steady state; the arena needs no clearing, rows outside the bitmap are
+            # never read)
+            if self._ws_arena is None or self._ws_arena.numel() < n_arena:
+                self._ws_arena = None
+                self._ws_arena = torch.empty(int(n_arena * 1.25), dtype=torch.int32, device=dev)
+            if self._ws_state is None or self._ws_state.numel() < n_state:
+                self._ws_state = torch.empty(int(n_state * 1.25), dtype=torch.int32, device=dev)
+            sl.arena = self._ws_arena[:n_arena]
+            sl.state = self._ws_state[:n_state].zero_()
+        else:
+            sl.arena = torch.empty(n_arena, dtype=torch.int32, device=dev)
+            sl.state = torch.zeros(n_state, dtype=torch.int32, device=dev)                    # one memset
         sl.overflow = sl.state[-1:]
         base = sl.state.data_ptr()
         sl.frontier = _lib.RlFrontier(bits, sl.arena.data_ptr(), base, base + 4 * n_mask,
