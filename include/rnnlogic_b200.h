@@ -210,6 +210,43 @@ int rl_filtered_rank_dense(int64_t Q, int64_t N, const float *logits, const uint
 int rl_rank_metrics(int64_t Q, const int64_t *LH, const double *weight, int32_t expectation,
                     const double *harmonic, double *sums, void *stream);
 
+/* ---- PredictorPlus (src/predictors.py:210-271, src/layers.py:63-126) ------------------------
+ * A candidate is a (query, entity) cell whose total path count is non-zero (predictors.py:239);
+ * candidates are numbered slot-major, entity-major, lane-minor:
+ *   index(slot, e, b) = cand_off[slot*N + e] + popcount(nzmask[slot*N + e] & ((1 << b) - 1)),
+ * cand_off = exclusive prefix sum of cand_cnt (done by the caller). */
+
+/* nzmask[S][N] (bit b <=> sum_rule count[e][b] != 0, empty-body rules included) and
+ * cand_cnt[S*N] = popcount(nzmask).  Replaces mask / candidate_set of predictors.py:220-239. */
+int rl_plus_mask(const rl_graph *g, const rl_rules *r, const rl_slots *s, const rl_frontier *fr,
+                 uint32_t *nzmask, int32_t *cand_cnt, void *stream);
+
+/* Rule-embedding aggregation per candidate, replaces the [C,R_q,H] broadcast of
+ * FuncToNodeSum / FuncToNode (layers.py:68-72, 94-99): out_sum[C][H] = sum_rule fp32(count)*emb;
+ * with pna != 0 also out_sq (count*emb^2), out_min/out_max over rules with count != 0, their
+ * arg rules (rows of emb), degree[C] = sum count + 1.  emb is [n][H] fp32, rule_local[rule id] its
+ * row.  cand_query[C] = index of the candidate's query in the call (b_n of predictors.py:240). */
+int rl_plus_features(const rl_graph *g, const rl_rules *r, const rl_slots *s, const rl_frontier *fr,
+                     const uint32_t *nzmask, const int64_t *cand_off, const int32_t *q_off,
+                     const int32_t *rule_local, const float *emb, int32_t H, int32_t pna,
+                     float *out_sum, float *out_sq, float *out_min, float *out_max, int32_t *arg_min,
+                     int32_t *arg_max, float *degree, int64_t *cand_query, void *stream);
+
+/* Z[S][N][32] = (candidate ? zc[index] : 0 | -inf) + bias[e] + extra[S][N][32]; replaces
+ * predictors.py:257-269.  bias / extra may be NULL. */
+int rl_plus_scatter(const rl_graph *g, const rl_slots *s, const uint32_t *nzmask, const int64_t *cand_off,
+                    const float *zc, const float *bias, const float *extra, int32_t fill_neg_inf,
+                    float *Z, void *stream);
+/* dz[index] = G[slot][e][b] at the candidate cells (backward of the scatter). */
+int rl_plus_gather(const rl_graph *g, const rl_slots *s, const uint32_t *nzmask, const int64_t *cand_off,
+                   const float *G, float *dz, void *stream);
+
+/* Backward of rl_plus_features into the rule embeddings: gA[row][h] += sum_cells fp32(count) *
+ * dA[cell][h] (and gB from dB, the squared-sum branch of PNA; dB/gB may be NULL).  ACCUMULATES. */
+int rl_plus_backward(const rl_graph *g, const rl_rules *r, const rl_slots *s, const rl_frontier *fr,
+                     const uint32_t *nzmask, const int64_t *cand_off, const int32_t *rule_local, int32_t H,
+                     const float *dA, const float *dB, int32_t max_terms, float *gA, float *gB, void *stream);
+
 /* Entity-major <-> reference layout: out[b][e] = Z[slot][e][b] for b < nq (fp32 [nq][N]). */
 int rl_slot_to_dense(int32_t N, int32_t nq, const float *Z_slot, float *out, int64_t out_stride,
                      void *stream);

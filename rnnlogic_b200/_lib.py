@@ -65,7 +65,7 @@ def nvcc_command(out=LIB_PATH):
 def build(force: bool = False) -> str:
     """Compile csrc/*.cu for sm_100a into rnnlogic_b200/lib/ (cross-compiles without a GPU)."""
     os.makedirs(os.path.dirname(LIB_PATH), exist_ok=True)
-    deps = [s for s in SOURCES if os.path.exists(s)] + [HEADER]
+    deps = [s for s in SOURCES if os.path.exists(s)] + [HEADER, os.path.join(_HERE, "csrc", "rl_device.cuh")]
     stale = force or not os.path.exists(LIB_PATH) or any(
         os.path.getmtime(d) > os.path.getmtime(LIB_PATH) for d in deps)
     if stale:
@@ -96,6 +96,13 @@ _PROTOS = {
                                    vp, vp, vp, vp, vp]),
     "rl_filtered_rank_dense": (C.c_int, [C.c_int64, C.c_int64, vp, vp, vp, vp, vp, vp]),
     "rl_rank_metrics": (C.c_int, [C.c_int64, vp, vp, C.c_int32, vp, vp, vp]),
+    "rl_plus_mask": (C.c_int, [C.POINTER(RlGraph), C.POINTER(RlRules), C.POINTER(RlSlots), C.POINTER(RlFrontier), vp, vp, vp]),
+    "rl_plus_features": (C.c_int, [C.POINTER(RlGraph), C.POINTER(RlRules), C.POINTER(RlSlots), C.POINTER(RlFrontier),
+                                   vp, vp, vp, vp, vp, C.c_int32, C.c_int32, vp, vp, vp, vp, vp, vp, vp, vp, vp]),
+    "rl_plus_scatter": (C.c_int, [C.POINTER(RlGraph), C.POINTER(RlSlots), vp, vp, vp, vp, vp, C.c_int32, vp, vp]),
+    "rl_plus_gather": (C.c_int, [C.POINTER(RlGraph), C.POINTER(RlSlots), vp, vp, vp, vp, vp]),
+    "rl_plus_backward": (C.c_int, [C.POINTER(RlGraph), C.POINTER(RlRules), C.POINTER(RlSlots), C.POINTER(RlFrontier),
+                                   vp, vp, vp, C.c_int32, vp, vp, C.c_int32, vp, vp, vp]),
     "rl_slot_to_dense": (C.c_int, [C.c_int32, C.c_int32, vp, vp, C.c_int64, vp]),
     "rl_mask_to_dense": (C.c_int, [C.c_int32, C.c_int32, vp, vp, C.c_int64, vp]),
 }

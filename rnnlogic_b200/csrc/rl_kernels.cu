@@ -5,73 +5,19 @@
 // All per-slot matrices are entity-major [row][32 lanes]: a warp owns rows, lane b owns query b,
 // so every frontier / logit access is one coalesced 128-byte line.  This is HBM/L2-bound
 // integer work: no tensor cores, the levers are coalescing, loads in flight and grid sizing.
-#include <cuda_runtime.h>
-#include <stdint.h>
-#include <stdio.h>
-#include <math.h>
-
-#include "rnnlogic_b200.h"
-
-#define FULL 0xffffffffu
-#define WARPS_PER_BLOCK 8
-#define SM_ROWS_PER_BLOCK 512   // entity rows per block in the softmax / rank sweeps
+#include "rl_device.cuh"
 
 static thread_local char g_err[512] = "";
 static long long g_launches = 0;   // kernels enqueued through this library (bench.py: gpu_launches)
 
-static int fail(int code, const char *what, cudaError_t e = cudaSuccess)
+int rl_fail(int code, const char *what, cudaError_t e)
 {
     if (e != cudaSuccess) snprintf(g_err, sizeof(g_err), "%s: %s", what, cudaGetErrorString(e));
     else snprintf(g_err, sizeof(g_err), "%s", what);
     return code;
 }
-
-#define CHECK_LAUNCH(name)                                             \
-    do {                                                               \
-        cudaError_t e_ = cudaGetLastError();                           \
-        if (e_ != cudaSuccess) return fail(RL_ERR_CUDA, name, e_);     \
-        ++g_launches;                                                  \
-    } while (0)
-
-// ------------------------------------------------------------------------------------------
-// device helpers
-// ------------------------------------------------------------------------------------------
-__device__ __forceinline__ int rank_row(const rl_graph &g, int rel, int e)
-{
-    const uint2 w = __ldg(reinterpret_cast<const uint2 *>(g.rank_tab) + (size_t)rel * g.rank_words + (e >> 5));  // g is a kernel parameter (constant bank), always inlined
-    const uint32_t bit = 1u << (e & 31);
-    return (w.x & bit) ? (int)(w.y + __popc(w.x & (bit - 1))) : -1;
-}
-
-__device__ __forceinline__ double warp_sum(double v)
-{
-#pragma unroll
-    for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(FULL, v, o);
-    return v;
-}
-__device__ __forceinline__ float warp_sumf(float v)
-{
-#pragma unroll
-    for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(FULL, v, o);
-    return v;
-}
-__device__ __forceinline__ int warp_sumi(int v)
-{
-#pragma unroll
-    for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(FULL, v, o);
-    return v;
-}
-
-// lower_bound over sorted keys; returns index or -1
-__device__ __forceinline__ int find_key(const rl_answers &a, long long key)
-{
-    long long lo = 0, hi = a.num_keys;
-    while (lo < hi) {
-        long long mid = (lo + hi) >> 1;
-        if (a.keys[mid] < key) lo = mid + 1; else hi = mid;
-    }
-    return (lo < a.num_keys && a.keys[lo] == key) ? (int)lo : -1;
-}
+void rl_count_launch() { ++g_launches; }
+static int fail(int code, const char *what, cudaError_t e = cudaSuccess) { return rl_fail(code, what, e); }
 
 // ------------------------------------------------------------------------------------------
 // slot preparation (trainer.py:69-82 batch tensors -> lane arrays)
@@ -339,11 +285,6 @@ k_numeric(rl_graph g, rl_rules r, rl_slots s, int depth, rl_frontier fr)
     if (__any_sync(FULL, ovf) && lane == 0) *fr.overflow = 1;
 }
 
-__device__ __forceinline__ bool row_valid(const int32_t *__restrict__ node_chunk0, const uint32_t *mbase, int hc0, int v, int row)
-{
-    return (mbase[node_chunk0[v] - hc0 + (row >> 5)] >> (row & 31)) & 1u;
-}
-
 // dense int64 [32][N] view of one node (debug / KnowledgeGraph.grounding return value)
 template <typename CT>
 __global__ void k_node_dense(rl_graph g, rl_rules r, rl_slots s, int slot, int node, rl_frontier fr,
@@ -406,33 +347,12 @@ k_predictor_scores(rl_graph g, rl_rules r, rl_slots s, rl_frontier fr, const flo
         double acc = 0.0;
         bool any = false;
         if ((act >> i) & 1u) {
-            const int p0 = g.ent_ptr[e], p1 = g.ent_ptr[e + 1];
-            for (int pb = p0; pb < p1; pb += 32) {
-                const int pi = pb + lane;
-                int row = 0, t0 = 0, t1 = 0;
-                if (pi < p1) {
-                    const int rel = g.ent_rel[pi];
-                    row = g.ent_row[pi];
-                    t0 = tp[rel];
-                    t1 = tp[rel + 1];
+            scan_entity<CT>(g, r, arena, abase, mbase, hc0, tp, e, [&](CT c, int t) {
+                if (c != 0) {
+                    acc += (double)(float)c * (double)__ldg(w + r.term_rule[t]);   // x.float() * w (predictors.py:64)
+                    any = true;
                 }
-                uint32_t have = __ballot_sync(FULL, t1 > t0);
-                while (have) {
-                    const int k = __ffs(have) - 1;
-                    have &= have - 1;
-                    const int a0 = __shfl_sync(FULL, t0, k), a1 = __shfl_sync(FULL, t1, k);
-                    const int rw = __shfl_sync(FULL, row, k);
-                    for (int t = a0; t < a1; ++t) {
-                        const int v = __ldg(r.term_node + t);
-                        if (!row_valid(r.node_chunk0, mbase, hc0, v, rw)) continue;
-                        const CT c = arena[(abase + (size_t)r.node_row_off[v] + rw) * RL_LANES + lane];
-                        if (c != 0) {
-                            acc += (double)(float)c * (double)__ldg(w + r.term_rule[t]);   // x.float() * w (predictors.py:64)
-                            any = true;
-                        }
-                    }
-                }
-            }
+            });
             if (h == e && z1 > z0) { acc += zsum; any = true; }   // empty-body rules: count = one_hot(h)
         }
         float z = (float)acc;

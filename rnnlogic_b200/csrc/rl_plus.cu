@@ -1,0 +1,346 @@
+// rnnlogic_b200 -- PredictorPlus kernels: candidate compaction, rule-embedding aggregation
+// (sum / PNA statistics), scatter of candidate scores into the logit matrix, and the backward into
+// the rule embeddings.  Reference: src/predictors.py:210-271, src/layers.py:63-77 / 89-126.
+//
+// A candidate is a (query, entity) cell with a non-zero total path count (predictors.py:239).
+// Candidates are numbered slot-major, entity-major, lane-minor; the order is internal (every
+// per-candidate op of the reference is row-wise or an order-free reduction).
+#include "rl_device.cuh"
+
+#define HC 16   // hidden-dim chunk kept in registers per pass
+
+// ------------------------------------------------------------------------------------------
+// pass 1: nzmask[S][N] (bit b <=> sum_rule count != 0) and cand_cnt[S*N] = popcount
+// ------------------------------------------------------------------------------------------
+template <typename CT>
+__global__ void __launch_bounds__(WARPS_PER_BLOCK * 32)
+k_plus_mask(rl_graph g, rl_rules r, rl_slots s, rl_frontier fr, uint32_t *__restrict__ nzmask,
+            int32_t *__restrict__ cand_cnt)
+{
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int slot = blockIdx.y;
+    const int ew = blockIdx.x * WARPS_PER_BLOCK + warp;
+    const int N = g.num_entities, R = g.num_relations;
+    if (ew >= g.rank_words) return;
+    const int q = s.slot_head[slot];
+    const int hc0 = r.lvl_ptr[(size_t)q * (r.max_len + 1)];
+    const uint32_t *mbase = fr.row_mask + (size_t)s.mask_off[slot];
+    const size_t abase = (size_t)s.arena_off[slot];
+    const CT *arena = reinterpret_cast<const CT *>(fr.arena);
+    const int32_t *tp = r.term_ptr + (size_t)q * R;
+    const int h = s.lane_h[slot * RL_LANES + lane];
+    const bool has_zr = r.zr_ptr[q + 1] > r.zr_ptr[q];
+    uint32_t act = fr.ent_active[(size_t)slot * g.rank_words + ew];
+    if (has_zr) act |= __reduce_or_sync(FULL, (h >= 0 && (h >> 5) == ew) ? (1u << (h & 31)) : 0u);
+    const int e1 = min(32, N - ew * 32);
+    uint32_t my_bits = 0;                                   // lane i keeps the word of entity ew*32+i
+    for (int i = 0; i < e1; ++i) {
+        if (!((act >> i) & 1u)) continue;
+        const int e = ew * 32 + i;
+        bool any = false;
+        scan_entity<CT>(g, r, arena, abase, mbase, hc0, tp, e, [&](CT c, int) { any |= (c != 0); });
+        if (has_zr && h == e) any = true;
+        const uint32_t bits = __ballot_sync(FULL, any);
+        if (lane == i) my_bits = bits;
+    }
+    if (lane < e1) {
+        nzmask[(size_t)slot * N + ew * 32 + lane] = my_bits;
+        cand_cnt[(size_t)slot * N + ew * 32 + lane] = __popc(my_bits);
+    }
+}
+
+// ------------------------------------------------------------------------------------------
+// pass 2: per-candidate aggregates.  out[C][H] = sum_rule fp32(count) * emb[rule]  (layers.py:68-72);
+// PNA additionally sum of count*emb^2, min / max of emb over rules with count != 0 and their
+// arg-rules (layers.py:94-99), and degree = sum count + 1 (layers.py:92).
+// ------------------------------------------------------------------------------------------
+template <typename CT, bool PNA>
+__global__ void __launch_bounds__(WARPS_PER_BLOCK * 32)
+k_plus_features(rl_graph g, rl_rules r, rl_slots s, rl_frontier fr, const uint32_t *__restrict__ nzmask,
+                const int64_t *__restrict__ cand_off, const int32_t *__restrict__ q_off,
+                const int32_t *__restrict__ rule_local, const float *__restrict__ emb, int H,
+                float *__restrict__ out_sum, float *__restrict__ out_sq, float *__restrict__ out_min,
+                float *__restrict__ out_max, int32_t *__restrict__ arg_min, int32_t *__restrict__ arg_max,
+                float *__restrict__ degree, int64_t *__restrict__ cand_query)
+{
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int slot = blockIdx.y;
+    const int e = blockIdx.x * WARPS_PER_BLOCK + warp;
+    const int N = g.num_entities, R = g.num_relations;
+    if (e >= N) return;
+    const uint32_t bits = nzmask[(size_t)slot * N + e];
+    if (bits == 0u) return;
+    const int q = s.slot_head[slot];
+    const int hc0 = r.lvl_ptr[(size_t)q * (r.max_len + 1)];
+    const uint32_t *mbase = fr.row_mask + (size_t)s.mask_off[slot];
+    const size_t abase = (size_t)s.arena_off[slot];
+    const CT *arena = reinterpret_cast<const CT *>(fr.arena);
+    const int32_t *tp = r.term_ptr + (size_t)q * R;
+    const int h = s.lane_h[slot * RL_LANES + lane];
+    const bool mine = (bits >> lane) & 1u;
+    const long long idx = cand_off[(size_t)slot * N + e] + __popc(bits & ((1u << lane) - 1u));
+    for (int h0 = 0; h0 < H; h0 += HC) {
+        double a1[HC], a2[PNA ? HC : 1];
+        float mn[PNA ? HC : 1], mx[PNA ? HC : 1];
+        int amn[PNA ? HC : 1], amx[PNA ? HC : 1];
+        double deg = 1.0;
+#pragma unroll
+        for (int k = 0; k < HC; ++k) {
+            a1[k] = 0.0;
+            if (PNA) { a2[k] = 0.0; mn[k] = INFINITY; mx[k] = -INFINITY; amn[k] = -1; amx[k] = -1; }
+        }
+        auto add = [&](float cf, int rule) {
+            const int lr = rule_local[rule];
+            const float *er = emb + (size_t)lr * H + h0;
+            deg += (double)cf;
+#pragma unroll
+            for (int k = 0; k < HC; ++k) {
+                if (h0 + k < H) {
+                    const float ev = __ldg(er + k);
+                    a1[k] += (double)cf * (double)ev;
+                    if (PNA) {
+                        a2[k] += (double)cf * (double)(ev * ev);
+                        if (cf != 0.f) {
+                            if (ev < mn[k]) { mn[k] = ev; amn[k] = lr; }
+                            if (ev > mx[k]) { mx[k] = ev; amx[k] = lr; }
+                        }
+                    }
+                }
+            }
+        };
+        scan_entity<CT>(g, r, arena, abase, mbase, hc0, tp, e, [&](CT c, int t) {
+            if (__any_sync(FULL, c != 0)) add((float)c, r.term_rule[t]);
+        });
+        if (h == e)                                            // empty-body rules: count = one_hot(h)
+            for (int t = r.zr_ptr[q]; t < r.zr_ptr[q + 1]; ++t) add(1.f, r.zr_rule[t]);
+        if (mine) {
+#pragma unroll
+            for (int k = 0; k < HC; ++k) {
+                if (h0 + k < H) {
+                    out_sum[idx * H + h0 + k] = (float)a1[k];
+                    if (PNA) {
+                        out_sq[idx * H + h0 + k] = (float)a2[k];
+                        out_min[idx * H + h0 + k] = mn[k];
+                        out_max[idx * H + h0 + k] = mx[k];
+                        arg_min[idx * H + h0 + k] = amn[k];
+                        arg_max[idx * H + h0 + k] = amx[k];
+                    }
+                }
+            }
+            if (h0 == 0) {
+                if (degree) degree[idx] = (float)deg;
+                cand_query[idx] = (int64_t)q_off[slot] + lane;
+            }
+        }
+    }
+}
+
+// ------------------------------------------------------------------------------------------
+// candidate scores -> logits (predictors.py:257-269), and the reverse gather for the backward
+// ------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256)
+k_plus_scatter(int N, const uint32_t *__restrict__ nzmask, const int64_t *__restrict__ cand_off,
+               const float *__restrict__ zc, const float *__restrict__ bias, const float *__restrict__ extra,
+               int fill_neg_inf, float *__restrict__ Z)
+{
+    const int slot = blockIdx.y;
+    const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= (size_t)N * RL_LANES) return;
+    const int e = (int)(i >> 5), lane = (int)(i & 31);
+    const uint32_t bits = nzmask[(size_t)slot * N + e];
+    float z = 0.f;
+    if ((bits >> lane) & 1u) z = zc[cand_off[(size_t)slot * N + e] + __popc(bits & ((1u << lane) - 1u))];
+    else if (fill_neg_inf) z = -INFINITY;
+    if (bias) z += bias[e];
+    if (extra) z += extra[(size_t)slot * N * RL_LANES + i];
+    Z[(size_t)slot * N * RL_LANES + i] = z;
+}
+
+__global__ void __launch_bounds__(256)
+k_plus_gather(int N, const uint32_t *__restrict__ nzmask, const int64_t *__restrict__ cand_off,
+              const float *__restrict__ G, float *__restrict__ dz)
+{
+    const int slot = blockIdx.y;
+    const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= (size_t)N * RL_LANES) return;
+    const int e = (int)(i >> 5), lane = (int)(i & 31);
+    const uint32_t bits = nzmask[(size_t)slot * N + e];
+    if ((bits >> lane) & 1u)
+        dz[cand_off[(size_t)slot * N + e] + __popc(bits & ((1u << lane) - 1u))] = G[(size_t)slot * N * RL_LANES + i];
+}
+
+// ------------------------------------------------------------------------------------------
+// backward into the rule embeddings: gA[rule][h] += sum_cells fp32(count) * dA[cell][h]
+// (and gB from dB for the PNA squared-sum branch).  Block per (slot, rule end).
+// ------------------------------------------------------------------------------------------
+template <typename CT>
+__global__ void __launch_bounds__(128)
+k_plus_backward(rl_graph g, rl_rules r, rl_slots s, rl_frontier fr, const uint32_t *__restrict__ nzmask,
+                const int64_t *__restrict__ cand_off, const int32_t *__restrict__ rule_local, int H,
+                const float *__restrict__ dA, const float *__restrict__ dB, float *__restrict__ gA,
+                float *__restrict__ gB)
+{
+    __shared__ float red[4][2][HC];
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int slot = blockIdx.y;
+    const int N = g.num_entities, R = g.num_relations;
+    const int q = s.slot_head[slot];
+    const uint32_t *ms = nzmask + (size_t)slot * N;
+    const int64_t *co = cand_off + (size_t)slot * N;
+    if (blockIdx.x == 0 && warp == 0 && r.zr_ptr[q + 1] > r.zr_ptr[q]) {   // empty-body rules
+        const int h = s.lane_h[slot * RL_LANES + lane];
+        const uint32_t bits = h >= 0 ? ms[h] : 0u;
+        if ((bits >> lane) & 1u) {
+            const long long idx = co[h] + __popc(bits & ((1u << lane) - 1u));
+            for (int t = r.zr_ptr[q]; t < r.zr_ptr[q + 1]; ++t) {
+                const int lr = rule_local[r.zr_rule[t]];
+                for (int k = 0; k < H; ++k) {
+                    atomicAdd(gA + (size_t)lr * H + k, dA[idx * H + k]);
+                    if (dB) atomicAdd(gB + (size_t)lr * H + k, dB[idx * H + k]);
+                }
+            }
+        }
+    }
+    const int t = r.term_ptr[(size_t)q * R] + blockIdx.x;
+    if (t >= r.term_ptr[(size_t)(q + 1) * R]) return;
+    const int v = r.term_node[t];
+    if (fr.node_cnt[s.nz_off[slot] - r.head_node_ptr[q] + v] == 0) return;
+    const int rho = r.node_rel[v];
+    const int rb = g.dst_ptr[rho], nrows = g.dst_ptr[rho + 1] - rb;
+    const int nw = (nrows + 31) >> 5;
+    const uint32_t *cm = fr.row_mask + (size_t)s.mask_off[slot] + (r.node_chunk0[v] - r.lvl_ptr[(size_t)q * (r.max_len + 1)]);
+    const CT *Xv = reinterpret_cast<const CT *>(fr.arena) + ((size_t)s.arena_off[slot] + r.node_row_off[v]) * RL_LANES;
+    const int lr = rule_local[r.term_rule[t]];
+    for (int h0 = 0; h0 < H; h0 += HC) {
+        float a[HC], b[HC];
+#pragma unroll
+        for (int k = 0; k < HC; ++k) { a[k] = 0.f; b[k] = 0.f; }
+        for (int wi = warp; wi < nw; wi += 4) {
+            uint32_t word = cm[wi];
+            while (word) {
+                const int j = wi * 32 + __ffs(word) - 1;
+                word &= word - 1;
+                const CT c = Xv[(size_t)j * RL_LANES + lane];
+                if (c != 0) {
+                    const int e = __ldg(g.row_dst + rb + j);
+                    const uint32_t bits = ms[e];
+                    const long long idx = co[e] + __popc(bits & ((1u << lane) - 1u));
+                    const float cf = (float)c;
+#pragma unroll
+                    for (int k = 0; k < HC; ++k) {
+                        if (h0 + k < H) {
+                            a[k] += cf * dA[idx * H + h0 + k];
+                            if (dB) b[k] += cf * dB[idx * H + h0 + k];
+                        }
+                    }
+                }
+            }
+        }
+#pragma unroll
+        for (int k = 0; k < HC; ++k) {
+            a[k] = warp_sumf(a[k]);
+            b[k] = warp_sumf(b[k]);
+        }
+        __syncthreads();
+        if (lane == 0) {
+#pragma unroll
+            for (int k = 0; k < HC; ++k) { red[warp][0][k] = a[k]; red[warp][1][k] = b[k]; }
+        }
+        __syncthreads();
+        if (threadIdx.x < HC && h0 + threadIdx.x < H) {
+            const int k = threadIdx.x;
+            const float ta = red[0][0][k] + red[1][0][k] + red[2][0][k] + red[3][0][k];
+            if (ta != 0.f) atomicAdd(gA + (size_t)lr * H + h0 + k, ta);
+            if (dB) {
+                const float tb = red[0][1][k] + red[1][1][k] + red[2][1][k] + red[3][1][k];
+                if (tb != 0.f) atomicAdd(gB + (size_t)lr * H + h0 + k, tb);
+            }
+        }
+    }
+}
+
+// ------------------------------------------------------------------------------------------
+// C-ABI
+// ------------------------------------------------------------------------------------------
+static int bad_frontier(const rl_frontier *fr)
+{
+    return !fr || !fr->arena || !fr->row_mask || !fr->node_cnt || !fr->ent_active ||
+           (fr->count_bits != 32 && fr->count_bits != 64);
+}
+
+extern "C" {
+
+int rl_plus_mask(const rl_graph *g, const rl_rules *r, const rl_slots *s, const rl_frontier *fr, uint32_t *nzmask,
+                 int32_t *cand_cnt, void *stream)
+{
+    if (!g || !r || !s || !nzmask || !cand_cnt || bad_frontier(fr)) return rl_fail(RL_ERR_ARG, "rl_plus_mask: bad argument");
+    if (s->num_slots <= 0) return RL_OK;
+    dim3 grid((g->rank_words + WARPS_PER_BLOCK - 1) / WARPS_PER_BLOCK, s->num_slots);
+    cudaStream_t st = (cudaStream_t)stream;
+    if (fr->count_bits == 32) k_plus_mask<uint32_t><<<grid, WARPS_PER_BLOCK * 32, 0, st>>>(*g, *r, *s, *fr, nzmask, cand_cnt);
+    else k_plus_mask<unsigned long long><<<grid, WARPS_PER_BLOCK * 32, 0, st>>>(*g, *r, *s, *fr, nzmask, cand_cnt);
+    CHECK_LAUNCH("k_plus_mask");
+    return RL_OK;
+}
+
+int rl_plus_features(const rl_graph *g, const rl_rules *r, const rl_slots *s, const rl_frontier *fr,
+                     const uint32_t *nzmask, const int64_t *cand_off, const int32_t *q_off, const int32_t *rule_local,
+                     const float *emb, int32_t H, int32_t pna, float *out_sum, float *out_sq, float *out_min,
+                     float *out_max, int32_t *arg_min, int32_t *arg_max, float *degree, int64_t *cand_query,
+                     void *stream)
+{
+    if (!g || !r || !s || !nzmask || !cand_off || !q_off || !rule_local || !emb || !out_sum || !cand_query || bad_frontier(fr) || H <= 0)
+        return rl_fail(RL_ERR_ARG, "rl_plus_features: bad argument");
+    if (pna && (!out_sq || !out_min || !out_max || !arg_min || !arg_max || !degree))
+        return rl_fail(RL_ERR_ARG, "rl_plus_features: PNA outputs missing");
+    if (s->num_slots <= 0) return RL_OK;
+    dim3 grid((g->num_entities + WARPS_PER_BLOCK - 1) / WARPS_PER_BLOCK, s->num_slots);
+    cudaStream_t st = (cudaStream_t)stream;
+#define LAUNCH_FEAT(CT, P) k_plus_features<CT, P><<<grid, WARPS_PER_BLOCK * 32, 0, st>>>(*g, *r, *s, *fr, nzmask, cand_off, q_off, rule_local, emb, H, out_sum, out_sq, out_min, out_max, arg_min, arg_max, degree, cand_query)
+    if (fr->count_bits == 32) { if (pna) LAUNCH_FEAT(uint32_t, true); else LAUNCH_FEAT(uint32_t, false); }
+    else { if (pna) LAUNCH_FEAT(unsigned long long, true); else LAUNCH_FEAT(unsigned long long, false); }
+#undef LAUNCH_FEAT
+    CHECK_LAUNCH("k_plus_features");
+    return RL_OK;
+}
+
+int rl_plus_scatter(const rl_graph *g, const rl_slots *s, const uint32_t *nzmask, const int64_t *cand_off,
+                    const float *zc, const float *bias, const float *extra, int32_t fill_neg_inf, float *Z, void *stream)
+{
+    if (!g || !s || !nzmask || !cand_off || !zc || !Z) return rl_fail(RL_ERR_ARG, "rl_plus_scatter: null argument");
+    if (s->num_slots <= 0) return RL_OK;
+    const size_t n = (size_t)g->num_entities * RL_LANES;
+    k_plus_scatter<<<dim3((unsigned)((n + 255) / 256), s->num_slots), 256, 0, (cudaStream_t)stream>>>(
+        g->num_entities, nzmask, cand_off, zc, bias, extra, fill_neg_inf, Z);
+    CHECK_LAUNCH("k_plus_scatter");
+    return RL_OK;
+}
+
+int rl_plus_gather(const rl_graph *g, const rl_slots *s, const uint32_t *nzmask, const int64_t *cand_off,
+                   const float *G, float *dz, void *stream)
+{
+    if (!g || !s || !nzmask || !cand_off || !G || !dz) return rl_fail(RL_ERR_ARG, "rl_plus_gather: null argument");
+    if (s->num_slots <= 0) return RL_OK;
+    const size_t n = (size_t)g->num_entities * RL_LANES;
+    k_plus_gather<<<dim3((unsigned)((n + 255) / 256), s->num_slots), 256, 0, (cudaStream_t)stream>>>(
+        g->num_entities, nzmask, cand_off, G, dz);
+    CHECK_LAUNCH("k_plus_gather");
+    return RL_OK;
+}
+
+int rl_plus_backward(const rl_graph *g, const rl_rules *r, const rl_slots *s, const rl_frontier *fr,
+                     const uint32_t *nzmask, const int64_t *cand_off, const int32_t *rule_local, int32_t H,
+                     const float *dA, const float *dB, int32_t max_terms, float *gA, float *gB, void *stream)
+{
+    if (!g || !r || !s || !nzmask || !cand_off || !rule_local || !dA || !gA || bad_frontier(fr) || H <= 0 || (dB && !gB))
+        return rl_fail(RL_ERR_ARG, "rl_plus_backward: bad argument");
+    if (s->num_slots <= 0) return RL_OK;
+    dim3 grid(max_terms > 0 ? max_terms : 1, s->num_slots);
+    cudaStream_t st = (cudaStream_t)stream;
+    if (fr->count_bits == 32) k_plus_backward<uint32_t><<<grid, 128, 0, st>>>(*g, *r, *s, *fr, nzmask, cand_off, rule_local, H, dA, dB, gA, gB);
+    else k_plus_backward<unsigned long long><<<grid, 128, 0, st>>>(*g, *r, *s, *fr, nzmask, cand_off, rule_local, H, dA, dB, gA, gB);
+    CHECK_LAUNCH("k_plus_backward");
+    return RL_OK;
+}
+
+}  // extern "C"

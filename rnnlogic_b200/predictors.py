@@ -238,3 +238,273 @@ def _valid_lanes(sl, LH):
 Predictor.fused_train_step = _predictor_fused_train
 Predictor.step_on_slots = _predictor_step_on_slots
 Predictor.fused_rank = _predictor_fused_rank
+
+
+# ================================================================================================
+# PredictorPlus (src/predictors.py:121-271)
+# ================================================================================================
+from .layers import MLP, FuncToNode, FuncToNodeSum  # noqa: E402
+from .engine import _stream  # noqa: E402
+
+
+class _PlusCtx:
+    """Everything the PredictorPlus kernels of one call share."""
+
+    def __init__(self, sk, sl, H, pna):
+        self.sk, self.sl, self.H, self.pna = sk, sl, H, pna
+        dev = sk.device
+        N, S = sk.N, sl.S
+        self.nzmask = torch.empty(S, N, dtype=torch.int32, device=dev)
+        cand_cnt = torch.empty(S * N, dtype=torch.int32, device=dev)
+        _lib.check(_lib.lib().rl_plus_mask(sk.dg.ref(), sk.dr.ref(), sl.ref(), sl.fref(), self.nzmask.data_ptr(),
+                                           cand_cnt.data_ptr(), _stream()), "rl_plus_mask")
+        csum = torch.cumsum(cand_cnt, 0, dtype=torch.int64)
+        self.cand_off = (csum - cand_cnt).contiguous()
+        self.C = int(csum[-1].item())                     # host sync, as torch.nonzero in predictors.py:239
+        self.rule_local = None
+        self.arg_min = self.arg_max = None
+
+
+class _PlusAggregateFn(torch.autograd.Function):
+    """emb[n,H] -> per-candidate statistics (kernel rl_plus_features) with the backward into emb
+    (kernel rl_plus_backward).  sum: (F,) ; pna: (S1, S2, MN, MX)."""
+
+    @staticmethod
+    def forward(ctx, emb, pc):
+        sk, sl, H, C = pc.sk, pc.sl, pc.H, pc.C
+        dev = emb.device
+        embc = emb.detach().contiguous().float()
+        n_out = 4 if pc.pna else 1
+        out = torch.empty(n_out, C, H, dtype=torch.float32, device=dev)
+        pc.cand_query = torch.empty(C, dtype=torch.int64, device=dev)
+        pc.degree = torch.empty(C, dtype=torch.float32, device=dev) if pc.pna else None
+        if pc.pna:
+            pc.arg_min = torch.empty(C, H, dtype=torch.int32, device=dev)
+            pc.arg_max = torch.empty(C, H, dtype=torch.int32, device=dev)
+        _lib.check(_lib.lib().rl_plus_features(
+            sk.dg.ref(), sk.dr.ref(), sl.ref(), sl.fref(), pc.nzmask.data_ptr(), pc.cand_off.data_ptr(),
+            sl.q_off_dev.data_ptr(), pc.rule_local.data_ptr(), embc.data_ptr(), H, int(pc.pna),
+            out[0].data_ptr(), out[1].data_ptr() if pc.pna else None, out[2].data_ptr() if pc.pna else None,
+            out[3].data_ptr() if pc.pna else None, pc.arg_min.data_ptr() if pc.pna else None,
+            pc.arg_max.data_ptr() if pc.pna else None, pc.degree.data_ptr() if pc.pna else None,
+            pc.cand_query.data_ptr(), _stream()), "rl_plus_features")
+        ctx.pc = pc
+        ctx.save_for_backward(embc)
+        return tuple(out[i] for i in range(n_out))
+
+    @staticmethod
+    def backward(ctx, *grads):
+        pc = ctx.pc
+        (embc,) = ctx.saved_tensors
+        sk, sl, H = pc.sk, pc.sl, pc.H
+        dA = grads[0].contiguous().float()
+        dB = grads[1].contiguous().float() if pc.pna else None
+        gA = torch.zeros_like(embc)
+        gB = torch.zeros_like(embc) if pc.pna else None
+        max_terms = int(sk.cr.head_terms[sl.heads].max())
+        _lib.check(_lib.lib().rl_plus_backward(
+            sk.dg.ref(), sk.dr.ref(), sl.ref(), sl.fref(), pc.nzmask.data_ptr(), pc.cand_off.data_ptr(),
+            pc.rule_local.data_ptr(), H, dA.data_ptr(), dB.data_ptr() if dB is not None else None, max_terms,
+            gA.data_ptr(), gB.data_ptr() if gB is not None else None, _stream()), "rl_plus_backward")
+        g = gA
+        if pc.pna:
+            g = g + 2.0 * embc * gB                       # d/d emb of sum count * emb^2
+            cols = torch.arange(H, device=g.device).unsqueeze(0)
+            flat = g.view(-1)
+            for arg, dv in ((pc.arg_min, grads[2]), (pc.arg_max, grads[3])):   # min/max route to their arg rule
+                flat.index_add_(0, (arg.long() * H + cols).view(-1), dv.contiguous().view(-1).float())
+        return g, None
+
+
+class _PlusScatterFn(torch.autograd.Function):
+    """candidate scores (+ bias, + entity-feature logits) -> entity-major logits Z[S][N][32]."""
+
+    @staticmethod
+    def forward(ctx, zc, bias, extra, pc, fill_neg_inf):
+        sk, sl = pc.sk, pc.sl
+        Z = torch.empty(sl.S, sk.N, LANES, dtype=torch.float32, device=sk.device)
+        zcc = zc.detach().contiguous().float() if zc is not None else torch.zeros(1, device=sk.device)
+        _lib.check(_lib.lib().rl_plus_scatter(
+            sk.dg.ref(), sl.ref(), pc.nzmask.data_ptr(), pc.cand_off.data_ptr(), zcc.data_ptr(),
+            bias.detach().contiguous().data_ptr() if bias is not None else None,
+            extra.detach().contiguous().data_ptr() if extra is not None else None, int(fill_neg_inf),
+            Z.data_ptr(), _stream()), "rl_plus_scatter")
+        ctx.pc = pc
+        ctx.flags = (zc is not None, bias is not None, extra is not None)
+        return Z
+
+    @staticmethod
+    def backward(ctx, G):
+        pc = ctx.pc
+        sk, sl = pc.sk, pc.sl
+        has_z, has_b, has_x = ctx.flags
+        G = G.contiguous()
+        dz = db = None
+        if has_z:
+            dz = torch.zeros(max(1, pc.C), dtype=torch.float32, device=G.device)
+            _lib.check(_lib.lib().rl_plus_gather(sk.dg.ref(), sl.ref(), pc.nzmask.data_ptr(), pc.cand_off.data_ptr(),
+                                                 G.data_ptr(), dz.data_ptr(), _stream()), "rl_plus_gather")
+            dz = dz[:pc.C]
+        if has_b:
+            # NaN-safe: cells filled with -inf never coexist with a bias (mask mode has none)
+            db = G.sum(dim=(0, 2))
+        return dz, db, (G if has_x else None), None, None
+
+
+class _ToDenseFn(torch.autograd.Function):
+    """entity-major Z[S][N][32] -> the reference's [B,N] layout (and back for the gradient)."""
+
+    @staticmethod
+    def forward(ctx, Z, nzmask, sk, sl):
+        score, nz = sk.to_dense(sl, Z.contiguous(), nzmask)
+        ctx.sk, ctx.sl = sk, sl
+        ctx.mark_non_differentiable(nz)
+        return score, nz
+
+    @staticmethod
+    def backward(ctx, gscore, _gnz):
+        return ctx.sk.from_dense(ctx.sl, gscore.contiguous()), None, None, None
+
+
+class PredictorPlus(_RuleModel):
+    def __init__(self, graph, type='emb', num_layers=3, hidden_dim=16, entity_feature='bias', aggregator='sum',
+                 embedding_path=None):
+        super(PredictorPlus, self).__init__()
+        self.graph = graph
+        self.type = type
+        self.num_layers = num_layers
+        self.hidden_dim = hidden_dim
+        self.entity_feature = entity_feature
+        self.aggregator = aggregator
+        self.embedding_path = embedding_path
+        self.num_entities = graph.entity_size
+        self.num_relations = graph.relation_size
+        self.padding_index = graph.relation_size
+        self.vocab_emb = torch.nn.Embedding(self.num_relations + 1, self.hidden_dim, padding_idx=self.num_relations)
+        if self.type == 'lstm':
+            self.rnn = torch.nn.LSTM(self.hidden_dim, self.hidden_dim, self.num_layers, batch_first=True)
+        elif self.type == 'gru':
+            self.rnn = torch.nn.GRU(self.hidden_dim, self.hidden_dim, self.num_layers, batch_first=True)
+        elif self.type == 'rnn':
+            self.rnn = torch.nn.RNN(self.hidden_dim, self.hidden_dim, self.num_layers, batch_first=True)
+        elif self.type == 'emb':
+            self.rule_emb = None
+        else:
+            raise NotImplementedError
+        if aggregator == 'sum':
+            self.rule_to_entity = FuncToNodeSum(self.hidden_dim)
+        elif aggregator == 'pna':
+            self.rule_to_entity = FuncToNode(self.hidden_dim)
+        else:
+            raise NotImplementedError
+        self.relation_emb = torch.nn.Embedding(self.num_relations, self.hidden_dim)
+        self.score_model = MLP(self.hidden_dim * 2, [128, 1])
+        if entity_feature == 'bias':
+            self.bias = torch.nn.parameter.Parameter(torch.zeros(self.num_entities))
+        elif entity_feature == 'RotatE':
+            from .embedding import RotatE
+            self.RotatE = RotatE(embedding_path)
+
+    def set_rules(self, input):
+        self._load_rules(input, "Predictor+")
+        self.max_length = max([len(rule[1]) for rule in self.rules])
+        feats = [[h] + list(b) + [self.padding_index] * (self.max_length - len(b)) for h, b in self.rules]
+        self.rule_features = torch.tensor(feats, dtype=torch.long)
+        if self.type == 'emb':
+            dev = self.relation_emb.weight.device
+            self.rule_emb = nn.parameter.Parameter(torch.zeros(self.num_rules, self.hidden_dim, device=dev))
+            nn.init.kaiming_uniform_(self.rule_emb, a=math.sqrt(5), mode="fan_in")
+
+    def encode_rules(self, rule_features):
+        """predictors.py:201-208: embed [head, body..., pad], run the RNN, take the last non-pad output."""
+        rule_masks = rule_features != self.num_relations
+        x = self.vocab_emb(rule_features)
+        output, hidden = self.rnn(x)
+        idx = (rule_masks.sum(-1) - 1).long()
+        idx = idx.unsqueeze(-1).unsqueeze(-1).expand(-1, -1, self.hidden_dim)
+        return torch.gather(output, 1, idx).squeeze(1)
+
+    # ---- shared by the API forward and the fused trainer paths ---------------------------------
+    def _logits(self, sk, sl):
+        """Z[S][N][32] (autograd-connected to every parameter), nzmask[S][N]."""
+        device = sk.device
+        H = self.hidden_dim
+        ef = self.entity_feature
+        pc = _PlusCtx(sk, sl, H, self.aggregator == 'pna')
+        zc = None
+        if pc.C > 0:
+            heads = sorted(set(int(h) for h in sl.heads))
+            rule_ids = torch.tensor([i for q in heads for i in self.compiled.head_rules[q]], dtype=torch.long,
+                                    device=device)
+            pc.rule_local = torch.full((self.num_rules,), -1, dtype=torch.int32, device=device)
+            pc.rule_local[rule_ids] = torch.arange(rule_ids.numel(), dtype=torch.int32, device=device)
+            if self.type == 'emb':
+                emb = self.rule_emb[rule_ids]
+            else:
+                if self.rule_features.device != device:
+                    self.rule_features = self.rule_features.to(device)
+                emb = self.encode_rules(self.rule_features[rule_ids])
+            stats = _PlusAggregateFn.apply(emb, pc)
+            if self.aggregator == 'sum':
+                out = self.rule_to_entity.post(stats[0])
+            else:
+                out = self.rule_to_entity.post(stats[0], stats[1], stats[2], stats[3], pc.degree, pc.cand_query,
+                                               int(sl.q_off[-1]))
+            qhead = torch.from_numpy(np.repeat(sl.heads, sl.nq)).to(device)
+            rel = self.relation_emb(qhead[pc.cand_query])
+            zc = self.score_model(torch.cat([out, rel], dim=-1)).squeeze(-1)
+        bias = self.bias if ef == 'bias' else None
+        extra = self.RotatE.slot_scores(sk, sl) if ef == 'RotatE' else None
+        Z = _PlusScatterFn.apply(zc, bias, extra, pc, ef not in ('bias', 'RotatE'))
+        return Z, pc
+
+    def forward(self, all_h, all_r, edges_to_remove):
+        query_r, sk, sl = self._ground(all_h, all_r, edges_to_remove)
+        Z, pc = self._logits(sk, sl)
+        score, nz = _ToDenseFn.apply(Z, pc.nzmask, sk, sl)
+        dense_feature = self.entity_feature in ('bias', 'RotatE')
+        if pc.C == 0 and not dense_feature:                              # predictors.py:236-237
+            return torch.full_like(score, float("inf")), torch.zeros_like(nz)
+        if dense_feature:
+            return score, torch.ones_like(nz)
+        return score, nz
+
+
+def _plus_fused_train(self, batches, smoothing, grad_scale=1.0):
+    """Fused train step for PredictorPlus: CUDA grounding / aggregation / CE, torch autograd only for
+    the small dense tail (rule encoder, Linear/LayerNorm/MLP on the C candidate rows)."""
+    device = self.relation_emb.weight.device
+    sk = self._driver(device)
+    use_mask = self.entity_feature not in ('bias', 'RotatE')
+    sl = sk.gr.make_slots_host(batches, with_etr=True)
+    sl.use_workspace = False          # autograd keeps the frontier until backward
+    gptr, ng = _group_ptr(sl, device)
+    sk.gr.ground(sl)
+    Z, pc = self._logits(sk, sl)
+    loss, tsum, G = sk.softmax_ce(sl, Z.detach(), pc.nzmask, smoothing, use_mask, gptr, ng, want_grad=True)
+    if grad_scale != 1.0:
+        G = G * grad_scale
+    if Z.requires_grad:
+        Z.backward(G)
+    parts = [loss, tsum] + ([_group_mask_sum(sl, pc.nzmask, ng)] if use_mask else [])
+    host = torch.cat(parts).cpu()
+    self.last_h2d_bytes = sl.h2d_bytes
+    self.last_d2h_bytes = int(host.numel() * 4) + 8
+    self.last_mask_sum = host[2 * ng:3 * ng].tolist() if use_mask else None
+    return host[:ng], host[ng:2 * ng]
+
+
+@torch.no_grad()
+def _plus_fused_rank(self, batches, split):
+    device = self.relation_emb.weight.device
+    sk = self._driver(device)
+    use_mask = self.entity_feature not in ('bias', 'RotatE')
+    sl = sk.gr.make_slots_host(batches, with_etr=False)
+    sk.gr.ground(sl)
+    Z, pc = self._logits(sk, sl)
+    LH = sk.filtered_rank(sl, Z.contiguous(), pc.nzmask, "hr2oo" if split == "valid" else "hr2ooo", use_mask)
+    return _valid_lanes(sl, LH)
+
+
+PredictorPlus.fused_train_step = _plus_fused_train
+PredictorPlus.fused_rank = _plus_fused_rank

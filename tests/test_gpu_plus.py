@@ -1,0 +1,138 @@
+"""GPU parity of PredictorPlus (emb/lstm/gru/rnn x sum/pna x bias/none/RotatE) against the
+reference's golden outputs: scores rtol 1e-4 (the reference itself sums [C,R_q,H] broadcasts in a
+different order), loss rtol 1e-5, every parameter gradient rtol 1e-3."""
+import numpy as np
+import pytest
+import torch
+
+from tests import _golden as G
+
+pytestmark = pytest.mark.gpu
+DEV = "cuda:0"
+
+
+def make_kg(fx):
+    from rnnlogic_b200 import KnowledgeGraph
+    return KnowledgeGraph(entity_size=int(fx["N"]), relation_size=int(fx["R"]), train=fx["train"],
+                          valid=fx["valid"], test=fx["test"])
+
+
+def make_model(fx, kg, tag, tmp_path):
+    from rnnlogic_b200.predictors import PredictorPlus
+    cfg = G.plus_cfg(fx, tag)
+    kw = dict(type=cfg["type"], num_layers=cfg["num_layers"], hidden_dim=16, entity_feature=cfg["entity_feature"],
+              aggregator=cfg["aggregator"])
+    sd = G.plus_state(fx, tag)
+    if cfg["entity_feature"] == "RotatE":
+        import json
+        d = tmp_path / ("rot_" + tag)
+        d.mkdir(exist_ok=True)
+        D = sd["RotatE.remb"].shape[1]
+        np.save(d / "entity_embedding.npy", sd["RotatE.eemb"].numpy())
+        np.save(d / "relation_embedding.npy", sd["RotatE.remb"].numpy()[: sd["RotatE.remb"].shape[0] // 2])
+        (d / "config.json").write_text(json.dumps({"hidden_dim": D, "gamma": cfg["gamma"], "nentity": kg.entity_size}))
+        kw["embedding_path"] = str(d)
+    m = PredictorPlus(kg, **kw)
+    m.set_rules(G.rules_of(fx))
+    missing, unexpected = m.load_state_dict(sd, strict=True)
+    return m.cuda(), cfg
+
+
+def ref_loss(score, mask, target, all_t, smoothing=0.2):
+    tgt = target * smoothing + torch.nn.functional.one_hot(all_t, target.shape[1]) * (1 - smoothing)
+    lp = (torch.softmax(score, dim=1) + 1e-8).log()
+    return -(lp[mask] * tgt[mask]).sum() / torch.clamp(tgt[mask].sum(), min=1)
+
+
+def check_grads(m, fx, tag, j, name):
+    seen = 0
+    for pn, par in m.named_parameters():
+        key = "%s_tb%d_g_%s" % (tag, j, pn)
+        if key in fx:
+            assert par.grad is not None, pn
+            want = fx[key]
+            scale = max(1e-6, float(np.abs(want).max()))
+            np.testing.assert_allclose(par.grad.cpu().numpy(), want, rtol=1e-3, atol=3e-4 * scale,
+                                       err_msg="%s %s tb%d %s" % (name, tag, j, pn))
+            seen += 1
+    assert seen >= 4
+
+
+@pytest.fixture(scope="module", params=G.DATASETS)
+def ds(request):
+    fx = G.load(request.param)
+    return request.param, fx, make_kg(fx)
+
+
+def variant_tags(fx, rotate):
+    return [t for t in G.plus_tags(fx) if (G.plus_cfg(fx, t)["entity_feature"] == "RotatE") == rotate]
+
+
+@pytest.mark.parametrize("rotate", [False, True])
+def test_forward_loss_autograd(ds, tmp_path, rotate):
+    name, fx, kg = ds
+    tags = variant_tags(fx, rotate)
+    if not tags:
+        pytest.skip("no such variant in this fixture")
+    for tag in tags:
+        m, cfg = make_model(fx, kg, tag, tmp_path)
+        for j in range(3):
+            if "%s_tb%d_score" % (tag, j) not in fx:
+                continue
+            tri, target, etr = G.train_batch_inputs(fx, j)
+            tri_t = torch.from_numpy(tri).to(DEV)
+            m.zero_grad()
+            score, mask = m(tri_t[:, 0], tri_t[:, 1], etr.to(DEV))
+            assert np.array_equal(mask.cpu().numpy(), fx["%s_tb%d_mask" % (tag, j)]), (name, tag, j)
+            np.testing.assert_allclose(score.detach().cpu().numpy(), fx["%s_tb%d_score" % (tag, j)], rtol=1e-4, atol=1e-5,
+                                       err_msg="%s %s %d" % (name, tag, j))
+            if "%s_tb%d_loss" % (tag, j) in fx:
+                loss = ref_loss(score, mask, target.to(DEV), tri_t[:, 2])
+                loss.backward()
+                np.testing.assert_allclose(loss.item(), fx["%s_tb%d_loss" % (tag, j)], rtol=1e-5)
+                check_grads(m, fx, tag, j, name)
+        for j in range(2):
+            key = "%s_vb%d_score" % (tag, j)
+            if key not in fx:
+                continue
+            tri, flag = G.valid_batch_inputs(fx, j)
+            tri_t = torch.from_numpy(tri).to(DEV)
+            with torch.no_grad():
+                score, mask = m(tri_t[:, 0], tri_t[:, 1], None)
+            assert np.array_equal(mask.cpu().numpy(), fx["%s_vb%d_mask" % (tag, j)])
+            np.testing.assert_allclose(score.cpu().numpy(), fx[key], rtol=1e-4, atol=1e-5)
+
+
+@pytest.mark.parametrize("rotate", [False, True])
+def test_fused_train_step(ds, tmp_path, rotate):
+    name, fx, kg = ds
+    tags = variant_tags(fx, rotate)
+    if not tags:
+        pytest.skip("no such variant in this fixture")
+    for tag in tags:
+        m, cfg = make_model(fx, kg, tag, tmp_path)
+        for j in range(3):
+            if "%s_tb%d_loss" % (tag, j) not in fx:
+                continue
+            tri, _, _ = G.train_batch_inputs(fx, j)
+            m.zero_grad()
+            loss, tsum = m.fused_train_step([[tuple(x) for x in tri.tolist()]], 0.2)
+            np.testing.assert_allclose(loss[0].item(), fx["%s_tb%d_loss" % (tag, j)], rtol=1e-5)
+            check_grads(m, fx, tag, j, name)
+
+
+def test_layers_reference_signature():
+    """FuncToNodeSum / FuncToNode keep forward(A_fn, x_f, b_n) (layers.py:63,89)."""
+    from rnnlogic_b200.layers import FuncToNode, FuncToNodeSum
+    from oracle import rnnlogic_oracle as O
+    torch.manual_seed(0)
+    A = (torch.rand(7, 11) < 0.4).float() * torch.randint(1, 5, (7, 11)).float()
+    A[:, A.sum(0) == 0] = 1.0
+    x = torch.randn(7, 16)
+    b_n = torch.tensor([0, 0, 1, 1, 1, 2, 2, 2, 2, 3, 3])
+    for cls, fn in ((FuncToNodeSum, lambda p: O.agg_sum(A, x, p)), (FuncToNode, lambda p: O.agg_pna(A, x, b_n, p))):
+        mod = cls(16)
+        p = {"rule_to_entity." + k: v for k, v in mod.state_dict().items()}
+        want = fn(p)
+        got = mod.cuda()(A.cuda(), x.cuda(), b_n.cuda()).cpu()
+        np.testing.assert_allclose(got.detach().numpy(), want.detach().numpy(), rtol=1e-4, atol=1e-5)
