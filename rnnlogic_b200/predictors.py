@@ -381,6 +381,10 @@ class PredictorPlus(_RuleModel):
         self.num_relations = graph.relation_size
         self.padding_index = graph.relation_size
         self.vocab_emb = torch.nn.Embedding(self.num_relations + 1, self.hidden_dim, padding_idx=self.num_relations)
+        if self.type in ('lstm', 'gru', 'rnn'):
+            # cuDNN RNNs default to TF32 matmuls (forward AND backward); the rule encoder must stay in
+            # true fp32 for the 1e-5 parity bar, and the backward runs outside any context manager
+            torch.backends.cudnn.allow_tf32 = False
         if self.type == 'lstm':
             self.rnn = torch.nn.LSTM(self.hidden_dim, self.hidden_dim, self.num_layers, batch_first=True)
         elif self.type == 'gru':
