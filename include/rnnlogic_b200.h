@@ -247,6 +247,18 @@ int rl_plus_backward(const rl_graph *g, const rl_rules *r, const rl_slots *s, co
                      const uint32_t *nzmask, const int64_t *cand_off, const int32_t *rule_local, int32_t H,
                      const float *dA, const float *dB, int32_t max_terms, float *gA, float *gB, void *stream);
 
+/* ---- RotatE entity feature (src/embedding.py:28-70) -----------------------------------------
+ * out[S][N][32] = gamma - sum_d |h_b o rot(remb[head]) - e|_d for every entity e; eemb fp32[N][2D]
+ * (re | im), remb fp32[R][D] (already doubled with the negated copy, embedding.py:23-26).
+ * P is scratch [S][2D][32] (the projected heads, kept for the backward). */
+int rl_rotate_scores(const rl_graph *g, const rl_slots *s, int32_t D, float gamma, const float *eemb,
+                     const float *remb, float *P, float *out, void *stream);
+/* Backward of rl_rotate_scores for G[S][N][32] = d loss / d out: ACCUMULATES into d_eemb[N][2D] and
+ * d_remb[R][D]; dP is zeroed scratch [S][2D][32]. */
+int rl_rotate_backward(const rl_graph *g, const rl_slots *s, int32_t D, float gamma, const float *eemb,
+                       const float *remb, const float *P, const float *G, float *dP, float *d_eemb,
+                       float *d_remb, void *stream);
+
 /* Entity-major <-> reference layout: out[b][e] = Z[slot][e][b] for b < nq (fp32 [nq][N]). */
 int rl_slot_to_dense(int32_t N, int32_t nq, const float *Z_slot, float *out, int64_t out_stride,
                      void *stream);
