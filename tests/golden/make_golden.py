@@ -166,7 +166,7 @@ def pick_batches(ds, n, seed):
 
 
 def sd_to_np(sd):
-    return {k: v.detach().cpu().numpy() for k, v in sd.items()}
+    return {k: v.detach().cpu().numpy().copy() for k, v in sd.items()}     # copy: parameters are trained in place later
 
 
 def main():
