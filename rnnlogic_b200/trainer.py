@@ -33,6 +33,28 @@ def shard_indices(n_items, world_size, rank, shuffle=True, seed=0, epoch=0):
     return list(iter(sampler))
 
 
+def allreduce_mean_grads(params, world_size):
+    """The path's one collective: a single flat all-reduce of every gradient, then / world_size
+    (DDP mean semantics, trainer.py:56-60).  A usage flag per parameter rides along so that a
+    parameter no rank used keeps grad=None (find_unused_parameters=True behaviour)."""
+    if world_size == 1 or not params:
+        return
+    device = params[0].device
+    used = torch.tensor([0.0 if p.grad is None else 1.0 for p in params], device=device)
+    flat = torch.cat([(p.grad if p.grad is not None else torch.zeros_like(p)).reshape(-1).float() for p in params]
+                     + [used])
+    comm.all_reduce_sum_(flat)
+    n_par = len(params)
+    flat[:-n_par] /= world_size
+    used = flat[-n_par:].cpu().tolist()
+    off = 0
+    for p, u in zip(params, used):
+        n = p.numel()
+        if u > 0:
+            p.grad = flat[off:off + n].view_as(p).clone()
+        off += n
+
+
 class TrainerPredictor(object):
     slots_per_step = 1      # train batches per optimizer step (1 = the reference's schedule)
     eval_batches_per_call = 64
@@ -68,22 +90,8 @@ class TrainerPredictor(object):
         self.optimizer = optimizer
         self.scheduler = scheduler
 
-    # ---- gradient exchange: one flat all-reduce (mean), unused parameters stay None -------------
     def _allreduce_grads(self):
-        if self.world_size == 1:
-            return
-        params = [p for p in self.model.parameters() if p.requires_grad]
-        used = torch.tensor([0.0 if p.grad is None else 1.0 for p in params], device=self.device)
-        flat = torch.cat([(p.grad if p.grad is not None else torch.zeros_like(p)).reshape(-1) for p in params] + [used])
-        comm.all_reduce_sum_(flat)
-        flat[:-len(params)] /= self.world_size
-        used = flat[-len(params):].cpu()
-        off = 0
-        for p, u in zip(params, used.tolist()):
-            n = p.numel()
-            if u > 0:
-                p.grad = flat[off:off + n].view_as(p).clone()
-            off += n
+        allreduce_mean_grads([p for p in self.model.parameters() if p.requires_grad], self.world_size)
 
     def train(self, batch_per_epoch, smoothing, print_every):
         if comm.get_rank() == 0:

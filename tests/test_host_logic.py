@@ -1,0 +1,178 @@
+"""CPU tests (no GPU): the C-ABI library loads and exports every symbol the header declares, the
+host-side graph / rule compilers build what the kernels expect, and the multi-process pieces
+(batch sharding, flat gradient all-reduce, rank-row gather) work at world size 2 over gloo."""
+import os
+import re
+
+import numpy as np
+import pytest
+import torch
+
+from tests import _golden as G
+
+
+def test_cabi_library_exports_every_declared_symbol():
+    from rnnlogic_b200 import _lib
+    import ctypes
+    header = open(os.path.join(G.ROOT, "include", "rnnlogic_b200.h")).read()
+    header = re.sub(r"/\*.*?\*/", "", header, flags=re.S)
+    declared = set(re.findall(r"\b(rl_[a-z0-9_]+)\s*\(", header))
+    assert len(declared) >= 20
+    assert os.path.exists(_lib.LIB_PATH), "build with __graft_entry__.build()"
+    L = ctypes.CDLL(_lib.LIB_PATH)
+    for name in sorted(declared):
+        assert hasattr(L, name), "missing export " + name
+    assert declared == set(_lib.exported_symbols()), declared ^ set(_lib.exported_symbols())
+    assert _lib.lib().rl_abi_version() == 1
+    if not torch.cuda.is_available():           # no compute without a GPU -- and no silent fallback
+        assert _lib.lib().rl_device_count() < 0
+        assert b"no CPU fallback" in _lib.lib().rl_last_error()
+
+
+def brute_rows(train, R):
+    rows = {}
+    for h, r, t in train.tolist():
+        rows.setdefault((r, t), []).append(h)
+    return rows
+
+
+@pytest.mark.parametrize("name", G.DATASETS)
+def test_graph_dcsr_matches_brute_force(name):
+    from rnnlogic_b200 import KnowledgeGraph
+    fx = G.load(name)
+    N, R = int(fx["N"]), int(fx["R"])
+    kg = KnowledgeGraph(entity_size=N, relation_size=R, train=fx["train"], valid=fx["valid"], test=fx["test"])
+    H = kg.host
+    rows = brute_rows(fx["train"].astype(np.int64), R)
+    W = kg.rank_words
+    rank = H["rank_tab"].reshape(R * W, 2)
+    srank = H["srank_tab"].reshape(R * W, 2)
+    assert H["row_dst"].shape[0] == len(rows)
+    for r in range(R):
+        for k in range(H["dst_ptr"][r], H["dst_ptr"][r + 1]):
+            t = int(H["row_dst"][k])
+            srcs = H["edge_src"][H["row_start"][k]:H["row_start"][k + 1]].tolist()
+            assert sorted(srcs) == sorted(rows[(r, t)])
+            bits, pre = rank[r * W + (t >> 5)]
+            assert (int(bits) >> (t & 31)) & 1
+            assert int(pre) + bin(int(bits) & ((1 << (t & 31)) - 1)).count("1") == k - H["dst_ptr"][r]
+    # forward DCSR: every out-edge points at the local row of its tail
+    for r in range(R):
+        for k in range(H["fsrc_ptr"][r], H["fsrc_ptr"][r + 1]):
+            for e in range(H["frow_start"][k], H["frow_start"][k + 1]):
+                t = int(H["row_dst"][H["dst_ptr"][r] + H["fedge_dstrow"][e]])
+                assert (r, t) in rows
+    assert H["frow_start"][-1] == fx["train"].shape[0] and int(np.bitwise_count(srank[:, 0]).sum()) == H["fsrc_ptr"][-1]
+    # reference edge order + edges_to_remove lookup (data.py:66-69, 214-216)
+    ht = kg.relation2ht2index
+    idx = kg.edge_index_of(fx["train"])
+    for (h, r, t), k in list(zip(fx["train"].tolist(), idx.tolist()))[::37]:
+        assert ht[r][kg.encode_ht(h, t)] == k
+        assert H["ord_h"][H["ord_ptr"][r] + k] == h and H["ord_t"][H["ord_ptr"][r] + k] == t
+    with pytest.raises(KeyError):
+        kg.edge_index_of(np.array([[0, 0, 0]]) if (0, 0, 0) not in set(map(tuple, fx["train"].tolist())) else np.array([[N - 1, 0, N - 1]]))
+    # answer lists == the reference dicts, de-duplicated
+    for which in ("hr2o", "hr2oo", "hr2ooo"):
+        keys, ptr, ent = kg.answers_csr(which)
+        d = getattr(kg, which)
+        assert sorted(d.keys()) == keys.tolist()
+        for i in range(0, len(keys), 23):
+            assert sorted(set(d[int(keys[i])])) == ent[ptr[i]:ptr[i + 1]].tolist()
+
+
+def test_rule_compiler_tries():
+    from rnnlogic_b200 import KnowledgeGraph, CompiledRules, parse_rules
+    fx = G.load("umls")
+    kg = KnowledgeGraph(entity_size=int(fx["N"]), relation_size=int(fx["R"]), train=fx["train"])
+    full = parse_rules(G.rules_of(fx, "mined_rules"))
+    cr = CompiledRules(kg, full)
+    assert len(full) == 39283 and cr.num_nodes == 42956          # SURVEY.md section 7 step 2 (UMLS mined rules)
+    rules = parse_rules(G.rules_of(fx))
+    cr = CompiledRules(kg, rules)
+    H = cr.host
+    prefixes = set()
+    for h, b in rules:
+        for k in range(1, len(b) + 1):
+            prefixes.add((h,) + tuple(b[:k]))
+    assert cr.num_nodes == len(prefixes)
+    # every rule end is the node spelled by walking parents back to the root
+    for rid in range(0, len(rules), 11):
+        node = int(cr.rule_node[rid])
+        body = []
+        while node >= 0:
+            body.append(int(H["node_rel"][node]))
+            node = int(H["node_parent"][node])
+        assert body[::-1] == list(rules[rid][1])
+    # chunks tile every node exactly once; depth ranges are contiguous
+    rows = kg.rel_rows[H["node_rel"]]
+    covered = np.zeros(cr.num_nodes, dtype=np.int64)
+    np.add.at(covered, H["chunk_node"], np.minimum(32, rows[H["chunk_node"]] - H["chunk_row0"]))
+    assert np.array_equal(covered, rows)
+    assert cr.level_chunks.sum() == cr.num_chunks and cr.level_nodes.sum() == cr.num_nodes
+    assert sum(len(b) == 0 for _, b in rules) == H["zr_ptr"][-1]
+    with pytest.raises(ValueError):
+        CompiledRules(kg, [(0, [kg.relation_size])])
+    with pytest.raises(ValueError):
+        parse_rules(3.5)
+
+
+def test_datasets_follow_reference_random_order():
+    """Same python-random call order as src/data.py:186-196, 232-238 => same batches as the golden run."""
+    import random
+    from rnnlogic_b200.data import KnowledgeGraph, TrainDataset, ValidDataset, TestDataset
+    fx = G.load("umls")
+    kg = KnowledgeGraph(entity_size=int(fx["N"]), relation_size=int(fx["R"]), train=fx["train"], valid=fx["valid"], test=fx["test"])
+    random.seed(1)
+    np.random.seed(1)
+    torch.manual_seed(1)
+    tr, va, te = TrainDataset(kg, 32), ValidDataset(kg, 32), TestDataset(kg, 32)
+    got = set(tuple(map(tuple, b)) for b in tr.batches)
+    for j in range(int(fx["tb_n"])):
+        assert tuple(map(tuple, fx["tb%d_triples" % j].tolist())) in got
+    tri, target, etr = G.train_batch_inputs(fx, 0)
+    i = [k for k, b in enumerate(tr.batches) if tuple(map(tuple, b)) == tuple(map(tuple, tri.tolist()))][0]
+    item = tr[i]
+    assert torch.equal(item[3], target) and torch.equal(item[4], etr)
+    tri, flag = G.valid_batch_inputs(fx, 0)
+    i = [k for k, b in enumerate(va.batches) if tuple(map(tuple, b)) == tuple(map(tuple, tri.tolist()))][0]
+    assert torch.equal(va[i][3], flag)
+
+
+def test_shard_indices_is_distributed_sampler():
+    from rnnlogic_b200.trainer import shard_indices, dedup_weights
+    a, b = shard_indices(11, 2, 0), shard_indices(11, 2, 1)
+    assert len(a) == len(b) == 6 and set(a) | set(b) == set(range(11))      # padded by wrap-around
+    assert shard_indices(11, 1, 0) == shard_indices(11, 1, 0) and sorted(shard_indices(11, 1, 0)) == list(range(11))
+    rows = np.array([[1, 2, 3, 1, 5], [4, 5, 6, 2, 3], [1, 2, 3, 7, 9]])
+    assert dedup_weights(rows).tolist() == [0.0, 1.0, 1.0]                    # last (h,r,t) row wins
+
+
+def _worker(rank, world, port, out):
+    import torch.distributed as dist
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port), RANK=str(rank), WORLD_SIZE=str(world))
+    from rnnlogic_b200 import comm
+    from rnnlogic_b200.trainer import allreduce_mean_grads, shard_indices
+    comm.init_process_group("gloo", init_method="env://")
+    torch.manual_seed(0)
+    p = [torch.nn.Parameter(torch.zeros(5)), torch.nn.Parameter(torch.zeros(2, 3)), torch.nn.Parameter(torch.zeros(4))]
+    p[0].grad = torch.full((5,), float(rank + 1))
+    if rank == 1:
+        p[1].grad = torch.ones(2, 3) * 4.0           # used by one rank only -> averaged with zeros
+    allreduce_mean_grads(p, world)                    # p[2] unused everywhere -> stays None
+    rows = torch.arange(5 * (rank + 2)).view(rank + 2, 5)
+    cat = comm.cat_rows(rows)
+    mine = shard_indices(9, world, rank)
+    res = {"g0": p[0].grad.tolist(), "g1": p[1].grad.tolist(), "g2": p[2].grad, "cat": cat.shape[0], "mine": mine}
+    torch.save(res, os.path.join(out, "r%d.pt" % rank))
+    dist.barrier()
+    dist.destroy_process_group()
+
+
+def test_world2_gloo_collectives(tmp_path):
+    import torch.multiprocessing as mp
+    port = 29500 + (os.getpid() % 2000)
+    mp.spawn(_worker, args=(2, port, str(tmp_path)), nprocs=2, join=True)
+    r0, r1 = torch.load(tmp_path / "r0.pt"), torch.load(tmp_path / "r1.pt")
+    for r in (r0, r1):
+        assert r["g0"] == [1.5] * 5 and r["g1"] == [[2.0] * 3] * 2 and r["g2"] is None and r["cat"] == 5
+    assert len(r0["mine"]) == len(r1["mine"]) == 5 and set(r0["mine"]) | set(r1["mine"]) == set(range(9))
