@@ -67,6 +67,8 @@ __device__ __forceinline__ bool row_valid(const int32_t *__restrict__ node_chunk
 // Warp-cooperative walk over every (non-zero terminal row, rule end) that can contribute to entity e
 // of one slot: f(count_of_this_lane, term_index) is called by all 32 lanes (lane = query).  Order is
 // fixed: the entity's (relation,row) pairs ascending, then the head's rule ends of that relation.
+// The (pair, rule end) items are flattened over the lanes so that the dependent look-ups
+// (rule end -> node -> row bitmap) run 32 wide; only items whose row is non-zero touch the arena.
 template <typename CT, typename F>
 __device__ __forceinline__ void scan_entity(const rl_graph &g, const rl_rules &r, const CT *__restrict__ arena, size_t abase,
                                             const uint32_t *__restrict__ mbase, int hc0, const int32_t *__restrict__ tp, int e, F f)
@@ -75,23 +77,41 @@ __device__ __forceinline__ void scan_entity(const rl_graph &g, const rl_rules &r
     const int p0 = g.ent_ptr[e], p1 = g.ent_ptr[e + 1];
     for (int pb = p0; pb < p1; pb += 32) {
         const int pi = pb + lane;
-        int row = 0, t0 = 0, t1 = 0;
+        int row = 0, t0 = 0, cnt = 0;
         if (pi < p1) {
             const int rel = g.ent_rel[pi];
             row = g.ent_row[pi];
             t0 = tp[rel];
-            t1 = tp[rel + 1];
+            cnt = tp[rel + 1] - t0;
         }
-        uint32_t have = __ballot_sync(FULL, t1 > t0);
-        while (have) {
-            const int k = __ffs(have) - 1;
-            have &= have - 1;
-            const int a0 = __shfl_sync(FULL, t0, k), a1 = __shfl_sync(FULL, t1, k);
-            const int rw = __shfl_sync(FULL, row, k);
-            for (int t = a0; t < a1; ++t) {
+        int P = cnt;                                        // inclusive scan: items of pairs 0..lane
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) {
+            const int t = __shfl_up_sync(FULL, P, o);
+            if (lane >= o) P += t;
+        }
+        const int T = __shfl_sync(FULL, P, 31);
+        const int first = P - cnt;
+        for (int base = 0; base < T; base += 32) {
+            const int k = min(base + lane, T - 1);
+            int pr = 0;                                      // pair of item k: #lanes with P <= k
+#pragma unroll
+            for (int step = 16; step > 0; step >>= 1)
+                if (__shfl_sync(FULL, P, pr + step - 1) <= k) pr += step;
+            const int t = __shfl_sync(FULL, t0, pr) + (k - __shfl_sync(FULL, first, pr));
+            const int rw = __shfl_sync(FULL, row, pr);
+            long long addr = -1;
+            if (base + lane < T) {
                 const int v = __ldg(r.term_node + t);
-                if (!row_valid(r.node_chunk0, mbase, hc0, v, rw)) continue;
-                f(arena[(abase + (size_t)r.node_row_off[v] + rw) * RL_LANES + lane], t);
+                if (row_valid(r.node_chunk0, mbase, hc0, v, rw)) addr = (long long)r.node_row_off[v] + rw;
+            }
+            uint32_t live = __ballot_sync(FULL, addr >= 0);
+            while (live) {
+                const int j = __ffs(live) - 1;
+                live &= live - 1;
+                const long long a = __shfl_sync(FULL, addr, j);
+                const int tj = __shfl_sync(FULL, t, j);
+                f(arena[(abase + (size_t)a) * RL_LANES + lane], tj);
             }
         }
     }

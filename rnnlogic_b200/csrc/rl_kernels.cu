@@ -138,7 +138,7 @@ k_symbolic(rl_graph g, rl_rules r, rl_slots s, int depth, rl_frontier fr, int de
 #define EDGE_GROUP 8
 // One chunk (<= 32 destination rows of node v starting at row0) with valid-row word m.
 // Returns the word of rows that ended up NON-ZERO (exact frontier support).
-template <typename CT, bool ROOT>
+template <typename CT, bool ROOT, bool PRUNE>
 __device__ __forceinline__ uint32_t numeric_chunk(const rl_graph &g, const rl_rules &r, const rl_slots &s, const rl_frontier &fr,
                                                   int slot, int q, int hc0, const uint32_t *mbase, int v, int row0, uint32_t m,
                                                   int h, int lane_eh, int lane_et, bool &ovf)
@@ -192,7 +192,7 @@ __device__ __forceinline__ uint32_t numeric_chunk(const rl_graph &g, const rl_ru
             acc -= sub;
         }
         if (sizeof(CT) == 4 && (acc >> 32)) ovf = true;
-        if (__any_sync(FULL, acc != 0)) {                    // all-zero rows are dropped from the bitmap
+        if (!PRUNE || __any_sync(FULL, acc != 0)) {          // all-zero rows are dropped from the bitmap
             Y[(size_t)j * RL_LANES + lane] = (CT)acc;
             nzrows |= 1u << j;
         }
@@ -213,24 +213,27 @@ __device__ __forceinline__ uint32_t numeric_chunk(const rl_graph &g, const rl_ru
             pr = rank_row(g, prel, src);
             if (pr >= 0 && !((pm[pr >> 5] >> (pr & 31)) & 1u)) pr = -1;
         }
-        for (int k0 = 0; k0 < n; k0 += EDGE_GROUP) {
+        // only edges whose parent row is non-zero are pulled (ROOT: every edge, the value is a compare)
+        uint32_t todo = ROOT ? (n == 32 ? FULL : ((1u << n) - 1u)) : __ballot_sync(FULL, pr >= 0);
+        while (todo) {
             CT vals[EDGE_GROUP];
             int rws[EDGE_GROUP];
 #pragma unroll
-            for (int u = 0; u < EDGE_GROUP; ++u) {
-                const int kk = (k0 + u) & 31;
-                rws[u] = __shfl_sync(FULL, row, kk);
+            for (int u = 0; u < EDGE_GROUP; ++u) {           // EDGE_GROUP row loads in flight
+                const int kk = todo ? __ffs(todo) - 1 : -1;
+                todo &= todo - 1;
+                rws[u] = kk >= 0 ? __shfl_sync(FULL, row, kk) : -1;
                 if (ROOT) {
-                    const int sv = __shfl_sync(FULL, src, kk);
-                    vals[u] = (CT)((k0 + u < n) && (sv == h));
+                    const int sv = __shfl_sync(FULL, src, kk & 31);
+                    vals[u] = (CT)((kk >= 0) && (sv == h));
                 } else {
-                    const int p = __shfl_sync(FULL, pr, kk);
-                    vals[u] = (k0 + u < n && p >= 0) ? X[(size_t)p * RL_LANES + lane] : (CT)0;
+                    const int p = __shfl_sync(FULL, pr, kk & 31);
+                    vals[u] = kk >= 0 ? X[(size_t)p * RL_LANES + lane] : (CT)0;
                 }
             }
 #pragma unroll
             for (int u = 0; u < EDGE_GROUP; ++u) {
-                if (k0 + u < n) {
+                if (rws[u] >= 0) {
                     if (rws[u] != cur) {
                         if (cur >= 0) flush(cur);
                         cur = rws[u];
@@ -248,7 +251,7 @@ __device__ __forceinline__ uint32_t numeric_chunk(const rl_graph &g, const rl_ru
 
 // One warp = 32 consecutive chunks of one slot at this depth: the 32 valid-row words are read with
 // one coalesced load and only chunks with a non-zero word are expanded.
-template <typename CT, bool ROOT>
+template <typename CT, bool ROOT, bool PRUNE>
 __global__ void __launch_bounds__(WARPS_PER_BLOCK * 32)
 k_numeric(rl_graph g, rl_rules r, rl_slots s, int depth, rl_frontier fr)
 {
@@ -277,7 +280,7 @@ k_numeric(rl_graph g, rl_rules r, rl_slots s, int depth, rl_frontier fr)
         const int chunk = c0 + c;
         const uint32_t m = __shfl_sync(FULL, my_m, c);
         const int v = r.chunk_node[chunk], row0 = r.chunk_row0[chunk];
-        const uint32_t nz = numeric_chunk<CT, ROOT>(g, r, s, fr, slot, q, hc0, mbase, v, row0, m, h, leh, let_, ovf);
+        const uint32_t nz = numeric_chunk<CT, ROOT, PRUNE>(g, r, s, fr, slot, q, hc0, mbase, v, row0, m, h, leh, let_, ovf);
         if (lane == c) my_out = nz;
         if (lane == 0 && nz) atomicAdd(fr.node_cnt + nzb + v, __popc(nz));
     }
@@ -840,13 +843,16 @@ int rl_expand_level(const rl_graph *g, const rl_rules *r, const rl_slots *s, int
     else k_symbolic<false><<<gs, WARPS_PER_BLOCK * 32, 0, st>>>(*g, *r, *s, depth, *fr, dense_num, dense_den, force_dense);
     CHECK_LAUNCH("k_symbolic");
     dim3 grid((grid_chunks + WARPS_PER_BLOCK * 32 - 1) / (WARPS_PER_BLOCK * 32), s->num_slots);
+    // force_dense: plain dense SpMM -- every row of every node is written (zeros included) and read
+#define LAUNCH_NUM(CT, ROOT, PRUNE) k_numeric<CT, ROOT, PRUNE><<<grid, WARPS_PER_BLOCK * 32, 0, st>>>(*g, *r, *s, depth, *fr)
     if (fr->count_bits == 32) {
-        if (depth == 1) k_numeric<uint32_t, true><<<grid, WARPS_PER_BLOCK * 32, 0, st>>>(*g, *r, *s, depth, *fr);
-        else k_numeric<uint32_t, false><<<grid, WARPS_PER_BLOCK * 32, 0, st>>>(*g, *r, *s, depth, *fr);
+        if (depth == 1) { if (force_dense) LAUNCH_NUM(uint32_t, true, false); else LAUNCH_NUM(uint32_t, true, true); }
+        else { if (force_dense) LAUNCH_NUM(uint32_t, false, false); else LAUNCH_NUM(uint32_t, false, true); }
     } else {
-        if (depth == 1) k_numeric<unsigned long long, true><<<grid, WARPS_PER_BLOCK * 32, 0, st>>>(*g, *r, *s, depth, *fr);
-        else k_numeric<unsigned long long, false><<<grid, WARPS_PER_BLOCK * 32, 0, st>>>(*g, *r, *s, depth, *fr);
+        if (depth == 1) { if (force_dense) LAUNCH_NUM(unsigned long long, true, false); else LAUNCH_NUM(unsigned long long, true, true); }
+        else { if (force_dense) LAUNCH_NUM(unsigned long long, false, false); else LAUNCH_NUM(unsigned long long, false, true); }
     }
+#undef LAUNCH_NUM
     CHECK_LAUNCH("k_numeric");
     return RL_OK;
 }
