@@ -208,7 +208,7 @@ def main():
     per = args.batches
     n_steps = args.warmup + args.steps
     step_batches = [[my[(s * per + j) % len(my)] for j in range(per)] for s in range(n_steps)]
-    step_lists = [[[tuple(x) for x in b.tolist()] for b in sb] for sb in step_batches]
+    step_lists = step_batches            # int arrays [n,3] per batch, what the datasets hold (batch_arrays)
     queries_per_step = [sum(len(b) for b in sb) for sb in step_batches]
 
     def allreduce_and_step(gw, gb):

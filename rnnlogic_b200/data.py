@@ -7,6 +7,7 @@ trainer does not use them -- it reads ``batches[idx]`` and lets the kernels look
 filters up in the device-resident answer lists (rl_answers)."""
 import random
 
+import numpy as np
 import torch
 from torch.utils.data import Dataset
 
@@ -30,6 +31,7 @@ class TrainDataset(Dataset):
             for k in range(0, len(instances), self.batch_size):
                 self.batches.append(instances[k:min(k + self.batch_size, len(instances))])
         random.shuffle(self.batches)
+        self.batch_arrays = [np.array(b, dtype=np.int64).reshape(-1, 3) for b in self.batches]
 
     def __len__(self):
         return len(self.batches)
@@ -64,6 +66,7 @@ class _EvalDataset(Dataset):
             random.shuffle(instances)
             for k in range(0, len(instances), self.batch_size):
                 self.batches.append(instances[k:min(k + self.batch_size, len(instances))])
+        self.batch_arrays = [np.array(b, dtype=np.int64).reshape(-1, 3) for b in self.batches]
 
     def __len__(self):
         return len(self.batches)

@@ -110,9 +110,13 @@ class Grounder:
         """Slots for a list of single-relation batches given as host lists of (h, r, t) triples
         (what the datasets hold).  One packed host->device copy carries h, t and the removed-edge
         indices; with_etr looks the indices up in the graph's train-edge table (data.py:214-216)."""
-        heads = [b[0][1] for b in batches]
+        if isinstance(batches[0], np.ndarray):                  # int arrays [n,3]: no per-triple Python work
+            flat = np.concatenate(batches).astype(np.int64, copy=False).reshape(-1, 3)
+            heads = [int(b[0, 1]) for b in batches]
+        else:
+            flat = np.array([x for b in batches for x in b], dtype=np.int64).reshape(-1, 3)
+            heads = [b[0][1] for b in batches]
         sizes = [len(b) for b in batches]
-        flat = np.array([x for b in batches for x in b], dtype=np.int64).reshape(-1, 3)
         rows = [flat[:, 0], flat[:, 2]]
         if with_etr:
             if etr_lists is not None:

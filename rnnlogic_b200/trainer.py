@@ -108,7 +108,7 @@ class TrainerPredictor(object):
         N = self.train_set.graph.entity_size
         done = 0
         for s0 in range(0, len(order), k):
-            batches = [self.train_set.batches[i] for i in order[s0:s0 + k]]
+            batches = [self.train_set.batch_arrays[i] for i in order[s0:s0 + k]]
             self.optimizer.zero_grad(set_to_none=True)
             loss, tsum = model.fused_train_step(batches, smoothing, grad_scale=1.0 / len(batches))
             cand = getattr(model, "last_mask_sum", None)          # per-batch mask.sum() in mask mode
@@ -165,9 +165,9 @@ class TrainerPredictor(object):
         rows = []
         step = max(1, int(self.eval_batches_per_call))
         for s0 in range(0, len(order), step):
-            batches = [test_set.batches[i] for i in order[s0:s0 + step]]
+            batches = [test_set.batch_arrays[i] for i in order[s0:s0 + step]]
             LH = model.fused_rank(batches, split)
-            tri = torch.tensor([x for b in batches for x in b], dtype=torch.long, device=self.device)
+            tri = torch.from_numpy(np.concatenate(batches)).to(self.device)
             rows.append(torch.cat([tri, LH], dim=1))
         ranks = torch.cat(rows, dim=0) if rows else torch.zeros(0, 5, dtype=torch.long, device=self.device)
         ranks = comm.cat_rows(ranks)                              # trainer.py:204-205
