@@ -32,8 +32,11 @@ __global__ void k_prepare_slots(rl_graph g, int S, const int32_t *__restrict__ s
     int s = i >> 5, lane = i & 31;
     int qi = q_off[s] + lane;
     bool valid = qi < q_off[s + 1];
-    lane_h[i] = valid ? (int32_t)all_h[qi] : -1;
-    lane_t[i] = (valid && all_t) ? (int32_t)all_t[qi] : -1;
+    int64_t hv = valid ? all_h[qi] : -1, tv = (valid && all_t) ? all_t[qi] : -1;
+    if (hv < 0 || hv >= g.num_entities) hv = -1;            // out-of-range ids become padding lanes
+    if (tv < 0 || tv >= g.num_entities) tv = -1;
+    lane_h[i] = (int32_t)hv;
+    lane_t[i] = (int32_t)tv;
     int eh = -1, et = -1;
     if (valid && etr) {
         int rel = slot_head[s];

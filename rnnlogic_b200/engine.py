@@ -102,6 +102,9 @@ class Grounder:
             pos += int(n)
         if not sh:
             raise ValueError("empty batch")
+        for name, t in (("all_h", all_h), ("all_t", all_t), ("edges_to_remove", etr)):
+            if t is not None and int(t.numel()) != pos:
+                raise ValueError("%s has %d entries for %d queries" % (name, int(t.numel()), pos))
         return Slots(self.dg, self.cr, np.array(sh, dtype=np.int64), np.array(qo, dtype=np.int64),
                      all_h.contiguous(), None if all_t is None else all_t.contiguous(),
                      None if etr is None else etr.contiguous())

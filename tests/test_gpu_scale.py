@@ -62,8 +62,11 @@ def test_counts_vs_oracle_and_modes_agree(name):
             assert np.array_equal(got[k], want), (name, q, rid, rules[rid])
             maxc = max(maxc, int(want.max()))
         # batch independence: the first 5 queries alone give the same rows
-        s3 = sparse.ground(sparse.make_slots([q], [5], h[:5].contiguous(), None, etr[:5].contiguous()))
-        assert torch.equal(sparse.rule_counts(s3, pick[:4]), c1[:4, :5])
+        n5 = min(5, len(b))
+        s3 = sparse.ground(sparse.make_slots([q], [n5], h[:n5].contiguous(), None, etr[:n5].contiguous()))
+        assert torch.equal(sparse.rule_counts(s3, pick[:4]), c1[:4, :n5])
+        with pytest.raises(ValueError):
+            sparse.make_slots([q], [len(b) + 2], h, None, etr)
     assert maxc >= 1
 
 
