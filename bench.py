@@ -200,7 +200,7 @@ def main():
     with torch.no_grad():
         model.rule_weights.copy_(torch.randn(model.num_rules, generator=g) * 0.1)
     model = model.cuda(dev)
-    opt = torch.optim.Adam(model.parameters(), lr=0.005)
+    opt = torch.optim.Adam(model.parameters(), lr=0.005, fused=True)     # torch's single-kernel Adam
     sk = model._driver(dev)
     cr = model.compiled
 

@@ -91,6 +91,10 @@ typedef struct rl_rules {
     const int32_t *lvl_node_ptr;  /* [R*(max_len+1)] node range per (head, depth), like lvl_ptr */
     const int32_t *node_chunk0;   /* [num_nodes] global id of the node's first chunk */
     const int32_t *node_nterm;    /* [num_nodes] number of rules ending at the node */
+    /* packed per-node record, 32-byte aligned: {rel, parent, parent rel, dst_ptr[rel],
+     *  rows(rel), chunk0, parent chunk0, nterm} -- one load instead of a look-up chain */
+    const int32_t *node_rec;      /* [num_nodes*8] */
+    const int64_t *node_prow_off; /* [num_nodes] node_row_off of the parent (0 for depth 1) */
 } rl_rules;
 
 /* One call's queries, cut into slots (<= 32 queries of one head relation each). */

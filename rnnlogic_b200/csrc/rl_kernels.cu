@@ -95,25 +95,27 @@ k_symbolic(rl_graph g, rl_rules r, rl_slots s, int depth, rl_frontier fr, int de
     const int32_t *np = r.lvl_node_ptr + (size_t)q * (r.max_len + 1);
     const int v = np[depth - 1] + blockIdx.x * WARPS_PER_BLOCK + warp;
     if (v >= np[depth]) return;
-    const int rho = r.node_rel[v];
-    const int D = g.dst_ptr[rho + 1] - g.dst_ptr[rho];
+    const int4 ra = __ldg(reinterpret_cast<const int4 *>(r.node_rec) + 2 * (size_t)v);
+    const int4 rb4 = __ldg(reinterpret_cast<const int4 *>(r.node_rec) + 2 * (size_t)v + 1);
+    const int rho = ra.x;
+    const int D = rb4.x;
     const int nw = (D + 31) >> 5;
     if (nw == 0) return;
     const int hc0 = r.lvl_ptr[(size_t)q * (r.max_len + 1)];
     uint32_t *mbase = fr.row_mask + (size_t)s.mask_off[slot];
-    uint32_t *cm = mbase + (r.node_chunk0[v] - hc0);
+    uint32_t *cm = mbase + (rb4.y - hc0);
     const int nzb = s.nz_off[slot] - r.head_node_ptr[q];
     bool dense = force_dense != 0;
     const uint32_t *pm = nullptr;
     int rho_p = -1, Dp = 0;
     if (!ROOT) {
-        const int p = r.node_parent[v];
+        const int p = ra.y;
         const int cntp = fr.node_cnt[nzb + p];
         if (!dense && cntp == 0) return;                       // empty parent => empty node
-        rho_p = r.node_rel[p];
+        rho_p = ra.z;
         Dp = g.dst_ptr[rho_p + 1] - g.dst_ptr[rho_p];
         if ((long long)cntp * dense_den > (long long)Dp * dense_num) dense = true;
-        pm = mbase + (r.node_chunk0[p] - hc0);
+        pm = mbase + (rb4.z - hc0);
     }
     if (dense) {
         for (int w = lane; w < nw; w += 32)
@@ -147,21 +149,21 @@ __device__ __forceinline__ uint32_t numeric_chunk(const rl_graph &g, const rl_ru
                                                   int h, int lane_eh, int lane_et, bool &ovf)
 {
     const int lane = threadIdx.x & 31;
-    const int rho = r.node_rel[v];
+    // one 32-byte node record instead of a chain of dependent look-ups
+    const int4 ra = __ldg(reinterpret_cast<const int4 *>(r.node_rec) + 2 * (size_t)v);
+    const int4 rb4 = __ldg(reinterpret_cast<const int4 *>(r.node_rec) + 2 * (size_t)v + 1);
+    const int rho = ra.x, prel = ra.z, nterm = rb4.w;
     const size_t abase = (size_t)s.arena_off[slot];
     CT *arena = reinterpret_cast<CT *>(fr.arena);
     const CT *__restrict__ X = nullptr;
     const uint32_t *__restrict__ pm = nullptr;
-    int prel = -1;
     if (!ROOT) {
-        const int p = r.node_parent[v];
-        prel = r.node_rel[p];
-        X = arena + (abase + (size_t)r.node_row_off[p]) * RL_LANES;
-        pm = mbase + (r.node_chunk0[p] - hc0);
+        X = arena + (abase + (size_t)r.node_prow_off[v]) * RL_LANES;
+        pm = mbase + (rb4.z - hc0);
     }
     CT *__restrict__ Y = arena + (abase + (size_t)r.node_row_off[v] + row0) * RL_LANES;
-    const int rbase = g.dst_ptr[rho] + row0;
-    const int nr = min(32, g.dst_ptr[rho + 1] - rbase);
+    const int rbase = ra.w + row0;
+    const int nr = min(32, rb4.x - row0);
     const int my_rs = g.row_start[rbase + min(lane, nr)];
     const int my_re = g.row_start[rbase + min(lane + 1, nr)];
     const int my_dst = lane < nr ? g.row_dst[rbase + lane] : -1;
@@ -247,7 +249,7 @@ __device__ __forceinline__ uint32_t numeric_chunk(const rl_graph &g, const rl_ru
         }
     }
     if (cur >= 0) flush(cur);
-    if (r.node_nterm[v] > 0 && ((nzrows >> lane) & 1u))      // candidate entities for the aggregation
+    if (nterm > 0 && ((nzrows >> lane) & 1u))                // candidate entities for the aggregation
         atomicOr(fr.ent_active + (size_t)slot * g.rank_words + (my_dst >> 5), 1u << (my_dst & 31));
     return nzrows;
 }
@@ -560,62 +562,46 @@ k_grad_sparse(rl_graph g, rl_slots s, rl_answers ans, float smoothing, int use_m
 // ------------------------------------------------------------------------------------------
 // kernel (2c): backward into rule weights / bias
 // ------------------------------------------------------------------------------------------
+// Entity-centric like the forward: only candidate entities (ent_active) are visited; for each of
+// their non-zero terminal rows the warp reduces <fp32(count), G[e]> over the 32 queries and adds it
+// to the rule's gradient (one atomic per (row, rule end)).
 template <typename CT>
-__global__ void __launch_bounds__(128)
+__global__ void __launch_bounds__(WARPS_PER_BLOCK * 32)
 k_predictor_bwd_w(rl_graph g, rl_rules r, rl_slots s, rl_frontier fr, const float *__restrict__ G,
                   const float *__restrict__ slot_scale, float *__restrict__ grad_w)
 {
-    __shared__ double red[4];
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const int slot = blockIdx.y;
+    const int ew = blockIdx.x * WARPS_PER_BLOCK + warp;           // entity word
     const int N = g.num_entities, R = g.num_relations;
+    if (ew >= g.rank_words) return;
     const int q = s.slot_head[slot];
     const float scale = slot_scale ? slot_scale[slot] : 1.f;
     const float *Gs = G + (size_t)slot * N * RL_LANES;
-    if (blockIdx.x == 0 && warp == 0 && r.zr_ptr[q + 1] > r.zr_ptr[q]) {   // empty-body rules
-        const int h = s.lane_h[slot * RL_LANES + lane];
+    const int h = s.lane_h[slot * RL_LANES + lane];
+    const int z0 = r.zr_ptr[q], z1 = r.zr_ptr[q + 1];
+    if (ew == 0 && z1 > z0) {                                      // empty-body rules: count = one_hot(h)
         double v = h >= 0 ? (double)Gs[(size_t)h * RL_LANES + lane] : 0.0;
         v = warp_sum(v);
         if (lane == 0)
-            for (int t = r.zr_ptr[q]; t < r.zr_ptr[q + 1]; ++t) atomicAdd(grad_w + r.zr_rule[t], (float)v * scale);
+            for (int t = z0; t < z1; ++t) atomicAdd(grad_w + r.zr_rule[t], (float)v * scale);
     }
-    const int t = r.term_ptr[(size_t)q * R] + blockIdx.x;
-    if (t >= r.term_ptr[(size_t)(q + 1) * R]) return;
-    const int v = r.term_node[t];
-    if (fr.node_cnt[s.nz_off[slot] - r.head_node_ptr[q] + v] == 0) return;
-    const int rho = r.node_rel[v];
-    const int rb = g.dst_ptr[rho], nrows = g.dst_ptr[rho + 1] - rb;
-    const int nw = (nrows + 31) >> 5;
-    const uint32_t *cm = fr.row_mask + (size_t)s.mask_off[slot] + (r.node_chunk0[v] - r.lvl_ptr[(size_t)q * (r.max_len + 1)]);
-    const CT *Xv = reinterpret_cast<const CT *>(fr.arena) + ((size_t)s.arena_off[slot] + r.node_row_off[v]) * RL_LANES;
-    double acc = 0.0;
-    for (int wi = warp; wi < nw; wi += 4) {
-        uint32_t word = cm[wi];
-        while (word) {
-            int j[4];
-            CT c[4];
-            float gv[4];
-#pragma unroll
-            for (int u = 0; u < 4; ++u) {                      // 4 rows in flight
-                j[u] = word ? wi * 32 + __ffs(word) - 1 : -1;
-                word &= word - 1;
-            }
-#pragma unroll
-            for (int u = 0; u < 4; ++u) c[u] = j[u] >= 0 ? Xv[(size_t)j[u] * RL_LANES + lane] : (CT)0;
-#pragma unroll
-            for (int u = 0; u < 4; ++u)
-                gv[u] = j[u] >= 0 ? Gs[(size_t)__ldg(g.row_dst + rb + j[u]) * RL_LANES + lane] : 0.f;
-#pragma unroll
-            for (int u = 0; u < 4; ++u)
-                if (c[u] != 0) acc += (double)(float)c[u] * (double)gv[u];
-        }
-    }
-    acc = warp_sum(acc);
-    if (lane == 0) red[warp] = acc;
-    __syncthreads();
-    if (threadIdx.x == 0) {
-        const double tot = red[0] + red[1] + red[2] + red[3];
-        if (tot != 0.0) atomicAdd(grad_w + r.term_rule[t], (float)tot * scale);
+    uint32_t act = fr.ent_active[(size_t)slot * g.rank_words + ew];
+    if (act == 0u) return;
+    const int hc0 = r.lvl_ptr[(size_t)q * (r.max_len + 1)];
+    const uint32_t *mbase = fr.row_mask + (size_t)s.mask_off[slot];
+    const size_t abase = (size_t)s.arena_off[slot];
+    const CT *arena = reinterpret_cast<const CT *>(fr.arena);
+    const int32_t *tp = r.term_ptr + (size_t)q * R;
+    while (act) {
+        const int e = ew * 32 + __ffs(act) - 1;
+        act &= act - 1;
+        const float gv = Gs[(size_t)e * RL_LANES + lane];
+        scan_entity<CT>(g, r, arena, abase, mbase, hc0, tp, e, [&](CT c, int t) {
+            double v = c != 0 ? (double)(float)c * (double)gv : 0.0;   // skips NaN*0 of masked cells
+            v = warp_sum(v);
+            if (lane == 0 && v != 0.0) atomicAdd(grad_w + r.term_rule[t], (float)v * scale);
+        });
     }
 }
 
@@ -928,9 +914,10 @@ int rl_predictor_backward(const rl_graph *g, const rl_rules *r, const rl_slots *
     const int S = s->num_slots, N = g->num_entities;
     if (S <= 0) return RL_OK;
     cudaStream_t st = (cudaStream_t)stream;
-    dim3 grid(max_terms > 0 ? max_terms : 1, S);
-    if (fr->count_bits == 32) k_predictor_bwd_w<uint32_t><<<grid, 128, 0, st>>>(*g, *r, *s, *fr, G, slot_scale, grad_w);
-    else k_predictor_bwd_w<unsigned long long><<<grid, 128, 0, st>>>(*g, *r, *s, *fr, G, slot_scale, grad_w);
+    (void)max_terms;
+    dim3 grid((g->rank_words + WARPS_PER_BLOCK - 1) / WARPS_PER_BLOCK, S);
+    if (fr->count_bits == 32) k_predictor_bwd_w<uint32_t><<<grid, WARPS_PER_BLOCK * 32, 0, st>>>(*g, *r, *s, *fr, G, slot_scale, grad_w);
+    else k_predictor_bwd_w<unsigned long long><<<grid, WARPS_PER_BLOCK * 32, 0, st>>>(*g, *r, *s, *fr, G, slot_scale, grad_w);
     CHECK_LAUNCH("k_predictor_bwd_w");
     if (grad_bias) {
         k_bias_grad<<<(N + WARPS_PER_BLOCK - 1) / WARPS_PER_BLOCK, WARPS_PER_BLOCK * 32, 0, st>>>(N, S, G, slot_scale, grad_bias);

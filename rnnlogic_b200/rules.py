@@ -142,6 +142,21 @@ class CompiledRules:
         self.head_ground_bytes = nb[head_node_ptr[1:]] - nb[head_node_ptr[:-1]]
         self.node_depth, self.node_rel_host, self.node_head = node_depth, node_rel, node_head
         self.head_node_ptr = head_node_ptr
+        # packed node records (one 32-byte load in the kernels)
+        has_p = node_parent >= 0
+        psafe = np.where(has_p, node_parent, 0)
+        rec = np.zeros((max(1, self.num_nodes), 8), dtype=np.int64)
+        if self.num_nodes:
+            dst_ptr = np.concatenate([[0], np.cumsum(rel_rows)])
+            rec[:, 0] = node_rel
+            rec[:, 1] = node_parent
+            rec[:, 2] = np.where(has_p, node_rel[psafe], -1)
+            rec[:, 3] = dst_ptr[node_rel]
+            rec[:, 4] = node_rows
+            rec[:, 5] = cstart[:-1]
+            rec[:, 6] = np.where(has_p, cstart[:-1][psafe], 0)
+            rec[:, 7] = node_nterm[:self.num_nodes]
+        node_prow_off = np.where(has_p, node_row_off[psafe], 0) if self.num_nodes else np.zeros(0, np.int64)
         i32 = lambda a: np.ascontiguousarray(a, dtype=np.int32)
         if self.num_chunks >= 2 ** 31 or self.num_nodes >= 2 ** 31:
             raise ValueError("rule set too large for 32-bit work tables")
@@ -152,6 +167,7 @@ class CompiledRules:
             "chunk_node": i32(chunk_node), "chunk_row0": i32(chunk_row0), "term_ptr": i32(term_ptr),
             "term_node": i32(t_node), "term_rule": i32(t_rule), "zr_ptr": i32(zr_ptr), "zr_rule": i32(zr_rule),
             "lvl_node_ptr": i32(lvl_node_ptr.reshape(-1)), "node_chunk0": i32(cstart[:-1]), "node_nterm": i32(node_nterm),
+            "node_rec": i32(rec.reshape(-1)), "node_prow_off": np.ascontiguousarray(node_prow_off, dtype=np.int64),
         }
         self._devices = {}
 
@@ -174,7 +190,8 @@ class DeviceRules:
             t["head_node_ptr"].data_ptr(), t["lvl_ptr"].data_ptr(), t["chunk_node"].data_ptr(),
             t["chunk_row0"].data_ptr(), t["term_ptr"].data_ptr(), t["term_node"].data_ptr(),
             t["term_rule"].data_ptr(), t["zr_ptr"].data_ptr(), t["zr_rule"].data_ptr(),
-            t["lvl_node_ptr"].data_ptr(), t["node_chunk0"].data_ptr(), t["node_nterm"].data_ptr())
+            t["lvl_node_ptr"].data_ptr(), t["node_chunk0"].data_ptr(), t["node_nterm"].data_ptr(),
+            t["node_rec"].data_ptr(), t["node_prow_off"].data_ptr())
 
     def ref(self):
         return C.byref(self.struct)
