@@ -41,7 +41,7 @@ class Slots:
         # one packed H2D copy for the slot descriptors
         pack = np.concatenate([heads.astype(np.int64), q_off.astype(np.int64), nz_off[:-1], arena_off[:-1],
                                mask_off[:-1]])
-        d = torch.from_numpy(pack).to(dev, non_blocking=True)
+        d = torch.from_numpy(pack).pin_memory().to(dev, non_blocking=True)      # pinned staging, async copy
         self.slot_head = d[:S].to(torch.int32)
         self.q_off_dev = d[S:2 * S + 1].to(torch.int32)
         self.nz_off = d[2 * S + 1:3 * S + 1].to(torch.int32)
@@ -126,7 +126,7 @@ class Grounder:
                 rows.append(np.array([e for l in etr_lists for e in l], dtype=np.int64))
             else:
                 rows.append(self.graph.edge_index_of(flat))
-        d = torch.from_numpy(np.ascontiguousarray(np.stack(rows))).to(self.device, non_blocking=True)
+        d = torch.from_numpy(np.ascontiguousarray(np.stack(rows))).pin_memory().to(self.device, non_blocking=True)
         sl = self.make_slots(heads, sizes, d[0], d[1], d[2] if with_etr else None)
         sl.use_workspace = True
         sl.group_sizes = sizes

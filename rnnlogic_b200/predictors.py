@@ -187,6 +187,45 @@ def _predictor_step_on_slots(self, sk, sl, smoothing, grad_scale=1.0, bits=32):
     return loss, tsum, msum, gw, gb
 
 
+class _StepTicket:
+    """Handle of an enqueued fused train step: everything is on the stream, nothing was synchronised.
+    ``result()`` does the step's one device->host read (losses, target sums, overflow flag)."""
+
+    def __init__(self, model, sk, sl, batches, smoothing, grad_scale, pack, gw, gb, ng, use_bias):
+        self.model, self.sk, self.sl, self.batches = model, sk, sl, batches
+        self.smoothing, self.grad_scale = smoothing, grad_scale
+        self.gw, self.gb, self.ng, self.use_bias = gw, gb, ng, use_bias
+        self.pinned = torch.empty(pack.numel(), dtype=torch.float32, pin_memory=True)
+        self.pinned.copy_(pack, non_blocking=True)
+        self.event = torch.cuda.Event()
+        self.event.record()
+        self.h2d_bytes = sl.h2d_bytes
+        self.d2h_bytes = int(pack.numel() * 4)
+
+    def result(self):
+        self.event.synchronize()
+        host = self.pinned
+        ng = self.ng
+        if host[-1].item() != 0:
+            raise _lib.RlError("a path count overflowed 32 bits inside an enqueued step; rerun the step with "
+                               "model.fused_train_step (it falls back to exact 64-bit rows)")
+        self.model.last_mask_sum = None if self.use_bias else host[2 * ng:3 * ng].tolist()
+        return host[:ng], host[ng:2 * ng]
+
+
+def _predictor_submit_train(self, batches, smoothing, grad_scale=1.0):
+    """Enqueue one fused train step (host pack -> H2D -> kernels -> async D2H) and return a ticket; the
+    gradients are in ticket.gw / ticket.gb (device).  Lets the host prepare step k+1 while step k runs."""
+    device = self.rule_weights.device
+    sk = self._driver(device)
+    use_bias = self.entity_feature == "bias"
+    sl = sk.gr.make_slots_host(batches, with_etr=True)
+    loss, tsum, msum, gw, gb = _predictor_step_on_slots(self, sk, sl, smoothing, grad_scale, sk.gr.force_bits or 32)
+    parts = [loss, tsum] + ([msum] if msum is not None else [])
+    pack = torch.cat(parts + [sl.overflow.float()])
+    return _StepTicket(self, sk, sl, batches, smoothing, grad_scale, pack, gw, gb, len(batches), use_bias)
+
+
 def _predictor_fused_train(self, batches, smoothing, grad_scale=1.0):
     """One fused step over a list of single-relation train batches (trainer.py:68-93 for each):
     ground -> aggregate -> log(softmax+1e-8) CE -> backward.  Gradients of ``grad_scale * sum of
@@ -236,6 +275,7 @@ def _valid_lanes(sl, LH):
 
 
 Predictor.fused_train_step = _predictor_fused_train
+Predictor.submit_train_step = _predictor_submit_train
 Predictor.step_on_slots = _predictor_step_on_slots
 Predictor.fused_rank = _predictor_fused_rank
 
