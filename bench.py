@@ -65,7 +65,7 @@ class ClockSampler:
     def start(self):
         try:
             self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.index), "--query-gpu=" + self.QUERY,
-                                          "--format=csv,noheader,nounits", "-lms", "100"],
+                                          "--format=csv,noheader,nounits", "-lms", "25"],
                                          stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
             self.thread = threading.Thread(target=self._read, daemon=True)
             self.thread.start()
@@ -144,15 +144,73 @@ def cpu_reference_run(N, R, train, valid, test, rules, batches, steps, warmup, b
             "steps_done": len(times), "ms_per_step": 1e3 * total / len(times)}
 
 
+def _timed(fn, n_warm, n):
+    for _ in range(n_warm):
+        fn()
+    torch.cuda.synchronize()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(n):
+        fn()
+    e1.record()
+    torch.cuda.synchronize()
+    return e0.elapsed_time(e1) / n
+
+
+def extras(args, kg, model, rules, batches, test, valid, dev):
+    """Side measurements on the same workload (short loops, end to end from host batches):
+    eval mode (ground -> aggregate -> filtered rank) and PredictorPlus train steps (the reference's
+    FB15k-237 config: lstm / sum / bias, and the RotatE entity feature of BASELINE config 4)."""
+    from rnnlogic_b200.predictors import PredictorPlus
+    out = {}
+    per = args.batches
+    R = kg.relation_size
+    tb = make_batches(test, R, seed=2)
+    state = {"i": 0}
+
+    def eval_step():
+        sb = [tb[(state["i"] * per + j) % len(tb)] for j in range(per)]
+        state["i"] += 1
+        model.fused_rank(sb, "test")
+        state["q"] = sum(len(b) for b in sb)
+
+    ms = _timed(eval_step, 3, 10)
+    out["eval_filtered_rank_queries_per_sec"] = state["q"] / (ms / 1e3)
+    rule_lists = [[h] + list(b) for h, b in rules]
+    for tag, kw in (("plus_lstm_sum_bias", dict(type="lstm", num_layers=3, hidden_dim=16, entity_feature="bias", aggregator="sum")),
+                    ("plus_emb_pna_bias", dict(type="emb", hidden_dim=16, entity_feature="bias", aggregator="pna"))):
+        torch.manual_seed(0)
+        pm = PredictorPlus(kg, **kw)
+        pm.set_rules(rule_lists)
+        pm = pm.cuda(dev)
+        popt = torch.optim.Adam(pm.parameters(), lr=0.005)
+        st = {"i": 0}
+
+        def plus_step():
+            sb = [batches[(st["i"] * per + j) % len(batches)] for j in range(per)]
+            st["i"] += 1
+            popt.zero_grad(set_to_none=True)
+            pm.fused_train_step(sb, 0.2, grad_scale=1.0 / per)
+            popt.step()
+            st["q"] = sum(len(b) for b in sb)
+
+        ms = _timed(plus_step, 3, 8)
+        out[tag + "_train_queries_per_sec"] = st["q"] / (ms / 1e3)
+        del pm, popt
+        torch.cuda.empty_cache()
+    return out
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--steps", type=int, default=100)
     ap.add_argument("--warmup", type=int, default=5)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--batches", type=int, default=64, help="reference batches (of <=32 queries) per step per GPU")
     ap.add_argument("--dense", action="store_true", help="expand every row of every trie node (dense SpMM; roofline mode)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-extras", action="store_true", help="skip the eval-mode / PredictorPlus side measurements")
     ap.add_argument("--mode", default="train", choices=["train", "eval"])
     args = ap.parse_args()
     if args.warmup < 3:
@@ -258,7 +316,6 @@ def main():
     ovf = int(ovf_acc.item())
     assert ovf == 0, "32-bit count overflow inside the timed region (rerun needed in 64-bit)"
     assert all(torch.isfinite(l).all().item() for l in losses)
-    clk = clocks.stop() if rank == 0 else None
     t = torch.tensor([elapsed_ms], dtype=torch.float64, device=dev)
     if world > 1:
         torch.distributed.all_reduce(t, op=torch.distributed.ReduceOp.MAX)
@@ -355,6 +412,7 @@ def main():
         torch.distributed.all_reduce(te, op=torch.distributed.ReduceOp.MAX)
     e2e_value = float(qt.item()) / (float(te.item()) / 1e3)
 
+    clk = clocks.stop() if rank == 0 else None      # sampled over all timed regions (value, dense roofline, e2e)
     if world > 1:
         torch.distributed.barrier()
         torch.distributed.destroy_process_group()
@@ -372,6 +430,8 @@ def main():
             "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d // args.steps,
                     "d2h_bytes_per_step": d2h // args.steps},
             "gpu_launches": int(launches), "clocks": clk}
+    if world == 1 and not args.no_extras:
+        line["extras"] = extras(args, kg, model, rules, batches, test, valid, dev)
     if world == 1 and not args.no_cpu_baseline:
         res = cpu_reference_run(N, R, train, valid, test, rules, batches, 1000, 1, budget_s=15.0)
         line["cpu_baseline"] = {k: res[k] for k in ("value", "unit", "cores", "kind", "sample")}
