@@ -262,21 +262,39 @@ def main():
     sk = model._driver(dev)
     cr = model.compiled
 
-    my = batches[rank::world]
     per = args.batches
     n_steps = args.warmup + args.steps
-    step_batches = [[my[(s * per + j) % len(my)] for j in range(per)] for s in range(n_steps)]
+    # query-batch sharding: every global step takes world*per batches and deals them to the ranks
+    # largest-first in snake order of their grounding cost (rows of the head's trie), so that the
+    # per-step all-reduce does not wait for one unlucky rank
+    step_batches = []
+    for s in range(n_steps):
+        glob = [batches[(s * per * world + j) % len(batches)] for j in range(per * world)]
+        order = sorted(range(len(glob)), key=lambda j: -int(cr.head_rows[int(glob[j][0, 1])]))
+        mine = [glob[j] for k, j in enumerate(order) if (k % (2 * world) == rank or k % (2 * world) == 2 * world - 1 - rank)]
+        step_batches.append(mine)
     step_lists = step_batches            # int arrays [n,3] per batch, what the datasets hold (batch_arrays)
     queries_per_step = [sum(len(b) for b in sb) for sb in step_batches]
 
-    def allreduce_and_step(gw, gb):
-        if world > 1:
-            flat = torch.cat([gw, gb])
-            comm.all_reduce_sum_(flat)
+    def start_allreduce(gw, gb):
+        """One flat all-reduce of the gradients, asynchronous w.r.t. the compute stream."""
+        if world == 1:
+            return (gw, gb, None, None)
+        flat = torch.cat([gw, gb])
+        work = torch.distributed.all_reduce(flat, op=torch.distributed.ReduceOp.SUM, async_op=True)
+        return (gw, gb, flat, work)
+
+    def finish_step(pending):
+        gw, gb, flat, work = pending
+        if work is not None:
+            work.wait()
             flat /= world
             gw, gb = flat[:gw.numel()], flat[gw.numel():]
         model.rule_weights.grad, model.bias.grad = gw, gb
         opt.step()
+
+    def allreduce_and_step(gw, gb):
+        finish_step(start_allreduce(gw, gb))
 
     # ---------------- device-resident timing (`value`) ----------------
     slots = [sk.gr.make_slots_host(sl, with_etr=True) for sl in step_lists]       # inputs now in HBM
@@ -301,10 +319,14 @@ def main():
     ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     ev0.record()
     losses = []
+    sk.gr._run(slots[args.warmup], 32)
     for s in range(args.warmup, n_steps):
-        loss, tsum, _, gw, gb = model.step_on_slots(sk, slots[s], 0.2, 1.0 / per)
         ovf_acc += slots[s].overflow   # the frontier workspace is reused by the next step
-        allreduce_and_step(gw, gb)
+        loss, tsum, _, gw, gb = model.step_on_slots(sk, slots[s], 0.2, 1.0 / per, expanded=True)
+        pending = start_allreduce(gw, gb)
+        if s + 1 < n_steps:            # grounding is parameter-independent: run it under the all-reduce
+            sk.gr._run(slots[s + 1], 32)
+        finish_step(pending)
         losses.append(loss)
     ev1.record()
     torch.cuda.synchronize()

@@ -167,13 +167,16 @@ def _group_mask_sum(sl, nzmask, ng):
     return torch.zeros(ng, dtype=torch.float32, device=nzmask.device).index_add_(0, gid, per_slot)
 
 
-def _predictor_step_on_slots(self, sk, sl, smoothing, grad_scale=1.0, bits=32):
+def _predictor_step_on_slots(self, sk, sl, smoothing, grad_scale=1.0, bits=32, expanded=False):
     """Enqueue ground -> aggregate -> CE -> backward for prepared slots (no host sync).
-    Returns the device tensors (loss[ng], tsum[ng], mask_sum[ng] | None, grad_w, grad_b)."""
+    Returns the device tensors (loss[ng], tsum[ng], mask_sum[ng] | None, grad_w, grad_b).
+    expanded=True: the frontier of ``sl`` was already expanded (sk.gr._run) -- grounding does not
+    depend on the parameters, so a caller may run it ahead of the previous step's gradient exchange."""
     device = sk.device
     use_bias = self.entity_feature == "bias"
     gptr, ng = _group_ptr(sl, device)
-    sk.gr._run(sl, bits)
+    if not expanded:
+        sk.gr._run(sl, bits)
     Z, nzmask = sk.predictor_scores(sl, self.rule_weights.detach(), self.bias.detach() if use_bias else None,
                                     not use_bias)
     loss, tsum, G = sk.softmax_ce(sl, Z, nzmask, smoothing, not use_bias, gptr, ng, want_grad=True)
