@@ -6,6 +6,7 @@
 // so every frontier / logit access is one coalesced 128-byte line.  This is HBM/L2-bound
 // integer work: no tensor cores, the levers are coalescing, loads in flight and grid sizing.
 #include "rl_device.cuh"
+#include <stdlib.h>
 
 static thread_local char g_err[512] = "";
 static long long g_launches = 0;   // kernels enqueued through this library (bench.py: gpu_launches)
@@ -258,20 +259,20 @@ __device__ __forceinline__ uint32_t numeric_chunk(const rl_graph &g, const rl_ru
 // one coalesced load and only chunks with a non-zero word are expanded.
 template <typename CT, bool ROOT, bool PRUNE>
 __global__ void __launch_bounds__(WARPS_PER_BLOCK * 32)
-k_numeric(rl_graph g, rl_rules r, rl_slots s, int depth, rl_frontier fr)
+k_numeric(rl_graph g, rl_rules r, rl_slots s, int depth, rl_frontier fr, int cpw)
 {
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const int slot = blockIdx.y;
     const int q = s.slot_head[slot];
     const int32_t *lp = r.lvl_ptr + (size_t)q * (r.max_len + 1);
     const int c_end = lp[depth];
-    const int c0 = lp[depth - 1] + (blockIdx.x * WARPS_PER_BLOCK + warp) * 32;
+    const int c0 = lp[depth - 1] + (blockIdx.x * WARPS_PER_BLOCK + warp) * cpw;   // cpw (<= 32) chunks per warp
     if (c0 >= c_end) return;
     const int hc0 = lp[0];
     uint32_t *mbase = fr.row_mask + (size_t)s.mask_off[slot];
     const int nzb = s.nz_off[slot] - r.head_node_ptr[q];
     const int my_chunk = c0 + lane;
-    uint32_t my_m = my_chunk < c_end ? mbase[my_chunk - hc0] : 0u;
+    uint32_t my_m = (lane < cpw && my_chunk < c_end) ? mbase[my_chunk - hc0] : 0u;
     uint32_t todo = __ballot_sync(FULL, my_m != 0u);
     if (todo == 0u) return;
     const int h = s.lane_h[slot * RL_LANES + lane];
@@ -831,9 +832,13 @@ int rl_expand_level(const rl_graph *g, const rl_rules *r, const rl_slots *s, int
     if (depth == 1) k_symbolic<true><<<gs, WARPS_PER_BLOCK * 32, 0, st>>>(*g, *r, *s, depth, *fr, dense_num, dense_den, force_dense);
     else k_symbolic<false><<<gs, WARPS_PER_BLOCK * 32, 0, st>>>(*g, *r, *s, depth, *fr, dense_num, dense_den, force_dense);
     CHECK_LAUNCH("k_symbolic");
-    dim3 grid((grid_chunks + WARPS_PER_BLOCK * 32 - 1) / (WARPS_PER_BLOCK * 32), s->num_slots);
+    // chunks per warp: many when most chunks are empty (one coalesced read of their bitmap words),
+    // few when every chunk is expanded (more warps in flight to hide the look-up latency)
+    int cpw = force_dense ? 4 : 8;
+    if (const char *e = getenv("RL_CPW")) { int v = atoi(e); if (v >= 1 && v <= 32) cpw = v; }
+    dim3 grid((grid_chunks + WARPS_PER_BLOCK * cpw - 1) / (WARPS_PER_BLOCK * cpw), s->num_slots);
     // force_dense: plain dense SpMM -- every row of every node is written (zeros included) and read
-#define LAUNCH_NUM(CT, ROOT, PRUNE) k_numeric<CT, ROOT, PRUNE><<<grid, WARPS_PER_BLOCK * 32, 0, st>>>(*g, *r, *s, depth, *fr)
+#define LAUNCH_NUM(CT, ROOT, PRUNE) k_numeric<CT, ROOT, PRUNE><<<grid, WARPS_PER_BLOCK * 32, 0, st>>>(*g, *r, *s, depth, *fr, cpw)
     if (fr->count_bits == 32) {
         if (depth == 1) { if (force_dense) LAUNCH_NUM(uint32_t, true, false); else LAUNCH_NUM(uint32_t, true, true); }
         else { if (force_dense) LAUNCH_NUM(uint32_t, false, false); else LAUNCH_NUM(uint32_t, false, true); }
