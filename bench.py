@@ -358,6 +358,13 @@ def main():
         pass
     peak = float(peaks.get("hbm_gbs", 6650.0))
 
+    traffic = None
+    try:      # DRAM bytes of the expansion launches from the committed ncu capture (dense mode, 64 batches/step)
+        with open(os.path.join(ROOT, "profiles", "r1_traffic.json")) as f:
+            traffic = json.load(f)
+    except OSError:
+        pass
+
     def roofline_of(events, heads, step_ms, mode, note):
         exp_ms = {}
         for depth, e0, e1 in events:
@@ -397,9 +404,14 @@ def main():
         dense_events, sk.gr.level_events = sk.gr.level_events, None
         sk.gr.force_dense = False
         heads_d = np.concatenate([slots[s].heads for s in range(args.warmup, args.warmup + nd)])
-        roofline = roofline_of(dense_events, heads_d, d0.elapsed_time(d1), "dense SpMM (force_dense), same kernel + workload",
-                               "every algorithmic byte is moved; timed in a second region right after the product loop "
-                               "(%d steps, no optimizer step)" % nd)
+        roofline = roofline_of(dense_events, heads_d, d0.elapsed_time(d1), "dense expansion (force_dense), same kernel + workload",
+                               "every row of every trie node is expanded (all in-edges examined); rows that are zero for "
+                               "EVERY query (no in-edge from the parent relation's tails) and L2 hits keep DRAM traffic "
+                               "below the algorithmic bytes; timed in a second region right after the product loop "
+                               "(%d steps)" % nd)
+        if traffic is not None and per == 64:
+            roofline["traffic"] = traffic["dram_bytes_per_launch"]
+            roofline["traffic_source"] = traffic["source"]
 
     # ---------------- end-to-end through the public fused API (host lists in, losses out) --------
     torch.cuda.synchronize()
