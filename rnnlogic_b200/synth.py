@@ -19,28 +19,36 @@ def load_shape(name: str) -> dict:
         return json.load(f)
 
 
-def _draw_triples(rng, n_target, half, N, rw, ew, perm, taken: set):
-    """i.i.d. (r ~ rw, h,t ~ Zipf popularity), no self loops / duplicates."""
-    out = np.zeros((0, 3), dtype=np.int64)
-    keys = set()
+def _draw_triples(rng, n_target, half, N, rw, ew, perm, taken):
+    """i.i.d. (r ~ rw, h,t ~ Zipf popularity), no self loops / duplicates / triples
+    already in ``taken`` (a list of sorted int64 key arrays, extended in place).  Fully vectorised."""
+    out_keys = np.zeros(0, dtype=np.int64)
+    order = np.zeros(0, dtype=np.int64)
     cdf_r, cdf_e = np.cumsum(rw), np.cumsum(ew)
-    while out.shape[0] < n_target:
-        k = int((n_target - out.shape[0]) * 1.15) + 16
-        r = np.minimum(np.searchsorted(cdf_r, rng.random(k)), half - 1)
-        h = perm[np.minimum(np.searchsorted(cdf_e, rng.random(k)), N - 1)]
-        t = perm[np.minimum(np.searchsorted(cdf_e, rng.random(k)), N - 1)]
+    while out_keys.shape[0] < n_target:
+        k = int((n_target - out_keys.shape[0]) * 1.2) + 64
+        r = np.minimum(np.searchsorted(cdf_r, rng.random(k)), half - 1).astype(np.int64)
+        h = perm[np.minimum(np.searchsorted(cdf_e, rng.random(k)), N - 1)].astype(np.int64)
+        t = perm[np.minimum(np.searchsorted(cdf_e, rng.random(k)), N - 1)].astype(np.int64)
         key = (r * N + h) * N + t
         ok = h != t
-        _, first = np.unique(key, return_index=True)
+        _, first = np.unique(key, return_index=True)            # first occurrence inside this draw
         uniq = np.zeros(k, dtype=bool)
         uniq[first] = True
         ok &= uniq
-        ok &= np.array([kk not in taken and kk not in keys for kk in key.tolist()], dtype=bool)
-        cand = np.stack([h, r, t], 1)[ok][: n_target - out.shape[0]]
-        keys.update(((cand[:, 1] * N + cand[:, 0]) * N + cand[:, 2]).tolist())
-        out = np.concatenate([out, cand], 0)
-    taken |= keys
-    return out
+        for prev in taken + [out_keys]:
+            if prev.shape[0]:
+                pos = np.minimum(np.searchsorted(prev, key), prev.shape[0] - 1)
+                ok &= prev[pos] != key
+        new = key[ok][: n_target - out_keys.shape[0]]             # draw order kept
+        out_keys = np.sort(np.concatenate([out_keys, new]))
+        order = np.concatenate([order, new])
+    taken.append(out_keys)
+    key = order
+    t = key % N
+    h = (key // N) % N
+    r = key // (N * N)
+    return np.stack([h, r, t], 1)
 
 
 def _with_inverses(base: np.ndarray, half: int) -> np.ndarray:
@@ -60,7 +68,7 @@ def synthetic_kg(shape: dict, seed: int = None, scale: float = 1.0):
     ew = (np.arange(N) + 1.0) ** (-shape["entity_zipf"])
     ew /= ew.sum()
     perm = rng.permutation(N)
-    taken: set = set()
+    taken: list = []
     n_valid, n_test = shape["valid_triples"] // 2, shape["test_triples"] // 2
     valid = _draw_triples(rng, int(n_valid * scale), half, N, rw, ew, perm, taken)
     test = _draw_triples(rng, int(n_test * scale), half, N, rw, ew, perm, taken)
