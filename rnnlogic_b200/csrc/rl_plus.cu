@@ -65,11 +65,13 @@ k_plus_features(rl_graph g, rl_rules r, rl_slots s, rl_frontier fr, const uint32
 {
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const int slot = blockIdx.y;
-    const int e = blockIdx.x * WARPS_PER_BLOCK + warp;
+    const int ew = blockIdx.x * WARPS_PER_BLOCK + warp;           // entity word: 32 entities, one coalesced mask read
     const int N = g.num_entities, R = g.num_relations;
-    if (e >= N) return;
-    const uint32_t bits = nzmask[(size_t)slot * N + e];
-    if (bits == 0u) return;
+    if (ew >= g.rank_words) return;
+    const int e_lane = ew * 32 + lane;
+    const uint32_t my_bits = e_lane < N ? nzmask[(size_t)slot * N + e_lane] : 0u;
+    uint32_t cand_ents = __ballot_sync(FULL, my_bits != 0u);
+    if (cand_ents == 0u) return;
     const int q = s.slot_head[slot];
     const int hc0 = r.lvl_ptr[(size_t)q * (r.max_len + 1)];
     const uint32_t *mbase = fr.row_mask + (size_t)s.mask_off[slot];
@@ -77,6 +79,11 @@ k_plus_features(rl_graph g, rl_rules r, rl_slots s, rl_frontier fr, const uint32
     const CT *arena = reinterpret_cast<const CT *>(fr.arena);
     const int32_t *tp = r.term_ptr + (size_t)q * R;
     const int h = s.lane_h[slot * RL_LANES + lane];
+  while (cand_ents) {
+    const int ei = __ffs(cand_ents) - 1;
+    cand_ents &= cand_ents - 1;
+    const int e = ew * 32 + ei;
+    const uint32_t bits = __shfl_sync(FULL, my_bits, ei);
     const bool mine = (bits >> lane) & 1u;
     const long long idx = cand_off[(size_t)slot * N + e] + __popc(bits & ((1u << lane) - 1u));
     for (int h0 = 0; h0 < H; h0 += HC) {
@@ -133,6 +140,7 @@ k_plus_features(rl_graph g, rl_rules r, rl_slots s, rl_frontier fr, const uint32
             }
         }
     }
+  }
 }
 
 // ------------------------------------------------------------------------------------------
@@ -173,89 +181,65 @@ k_plus_gather(int N, const uint32_t *__restrict__ nzmask, const int64_t *__restr
 // backward into the rule embeddings: gA[rule][h] += sum_cells fp32(count) * dA[cell][h]
 // (and gB from dB for the PNA squared-sum branch).  Block per (slot, rule end).
 // ------------------------------------------------------------------------------------------
+// Entity-centric (like the forward): for every candidate entity, every non-zero terminal row and
+// every query lane with a non-zero count, lanes 0..H-1 add count * dA[cell][h] into gA[rule][h].
 template <typename CT>
-__global__ void __launch_bounds__(128)
+__global__ void __launch_bounds__(WARPS_PER_BLOCK * 32)
 k_plus_backward(rl_graph g, rl_rules r, rl_slots s, rl_frontier fr, const uint32_t *__restrict__ nzmask,
                 const int64_t *__restrict__ cand_off, const int32_t *__restrict__ rule_local, int H,
                 const float *__restrict__ dA, const float *__restrict__ dB, float *__restrict__ gA,
                 float *__restrict__ gB)
 {
-    __shared__ float red[4][2][HC];
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const int slot = blockIdx.y;
+    const int ew = blockIdx.x * WARPS_PER_BLOCK + warp;
     const int N = g.num_entities, R = g.num_relations;
+    if (ew >= g.rank_words) return;
     const int q = s.slot_head[slot];
     const uint32_t *ms = nzmask + (size_t)slot * N;
     const int64_t *co = cand_off + (size_t)slot * N;
-    if (blockIdx.x == 0 && warp == 0 && r.zr_ptr[q + 1] > r.zr_ptr[q]) {   // empty-body rules
-        const int h = s.lane_h[slot * RL_LANES + lane];
-        const uint32_t bits = h >= 0 ? ms[h] : 0u;
-        if ((bits >> lane) & 1u) {
-            const long long idx = co[h] + __popc(bits & ((1u << lane) - 1u));
-            for (int t = r.zr_ptr[q]; t < r.zr_ptr[q + 1]; ++t) {
-                const int lr = rule_local[r.zr_rule[t]];
-                for (int k = 0; k < H; ++k) {
-                    atomicAdd(gA + (size_t)lr * H + k, dA[idx * H + k]);
-                    if (dB) atomicAdd(gB + (size_t)lr * H + k, dB[idx * H + k]);
-                }
-            }
-        }
-    }
-    const int t = r.term_ptr[(size_t)q * R] + blockIdx.x;
-    if (t >= r.term_ptr[(size_t)(q + 1) * R]) return;
-    const int v = r.term_node[t];
-    if (fr.node_cnt[s.nz_off[slot] - r.head_node_ptr[q] + v] == 0) return;
-    const int rho = r.node_rel[v];
-    const int rb = g.dst_ptr[rho], nrows = g.dst_ptr[rho + 1] - rb;
-    const int nw = (nrows + 31) >> 5;
-    const uint32_t *cm = fr.row_mask + (size_t)s.mask_off[slot] + (r.node_chunk0[v] - r.lvl_ptr[(size_t)q * (r.max_len + 1)]);
-    const CT *Xv = reinterpret_cast<const CT *>(fr.arena) + ((size_t)s.arena_off[slot] + r.node_row_off[v]) * RL_LANES;
-    const int lr = rule_local[r.term_rule[t]];
-    for (int h0 = 0; h0 < H; h0 += HC) {
-        float a[HC], b[HC];
-#pragma unroll
-        for (int k = 0; k < HC; ++k) { a[k] = 0.f; b[k] = 0.f; }
-        for (int wi = warp; wi < nw; wi += 4) {
-            uint32_t word = cm[wi];
-            while (word) {
-                const int j = wi * 32 + __ffs(word) - 1;
-                word &= word - 1;
-                const CT c = Xv[(size_t)j * RL_LANES + lane];
-                if (c != 0) {
-                    const int e = __ldg(g.row_dst + rb + j);
-                    const uint32_t bits = ms[e];
-                    const long long idx = co[e] + __popc(bits & ((1u << lane) - 1u));
-                    const float cf = (float)c;
-#pragma unroll
-                    for (int k = 0; k < HC; ++k) {
-                        if (h0 + k < H) {
-                            a[k] += cf * dA[idx * H + h0 + k];
-                            if (dB) b[k] += cf * dB[idx * H + h0 + k];
-                        }
+    const int e_lane = ew * 32 + lane;
+    const uint32_t my_bits = e_lane < N ? ms[e_lane] : 0u;
+    uint32_t cand_ents = __ballot_sync(FULL, my_bits != 0u);
+    if (cand_ents == 0u) return;
+    const int hc0 = r.lvl_ptr[(size_t)q * (r.max_len + 1)];
+    const uint32_t *mbase = fr.row_mask + (size_t)s.mask_off[slot];
+    const size_t abase = (size_t)s.arena_off[slot];
+    const CT *arena = reinterpret_cast<const CT *>(fr.arena);
+    const int32_t *tp = r.term_ptr + (size_t)q * R;
+    const int hq = s.lane_h[slot * RL_LANES + lane];
+    while (cand_ents) {
+        const int ei = __ffs(cand_ents) - 1;
+        cand_ents &= cand_ents - 1;
+        const int e = ew * 32 + ei;
+        const uint32_t bits = __shfl_sync(FULL, my_bits, ei);
+        const long long base = co[e];
+        auto contribute = [&](float cf, int rule) {             // cf = this lane's count (0 if none)
+            const int lr = rule_local[rule];
+            uint32_t nzl = __ballot_sync(FULL, cf != 0.f);
+            for (int h0 = 0; h0 < H; h0 += 32) {
+                float a = 0.f, b = 0.f;
+                uint32_t todo = nzl;
+                while (todo) {
+                    const int bq = __ffs(todo) - 1;
+                    todo &= todo - 1;
+                    const float cb = __shfl_sync(FULL, cf, bq);
+                    const long long idx = base + __popc(bits & ((1u << bq) - 1u));
+                    if (h0 + lane < H) {
+                        a += cb * dA[idx * H + h0 + lane];
+                        if (dB) b += cb * dB[idx * H + h0 + lane];
                     }
                 }
+                if (h0 + lane < H) {
+                    if (a != 0.f) atomicAdd(gA + (size_t)lr * H + h0 + lane, a);
+                    if (dB && b != 0.f) atomicAdd(gB + (size_t)lr * H + h0 + lane, b);
+                }
             }
-        }
-#pragma unroll
-        for (int k = 0; k < HC; ++k) {
-            a[k] = warp_sumf(a[k]);
-            b[k] = warp_sumf(b[k]);
-        }
-        __syncthreads();
-        if (lane == 0) {
-#pragma unroll
-            for (int k = 0; k < HC; ++k) { red[warp][0][k] = a[k]; red[warp][1][k] = b[k]; }
-        }
-        __syncthreads();
-        if (threadIdx.x < HC && h0 + threadIdx.x < H) {
-            const int k = threadIdx.x;
-            const float ta = red[0][0][k] + red[1][0][k] + red[2][0][k] + red[3][0][k];
-            if (ta != 0.f) atomicAdd(gA + (size_t)lr * H + h0 + k, ta);
-            if (dB) {
-                const float tb = red[0][1][k] + red[1][1][k] + red[2][1][k] + red[3][1][k];
-                if (tb != 0.f) atomicAdd(gB + (size_t)lr * H + h0 + k, tb);
-            }
-        }
+        };
+        scan_entity<CT>(g, r, arena, abase, mbase, hc0, tp, e, [&](CT c, int t) { contribute((float)c, r.term_rule[t]); });
+        const bool zr_here = __any_sync(FULL, hq == e);
+        if (zr_here)
+            for (int t = r.zr_ptr[q]; t < r.zr_ptr[q + 1]; ++t) contribute(hq == e ? 1.f : 0.f, r.zr_rule[t]);
     }
 }
 
@@ -294,7 +278,7 @@ int rl_plus_features(const rl_graph *g, const rl_rules *r, const rl_slots *s, co
     if (pna && (!out_sq || !out_min || !out_max || !arg_min || !arg_max || !degree))
         return rl_fail(RL_ERR_ARG, "rl_plus_features: PNA outputs missing");
     if (s->num_slots <= 0) return RL_OK;
-    dim3 grid((g->num_entities + WARPS_PER_BLOCK - 1) / WARPS_PER_BLOCK, s->num_slots);
+    dim3 grid((g->rank_words + WARPS_PER_BLOCK - 1) / WARPS_PER_BLOCK, s->num_slots);
     cudaStream_t st = (cudaStream_t)stream;
 #define LAUNCH_FEAT(CT, P) k_plus_features<CT, P><<<grid, WARPS_PER_BLOCK * 32, 0, st>>>(*g, *r, *s, *fr, nzmask, cand_off, q_off, rule_local, emb, H, out_sum, out_sq, out_min, out_max, arg_min, arg_max, degree, cand_query)
     if (fr->count_bits == 32) { if (pna) LAUNCH_FEAT(uint32_t, true); else LAUNCH_FEAT(uint32_t, false); }
@@ -335,10 +319,11 @@ int rl_plus_backward(const rl_graph *g, const rl_rules *r, const rl_slots *s, co
     if (!g || !r || !s || !nzmask || !cand_off || !rule_local || !dA || !gA || bad_frontier(fr) || H <= 0 || (dB && !gB))
         return rl_fail(RL_ERR_ARG, "rl_plus_backward: bad argument");
     if (s->num_slots <= 0) return RL_OK;
-    dim3 grid(max_terms > 0 ? max_terms : 1, s->num_slots);
+    (void)max_terms;
+    dim3 grid((g->rank_words + WARPS_PER_BLOCK - 1) / WARPS_PER_BLOCK, s->num_slots);
     cudaStream_t st = (cudaStream_t)stream;
-    if (fr->count_bits == 32) k_plus_backward<uint32_t><<<grid, 128, 0, st>>>(*g, *r, *s, *fr, nzmask, cand_off, rule_local, H, dA, dB, gA, gB);
-    else k_plus_backward<unsigned long long><<<grid, 128, 0, st>>>(*g, *r, *s, *fr, nzmask, cand_off, rule_local, H, dA, dB, gA, gB);
+    if (fr->count_bits == 32) k_plus_backward<uint32_t><<<grid, WARPS_PER_BLOCK * 32, 0, st>>>(*g, *r, *s, *fr, nzmask, cand_off, rule_local, H, dA, dB, gA, gB);
+    else k_plus_backward<unsigned long long><<<grid, WARPS_PER_BLOCK * 32, 0, st>>>(*g, *r, *s, *fr, nzmask, cand_off, rule_local, H, dA, dB, gA, gB);
     CHECK_LAUNCH("k_plus_backward");
     return RL_OK;
 }
