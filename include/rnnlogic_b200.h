@@ -251,6 +251,24 @@ int rl_plus_backward(const rl_graph *g, const rl_rules *r, const rl_slots *s, co
                      const uint32_t *nzmask, const int64_t *cand_off, const int32_t *rule_local, int32_t H,
                      const float *dA, const float *dB, int32_t max_terms, float *gA, float *gB, void *stream);
 
+/* Fused dense tail of PredictorPlus with the `sum` aggregator, one thread per candidate cell
+ * (src/layers.py:73-75: Linear(H,H) -> LayerNorm -> ReLU; src/predictors.py:253-255: concat with
+ * relation_emb[head], Linear(2H,J) -> ReLU -> Linear(J,1)).  F[C][H] from rl_plus_features,
+ * cand_head[C] the head relation of each candidate's query, z[C] the candidate scores.  H in {16,32},
+ * J <= 256; row-major weights as in torch (W0[H][H], W1[J][2H], W2[J]). */
+int rl_sum_tail_forward(int64_t C, int32_t H, int32_t J, const float *F, const int32_t *cand_head,
+                        const float *W0, const float *b0, const float *gamma, const float *beta,
+                        const float *W1, const float *b1, const float *W2, const float *b2,
+                        const float *rel_emb, float *z, void *stream);
+/* Backward: recomputes the forward; writes dF[C][H] and the per-candidate factors delta1[C][J],
+ * U[C][2H], dY[C][H], dRel[C][H] (dW1 = delta1^T U, dW0 = dY^T F, d relation_emb = index_add(dRel));
+ * ACCUMULATES the small gradients into g_small = [b0 H | gamma H | beta H | b1 J | W2 J | b2 1]. */
+int rl_sum_tail_backward(int64_t C, int32_t H, int32_t J, const float *F, const int32_t *cand_head,
+                         const float *W0, const float *b0, const float *gamma, const float *beta,
+                         const float *W1, const float *b1, const float *W2, const float *b2,
+                         const float *rel_emb, const float *dz, float *dF, float *delta1, float *U,
+                         float *dY, float *dRel, float *g_small, void *stream);
+
 /* ---- RotatE entity feature (src/embedding.py:28-70) -----------------------------------------
  * out[S][N][32] = gamma - sum_d |h_b o rot(remb[head]) - e|_d for every entity e; eemb fp32[N][2D]
  * (re | im), remb fp32[R][D] (already doubled with the negated copy, embedding.py:23-26).

@@ -12,7 +12,7 @@ import subprocess
 _HERE = os.path.dirname(os.path.abspath(__file__))
 ROOT = os.path.dirname(_HERE)
 LIB_PATH = os.path.join(_HERE, "lib", "librnnlogic_b200.so")
-SOURCES = [os.path.join(_HERE, "csrc", f) for f in ("rl_kernels.cu", "rl_plus.cu", "rl_rotate.cu")]
+SOURCES = [os.path.join(_HERE, "csrc", f) for f in ("rl_kernels.cu", "rl_plus.cu", "rl_rotate.cu", "rl_tail.cu")]
 HEADER = os.path.join(ROOT, "include", "rnnlogic_b200.h")
 
 LANES = 32
@@ -103,6 +103,8 @@ _PROTOS = {
     "rl_plus_gather": (C.c_int, [C.POINTER(RlGraph), C.POINTER(RlSlots), vp, vp, vp, vp, vp]),
     "rl_plus_backward": (C.c_int, [C.POINTER(RlGraph), C.POINTER(RlRules), C.POINTER(RlSlots), C.POINTER(RlFrontier),
                                    vp, vp, vp, C.c_int32, vp, vp, C.c_int32, vp, vp, vp]),
+    "rl_sum_tail_forward": (C.c_int, [C.c_int64, C.c_int32, C.c_int32] + [vp] * 13),
+    "rl_sum_tail_backward": (C.c_int, [C.c_int64, C.c_int32, C.c_int32] + [vp] * 19),
     "rl_rotate_scores": (C.c_int, [C.POINTER(RlGraph), C.POINTER(RlSlots), C.c_int32, C.c_float, vp, vp, vp, vp, vp]),
     "rl_rotate_backward": (C.c_int, [C.POINTER(RlGraph), C.POINTER(RlSlots), C.c_int32, C.c_float, vp, vp, vp, vp, vp,
                                      vp, vp, vp]),

@@ -359,6 +359,48 @@ class _PlusAggregateFn(torch.autograd.Function):
         return g, None
 
 
+class _SumTailFn(torch.autograd.Function):
+    """Fused dense tail for the `sum` aggregator (kernels rl_sum_tail_forward / _backward):
+    z = MLP([relu(LN(Linear(F))), relation_emb[head]]) per candidate."""
+
+    @staticmethod
+    def forward(ctx, F_, cand_head, W0, b0, gamma, beta, W1, b1, W2, b2, rel_w):
+        C_, H = F_.shape
+        J = W1.shape[0]
+        ts = [t.detach().contiguous().float() for t in (F_, W0, b0, gamma, beta, W1, b1, W2, b2, rel_w)]
+        z = torch.empty(C_, dtype=torch.float32, device=F_.device)
+        _lib.check(_lib.lib().rl_sum_tail_forward(C_, H, J, ts[0].data_ptr(), cand_head.data_ptr(),
+                                                  *[t.data_ptr() for t in ts[1:]], z.data_ptr(), _stream()),
+                   "rl_sum_tail_forward")
+        ctx.save_for_backward(cand_head, *ts)
+        return z
+
+    @staticmethod
+    def backward(ctx, dz):
+        cand_head, F_, W0, b0, gamma, beta, W1, b1, W2, b2, rel_w = ctx.saved_tensors
+        C_, H = F_.shape
+        J = W1.shape[0]
+        dev = F_.device
+        dz = dz.contiguous().float()
+        dF = torch.empty_like(F_)
+        delta1 = torch.empty(C_, J, dtype=torch.float32, device=dev)
+        U = torch.empty(C_, 2 * H, dtype=torch.float32, device=dev)
+        dY = torch.empty_like(F_)
+        dRel = torch.empty_like(F_)
+        g_small = torch.zeros(3 * H + 2 * J + 1, dtype=torch.float32, device=dev)
+        _lib.check(_lib.lib().rl_sum_tail_backward(
+            C_, H, J, F_.data_ptr(), cand_head.data_ptr(), W0.data_ptr(), b0.data_ptr(), gamma.data_ptr(),
+            beta.data_ptr(), W1.data_ptr(), b1.data_ptr(), W2.data_ptr(), b2.data_ptr(), rel_w.data_ptr(),
+            dz.data_ptr(), dF.data_ptr(), delta1.data_ptr(), U.data_ptr(), dY.data_ptr(), dRel.data_ptr(),
+            g_small.data_ptr(), _stream()), "rl_sum_tail_backward")
+        dW1 = delta1.t() @ U                                   # the three outer-product gradients: one GEMM each
+        dW0 = dY.t() @ F_
+        drel = torch.zeros_like(rel_w).index_add_(0, cand_head.long(), dRel)
+        db0, dgamma, dbeta = g_small[:H], g_small[H:2 * H], g_small[2 * H:3 * H]
+        db1, dW2, db2 = g_small[3 * H:3 * H + J], g_small[3 * H + J:3 * H + 2 * J], g_small[3 * H + 2 * J:]
+        return dF, None, dW0, db0, dgamma, dbeta, dW1, db1, dW2.view(1, J), db2, drel
+
+
 class _PlusScatterFn(torch.autograd.Function):
     """candidate scores (+ bias, + entity-feature logits) -> entity-major logits Z[S][N][32]."""
 
@@ -410,6 +452,8 @@ class _ToDenseFn(torch.autograd.Function):
 
 
 class PredictorPlus(_RuleModel):
+    fused_tail = True         # `sum` aggregator: run the dense tail in the fused CUDA kernels (rl_tail.cu)
+
     def __init__(self, graph, type='emb', num_layers=3, hidden_dim=16, entity_feature='bias', aggregator='sum',
                  embedding_path=None):
         super(PredictorPlus, self).__init__()
@@ -492,14 +536,27 @@ class PredictorPlus(_RuleModel):
                     self.rule_features = self.rule_features.to(device)
                 emb = self.encode_rules(self.rule_features[rule_ids])
             stats = _PlusAggregateFn.apply(emb, pc)
-            if self.aggregator == 'sum':
-                out = self.rule_to_entity.post(stats[0])
-            else:
-                out = self.rule_to_entity.post(stats[0], stats[1], stats[2], stats[3], pc.degree, pc.cand_query,
-                                               int(sl.q_off[-1]))
             qhead = torch.from_numpy(np.repeat(sl.heads, sl.nq)).to(device)
-            rel = self.relation_emb(qhead[pc.cand_query])
-            zc = self.score_model(torch.cat([out, rel], dim=-1)).squeeze(-1)
+            cand_head = qhead[pc.cand_query]
+            sm = self.score_model
+            fused_tail = (self.fused_tail and self.aggregator == 'sum' and H in (16, 32) and len(sm.layers) == 2
+                          and sm.layers[1].out_features == 1 and sm.layers[0].out_features <= 256
+                          and sm.batch_norms is None and not sm.short_cut and sm.dropout is None)
+            if fused_tail:
+                r2e = self.rule_to_entity
+                lin0 = r2e.add_model.layers[0]
+                zc = _SumTailFn.apply(stats[0], cand_head.to(torch.int32), lin0.weight, lin0.bias,
+                                      r2e.layer_norm.weight, r2e.layer_norm.bias, sm.layers[0].weight,
+                                      sm.layers[0].bias, sm.layers[1].weight, sm.layers[1].bias,
+                                      self.relation_emb.weight)
+            else:
+                if self.aggregator == 'sum':
+                    out = self.rule_to_entity.post(stats[0])
+                else:
+                    out = self.rule_to_entity.post(stats[0], stats[1], stats[2], stats[3], pc.degree, pc.cand_query,
+                                                   int(sl.q_off[-1]))
+                rel = self.relation_emb(cand_head)
+                zc = self.score_model(torch.cat([out, rel], dim=-1)).squeeze(-1)
         bias = self.bias if ef == 'bias' else None
         extra = self.RotatE.slot_scores(sk, sl) if ef == 'RotatE' else None
         Z = _PlusScatterFn.apply(zc, bias, extra, pc, ef not in ('bias', 'RotatE'))
