@@ -251,6 +251,13 @@ int rl_plus_backward(const rl_graph *g, const rl_rules *r, const rl_slots *s, co
                      const uint32_t *nzmask, const int64_t *cand_off, const int32_t *rule_local, int32_t H,
                      const float *dA, const float *dB, int32_t max_terms, float *gA, float *gB, void *stream);
 
+/* E-step statistics, replaces the per-rule dense tensors of Predictor.compute_H
+ * (src/predictors.py:93-112): for slot s, the i-th rule end of the slot's head (i = term index -
+ * term_ptr[head*R]) and lane b: sum_cnt[s][i][b] = sum_e count, pos_cnt[s][i][b] = count at lane_t.
+ * Both fp64 [S][max_terms][32], zeroed by the caller. */
+int rl_rule_stats(const rl_graph *g, const rl_rules *r, const rl_slots *s, const rl_frontier *fr,
+                  int32_t max_terms, double *sum_cnt, double *pos_cnt, void *stream);
+
 /* Fused dense tail of PredictorPlus with the `sum` aggregator, one thread per candidate cell
  * (src/layers.py:73-75: Linear(H,H) -> LayerNorm -> ReLU; src/predictors.py:253-255: concat with
  * relation_emb[head], Linear(2H,J) -> ReLU -> Linear(J,1)).  F[C][H] from rl_plus_features,

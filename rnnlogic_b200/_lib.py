@@ -99,6 +99,8 @@ _PROTOS = {
     "rl_plus_mask": (C.c_int, [C.POINTER(RlGraph), C.POINTER(RlRules), C.POINTER(RlSlots), C.POINTER(RlFrontier), vp, vp, vp]),
     "rl_plus_features": (C.c_int, [C.POINTER(RlGraph), C.POINTER(RlRules), C.POINTER(RlSlots), C.POINTER(RlFrontier),
                                    vp, vp, vp, vp, vp, C.c_int32, C.c_int32, vp, vp, vp, vp, vp, vp, vp, vp, vp]),
+    "rl_rule_stats": (C.c_int, [C.POINTER(RlGraph), C.POINTER(RlRules), C.POINTER(RlSlots), C.POINTER(RlFrontier),
+                                C.c_int32, vp, vp, vp]),
     "rl_plus_scatter": (C.c_int, [C.POINTER(RlGraph), C.POINTER(RlSlots), vp, vp, vp, vp, vp, C.c_int32, vp, vp]),
     "rl_plus_gather": (C.c_int, [C.POINTER(RlGraph), C.POINTER(RlSlots), vp, vp, vp, vp, vp]),
     "rl_plus_backward": (C.c_int, [C.POINTER(RlGraph), C.POINTER(RlRules), C.POINTER(RlSlots), C.POINTER(RlFrontier),

@@ -244,6 +244,44 @@ k_plus_backward(rl_graph g, rl_rules r, rl_slots s, rl_frontier fr, const uint32
 }
 
 // ------------------------------------------------------------------------------------------
+// E-step statistics (Predictor.compute_H, src/predictors.py:82-119): per rule end and query,
+// the count at the query's answer entity and the sum of the counts over all entities.
+// ------------------------------------------------------------------------------------------
+template <typename CT>
+__global__ void __launch_bounds__(WARPS_PER_BLOCK * 32)
+k_rule_stats(rl_graph g, rl_rules r, rl_slots s, rl_frontier fr, int max_terms, double *__restrict__ sum_cnt,
+             double *__restrict__ pos_cnt)
+{
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int slot = blockIdx.y;
+    const int ew = blockIdx.x * WARPS_PER_BLOCK + warp;
+    const int R = g.num_relations;
+    if (ew >= g.rank_words) return;
+    uint32_t act = fr.ent_active[(size_t)slot * g.rank_words + ew];
+    if (act == 0u) return;
+    const int q = s.slot_head[slot];
+    const int hc0 = r.lvl_ptr[(size_t)q * (r.max_len + 1)];
+    const uint32_t *mbase = fr.row_mask + (size_t)s.mask_off[slot];
+    const size_t abase = (size_t)s.arena_off[slot];
+    const CT *arena = reinterpret_cast<const CT *>(fr.arena);
+    const int32_t *tp = r.term_ptr + (size_t)q * R;
+    const int t_first = tp[0];
+    const int ans = s.lane_t[slot * RL_LANES + lane];
+    double *sums = sum_cnt + (size_t)slot * max_terms * RL_LANES;
+    double *poss = pos_cnt + (size_t)slot * max_terms * RL_LANES;
+    while (act) {
+        const int e = ew * 32 + __ffs(act) - 1;
+        act &= act - 1;
+        scan_entity<CT>(g, r, arena, abase, mbase, hc0, tp, e, [&](CT c, int t) {
+            if (c != 0) {
+                atomicAdd(sums + (size_t)(t - t_first) * RL_LANES + lane, (double)c);
+                if (e == ans) poss[(size_t)(t - t_first) * RL_LANES + lane] = (double)c;
+            }
+        });
+    }
+}
+
+// ------------------------------------------------------------------------------------------
 // C-ABI
 // ------------------------------------------------------------------------------------------
 static int bad_frontier(const rl_frontier *fr)
@@ -285,6 +323,19 @@ int rl_plus_features(const rl_graph *g, const rl_rules *r, const rl_slots *s, co
     else { if (pna) LAUNCH_FEAT(unsigned long long, true); else LAUNCH_FEAT(unsigned long long, false); }
 #undef LAUNCH_FEAT
     CHECK_LAUNCH("k_plus_features");
+    return RL_OK;
+}
+
+int rl_rule_stats(const rl_graph *g, const rl_rules *r, const rl_slots *s, const rl_frontier *fr, int32_t max_terms,
+                  double *sum_cnt, double *pos_cnt, void *stream)
+{
+    if (!g || !r || !s || !sum_cnt || !pos_cnt || bad_frontier(fr) || max_terms <= 0) return rl_fail(RL_ERR_ARG, "rl_rule_stats: bad argument");
+    if (s->num_slots <= 0) return RL_OK;
+    dim3 grid((g->rank_words + WARPS_PER_BLOCK - 1) / WARPS_PER_BLOCK, s->num_slots);
+    cudaStream_t st = (cudaStream_t)stream;
+    if (fr->count_bits == 32) k_rule_stats<uint32_t><<<grid, WARPS_PER_BLOCK * 32, 0, st>>>(*g, *r, *s, *fr, max_terms, sum_cnt, pos_cnt);
+    else k_rule_stats<unsigned long long><<<grid, WARPS_PER_BLOCK * 32, 0, st>>>(*g, *r, *s, *fr, max_terms, sum_cnt, pos_cnt);
+    CHECK_LAUNCH("k_rule_stats");
     return RL_OK;
 }
 

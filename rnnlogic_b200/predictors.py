@@ -114,30 +114,47 @@ class Predictor(_RuleModel):
 
     @torch.no_grad()
     def compute_H(self, all_h, all_r, all_t, edges_to_remove):
-        """E-step rule scores (src/predictors.py:82-119)."""
-        query_r, sk, sl = self._ground(all_h, all_r, edges_to_remove)
+        """E-step rule scores (src/predictors.py:82-119): per rule H = score[b,t] - mean over the
+        batch's candidates of score[b,.], softmax over the head's rules, summed over the queries.
+        The per-rule statistics come from one kernel (rl_rule_stats); no [R_q,B,N] tensor exists."""
+        query_r = all_r[0].item()
+        assert (all_r != query_r).sum() == 0
+        device = all_r.device
         ids = self.compiled.head_rules[query_r]
         if len(ids) == 0:
             return None, None
-        device = all_r.device
-        all_t = all_t.to(device)
-        B, N = all_h.size(0), self.num_entities
-        neg = torch.zeros(B, N, dtype=torch.bool, device=device)
-        pos_cnt = torch.empty(len(ids), B, dtype=torch.float32, device=device)
-        sum_cnt = torch.empty(len(ids), B, dtype=torch.float32, device=device)
-        for c0 in range(0, len(ids), 64):
-            chunk = ids[c0:c0 + 64]
-            x = sk.gr.rule_counts(sl, chunk)                              # [k,B,N] int64
-            neg |= (x != 0).any(0)
-            xf = x.float()
-            pos_cnt[c0:c0 + len(chunk)] = xf.gather(2, all_t.view(1, B, 1).expand(len(chunk), B, 1)).squeeze(2)
-            sum_cnt[c0:c0 + len(chunk)] = xf.sum(2)
-        w = self.rule_weights[torch.tensor(ids, device=device)].unsqueeze(1)
-        pos_score = pos_cnt * w                                           # pos_index has exactly one entry per row
-        neg_n = torch.clamp(neg.sum(1), min=1).unsqueeze(0)
-        # (score * neg_index).sum(1): counts are zero outside neg_index, so the plain row sum is the same
-        neg_score = sum_cnt * w / neg_n
-        H = torch.softmax((pos_score - neg_score).t(), dim=-1).sum(0)
+        sk = self._driver(device)
+        sl = sk.gr.make_slots([query_r], [all_h.size(0)], all_h, all_t.to(device), edges_to_remove)
+        sk.gr.ground(sl)
+        cr = self.compiled
+        R = self.num_relations
+        n_terms = max(1, int(cr.head_terms[query_r]))
+        stats = torch.zeros(2, sl.S, n_terms, LANES, dtype=torch.float64, device=device)
+        nzmask = torch.empty(sl.S, sk.N, dtype=torch.int32, device=device)
+        cand_cnt = torch.empty(sl.S * sk.N, dtype=torch.int32, device=device)
+        L = _lib.lib()
+        _lib.check(L.rl_plus_mask(sk.dg.ref(), sk.dr.ref(), sl.ref(), sl.fref(), nzmask.data_ptr(), cand_cnt.data_ptr(),
+                                  _stream()), "rl_plus_mask")
+        _lib.check(L.rl_rule_stats(sk.dg.ref(), sk.dr.ref(), sl.ref(), sl.fref(), n_terms, stats[0].data_ptr(),
+                                   stats[1].data_ptr(), _stream()), "rl_rule_stats")
+        B = all_h.size(0)
+        lanes = torch.arange(LANES, device=device, dtype=torch.int32)
+        per_lane = ((nzmask.unsqueeze(-1) >> lanes) & 1).sum(1)                    # [S,32] candidates per query
+        valid = torch.from_numpy(np.concatenate([s_ * LANES + np.arange(n) for s_, n in enumerate(sl.nq)])).to(device)
+        neg_n = torch.clamp(per_lane.reshape(-1)[valid], min=1).to(torch.float32)    # [B]
+        # [S,T,32] -> [B,T] in query order, then pick the head's rules in rule-file order
+        to_q = lambda x: x.permute(0, 2, 1).reshape(sl.S * LANES, n_terms)[valid]
+        sum_q, pos_q = to_q(stats[0]), to_q(stats[1])
+        term_local = torch.from_numpy(cr.rule_term[ids] - cr.term_ptr_host[query_r * R]).to(device)
+        has_body = term_local >= 0                                                   # empty-body rules: count = one_hot(h)
+        tl = term_local.clamp(min=0)
+        sum_c = torch.where(has_body.unsqueeze(0), sum_q[:, tl], torch.ones(B, len(ids), dtype=torch.float64, device=device))
+        at_h = (all_h == all_t.to(device)).to(torch.float64).unsqueeze(1)
+        pos_c = torch.where(has_body.unsqueeze(0), pos_q[:, tl], at_h.expand(B, len(ids)))
+        w = self.rule_weights[torch.tensor(ids, device=device)].unsqueeze(0)
+        pos_score = pos_c.float() * w
+        neg_score = sum_c.float() * w / neg_n.unsqueeze(1)
+        H = torch.softmax(pos_score - neg_score, dim=-1).sum(0)
         return H, torch.tensor(ids, dtype=torch.long, device=device)
 
 

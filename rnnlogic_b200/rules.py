@@ -124,6 +124,9 @@ class CompiledRules:
         self.head_terms = term_ptr[(np.arange(R) + 1) * R] - term_ptr[np.arange(R) * R]
         self.rule_node = np.full(self.num_rules, -1, dtype=np.int64)
         self.rule_node[t_rule] = t_node
+        self.rule_term = np.full(self.num_rules, -1, dtype=np.int64)        # global term index of a rule (-1: empty body)
+        self.rule_term[t_rule] = np.arange(t_rule.shape[0])
+        self.term_ptr_host = term_ptr
         node_nterm = np.bincount(t_node, minlength=max(1, self.num_nodes))
         zr_ptr = np.zeros(R + 1, dtype=np.int64)
         np.cumsum([len(z) for z in zero_rules], out=zr_ptr[1:])
