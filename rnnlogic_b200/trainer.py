@@ -223,5 +223,5 @@ def summarize_ranks(model, ranks: torch.Tensor, expectation: bool, num_entities:
     sk = next(iter(model._drivers.values()))
     sums = sk.rank_metrics(ranks[:, 3:5].contiguous(), torch.from_numpy(w).to(ranks.device), expectation).cpu().numpy()
     n = max(1, host.shape[0])
-    return {"data": int(w.sum()), "hit1": sums[0] / n, "hit3": sums[1] / n, "hit10": sums[2] / n,
-            "mr": sums[3] / n, "mrr": sums[4] / n}
+    return {"data": int(w.sum()), "hit1": float(sums[0] / n), "hit3": float(sums[1] / n), "hit10": float(sums[2] / n),
+            "mr": float(sums[3] / n), "mrr": float(sums[4] / n)}

@@ -44,5 +44,5 @@ else:
     solver.train(batch_per_epoch=12, smoothing=0.2, print_every=1000)
 mrr = solver.evaluate("valid", expectation=True)
 if rank == 0:
-    torch.save({"sd": {k: v.detach().cpu() for k, v in model.state_dict().items()}, "mrr": mrr}, out)
+    torch.save({"sd": {k: v.detach().cpu() for k, v in model.state_dict().items()}, "mrr": float(mrr)}, out)
 comm.synchronize()
