@@ -95,6 +95,11 @@ typedef struct rl_rules {
      *  rows(rel), chunk0, parent chunk0, nterm} -- one load instead of a look-up chain */
     const int32_t *node_rec;      /* [num_nodes*8] */
     const int64_t *node_prow_off; /* [num_nodes] node_row_off of the parent (0 for depth 1) */
+    /* symbolic-phase work items: (node, first parent bitmap word); one item per 32 parent words
+     * (one item per node at depth 1); lvl_sym_ptr is indexed like lvl_ptr */
+    const int32_t *lvl_sym_ptr;   /* [R*(max_len+1)] */
+    const int32_t *sym_node;      /* [#items] */
+    const int32_t *sym_w0;        /* [#items] */
 } rl_rules;
 
 /* One call's queries, cut into slots (<= 32 queries of one head relation each). */
@@ -151,8 +156,8 @@ int rl_prepare_slots(const rl_graph *g, int32_t num_slots, const int32_t *slot_h
  * KnowledgeGraph.propagate (src/data.py:149-173) for all rules of the head at once.  Two
  * launches: k_symbolic (which destination rows can be non-zero -> row_mask) and k_numeric (the
  * segmented pull SpMM over those rows, query edge removed on hops of the head relation).
- * grid_nodes / grid_chunks = max over the call's slots of the number of trie nodes / chunks at
- * this depth.  A node whose parent has more than dense_num/dense_den of its rows valid takes all
+ * grid_nodes / grid_chunks = max over the call's slots of the number of symbolic work items
+ * (lvl_sym_ptr) / chunks at this depth.  A node whose parent has more than dense_num/dense_den of its rows valid takes all
  * its rows; force_dense != 0 does that for every node (plain dense SpMM: every algorithmic byte
  * of SURVEY.md 8d is moved -- the mode the roofline figure is quoted on). */
 int rl_expand_level(const rl_graph *g, const rl_rules *r, const rl_slots *s, int32_t depth,

@@ -39,7 +39,8 @@ class RlRules(C.Structure):
                 ("node_rel", vp), ("node_parent", vp), ("node_row_off", vp), ("head_node_ptr", vp),
                 ("lvl_ptr", vp), ("chunk_node", vp), ("chunk_row0", vp), ("term_ptr", vp),
                 ("term_node", vp), ("term_rule", vp), ("zr_ptr", vp), ("zr_rule", vp),
-                ("lvl_node_ptr", vp), ("node_chunk0", vp), ("node_nterm", vp), ("node_rec", vp), ("node_prow_off", vp)]
+                ("lvl_node_ptr", vp), ("node_chunk0", vp), ("node_nterm", vp), ("node_rec", vp), ("node_prow_off", vp),
+                ("lvl_sym_ptr", vp), ("sym_node", vp), ("sym_w0", vp)]
 
 
 class RlSlots(C.Structure):

@@ -86,6 +86,8 @@ __device__ __forceinline__ void mark_out_edges(const rl_graph &g, int rho, int e
     }
 }
 
+// Work item = (trie node, block of 32 parent bitmap words): hub relations with thousands of valid
+// parent rows are spread over many warps instead of serialising in one.
 template <bool ROOT>
 __global__ void __launch_bounds__(WARPS_PER_BLOCK * 32)
 k_symbolic(rl_graph g, rl_rules r, rl_slots s, int depth, rl_frontier fr, int dense_num, int dense_den, int force_dense)
@@ -93,9 +95,10 @@ k_symbolic(rl_graph g, rl_rules r, rl_slots s, int depth, rl_frontier fr, int de
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const int slot = blockIdx.y;
     const int q = s.slot_head[slot];
-    const int32_t *np = r.lvl_node_ptr + (size_t)q * (r.max_len + 1);
-    const int v = np[depth - 1] + blockIdx.x * WARPS_PER_BLOCK + warp;
-    if (v >= np[depth]) return;
+    const int32_t *ip = r.lvl_sym_ptr + (size_t)q * (r.max_len + 1);
+    const int item = ip[depth - 1] + blockIdx.x * WARPS_PER_BLOCK + warp;
+    if (item >= ip[depth]) return;
+    const int v = r.sym_node[item], w0 = r.sym_w0[item];
     const int4 ra = __ldg(reinterpret_cast<const int4 *>(r.node_rec) + 2 * (size_t)v);
     const int4 rb4 = __ldg(reinterpret_cast<const int4 *>(r.node_rec) + 2 * (size_t)v + 1);
     const int rho = ra.x;
@@ -119,8 +122,9 @@ k_symbolic(rl_graph g, rl_rules r, rl_slots s, int depth, rl_frontier fr, int de
         pm = mbase + (rb4.z - hc0);
     }
     if (dense) {
-        for (int w = lane; w < nw; w += 32)
-            cm[w] = (w == nw - 1 && (D & 31)) ? ((1u << (D & 31)) - 1u) : 0xffffffffu;
+        if (w0 == 0)                                            // the node's first item fills the whole bitmap
+            for (int w = lane; w < nw; w += 32)
+                cm[w] = (w == nw - 1 && (D & 31)) ? ((1u << (D & 31)) - 1u) : 0xffffffffu;
         return;
     }
     if (ROOT) {
@@ -129,13 +133,29 @@ k_symbolic(rl_graph g, rl_rules r, rl_slots s, int depth, rl_frontier fr, int de
     } else {
         const int nwp = (Dp + 31) >> 5;
         const int pb = g.dst_ptr[rho_p];
-        for (int w0 = 0; w0 < nwp; w0 += 32) {
-            const int wi = w0 + lane;
-            uint32_t word = wi < nwp ? pm[wi] : 0u;
-            while (word) {
-                const int bit = __ffs(word) - 1;
-                word &= word - 1;
-                mark_out_edges(g, rho, __ldg(g.row_dst + pb + wi * 32 + bit), cm);
+        const int wi = w0 + lane;
+        uint32_t word = wi < nwp ? pm[wi] : 0u;
+        // spread the valid parent rows of these 32 words evenly over the lanes
+        const int mine = __popc(word);
+        int P = mine;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) {
+            const int t = __shfl_up_sync(FULL, P, o);
+            if (lane >= o) P += t;
+        }
+        const int T = __shfl_sync(FULL, P, 31);
+        const int first = P - mine;
+        for (int base = 0; base < T; base += 32) {
+            const int k = min(base + lane, T - 1);
+            int src_lane = 0;
+#pragma unroll
+            for (int step = 16; step > 0; step >>= 1)
+                if (__shfl_sync(FULL, P, src_lane + step - 1) <= k) src_lane += step;
+            const uint32_t wsel = __shfl_sync(FULL, word, src_lane);
+            const int nth = k - __shfl_sync(FULL, first, src_lane);
+            if (base + lane < T) {
+                const int bit = __fns(wsel, 0, nth + 1);
+                mark_out_edges(g, rho, __ldg(g.row_dst + pb + (w0 + src_lane) * 32 + bit), cm);
             }
         }
     }
@@ -828,7 +848,7 @@ int rl_expand_level(const rl_graph *g, const rl_rules *r, const rl_slots *s, int
     if (dense_den <= 0 || dense_num < 0) return fail(RL_ERR_ARG, "rl_expand_level: bad dense threshold");
     if (grid_chunks <= 0 || grid_nodes <= 0 || s->num_slots <= 0) return RL_OK;
     cudaStream_t st = (cudaStream_t)stream;
-    dim3 gs((grid_nodes + WARPS_PER_BLOCK - 1) / WARPS_PER_BLOCK, s->num_slots);
+    dim3 gs((grid_nodes + WARPS_PER_BLOCK - 1) / WARPS_PER_BLOCK, s->num_slots);   // grid_nodes = symbolic work items
     if (depth == 1) k_symbolic<true><<<gs, WARPS_PER_BLOCK * 32, 0, st>>>(*g, *r, *s, depth, *fr, dense_num, dense_den, force_dense);
     else k_symbolic<false><<<gs, WARPS_PER_BLOCK * 32, 0, st>>>(*g, *r, *s, depth, *fr, dense_num, dense_den, force_dense);
     CHECK_LAUNCH("k_symbolic");

@@ -160,7 +160,7 @@ class Grounder:
                                       base + 4 * (n_mask + n_cnt), sl.overflow.data_ptr())
         L = _lib.lib()
         lc = self.cr.level_chunks[sl.heads]                               # [S, max_len]
-        ln = self.cr.level_nodes[sl.heads]
+        ln = self.cr.level_sym_items[sl.heads]
         for depth in range(1, self.cr.max_len + 1):
             gc, gn = int(lc[:, depth - 1].max()), int(ln[:, depth - 1].max())
             if gc == 0:

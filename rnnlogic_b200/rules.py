@@ -160,6 +160,19 @@ class CompiledRules:
             rec[:, 6] = np.where(has_p, cstart[:-1][psafe], 0)
             rec[:, 7] = node_nterm[:self.num_nodes]
         node_prow_off = np.where(has_p, node_row_off[psafe], 0) if self.num_nodes else np.zeros(0, np.int64)
+        # symbolic work items: one per 32 parent bitmap words (1024 parent rows); one per node at depth 1
+        if self.num_nodes:
+            pwords = np.where(has_p, (node_rows[psafe] + 31) // 32, 1)
+            n_items = np.maximum(1, (pwords + 31) // 32)
+            sym_node = np.repeat(np.arange(self.num_nodes), n_items)
+            istart = np.zeros(self.num_nodes + 1, dtype=np.int64)
+            np.cumsum(n_items, out=istart[1:])
+            sym_w0 = (np.arange(sym_node.shape[0]) - istart[sym_node]) * 32
+            lvl_sym_ptr = istart[first_node].reshape(R, L1)
+        else:
+            sym_node = sym_w0 = np.zeros(0, np.int64)
+            lvl_sym_ptr = np.zeros((R, L1), dtype=np.int64)
+        self.level_sym_items = np.diff(lvl_sym_ptr, axis=1)
         i32 = lambda a: np.ascontiguousarray(a, dtype=np.int32)
         if self.num_chunks >= 2 ** 31 or self.num_nodes >= 2 ** 31:
             raise ValueError("rule set too large for 32-bit work tables")
@@ -171,6 +184,7 @@ class CompiledRules:
             "term_node": i32(t_node), "term_rule": i32(t_rule), "zr_ptr": i32(zr_ptr), "zr_rule": i32(zr_rule),
             "lvl_node_ptr": i32(lvl_node_ptr.reshape(-1)), "node_chunk0": i32(cstart[:-1]), "node_nterm": i32(node_nterm),
             "node_rec": i32(rec.reshape(-1)), "node_prow_off": np.ascontiguousarray(node_prow_off, dtype=np.int64),
+            "lvl_sym_ptr": i32(lvl_sym_ptr.reshape(-1)), "sym_node": i32(sym_node), "sym_w0": i32(sym_w0),
         }
         self._devices = {}
 
@@ -194,7 +208,8 @@ class DeviceRules:
             t["chunk_row0"].data_ptr(), t["term_ptr"].data_ptr(), t["term_node"].data_ptr(),
             t["term_rule"].data_ptr(), t["zr_ptr"].data_ptr(), t["zr_rule"].data_ptr(),
             t["lvl_node_ptr"].data_ptr(), t["node_chunk0"].data_ptr(), t["node_nterm"].data_ptr(),
-            t["node_rec"].data_ptr(), t["node_prow_off"].data_ptr())
+            t["node_rec"].data_ptr(), t["node_prow_off"].data_ptr(), t["lvl_sym_ptr"].data_ptr(),
+            t["sym_node"].data_ptr(), t["sym_w0"].data_ptr())
 
     def ref(self):
         return C.byref(self.struct)
