@@ -127,6 +127,15 @@ typedef struct rl_frontier {
     int32_t *overflow;     /* set to 1 when a 32-bit count overflowed */
 } rl_frontier;
 
+/* Optional forward->backward hand-over: the aggregation records every (row, rule end, entity)
+ * triple it read, S regions of cap_per_slot int32x4 records; count[S] (zeroed by the caller) may
+ * exceed the capacity, in which case the backward walks the tables again for that slot. */
+typedef struct rl_items {
+    int32_t cap_per_slot;
+    int32_t *items;   /* [S * cap_per_slot * 4], 16-byte aligned */
+    int32_t *count;   /* [S] */
+} rl_items;
+
 /* Known-answer lists, replaces KnowledgeGraph.hr2o / hr2oo / hr2ooo (src/data.py:36-38,49-61,
  * 79-99): sorted keys r*N+h, CSR of de-duplicated tails.  Used for the smoothed multi-hot
  * target (data.py:207-212) and the eval filter (data.py:250-254, 287-291). */
@@ -176,7 +185,8 @@ int rl_node_counts_dense(const rl_graph *g, const rl_rules *r, const rl_slots *s
  * fill_neg_inf != 0 cells with a clear bit get -inf (entity_feature != 'bias'). */
 int rl_predictor_scores(const rl_graph *g, const rl_rules *r, const rl_slots *s,
                         const rl_frontier *fr, const float *rule_weights, const float *bias,
-                        int32_t fill_neg_inf, float *Z, uint32_t *nzmask, void *stream);
+                        int32_t fill_neg_inf, float *Z, uint32_t *nzmask, const rl_items *items,
+                        void *stream);
 
 /* Kernel (2b): log(softmax + 1e-8) cross-entropy against the smoothed target, replaces
  * src/trainer.py:84,88-89, fused with its backward.  target = smoothing * multi_hot(train
@@ -198,7 +208,8 @@ int rl_softmax_ce(const rl_graph *g, const rl_slots *s, const rl_answers *train_
  * into (zero them first): grad_w[i] += sum_s slot_scale[s] * <G_s, fp32(count_i)>. */
 int rl_predictor_backward(const rl_graph *g, const rl_rules *r, const rl_slots *s,
                           const rl_frontier *fr, const float *G, const float *slot_scale,
-                          int32_t max_terms, float *grad_w, float *grad_bias, void *stream);
+                          int32_t max_terms, float *grad_w, float *grad_bias, const rl_items *items,
+                          void *stream);
 
 /* Kernel (3): filtered rank bounds, replaces src/trainer.py:189-201.  LH[S*32][2] int64:
  * L = #{e not known: z_e > z_t} + 1, H = #{e not known: z_e >= z_t} + 2; (1, N+1) when the

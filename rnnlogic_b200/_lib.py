@@ -53,6 +53,10 @@ class RlFrontier(C.Structure):
                 ("ent_active", vp), ("overflow", vp)]
 
 
+class RlItems(C.Structure):
+    _fields_ = [("cap_per_slot", C.c_int32), ("items", vp), ("count", vp)]
+
+
 class RlAnswers(C.Structure):
     _fields_ = [("num_keys", C.c_int64), ("keys", vp), ("ptr", vp), ("ent", vp)]
 
@@ -87,12 +91,12 @@ _PROTOS = {
     "rl_node_counts_dense": (C.c_int, [C.POINTER(RlGraph), C.POINTER(RlRules), C.POINTER(RlSlots), C.c_int32,
                                        C.c_int32, C.POINTER(RlFrontier), vp, vp]),
     "rl_predictor_scores": (C.c_int, [C.POINTER(RlGraph), C.POINTER(RlRules), C.POINTER(RlSlots),
-                                      C.POINTER(RlFrontier), vp, vp, C.c_int32, vp, vp, vp]),
+                                      C.POINTER(RlFrontier), vp, vp, C.c_int32, vp, vp, C.POINTER(RlItems), vp]),
     "rl_softmax_blocks": (C.c_int, [C.c_int32]),
     "rl_softmax_ce": (C.c_int, [C.POINTER(RlGraph), C.POINTER(RlSlots), C.POINTER(RlAnswers), C.c_float,
                                 C.c_int32, vp, vp, C.c_int32, vp, vp, vp, vp, vp, vp, vp, vp]),
     "rl_predictor_backward": (C.c_int, [C.POINTER(RlGraph), C.POINTER(RlRules), C.POINTER(RlSlots),
-                                        C.POINTER(RlFrontier), vp, vp, C.c_int32, vp, vp, vp]),
+                                        C.POINTER(RlFrontier), vp, vp, C.c_int32, vp, vp, C.POINTER(RlItems), vp]),
     "rl_filtered_rank": (C.c_int, [C.POINTER(RlGraph), C.POINTER(RlSlots), C.POINTER(RlAnswers), C.c_int32,
                                    vp, vp, vp, vp, vp]),
     "rl_filtered_rank_dense": (C.c_int, [C.c_int64, C.c_int64, vp, vp, vp, vp, vp, vp]),

@@ -351,7 +351,7 @@ template <typename CT>
 __global__ void __launch_bounds__(WARPS_PER_BLOCK * 32)
 k_predictor_scores(rl_graph g, rl_rules r, rl_slots s, rl_frontier fr, const float *__restrict__ w,
                    const float *__restrict__ bias, int fill_neg_inf, float *__restrict__ Z,
-                   uint32_t *__restrict__ nzmask)
+                   uint32_t *__restrict__ nzmask, int4 *__restrict__ items, int *__restrict__ item_count, int item_cap)
 {
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const int slot = blockIdx.y;
@@ -371,6 +371,7 @@ k_predictor_scores(rl_graph g, rl_rules r, rl_slots s, rl_frontier fr, const flo
     double zsum = 0.0;
     if (z1 > z0) for (int t = z0; t < z1; ++t) zsum += (double)__ldg(w + r.zr_rule[t]);
     const int e1 = min(32, N - ew * 32);
+    ItemSink sink{items ? items + (size_t)slot * item_cap : nullptr, item_count ? item_count + slot : nullptr, item_cap};
     for (int i = 0; i < e1; ++i) {
         const int e = ew * 32 + i;
         double acc = 0.0;
@@ -381,7 +382,7 @@ k_predictor_scores(rl_graph g, rl_rules r, rl_slots s, rl_frontier fr, const flo
                     acc += (double)(float)c * (double)__ldg(w + r.term_rule[t]);   // x.float() * w (predictors.py:64)
                     any = true;
                 }
-            });
+            }, items ? &sink : nullptr);
             if (h == e && z1 > z0) { acc += zsum; any = true; }   // empty-body rules: count = one_hot(h)
         }
         float z = (float)acc;
@@ -589,10 +590,12 @@ k_grad_sparse(rl_graph g, rl_slots s, rl_answers ans, float smoothing, int use_m
 template <typename CT>
 __global__ void __launch_bounds__(WARPS_PER_BLOCK * 32)
 k_predictor_bwd_w(rl_graph g, rl_rules r, rl_slots s, rl_frontier fr, const float *__restrict__ G,
-                  const float *__restrict__ slot_scale, float *__restrict__ grad_w)
+                  const float *__restrict__ slot_scale, float *__restrict__ grad_w,
+                  const int *__restrict__ item_count, int item_cap)
 {
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const int slot = blockIdx.y;
+    if (item_count && item_count[slot] <= item_cap) return;      // this slot was done from its item list
     const int ew = blockIdx.x * WARPS_PER_BLOCK + warp;           // entity word
     const int N = g.num_entities, R = g.num_relations;
     if (ew >= g.rank_words) return;
@@ -623,6 +626,42 @@ k_predictor_bwd_w(rl_graph g, rl_rules r, rl_slots s, rl_frontier fr, const floa
             v = warp_sum(v);
             if (lane == 0 && v != 0.0) atomicAdd(grad_w + r.term_rule[t], (float)v * scale);
         });
+    }
+}
+
+// Backward over the item list recorded by the forward: one warp per (row, rule end) item.
+// A slot whose list overflowed is left to k_predictor_bwd_w (which otherwise skips it).
+#define ITEM_BLOCKS 32
+template <typename CT>
+__global__ void __launch_bounds__(WARPS_PER_BLOCK * 32)
+k_predictor_bwd_items(rl_graph g, rl_rules r, rl_slots s, rl_frontier fr, const float *__restrict__ G,
+                      const float *__restrict__ slot_scale, const int4 *__restrict__ items,
+                      const int *__restrict__ item_count, int item_cap, float *__restrict__ grad_w)
+{
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int slot = blockIdx.y;
+    const int n = item_count[slot];
+    if (n > item_cap) return;                                     // overflow: the scanning kernel handles this slot
+    const int N = g.num_entities;
+    const int q = s.slot_head[slot];
+    const float scale = slot_scale ? slot_scale[slot] : 1.f;
+    const float *Gs = G + (size_t)slot * N * RL_LANES;
+    const int z0 = r.zr_ptr[q], z1 = r.zr_ptr[q + 1];
+    if (blockIdx.x == 0 && warp == 0 && z1 > z0) {                 // empty-body rules: count = one_hot(h)
+        const int h = s.lane_h[slot * RL_LANES + lane];
+        double v = h >= 0 ? (double)Gs[(size_t)h * RL_LANES + lane] : 0.0;
+        v = warp_sum(v);
+        if (lane == 0)
+            for (int t = z0; t < z1; ++t) atomicAdd(grad_w + r.zr_rule[t], (float)v * scale);
+    }
+    const CT *arena = reinterpret_cast<const CT *>(fr.arena) + (size_t)s.arena_off[slot] * RL_LANES;
+    const int4 *it = items + (size_t)slot * item_cap;
+    for (int i = blockIdx.x * WARPS_PER_BLOCK + warp; i < n; i += ITEM_BLOCKS * WARPS_PER_BLOCK) {
+        const int4 rec = __ldg(it + i);                            // {row, rule end, entity, -}
+        const CT c = arena[(size_t)rec.x * RL_LANES + lane];
+        double v = c != 0 ? (double)(float)c * (double)Gs[(size_t)rec.z * RL_LANES + lane] : 0.0;
+        v = warp_sum(v);
+        if (lane == 0 && v != 0.0) atomicAdd(grad_w + r.term_rule[rec.y], (float)v * scale);
     }
 }
 
@@ -886,15 +925,19 @@ int rl_node_counts_dense(const rl_graph *g, const rl_rules *r, const rl_slots *s
 
 int rl_predictor_scores(const rl_graph *g, const rl_rules *r, const rl_slots *s, const rl_frontier *fr,
                         const float *w, const float *bias, int32_t fill_neg_inf, float *Z, uint32_t *nzmask,
-                        void *stream)
+                        const rl_items *it, void *stream)
 {
+    if (it && (!it->items || !it->count || it->cap_per_slot <= 0)) return fail(RL_ERR_ARG, "rl_predictor_scores: incomplete rl_items");
+    int4 *items = it ? reinterpret_cast<int4 *>(it->items) : nullptr;
+    int *icount = it ? it->count : nullptr;
+    const int icap = it ? it->cap_per_slot : 0;
     if (!g || !r || !s || !w || !Z || !nzmask) return fail(RL_ERR_ARG, "rl_predictor_scores: null argument");
     if (check_frontier(fr, "rl_predictor_scores: incomplete rl_frontier") != RL_OK) return RL_ERR_ARG;
     if (s->num_slots <= 0) return RL_OK;
     dim3 grid((g->rank_words + WARPS_PER_BLOCK - 1) / WARPS_PER_BLOCK, s->num_slots);
     cudaStream_t st = (cudaStream_t)stream;
-    if (fr->count_bits == 32) k_predictor_scores<uint32_t><<<grid, WARPS_PER_BLOCK * 32, 0, st>>>(*g, *r, *s, *fr, w, bias, fill_neg_inf, Z, nzmask);
-    else k_predictor_scores<unsigned long long><<<grid, WARPS_PER_BLOCK * 32, 0, st>>>(*g, *r, *s, *fr, w, bias, fill_neg_inf, Z, nzmask);
+    if (fr->count_bits == 32) k_predictor_scores<uint32_t><<<grid, WARPS_PER_BLOCK * 32, 0, st>>>(*g, *r, *s, *fr, w, bias, fill_neg_inf, Z, nzmask, items, icount, icap);
+    else k_predictor_scores<unsigned long long><<<grid, WARPS_PER_BLOCK * 32, 0, st>>>(*g, *r, *s, *fr, w, bias, fill_neg_inf, Z, nzmask, items, icount, icap);
     CHECK_LAUNCH("k_predictor_scores");
     return RL_OK;
 }
@@ -932,8 +975,12 @@ int rl_softmax_ce(const rl_graph *g, const rl_slots *s, const rl_answers *ans, f
 
 int rl_predictor_backward(const rl_graph *g, const rl_rules *r, const rl_slots *s, const rl_frontier *fr,
                           const float *G, const float *slot_scale, int32_t max_terms, float *grad_w,
-                          float *grad_bias, void *stream)
+                          float *grad_bias, const rl_items *it, void *stream)
 {
+    if (it && (!it->items || !it->count || it->cap_per_slot <= 0)) return fail(RL_ERR_ARG, "rl_predictor_backward: incomplete rl_items");
+    const int4 *items = it ? reinterpret_cast<const int4 *>(it->items) : nullptr;
+    const int *icount = it ? it->count : nullptr;
+    const int icap = it ? it->cap_per_slot : 0;
     if (!g || !r || !s || !G || !grad_w) return fail(RL_ERR_ARG, "rl_predictor_backward: null argument");
     if (check_frontier(fr, "rl_predictor_backward: incomplete rl_frontier") != RL_OK) return RL_ERR_ARG;
     const int S = s->num_slots, N = g->num_entities;
@@ -941,8 +988,14 @@ int rl_predictor_backward(const rl_graph *g, const rl_rules *r, const rl_slots *
     cudaStream_t st = (cudaStream_t)stream;
     (void)max_terms;
     dim3 grid((g->rank_words + WARPS_PER_BLOCK - 1) / WARPS_PER_BLOCK, S);
-    if (fr->count_bits == 32) k_predictor_bwd_w<uint32_t><<<grid, WARPS_PER_BLOCK * 32, 0, st>>>(*g, *r, *s, *fr, G, slot_scale, grad_w);
-    else k_predictor_bwd_w<unsigned long long><<<grid, WARPS_PER_BLOCK * 32, 0, st>>>(*g, *r, *s, *fr, G, slot_scale, grad_w);
+    if (items) {
+        dim3 gi(ITEM_BLOCKS, S);
+        if (fr->count_bits == 32) k_predictor_bwd_items<uint32_t><<<gi, WARPS_PER_BLOCK * 32, 0, st>>>(*g, *r, *s, *fr, G, slot_scale, items, icount, icap, grad_w);
+        else k_predictor_bwd_items<unsigned long long><<<gi, WARPS_PER_BLOCK * 32, 0, st>>>(*g, *r, *s, *fr, G, slot_scale, items, icount, icap, grad_w);
+        CHECK_LAUNCH("k_predictor_bwd_items");
+    }
+    if (fr->count_bits == 32) k_predictor_bwd_w<uint32_t><<<grid, WARPS_PER_BLOCK * 32, 0, st>>>(*g, *r, *s, *fr, G, slot_scale, grad_w, icount, icap);
+    else k_predictor_bwd_w<unsigned long long><<<grid, WARPS_PER_BLOCK * 32, 0, st>>>(*g, *r, *s, *fr, G, slot_scale, grad_w, icount, icap);
     CHECK_LAUNCH("k_predictor_bwd_w");
     if (grad_bias) {
         k_bias_grad<<<(N + WARPS_PER_BLOCK - 1) / WARPS_PER_BLOCK, WARPS_PER_BLOCK * 32, 0, st>>>(N, S, G, slot_scale, grad_bias);
