@@ -115,19 +115,20 @@ __device__ __forceinline__ void scan_entity(const rl_graph &g, const rl_rules &r
                 if (row_valid(r.node_chunk0, mbase, hc0, v, rw)) addr = (long long)r.node_row_off[v] + rw;
             }
             uint32_t live = __ballot_sync(FULL, addr >= 0);
-            if (sink && live) {                              // one atomic per group of live items
-                int slot0 = 0;
-                if (lane == 0) slot0 = atomicAdd(sink->count, __popc(live));
-                slot0 = __shfl_sync(FULL, slot0, 0);
-                const int mine = slot0 + __popc(live & ((1u << lane) - 1u));
-                if (addr >= 0 && mine < sink->cap) sink->items[mine] = make_int4((int)addr, t, e, 0);
-            }
+            const uint32_t live0 = live;
+            int slot0 = 0;                                   // one atomic per group of live items; its result is
+            if (sink && live0 && lane == 0) slot0 = atomicAdd(sink->count, __popc(live0));   // only needed after the row loads
             while (live) {
                 const int j = __ffs(live) - 1;
                 live &= live - 1;
                 const long long a = __shfl_sync(FULL, addr, j);
                 const int tj = __shfl_sync(FULL, t, j);
                 f(arena[(abase + (size_t)a) * RL_LANES + lane], tj);
+            }
+            if (sink && live0) {
+                slot0 = __shfl_sync(FULL, slot0, 0);
+                const int mine = slot0 + __popc(live0 & ((1u << lane) - 1u));
+                if (addr >= 0 && mine < sink->cap) sink->items[mine] = make_int4((int)addr, t, e, 0);
             }
         }
     }

@@ -631,7 +631,7 @@ k_predictor_bwd_w(rl_graph g, rl_rules r, rl_slots s, rl_frontier fr, const floa
 
 // Backward over the item list recorded by the forward: one warp per (row, rule end) item.
 // A slot whose list overflowed is left to k_predictor_bwd_w (which otherwise skips it).
-#define ITEM_BLOCKS 32
+#define ITEM_BLOCKS 96
 template <typename CT>
 __global__ void __launch_bounds__(WARPS_PER_BLOCK * 32)
 k_predictor_bwd_items(rl_graph g, rl_rules r, rl_slots s, rl_frontier fr, const float *__restrict__ G,
@@ -656,12 +656,21 @@ k_predictor_bwd_items(rl_graph g, rl_rules r, rl_slots s, rl_frontier fr, const 
     }
     const CT *arena = reinterpret_cast<const CT *>(fr.arena) + (size_t)s.arena_off[slot] * RL_LANES;
     const int4 *it = items + (size_t)slot * item_cap;
-    for (int i = blockIdx.x * WARPS_PER_BLOCK + warp; i < n; i += ITEM_BLOCKS * WARPS_PER_BLOCK) {
-        const int4 rec = __ldg(it + i);                            // {row, rule end, entity, -}
-        const CT c = arena[(size_t)rec.x * RL_LANES + lane];
-        double v = c != 0 ? (double)(float)c * (double)Gs[(size_t)rec.z * RL_LANES + lane] : 0.0;
-        v = warp_sum(v);
-        if (lane == 0 && v != 0.0) atomicAdd(grad_w + r.term_rule[rec.y], (float)v * scale);
+    const int stride = ITEM_BLOCKS * WARPS_PER_BLOCK;
+    for (int i = blockIdx.x * WARPS_PER_BLOCK + warp; i < n; i += 2 * stride) {     // two items in flight
+        const int i2 = i + stride;
+        const int4 ra = __ldg(it + i);                             // {row, rule end, entity, -}
+        const int4 rb = i2 < n ? __ldg(it + i2) : ra;
+        const CT ca = arena[(size_t)ra.x * RL_LANES + lane];
+        const CT cb = arena[(size_t)rb.x * RL_LANES + lane];
+        const float ga = Gs[(size_t)ra.z * RL_LANES + lane];
+        const float gb = Gs[(size_t)rb.z * RL_LANES + lane];
+        double va = ca != 0 ? (double)(float)ca * (double)ga : 0.0;
+        double vb = (i2 < n && cb != 0) ? (double)(float)cb * (double)gb : 0.0;
+        va = warp_sum(va);
+        vb = warp_sum(vb);
+        if (lane == 0 && va != 0.0) atomicAdd(grad_w + r.term_rule[ra.y], (float)va * scale);
+        if (lane == 0 && vb != 0.0) atomicAdd(grad_w + r.term_rule[rb.y], (float)vb * scale);
     }
 }
 
