@@ -298,6 +298,7 @@ def main():
 
     # ---------------- device-resident timing (`value`) ----------------
     slots = [sk.gr.make_slots_host(sl, with_etr=True) for sl in step_lists]       # inputs now in HBM
+    sk.gr.reserve(slots)                                                            # no cudaMalloc inside the timed loops
     torch.cuda.synchronize()
     if world > 1:
         torch.distributed.barrier()

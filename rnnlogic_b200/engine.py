@@ -175,6 +175,18 @@ class Grounder:
                 e1.record()
                 self.level_events.append((depth, e0, e1))
 
+    def reserve(self, slots_list):
+        """Size the reusable frontier workspace for the largest of the given calls up front, so that no
+        step of a steady-state loop triggers a cudaMalloc."""
+        W = self.graph.rank_words
+        n_arena = max(max(1, sl.arena_rows) * LANES for sl in slots_list)
+        n_state = max(sl.mask_words + 1 + sl.nz_total + 1 + sl.S * W + 1 for sl in slots_list)
+        if self._ws_arena is None or self._ws_arena.numel() < n_arena:
+            self._ws_arena = None
+            self._ws_arena = torch.empty(n_arena, dtype=torch.int32, device=self.device)
+        if self._ws_state is None or self._ws_state.numel() < n_state:
+            self._ws_state = torch.empty(n_state, dtype=torch.int32, device=self.device)
+
     def _run_empty(self, sl: Slots):
         sl.arena = torch.zeros(LANES, dtype=torch.int32, device=self.device)
         sl.state = torch.zeros(8, dtype=torch.int32, device=self.device)
