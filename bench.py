@@ -30,9 +30,9 @@ UNIT = "queries/s"
 B = 32
 
 
-def build_workload(seed=237, scale=1.0):
+def build_workload(name="fb15k237", scale=1.0):
     from rnnlogic_b200 import synth
-    shape = synth.load_shape("fb15k237")
+    shape = synth.load_shape(name)
     N, R, train, valid, test = synth.synthetic_kg(shape, scale=scale)
     rules = synth.synthetic_rules(shape)
     return shape, N, R, train, valid, test, rules
@@ -211,7 +211,8 @@ def main():
     ap.add_argument("--dense", action="store_true", help="expand every row of every trie node (dense SpMM; roofline mode)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-extras", action="store_true", help="skip the eval-mode / PredictorPlus side measurements")
-    ap.add_argument("--mode", default="train", choices=["train", "eval"])
+    ap.add_argument("--shape", default="fb15k237", choices=["fb15k237", "wn18rr"],
+                    help="synthetic workload shape (the headline metric is quoted on fb15k237)")
     args = ap.parse_args()
     if args.warmup < 3:
         args.warmup = 3
@@ -220,11 +221,11 @@ def main():
     world = int(os.environ.get("WORLD_SIZE", "1"))
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))
 
-    shape, N, R, train, valid, test, rules = build_workload()
+    shape, N, R, train, valid, test, rules = build_workload(args.shape)
     batches = make_batches(train, R, seed=1)
-    workload = ("FB15k-237-shape synthetic KG (N=%d, R=%d, E=%d train triples incl. inverses), %d synthetic rules "
-                "of the reference rule file's shape (L<=3), Predictor(bias) train step, B=32 per batch, %d batches/step/GPU"
-                % (N, R, train.shape[0], len(rules), args.batches))
+    workload = (shape["name"] + "-shape synthetic KG (N=%d, R=%d, E=%d train triples incl. inverses), %d synthetic rules "
+                "of the reference rule file's shape (L<=%d), Predictor(bias) train step, B=32 per batch, %d batches/step/GPU"
+                % (N, R, train.shape[0], len(rules), shape["max_len"], args.batches))
 
     if args.impl == "reference":
         if rank != 0:
