@@ -52,7 +52,8 @@ def test_predictor_forward_matches_oracle(world, ef, B):
         n_q = int(okg.rel_ptr[q + 1] - okg.rel_ptr[q])
         for etr in (None, rng.integers(n_q, size=B) if n_q else None):   # ANY edge of relation q, not the query's own
             ht, rt = torch.from_numpy(h).to(DEV), torch.full((B,), q, device=DEV)
-            score, mask = m(ht, rt, None if etr is None else torch.from_numpy(etr).to(DEV))
+            with torch.no_grad():
+                score, mask = m(ht, rt, None if etr is None else torch.from_numpy(etr).to(DEV))
             want, wmask = oracle_scores(okg, rules, w, b, h, q, etr)
             assert torch.equal(mask.cpu(), wmask), (q, ef)
             assert torch.equal(torch.isinf(score.cpu()), torch.isinf(want))
