@@ -41,7 +41,61 @@ def rotate_slot_scores(mod, sk, sl):
     return _RotateFn.apply(mod.eemb, mod.remb, mod.gamma, sk, sl)
 
 
+class _MiniDriver:
+    """Just enough of ScoreKernels / Slots for the RotatE kernels (they only read num_entities,
+    slot_head and lane_h): lets RotatE.forward run without a KnowledgeGraph."""
+
+    def __init__(self, N, device, heads, lane_h):
+        self.N, self.device = N, device
+        self.struct_g = _lib.RlGraph()
+        self.struct_g.num_entities = N
+        self.S = int(heads.shape[0])
+        self.heads_t, self.lane_t = heads, lane_h
+        self.struct_s = _lib.RlSlots(self.S, heads.data_ptr(), lane_h.data_ptr(), None, None, None, None, None, None)
+
+    class _Ref:
+        def __init__(self, st):
+            self.st = st
+
+        def ref(self):
+            import ctypes
+            return ctypes.byref(self.st)
+
+    @property
+    def dg(self):
+        return self._Ref(self.struct_g)
+
+    def ref(self):
+        import ctypes
+        return ctypes.byref(self.struct_s)
+
+
 def rotate_dense_scores(mod, all_h, all_r):
-    """RotatE.forward(all_h, all_r) -> fp32[B,N]; one relation per call like the predictors."""
-    raise NotImplementedError("use PredictorPlus(entity_feature='RotatE'); the stand-alone dense entry point "
-                              "needs a graph-bound driver")
+    """RotatE.forward(all_h, all_r) -> fp32[B,N] (embedding.py:64-70); any relation per query."""
+    _lib.require_cuda(all_h, "all_h")
+    dev = all_h.device
+    B, N = int(all_h.shape[0]), int(mod.eemb.shape[0])
+    # one slot per distinct relation chunk of <= 32 queries
+    r_host = all_r.detach().cpu().tolist()
+    order = sorted(range(B), key=lambda i: r_host[i])
+    heads, lanes, where = [], [], []
+    i = 0
+    while i < B:
+        j = i
+        while j < B and j - i < LANES and r_host[order[j]] == r_host[order[i]]:
+            j += 1
+        heads.append(r_host[order[i]])
+        lanes.append(order[i:j] + [-1] * (LANES - (j - i)))
+        where += [(len(heads) - 1, k) for k in range(j - i)]
+        i = j
+    idx = torch.tensor(lanes, dtype=torch.long, device=dev)
+    lane_h = torch.where(idx >= 0, all_h[idx.clamp(min=0)], torch.full_like(idx, -1)).to(torch.int32).contiguous()
+    heads_t = torch.tensor(heads, dtype=torch.int32, device=dev)
+    drv = _MiniDriver(N, dev, heads_t, lane_h.view(-1))
+    out = _RotateFn.apply(mod.eemb, mod.remb, mod.gamma, drv, drv)        # [S][N][32]
+    slot = torch.tensor([w[0] for w in where], device=dev)
+    lane = torch.tensor([w[1] for w in where], device=dev)
+    rows = out[slot, :, lane]                                             # queries in sorted order
+    inv = torch.empty(B, dtype=torch.long, device=dev)
+    inv[torch.tensor(order, device=dev)] = torch.arange(B, device=dev)
+    return rows[inv]

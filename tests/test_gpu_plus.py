@@ -149,3 +149,33 @@ def test_layers_reference_signature():
         want = fn(p)
         got = mod.cuda()(A.cuda(), x.cuda(), b_n.cuda()).cpu()
         np.testing.assert_allclose(got.detach().numpy(), want.detach().numpy(), rtol=1e-4, atol=1e-5)
+
+
+def test_rotate_module_forward_and_grad(tmp_path):
+    """RotatE.forward(all_h, all_r) (embedding.py:64-70) stand-alone, mixed relations, vs the oracle."""
+    import json
+    from rnnlogic_b200.embedding import RotatE
+    from oracle import rnnlogic_oracle as O
+    rng = np.random.default_rng(0)
+    N, Rh, D, gamma = 70, 5, 24, 6.0
+    d = tmp_path / "rot"
+    d.mkdir()
+    rg = (gamma + 2.0) / D
+    np.save(d / "entity_embedding.npy", rng.uniform(-rg, rg, size=(N, 2 * D)).astype(np.float32))
+    np.save(d / "relation_embedding.npy", rng.uniform(-rg, rg, size=(Rh, D)).astype(np.float32))
+    (d / "config.json").write_text(json.dumps({"hidden_dim": D, "gamma": gamma, "nentity": N}))
+    mod = RotatE(str(d)).cuda()
+    assert mod.remb.shape == (2 * Rh, D)
+    all_h = torch.from_numpy(rng.integers(N, size=41))
+    all_r = torch.from_numpy(rng.integers(2 * Rh, size=41))
+    got = mod(all_h.cuda(), all_r.cuda())
+    e = mod.eemb.detach().cpu().clone().requires_grad_()
+    r = mod.remb.detach().cpu().clone().requires_grad_()
+    want = O.rotate_score(e, r, gamma, all_h, all_r)
+    np.testing.assert_allclose(got.detach().cpu().numpy(), want.detach().numpy(), rtol=1e-5, atol=1e-5)
+    wgt = torch.from_numpy(rng.normal(size=want.shape).astype(np.float32))
+    (got * wgt.cuda()).sum().backward()
+    (want * wgt).sum().backward()
+    for mine, ref in ((mod.eemb.grad, e.grad), (mod.remb.grad, r.grad)):
+        scale = ref.abs().max().item()
+        np.testing.assert_allclose(mine.cpu().numpy(), ref.numpy(), rtol=1e-3, atol=2e-4 * scale)
