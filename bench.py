@@ -177,8 +177,20 @@ def extras(args, kg, model, rules, batches, test, valid, dev):
     ms = _timed(eval_step, 3, 10)
     out["eval_filtered_rank_queries_per_sec"] = state["q"] / (ms / 1e3)
     rule_lists = [[h] + list(b) for h, b in rules]
+    # BASELINE config 4: RotatE-shaped random entity features (hidden_dim 1000 -> eemb [N,2000], remb [R/2,1000])
+    import tempfile
+    rot_dir = tempfile.mkdtemp(prefix="rotate_")
+    rng = np.random.default_rng(237)
+    D, gamma = 1000, 9.0
+    rr = (gamma + 2.0) / D
+    np.save(os.path.join(rot_dir, "entity_embedding.npy"), rng.uniform(-rr, rr, size=(kg.entity_size, 2 * D)).astype(np.float32))
+    np.save(os.path.join(rot_dir, "relation_embedding.npy"), rng.uniform(-rr, rr, size=(R // 2, D)).astype(np.float32))
+    with open(os.path.join(rot_dir, "config.json"), "w") as f:
+        json.dump({"hidden_dim": D, "gamma": gamma, "nentity": kg.entity_size}, f)
     for tag, kw in (("plus_lstm_sum_bias", dict(type="lstm", num_layers=3, hidden_dim=16, entity_feature="bias", aggregator="sum")),
-                    ("plus_emb_pna_bias", dict(type="emb", hidden_dim=16, entity_feature="bias", aggregator="pna"))):
+                    ("plus_emb_pna_bias", dict(type="emb", hidden_dim=16, entity_feature="bias", aggregator="pna")),
+                    ("plus_lstm_sum_rotate1000", dict(type="lstm", num_layers=3, hidden_dim=16, entity_feature="RotatE",
+                                                      aggregator="sum", embedding_path=rot_dir))):
         torch.manual_seed(0)
         pm = PredictorPlus(kg, **kw)
         pm.set_rules(rule_lists)
@@ -194,7 +206,7 @@ def extras(args, kg, model, rules, batches, test, valid, dev):
             popt.step()
             st["q"] = sum(len(b) for b in sb)
 
-        ms = _timed(plus_step, 3, 8)
+        ms = _timed(plus_step, 2, 4 if "rotate" in tag else 8)
         out[tag + "_train_queries_per_sec"] = st["q"] / (ms / 1e3)
         del pm, popt
         torch.cuda.empty_cache()
