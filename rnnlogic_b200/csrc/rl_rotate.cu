@@ -33,12 +33,26 @@ k_rotate_project(int D, float inv_scale, const float *__restrict__ eemb, const f
     P[((size_t)slot * 2 * D + D + d) * RL_LANES + lane] = pi;
 }
 
+// |z| = z^2 * rsqrt(z^2): one MUFU + one FMUL instead of the IEEE sqrt sequence (error ~2 ulp per
+// term, ~1e-7 relative on the sum over D terms -- far inside the 1e-5 parity bar).
+__device__ __forceinline__ float rsqrt_approx(float x)
+{
+    float y;
+    asm("rsqrt.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));     // one MUFU.RSQ, no denormal fix-up code
+    return y;
+}
+__device__ __forceinline__ float fast_norm2(float dr, float di)
+{
+    const float n2 = fmaf(dr, dr, di * di);
+    return n2 * rsqrt_approx(fmaxf(n2, 1e-30f));                // 0 at the origin
+}
+
 __global__ void __launch_bounds__(256)
 k_rotate_scores(int N, int D, float gamma, const float *__restrict__ eemb, const float *__restrict__ P,
                 float *__restrict__ out)
 {
-    __shared__ float sP[2][RT_DT][32];
-    __shared__ float sE[RT_ENT][2][RT_DT + 1];
+    __shared__ float2 sP[RT_DT][32];              // (re, im) of the projected heads, [d][query]
+    __shared__ float2 sE[RT_ENT][RT_DT];          // (re, im) of the block's entities, [entity][d]
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const int slot = blockIdx.y;
     const int e0 = blockIdx.x * RT_ENT;
@@ -49,26 +63,30 @@ k_rotate_scores(int N, int D, float gamma, const float *__restrict__ eemb, const
     for (int d0 = 0; d0 < D; d0 += RT_DT) {
         const int nd = min(RT_DT, D - d0);
         __syncthreads();
-        for (int i = threadIdx.x; i < 2 * RT_DT * 32; i += 256) {          // projected heads, coalesced
-            const int part = i / (RT_DT * 32), rem = i % (RT_DT * 32), d = rem >> 5, l = rem & 31;
-            sP[part][d][l] = d < nd ? Ps[((size_t)part * D + d0 + d) * RL_LANES + l] : 0.f;
+        for (int i = threadIdx.x; i < RT_DT * 32; i += 256) {               // projected heads, coalesced
+            const int d = i >> 5, l = i & 31;
+            float2 v = make_float2(0.f, 0.f);
+            if (d < nd) { v.x = Ps[((size_t)d0 + d) * RL_LANES + l]; v.y = Ps[((size_t)D + d0 + d) * RL_LANES + l]; }
+            sP[d][l] = v;
         }
-        for (int i = threadIdx.x; i < RT_ENT * 2 * RT_DT; i += 256) {       // entity rows, 128-byte segments
-            const int ent = i / (2 * RT_DT), rem = i % (2 * RT_DT), part = rem / RT_DT, d = rem % RT_DT;
+        for (int i = threadIdx.x; i < RT_ENT * RT_DT; i += 256) {            // entity rows, 128-byte segments
+            const int ent = i / RT_DT, d = i % RT_DT;
             const int e = e0 + ent;
-            sE[ent][part][d] = (e < N && d < nd) ? eemb[(size_t)e * 2 * D + (size_t)part * D + d0 + d] : 0.f;
+            float2 v = make_float2(0.f, 0.f);
+            if (e < N && d < nd) { v.x = eemb[(size_t)e * 2 * D + d0 + d]; v.y = eemb[(size_t)e * 2 * D + D + d0 + d]; }
+            sE[ent][d] = v;
         }
         __syncthreads();
         float part_sum[8];
 #pragma unroll
         for (int j = 0; j < 8; ++j) part_sum[j] = 0.f;
+#pragma unroll 4
         for (int d = 0; d < nd; ++d) {
-            const float pr = sP[0][d][lane], pi = sP[1][d][lane];
+            const float2 p = sP[d][lane];
 #pragma unroll
             for (int j = 0; j < 8; ++j) {
-                const float dr = pr - sE[warp * 8 + j][0][d];
-                const float di = pi - sE[warp * 8 + j][1][d];
-                part_sum[j] += sqrtf(dr * dr + di * di);
+                const float2 ev = sE[warp * 8 + j][d];                       // broadcast
+                part_sum[j] += fast_norm2(p.x - ev.x, p.y - ev.y);
             }
         }
 #pragma unroll
@@ -126,7 +144,7 @@ k_rotate_bwd(int N, int D, int S, const float *__restrict__ eemb, const float *_
                 const float g = sG[warp * 8 + j][b];
                 const float dr = pr - er[j], di = pi - ei[j];
                 const float n2 = dr * dr + di * di;
-                const float t = n2 > 0.f ? g * rsqrtf(n2) : 0.f;      // d|z|/dz = z/|z|, 0 at the origin (torch.norm)
+                const float t = n2 > 0.f ? g * rsqrt_approx(fmaxf(n2, 1e-30f)) : 0.f;   // d|z|/dz = z/|z|, 0 at the origin (torch.norm)
                 ger[j] += t * dr;                                     // score = gamma - sum |p - e|
                 gei[j] += t * di;
                 dpr -= t * dr;

@@ -597,9 +597,8 @@ def _plus_fused_train(self, batches, smoothing, grad_scale=1.0):
     device = self.relation_emb.weight.device
     sk = self._driver(device)
     use_mask = self.entity_feature not in ('bias', 'RotatE')
-    sl = sk.gr.make_slots_host(batches, with_etr=True)
-    sl.use_workspace = False          # autograd keeps the frontier until backward
-    gptr, ng = _group_ptr(sl, device)
+    sl = sk.gr.make_slots_host(batches, with_etr=True)    # frontier in the reusable workspace: the autograd
+    gptr, ng = _group_ptr(sl, device)                     # backward below runs before this call returns
     sk.gr.ground(sl)
     Z, pc = self._logits(sk, sl)
     loss, tsum, G = sk.softmax_ce(sl, Z.detach(), pc.nzmask, smoothing, use_mask, gptr, ng, want_grad=True)
