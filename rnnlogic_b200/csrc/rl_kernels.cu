@@ -162,12 +162,12 @@ k_symbolic(rl_graph g, rl_rules r, rl_slots s, int depth, rl_frontier fr, int de
 }
 
 #define EDGE_GROUP 8
-// One chunk (<= 32 destination rows of node v starting at row0) with valid-row word m.
-// Returns the word of rows that ended up NON-ZERO (exact frontier support).
+// Up to 32 valid destination rows of node v, one per lane (myrow = row index inside the node, -1 =
+// none).  Returns the lanes whose row ended up NON-ZERO (exact frontier support).
 template <typename CT, bool ROOT, bool PRUNE>
-__device__ __forceinline__ uint32_t numeric_chunk(const rl_graph &g, const rl_rules &r, const rl_slots &s, const rl_frontier &fr,
-                                                  int slot, int q, int hc0, const uint32_t *mbase, int v, int row0, uint32_t m,
-                                                  int h, int lane_eh, int lane_et, bool &ovf)
+__device__ __forceinline__ uint32_t numeric_rows(const rl_graph &g, const rl_rules &r, const rl_slots &s, const rl_frontier &fr,
+                                                 int slot, int q, int hc0, const uint32_t *mbase, int v, int myrow,
+                                                 int h, int lane_eh, int lane_et, bool &ovf)
 {
     const int lane = threadIdx.x & 31;
     // one 32-byte node record instead of a chain of dependent look-ups
@@ -182,14 +182,13 @@ __device__ __forceinline__ uint32_t numeric_chunk(const rl_graph &g, const rl_ru
         X = arena + (abase + (size_t)r.node_prow_off[v]) * RL_LANES;
         pm = mbase + (rb4.z - hc0);
     }
-    CT *__restrict__ Y = arena + (abase + (size_t)r.node_row_off[v] + row0) * RL_LANES;
-    const int rbase = ra.w + row0;
-    const int nr = min(32, rb4.x - row0);
-    const int my_rs = g.row_start[rbase + min(lane, nr)];
-    const int my_re = g.row_start[rbase + min(lane + 1, nr)];
-    const int my_dst = lane < nr ? g.row_dst[rbase + lane] : -1;
-    const bool active = (m >> lane) & 1u;
-    const int deg = active ? my_re - my_rs : 0;
+    CT *__restrict__ Y = arena + (abase + (size_t)r.node_row_off[v]) * RL_LANES;
+    const bool active = myrow >= 0;
+    const int grow = ra.w + max(myrow, 0);                   // global row (dst_ptr[rel] + row)
+    const int my_rs = active ? g.row_start[grow] : 0;
+    const int my_re = active ? g.row_start[grow + 1] : 0;
+    const int my_dst = active ? g.row_dst[grow] : -1;
+    const int deg = my_re - my_rs;
     int P = deg;                                            // inclusive scan of deg over lanes
 #pragma unroll
     for (int o = 1; o < 32; o <<= 1) {
@@ -219,7 +218,7 @@ __device__ __forceinline__ uint32_t numeric_chunk(const rl_graph &g, const rl_ru
         }
         if (sizeof(CT) == 4 && (acc >> 32)) ovf = true;
         if (!PRUNE || __any_sync(FULL, acc != 0)) {          // all-zero rows are dropped from the bitmap
-            Y[(size_t)j * RL_LANES + lane] = (CT)acc;
+            Y[(size_t)__shfl_sync(FULL, myrow, j) * RL_LANES + lane] = (CT)acc;
             nzrows |= 1u << j;
         }
         acc = 0;
@@ -275,8 +274,9 @@ __device__ __forceinline__ uint32_t numeric_chunk(const rl_graph &g, const rl_ru
     return nzrows;
 }
 
-// One warp = 32 consecutive chunks of one slot at this depth: the 32 valid-row words are read with
-// one coalesced load and only chunks with a non-zero word are expanded.
+// One warp = cpw consecutive chunks of one slot at this depth: their valid-row words are read with
+// one coalesced load, then the valid rows of all chunks of the same trie node are merged and expanded
+// 32 at a time (full tiles even when each chunk holds only a few valid rows).
 template <typename CT, bool ROOT, bool PRUNE>
 __global__ void __launch_bounds__(WARPS_PER_BLOCK * 32)
 k_numeric(rl_graph g, rl_rules r, rl_slots s, int depth, rl_frontier fr, int cpw)
@@ -292,25 +292,46 @@ k_numeric(rl_graph g, rl_rules r, rl_slots s, int depth, rl_frontier fr, int cpw
     uint32_t *mbase = fr.row_mask + (size_t)s.mask_off[slot];
     const int nzb = s.nz_off[slot] - r.head_node_ptr[q];
     const int my_chunk = c0 + lane;
-    uint32_t my_m = (lane < cpw && my_chunk < c_end) ? mbase[my_chunk - hc0] : 0u;
+    const bool mine = lane < cpw && my_chunk < c_end;
+    const uint32_t my_m = mine ? mbase[my_chunk - hc0] : 0u;
     uint32_t todo = __ballot_sync(FULL, my_m != 0u);
     if (todo == 0u) return;
+    const int my_node = my_m ? r.chunk_node[my_chunk] : -1;
+    const int my_row0 = my_m ? r.chunk_row0[my_chunk] : 0;
     const int h = s.lane_h[slot * RL_LANES + lane];
     const int leh = s.lane_eh[slot * RL_LANES + lane];
     const int let_ = s.lane_et[slot * RL_LANES + lane];
     bool ovf = false;
-    uint32_t my_out = 0u;
     while (todo) {
-        const int c = __ffs(todo) - 1;
-        todo &= todo - 1;
-        const int chunk = c0 + c;
-        const uint32_t m = __shfl_sync(FULL, my_m, c);
-        const int v = r.chunk_node[chunk], row0 = r.chunk_row0[chunk];
-        const uint32_t nz = numeric_chunk<CT, ROOT, PRUNE>(g, r, s, fr, slot, q, hc0, mbase, v, row0, m, h, leh, let_, ovf);
-        if (lane == c) my_out = nz;
-        if (lane == 0 && nz) atomicAdd(fr.node_cnt + nzb + v, __popc(nz));
+        const int v = __shfl_sync(FULL, my_node, __ffs(todo) - 1);
+        const uint32_t seg = __ballot_sync(FULL, my_m != 0u && my_node == v);       // this node's chunks in my range
+        todo &= ~seg;
+        const int cnt = ((seg >> lane) & 1u) ? __popc(my_m) : 0;
+        int P = cnt;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) {
+            const int t = __shfl_up_sync(FULL, P, o);
+            if (lane >= o) P += t;
+        }
+        const int V = __shfl_sync(FULL, P, 31);
+        const int first = P - cnt;
+        for (int g0 = 0; g0 < V; g0 += 32) {
+            const bool have = g0 + lane < V;
+            const int k = min(g0 + lane, V - 1);
+            int sl = 0;                                                             // lane holding the k-th valid row's chunk
+#pragma unroll
+            for (int step = 16; step > 0; step >>= 1)
+                if (__shfl_sync(FULL, P, sl + step - 1) <= k) sl += step;
+            const uint32_t wsel = __shfl_sync(FULL, my_m, sl);
+            const int nth = k - __shfl_sync(FULL, first, sl);
+            const int r0 = __shfl_sync(FULL, my_row0, sl);
+            const int bit = __fns(wsel, 0, nth + 1);
+            const int myrow = have ? r0 + bit : -1;
+            const uint32_t nz = numeric_rows<CT, ROOT, PRUNE>(g, r, s, fr, slot, q, hc0, mbase, v, myrow, h, leh, let_, ovf);
+            if (have && !((nz >> lane) & 1u)) atomicAnd(mbase + (c0 + sl - hc0), ~(1u << bit));   // bitmap = exact support
+            if (lane == 0 && nz) atomicAdd(fr.node_cnt + nzb + v, __popc(nz));
+        }
     }
-    if (my_m != my_out) mbase[my_chunk - hc0] = my_out;      // bitmap now = rows that are non-zero
     if (__any_sync(FULL, ovf) && lane == 0) *fr.overflow = 1;
 }
 
