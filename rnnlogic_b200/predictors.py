@@ -203,6 +203,7 @@ def _predictor_step_on_slots(self, sk, sl, smoothing, grad_scale=1.0, bits=32, e
     if grad_scale != 1.0:
         scale = torch.full((sl.S,), float(grad_scale), dtype=torch.float32, device=device)
     sk.predictor_backward(sl, G, scale, gw, gb)
+    sl.items = None                       # hand the item list back to the allocator (stream-ordered reuse)
     msum = None if use_bias else _group_mask_sum(sl, nzmask, ng)
     return loss, tsum, msum, gw, gb
 
