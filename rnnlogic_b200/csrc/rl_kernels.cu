@@ -427,12 +427,20 @@ k_softmax_partial(int N, const float *__restrict__ Z, float *__restrict__ partia
     const float *Zs = Z + (size_t)slot * N * RL_LANES;
     const int e0 = blockIdx.x * SM_ROWS_PER_BLOCK;
     const int e1 = min(N, e0 + SM_ROWS_PER_BLOCK);
-    float m = -INFINITY, sum = 0.f;
-    for (int e = e0 + warp; e < e1; e += WARPS_PER_BLOCK) {
-        const float z = Zs[(size_t)e * RL_LANES + lane];
-        if (z > m) { sum = sum * expf(m - z) + 1.f; m = z; }
-        else if (z != -INFINITY) sum += expf(z - m);
+    // two passes over the warp's rows (the second one hits L1): max first, then one expf per logit with
+    // four independent accumulators -- no serial max/sum dependency chain, half the MUFU work
+    float m = -INFINITY;
+    for (int e = e0 + warp; e < e1; e += WARPS_PER_BLOCK) m = fmaxf(m, Zs[(size_t)e * RL_LANES + lane]);
+    float s4[4] = {0.f, 0.f, 0.f, 0.f};
+    if (m != -INFINITY) {
+        int e = e0 + warp;
+        for (; e + 3 * WARPS_PER_BLOCK < e1; e += 4 * WARPS_PER_BLOCK) {
+#pragma unroll
+            for (int u = 0; u < 4; ++u) s4[u] += expf(Zs[(size_t)(e + u * WARPS_PER_BLOCK) * RL_LANES + lane] - m);
+        }
+        for (; e < e1; e += WARPS_PER_BLOCK) s4[0] += expf(Zs[(size_t)e * RL_LANES + lane] - m);
     }
+    const float sum = (s4[0] + s4[1]) + (s4[2] + s4[3]);
     sm_m[warp][lane] = m;
     sm_s[warp][lane] = sum;
     __syncthreads();
@@ -530,7 +538,7 @@ k_ce_finalize(rl_graph g, rl_slots s, rl_answers ans, float smoothing, int use_m
 // (trainer.py:89); slot_invT[s] = 1 / max(T_group, 1)
 __global__ void k_group_reduce(int n_groups, const int32_t *__restrict__ group_ptr, const float *__restrict__ slot_lsum,
                                const float *__restrict__ slot_tsum, float *__restrict__ group_loss,
-                               float *__restrict__ group_tsum, float *__restrict__ slot_invT)
+                               float *__restrict__ group_tsum, float *__restrict__ slot_invT, float *__restrict__ stats)
 {
     const int gi = blockIdx.x * blockDim.x + threadIdx.x;
     if (gi >= n_groups) return;
@@ -540,7 +548,13 @@ __global__ void k_group_reduce(int n_groups, const int32_t *__restrict__ group_p
     const float Tf = fmaxf((float)T, 1.f);
     group_tsum[gi] = (float)T;
     group_loss[gi] = (float)L / Tf;
-    for (int k = s0; k < s1; ++k) slot_invT[k] = 1.f / Tf;
+    for (int k = s0; k < s1; ++k) {
+        slot_invT[k] = 1.f / Tf;
+        for (int b = 0; b < 32; ++b) {                       // stats[.][3]: valid flag -> softmax-gradient coefficient
+            float *st = stats + ((size_t)k * 32 + b) * 4;
+            st[3] = st[3] != 0.f ? st[2] / st[1] / Tf : 0.f;  // S_b / sum-exp / T'
+        }
+    }
 }
 
 // G[e][b] = softmax * S_b / T'   (dense part of dloss/dZ)
@@ -553,11 +567,10 @@ k_grad_dense(int N, const float *__restrict__ Z, const float *__restrict__ stats
     if (i >= (size_t)N * RL_LANES) return;
     const int b = (int)(i & 31);
     const float *st = stats + ((size_t)slot * 32 + b) * 4;
-    const float iT = slot_invT[slot];
     float gval = 0.f;
-    if (st[3] != 0.f) {
+    if (st[3] != 0.f) {                                      // st[3] = S_b / sum-exp / T'
         const float z = Z[(size_t)slot * N * RL_LANES + i];
-        if (z != -INFINITY) gval = expf(z - st[0]) / st[1] * st[2] * iT;
+        if (z != -INFINITY) gval = expf(z - st[0]) * st[3];
     }
     G[(size_t)slot * N * RL_LANES + i] = gval;
 }
@@ -991,7 +1004,7 @@ int rl_softmax_ce(const rl_graph *g, const rl_slots *s, const rl_answers *ans, f
     CHECK_LAUNCH("k_softmax_partial");
     k_ce_finalize<<<S, WARPS_PER_BLOCK * 32, 0, st>>>(*g, *s, *ans, smoothing, use_mask, Z, nzmask, partial, nblk, stats, slot_lsum, slot_tsum);
     CHECK_LAUNCH("k_ce_finalize");
-    k_group_reduce<<<(n_groups + 127) / 128, 128, 0, st>>>(n_groups, group_ptr, slot_lsum, slot_tsum, group_loss, group_tsum, slot_invT);
+    k_group_reduce<<<(n_groups + 127) / 128, 128, 0, st>>>(n_groups, group_ptr, slot_lsum, slot_tsum, group_loss, group_tsum, slot_invT, stats);
     CHECK_LAUNCH("k_group_reduce");
     if (G) {
         const size_t n = (size_t)N * RL_LANES;
