@@ -364,10 +364,31 @@ __global__ void k_node_dense(rl_graph g, rl_rules r, rl_slots s, int slot, int n
 
 // ------------------------------------------------------------------------------------------
 // kernel (2a): pull aggregation of the rule weights.  One warp = 32 consecutive entities of one
-// slot.  Entities no rule end reaches (ent_active bit clear) only get their bias / -inf row; a
-// candidate entity walks the (relation, row) pairs in which it is a tail and, per pair, the rules
-// of the slot's head that end in that relation (deterministic order, fp64 accumulation).
+// slot.  Every entity first gets its default row (bias / -inf, empty-body rules).  Then the
+// (relation,row) pairs of ALL candidate entities of the word are flattened over the lanes, then their
+// (pair, rule end) items -- every dependent look-up stage (pair -> rule ends -> node -> row bitmap)
+// runs 32 wide for the whole word -- and the live items are pulled in entity order with a segmented
+// fp64 reduction (same fixed order as a per-entity walk: pairs ascending, then rule ends).
 // ------------------------------------------------------------------------------------------
+__device__ __forceinline__ int lane_of(int P, int k)        // #lanes whose inclusive scan value is <= k
+{
+    int l = 0;
+#pragma unroll
+    for (int step = 16; step > 0; step >>= 1)
+        if (__shfl_sync(FULL, P, l + step - 1) <= k) l += step;
+    return l;
+}
+__device__ __forceinline__ int warp_scan_incl(int v)
+{
+    const int lane = threadIdx.x & 31;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+        const int t = __shfl_up_sync(FULL, v, o);
+        if (lane >= o) v += t;
+    }
+    return v;
+}
+
 template <typename CT>
 __global__ void __launch_bounds__(WARPS_PER_BLOCK * 32)
 k_predictor_scores(rl_graph g, rl_rules r, rl_slots s, rl_frontier fr, const float *__restrict__ w,
@@ -387,31 +408,96 @@ k_predictor_scores(rl_graph g, rl_rules r, rl_slots s, rl_frontier fr, const flo
     const int32_t *tp = r.term_ptr + (size_t)q * R;
     const int h = s.lane_h[slot * RL_LANES + lane];
     const int z0 = r.zr_ptr[q], z1 = r.zr_ptr[q + 1];
-    uint32_t act = fr.ent_active[(size_t)slot * g.rank_words + ew];
-    if (z1 > z0) act |= __reduce_or_sync(FULL, (h >= 0 && (h >> 5) == ew) ? (1u << (h & 31)) : 0u);
+    const uint32_t act = fr.ent_active[(size_t)slot * g.rank_words + ew];
     double zsum = 0.0;
     if (z1 > z0) for (int t = z0; t < z1; ++t) zsum += (double)__ldg(w + r.zr_rule[t]);
+    float *Zs = Z + (size_t)slot * N * RL_LANES;
+    uint32_t *ms = nzmask + (size_t)slot * N;
     const int e1 = min(32, N - ew * 32);
-    ItemSink sink{items ? items + (size_t)slot * item_cap : nullptr, item_count ? item_count + slot : nullptr, item_cap};
-    for (int i = 0; i < e1; ++i) {
-        const int e = ew * 32 + i;
-        double acc = 0.0;
-        bool any = false;
-        if ((act >> i) & 1u) {
-            scan_entity<CT>(g, r, arena, abase, mbase, hc0, tp, e, [&](CT c, int t) {
-                if (c != 0) {
-                    acc += (double)(float)c * (double)__ldg(w + r.term_rule[t]);   // x.float() * w (predictors.py:64)
-                    any = true;
-                }
-            }, items ? &sink : nullptr);
-            if (h == e && z1 > z0) { acc += zsum; any = true; }   // empty-body rules: count = one_hot(h)
-        }
+    auto finish = [&](int e, double acc, bool any) {              // one logit row (all lanes) + its nzmask word
+        if (z1 > z0 && h == e) { acc += zsum; any = true; }       // empty-body rules: count = one_hot(h)
         float z = (float)acc;
         if (bias) z += bias[e];
         if (fill_neg_inf && !any) z = -INFINITY;
-        Z[((size_t)slot * N + e) * RL_LANES + lane] = z;
+        Zs[(size_t)e * RL_LANES + lane] = z;
         const uint32_t bits = __ballot_sync(FULL, any);
-        if (lane == 0) nzmask[(size_t)slot * N + e] = bits;
+        if (lane == 0) ms[e] = bits;
+    };
+    for (int i = 0; i < e1; ++i)                                  // default rows (non-candidates stay like this)
+        if (!((act >> i) & 1u)) finish(ew * 32 + i, 0.0, false);
+    if (act == 0u) return;
+    // ---- stage A: (relation,row) pairs of the word's candidate entities, flattened over the lanes
+    const int e_l = ew * 32 + lane;
+    const bool cand = (act >> lane) & 1u;
+    const int p0 = cand ? g.ent_ptr[e_l] : 0;
+    const int np = cand ? g.ent_ptr[e_l + 1] - p0 : 0;
+    const int PP = warp_scan_incl(np);
+    const int TP = __shfl_sync(FULL, PP, 31);
+    const int firstP = PP - np;
+    ItemSink sink{items ? items + (size_t)slot * item_cap : nullptr, item_count ? item_count + slot : nullptr, item_cap};
+    int cur = -1;                                                 // entity (lane index) being accumulated
+    uint32_t done = 0u;                                           // candidates that produced at least one live item
+    double acc = 0.0;
+    bool any = false;
+    for (int pb = 0; pb < TP; pb += 32) {
+        const int k = min(pb + lane, TP - 1);
+        const int el = lane_of(PP, k);                            // entity lane of pair k
+        const int pi = __shfl_sync(FULL, p0, el) + (k - __shfl_sync(FULL, firstP, el));
+        int row = 0, t0 = 0, cnt = 0;
+        if (pb + lane < TP) {
+            const int rel = g.ent_rel[pi];
+            row = g.ent_row[pi];
+            t0 = tp[rel];
+            cnt = tp[rel + 1] - t0;
+        }
+        // ---- stage B: (pair, rule end) items of these 32 pairs, flattened again
+        const int PI = warp_scan_incl(cnt);
+        const int TI = __shfl_sync(FULL, PI, 31);
+        const int firstI = PI - cnt;
+        for (int ib = 0; ib < TI; ib += 32) {
+            const int m = min(ib + lane, TI - 1);
+            const int pl = lane_of(PI, m);                        // pair lane of item m
+            const int t = __shfl_sync(FULL, t0, pl) + (m - __shfl_sync(FULL, firstI, pl));
+            const int rw = __shfl_sync(FULL, row, pl);
+            const int ei = __shfl_sync(FULL, el, pl);             // entity lane of the item
+            long long addr = -1;
+            if (ib + lane < TI) {
+                const int v = __ldg(r.term_node + t);
+                if (row_valid(r.node_chunk0, mbase, hc0, v, rw)) addr = (long long)r.node_row_off[v] + rw;
+            }
+            uint32_t live = __ballot_sync(FULL, addr >= 0);
+            const uint32_t live0 = live;
+            int slot0 = 0;
+            if (sink.items && live0 && lane == 0) slot0 = atomicAdd(sink.count, __popc(live0));
+            while (live) {
+                const int j = __ffs(live) - 1;
+                live &= live - 1;
+                const long long a = __shfl_sync(FULL, addr, j);
+                const int tj = __shfl_sync(FULL, t, j);
+                const int ej = __shfl_sync(FULL, ei, j);
+                if (ej != cur) {
+                    if (cur >= 0) { finish(ew * 32 + cur, acc, any); done |= 1u << cur; }
+                    cur = ej; acc = 0.0; any = false;
+                }
+                const CT c = arena[(abase + (size_t)a) * RL_LANES + lane];
+                if (c != 0) {
+                    acc += (double)(float)c * (double)__ldg(w + r.term_rule[tj]);   // x.float() * w (predictors.py:64)
+                    any = true;
+                }
+            }
+            if (sink.items && live0) {
+                slot0 = __shfl_sync(FULL, slot0, 0);
+                const int mine = slot0 + __popc(live0 & ((1u << lane) - 1u));
+                if (addr >= 0 && mine < sink.cap) sink.items[mine] = make_int4((int)addr, t, ew * 32 + ei, 0);
+            }
+        }
+    }
+    if (cur >= 0) { finish(ew * 32 + cur, acc, any); done |= 1u << cur; }
+    uint32_t rest = act & ~done;                                  // candidates whose rows all turned out empty
+    while (rest) {
+        const int i = __ffs(rest) - 1;
+        rest &= rest - 1;
+        if (i < e1) finish(ew * 32 + i, 0.0, false);
     }
 }
 
