@@ -470,19 +470,30 @@ k_predictor_scores(rl_graph g, rl_rules r, rl_slots s, rl_frontier fr, const flo
             int slot0 = 0;
             if (sink.items && live0 && lane == 0) slot0 = atomicAdd(sink.count, __popc(live0));
             while (live) {
-                const int j = __ffs(live) - 1;
-                live &= live - 1;
-                const long long a = __shfl_sync(FULL, addr, j);
-                const int tj = __shfl_sync(FULL, t, j);
-                const int ej = __shfl_sync(FULL, ei, j);
-                if (ej != cur) {
-                    if (cur >= 0) { finish(ew * 32 + cur, acc, any); done |= 1u << cur; }
-                    cur = ej; acc = 0.0; any = false;
+                CT cv[4];
+                float wv[4];
+                int ev[4];
+#pragma unroll
+                for (int u = 0; u < 4; ++u) {                      // four row loads in flight
+                    const int j = live ? __ffs(live) - 1 : -1;
+                    live &= live - 1;
+                    const long long a = __shfl_sync(FULL, addr, j & 31);
+                    const int tj = __shfl_sync(FULL, t, j & 31);
+                    ev[u] = j >= 0 ? __shfl_sync(FULL, ei, j & 31) : -1;
+                    cv[u] = j >= 0 ? arena[(abase + (size_t)a) * RL_LANES + lane] : (CT)0;
+                    wv[u] = j >= 0 ? __ldg(w + r.term_rule[tj]) : 0.f;
                 }
-                const CT c = arena[(abase + (size_t)a) * RL_LANES + lane];
-                if (c != 0) {
-                    acc += (double)(float)c * (double)__ldg(w + r.term_rule[tj]);   // x.float() * w (predictors.py:64)
-                    any = true;
+#pragma unroll
+                for (int u = 0; u < 4; ++u) {
+                    if (ev[u] < 0) continue;
+                    if (ev[u] != cur) {
+                        if (cur >= 0) { finish(ew * 32 + cur, acc, any); done |= 1u << cur; }
+                        cur = ev[u]; acc = 0.0; any = false;
+                    }
+                    if (cv[u] != 0) {
+                        acc += (double)(float)cv[u] * (double)wv[u];     // x.float() * w (predictors.py:64)
+                        any = true;
+                    }
                 }
             }
             if (sink.items && live0) {
