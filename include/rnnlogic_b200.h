@@ -100,6 +100,9 @@ typedef struct rl_rules {
     const int32_t *lvl_sym_ptr;   /* [R*(max_len+1)] */
     const int32_t *sym_node;      /* [#items] */
     const int32_t *sym_w0;        /* [#items] */
+    /* rules ending at a node: node_term_rule[node_term_ptr[v] .. node_term_ptr[v+1]) */
+    const int32_t *node_term_ptr;  /* [num_nodes+1] */
+    const int32_t *node_term_rule; /* [num_terms] */
 } rl_rules;
 
 /* One call's queries, cut into slots (<= 32 queries of one head relation each). */
@@ -125,16 +128,18 @@ typedef struct rl_frontier {
     int32_t *node_cnt;     /* valid rows per (slot, node) */
     uint32_t *ent_active;  /* [S][rank_words] entities some rule end may reach */
     int32_t *overflow;     /* set to 1 when a 32-bit count overflowed */
+    /* Item list (may be all NULL when only the PredictorPlus / debug entry points are used): one
+     * int32x4 record {row (slot-relative), node, entity, -} per NON-ZERO row of every rule-end node,
+     * appended by k_numeric; slot s owns [item_off[s], item_off[s+1]) (capacity = rows of its head's
+     * rule-end nodes, so it cannot overflow).  item_cnt[S], bucket_cnt[S*rank_words] zeroed by the
+     * caller; items_sorted / bucket_off[S*(rank_words+1)] are scratch of rl_predictor_scores. */
+    int32_t *items;        /* as int32x4, 16-byte aligned */
+    int32_t *items_sorted;
+    const int64_t *item_off;
+    int32_t *item_cnt;
+    int32_t *bucket_cnt;
+    int32_t *bucket_off;
 } rl_frontier;
-
-/* Optional forward->backward hand-over: the aggregation records every (row, rule end, entity)
- * triple it read, S regions of cap_per_slot int32x4 records; count[S] (zeroed by the caller) may
- * exceed the capacity, in which case the backward walks the tables again for that slot. */
-typedef struct rl_items {
-    int32_t cap_per_slot;
-    int32_t *items;   /* [S * cap_per_slot * 4], 16-byte aligned */
-    int32_t *count;   /* [S] */
-} rl_items;
 
 /* Known-answer lists, replaces KnowledgeGraph.hr2o / hr2oo / hr2ooo (src/data.py:36-38,49-61,
  * 79-99): sorted keys r*N+h, CSR of de-duplicated tails.  Used for the smoothed multi-hot
@@ -185,8 +190,7 @@ int rl_node_counts_dense(const rl_graph *g, const rl_rules *r, const rl_slots *s
  * fill_neg_inf != 0 cells with a clear bit get -inf (entity_feature != 'bias'). */
 int rl_predictor_scores(const rl_graph *g, const rl_rules *r, const rl_slots *s,
                         const rl_frontier *fr, const float *rule_weights, const float *bias,
-                        int32_t fill_neg_inf, float *Z, uint32_t *nzmask, const rl_items *items,
-                        void *stream);
+                        int32_t fill_neg_inf, float *Z, uint32_t *nzmask, void *stream);
 
 /* Kernel (2b): log(softmax + 1e-8) cross-entropy against the smoothed target, replaces
  * src/trainer.py:84,88-89, fused with its backward.  target = smoothing * multi_hot(train
@@ -208,8 +212,7 @@ int rl_softmax_ce(const rl_graph *g, const rl_slots *s, const rl_answers *train_
  * into (zero them first): grad_w[i] += sum_s slot_scale[s] * <G_s, fp32(count_i)>. */
 int rl_predictor_backward(const rl_graph *g, const rl_rules *r, const rl_slots *s,
                           const rl_frontier *fr, const float *G, const float *slot_scale,
-                          int32_t max_terms, float *grad_w, float *grad_bias, const rl_items *items,
-                          void *stream);
+                          float *grad_w, float *grad_bias, void *stream);
 
 /* Kernel (3): filtered rank bounds, replaces src/trainer.py:189-201.  LH[S*32][2] int64:
  * L = #{e not known: z_e > z_t} + 1, H = #{e not known: z_e >= z_t} + 2; (1, N+1) when the

@@ -40,7 +40,7 @@ class RlRules(C.Structure):
                 ("lvl_ptr", vp), ("chunk_node", vp), ("chunk_row0", vp), ("term_ptr", vp),
                 ("term_node", vp), ("term_rule", vp), ("zr_ptr", vp), ("zr_rule", vp),
                 ("lvl_node_ptr", vp), ("node_chunk0", vp), ("node_nterm", vp), ("node_rec", vp), ("node_prow_off", vp),
-                ("lvl_sym_ptr", vp), ("sym_node", vp), ("sym_w0", vp)]
+                ("lvl_sym_ptr", vp), ("sym_node", vp), ("sym_w0", vp), ("node_term_ptr", vp), ("node_term_rule", vp)]
 
 
 class RlSlots(C.Structure):
@@ -50,11 +50,8 @@ class RlSlots(C.Structure):
 
 class RlFrontier(C.Structure):
     _fields_ = [("count_bits", C.c_int32), ("arena", vp), ("row_mask", vp), ("node_cnt", vp),
-                ("ent_active", vp), ("overflow", vp)]
-
-
-class RlItems(C.Structure):
-    _fields_ = [("cap_per_slot", C.c_int32), ("items", vp), ("count", vp)]
+                ("ent_active", vp), ("overflow", vp), ("items", vp), ("items_sorted", vp), ("item_off", vp),
+                ("item_cnt", vp), ("bucket_cnt", vp), ("bucket_off", vp)]
 
 
 class RlAnswers(C.Structure):
@@ -91,12 +88,12 @@ _PROTOS = {
     "rl_node_counts_dense": (C.c_int, [C.POINTER(RlGraph), C.POINTER(RlRules), C.POINTER(RlSlots), C.c_int32,
                                        C.c_int32, C.POINTER(RlFrontier), vp, vp]),
     "rl_predictor_scores": (C.c_int, [C.POINTER(RlGraph), C.POINTER(RlRules), C.POINTER(RlSlots),
-                                      C.POINTER(RlFrontier), vp, vp, C.c_int32, vp, vp, C.POINTER(RlItems), vp]),
+                                      C.POINTER(RlFrontier), vp, vp, C.c_int32, vp, vp, vp]),
     "rl_softmax_blocks": (C.c_int, [C.c_int32]),
     "rl_softmax_ce": (C.c_int, [C.POINTER(RlGraph), C.POINTER(RlSlots), C.POINTER(RlAnswers), C.c_float,
                                 C.c_int32, vp, vp, C.c_int32, vp, vp, vp, vp, vp, vp, vp, vp]),
     "rl_predictor_backward": (C.c_int, [C.POINTER(RlGraph), C.POINTER(RlRules), C.POINTER(RlSlots),
-                                        C.POINTER(RlFrontier), vp, vp, C.c_int32, vp, vp, C.POINTER(RlItems), vp]),
+                                        C.POINTER(RlFrontier), vp, vp, C.c_int32, vp, vp, vp]),
     "rl_filtered_rank": (C.c_int, [C.POINTER(RlGraph), C.POINTER(RlSlots), C.POINTER(RlAnswers), C.c_int32,
                                    vp, vp, vp, vp, vp]),
     "rl_filtered_rank_dense": (C.c_int, [C.c_int64, C.c_int64, vp, vp, vp, vp, vp, vp]),

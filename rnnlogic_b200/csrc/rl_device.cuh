@@ -69,18 +69,9 @@ __device__ __forceinline__ bool row_valid(const int32_t *__restrict__ node_chunk
 // fixed: the entity's (relation,row) pairs ascending, then the head's rule ends of that relation.
 // The (pair, rule end) items are flattened over the lanes so that the dependent look-ups
 // (rule end -> node -> row bitmap) run 32 wide; only items whose row is non-zero touch the arena.
-// An optional item sink records every live (row, rule end, entity) triple so that a later pass
-// (the backward) can revisit exactly these rows without walking the tables again.
-struct ItemSink {
-    int4 *items;       // this slot's region
-    int *count;        // this slot's counter (may exceed cap: overflow)
-    int cap;
-};
-
 template <typename CT, typename F>
 __device__ __forceinline__ void scan_entity(const rl_graph &g, const rl_rules &r, const CT *__restrict__ arena, size_t abase,
-                                            const uint32_t *__restrict__ mbase, int hc0, const int32_t *__restrict__ tp, int e, F f,
-                                            const ItemSink *sink = nullptr)
+                                            const uint32_t *__restrict__ mbase, int hc0, const int32_t *__restrict__ tp, int e, F f)
 {
     const int lane = threadIdx.x & 31;
     const int p0 = g.ent_ptr[e], p1 = g.ent_ptr[e + 1];
@@ -115,20 +106,12 @@ __device__ __forceinline__ void scan_entity(const rl_graph &g, const rl_rules &r
                 if (row_valid(r.node_chunk0, mbase, hc0, v, rw)) addr = (long long)r.node_row_off[v] + rw;
             }
             uint32_t live = __ballot_sync(FULL, addr >= 0);
-            const uint32_t live0 = live;
-            int slot0 = 0;                                   // one atomic per group of live items; its result is
-            if (sink && live0 && lane == 0) slot0 = atomicAdd(sink->count, __popc(live0));   // only needed after the row loads
             while (live) {
                 const int j = __ffs(live) - 1;
                 live &= live - 1;
                 const long long a = __shfl_sync(FULL, addr, j);
                 const int tj = __shfl_sync(FULL, t, j);
                 f(arena[(abase + (size_t)a) * RL_LANES + lane], tj);
-            }
-            if (sink && live0) {
-                slot0 = __shfl_sync(FULL, slot0, 0);
-                const int mine = slot0 + __popc(live0 & ((1u << lane) - 1u));
-                if (addr >= 0 && mine < sink->cap) sink->items[mine] = make_int4((int)addr, t, e, 0);
             }
         }
     }

@@ -269,8 +269,21 @@ __device__ __forceinline__ uint32_t numeric_rows(const rl_graph &g, const rl_rul
         }
     }
     if (cur >= 0) flush(cur);
-    if (nterm > 0 && ((nzrows >> lane) & 1u))                // candidate entities for the aggregation
-        atomicOr(fr.ent_active + (size_t)slot * g.rank_words + (my_dst >> 5), 1u << (my_dst & 31));
+    if (nterm > 0 && nzrows) {
+        const bool mine = (nzrows >> lane) & 1u;
+        if (mine)                                            // candidate entities (PredictorPlus kernels)
+            atomicOr(fr.ent_active + (size_t)slot * g.rank_words + (my_dst >> 5), 1u << (my_dst & 31));
+        if (fr.items) {                                      // (row, node, entity) items for the aggregation / backward
+            int base = 0;
+            if (lane == 0) base = atomicAdd(fr.item_cnt + slot, __popc(nzrows));
+            base = __shfl_sync(FULL, base, 0);
+            if (mine) {
+                const long long pos = fr.item_off[slot] + base + __popc(nzrows & ((1u << lane) - 1u));
+                reinterpret_cast<int4 *>(fr.items)[pos] = make_int4((int)(r.node_row_off[v] + myrow), v, my_dst, 0);
+                atomicAdd(fr.bucket_cnt + (size_t)slot * g.rank_words + (my_dst >> 5), 1);
+            }
+        }
+    }
     return nzrows;
 }
 
@@ -363,52 +376,61 @@ __global__ void k_node_dense(rl_graph g, rl_rules r, rl_slots s, int slot, int n
 }
 
 // ------------------------------------------------------------------------------------------
-// kernel (2a): pull aggregation of the rule weights.  One warp = 32 consecutive entities of one
-// slot.  Every entity first gets its default row (bias / -inf, empty-body rules).  Then the
-// (relation,row) pairs of ALL candidate entities of the word are flattened over the lanes, then their
-// (pair, rule end) items -- every dependent look-up stage (pair -> rule ends -> node -> row bitmap)
-// runs 32 wide for the whole word -- and the live items are pulled in entity order with a segmented
-// fp64 reduction (same fixed order as a per-entity walk: pairs ascending, then rule ends).
+// kernel (2a): rule-weight aggregation from the item list.  k_numeric appended one item
+// {row, node, entity} per NON-ZERO row of every rule-end node (exactly the rows that contribute).
+// k_items_sort buckets the items of a slot by entity word (counting sort); k_predictor_scores then
+// gives one warp the 32 entities of a word: default rows (bias / -inf, empty-body rules) for entities
+// without items, and for the others an fp64 accumulation of fp32(count) * w over their items.
+// No table walk: work is proportional to the non-zero terminal rows.
 // ------------------------------------------------------------------------------------------
-__device__ __forceinline__ int lane_of(int P, int k)        // #lanes whose inclusive scan value is <= k
+__global__ void __launch_bounds__(512)
+k_items_sort(int W, rl_frontier fr)
 {
-    int l = 0;
-#pragma unroll
-    for (int step = 16; step > 0; step >>= 1)
-        if (__shfl_sync(FULL, P, l + step - 1) <= k) l += step;
-    return l;
-}
-__device__ __forceinline__ int warp_scan_incl(int v)
-{
-    const int lane = threadIdx.x & 31;
-#pragma unroll
-    for (int o = 1; o < 32; o <<= 1) {
-        const int t = __shfl_up_sync(FULL, v, o);
-        if (lane >= o) v += t;
+    __shared__ int part[512];
+    const int slot = blockIdx.x, tid = threadIdx.x;
+    int *cnt = fr.bucket_cnt + (size_t)slot * W;
+    int *off = fr.bucket_off + (size_t)slot * (W + 1);
+    const int per = (W + 511) / 512;
+    const int w0 = tid * per, w1 = min(W, w0 + per);
+    int sum = 0;
+    for (int w = w0; w < w1; ++w) sum += cnt[w];
+    part[tid] = sum;
+    __syncthreads();
+    for (int o = 1; o < 512; o <<= 1) {                          // inclusive scan of the per-thread sums
+        const int v = tid >= o ? part[tid - o] : 0;
+        __syncthreads();
+        part[tid] += v;
+        __syncthreads();
     }
-    return v;
+    int run = part[tid] - sum;
+    for (int w = w0; w < w1; ++w) { off[w] = run; run += cnt[w]; cnt[w] = 0; }
+    if (tid == 511) off[W] = part[511];
+    __syncthreads();
+    const int n = fr.item_cnt[slot];
+    const int4 *in = reinterpret_cast<const int4 *>(fr.items) + fr.item_off[slot];
+    int4 *out = reinterpret_cast<int4 *>(fr.items_sorted) + fr.item_off[slot];
+    for (int i = tid; i < n; i += 512) {
+        const int4 it = in[i];
+        const int bkt = it.z >> 5;
+        out[off[bkt] + atomicAdd(cnt + bkt, 1)] = it;            // cnt ends as the bucket sizes again
+    }
 }
 
 template <typename CT>
 __global__ void __launch_bounds__(WARPS_PER_BLOCK * 32)
 k_predictor_scores(rl_graph g, rl_rules r, rl_slots s, rl_frontier fr, const float *__restrict__ w,
                    const float *__restrict__ bias, int fill_neg_inf, float *__restrict__ Z,
-                   uint32_t *__restrict__ nzmask, int4 *__restrict__ items, int *__restrict__ item_count, int item_cap)
+                   uint32_t *__restrict__ nzmask)
 {
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const int slot = blockIdx.y;
     const int ew = blockIdx.x * WARPS_PER_BLOCK + warp;           // entity word
-    const int N = g.num_entities, R = g.num_relations;
-    if (ew >= g.rank_words) return;
+    const int N = g.num_entities, W = g.rank_words;
+    if (ew >= W) return;
     const int q = s.slot_head[slot];
-    const int hc0 = r.lvl_ptr[(size_t)q * (r.max_len + 1)];
-    const uint32_t *mbase = fr.row_mask + (size_t)s.mask_off[slot];
-    const size_t abase = (size_t)s.arena_off[slot];
-    const CT *arena = reinterpret_cast<const CT *>(fr.arena);
-    const int32_t *tp = r.term_ptr + (size_t)q * R;
+    const CT *arena = reinterpret_cast<const CT *>(fr.arena) + (size_t)s.arena_off[slot] * RL_LANES;
     const int h = s.lane_h[slot * RL_LANES + lane];
     const int z0 = r.zr_ptr[q], z1 = r.zr_ptr[q + 1];
-    const uint32_t act = fr.ent_active[(size_t)slot * g.rank_words + ew];
     double zsum = 0.0;
     if (z1 > z0) for (int t = z0; t < z1; ++t) zsum += (double)__ldg(w + r.zr_rule[t]);
     float *Zs = Z + (size_t)slot * N * RL_LANES;
@@ -423,92 +445,48 @@ k_predictor_scores(rl_graph g, rl_rules r, rl_slots s, rl_frontier fr, const flo
         const uint32_t bits = __ballot_sync(FULL, any);
         if (lane == 0) ms[e] = bits;
     };
-    for (int i = 0; i < e1; ++i)                                  // default rows (non-candidates stay like this)
-        if (!((act >> i) & 1u)) finish(ew * 32 + i, 0.0, false);
-    if (act == 0u) return;
-    // ---- stage A: (relation,row) pairs of the word's candidate entities, flattened over the lanes
-    const int e_l = ew * 32 + lane;
-    const bool cand = (act >> lane) & 1u;
-    const int p0 = cand ? g.ent_ptr[e_l] : 0;
-    const int np = cand ? g.ent_ptr[e_l + 1] - p0 : 0;
-    const int PP = warp_scan_incl(np);
-    const int TP = __shfl_sync(FULL, PP, 31);
-    const int firstP = PP - np;
-    ItemSink sink{items ? items + (size_t)slot * item_cap : nullptr, item_count ? item_count + slot : nullptr, item_cap};
-    int cur = -1;                                                 // entity (lane index) being accumulated
-    uint32_t done = 0u;                                           // candidates that produced at least one live item
-    double acc = 0.0;
-    bool any = false;
-    for (int pb = 0; pb < TP; pb += 32) {
-        const int k = min(pb + lane, TP - 1);
-        const int el = lane_of(PP, k);                            // entity lane of pair k
-        const int pi = __shfl_sync(FULL, p0, el) + (k - __shfl_sync(FULL, firstP, el));
-        int row = 0, t0 = 0, cnt = 0;
-        if (pb + lane < TP) {
-            const int rel = g.ent_rel[pi];
-            row = g.ent_row[pi];
-            t0 = tp[rel];
-            cnt = tp[rel + 1] - t0;
-        }
-        // ---- stage B: (pair, rule end) items of these 32 pairs, flattened again
-        const int PI = warp_scan_incl(cnt);
-        const int TI = __shfl_sync(FULL, PI, 31);
-        const int firstI = PI - cnt;
-        for (int ib = 0; ib < TI; ib += 32) {
-            const int m = min(ib + lane, TI - 1);
-            const int pl = lane_of(PI, m);                        // pair lane of item m
-            const int t = __shfl_sync(FULL, t0, pl) + (m - __shfl_sync(FULL, firstI, pl));
-            const int rw = __shfl_sync(FULL, row, pl);
-            const int ei = __shfl_sync(FULL, el, pl);             // entity lane of the item
-            long long addr = -1;
-            if (ib + lane < TI) {
-                const int v = __ldg(r.term_node + t);
-                if (row_valid(r.node_chunk0, mbase, hc0, v, rw)) addr = (long long)r.node_row_off[v] + rw;
-            }
-            uint32_t live = __ballot_sync(FULL, addr >= 0);
-            const uint32_t live0 = live;
-            int slot0 = 0;
-            if (sink.items && live0 && lane == 0) slot0 = atomicAdd(sink.count, __popc(live0));
-            while (live) {
+    const int *off = fr.bucket_off + (size_t)slot * (W + 1);
+    const int b0 = off[ew], n = off[ew + 1] - b0;
+    const int4 *its = reinterpret_cast<const int4 *>(fr.items_sorted) + fr.item_off[slot] + b0;
+    uint32_t present = 0u;                                        // entities of this word that own items
+    int4 it0 = make_int4(0, 0, -1, 0);
+    for (int c0 = 0; c0 < n; c0 += 32) {
+        const int4 it = c0 + lane < n ? its[c0 + lane] : make_int4(0, 0, -1, 0);
+        if (c0 == 0) it0 = it;
+        present |= __reduce_or_sync(FULL, it.z >= 0 ? 1u << (it.z & 31) : 0u);
+    }
+    for (int i = 0; i < e1; ++i)
+        if (!((present >> i) & 1u)) finish(ew * 32 + i, 0.0, false);
+    while (present) {
+        const int i = __ffs(present) - 1;
+        present &= present - 1;
+        double acc = 0.0;
+        bool any = false;
+        for (int c0 = 0; c0 < n; c0 += 32) {
+            const int4 it = c0 == 0 ? it0 : (c0 + lane < n ? its[c0 + lane] : make_int4(0, 0, -1, 0));
+            uint32_t sel = __ballot_sync(FULL, it.z >= 0 && (it.z & 31) == i);
+            while (sel) {
                 CT cv[4];
-                float wv[4];
-                int ev[4];
+                int nv[4];
 #pragma unroll
                 for (int u = 0; u < 4; ++u) {                      // four row loads in flight
-                    const int j = live ? __ffs(live) - 1 : -1;
-                    live &= live - 1;
-                    const long long a = __shfl_sync(FULL, addr, j & 31);
-                    const int tj = __shfl_sync(FULL, t, j & 31);
-                    ev[u] = j >= 0 ? __shfl_sync(FULL, ei, j & 31) : -1;
-                    cv[u] = j >= 0 ? arena[(abase + (size_t)a) * RL_LANES + lane] : (CT)0;
-                    wv[u] = j >= 0 ? __ldg(w + r.term_rule[tj]) : 0.f;
+                    const int j = sel ? __ffs(sel) - 1 : -1;
+                    sel &= sel - 1;
+                    const int a = __shfl_sync(FULL, it.x, j & 31);
+                    nv[u] = j >= 0 ? __shfl_sync(FULL, it.y, j & 31) : -1;
+                    cv[u] = j >= 0 ? arena[(size_t)a * RL_LANES + lane] : (CT)0;
                 }
 #pragma unroll
                 for (int u = 0; u < 4; ++u) {
-                    if (ev[u] < 0) continue;
-                    if (ev[u] != cur) {
-                        if (cur >= 0) { finish(ew * 32 + cur, acc, any); done |= 1u << cur; }
-                        cur = ev[u]; acc = 0.0; any = false;
-                    }
-                    if (cv[u] != 0) {
-                        acc += (double)(float)cv[u] * (double)wv[u];     // x.float() * w (predictors.py:64)
-                        any = true;
-                    }
+                    if (nv[u] < 0) continue;
+                    const float cf = (float)cv[u];                 // x.float() * w (predictors.py:64)
+                    for (int t = r.node_term_ptr[nv[u]]; t < r.node_term_ptr[nv[u] + 1]; ++t)
+                        acc += (double)cf * (double)__ldg(w + r.node_term_rule[t]);
+                    any |= cv[u] != 0;
                 }
             }
-            if (sink.items && live0) {
-                slot0 = __shfl_sync(FULL, slot0, 0);
-                const int mine = slot0 + __popc(live0 & ((1u << lane) - 1u));
-                if (addr >= 0 && mine < sink.cap) sink.items[mine] = make_int4((int)addr, t, ew * 32 + ei, 0);
-            }
         }
-    }
-    if (cur >= 0) { finish(ew * 32 + cur, acc, any); done |= 1u << cur; }
-    uint32_t rest = act & ~done;                                  // candidates whose rows all turned out empty
-    while (rest) {
-        const int i = __ffs(rest) - 1;
-        rest &= rest - 1;
-        if (i < e1) finish(ew * 32 + i, 0.0, false);
+        finish(ew * 32 + i, acc, any);
     }
 }
 
@@ -715,64 +693,17 @@ k_grad_sparse(rl_graph g, rl_slots s, rl_answers ans, float smoothing, int use_m
 // ------------------------------------------------------------------------------------------
 // kernel (2c): backward into rule weights / bias
 // ------------------------------------------------------------------------------------------
-// Entity-centric like the forward: only candidate entities (ent_active) are visited; for each of
-// their non-zero terminal rows the warp reduces <fp32(count), G[e]> over the 32 queries and adds it
-// to the rule's gradient (one atomic per (row, rule end)).
-template <typename CT>
-__global__ void __launch_bounds__(WARPS_PER_BLOCK * 32)
-k_predictor_bwd_w(rl_graph g, rl_rules r, rl_slots s, rl_frontier fr, const float *__restrict__ G,
-                  const float *__restrict__ slot_scale, float *__restrict__ grad_w,
-                  const int *__restrict__ item_count, int item_cap)
-{
-    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    const int slot = blockIdx.y;
-    if (item_count && item_count[slot] <= item_cap) return;      // this slot was done from its item list
-    const int ew = blockIdx.x * WARPS_PER_BLOCK + warp;           // entity word
-    const int N = g.num_entities, R = g.num_relations;
-    if (ew >= g.rank_words) return;
-    const int q = s.slot_head[slot];
-    const float scale = slot_scale ? slot_scale[slot] : 1.f;
-    const float *Gs = G + (size_t)slot * N * RL_LANES;
-    const int h = s.lane_h[slot * RL_LANES + lane];
-    const int z0 = r.zr_ptr[q], z1 = r.zr_ptr[q + 1];
-    if (ew == 0 && z1 > z0) {                                      // empty-body rules: count = one_hot(h)
-        double v = h >= 0 ? (double)Gs[(size_t)h * RL_LANES + lane] : 0.0;
-        v = warp_sum(v);
-        if (lane == 0)
-            for (int t = z0; t < z1; ++t) atomicAdd(grad_w + r.zr_rule[t], (float)v * scale);
-    }
-    uint32_t act = fr.ent_active[(size_t)slot * g.rank_words + ew];
-    if (act == 0u) return;
-    const int hc0 = r.lvl_ptr[(size_t)q * (r.max_len + 1)];
-    const uint32_t *mbase = fr.row_mask + (size_t)s.mask_off[slot];
-    const size_t abase = (size_t)s.arena_off[slot];
-    const CT *arena = reinterpret_cast<const CT *>(fr.arena);
-    const int32_t *tp = r.term_ptr + (size_t)q * R;
-    while (act) {
-        const int e = ew * 32 + __ffs(act) - 1;
-        act &= act - 1;
-        const float gv = Gs[(size_t)e * RL_LANES + lane];
-        scan_entity<CT>(g, r, arena, abase, mbase, hc0, tp, e, [&](CT c, int t) {
-            double v = c != 0 ? (double)(float)c * (double)gv : 0.0;   // skips NaN*0 of masked cells
-            v = warp_sum(v);
-            if (lane == 0 && v != 0.0) atomicAdd(grad_w + r.term_rule[t], (float)v * scale);
-        });
-    }
-}
-
-// Backward over the item list recorded by the forward: one warp per (row, rule end) item.
-// A slot whose list overflowed is left to k_predictor_bwd_w (which otherwise skips it).
+// Backward over the item list: one warp per non-zero terminal row: <G[e], fp32(count row)> goes to
+// every rule ending at the row's node (one atomic each).
 #define ITEM_BLOCKS 96
 template <typename CT>
 __global__ void __launch_bounds__(WARPS_PER_BLOCK * 32)
 k_predictor_bwd_items(rl_graph g, rl_rules r, rl_slots s, rl_frontier fr, const float *__restrict__ G,
-                      const float *__restrict__ slot_scale, const int4 *__restrict__ items,
-                      const int *__restrict__ item_count, int item_cap, float *__restrict__ grad_w)
+                      const float *__restrict__ slot_scale, float *__restrict__ grad_w)
 {
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const int slot = blockIdx.y;
-    const int n = item_count[slot];
-    if (n > item_cap) return;                                     // overflow: the scanning kernel handles this slot
+    const int n = fr.item_cnt[slot];
     const int N = g.num_entities;
     const int q = s.slot_head[slot];
     const float scale = slot_scale ? slot_scale[slot] : 1.f;
@@ -786,22 +717,24 @@ k_predictor_bwd_items(rl_graph g, rl_rules r, rl_slots s, rl_frontier fr, const 
             for (int t = z0; t < z1; ++t) atomicAdd(grad_w + r.zr_rule[t], (float)v * scale);
     }
     const CT *arena = reinterpret_cast<const CT *>(fr.arena) + (size_t)s.arena_off[slot] * RL_LANES;
-    const int4 *it = items + (size_t)slot * item_cap;
+    const int4 *it = reinterpret_cast<const int4 *>(fr.items) + fr.item_off[slot];
     const int stride = ITEM_BLOCKS * WARPS_PER_BLOCK;
     for (int i = blockIdx.x * WARPS_PER_BLOCK + warp; i < n; i += 2 * stride) {     // two items in flight
         const int i2 = i + stride;
-        const int4 ra = __ldg(it + i);                             // {row, rule end, entity, -}
+        const int4 ra = __ldg(it + i);                             // {row, node, entity, -}
         const int4 rb = i2 < n ? __ldg(it + i2) : ra;
         const CT ca = arena[(size_t)ra.x * RL_LANES + lane];
         const CT cb = arena[(size_t)rb.x * RL_LANES + lane];
         const float ga = Gs[(size_t)ra.z * RL_LANES + lane];
         const float gb = Gs[(size_t)rb.z * RL_LANES + lane];
-        double va = ca != 0 ? (double)(float)ca * (double)ga : 0.0;
+        double va = ca != 0 ? (double)(float)ca * (double)ga : 0.0;     // skips NaN*0 of masked cells
         double vb = (i2 < n && cb != 0) ? (double)(float)cb * (double)gb : 0.0;
         va = warp_sum(va);
         vb = warp_sum(vb);
-        if (lane == 0 && va != 0.0) atomicAdd(grad_w + r.term_rule[ra.y], (float)va * scale);
-        if (lane == 0 && vb != 0.0) atomicAdd(grad_w + r.term_rule[rb.y], (float)vb * scale);
+        if (lane == 0 && va != 0.0)
+            for (int t = r.node_term_ptr[ra.y]; t < r.node_term_ptr[ra.y + 1]; ++t) atomicAdd(grad_w + r.node_term_rule[t], (float)va * scale);
+        if (lane == 0 && vb != 0.0)
+            for (int t = r.node_term_ptr[rb.y]; t < r.node_term_ptr[rb.y + 1]; ++t) atomicAdd(grad_w + r.node_term_rule[t], (float)vb * scale);
     }
 }
 
@@ -1063,21 +996,26 @@ int rl_node_counts_dense(const rl_graph *g, const rl_rules *r, const rl_slots *s
     return RL_OK;
 }
 
+static int check_items(const rl_frontier *fr, const char *who)
+{
+    if (!fr->items || !fr->items_sorted || !fr->item_off || !fr->item_cnt || !fr->bucket_cnt || !fr->bucket_off) return fail(RL_ERR_ARG, who);
+    return RL_OK;
+}
+
 int rl_predictor_scores(const rl_graph *g, const rl_rules *r, const rl_slots *s, const rl_frontier *fr,
                         const float *w, const float *bias, int32_t fill_neg_inf, float *Z, uint32_t *nzmask,
-                        const rl_items *it, void *stream)
+                        void *stream)
 {
-    if (it && (!it->items || !it->count || it->cap_per_slot <= 0)) return fail(RL_ERR_ARG, "rl_predictor_scores: incomplete rl_items");
-    int4 *items = it ? reinterpret_cast<int4 *>(it->items) : nullptr;
-    int *icount = it ? it->count : nullptr;
-    const int icap = it ? it->cap_per_slot : 0;
     if (!g || !r || !s || !w || !Z || !nzmask) return fail(RL_ERR_ARG, "rl_predictor_scores: null argument");
     if (check_frontier(fr, "rl_predictor_scores: incomplete rl_frontier") != RL_OK) return RL_ERR_ARG;
+    if (check_items(fr, "rl_predictor_scores: the frontier was expanded without an item list") != RL_OK) return RL_ERR_ARG;
     if (s->num_slots <= 0) return RL_OK;
-    dim3 grid((g->rank_words + WARPS_PER_BLOCK - 1) / WARPS_PER_BLOCK, s->num_slots);
     cudaStream_t st = (cudaStream_t)stream;
-    if (fr->count_bits == 32) k_predictor_scores<uint32_t><<<grid, WARPS_PER_BLOCK * 32, 0, st>>>(*g, *r, *s, *fr, w, bias, fill_neg_inf, Z, nzmask, items, icount, icap);
-    else k_predictor_scores<unsigned long long><<<grid, WARPS_PER_BLOCK * 32, 0, st>>>(*g, *r, *s, *fr, w, bias, fill_neg_inf, Z, nzmask, items, icount, icap);
+    k_items_sort<<<s->num_slots, 512, 0, st>>>(g->rank_words, *fr);
+    CHECK_LAUNCH("k_items_sort");
+    dim3 grid((g->rank_words + WARPS_PER_BLOCK - 1) / WARPS_PER_BLOCK, s->num_slots);
+    if (fr->count_bits == 32) k_predictor_scores<uint32_t><<<grid, WARPS_PER_BLOCK * 32, 0, st>>>(*g, *r, *s, *fr, w, bias, fill_neg_inf, Z, nzmask);
+    else k_predictor_scores<unsigned long long><<<grid, WARPS_PER_BLOCK * 32, 0, st>>>(*g, *r, *s, *fr, w, bias, fill_neg_inf, Z, nzmask);
     CHECK_LAUNCH("k_predictor_scores");
     return RL_OK;
 }
@@ -1114,29 +1052,18 @@ int rl_softmax_ce(const rl_graph *g, const rl_slots *s, const rl_answers *ans, f
 }
 
 int rl_predictor_backward(const rl_graph *g, const rl_rules *r, const rl_slots *s, const rl_frontier *fr,
-                          const float *G, const float *slot_scale, int32_t max_terms, float *grad_w,
-                          float *grad_bias, const rl_items *it, void *stream)
+                          const float *G, const float *slot_scale, float *grad_w, float *grad_bias, void *stream)
 {
-    if (it && (!it->items || !it->count || it->cap_per_slot <= 0)) return fail(RL_ERR_ARG, "rl_predictor_backward: incomplete rl_items");
-    const int4 *items = it ? reinterpret_cast<const int4 *>(it->items) : nullptr;
-    const int *icount = it ? it->count : nullptr;
-    const int icap = it ? it->cap_per_slot : 0;
     if (!g || !r || !s || !G || !grad_w) return fail(RL_ERR_ARG, "rl_predictor_backward: null argument");
     if (check_frontier(fr, "rl_predictor_backward: incomplete rl_frontier") != RL_OK) return RL_ERR_ARG;
+    if (check_items(fr, "rl_predictor_backward: the frontier was expanded without an item list") != RL_OK) return RL_ERR_ARG;
     const int S = s->num_slots, N = g->num_entities;
     if (S <= 0) return RL_OK;
     cudaStream_t st = (cudaStream_t)stream;
-    (void)max_terms;
-    dim3 grid((g->rank_words + WARPS_PER_BLOCK - 1) / WARPS_PER_BLOCK, S);
-    if (items) {
-        dim3 gi(ITEM_BLOCKS, S);
-        if (fr->count_bits == 32) k_predictor_bwd_items<uint32_t><<<gi, WARPS_PER_BLOCK * 32, 0, st>>>(*g, *r, *s, *fr, G, slot_scale, items, icount, icap, grad_w);
-        else k_predictor_bwd_items<unsigned long long><<<gi, WARPS_PER_BLOCK * 32, 0, st>>>(*g, *r, *s, *fr, G, slot_scale, items, icount, icap, grad_w);
-        CHECK_LAUNCH("k_predictor_bwd_items");
-    }
-    if (fr->count_bits == 32) k_predictor_bwd_w<uint32_t><<<grid, WARPS_PER_BLOCK * 32, 0, st>>>(*g, *r, *s, *fr, G, slot_scale, grad_w, icount, icap);
-    else k_predictor_bwd_w<unsigned long long><<<grid, WARPS_PER_BLOCK * 32, 0, st>>>(*g, *r, *s, *fr, G, slot_scale, grad_w, icount, icap);
-    CHECK_LAUNCH("k_predictor_bwd_w");
+    dim3 gi(ITEM_BLOCKS, S);
+    if (fr->count_bits == 32) k_predictor_bwd_items<uint32_t><<<gi, WARPS_PER_BLOCK * 32, 0, st>>>(*g, *r, *s, *fr, G, slot_scale, grad_w);
+    else k_predictor_bwd_items<unsigned long long><<<gi, WARPS_PER_BLOCK * 32, 0, st>>>(*g, *r, *s, *fr, G, slot_scale, grad_w);
+    CHECK_LAUNCH("k_predictor_bwd_items");
     if (grad_bias) {
         k_bias_grad<<<(N + WARPS_PER_BLOCK - 1) / WARPS_PER_BLOCK, WARPS_PER_BLOCK * 32, 0, st>>>(N, S, G, slot_scale, grad_bias);
         CHECK_LAUNCH("k_bias_grad");

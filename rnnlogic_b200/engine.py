@@ -37,16 +37,20 @@ class Slots:
         np.cumsum(cr.head_nodes[heads], out=nz_off[1:])
         mask_off = np.zeros(S + 1, dtype=np.int64)
         np.cumsum(cr.head_chunks[heads], out=mask_off[1:])
+        item_off = np.zeros(S + 1, dtype=np.int64)
+        np.cumsum(cr.head_item_cap[heads], out=item_off[1:])
         self.arena_rows, self.nz_total, self.mask_words = int(arena_off[-1]), int(nz_off[-1]), int(mask_off[-1])
+        self.item_cap = int(item_off[-1])
         # one packed H2D copy for the slot descriptors
         pack = np.concatenate([heads.astype(np.int64), q_off.astype(np.int64), nz_off[:-1], arena_off[:-1],
-                               mask_off[:-1]])
+                               mask_off[:-1], item_off])
         d = torch.from_numpy(pack).pin_memory().to(dev, non_blocking=True)      # pinned staging, async copy
         self.slot_head = d[:S].to(torch.int32)
         self.q_off_dev = d[S:2 * S + 1].to(torch.int32)
         self.nz_off = d[2 * S + 1:3 * S + 1].to(torch.int32)
         self.arena_off = d[3 * S + 1:4 * S + 1].contiguous()
         self.mask_off = d[4 * S + 1:5 * S + 1].contiguous()
+        self.item_off = d[5 * S + 1:6 * S + 2].contiguous()
         self.lane = torch.empty(4, S * LANES, dtype=torch.int32, device=dev)
         _lib.check(_lib.lib().rl_prepare_slots(
             dg.ref(), S, self.slot_head.data_ptr(), self.q_off_dev.data_ptr(), all_h.data_ptr(),
@@ -85,6 +89,7 @@ class Grounder:
         self.force_bits: Optional[int] = None
         self._ws_arena = None
         self._ws_state = None
+        self._ws_items = None
         self.level_events = None      # bench.py: list collecting (depth, start, end) CUDA events
 
     def make_slots(self, heads: Sequence[int], sizes: Sequence[int], all_h, all_t=None, etr=None) -> Slots:
@@ -139,25 +144,37 @@ class Grounder:
         W = self.graph.rank_words
         n_mask, n_cnt, n_ent = sl.mask_words + 1, sl.nz_total + 1, sl.S * W
         n_arena = max(1, sl.arena_rows) * LANES * (1 if bits == 32 else 2)
-        n_state = n_mask + n_cnt + n_ent + 1
+        n_bkt, n_boff = sl.S * W, sl.S * (W + 1)
+        n_state = n_mask + n_cnt + n_ent + sl.S + n_bkt + 1            # zeroed: masks | node counts | entity bits | item counts | buckets | overflow
+        n_items = 4 * max(1, sl.item_cap)                              # int32x4 records, exact upper bound (cannot overflow)
+        n_scratch = 2 * n_items + n_boff
         if getattr(sl, "use_workspace", False):
-            # fused paths consume the frontier inside the call: reuse one grow-only buffer (no
-            # cudaMalloc in steady state; the arena needs no clearing, rows outside the bitmap are
-            # never read)
+            # fused paths consume the frontier inside the call: reuse grow-only buffers (no cudaMalloc in
+            # steady state; the arena needs no clearing, rows outside the bitmap are never read)
             if self._ws_arena is None or self._ws_arena.numel() < n_arena:
                 self._ws_arena = None
                 self._ws_arena = torch.empty(int(n_arena * 1.25), dtype=torch.int32, device=dev)
             if self._ws_state is None or self._ws_state.numel() < n_state:
                 self._ws_state = torch.empty(int(n_state * 1.25), dtype=torch.int32, device=dev)
+            if self._ws_items is None or self._ws_items.numel() < n_scratch:
+                self._ws_items = None
+                self._ws_items = torch.empty(int(n_scratch * 1.25), dtype=torch.int32, device=dev)
             sl.arena = self._ws_arena[:n_arena]
             sl.state = self._ws_state[:n_state].zero_()
+            scratch = self._ws_items[:n_scratch]
         else:
             sl.arena = torch.empty(n_arena, dtype=torch.int32, device=dev)
             sl.state = torch.zeros(n_state, dtype=torch.int32, device=dev)                    # one memset
+            scratch = torch.empty(n_scratch, dtype=torch.int32, device=dev)
+        sl.scratch = scratch
         sl.overflow = sl.state[-1:]
         base = sl.state.data_ptr()
-        sl.frontier = _lib.RlFrontier(bits, sl.arena.data_ptr(), base, base + 4 * n_mask,
-                                      base + 4 * (n_mask + n_cnt), sl.overflow.data_ptr())
+        o_cnt, o_ent = n_mask, n_mask + n_cnt
+        o_icnt, o_bkt = o_ent + n_ent, o_ent + n_ent + sl.S
+        sb = scratch.data_ptr()
+        sl.frontier = _lib.RlFrontier(bits, sl.arena.data_ptr(), base, base + 4 * o_cnt, base + 4 * o_ent,
+                                      sl.overflow.data_ptr(), sb, sb + 4 * n_items, sl.item_off.data_ptr(),
+                                      base + 4 * o_icnt, base + 4 * o_bkt, sb + 8 * n_items)
         L = _lib.lib()
         lc = self.cr.level_chunks[sl.heads]                               # [S, max_len]
         ln = self.cr.level_sym_items[sl.heads]
@@ -180,19 +197,21 @@ class Grounder:
         step of a steady-state loop triggers a cudaMalloc."""
         W = self.graph.rank_words
         n_arena = max(max(1, sl.arena_rows) * LANES for sl in slots_list)
-        n_state = max(sl.mask_words + 1 + sl.nz_total + 1 + sl.S * W + 1 for sl in slots_list)
-        if self._ws_arena is None or self._ws_arena.numel() < n_arena:
-            self._ws_arena = None
-            self._ws_arena = torch.empty(n_arena, dtype=torch.int32, device=self.device)
-        if self._ws_state is None or self._ws_state.numel() < n_state:
-            self._ws_state = torch.empty(n_state, dtype=torch.int32, device=self.device)
+        n_state = max(sl.mask_words + 1 + sl.nz_total + 1 + 2 * sl.S * W + sl.S + 1 for sl in slots_list)
+        n_scratch = max(8 * max(1, sl.item_cap) + sl.S * (W + 1) for sl in slots_list)
+        for name, n in (("_ws_arena", n_arena), ("_ws_state", n_state), ("_ws_items", n_scratch)):
+            cur = getattr(self, name)
+            if cur is None or cur.numel() < n:
+                setattr(self, name, None)
+                setattr(self, name, torch.empty(n, dtype=torch.int32, device=self.device))
 
     def _run_empty(self, sl: Slots):
         sl.arena = torch.zeros(LANES, dtype=torch.int32, device=self.device)
         sl.state = torch.zeros(8, dtype=torch.int32, device=self.device)
         sl.overflow = sl.state[-1:]
         p = sl.state.data_ptr()
-        sl.frontier = _lib.RlFrontier(32, sl.arena.data_ptr(), p, p + 4, p + 8, sl.overflow.data_ptr())
+        sl.frontier = _lib.RlFrontier(32, sl.arena.data_ptr(), p, p + 4, p + 8, sl.overflow.data_ptr(),
+                                      None, None, None, None, None, None)
 
     def ground(self, sl: Slots, check_overflow: bool = True) -> Slots:
         """Run all depths.  Counts are kept in 32-bit rows; if any count does not fit (host sync on

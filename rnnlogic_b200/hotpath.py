@@ -26,21 +26,13 @@ class ScoreKernels:
         self.nblk = _lib.lib().rl_softmax_blocks(self.N)
 
     # ---- kernel (2a) -------------------------------------------------------------------------
-    ITEM_CAP = 32768          # recorded (row, rule end, entity) triples per slot; overflow falls back to a re-scan
-
-    def predictor_scores(self, sl: Slots, w: torch.Tensor, bias: Optional[torch.Tensor], fill_neg_inf: bool,
-                         record_items: bool = False):
+    def predictor_scores(self, sl: Slots, w: torch.Tensor, bias: Optional[torch.Tensor], fill_neg_inf: bool):
         Z = torch.empty(sl.S, self.N, LANES, dtype=torch.float32, device=self.device)
         nzmask = torch.empty(sl.S, self.N, dtype=torch.int32, device=self.device)
-        sl.items = None
-        if record_items:
-            buf = torch.empty(sl.S * self.ITEM_CAP * 4, dtype=torch.int32, device=self.device)
-            cnt = torch.zeros(sl.S, dtype=torch.int32, device=self.device)
-            sl.items = (_lib.RlItems(self.ITEM_CAP, buf.data_ptr(), cnt.data_ptr()), buf, cnt)
         _lib.check(_lib.lib().rl_predictor_scores(
             self.dg.ref(), self.dr.ref(), sl.ref(), sl.fref(), w.data_ptr(),
             bias.data_ptr() if bias is not None else None, int(fill_neg_inf), Z.data_ptr(), nzmask.data_ptr(),
-            C.byref(sl.items[0]) if sl.items is not None else None, _stream()), "rl_predictor_scores")
+            _stream()), "rl_predictor_scores")
         return Z, nzmask
 
     # ---- kernel (2b) -------------------------------------------------------------------------
@@ -65,12 +57,10 @@ class ScoreKernels:
     # ---- kernel (2c) -------------------------------------------------------------------------
     def predictor_backward(self, sl: Slots, G, slot_scale: Optional[torch.Tensor], grad_w: torch.Tensor,
                            grad_bias: Optional[torch.Tensor]):
-        max_terms = int(self.cr.head_terms[sl.heads].max())
         _lib.check(_lib.lib().rl_predictor_backward(
             self.dg.ref(), self.dr.ref(), sl.ref(), sl.fref(), G.data_ptr(),
-            slot_scale.data_ptr() if slot_scale is not None else None, max_terms, grad_w.data_ptr(),
-            grad_bias.data_ptr() if grad_bias is not None else None,
-            C.byref(sl.items[0]) if getattr(sl, "items", None) is not None else None, _stream()), "rl_predictor_backward")
+            slot_scale.data_ptr() if slot_scale is not None else None, grad_w.data_ptr(),
+            grad_bias.data_ptr() if grad_bias is not None else None, _stream()), "rl_predictor_backward")
 
     # ---- kernel (3) --------------------------------------------------------------------------
     def filtered_rank(self, sl: Slots, Z, nzmask, which: str, use_mask: bool) -> torch.Tensor:

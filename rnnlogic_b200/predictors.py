@@ -195,7 +195,7 @@ def _predictor_step_on_slots(self, sk, sl, smoothing, grad_scale=1.0, bits=32, e
     if not expanded:
         sk.gr._run(sl, bits)
     Z, nzmask = sk.predictor_scores(sl, self.rule_weights.detach(), self.bias.detach() if use_bias else None,
-                                    not use_bias, record_items=True)
+                                    not use_bias)
     loss, tsum, G = sk.softmax_ce(sl, Z, nzmask, smoothing, not use_bias, gptr, ng, want_grad=True)
     gw = torch.zeros_like(self.rule_weights)
     gb = torch.zeros_like(self.bias) if use_bias else None
@@ -203,7 +203,6 @@ def _predictor_step_on_slots(self, sk, sl, smoothing, grad_scale=1.0, bits=32, e
     if grad_scale != 1.0:
         scale = torch.full((sl.S,), float(grad_scale), dtype=torch.float32, device=device)
     sk.predictor_backward(sl, G, scale, gw, gb)
-    sl.items = None                       # hand the item list back to the allocator (stream-ordered reuse)
     msum = None if use_bias else _group_mask_sum(sl, nzmask, ng)
     return loss, tsum, msum, gw, gb
 

@@ -128,6 +128,15 @@ class CompiledRules:
         self.rule_term[t_rule] = np.arange(t_rule.shape[0])
         self.term_ptr_host = term_ptr
         node_nterm = np.bincount(t_node, minlength=max(1, self.num_nodes))
+        # rules ending at a node (CSR by node) and the item capacity of a head = rows of its rule-end nodes
+        o_n = np.lexsort((t_rule, t_node)) if t_rule.shape[0] else np.zeros(0, np.int64)
+        node_term_rule = t_rule[o_n] if t_rule.shape[0] else np.zeros(0, np.int64)
+        node_term_ptr = np.zeros(max(1, self.num_nodes) + 1, dtype=np.int64)
+        np.cumsum(node_nterm, out=node_term_ptr[1:])
+        term_rows = np.where(node_nterm[:self.num_nodes] > 0, node_rows, 0) if self.num_nodes else np.zeros(0, np.int64)
+        tr_sum = np.zeros(self.num_nodes + 1, dtype=np.int64)
+        np.cumsum(term_rows, out=tr_sum[1:])
+        self.head_item_cap = tr_sum[head_node_ptr[1:]] - tr_sum[head_node_ptr[:-1]]
         zr_ptr = np.zeros(R + 1, dtype=np.int64)
         np.cumsum([len(z) for z in zero_rules], out=zr_ptr[1:])
         zr_rule = np.array([i for z in zero_rules for i in z], dtype=np.int64)
@@ -185,6 +194,7 @@ class CompiledRules:
             "lvl_node_ptr": i32(lvl_node_ptr.reshape(-1)), "node_chunk0": i32(cstart[:-1]), "node_nterm": i32(node_nterm),
             "node_rec": i32(rec.reshape(-1)), "node_prow_off": np.ascontiguousarray(node_prow_off, dtype=np.int64),
             "lvl_sym_ptr": i32(lvl_sym_ptr.reshape(-1)), "sym_node": i32(sym_node), "sym_w0": i32(sym_w0),
+            "node_term_ptr": i32(node_term_ptr), "node_term_rule": i32(node_term_rule),
         }
         self._devices = {}
 
@@ -209,7 +219,8 @@ class DeviceRules:
             t["term_rule"].data_ptr(), t["zr_ptr"].data_ptr(), t["zr_rule"].data_ptr(),
             t["lvl_node_ptr"].data_ptr(), t["node_chunk0"].data_ptr(), t["node_nterm"].data_ptr(),
             t["node_rec"].data_ptr(), t["node_prow_off"].data_ptr(), t["lvl_sym_ptr"].data_ptr(),
-            t["sym_node"].data_ptr(), t["sym_w0"].data_ptr())
+            t["sym_node"].data_ptr(), t["sym_w0"].data_ptr(), t["node_term_ptr"].data_ptr(),
+            t["node_term_rule"].data_ptr())
 
     def ref(self):
         return C.byref(self.struct)

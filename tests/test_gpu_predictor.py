@@ -98,23 +98,6 @@ def test_fused_train_step_matches_reference(ds, ef):
     np.testing.assert_allclose(m.rule_weights.grad.cpu().numpy(), acc_w, rtol=1e-4, atol=2e-6)
 
 
-def test_fused_step_item_list_overflow_falls_back(ds, monkeypatch):
-    """The forward->backward item list is an optimisation: with a tiny capacity every slot overflows
-    and the backward re-walks the tables; gradients must not change."""
-    from rnnlogic_b200.hotpath import ScoreKernels
-    name, fx, kg = ds
-    m = make_predictor(fx, kg, "bias")
-    js = [j for j in range(5) if "pred_bias_tb%d_loss" % j in fx]
-    batches = [[tuple(x) for x in G.train_batch_inputs(fx, j)[0].tolist()] for j in js]
-    m.zero_grad()
-    m.fused_train_step(batches, 0.2)
-    ref = m.rule_weights.grad.clone()
-    monkeypatch.setattr(ScoreKernels, "ITEM_CAP", 16)
-    m.zero_grad()
-    m.fused_train_step(batches, 0.2)
-    np.testing.assert_allclose(m.rule_weights.grad.cpu().numpy(), ref.cpu().numpy(), rtol=1e-5, atol=1e-7)
-
-
 def test_compute_H(ds):
     name, fx, kg = ds
     m = make_predictor(fx, kg, "bias")
