@@ -178,6 +178,10 @@ int rl_expand_level(const rl_graph *g, const rl_rules *r, const rl_slots *s, int
                     int32_t grid_nodes, int32_t grid_chunks, const rl_frontier *fr,
                     int32_t dense_num, int32_t dense_den, int32_t force_dense, void *stream);
 
+/* Bucket the frontier's item list by entity word (counting sort, idempotent).  Called by
+ * rl_predictor_scores and rl_plus_mask themselves; exported for callers that drive the kernels. */
+int rl_sort_items(const rl_graph *g, const rl_slots *s, const rl_frontier *fr, void *stream);
+
 /* Debug / API parity: dense int64[32][N] (lane-major, like the reference's [B,N]) counts of
  * one trie node of one slot; node < 0 selects the one-hot root (empty body).  Replaces the
  * return value of KnowledgeGraph.grounding (src/data.py:147). */

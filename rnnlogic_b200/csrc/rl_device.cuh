@@ -64,54 +64,60 @@ __device__ __forceinline__ bool row_valid(const int32_t *__restrict__ node_chunk
     return (mbase[node_chunk0[v] - hc0 + (row >> 5)] >> (row & 31)) & 1u;
 }
 
-// Warp-cooperative walk over every (non-zero terminal row, rule end) that can contribute to entity e
-// of one slot: f(count_of_this_lane, term_index) is called by all 32 lanes (lane = query).  Order is
-// fixed: the entity's (relation,row) pairs ascending, then the head's rule ends of that relation.
-// The (pair, rule end) items are flattened over the lanes so that the dependent look-ups
-// (rule end -> node -> row bitmap) run 32 wide; only items whose row is non-zero touch the arena.
-template <typename CT, typename F>
-__device__ __forceinline__ void scan_entity(const rl_graph &g, const rl_rules &r, const CT *__restrict__ arena, size_t abase,
-                                            const uint32_t *__restrict__ mbase, int hc0, const int32_t *__restrict__ tp, int e, F f)
+// ---- item list helpers -------------------------------------------------------------------------
+// k_numeric appends one item {row (slot-relative), node, entity, -} per NON-ZERO row of every rule-end
+// node; k_items_sort buckets a slot's items by entity word.  A warp that owns the 32 entities of a word
+// loads its bucket once (first 32 items stay in registers) and walks the items of one entity at a time.
+struct WordItems {
+    const int4 *its;      // the word's bucket inside items_sorted
+    int n;                // items in the bucket
+    int4 it0;             // lane's item of the first 32 (z = -1: none)
+    uint32_t present;     // entities of the word that own at least one item
+};
+
+__device__ __forceinline__ WordItems load_word_items(const rl_frontier &fr, const rl_slots &s, int W, int slot, int ew)
 {
     const int lane = threadIdx.x & 31;
-    const int p0 = g.ent_ptr[e], p1 = g.ent_ptr[e + 1];
-    for (int pb = p0; pb < p1; pb += 32) {
-        const int pi = pb + lane;
-        int row = 0, t0 = 0, cnt = 0;
-        if (pi < p1) {
-            const int rel = g.ent_rel[pi];
-            row = g.ent_row[pi];
-            t0 = tp[rel];
-            cnt = tp[rel + 1] - t0;
-        }
-        int P = cnt;                                        // inclusive scan: items of pairs 0..lane
+    WordItems wi;
+    const int *off = fr.bucket_off + (size_t)slot * (W + 1);
+    const int b0 = off[ew];
+    wi.n = off[ew + 1] - b0;
+    wi.its = reinterpret_cast<const int4 *>(fr.items_sorted) + fr.item_off[slot] + b0;
+    wi.present = 0u;
+    wi.it0 = make_int4(0, 0, -1, 0);
+    for (int c0 = 0; c0 < wi.n; c0 += 32) {
+        const int4 it = c0 + lane < wi.n ? wi.its[c0 + lane] : make_int4(0, 0, -1, 0);
+        if (c0 == 0) wi.it0 = it;
+        wi.present |= __reduce_or_sync(FULL, it.z >= 0 ? 1u << (it.z & 31) : 0u);
+    }
+    return wi;
+}
+
+// f(count_of_this_lane, t) for every (item of entity i of the word, rule t ending at the item's node);
+// t indexes rl_rules::node_term_rule.  Called by all 32 lanes (lane = query), four row loads in flight.
+template <typename CT, typename F>
+__device__ __forceinline__ void for_entity_items(const WordItems &wi, const rl_rules &r, const CT *__restrict__ arena_slot,
+                                                 int i, F f)
+{
+    const int lane = threadIdx.x & 31;
+    for (int c0 = 0; c0 < wi.n; c0 += 32) {
+        const int4 it = c0 == 0 ? wi.it0 : (c0 + lane < wi.n ? wi.its[c0 + lane] : make_int4(0, 0, -1, 0));
+        uint32_t sel = __ballot_sync(FULL, it.z >= 0 && (it.z & 31) == i);
+        while (sel) {
+            CT cv[4];
+            int nv[4];
 #pragma unroll
-        for (int o = 1; o < 32; o <<= 1) {
-            const int t = __shfl_up_sync(FULL, P, o);
-            if (lane >= o) P += t;
-        }
-        const int T = __shfl_sync(FULL, P, 31);
-        const int first = P - cnt;
-        for (int base = 0; base < T; base += 32) {
-            const int k = min(base + lane, T - 1);
-            int pr = 0;                                      // pair of item k: #lanes with P <= k
-#pragma unroll
-            for (int step = 16; step > 0; step >>= 1)
-                if (__shfl_sync(FULL, P, pr + step - 1) <= k) pr += step;
-            const int t = __shfl_sync(FULL, t0, pr) + (k - __shfl_sync(FULL, first, pr));
-            const int rw = __shfl_sync(FULL, row, pr);
-            long long addr = -1;
-            if (base + lane < T) {
-                const int v = __ldg(r.term_node + t);
-                if (row_valid(r.node_chunk0, mbase, hc0, v, rw)) addr = (long long)r.node_row_off[v] + rw;
+            for (int u = 0; u < 4; ++u) {
+                const int j = sel ? __ffs(sel) - 1 : -1;
+                sel &= sel - 1;
+                const int a = __shfl_sync(FULL, it.x, j & 31);
+                nv[u] = j >= 0 ? __shfl_sync(FULL, it.y, j & 31) : -1;
+                cv[u] = j >= 0 ? arena_slot[(size_t)a * RL_LANES + lane] : (CT)0;
             }
-            uint32_t live = __ballot_sync(FULL, addr >= 0);
-            while (live) {
-                const int j = __ffs(live) - 1;
-                live &= live - 1;
-                const long long a = __shfl_sync(FULL, addr, j);
-                const int tj = __shfl_sync(FULL, t, j);
-                f(arena[(abase + (size_t)a) * RL_LANES + lane], tj);
+#pragma unroll
+            for (int u = 0; u < 4; ++u) {
+                if (nv[u] < 0) continue;
+                for (int t = r.node_term_ptr[nv[u]]; t < r.node_term_ptr[nv[u] + 1]; ++t) f(cv[u], t);
             }
         }
     }

@@ -271,8 +271,6 @@ __device__ __forceinline__ uint32_t numeric_rows(const rl_graph &g, const rl_rul
     if (cur >= 0) flush(cur);
     if (nterm > 0 && nzrows) {
         const bool mine = (nzrows >> lane) & 1u;
-        if (mine)                                            // candidate entities (PredictorPlus kernels)
-            atomicOr(fr.ent_active + (size_t)slot * g.rank_words + (my_dst >> 5), 1u << (my_dst & 31));
         if (fr.items) {                                      // (row, node, entity) items for the aggregation / backward
             int base = 0;
             if (lane == 0) base = atomicAdd(fr.item_cnt + slot, __popc(nzrows));
@@ -445,47 +443,19 @@ k_predictor_scores(rl_graph g, rl_rules r, rl_slots s, rl_frontier fr, const flo
         const uint32_t bits = __ballot_sync(FULL, any);
         if (lane == 0) ms[e] = bits;
     };
-    const int *off = fr.bucket_off + (size_t)slot * (W + 1);
-    const int b0 = off[ew], n = off[ew + 1] - b0;
-    const int4 *its = reinterpret_cast<const int4 *>(fr.items_sorted) + fr.item_off[slot] + b0;
-    uint32_t present = 0u;                                        // entities of this word that own items
-    int4 it0 = make_int4(0, 0, -1, 0);
-    for (int c0 = 0; c0 < n; c0 += 32) {
-        const int4 it = c0 + lane < n ? its[c0 + lane] : make_int4(0, 0, -1, 0);
-        if (c0 == 0) it0 = it;
-        present |= __reduce_or_sync(FULL, it.z >= 0 ? 1u << (it.z & 31) : 0u);
-    }
+    WordItems wi = load_word_items(fr, s, W, slot, ew);
     for (int i = 0; i < e1; ++i)
-        if (!((present >> i) & 1u)) finish(ew * 32 + i, 0.0, false);
+        if (!((wi.present >> i) & 1u)) finish(ew * 32 + i, 0.0, false);
+    uint32_t present = wi.present;
     while (present) {
         const int i = __ffs(present) - 1;
         present &= present - 1;
         double acc = 0.0;
         bool any = false;
-        for (int c0 = 0; c0 < n; c0 += 32) {
-            const int4 it = c0 == 0 ? it0 : (c0 + lane < n ? its[c0 + lane] : make_int4(0, 0, -1, 0));
-            uint32_t sel = __ballot_sync(FULL, it.z >= 0 && (it.z & 31) == i);
-            while (sel) {
-                CT cv[4];
-                int nv[4];
-#pragma unroll
-                for (int u = 0; u < 4; ++u) {                      // four row loads in flight
-                    const int j = sel ? __ffs(sel) - 1 : -1;
-                    sel &= sel - 1;
-                    const int a = __shfl_sync(FULL, it.x, j & 31);
-                    nv[u] = j >= 0 ? __shfl_sync(FULL, it.y, j & 31) : -1;
-                    cv[u] = j >= 0 ? arena[(size_t)a * RL_LANES + lane] : (CT)0;
-                }
-#pragma unroll
-                for (int u = 0; u < 4; ++u) {
-                    if (nv[u] < 0) continue;
-                    const float cf = (float)cv[u];                 // x.float() * w (predictors.py:64)
-                    for (int t = r.node_term_ptr[nv[u]]; t < r.node_term_ptr[nv[u] + 1]; ++t)
-                        acc += (double)cf * (double)__ldg(w + r.node_term_rule[t]);
-                    any |= cv[u] != 0;
-                }
-            }
-        }
+        for_entity_items<CT>(wi, r, arena, i, [&](CT c, int t) {
+            acc += (double)(float)c * (double)__ldg(w + r.node_term_rule[t]);      // x.float() * w (predictors.py:64)
+            any |= c != 0;
+        });
         finish(ew * 32 + i, acc, any);
     }
 }
@@ -945,7 +915,7 @@ int rl_prepare_slots(const rl_graph *g, int32_t S, const int32_t *slot_head, con
 
 static int check_frontier(const rl_frontier *fr, const char *who)
 {
-    if (!fr || !fr->arena || !fr->row_mask || !fr->node_cnt || !fr->ent_active || !fr->overflow) return fail(RL_ERR_ARG, who);
+    if (!fr || !fr->arena || !fr->row_mask || !fr->node_cnt || !fr->overflow) return fail(RL_ERR_ARG, who);
     if (fr->count_bits != 32 && fr->count_bits != 64) return fail(RL_ERR_ARG, "count_bits must be 32 or 64");
     return RL_OK;
 }
@@ -999,6 +969,17 @@ int rl_node_counts_dense(const rl_graph *g, const rl_rules *r, const rl_slots *s
 static int check_items(const rl_frontier *fr, const char *who)
 {
     if (!fr->items || !fr->items_sorted || !fr->item_off || !fr->item_cnt || !fr->bucket_cnt || !fr->bucket_off) return fail(RL_ERR_ARG, who);
+    return RL_OK;
+}
+
+int rl_sort_items(const rl_graph *g, const rl_slots *s, const rl_frontier *fr, void *stream)
+{
+    if (!g || !s) return fail(RL_ERR_ARG, "rl_sort_items: null argument");
+    if (check_frontier(fr, "rl_sort_items: incomplete rl_frontier") != RL_OK) return RL_ERR_ARG;
+    if (check_items(fr, "rl_sort_items: the frontier was expanded without an item list") != RL_OK) return RL_ERR_ARG;
+    if (s->num_slots <= 0) return RL_OK;
+    k_items_sort<<<s->num_slots, 512, 0, (cudaStream_t)stream>>>(g->rank_words, *fr);
+    CHECK_LAUNCH("k_items_sort");
     return RL_OK;
 }
 

@@ -20,29 +20,26 @@ k_plus_mask(rl_graph g, rl_rules r, rl_slots s, rl_frontier fr, uint32_t *__rest
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const int slot = blockIdx.y;
     const int ew = blockIdx.x * WARPS_PER_BLOCK + warp;
-    const int N = g.num_entities, R = g.num_relations;
-    if (ew >= g.rank_words) return;
+    const int N = g.num_entities, W = g.rank_words;
+    if (ew >= W) return;
     const int q = s.slot_head[slot];
-    const int hc0 = r.lvl_ptr[(size_t)q * (r.max_len + 1)];
-    const uint32_t *mbase = fr.row_mask + (size_t)s.mask_off[slot];
-    const size_t abase = (size_t)s.arena_off[slot];
-    const CT *arena = reinterpret_cast<const CT *>(fr.arena);
-    const int32_t *tp = r.term_ptr + (size_t)q * R;
+    const CT *arena = reinterpret_cast<const CT *>(fr.arena) + (size_t)s.arena_off[slot] * RL_LANES;
     const int h = s.lane_h[slot * RL_LANES + lane];
     const bool has_zr = r.zr_ptr[q + 1] > r.zr_ptr[q];
-    uint32_t act = fr.ent_active[(size_t)slot * g.rank_words + ew];
-    if (has_zr) act |= __reduce_or_sync(FULL, (h >= 0 && (h >> 5) == ew) ? (1u << (h & 31)) : 0u);
-    const int e1 = min(32, N - ew * 32);
+    WordItems wi = load_word_items(fr, s, W, slot, ew);
+    uint32_t todo = wi.present;
+    if (has_zr) todo |= __reduce_or_sync(FULL, (h >= 0 && (h >> 5) == ew) ? (1u << (h & 31)) : 0u);
     uint32_t my_bits = 0;                                   // lane i keeps the word of entity ew*32+i
-    for (int i = 0; i < e1; ++i) {
-        if (!((act >> i) & 1u)) continue;
-        const int e = ew * 32 + i;
+    while (todo) {
+        const int i = __ffs(todo) - 1;
+        todo &= todo - 1;
         bool any = false;
-        scan_entity<CT>(g, r, arena, abase, mbase, hc0, tp, e, [&](CT c, int) { any |= (c != 0); });
-        if (has_zr && h == e) any = true;
+        if ((wi.present >> i) & 1u) for_entity_items<CT>(wi, r, arena, i, [&](CT c, int) { any |= (c != 0); });
+        if (has_zr && h == ew * 32 + i) any = true;
         const uint32_t bits = __ballot_sync(FULL, any);
         if (lane == i) my_bits = bits;
     }
+    const int e1 = min(32, N - ew * 32);
     if (lane < e1) {
         nzmask[(size_t)slot * N + ew * 32 + lane] = my_bits;
         cand_cnt[(size_t)slot * N + ew * 32 + lane] = __popc(my_bits);
@@ -66,19 +63,16 @@ k_plus_features(rl_graph g, rl_rules r, rl_slots s, rl_frontier fr, const uint32
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const int slot = blockIdx.y;
     const int ew = blockIdx.x * WARPS_PER_BLOCK + warp;           // entity word: 32 entities, one coalesced mask read
-    const int N = g.num_entities, R = g.num_relations;
+    const int N = g.num_entities;
     if (ew >= g.rank_words) return;
     const int e_lane = ew * 32 + lane;
     const uint32_t my_bits = e_lane < N ? nzmask[(size_t)slot * N + e_lane] : 0u;
     uint32_t cand_ents = __ballot_sync(FULL, my_bits != 0u);
     if (cand_ents == 0u) return;
     const int q = s.slot_head[slot];
-    const int hc0 = r.lvl_ptr[(size_t)q * (r.max_len + 1)];
-    const uint32_t *mbase = fr.row_mask + (size_t)s.mask_off[slot];
-    const size_t abase = (size_t)s.arena_off[slot];
-    const CT *arena = reinterpret_cast<const CT *>(fr.arena);
-    const int32_t *tp = r.term_ptr + (size_t)q * R;
+    const CT *arena = reinterpret_cast<const CT *>(fr.arena) + (size_t)s.arena_off[slot] * RL_LANES;
     const int h = s.lane_h[slot * RL_LANES + lane];
+    WordItems wi = load_word_items(fr, s, g.rank_words, slot, ew);
   while (cand_ents) {
     const int ei = __ffs(cand_ents) - 1;
     cand_ents &= cand_ents - 1;
@@ -115,9 +109,8 @@ k_plus_features(rl_graph g, rl_rules r, rl_slots s, rl_frontier fr, const uint32
                 }
             }
         };
-        scan_entity<CT>(g, r, arena, abase, mbase, hc0, tp, e, [&](CT c, int t) {
-            if (__any_sync(FULL, c != 0)) add((float)c, r.term_rule[t]);
-        });
+        if ((wi.present >> ei) & 1u)
+            for_entity_items<CT>(wi, r, arena, ei, [&](CT c, int t) { add((float)c, r.node_term_rule[t]); });
         if (h == e)                                            // empty-body rules: count = one_hot(h)
             for (int t = r.zr_ptr[q]; t < r.zr_ptr[q + 1]; ++t) add(1.f, r.zr_rule[t]);
         if (mine) {
@@ -181,8 +174,9 @@ k_plus_gather(int N, const uint32_t *__restrict__ nzmask, const int64_t *__restr
 // backward into the rule embeddings: gA[rule][h] += sum_cells fp32(count) * dA[cell][h]
 // (and gB from dB for the PNA squared-sum branch).  Block per (slot, rule end).
 // ------------------------------------------------------------------------------------------
-// Entity-centric (like the forward): for every candidate entity, every non-zero terminal row and
-// every query lane with a non-zero count, lanes 0..H-1 add count * dA[cell][h] into gA[rule][h].
+// One warp per item (non-zero row of a rule-end node): for every query lane with a non-zero count,
+// lanes 0..H-1 add count * dA[cell][h] into gA[rule][h] of every rule ending at the item's node.
+#define PLUS_ITEM_BLOCKS 96
 template <typename CT>
 __global__ void __launch_bounds__(WARPS_PER_BLOCK * 32)
 k_plus_backward(rl_graph g, rl_rules r, rl_slots s, rl_frontier fr, const uint32_t *__restrict__ nzmask,
@@ -192,60 +186,58 @@ k_plus_backward(rl_graph g, rl_rules r, rl_slots s, rl_frontier fr, const uint32
 {
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const int slot = blockIdx.y;
-    const int ew = blockIdx.x * WARPS_PER_BLOCK + warp;
-    const int N = g.num_entities, R = g.num_relations;
-    if (ew >= g.rank_words) return;
+    const int N = g.num_entities;
     const int q = s.slot_head[slot];
     const uint32_t *ms = nzmask + (size_t)slot * N;
     const int64_t *co = cand_off + (size_t)slot * N;
-    const int e_lane = ew * 32 + lane;
-    const uint32_t my_bits = e_lane < N ? ms[e_lane] : 0u;
-    uint32_t cand_ents = __ballot_sync(FULL, my_bits != 0u);
-    if (cand_ents == 0u) return;
-    const int hc0 = r.lvl_ptr[(size_t)q * (r.max_len + 1)];
-    const uint32_t *mbase = fr.row_mask + (size_t)s.mask_off[slot];
-    const size_t abase = (size_t)s.arena_off[slot];
-    const CT *arena = reinterpret_cast<const CT *>(fr.arena);
-    const int32_t *tp = r.term_ptr + (size_t)q * R;
-    const int hq = s.lane_h[slot * RL_LANES + lane];
-    while (cand_ents) {
-        const int ei = __ffs(cand_ents) - 1;
-        cand_ents &= cand_ents - 1;
-        const int e = ew * 32 + ei;
-        const uint32_t bits = __shfl_sync(FULL, my_bits, ei);
-        const long long base = co[e];
-        auto contribute = [&](float cf, int rule) {             // cf = this lane's count (0 if none)
-            const int lr = rule_local[rule];
-            uint32_t nzl = __ballot_sync(FULL, cf != 0.f);
-            for (int h0 = 0; h0 < H; h0 += 32) {
-                float a = 0.f, b = 0.f;
-                uint32_t todo = nzl;
-                while (todo) {
-                    const int bq = __ffs(todo) - 1;
-                    todo &= todo - 1;
-                    const float cb = __shfl_sync(FULL, cf, bq);
-                    const long long idx = base + __popc(bits & ((1u << bq) - 1u));
-                    if (h0 + lane < H) {
-                        a += cb * dA[idx * H + h0 + lane];
-                        if (dB) b += cb * dB[idx * H + h0 + lane];
-                    }
-                }
+    auto contribute = [&](float cf, int rule, uint32_t bits, long long base) {   // cf = this lane's count (0 if none)
+        const int lr = rule_local[rule];
+        const uint32_t nzl = __ballot_sync(FULL, cf != 0.f);
+        for (int h0 = 0; h0 < H; h0 += 32) {
+            float a = 0.f, b = 0.f;
+            uint32_t todo = nzl;
+            while (todo) {
+                const int bq = __ffs(todo) - 1;
+                todo &= todo - 1;
+                const float cb = __shfl_sync(FULL, cf, bq);
+                const long long idx = base + __popc(bits & ((1u << bq) - 1u));
                 if (h0 + lane < H) {
-                    if (a != 0.f) atomicAdd(gA + (size_t)lr * H + h0 + lane, a);
-                    if (dB && b != 0.f) atomicAdd(gB + (size_t)lr * H + h0 + lane, b);
+                    a += cb * dA[idx * H + h0 + lane];
+                    if (dB) b += cb * dB[idx * H + h0 + lane];
                 }
             }
-        };
-        scan_entity<CT>(g, r, arena, abase, mbase, hc0, tp, e, [&](CT c, int t) { contribute((float)c, r.term_rule[t]); });
-        const bool zr_here = __any_sync(FULL, hq == e);
-        if (zr_here)
-            for (int t = r.zr_ptr[q]; t < r.zr_ptr[q + 1]; ++t) contribute(hq == e ? 1.f : 0.f, r.zr_rule[t]);
+            if (h0 + lane < H) {
+                if (a != 0.f) atomicAdd(gA + (size_t)lr * H + h0 + lane, a);
+                if (dB && b != 0.f) atomicAdd(gB + (size_t)lr * H + h0 + lane, b);
+            }
+        }
+    };
+    if (blockIdx.x == 0 && warp == 0 && r.zr_ptr[q + 1] > r.zr_ptr[q]) {         // empty-body rules: count = one_hot(h)
+        const int hq = s.lane_h[slot * RL_LANES + lane];
+        for (int bq = 0; bq < 32; ++bq) {
+            const int e = __shfl_sync(FULL, hq, bq);
+            if (e < 0) continue;
+            const uint32_t bits = ms[e];
+            const long long base = co[e];
+            for (int t = r.zr_ptr[q]; t < r.zr_ptr[q + 1]; ++t) contribute(lane == bq ? 1.f : 0.f, r.zr_rule[t], bits, base);
+        }
+    }
+    const int n = fr.item_cnt[slot];
+    const CT *arena = reinterpret_cast<const CT *>(fr.arena) + (size_t)s.arena_off[slot] * RL_LANES;
+    const int4 *it = reinterpret_cast<const int4 *>(fr.items) + fr.item_off[slot];
+    for (int i = blockIdx.x * WARPS_PER_BLOCK + warp; i < n; i += PLUS_ITEM_BLOCKS * WARPS_PER_BLOCK) {
+        const int4 rec = __ldg(it + i);                            // {row, node, entity, -}
+        const float cf = (float)arena[(size_t)rec.x * RL_LANES + lane];
+        const uint32_t bits = ms[rec.z];
+        const long long base = co[rec.z];
+        for (int t = r.node_term_ptr[rec.y]; t < r.node_term_ptr[rec.y + 1]; ++t) contribute(cf, r.node_term_rule[t], bits, base);
     }
 }
 
 // ------------------------------------------------------------------------------------------
 // E-step statistics (Predictor.compute_H, src/predictors.py:82-119): per rule end and query,
 // the count at the query's answer entity and the sum of the counts over all entities.
+// Indexed by t - node_term_ptr[first node of the head] (the head's rules in node order).
 // ------------------------------------------------------------------------------------------
 template <typename CT>
 __global__ void __launch_bounds__(WARPS_PER_BLOCK * 32)
@@ -254,30 +246,22 @@ k_rule_stats(rl_graph g, rl_rules r, rl_slots s, rl_frontier fr, int max_terms, 
 {
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const int slot = blockIdx.y;
-    const int ew = blockIdx.x * WARPS_PER_BLOCK + warp;
-    const int R = g.num_relations;
-    if (ew >= g.rank_words) return;
-    uint32_t act = fr.ent_active[(size_t)slot * g.rank_words + ew];
-    if (act == 0u) return;
     const int q = s.slot_head[slot];
-    const int hc0 = r.lvl_ptr[(size_t)q * (r.max_len + 1)];
-    const uint32_t *mbase = fr.row_mask + (size_t)s.mask_off[slot];
-    const size_t abase = (size_t)s.arena_off[slot];
-    const CT *arena = reinterpret_cast<const CT *>(fr.arena);
-    const int32_t *tp = r.term_ptr + (size_t)q * R;
-    const int t_first = tp[0];
+    const int t_first = r.node_term_ptr[r.head_node_ptr[q]];
     const int ans = s.lane_t[slot * RL_LANES + lane];
     double *sums = sum_cnt + (size_t)slot * max_terms * RL_LANES;
     double *poss = pos_cnt + (size_t)slot * max_terms * RL_LANES;
-    while (act) {
-        const int e = ew * 32 + __ffs(act) - 1;
-        act &= act - 1;
-        scan_entity<CT>(g, r, arena, abase, mbase, hc0, tp, e, [&](CT c, int t) {
-            if (c != 0) {
-                atomicAdd(sums + (size_t)(t - t_first) * RL_LANES + lane, (double)c);
-                if (e == ans) poss[(size_t)(t - t_first) * RL_LANES + lane] = (double)c;
-            }
-        });
+    const int n = fr.item_cnt[slot];
+    const CT *arena = reinterpret_cast<const CT *>(fr.arena) + (size_t)s.arena_off[slot] * RL_LANES;
+    const int4 *it = reinterpret_cast<const int4 *>(fr.items) + fr.item_off[slot];
+    for (int i = blockIdx.x * WARPS_PER_BLOCK + warp; i < n; i += PLUS_ITEM_BLOCKS * WARPS_PER_BLOCK) {
+        const int4 rec = __ldg(it + i);
+        const CT c = arena[(size_t)rec.x * RL_LANES + lane];
+        if (c == 0) continue;
+        for (int t = r.node_term_ptr[rec.y]; t < r.node_term_ptr[rec.y + 1]; ++t) {
+            atomicAdd(sums + (size_t)(t - t_first) * RL_LANES + lane, (double)c);
+            if (rec.z == ans) poss[(size_t)(t - t_first) * RL_LANES + lane] = (double)c;
+        }
     }
 }
 
@@ -286,8 +270,8 @@ k_rule_stats(rl_graph g, rl_rules r, rl_slots s, rl_frontier fr, int max_terms, 
 // ------------------------------------------------------------------------------------------
 static int bad_frontier(const rl_frontier *fr)
 {
-    return !fr || !fr->arena || !fr->row_mask || !fr->node_cnt || !fr->ent_active ||
-           (fr->count_bits != 32 && fr->count_bits != 64);
+    return !fr || !fr->arena || !fr->row_mask || !fr->node_cnt || !fr->items || !fr->items_sorted || !fr->item_cnt ||
+           !fr->bucket_cnt || !fr->bucket_off || (fr->count_bits != 32 && fr->count_bits != 64);
 }
 
 extern "C" {
@@ -299,6 +283,8 @@ int rl_plus_mask(const rl_graph *g, const rl_rules *r, const rl_slots *s, const 
     if (s->num_slots <= 0) return RL_OK;
     dim3 grid((g->rank_words + WARPS_PER_BLOCK - 1) / WARPS_PER_BLOCK, s->num_slots);
     cudaStream_t st = (cudaStream_t)stream;
+    const int rc = rl_sort_items(g, s, fr, stream);              // bucket the item list by entity word first
+    if (rc != RL_OK) return rc;
     if (fr->count_bits == 32) k_plus_mask<uint32_t><<<grid, WARPS_PER_BLOCK * 32, 0, st>>>(*g, *r, *s, *fr, nzmask, cand_cnt);
     else k_plus_mask<unsigned long long><<<grid, WARPS_PER_BLOCK * 32, 0, st>>>(*g, *r, *s, *fr, nzmask, cand_cnt);
     CHECK_LAUNCH("k_plus_mask");
@@ -331,7 +317,7 @@ int rl_rule_stats(const rl_graph *g, const rl_rules *r, const rl_slots *s, const
 {
     if (!g || !r || !s || !sum_cnt || !pos_cnt || bad_frontier(fr) || max_terms <= 0) return rl_fail(RL_ERR_ARG, "rl_rule_stats: bad argument");
     if (s->num_slots <= 0) return RL_OK;
-    dim3 grid((g->rank_words + WARPS_PER_BLOCK - 1) / WARPS_PER_BLOCK, s->num_slots);
+    dim3 grid(PLUS_ITEM_BLOCKS, s->num_slots);
     cudaStream_t st = (cudaStream_t)stream;
     if (fr->count_bits == 32) k_rule_stats<uint32_t><<<grid, WARPS_PER_BLOCK * 32, 0, st>>>(*g, *r, *s, *fr, max_terms, sum_cnt, pos_cnt);
     else k_rule_stats<unsigned long long><<<grid, WARPS_PER_BLOCK * 32, 0, st>>>(*g, *r, *s, *fr, max_terms, sum_cnt, pos_cnt);
@@ -371,7 +357,7 @@ int rl_plus_backward(const rl_graph *g, const rl_rules *r, const rl_slots *s, co
         return rl_fail(RL_ERR_ARG, "rl_plus_backward: bad argument");
     if (s->num_slots <= 0) return RL_OK;
     (void)max_terms;
-    dim3 grid((g->rank_words + WARPS_PER_BLOCK - 1) / WARPS_PER_BLOCK, s->num_slots);
+    dim3 grid(PLUS_ITEM_BLOCKS, s->num_slots);
     cudaStream_t st = (cudaStream_t)stream;
     if (fr->count_bits == 32) k_plus_backward<uint32_t><<<grid, WARPS_PER_BLOCK * 32, 0, st>>>(*g, *r, *s, *fr, nzmask, cand_off, rule_local, H, dA, dB, gA, gB);
     else k_plus_backward<unsigned long long><<<grid, WARPS_PER_BLOCK * 32, 0, st>>>(*g, *r, *s, *fr, nzmask, cand_off, rule_local, H, dA, dB, gA, gB);

@@ -145,7 +145,7 @@ class Predictor(_RuleModel):
         # [S,T,32] -> [B,T] in query order, then pick the head's rules in rule-file order
         to_q = lambda x: x.permute(0, 2, 1).reshape(sl.S * LANES, n_terms)[valid]
         sum_q, pos_q = to_q(stats[0]), to_q(stats[1])
-        term_local = torch.from_numpy(cr.rule_term[ids] - cr.term_ptr_host[query_r * R]).to(device)
+        term_local = torch.from_numpy(np.where(cr.rule_nterm[ids] >= 0, cr.rule_nterm[ids] - cr.head_nterm0[query_r], -1)).to(device)
         has_body = term_local >= 0                                                   # empty-body rules: count = one_hot(h)
         tl = term_local.clamp(min=0)
         sum_c = torch.where(has_body.unsqueeze(0), sum_q[:, tl], torch.ones(B, len(ids), dtype=torch.float64, device=device))

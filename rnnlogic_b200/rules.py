@@ -133,6 +133,9 @@ class CompiledRules:
         node_term_rule = t_rule[o_n] if t_rule.shape[0] else np.zeros(0, np.int64)
         node_term_ptr = np.zeros(max(1, self.num_nodes) + 1, dtype=np.int64)
         np.cumsum(node_nterm, out=node_term_ptr[1:])
+        self.rule_nterm = np.full(self.num_rules, -1, dtype=np.int64)      # position of a rule in node_term_rule (-1: empty body)
+        self.rule_nterm[node_term_rule] = np.arange(node_term_rule.shape[0])
+        self.head_nterm0 = node_term_ptr[np.minimum(head_node_ptr[:-1], max(1, self.num_nodes))]   # first term of each head
         term_rows = np.where(node_nterm[:self.num_nodes] > 0, node_rows, 0) if self.num_nodes else np.zeros(0, np.int64)
         tr_sum = np.zeros(self.num_nodes + 1, dtype=np.int64)
         np.cumsum(term_rows, out=tr_sum[1:])
