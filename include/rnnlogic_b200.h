@@ -44,8 +44,7 @@ enum rl_status {
  * in-edges edge_src[row_start[k] .. row_start[k+1]).  rank_tab answers "which row of relation
  * rho is entity e" with one 8-byte load: word w = e>>5 holds {bits, rows before this word}.
  * ord_* keep the reference's per-relation edge order (train.txt order) so that an
- * `edges_to_remove` index (data.py:164-170) maps to its (head, tail). ent_* is the transpose:
- * for entity e the (relation, row-within-relation) pairs where e is a tail.  fsrc_ptr/frow_start/
+ * `edges_to_remove` index (data.py:164-170) maps to its (head, tail).  fsrc_ptr/frow_start/
  * fedge_dstrow/srank_tab are the same edges sorted by (relation, head, tail). */
 typedef struct rl_graph {
     int32_t num_entities, num_relations, rank_words, total_rows, num_edges;
@@ -57,9 +56,6 @@ typedef struct rl_graph {
     const int32_t *ord_ptr;    /* [R+1]            */
     const int32_t *ord_h;      /* [E] head of the k-th train edge of the relation */
     const int32_t *ord_t;      /* [E] tail ...                                    */
-    const int32_t *ent_ptr;    /* [N+1]            */
-    const int32_t *ent_rel;    /* [total_rows]     */
-    const int32_t *ent_row;    /* [total_rows] row index local to the relation */
     /* forward DCSR (by source), used to find which destination rows a frontier can reach */
     const int32_t *fsrc_ptr;     /* [R+1] distinct heads per relation */
     const int32_t *frow_start;   /* [total_srcs+1] out-edge offsets */
@@ -72,25 +68,19 @@ typedef struct rl_graph {
  * prefix); nodes of one head are contiguous and ordered by depth.  A node's frontier is a
  * [rows(node_rel) x 32] block at row offset node_row_off inside the slot's arena.  Work is cut
  * into chunks of <= 32 consecutive rows of one node; lvl_ptr[q*(max_len+1)+d] .. [..+d+1] is
- * the chunk range of depth d+1 of head q.  term_* lists, per (head, last relation), the
- * (node, rule id) pairs of rules ending at a node; zr_* the rules with an empty body. */
+ * the chunk range of depth d+1 of head q.  node_term_* lists the rules ending at each node; zr_* the
+ * rules with an empty body. */
 typedef struct rl_rules {
     int32_t num_nodes, num_rules, max_len, num_chunks, num_terms;
     const int32_t *node_rel;      /* [num_nodes] */
-    const int32_t *node_parent;   /* [num_nodes] global node id, -1 = the one-hot root */
     const int64_t *node_row_off;  /* [num_nodes] */
     const int32_t *head_node_ptr; /* [R+1] */
     const int32_t *lvl_ptr;       /* [R*(max_len+1)] */
     const int32_t *chunk_node;    /* [num_chunks] */
     const int32_t *chunk_row0;    /* [num_chunks] first row, local to the node */
-    const int32_t *term_ptr;      /* [R*R+1] key = head*R + last relation */
-    const int32_t *term_node;     /* [num_terms] */
-    const int32_t *term_rule;     /* [num_terms] */
     const int32_t *zr_ptr;        /* [R+1] */
     const int32_t *zr_rule;       /* [#empty-body rules] */
-    const int32_t *lvl_node_ptr;  /* [R*(max_len+1)] node range per (head, depth), like lvl_ptr */
     const int32_t *node_chunk0;   /* [num_nodes] global id of the node's first chunk */
-    const int32_t *node_nterm;    /* [num_nodes] number of rules ending at the node */
     /* packed per-node record, 32-byte aligned: {rel, parent, parent rel, dst_ptr[rel],
      *  rows(rel), chunk0, parent chunk0, nterm} -- one load instead of a look-up chain */
     const int32_t *node_rec;      /* [num_nodes*8] */
@@ -118,7 +108,7 @@ typedef struct rl_slots {
     const int64_t *mask_off;   /* [S] first row_mask word of the slot (one word per chunk) */
 } rl_slots;
 
-/* Per-call frontier state (all DEVICE memory owned by the caller; row_mask, node_cnt, ent_active
+/* Per-call frontier state (all DEVICE memory owned by the caller; row_mask, node_cnt
  * and overflow must be zero before depth 1).  A row of a node is meaningful iff its row_mask bit
  * is set; rows outside the bitmap are never written nor read (exact: they are all-zero). */
 typedef struct rl_frontier {
@@ -126,9 +116,8 @@ typedef struct rl_frontier {
     void *arena;           /* [rows][32] counts */
     uint32_t *row_mask;    /* one word per 32-row chunk */
     int32_t *node_cnt;     /* valid rows per (slot, node) */
-    uint32_t *ent_active;  /* [S][rank_words] entities some rule end may reach */
     int32_t *overflow;     /* set to 1 when a 32-bit count overflowed */
-    /* Item list (may be all NULL when only the PredictorPlus / debug entry points are used): one
+    /* Item list (may be all NULL when only rl_expand_level / rl_node_counts_dense are used): one
      * int32x4 record {row (slot-relative), node, entity, -} per NON-ZERO row of every rule-end node,
      * appended by k_numeric; slot s owns [item_off[s], item_off[s+1]) (capacity = rows of its head's
      * rule-end nodes, so it cannot overflow).  item_cnt[S], bucket_cnt[S*rank_words] zeroed by the

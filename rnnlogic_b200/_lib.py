@@ -29,17 +29,16 @@ class RlGraph(C.Structure):
     _fields_ = [("num_entities", C.c_int32), ("num_relations", C.c_int32), ("rank_words", C.c_int32),
                 ("total_rows", C.c_int32), ("num_edges", C.c_int32),
                 ("dst_ptr", vp), ("row_dst", vp), ("row_start", vp), ("edge_src", vp), ("rank_tab", vp),
-                ("ord_ptr", vp), ("ord_h", vp), ("ord_t", vp), ("ent_ptr", vp), ("ent_rel", vp), ("ent_row", vp),
+                ("ord_ptr", vp), ("ord_h", vp), ("ord_t", vp),
                 ("fsrc_ptr", vp), ("frow_start", vp), ("fedge_dstrow", vp), ("srank_tab", vp)]
 
 
 class RlRules(C.Structure):
     _fields_ = [("num_nodes", C.c_int32), ("num_rules", C.c_int32), ("max_len", C.c_int32),
                 ("num_chunks", C.c_int32), ("num_terms", C.c_int32),
-                ("node_rel", vp), ("node_parent", vp), ("node_row_off", vp), ("head_node_ptr", vp),
-                ("lvl_ptr", vp), ("chunk_node", vp), ("chunk_row0", vp), ("term_ptr", vp),
-                ("term_node", vp), ("term_rule", vp), ("zr_ptr", vp), ("zr_rule", vp),
-                ("lvl_node_ptr", vp), ("node_chunk0", vp), ("node_nterm", vp), ("node_rec", vp), ("node_prow_off", vp),
+                ("node_rel", vp), ("node_row_off", vp), ("head_node_ptr", vp),
+                ("lvl_ptr", vp), ("chunk_node", vp), ("chunk_row0", vp), ("zr_ptr", vp), ("zr_rule", vp),
+                ("node_chunk0", vp), ("node_rec", vp), ("node_prow_off", vp),
                 ("lvl_sym_ptr", vp), ("sym_node", vp), ("sym_w0", vp), ("node_term_ptr", vp), ("node_term_rule", vp)]
 
 
@@ -50,7 +49,7 @@ class RlSlots(C.Structure):
 
 class RlFrontier(C.Structure):
     _fields_ = [("count_bits", C.c_int32), ("arena", vp), ("row_mask", vp), ("node_cnt", vp),
-                ("ent_active", vp), ("overflow", vp), ("items", vp), ("items_sorted", vp), ("item_off", vp),
+                ("overflow", vp), ("items", vp), ("items_sorted", vp), ("item_off", vp),
                 ("item_cnt", vp), ("bucket_cnt", vp), ("bucket_off", vp)]
 
 

@@ -62,7 +62,7 @@ class Slots:
                                    self.nz_off.data_ptr(), self.mask_off.data_ptr())
         self._keep = (all_h, all_t, etr, d)
         self.arena = None
-        self.state = None         # int32 buffer: row_mask | node_cnt | ent_active | overflow
+        self.state = None         # int32 buffer: row_mask | node_cnt | item_cnt | bucket_cnt | overflow
         self.overflow = None
         self.frontier = None      # _lib.RlFrontier
         self.count_bits = 32
@@ -142,10 +142,10 @@ class Grounder:
         dev = self.device
         sl.count_bits = bits
         W = self.graph.rank_words
-        n_mask, n_cnt, n_ent = sl.mask_words + 1, sl.nz_total + 1, sl.S * W
+        n_mask, n_cnt = sl.mask_words + 1, sl.nz_total + 1
         n_arena = max(1, sl.arena_rows) * LANES * (1 if bits == 32 else 2)
         n_bkt, n_boff = sl.S * W, sl.S * (W + 1)
-        n_state = n_mask + n_cnt + n_ent + sl.S + n_bkt + 1            # zeroed: masks | node counts | entity bits | item counts | buckets | overflow
+        n_state = n_mask + n_cnt + sl.S + n_bkt + 1                    # zeroed: row bitmaps | node counts | item counts | buckets | overflow
         n_items = 4 * max(1, sl.item_cap)                              # int32x4 records, exact upper bound (cannot overflow)
         n_scratch = 2 * n_items + n_boff
         if getattr(sl, "use_workspace", False):
@@ -169,10 +169,10 @@ class Grounder:
         sl.scratch = scratch
         sl.overflow = sl.state[-1:]
         base = sl.state.data_ptr()
-        o_cnt, o_ent = n_mask, n_mask + n_cnt
-        o_icnt, o_bkt = o_ent + n_ent, o_ent + n_ent + sl.S
+        o_cnt = n_mask
+        o_icnt, o_bkt = o_cnt + n_cnt, o_cnt + n_cnt + sl.S
         sb = scratch.data_ptr()
-        sl.frontier = _lib.RlFrontier(bits, sl.arena.data_ptr(), base, base + 4 * o_cnt, base + 4 * o_ent,
+        sl.frontier = _lib.RlFrontier(bits, sl.arena.data_ptr(), base, base + 4 * o_cnt,
                                       sl.overflow.data_ptr(), sb, sb + 4 * n_items, sl.item_off.data_ptr(),
                                       base + 4 * o_icnt, base + 4 * o_bkt, sb + 8 * n_items)
         L = _lib.lib()
@@ -197,7 +197,7 @@ class Grounder:
         step of a steady-state loop triggers a cudaMalloc."""
         W = self.graph.rank_words
         n_arena = max(max(1, sl.arena_rows) * LANES for sl in slots_list)
-        n_state = max(sl.mask_words + 1 + sl.nz_total + 1 + 2 * sl.S * W + sl.S + 1 for sl in slots_list)
+        n_state = max(sl.mask_words + 1 + sl.nz_total + 1 + sl.S * W + sl.S + 1 for sl in slots_list)
         n_scratch = max(8 * max(1, sl.item_cap) + sl.S * (W + 1) for sl in slots_list)
         for name, n in (("_ws_arena", n_arena), ("_ws_state", n_state), ("_ws_items", n_scratch)):
             cur = getattr(self, name)
@@ -210,7 +210,7 @@ class Grounder:
         sl.state = torch.zeros(8, dtype=torch.int32, device=self.device)
         sl.overflow = sl.state[-1:]
         p = sl.state.data_ptr()
-        sl.frontier = _lib.RlFrontier(32, sl.arena.data_ptr(), p, p + 4, p + 8, sl.overflow.data_ptr(),
+        sl.frontier = _lib.RlFrontier(32, sl.arena.data_ptr(), p, p + 4, sl.overflow.data_ptr(),
                                       None, None, None, None, None, None)
 
     def ground(self, sl: Slots, check_overflow: bool = True) -> Slots:

@@ -44,7 +44,6 @@ class DeviceGraph:
             kg.entity_size, kg.relation_size, kg.rank_words, int(h["row_dst"].shape[0]), int(h["edge_src"].shape[0]),
             t["dst_ptr"].data_ptr(), t["row_dst"].data_ptr(), t["row_start"].data_ptr(), t["edge_src"].data_ptr(),
             t["rank_tab"].data_ptr(), t["ord_ptr"].data_ptr(), t["ord_h"].data_ptr(), t["ord_t"].data_ptr(),
-            t["ent_ptr"].data_ptr(), t["ent_rel"].data_ptr(), t["ent_row"].data_ptr(),
             t["fsrc_ptr"].data_ptr(), t["frow_start"].data_ptr(), t["fedge_dstrow"].data_ptr(),
             t["srank_tab"].data_ptr())
         self.answers = {}
@@ -225,10 +224,6 @@ class KnowledgeGraph(object):
         rank_tab = np.empty((R * W, 2), dtype=np.uint32)
         rank_tab[:, 0] = bits
         rank_tab[:, 1] = prefix.reshape(-1).astype(np.uint32)
-        # transpose: entity -> (relation, local row) pairs in which it is a tail
-        eo = np.lexsort((row_rel, row_dst))
-        ent_ptr = np.zeros(N + 1, dtype=np.int64)
-        np.cumsum(np.bincount(row_dst, minlength=N), out=ent_ptr[1:])
         # forward DCSR by source: edges sorted by (r, h, t); each out-edge stores the LOCAL row of its tail
         fs = np.lexsort((t, h, r))
         rf, hf, tf = r[fs], h[fs], t[fs]
@@ -260,7 +255,6 @@ class KnowledgeGraph(object):
             "dst_ptr": i32(dst_ptr), "row_dst": i32(row_dst), "row_start": i32(row_start), "edge_src": i32(hs),
             "rank_tab": np.ascontiguousarray(rank_tab.reshape(-1)),
             "ord_ptr": i32(ord_ptr), "ord_h": i32(h[order]), "ord_t": i32(t[order]),
-            "ent_ptr": i32(ent_ptr), "ent_rel": i32(row_rel[eo]), "ent_row": i32(local_row[eo]),
             "fsrc_ptr": i32(fsrc_ptr), "frow_start": i32(frow_start), "fedge_dstrow": i32(fedge_dstrow),
             "srank_tab": np.ascontiguousarray(srank_tab.reshape(-1)),
         }

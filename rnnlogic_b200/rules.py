@@ -118,15 +118,10 @@ class CompiledRules:
             t_rule, t_node, t_key = t_rule[o], t_node[o], t_key[o]
         else:
             t_key = np.zeros(0, np.int64)
-        term_ptr = np.zeros(R * R + 1, dtype=np.int64)
-        np.cumsum(np.bincount(t_key, minlength=R * R), out=term_ptr[1:])
         self.num_terms = int(t_rule.shape[0])
-        self.head_terms = term_ptr[(np.arange(R) + 1) * R] - term_ptr[np.arange(R) * R]
+        self.head_terms = np.bincount(node_head[t_node], minlength=R) if t_rule.shape[0] else np.zeros(R, np.int64)
         self.rule_node = np.full(self.num_rules, -1, dtype=np.int64)
         self.rule_node[t_rule] = t_node
-        self.rule_term = np.full(self.num_rules, -1, dtype=np.int64)        # global term index of a rule (-1: empty body)
-        self.rule_term[t_rule] = np.arange(t_rule.shape[0])
-        self.term_ptr_host = term_ptr
         node_nterm = np.bincount(t_node, minlength=max(1, self.num_nodes))
         # rules ending at a node (CSR by node) and the item capacity of a head = rows of its rule-end nodes
         o_n = np.lexsort((t_rule, t_node)) if t_rule.shape[0] else np.zeros(0, np.int64)
@@ -192,9 +187,8 @@ class CompiledRules:
             "node_rel": i32(node_rel), "node_parent": i32(node_parent),
             "node_row_off": np.ascontiguousarray(node_row_off, dtype=np.int64),
             "head_node_ptr": i32(head_node_ptr), "lvl_ptr": i32(lvl_ptr.reshape(-1)),
-            "chunk_node": i32(chunk_node), "chunk_row0": i32(chunk_row0), "term_ptr": i32(term_ptr),
-            "term_node": i32(t_node), "term_rule": i32(t_rule), "zr_ptr": i32(zr_ptr), "zr_rule": i32(zr_rule),
-            "lvl_node_ptr": i32(lvl_node_ptr.reshape(-1)), "node_chunk0": i32(cstart[:-1]), "node_nterm": i32(node_nterm),
+            "chunk_node": i32(chunk_node), "chunk_row0": i32(chunk_row0), "zr_ptr": i32(zr_ptr), "zr_rule": i32(zr_rule),
+            "node_chunk0": i32(cstart[:-1]),
             "node_rec": i32(rec.reshape(-1)), "node_prow_off": np.ascontiguousarray(node_prow_off, dtype=np.int64),
             "lvl_sym_ptr": i32(lvl_sym_ptr.reshape(-1)), "sym_node": i32(sym_node), "sym_w0": i32(sym_w0),
             "node_term_ptr": i32(node_term_ptr), "node_term_rule": i32(node_term_rule),
@@ -216,11 +210,10 @@ class DeviceRules:
         t = self.t
         self.struct = _lib.RlRules(
             cr.num_nodes, cr.num_rules, cr.max_len, cr.num_chunks, cr.num_terms,
-            t["node_rel"].data_ptr(), t["node_parent"].data_ptr(), t["node_row_off"].data_ptr(),
+            t["node_rel"].data_ptr(), t["node_row_off"].data_ptr(),
             t["head_node_ptr"].data_ptr(), t["lvl_ptr"].data_ptr(), t["chunk_node"].data_ptr(),
-            t["chunk_row0"].data_ptr(), t["term_ptr"].data_ptr(), t["term_node"].data_ptr(),
-            t["term_rule"].data_ptr(), t["zr_ptr"].data_ptr(), t["zr_rule"].data_ptr(),
-            t["lvl_node_ptr"].data_ptr(), t["node_chunk0"].data_ptr(), t["node_nterm"].data_ptr(),
+            t["chunk_row0"].data_ptr(), t["zr_ptr"].data_ptr(), t["zr_rule"].data_ptr(),
+            t["node_chunk0"].data_ptr(),
             t["node_rec"].data_ptr(), t["node_prow_off"].data_ptr(), t["lvl_sym_ptr"].data_ptr(),
             t["sym_node"].data_ptr(), t["sym_w0"].data_ptr(), t["node_term_ptr"].data_ptr(),
             t["node_term_rule"].data_ptr())
