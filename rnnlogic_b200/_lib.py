@@ -11,7 +11,7 @@ import subprocess
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
 ROOT = os.path.dirname(_HERE)
-LIB_PATH = os.path.join(_HERE, "lib", "librnnlogic_b200.so")
+LIB_PATH = os.environ.get("RNNLOGIC_B200_LIB") or os.path.join(_HERE, "lib", "librnnlogic_b200.so")   # env override: A/B builds
 SOURCES = [os.path.join(_HERE, "csrc", f) for f in ("rl_kernels.cu", "rl_plus.cu", "rl_rotate.cu", "rl_tail.cu")]
 HEADER = os.path.join(ROOT, "include", "rnnlogic_b200.h")
 

@@ -289,7 +289,7 @@ __device__ __forceinline__ uint32_t numeric_rows(const rl_graph &g, const rl_rul
 // one coalesced load, then the valid rows of all chunks of the same trie node are merged and expanded
 // 32 at a time (full tiles even when each chunk holds only a few valid rows).
 template <typename CT, bool ROOT, bool PRUNE>
-__global__ void __launch_bounds__(WARPS_PER_BLOCK * 32, 4)     // <= 64 registers: 4 blocks (32 warps) per SM
+__global__ void __launch_bounds__(WARPS_PER_BLOCK * 32, 6)     // <= 40 registers: 6 blocks (48 warps) per SM -- latency-bound, swept 4..8
 k_numeric(rl_graph g, rl_rules r, rl_slots s, int depth, rl_frontier fr, int cpw)
 {
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
