@@ -585,20 +585,20 @@ __global__ void k_group_reduce(int n_groups, const int32_t *__restrict__ group_p
                                const float *__restrict__ slot_tsum, float *__restrict__ group_loss,
                                float *__restrict__ group_tsum, float *__restrict__ slot_invT, float *__restrict__ stats)
 {
-    const int gi = blockIdx.x * blockDim.x + threadIdx.x;
+    const int gi = blockIdx.x, lane = threadIdx.x;               // one warp per group, lane = query lane
     if (gi >= n_groups) return;
     const int s0 = group_ptr ? group_ptr[gi] : gi, s1 = group_ptr ? group_ptr[gi + 1] : gi + 1;
     double L = 0.0, T = 0.0;
     for (int k = s0; k < s1; ++k) { L += (double)slot_lsum[k]; T += (double)slot_tsum[k]; }
     const float Tf = fmaxf((float)T, 1.f);
-    group_tsum[gi] = (float)T;
-    group_loss[gi] = (float)L / Tf;
+    if (lane == 0) {
+        group_tsum[gi] = (float)T;
+        group_loss[gi] = (float)L / Tf;
+    }
     for (int k = s0; k < s1; ++k) {
-        slot_invT[k] = 1.f / Tf;
-        for (int b = 0; b < 32; ++b) {                       // stats[.][3]: valid flag -> softmax-gradient coefficient
-            float *st = stats + ((size_t)k * 32 + b) * 4;
-            st[3] = st[3] != 0.f ? st[2] / st[1] / Tf : 0.f;  // S_b / sum-exp / T'
-        }
+        if (lane == 0) slot_invT[k] = 1.f / Tf;
+        float *st = stats + ((size_t)k * 32 + lane) * 4;          // stats[.][3]: valid flag -> softmax-gradient coefficient
+        st[3] = st[3] != 0.f ? st[2] / st[1] / Tf : 0.f;          // S_b / sum-exp / T'
     }
 }
 
@@ -1020,7 +1020,7 @@ int rl_softmax_ce(const rl_graph *g, const rl_slots *s, const rl_answers *ans, f
     CHECK_LAUNCH("k_softmax_partial");
     k_ce_finalize<<<S, WARPS_PER_BLOCK * 32, 0, st>>>(*g, *s, *ans, smoothing, use_mask, Z, nzmask, partial, nblk, stats, slot_lsum, slot_tsum);
     CHECK_LAUNCH("k_ce_finalize");
-    k_group_reduce<<<(n_groups + 127) / 128, 128, 0, st>>>(n_groups, group_ptr, slot_lsum, slot_tsum, group_loss, group_tsum, slot_invT, stats);
+    k_group_reduce<<<n_groups, 32, 0, st>>>(n_groups, group_ptr, slot_lsum, slot_tsum, group_loss, group_tsum, slot_invT, stats);
     CHECK_LAUNCH("k_group_reduce");
     if (G) {
         const size_t n = (size_t)N * RL_LANES;
