@@ -224,3 +224,22 @@ def test_compat_modules_resolve_the_reference_scripts_imports(monkeypatch):
             sys.path.remove(ref_src)
     for m in ("data", "predictors", "trainer", "comm", "utils", "_reference", "generators"):
         sys.modules.pop(m, None)
+
+
+def test_bench_reference_arm_contract():
+    """`bench.py --impl reference` (CPU oracle port, no GPU needed) prints ONE JSON line with the keys the
+    driver reads."""
+    import json
+    import subprocess
+    import sys
+    out = subprocess.run([sys.executable, os.path.join(G.ROOT, "bench.py"), "--impl", "reference", "--steps", "1", "--warmup", "3"],
+                         capture_output=True, text=True, timeout=900, cwd=G.ROOT)
+    assert out.returncode == 0, out.stderr[-2000:]
+    lines = [l for l in out.stdout.splitlines() if l.startswith("{")]
+    assert len(lines) == 1
+    d = json.loads(lines[0])
+    assert d["impl"] == "reference" and d["metric"] == "rule_grounded_train_queries_per_sec" and d["unit"] == "queries/s"
+    assert d["higher_is_better"] is True and d["value"] > 0 and d["vs_baseline"] is None and d["data"] == "synthetic"
+    assert d["cpu_baseline"]["kind"] == "port" and d["cpu_baseline"]["cores"] >= 1 and d["cpu_baseline"]["value"] == d["value"]
+    assert d["e2e"] == {"value": d["value"], "unit": "queries/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}
+    assert "workload" in d["config"] and "model" not in d["config"]
