@@ -233,6 +233,8 @@ def main():
     world = int(os.environ.get("WORLD_SIZE", "1"))
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))
 
+    if args.impl == "reference" and rank != 0:
+        return                                   # the CPU arm runs on rank 0 only; other ranks exit 0 without work
     shape, N, R, train, valid, test, rules = build_workload(args.shape)
     batches = make_batches(train, R, seed=1)
     workload = (shape["name"] + "-shape synthetic KG (N=%d, R=%d, E=%d train triples incl. inverses), %d synthetic rules "
@@ -240,8 +242,6 @@ def main():
                 % (N, R, train.shape[0], len(rules), shape["max_len"], args.batches))
 
     if args.impl == "reference":
-        if rank != 0:
-            return
         res = cpu_reference_run(N, R, train, valid, test, rules, batches, args.steps, args.warmup, budget_s=120.0)
         line = {"impl": "reference", "metric": METRIC, "value": res["value"], "unit": UNIT, "n_gpus": args.gpus,
                 "steps": res["steps_done"], "warmup": args.warmup, "ms_per_step": res["ms_per_step"],

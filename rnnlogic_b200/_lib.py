@@ -16,13 +16,7 @@ SOURCES = [os.path.join(_HERE, "csrc", f) for f in ("rl_kernels.cu", "rl_plus.cu
 HEADER = os.path.join(ROOT, "include", "rnnlogic_b200.h")
 
 LANES = 32
-i32p = C.POINTER(C.c_int32)
-i64p = C.POINTER(C.c_int64)
-u32p = C.POINTER(C.c_uint32)
-f32p = C.POINTER(C.c_float)
-f64p = C.POINTER(C.c_double)
-u8p = C.POINTER(C.c_uint8)
-vp = C.c_void_p
+vp = C.c_void_p          # every device pointer crosses the boundary as a plain address
 
 
 class RlGraph(C.Structure):

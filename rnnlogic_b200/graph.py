@@ -214,7 +214,6 @@ class KnowledgeGraph(object):
         row_start = np.concatenate([row_first, [E]])
         dst_ptr = np.zeros(R + 1, dtype=np.int64)
         np.cumsum(np.bincount(row_rel, minlength=R), out=dst_ptr[1:])
-        local_row = np.arange(TR) - dst_ptr[row_rel]
         # rank table {bits, rows-before-word} per (relation, 32-entity word)
         W = (N + 31) // 32
         bits = np.zeros(R * W, dtype=np.uint32)

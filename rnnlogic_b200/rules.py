@@ -106,18 +106,11 @@ class CompiledRules:
         first_node = np.searchsorted(nkey, want, side="left")
         lvl_ptr = cstart[first_node].reshape(R, L1)
         self.level_chunks = np.diff(lvl_ptr, axis=1)                  # [R, max_len] chunks per (head, depth)
-        lvl_node_ptr = first_node.reshape(R, L1)
-        self.level_nodes = np.diff(lvl_node_ptr, axis=1)              # [R, max_len] nodes per (head, depth)
+        self.level_nodes = np.diff(first_node.reshape(R, L1), axis=1)  # [R, max_len] nodes per (head, depth)
         self.head_chunks = lvl_ptr[:, -1] - lvl_ptr[:, 0]
-        # terminal lists keyed by (head, last relation)
+        # rule ends: (rule id, node) pairs of the rules with a non-empty body
         t_rule = np.array([i for i, lf in enumerate(rule_leaf) if lf is not None], dtype=np.int64)
         t_node = np.array([gid[lf[0]][lf[1]] for lf in rule_leaf if lf is not None], dtype=np.int64)
-        if t_rule.shape[0]:
-            t_key = node_head[t_node] * R + node_rel[t_node]
-            o = np.lexsort((t_rule, t_key))
-            t_rule, t_node, t_key = t_rule[o], t_node[o], t_key[o]
-        else:
-            t_key = np.zeros(0, np.int64)
         self.num_terms = int(t_rule.shape[0])
         self.head_terms = np.bincount(node_head[t_node], minlength=R) if t_rule.shape[0] else np.zeros(R, np.int64)
         self.rule_node = np.full(self.num_rules, -1, dtype=np.int64)
