@@ -68,6 +68,40 @@ def build(force: bool = False) -> str:
     return LIB_PATH
 
 
+HOST_LIB_PATH = os.path.join(_HERE, "lib", "librnnlogic_b200_host.so")
+HOST_SOURCE = os.path.join(_HERE, "csrc_host", "kg_loader.cpp")
+
+
+def build_host(force: bool = False) -> str:
+    """g++-compile the host-only helpers (dataset loader) into rnnlogic_b200/lib/."""
+    os.makedirs(os.path.dirname(HOST_LIB_PATH), exist_ok=True)
+    if force or not os.path.exists(HOST_LIB_PATH) or os.path.getmtime(HOST_SOURCE) > os.path.getmtime(HOST_LIB_PATH):
+        subprocess.check_call(["g++", "-O2", "-std=c++17", "-shared", "-fPIC", "-o", HOST_LIB_PATH, HOST_SOURCE])
+    return HOST_LIB_PATH
+
+
+_host = None
+
+
+def host_lib():
+    """Host-only native helpers (no CUDA): built on demand, g++ is part of the image."""
+    global _host
+    if _host is None:
+        L = C.CDLL(build_host())
+        L.rl_kg_load.restype = C.c_void_p
+        L.rl_kg_load.argtypes = [C.c_char_p]
+        L.rl_kg_load_error.restype = C.c_char_p
+        L.rl_kg_num_entities.restype = C.c_int64
+        L.rl_kg_num_entities.argtypes = [C.c_void_p]
+        L.rl_kg_num_relations.restype = C.c_int64
+        L.rl_kg_num_relations.argtypes = [C.c_void_p]
+        L.rl_kg_triples.restype = C.POINTER(C.c_int64)
+        L.rl_kg_triples.argtypes = [C.c_void_p, C.c_int, C.POINTER(C.c_int64)]
+        L.rl_kg_free.argtypes = [C.c_void_p]
+        _host = L
+    return _host
+
+
 _lib = None
 
 _PROTOS = {

@@ -32,6 +32,28 @@ def _answers_csr(N: int, parts: Sequence[np.ndarray]):
     return keys.astype(np.int64), ptr, pair[:, 1].astype(np.int32)
 
 
+def _load_triples_native(data_path, n_ent, n_rel):
+    """(train, valid, test) int64[E,3] id arrays through the native loader (csrc_host/kg_loader.cpp),
+    which replaces the per-line Python parse of src/data.py:43-99."""
+    import ctypes
+    H = _lib.host_lib()
+    h = H.rl_kg_load(os.fsencode(data_path))
+    if not h:
+        raise KeyError(H.rl_kg_load_error().decode(errors="replace"))
+    try:
+        if H.rl_kg_num_entities(h) != n_ent or H.rl_kg_num_relations(h) != n_rel:
+            raise ValueError("dictionary sizes disagree between the Python and the native loader")
+        out = []
+        for which in range(3):
+            cnt = ctypes.c_int64()
+            ptr = H.rl_kg_triples(h, which, ctypes.byref(cnt))
+            n = int(cnt.value)
+            out.append(np.ctypeslib.as_array(ptr, shape=(n * 3,)).copy().reshape(-1, 3) if n else np.zeros((0, 3), np.int64))
+        return out
+    finally:
+        H.rl_kg_free(h)
+
+
 class DeviceGraph:
     """Device-resident copy of the graph arrays + the C struct handed to the kernels."""
 
@@ -81,15 +103,7 @@ class KnowledgeGraph(object):
                     self.id2relation[int(i)] = name
             self.entity_size = len(self.entity2id)
             self.relation_size = len(self.relation2id)
-            splits = []
-            for name in ("train", "valid", "test"):
-                rows = []
-                with open(os.path.join(data_path, name + ".txt")) as fi:
-                    for line in fi:
-                        h, r, t = line.strip().split("\t")
-                        rows.append((self.entity2id[h], self.relation2id[r], self.entity2id[t]))
-                splits.append(np.array(rows, dtype=np.int64).reshape(-1, 3))
-            train, valid, test = splits
+            train, valid, test = _load_triples_native(data_path, self.entity_size, self.relation_size)
         else:
             self.entity_size = int(entity_size)
             self.relation_size = int(relation_size)

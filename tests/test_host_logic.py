@@ -243,3 +243,44 @@ def test_bench_reference_arm_contract():
     assert d["cpu_baseline"]["kind"] == "port" and d["cpu_baseline"]["cores"] >= 1 and d["cpu_baseline"]["value"] == d["value"]
     assert d["e2e"] == {"value": d["value"], "unit": "queries/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}
     assert "workload" in d["config"] and "model" not in d["config"]
+
+
+def test_native_dataset_loader(tmp_path):
+    """csrc_host/kg_loader.cpp == the reference's text parse (data.py:18-47,73-99): same ids, KeyError on
+    an unknown name, names with spaces, blank lines and CRLF tolerated like line.strip()."""
+    import time
+    from rnnlogic_b200 import KnowledgeGraph
+    fx = G.load("syn")
+    N, R = int(fx["N"]), int(fx["R"])
+    d = tmp_path / "ds"
+    d.mkdir()
+    (d / "entities.dict").write_text("".join("%d\tent %d\n" % (i, i) for i in range(N)))          # names with a space
+    (d / "relations.dict").write_text("".join("%d\t!rel/%d\r\n" % (i, i) for i in range(R)))        # CRLF
+    for split in ("train", "valid", "test"):
+        body = "".join("ent %d\t!rel/%d\tent %d\n" % tuple(x) for x in fx[split].tolist())
+        (d / (split + ".txt")).write_text(body + ("\n" if split == "valid" else ""))
+    kg = KnowledgeGraph(str(d))
+    assert kg.entity_size == N and kg.relation_size == R
+    for split in ("train", "valid", "test"):
+        assert np.array_equal(getattr(kg, split + "_array"), fx[split].astype(np.int64))
+    assert kg.train_facts[0] == tuple(fx["train"][0].tolist()) and kg.entity2id["ent 3"] == 3
+    (d / "test.txt").write_text("ent 1\t!rel/0\tnobody\n")
+    with pytest.raises(KeyError):
+        KnowledgeGraph(str(d))
+    # FB15k-237-sized file: the parse itself takes a fraction of a second
+    big = tmp_path / "big"
+    big.mkdir()
+    rng = np.random.default_rng(0)
+    tri = np.stack([rng.integers(14541, size=544230), rng.integers(474, size=544230), rng.integers(14541, size=544230)], 1)
+    (big / "entities.dict").write_text("".join("%d\t/m/%06d\n" % (i, i) for i in range(14541)))
+    (big / "relations.dict").write_text("".join("%d\t/rel/%d\n" % (i, i) for i in range(474)))
+    text = "".join("/m/%06d\t/rel/%d\t/m/%06d\n" % (h, r, t) for h, r, t in tri.tolist())
+    (big / "train.txt").write_text(text)
+    (big / "valid.txt").write_text("")
+    (big / "test.txt").write_text("")
+    from rnnlogic_b200.graph import _load_triples_native
+    t0 = time.perf_counter()
+    train, valid, test = _load_triples_native(str(big), 14541, 474)
+    dt = time.perf_counter() - t0
+    assert np.array_equal(train, tri) and valid.shape == (0, 3)
+    assert dt < 5.0, dt
