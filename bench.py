@@ -271,7 +271,8 @@ def main():
     with torch.no_grad():
         model.rule_weights.copy_(torch.randn(model.num_rules, generator=g) * 0.1)
     model = model.cuda(dev)
-    opt = torch.optim.Adam(model.parameters(), lr=0.005, fused=True)     # torch's single-kernel Adam
+    from rnnlogic_b200.optim import Adam
+    opt = Adam(model.parameters(), lr=0.005)          # torch.optim.Adam semantics, one element per thread (rl_adam_step)
     sk = model._driver(dev)
     cr = model.compiled
 

@@ -300,6 +300,12 @@ int rl_rotate_backward(const rl_graph *g, const rl_slots *s, int32_t D, float ga
                        const float *remb, const float *P, const float *G, float *dP, float *d_eemb,
                        float *d_remb, void *stream);
 
+/* One Adam step with torch.optim.Adam's arithmetic (run_predictorplus.py:51; weight_decay is L2, i.e.
+ * added to the gradient); step is the 1-based step count.  Optional: the trainer keeps working with any
+ * torch optimizer, this is what rnnlogic_b200.optim.Adam launches. */
+int rl_adam_step(int64_t n, float *param, const float *grad, float *exp_avg, float *exp_avg_sq, float lr,
+                 float beta1, float beta2, float eps, float weight_decay, int64_t step, void *stream);
+
 /* Entity-major <-> reference layout: out[b][e] = Z[slot][e][b] for b < nq (fp32 [nq][N]). */
 int rl_slot_to_dense(int32_t N, int32_t nq, const float *Z_slot, float *out, int64_t out_stride,
                      void *stream);

@@ -159,3 +159,20 @@ def test_dense_rank_kernel_matches_oracle():
     want = O.filtered_rank(logits, flag, mask, t)
     got = dense_filtered_rank(logits.cuda(), flag.cuda(), mask.cuda(), t.cuda()).cpu().numpy()
     assert np.array_equal(got, want)
+
+
+def test_adam_kernel_matches_torch():
+    from rnnlogic_b200.optim import Adam
+    g = torch.Generator().manual_seed(0)
+    for wd in (0.0, 0.01):
+        a = [torch.randn(1000, generator=g).cuda().requires_grad_(), torch.randn(7, 13, generator=g).cuda().requires_grad_()]
+        b = [x.detach().clone().requires_grad_() for x in a]
+        oa, ob = Adam(a, lr=0.005, weight_decay=wd), torch.optim.Adam(b, lr=0.005, weight_decay=wd)
+        for step in range(25):
+            for x, y in zip(a, b):
+                gr = torch.randn(x.shape, generator=g).cuda() * (0.1 if step % 3 else 10.0)
+                x.grad, y.grad = gr.clone(), gr.clone()
+            oa.step()
+            ob.step()
+        for x, y in zip(a, b):
+            np.testing.assert_allclose(x.detach().cpu().numpy(), y.detach().cpu().numpy(), rtol=2e-6, atol=2e-7)
