@@ -450,7 +450,7 @@ def main():
         nxt = model.submit_train_step(step_lists[s + 1], 0.2, grad_scale=1.0 / per) if s + 1 < n_steps else None
         loss, tsum = ticket.result()
         assert torch.isfinite(loss).all()
-        h2d += ticket.h2d_bytes + 8 * (5 * len(step_lists[s]) + 1)
+        h2d += ticket.h2d_bytes
         d2h += ticket.d2h_bytes
         ticket = nxt
     e1.record()

@@ -118,10 +118,13 @@ typedef struct rl_frontier {
     int32_t *node_cnt;     /* valid rows per (slot, node) */
     int32_t *overflow;     /* set to 1 when a 32-bit count overflowed */
     /* Item list (may be all NULL when only rl_expand_level / rl_node_counts_dense are used): one
-     * int32x4 record {row (slot-relative), node, entity, -} per NON-ZERO row of every rule-end node,
+     * int32x4 record {row (slot-relative), t0, entity, n} per NON-ZERO row of every rule-end node
+     * (the rules ending at that node are node_term_rule[t0 .. t0+n)),
      * appended by k_numeric; slot s owns [item_off[s], item_off[s+1]) (capacity = rows of its head's
-     * rule-end nodes, so it cannot overflow).  item_cnt[S], bucket_cnt[S*rank_words] zeroed by the
-     * caller; items_sorted / bucket_off[S*(rank_words+1)] are scratch of rl_predictor_scores. */
+     * rule-end nodes, so it cannot overflow).  item_cnt[S] and bucket_cnt[S*B] (per-entity item counts,
+     * B = rank_words*32 + 32 ints per slot, 16-byte aligned) zeroed by the caller; items_sorted /
+     * bucket_off[S*B] are filled by rl_sort_items: the items of entity e of a slot are
+     * items_sorted[item_off + bucket_off[e] .. bucket_off[e+1]). */
     int32_t *items;        /* as int32x4, 16-byte aligned */
     int32_t *items_sorted;
     const int64_t *item_off;
@@ -149,11 +152,14 @@ int rl_device_count(void);
 
 /* Fill lane_h / lane_t / lane_eh / lane_et from the reference's batch tensors
  * (all_h, all_t, edges_to_remove int64[Q] on the device; trainer.py:69-82).  Query i of slot s
- * is q_off[s] + lane (q_off is a DEVICE int32[S+1]).  all_t / edges_to_remove may be NULL. */
+ * is q_off[s] + lane (q_off is a DEVICE int32[S+1]).  all_t / edges_to_remove may be NULL.
+ * remove_query_edges != 0 with edges_to_remove == NULL: the removed edge of a query is its own
+ * triple (h, head, t) when that is a train edge -- what TrainDataset builds by looking the
+ * triple's index up (src/data.py:214-216) -- found on the device, no host look-up. */
 int rl_prepare_slots(const rl_graph *g, int32_t num_slots, const int32_t *slot_head,
                      const int32_t *q_off, const int64_t *all_h, const int64_t *all_t,
-                     const int64_t *edges_to_remove, int32_t *lane_h, int32_t *lane_t,
-                     int32_t *lane_eh, int32_t *lane_et, void *stream);
+                     const int64_t *edges_to_remove, int32_t remove_query_edges, int32_t *lane_h,
+                     int32_t *lane_t, int32_t *lane_eh, int32_t *lane_et, void *stream);
 
 /* Kernel (1): frontier expansion of one trie depth for every slot, replaces
  * KnowledgeGraph.propagate (src/data.py:149-173) for all rules of the head at once.  Two
@@ -180,10 +186,14 @@ int rl_node_counts_dense(const rl_graph *g, const rl_rules *r, const rl_slots *s
 /* Kernel (2a): rule-weight aggregation, replaces the loop of Predictor.forward
  * (src/predictors.py:58-65,73-78).  Z[S][N][32] fp32 = sum_rule w_rule * fp32(count) (+ bias[e]
  * when bias != NULL).  nzmask[S][N]: bit b set <=> sum_rule count[e][b] != 0.  With
- * fill_neg_inf != 0 cells with a clear bit get -inf (entity_feature != 'bias'). */
+ * fill_neg_inf != 0 cells with a clear bit get -inf (entity_feature != 'bias').
+ * softmax_partial (may be NULL): S * rl_softmax_blocks(N) * 64 floats; when given, the kernel also
+ * leaves the per-block (max, sum-exp) of every query there, which rl_predictor_ce_backward accepts
+ * (partial_ready != 0) instead of sweeping Z once more. */
 int rl_predictor_scores(const rl_graph *g, const rl_rules *r, const rl_slots *s,
                         const rl_frontier *fr, const float *rule_weights, const float *bias,
-                        int32_t fill_neg_inf, float *Z, uint32_t *nzmask, void *stream);
+                        int32_t fill_neg_inf, float *Z, uint32_t *nzmask, float *softmax_partial,
+                        void *stream);
 
 /* Kernel (2b): log(softmax + 1e-8) cross-entropy against the smoothed target, replaces
  * src/trainer.py:84,88-89, fused with its backward.  target = smoothing * multi_hot(train
@@ -206,6 +216,21 @@ int rl_softmax_ce(const rl_graph *g, const rl_slots *s, const rl_answers *train_
 int rl_predictor_backward(const rl_graph *g, const rl_rules *r, const rl_slots *s,
                           const rl_frontier *fr, const float *G, const float *slot_scale,
                           float *grad_w, float *grad_bias, void *stream);
+
+/* Kernels (2b)+(2c) in one call for Predictor's train step (src/trainer.py:84,88-90 + autograd
+ * through src/predictors.py:64,74): same loss outputs and scratch as rl_softmax_ce, then the
+ * backward with the passes fused (softmax gradient + bias gradient in one sweep over Z, target
+ * terms pushed into G and grad_bias together, item walk over the entity-grouped list).
+ * partial_ready != 0: `partial` was filled by rl_predictor_scores.  G[S][N][32] is scratch.
+ * grad_w[num_rules], grad_bias[N] (may be NULL) are ACCUMULATED into:
+ * += sum_groups slot_scale * d group_loss / d param. */
+int rl_predictor_ce_backward(const rl_graph *g, const rl_rules *r, const rl_slots *s,
+                             const rl_frontier *fr, const rl_answers *train_answers, float smoothing,
+                             int32_t use_mask, const float *Z, const uint32_t *nzmask, int32_t n_groups,
+                             const int32_t *group_ptr, float *partial, int32_t partial_ready,
+                             float *stats, float *slot_sums, float *group_loss, float *group_tsum,
+                             float *G, const float *slot_scale, float *grad_w, float *grad_bias,
+                             void *stream);
 
 /* Kernel (3): filtered rank bounds, replaces src/trainer.py:189-201.  LH[S*32][2] int64:
  * L = #{e not known: z_e > z_t} + 1, H = #{e not known: z_e >= z_t} + 2; (1, N+1) when the

@@ -109,14 +109,17 @@ _PROTOS = {
     "rl_last_error": (C.c_char_p, []),
     "rl_device_count": (C.c_int, []),
     "rl_launch_count": (C.c_longlong, []),
-    "rl_prepare_slots": (C.c_int, [C.POINTER(RlGraph), C.c_int32, vp, vp, vp, vp, vp, vp, vp, vp, vp, vp]),
+    "rl_prepare_slots": (C.c_int, [C.POINTER(RlGraph), C.c_int32, vp, vp, vp, vp, vp, C.c_int32, vp, vp, vp, vp, vp]),
     "rl_expand_level": (C.c_int, [C.POINTER(RlGraph), C.POINTER(RlRules), C.POINTER(RlSlots), C.c_int32,
                                   C.c_int32, C.c_int32, C.POINTER(RlFrontier), C.c_int32, C.c_int32, C.c_int32, vp]),
     "rl_sort_items": (C.c_int, [C.POINTER(RlGraph), C.POINTER(RlSlots), C.POINTER(RlFrontier), vp]),
     "rl_node_counts_dense": (C.c_int, [C.POINTER(RlGraph), C.POINTER(RlRules), C.POINTER(RlSlots), C.c_int32,
                                        C.c_int32, C.POINTER(RlFrontier), vp, vp]),
     "rl_predictor_scores": (C.c_int, [C.POINTER(RlGraph), C.POINTER(RlRules), C.POINTER(RlSlots),
-                                      C.POINTER(RlFrontier), vp, vp, C.c_int32, vp, vp, vp]),
+                                      C.POINTER(RlFrontier), vp, vp, C.c_int32, vp, vp, vp, vp]),
+    "rl_predictor_ce_backward": (C.c_int, [C.POINTER(RlGraph), C.POINTER(RlRules), C.POINTER(RlSlots),
+                                           C.POINTER(RlFrontier), C.POINTER(RlAnswers), C.c_float, C.c_int32, vp, vp,
+                                           C.c_int32, vp, vp, C.c_int32, vp, vp, vp, vp, vp, vp, vp, vp, vp]),
     "rl_softmax_blocks": (C.c_int, [C.c_int32]),
     "rl_softmax_ce": (C.c_int, [C.POINTER(RlGraph), C.POINTER(RlSlots), C.POINTER(RlAnswers), C.c_float,
                                 C.c_int32, vp, vp, C.c_int32, vp, vp, vp, vp, vp, vp, vp, vp]),

@@ -10,6 +10,14 @@
 #define FULL 0xffffffffu
 #define WARPS_PER_BLOCK 8
 #define SM_ROWS_PER_BLOCK 512   // entity rows per block in the softmax / rank sweeps
+#define SCORE_WARPS_MAX 8         // k_predictor_scores: warps (= entity words) per block, one softmax partial per block
+#ifndef SCORE_MIN_BLOCKS
+#define SCORE_MIN_BLOCKS 4      // 64 registers, no spills: swept 3..8 x 2..8 rows on the B200
+#endif
+#ifndef SCORE_ROWS
+#define SCORE_ROWS 4            // count rows a k_predictor_scores warp keeps in flight (8 spills at 64 registers)
+#endif
+#define CE_WARPS 32             // k_ce_finalize / k_grad_sparse: one warp per query lane of the slot
 
 // error state + launch counter live in rl_kernels.cu
 int rl_fail(int code, const char *what, cudaError_t e = cudaSuccess);
@@ -41,6 +49,12 @@ __device__ __forceinline__ float warp_sumf(float v)
     for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(FULL, v, o);
     return v;
 }
+__device__ __forceinline__ float warp_maxf(float v)
+{
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v = fmaxf(v, __shfl_xor_sync(FULL, v, o));
+    return v;
+}
 __device__ __forceinline__ int warp_sumi(int v)
 {
 #pragma unroll
@@ -65,60 +79,74 @@ __device__ __forceinline__ bool row_valid(const int32_t *__restrict__ node_chunk
 }
 
 // ---- item list helpers -------------------------------------------------------------------------
-// k_numeric appends one item {row (slot-relative), node, entity, -} per NON-ZERO row of every rule-end
-// node; k_items_sort buckets a slot's items by entity word.  A warp that owns the 32 entities of a word
-// loads its bucket once (first 32 items stay in registers) and walks the items of one entity at a time.
+// k_numeric appends one item {row (slot-relative), t0, entity, n} per NON-ZERO row of every rule-end node
+// (the rules ending there are node_term_rule[t0 .. t0 + n)) and counts it in bucket_cnt[slot][entity]; rl_sort_items (k_items_scan + k_items_scatter) turns the
+// counts into offsets and groups a slot's items by entity, so the items of entity e are the contiguous
+// range [bucket_off[e], bucket_off[e+1]) of items_sorted.  Both tables have RL_BUCKET_STRIDE ints per slot.
+#define RL_BUCKET_STRIDE(W) ((size_t)(W) * 32 + 32)
+
 struct WordItems {
-    const int4 *its;      // the word's bucket inside items_sorted
-    int n;                // items in the bucket
-    int4 it0;             // lane's item of the first 32 (z = -1: none)
+    const int4 *its;      // the slot's items, grouped by entity
+    int b0, b1;           // item range of the lane's entity (entity = word * 32 + lane)
+    int wbase, wend;      // window: lane holds item wbase + lane (the word's items are one contiguous range ending at wend)
+    int4 win;
     uint32_t present;     // entities of the word that own at least one item
 };
+
+__device__ __forceinline__ void word_items_window(WordItems &wi, int at)
+{
+    const int lane = threadIdx.x & 31;
+    wi.wbase = at;
+    wi.win = at + lane < wi.wend ? __ldg(wi.its + at + lane) : make_int4(0, 0, -1, 0);
+}
 
 __device__ __forceinline__ WordItems load_word_items(const rl_frontier &fr, const rl_slots &s, int W, int slot, int ew)
 {
     const int lane = threadIdx.x & 31;
     WordItems wi;
-    const int *off = fr.bucket_off + (size_t)slot * (W + 1);
-    const int b0 = off[ew];
-    wi.n = off[ew + 1] - b0;
-    wi.its = reinterpret_cast<const int4 *>(fr.items_sorted) + fr.item_off[slot] + b0;
-    wi.present = 0u;
-    wi.it0 = make_int4(0, 0, -1, 0);
-    for (int c0 = 0; c0 < wi.n; c0 += 32) {
-        const int4 it = c0 + lane < wi.n ? wi.its[c0 + lane] : make_int4(0, 0, -1, 0);
-        if (c0 == 0) wi.it0 = it;
-        wi.present |= __reduce_or_sync(FULL, it.z >= 0 ? 1u << (it.z & 31) : 0u);
-    }
+    const int *off = fr.bucket_off + (size_t)slot * RL_BUCKET_STRIDE(W) + (size_t)ew * 32;
+    wi.b0 = off[lane];                                       // padding entities of the last word: empty ranges
+    wi.b1 = off[lane + 1];
+    wi.its = reinterpret_cast<const int4 *>(fr.items_sorted) + fr.item_off[slot];
+    wi.present = __ballot_sync(FULL, wi.b1 > wi.b0);
+    wi.wend = __shfl_sync(FULL, wi.b1, 31);
+    word_items_window(wi, __shfl_sync(FULL, wi.b0, 0));      // most words fit one window: one item load per word
     return wi;
 }
 
 // f(count_of_this_lane, t) for every (item of entity i of the word, rule t ending at the item's node);
 // t indexes rl_rules::node_term_rule.  Called by all 32 lanes (lane = query), four row loads in flight.
-template <typename CT, typename F>
-__device__ __forceinline__ void for_entity_items(const WordItems &wi, const rl_rules &r, const CT *__restrict__ arena_slot,
+// Entities are normally visited in ascending order, so the 32-item window only moves forward.
+#ifndef ITEM_ROWS_IN_FLIGHT
+#define ITEM_ROWS_IN_FLIGHT 4
+#endif
+template <typename CT, typename F, int U = ITEM_ROWS_IN_FLIGHT>
+__device__ __forceinline__ void for_entity_items(WordItems &wi, const rl_rules &r, const CT *__restrict__ arena_slot,
                                                  int i, F f)
 {
     const int lane = threadIdx.x & 31;
-    for (int c0 = 0; c0 < wi.n; c0 += 32) {
-        const int4 it = c0 == 0 ? wi.it0 : (c0 + lane < wi.n ? wi.its[c0 + lane] : make_int4(0, 0, -1, 0));
-        uint32_t sel = __ballot_sync(FULL, it.z >= 0 && (it.z & 31) == i);
-        while (sel) {
-            CT cv[4];
-            int nv[4];
+    const int i0 = __shfl_sync(FULL, wi.b0, i), i1 = __shfl_sync(FULL, wi.b1, i);
+    int j = i0;
+    while (j < i1) {
+        if (j < wi.wbase || j >= wi.wbase + 32) word_items_window(wi, j);
+        const int cnt = min(i1, wi.wbase + 32) - j;          // items of this entity inside the window, from j on
+        for (int j0 = 0; j0 < cnt; j0 += U) {
+            CT cv[U];
+            int tv[U], nv[U];
 #pragma unroll
-            for (int u = 0; u < 4; ++u) {
-                const int j = sel ? __ffs(sel) - 1 : -1;
-                sel &= sel - 1;
-                const int a = __shfl_sync(FULL, it.x, j & 31);
-                nv[u] = j >= 0 ? __shfl_sync(FULL, it.y, j & 31) : -1;
-                cv[u] = j >= 0 ? arena_slot[(size_t)a * RL_LANES + lane] : (CT)0;
+            for (int u = 0; u < U; ++u) {
+                const int src = (j - wi.wbase + j0 + u) & 31;
+                const int a = __shfl_sync(FULL, wi.win.x, src);
+                const int t0 = __shfl_sync(FULL, wi.win.y, src);
+                const int nt = __shfl_sync(FULL, wi.win.w, src);
+                tv[u] = t0;
+                nv[u] = j0 + u < cnt ? nt : 0;
+                cv[u] = j0 + u < cnt ? arena_slot[(size_t)a * RL_LANES + lane] : (CT)0;
             }
 #pragma unroll
-            for (int u = 0; u < 4; ++u) {
-                if (nv[u] < 0) continue;
-                for (int t = r.node_term_ptr[nv[u]]; t < r.node_term_ptr[nv[u] + 1]; ++t) f(cv[u], t);
-            }
+            for (int u = 0; u < U; ++u)
+                for (int t = tv[u]; t < tv[u] + nv[u]; ++t) f(cv[u], t);
         }
+        j += cnt;
     }
 }

@@ -25,7 +25,7 @@ static int fail(int code, const char *what, cudaError_t e = cudaSuccess) { retur
 // ------------------------------------------------------------------------------------------
 __global__ void k_prepare_slots(rl_graph g, int S, const int32_t *__restrict__ slot_head,
                                 const int32_t *__restrict__ q_off, const int64_t *__restrict__ all_h,
-                                const int64_t *__restrict__ all_t, const int64_t *__restrict__ etr,
+                                const int64_t *__restrict__ all_t, const int64_t *__restrict__ etr, int remove_query_edges,
                                 int32_t *lane_h, int32_t *lane_t, int32_t *lane_eh, int32_t *lane_et)
 {
     int i = blockIdx.x * blockDim.x + threadIdx.x;
@@ -39,13 +39,21 @@ __global__ void k_prepare_slots(rl_graph g, int S, const int32_t *__restrict__ s
     lane_h[i] = (int32_t)hv;
     lane_t[i] = (int32_t)tv;
     int eh = -1, et = -1;
+    const int rel = slot_head[s];
     if (valid && etr) {
-        int rel = slot_head[s];
         int64_t k = etr[qi];
         int64_t n = g.ord_ptr[rel + 1] - g.ord_ptr[rel];
         if (k >= 0 && k < n) {
             eh = g.ord_h[g.ord_ptr[rel] + k];
             et = g.ord_t[g.ord_ptr[rel] + k];
+        }
+    } else if (valid && remove_query_edges && hv >= 0 && tv >= 0) {
+        // the query's own triple (h, head, t), when it is a train edge (data.py:214-216 looks its index up)
+        const int row = rank_row(g, rel, (int)tv);
+        if (row >= 0) {
+            const long long grow = g.dst_ptr[rel] + row;
+            for (long long k = g.row_start[grow]; k < g.row_start[grow + 1]; ++k)
+                if (g.edge_src[k] == (int)hv) { eh = (int)hv; et = (int)tv; break; }
         }
     }
     lane_eh[i] = eh;
@@ -271,14 +279,15 @@ __device__ __forceinline__ uint32_t numeric_rows(const rl_graph &g, const rl_rul
     if (cur >= 0) flush(cur);
     if (nterm > 0 && nzrows) {
         const bool mine = (nzrows >> lane) & 1u;
-        if (fr.items) {                                      // (row, node, entity) items for the aggregation / backward
+        if (fr.items) {                                      // {row, first rule end, entity, rule ends} items for the aggregation / backward
+            const int term0 = __ldg(r.node_term_ptr + v);
             int base = 0;
             if (lane == 0) base = atomicAdd(fr.item_cnt + slot, __popc(nzrows));
             base = __shfl_sync(FULL, base, 0);
             if (mine) {
                 const long long pos = fr.item_off[slot] + base + __popc(nzrows & ((1u << lane) - 1u));
-                reinterpret_cast<int4 *>(fr.items)[pos] = make_int4((int)(r.node_row_off[v] + myrow), v, my_dst, 0);
-                atomicAdd(fr.bucket_cnt + (size_t)slot * g.rank_words + (my_dst >> 5), 1);
+                reinterpret_cast<int4 *>(fr.items)[pos] = make_int4((int)(r.node_row_off[v] + myrow), term0, my_dst, nterm);
+                atomicAdd(fr.bucket_cnt + (size_t)slot * RL_BUCKET_STRIDE(g.rank_words) + my_dst, 1);
             }
         }
     }
@@ -375,56 +384,107 @@ __global__ void k_node_dense(rl_graph g, rl_rules r, rl_slots s, int slot, int n
 
 // ------------------------------------------------------------------------------------------
 // kernel (2a): rule-weight aggregation from the item list.  k_numeric appended one item
-// {row, node, entity} per NON-ZERO row of every rule-end node (exactly the rows that contribute).
+// {row, first rule end, entity, rule ends} per NON-ZERO row of every rule-end node (exactly the rows that
+// contribute; the rules ending at the node are node_term_rule[first .. first + n)).
 // k_items_sort buckets the items of a slot by entity word (counting sort); k_predictor_scores then
 // gives one warp the 32 entities of a word: default rows (bias / -inf, empty-body rules) for entities
 // without items, and for the others an fp64 accumulation of fp32(count) * w over their items.
 // No table walk: work is proportional to the non-zero terminal rows.
 // ------------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(512)
-k_items_sort(int W, rl_frontier fr)
+k_items_scan(int W, rl_frontier fr)
 {
-    __shared__ int part[512];
-    const int slot = blockIdx.x, tid = threadIdx.x;
-    int *cnt = fr.bucket_cnt + (size_t)slot * W;
-    int *off = fr.bucket_off + (size_t)slot * (W + 1);
-    const int per = (W + 511) / 512;
-    const int w0 = tid * per, w1 = min(W, w0 + per);
-    int sum = 0;
-    for (int w = w0; w < w1; ++w) sum += cnt[w];
-    part[tid] = sum;
-    __syncthreads();
-    for (int o = 1; o < 512; o <<= 1) {                          // inclusive scan of the per-thread sums
-        const int v = tid >= o ? part[tid - o] : 0;
+    // exclusive scan of the slot's per-entity item counts; one thread owns the 32 entities of a word (8 x int4)
+    __shared__ int wsum[16];
+    const int slot = blockIdx.x, tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    int4 *cnt4 = reinterpret_cast<int4 *>(fr.bucket_cnt + (size_t)slot * RL_BUCKET_STRIDE(W));
+    int4 *off4 = reinterpret_cast<int4 *>(fr.bucket_off + (size_t)slot * RL_BUCKET_STRIDE(W));
+    int carry = 0;
+    for (int w0 = 0; w0 < W; w0 += 512) {
+        const int w = w0 + tid;
+        int4 c[8];
+        int sum = 0;
+        if (w < W) {
+#pragma unroll
+            for (int k = 0; k < 8; ++k) {
+                c[k] = cnt4[(size_t)w * 8 + k];
+                sum += (c[k].x + c[k].y) + (c[k].z + c[k].w);
+            }
+        }
+        int incl = sum;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) {
+            const int v = __shfl_up_sync(FULL, incl, o);
+            if (lane >= o) incl += v;
+        }
+        if (lane == 31) wsum[warp] = incl;
         __syncthreads();
-        part[tid] += v;
+        int wbase = 0, total = 0;
+#pragma unroll
+        for (int k = 0; k < 16; ++k) {
+            const int v = wsum[k];
+            if (k < warp) wbase += v;
+            total += v;
+        }
+        int run = carry + wbase + incl - sum;
+        if (w < W) {
+#pragma unroll
+            for (int k = 0; k < 8; ++k) {
+                int4 o;
+                o.x = run; run += c[k].x;
+                o.y = run; run += c[k].y;
+                o.z = run; run += c[k].z;
+                o.w = run; run += c[k].w;
+                off4[(size_t)w * 8 + k] = o;
+                cnt4[(size_t)w * 8 + k] = make_int4(0, 0, 0, 0);      // becomes the scatter cursor
+            }
+        }
+        carry += total;
         __syncthreads();
     }
-    int run = part[tid] - sum;
-    for (int w = w0; w < w1; ++w) { off[w] = run; run += cnt[w]; cnt[w] = 0; }
-    if (tid == 511) off[W] = part[511];
-    __syncthreads();
+    if (tid == 0) fr.bucket_off[(size_t)slot * RL_BUCKET_STRIDE(W) + (size_t)W * 32] = carry;
+}
+
+#define SCATTER_BLOCKS 8
+__global__ void __launch_bounds__(256)
+k_items_scatter(int W, rl_frontier fr)
+{
+    const int slot = blockIdx.y;
+    int *cnt = fr.bucket_cnt + (size_t)slot * RL_BUCKET_STRIDE(W);
+    const int *off = fr.bucket_off + (size_t)slot * RL_BUCKET_STRIDE(W);
     const int n = fr.item_cnt[slot];
     const int4 *in = reinterpret_cast<const int4 *>(fr.items) + fr.item_off[slot];
     int4 *out = reinterpret_cast<int4 *>(fr.items_sorted) + fr.item_off[slot];
-    for (int i = tid; i < n; i += 512) {
+    for (int i = blockIdx.x * 256 + threadIdx.x; i < n; i += SCATTER_BLOCKS * 256) {
         const int4 it = in[i];
-        const int bkt = it.z >> 5;
-        out[off[bkt] + atomicAdd(cnt + bkt, 1)] = it;            // cnt ends as the bucket sizes again
+        out[off[it.z] + atomicAdd(cnt + it.z, 1)] = it;           // cnt ends as the per-entity item counts again
     }
 }
 
+static int launch_items_sort(const rl_graph *g, const rl_slots *s, const rl_frontier *fr, cudaStream_t st)
+{
+    k_items_scan<<<s->num_slots, 512, 0, st>>>(g->rank_words, *fr);
+    CHECK_LAUNCH("k_items_scan");
+    k_items_scatter<<<dim3(SCATTER_BLOCKS, s->num_slots), 256, 0, st>>>(g->rank_words, *fr);
+    CHECK_LAUNCH("k_items_scatter");
+    return RL_OK;
+}
+
 template <typename CT>
-__global__ void __launch_bounds__(WARPS_PER_BLOCK * 32)
+__global__ void __launch_bounds__(SCORE_WARPS_MAX * 32, SCORE_MIN_BLOCKS)       
 k_predictor_scores(rl_graph g, rl_rules r, rl_slots s, rl_frontier fr, const float *__restrict__ w,
                    const float *__restrict__ bias, int fill_neg_inf, float *__restrict__ Z,
-                   uint32_t *__restrict__ nzmask)
+                   uint32_t *__restrict__ nzmask, float *__restrict__ partial)
 {
-    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    __shared__ float sm_m[SCORE_WARPS_MAX][32];
+    __shared__ double sm_s[SCORE_WARPS_MAX][32];
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nwarps = blockDim.x >> 5;
     const int slot = blockIdx.y;
-    const int ew = blockIdx.x * WARPS_PER_BLOCK + warp;           // entity word
+    const int ew = blockIdx.x * nwarps + warp;                    // entity word
     const int N = g.num_entities, W = g.rank_words;
-    if (ew >= W) return;
+    float run_m = -INFINITY;                                      // online softmax of the lane's query over the warp's rows
+    double run_s = 0.0;
+    if (ew < W) {
     const int q = s.slot_head[slot];
     const CT *arena = reinterpret_cast<const CT *>(fr.arena) + (size_t)s.arena_off[slot] * RL_LANES;
     const int h = s.lane_h[slot * RL_LANES + lane];
@@ -434,29 +494,102 @@ k_predictor_scores(rl_graph g, rl_rules r, rl_slots s, rl_frontier fr, const flo
     float *Zs = Z + (size_t)slot * N * RL_LANES;
     uint32_t *ms = nzmask + (size_t)slot * N;
     const int e1 = min(32, N - ew * 32);
-    auto finish = [&](int e, double acc, bool any) {              // one logit row (all lanes) + its nzmask word
+    const float bias_l = (bias && lane < e1) ? bias[ew * 32 + lane] : 0.f;      // lane i: bias of entity i of the word
+    uint32_t my_bits = 0u;                                                       // lane i: nzmask word of entity i
+    auto finish = [&](int i, double acc, bool any) {              // one logit row (all lanes) + its nzmask word
+        const int e = ew * 32 + i;
         if (z1 > z0 && h == e) { acc += zsum; any = true; }       // empty-body rules: count = one_hot(h)
-        float z = (float)acc;
-        if (bias) z += bias[e];
+        float z = (float)acc + __shfl_sync(FULL, bias_l, i);
         if (fill_neg_inf && !any) z = -INFINITY;
         Zs[(size_t)e * RL_LANES + lane] = z;
         const uint32_t bits = __ballot_sync(FULL, any);
-        if (lane == 0) ms[e] = bits;
+        if (lane == i) my_bits = bits;
+        if (partial && z != -INFINITY) {
+            if (z > run_m) { run_s = run_s * (double)expf(run_m - z) + 1.0; run_m = z; }
+            else run_s += (double)expf(z - run_m);
+        }
     };
     WordItems wi = load_word_items(fr, s, W, slot, ew);
-    for (int i = 0; i < e1; ++i)
-        if (!((wi.present >> i) & 1u)) finish(ew * 32 + i, 0.0, false);
-    uint32_t present = wi.present;
-    while (present) {
-        const int i = __ffs(present) - 1;
-        present &= present - 1;
+    // Entities without items have the same logit for every query (bias[e], or -inf): their rows are plain
+    // broadcast stores and their softmax share is one warp reduction -- unless a query's head sits there
+    // and the head relation has empty-body rules, then the entity takes the general path.
+    uint32_t slow = wi.present;
+    if (z1 > z0) slow |= __reduce_or_sync(FULL, (h >= 0 && (h >> 5) == ew) ? 1u << (h & 31) : 0u);
+    const uint32_t fast = ~slow & (e1 == 32 ? FULL : (1u << e1) - 1u);
+    const float zdef = fill_neg_inf ? -INFINITY : bias_l;
+    for (uint32_t todo = fast; todo; todo &= todo - 1) {
+        const int i = __ffs(todo) - 1;
+        Zs[(size_t)(ew * 32 + i) * RL_LANES + lane] = __shfl_sync(FULL, zdef, i);
+    }
+    if (partial && !fill_neg_inf && fast) {
+        const bool mine = (fast >> lane) & 1u;
+        run_m = warp_maxf(mine ? bias_l : -INFINITY);
+        run_s = (double)warp_sumf(mine ? expf(bias_l - run_m) : 0.f);
+    }
+    // The word's items are one contiguous, entity-grouped range: stream it SCORE_ROWS rows at a time (the
+    // count rows and rule weights of a group are all in flight together, whatever entities they belong
+    // to) and close a logit row whenever the entity changes.
+    {
+        int cur = -1;
         double acc = 0.0;
         bool any = false;
-        for_entity_items<CT>(wi, r, arena, i, [&](CT c, int t) {
-            acc += (double)(float)c * (double)__ldg(w + r.node_term_rule[t]);      // x.float() * w (predictors.py:64)
-            any |= c != 0;
-        });
-        finish(ew * 32 + i, acc, any);
+        const int B0 = __shfl_sync(FULL, wi.b0, 0), B1 = wi.wend;
+        for (int c0 = B0; c0 < B1; c0 += 32) {
+            if (c0 != wi.wbase) word_items_window(wi, c0);
+            const int cnt = min(32, B1 - c0);
+            for (int j0 = 0; j0 < cnt; j0 += SCORE_ROWS) {
+                CT cv[SCORE_ROWS];
+                float wv[SCORE_ROWS];
+#pragma unroll
+                for (int u = 0; u < SCORE_ROWS; ++u) {
+                    const int src = (j0 + u) & 31;
+                    const int a = __shfl_sync(FULL, wi.win.x, src);
+                    const int t0 = __shfl_sync(FULL, wi.win.y, src);
+                    const bool ok = j0 + u < cnt;
+                    cv[u] = ok ? arena[(size_t)a * RL_LANES + lane] : (CT)0;
+                    wv[u] = ok ? __ldg(w + __ldg(r.node_term_rule + t0)) : 0.f;
+                }
+#pragma unroll
+                for (int u = 0; u < SCORE_ROWS; ++u) {
+                    if (j0 + u >= cnt) break;
+                    const int src = (j0 + u) & 31;
+                    const int i = __shfl_sync(FULL, wi.win.z, src) & 31;
+                    const int nt = __shfl_sync(FULL, wi.win.w, src);
+                    if (i != cur) {
+                        if (cur >= 0) finish(cur, acc, any);
+                        cur = i;
+                        acc = 0.0;
+                        any = false;
+                    }
+                    const double cf = (double)(float)cv[u];                               // x.float() * w (predictors.py:64)
+                    acc += cf * (double)wv[u];
+                    if (nt > 1) {                                                         // duplicate rules ending at the same node
+                        const int t0 = __shfl_sync(FULL, wi.win.y, src);
+                        for (int t = t0 + 1; t < t0 + nt; ++t) acc += cf * (double)__ldg(w + r.node_term_rule[t]);
+                    }
+                    any |= cv[u] != 0;
+                }
+            }
+        }
+        if (cur >= 0) finish(cur, acc, any);
+    }
+    for (uint32_t todo = slow & ~wi.present; todo; todo &= todo - 1) finish(__ffs(todo) - 1, 0.0, false);   // heads with empty-body rules only
+    if (lane < e1) ms[ew * 32 + lane] = my_bits;
+    }
+    if (!partial) return;
+    // one (max, sum-exp) pair per query and block, in k_softmax_partial's layout: one sweep over Z saved
+    sm_m[warp][lane] = run_m;
+    sm_s[warp][lane] = run_s;
+    __syncthreads();
+    if (warp == 0) {
+        float M = -INFINITY;
+        for (int k = 0; k < nwarps; ++k) M = fmaxf(M, sm_m[k][lane]);
+        double S = 0.0;
+        for (int k = 0; k < nwarps; ++k)
+            if (sm_m[k][lane] != -INFINITY) S += sm_s[k][lane] * (double)expf(sm_m[k][lane] - M);
+        float *p = partial + ((size_t)slot * gridDim.x + blockIdx.x) * 64;
+        p[lane] = M;
+        p[32 + lane] = (float)S;
     }
 }
 
@@ -501,79 +634,70 @@ k_softmax_partial(int N, const float *__restrict__ Z, float *__restrict__ partia
     }
 }
 
-// one block per slot: combine the partials, then walk the sparse targets
+// one block per slot, one warp per query lane: combine the lane's partials, then walk its sparse targets
 // stats[slot][lane][4] = (max, sumexp, S_b, valid)
-__global__ void __launch_bounds__(WARPS_PER_BLOCK * 32)
+__global__ void __launch_bounds__(CE_WARPS * 32)
 k_ce_finalize(rl_graph g, rl_slots s, rl_answers ans, float smoothing, int use_mask,
               const float *__restrict__ Z, const uint32_t *__restrict__ nzmask,
               const float *__restrict__ partial, int nblk, float *__restrict__ stats,
               float *__restrict__ slot_lsum, float *__restrict__ slot_tsum)
 {
-    __shared__ float sm_m[32], sm_s[32];
-    __shared__ double red_l[WARPS_PER_BLOCK], red_t[WARPS_PER_BLOCK];
-    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    __shared__ double red_l[CE_WARPS], red_t[CE_WARPS];
+    const int lane = threadIdx.x & 31, b = threadIdx.x >> 5;
     const int slot = blockIdx.x;
     const int N = g.num_entities;
     const int q = s.slot_head[slot];
-    if (warp == 0) {
-        float M = -INFINITY;
-        const float *p = partial + (size_t)slot * nblk * 64;
-        for (int k = 0; k < nblk; ++k) M = fmaxf(M, p[k * 64 + lane]);
-        float S = 0.f;
-        for (int k = 0; k < nblk; ++k) {
-            const float mk = p[k * 64 + lane];
-            if (mk != -INFINITY) S += p[k * 64 + 32 + lane] * expf(mk - M);
-        }
-        sm_m[lane] = M;
-        sm_s[lane] = S;
+    const float *pp = partial + (size_t)slot * nblk * 64;
+    float M = -INFINITY;
+    for (int k = lane; k < nblk; k += 32) M = fmaxf(M, pp[k * 64 + b]);
+    M = warp_maxf(M);
+    float S = 0.f;
+    for (int k = lane; k < nblk; k += 32) {
+        const float mk = pp[k * 64 + b];
+        if (mk != -INFINITY) S += pp[k * 64 + 32 + b] * expf(mk - M);
     }
-    __syncthreads();
+    S = warp_sumf(S);
     const float *Zs = Z + (size_t)slot * N * RL_LANES;
     const uint32_t *ms = nzmask + (size_t)slot * N;
-    double wl = 0.0, wt = 0.0;
-    for (int b = warp; b < 32; b += WARPS_PER_BLOCK) {
-        const int h = s.lane_h[slot * RL_LANES + b];
-        const int t = s.lane_t[slot * RL_LANES + b];
-        const float M = sm_m[b], S = sm_s[b];
-        float lsum = 0.f, tacc = 0.f, sb = 0.f;
-        bool saw_t = false;
-        if (h >= 0 && M != -INFINITY) {
-            const int ki = find_key(ans, (long long)q * N + h);
-            const int a0 = ki >= 0 ? ans.ptr[ki] : 0, a1 = ki >= 0 ? ans.ptr[ki + 1] : 0;
-            for (int a = a0 + lane; a < a1; a += 32) {
-                const int e = ans.ent[a];
-                float tg = smoothing;
-                if (e == t) { tg += 1.f - smoothing; saw_t = true; }
-                if (use_mask && !((ms[e] >> b) & 1u)) continue;
-                const float p = expf(Zs[(size_t)e * RL_LANES + b] - M) / S;
-                lsum += logf(p + 1e-8f) * tg;
-                tacc += tg;
-                sb += tg / (p + 1e-8f) * p;
-            }
-            saw_t = __any_sync(FULL, saw_t);
-            if (!saw_t && t >= 0 && lane == 0 && !(use_mask && !((ms[t] >> b) & 1u))) {
-                const float tg = 1.f - smoothing;
-                const float p = expf(Zs[(size_t)t * RL_LANES + b] - M) / S;
-                lsum += logf(p + 1e-8f) * tg;
-                tacc += tg;
-                sb += tg / (p + 1e-8f) * p;
-            }
+    const int h = s.lane_h[slot * RL_LANES + b];
+    const int t = s.lane_t[slot * RL_LANES + b];
+    float lsum = 0.f, tacc = 0.f, sb = 0.f;
+    bool saw_t = false;
+    if (h >= 0 && M != -INFINITY) {
+        const int ki = find_key(ans, (long long)q * N + h);
+        const int a0 = ki >= 0 ? ans.ptr[ki] : 0, a1 = ki >= 0 ? ans.ptr[ki + 1] : 0;
+        for (int a = a0 + lane; a < a1; a += 32) {
+            const int e = ans.ent[a];
+            float tg = smoothing;
+            if (e == t) { tg += 1.f - smoothing; saw_t = true; }
+            if (use_mask && !((ms[e] >> b) & 1u)) continue;
+            const float p = expf(Zs[(size_t)e * RL_LANES + b] - M) / S;
+            lsum += logf(p + 1e-8f) * tg;
+            tacc += tg;
+            sb += tg / (p + 1e-8f) * p;
         }
-        lsum = warp_sumf(lsum);
-        tacc = warp_sumf(tacc);
-        sb = warp_sumf(sb);
-        if (lane == 0) {
-            float *st = stats + ((size_t)slot * 32 + b) * 4;
-            st[0] = M; st[1] = S; st[2] = sb; st[3] = (h >= 0 && M != -INFINITY) ? 1.f : 0.f;
+        saw_t = __any_sync(FULL, saw_t);
+        if (!saw_t && t >= 0 && lane == 0 && !(use_mask && !((ms[t] >> b) & 1u))) {
+            const float tg = 1.f - smoothing;
+            const float p = expf(Zs[(size_t)t * RL_LANES + b] - M) / S;
+            lsum += logf(p + 1e-8f) * tg;
+            tacc += tg;
+            sb += tg / (p + 1e-8f) * p;
         }
-        wl += (double)lsum;
-        wt += (double)tacc;
     }
-    if (lane == 0) { red_l[warp] = wl; red_t[warp] = wt; }
+    lsum = warp_sumf(lsum);
+    tacc = warp_sumf(tacc);
+    sb = warp_sumf(sb);
+    if (lane == 0) {
+        float *st = stats + ((size_t)slot * 32 + b) * 4;
+        st[0] = M; st[1] = S; st[2] = sb; st[3] = (h >= 0 && M != -INFINITY) ? 1.f : 0.f;
+        red_l[b] = (double)lsum;
+        red_t[b] = (double)tacc;
+    }
     __syncthreads();
     if (threadIdx.x == 0) {
         double L = 0.0, T = 0.0;
-        for (int k = 0; k < WARPS_PER_BLOCK; ++k) { L += red_l[k]; T += red_t[k]; }
+        for (int k = 0; k < CE_WARPS; ++k) { L += red_l[k]; T += red_t[k]; }
         slot_tsum[slot] = (float)T;
         slot_lsum[slot] = (float)(-L);
     }
@@ -620,13 +744,15 @@ k_grad_dense(int N, const float *__restrict__ Z, const float *__restrict__ stats
     G[(size_t)slot * N * RL_LANES + i] = gval;
 }
 
-// sparse part: G[e][b] -= p * tgt / (p + eps) / T' at the target entries
-__global__ void __launch_bounds__(WARPS_PER_BLOCK * 32)
+// sparse part: G[e][b] -= p * tgt / (p + eps) / T' at the target entries (one warp per query lane); with
+// grad_bias != NULL the same terms also go into the bias gradient (the dense part comes from k_grad_dense_bias)
+__global__ void __launch_bounds__(CE_WARPS * 32)
 k_grad_sparse(rl_graph g, rl_slots s, rl_answers ans, float smoothing, int use_mask,
               const float *__restrict__ Z, const uint32_t *__restrict__ nzmask,
-              const float *__restrict__ stats, const float *__restrict__ slot_invT, float *__restrict__ G)
+              const float *__restrict__ stats, const float *__restrict__ slot_invT, float *__restrict__ G,
+              const float *__restrict__ slot_scale, float *__restrict__ grad_bias)
 {
-    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int lane = threadIdx.x & 31, b = threadIdx.x >> 5;
     const int slot = blockIdx.x;
     const int N = g.num_entities;
     const int q = s.slot_head[slot];
@@ -634,30 +760,30 @@ k_grad_sparse(rl_graph g, rl_slots s, rl_answers ans, float smoothing, int use_m
     float *Gs = G + (size_t)slot * N * RL_LANES;
     const uint32_t *ms = nzmask + (size_t)slot * N;
     const float iT = slot_invT[slot];
-    for (int b = warp; b < 32; b += WARPS_PER_BLOCK) {
-        const float *st = stats + ((size_t)slot * 32 + b) * 4;
-        if (st[3] == 0.f) continue;
-        const int h = s.lane_h[slot * RL_LANES + b];
-        const int t = s.lane_t[slot * RL_LANES + b];
-        const float M = st[0], S = st[1];
-        const int ki = find_key(ans, (long long)q * N + h);
-        const int a0 = ki >= 0 ? ans.ptr[ki] : 0, a1 = ki >= 0 ? ans.ptr[ki + 1] : 0;
-        bool saw_t = false;
-        for (int a = a0 + lane; a < a1; a += 32) {
-            const int e = ans.ent[a];
-            float tg = smoothing;
-            if (e == t) { tg += 1.f - smoothing; saw_t = true; }
-            if (use_mask && !((ms[e] >> b) & 1u)) continue;
-            const float p = expf(Zs[(size_t)e * RL_LANES + b] - M) / S;
-            Gs[(size_t)e * RL_LANES + b] -= p * (tg / (p + 1e-8f)) * iT;
-        }
-        saw_t = __any_sync(FULL, saw_t);
-        if (!saw_t && t >= 0 && lane == 0 && !(use_mask && !((ms[t] >> b) & 1u))) {
-            const float tg = 1.f - smoothing;
-            const float p = expf(Zs[(size_t)t * RL_LANES + b] - M) / S;
-            Gs[(size_t)t * RL_LANES + b] -= p * (tg / (p + 1e-8f)) * iT;
-        }
+    const float *st = stats + ((size_t)slot * 32 + b) * 4;
+    if (st[3] == 0.f) return;
+    const int h = s.lane_h[slot * RL_LANES + b];
+    const int t = s.lane_t[slot * RL_LANES + b];
+    const float M = st[0], S = st[1];
+    const float scale = slot_scale ? slot_scale[slot] : 1.f;
+    auto apply = [&](int e, float tg) {
+        const float p = expf(Zs[(size_t)e * RL_LANES + b] - M) / S;
+        const float term = p * (tg / (p + 1e-8f)) * iT;
+        Gs[(size_t)e * RL_LANES + b] -= term;
+        if (grad_bias) atomicAdd(grad_bias + e, -term * scale);
+    };
+    const int ki = find_key(ans, (long long)q * N + h);
+    const int a0 = ki >= 0 ? ans.ptr[ki] : 0, a1 = ki >= 0 ? ans.ptr[ki + 1] : 0;
+    bool saw_t = false;
+    for (int a = a0 + lane; a < a1; a += 32) {
+        const int e = ans.ent[a];
+        float tg = smoothing;
+        if (e == t) { tg += 1.f - smoothing; saw_t = true; }
+        if (use_mask && !((ms[e] >> b) & 1u)) continue;
+        apply(e, tg);
     }
+    saw_t = __any_sync(FULL, saw_t);
+    if (!saw_t && t >= 0 && lane == 0 && !(use_mask && !((ms[t] >> b) & 1u))) apply(t, 1.f - smoothing);
 }
 
 // ------------------------------------------------------------------------------------------
@@ -666,10 +792,11 @@ k_grad_sparse(rl_graph g, rl_slots s, rl_answers ans, float smoothing, int use_m
 // Backward over the item list: one warp per non-zero terminal row: <G[e], fp32(count row)> goes to
 // every rule ending at the row's node (one atomic each).
 #define ITEM_BLOCKS 96
+// sorted != 0: walk the entity-grouped list (after rl_sort_items) -- neighbouring warps then share rows of G.
 template <typename CT>
 __global__ void __launch_bounds__(WARPS_PER_BLOCK * 32)
 k_predictor_bwd_items(rl_graph g, rl_rules r, rl_slots s, rl_frontier fr, const float *__restrict__ G,
-                      const float *__restrict__ slot_scale, float *__restrict__ grad_w)
+                      const float *__restrict__ slot_scale, float *__restrict__ grad_w, int sorted)
 {
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const int slot = blockIdx.y;
@@ -678,33 +805,34 @@ k_predictor_bwd_items(rl_graph g, rl_rules r, rl_slots s, rl_frontier fr, const 
     const int q = s.slot_head[slot];
     const float scale = slot_scale ? slot_scale[slot] : 1.f;
     const float *Gs = G + (size_t)slot * N * RL_LANES;
+    auto grad_at = [&](int e) -> float { return Gs[(size_t)e * RL_LANES + lane]; };
     const int z0 = r.zr_ptr[q], z1 = r.zr_ptr[q + 1];
     if (blockIdx.x == 0 && warp == 0 && z1 > z0) {                 // empty-body rules: count = one_hot(h)
         const int h = s.lane_h[slot * RL_LANES + lane];
-        double v = h >= 0 ? (double)Gs[(size_t)h * RL_LANES + lane] : 0.0;
+        double v = h >= 0 ? (double)grad_at(h) : 0.0;
         v = warp_sum(v);
         if (lane == 0)
             for (int t = z0; t < z1; ++t) atomicAdd(grad_w + r.zr_rule[t], (float)v * scale);
     }
     const CT *arena = reinterpret_cast<const CT *>(fr.arena) + (size_t)s.arena_off[slot] * RL_LANES;
-    const int4 *it = reinterpret_cast<const int4 *>(fr.items) + fr.item_off[slot];
+    const int4 *it = reinterpret_cast<const int4 *>(sorted ? fr.items_sorted : fr.items) + fr.item_off[slot];
     const int stride = ITEM_BLOCKS * WARPS_PER_BLOCK;
     for (int i = blockIdx.x * WARPS_PER_BLOCK + warp; i < n; i += 2 * stride) {     // two items in flight
         const int i2 = i + stride;
-        const int4 ra = __ldg(it + i);                             // {row, node, entity, -}
+        const int4 ra = __ldg(it + i);                             // {row, first rule end, entity, rule ends}
         const int4 rb = i2 < n ? __ldg(it + i2) : ra;
         const CT ca = arena[(size_t)ra.x * RL_LANES + lane];
         const CT cb = arena[(size_t)rb.x * RL_LANES + lane];
-        const float ga = Gs[(size_t)ra.z * RL_LANES + lane];
-        const float gb = Gs[(size_t)rb.z * RL_LANES + lane];
+        const float ga = grad_at(ra.z);
+        const float gb = grad_at(rb.z);
         double va = ca != 0 ? (double)(float)ca * (double)ga : 0.0;     // skips NaN*0 of masked cells
         double vb = (i2 < n && cb != 0) ? (double)(float)cb * (double)gb : 0.0;
         va = warp_sum(va);
         vb = warp_sum(vb);
         if (lane == 0 && va != 0.0)
-            for (int t = r.node_term_ptr[ra.y]; t < r.node_term_ptr[ra.y + 1]; ++t) atomicAdd(grad_w + r.node_term_rule[t], (float)va * scale);
+            for (int t = ra.y; t < ra.y + ra.w; ++t) atomicAdd(grad_w + r.node_term_rule[t], (float)va * scale);
         if (lane == 0 && vb != 0.0)
-            for (int t = r.node_term_ptr[rb.y]; t < r.node_term_ptr[rb.y + 1]; ++t) atomicAdd(grad_w + r.node_term_rule[t], (float)vb * scale);
+            for (int t = rb.y; t < rb.y + rb.w; ++t) atomicAdd(grad_w + r.node_term_rule[t], (float)vb * scale);
     }
 }
 
@@ -720,6 +848,30 @@ k_bias_grad(int N, int S, const float *__restrict__ G, const float *__restrict__
         acc += (double)G[((size_t)sl * N + e) * RL_LANES + lane] * (double)(slot_scale ? slot_scale[sl] : 1.f);
     acc = warp_sum(acc);
     if (lane == 0) grad_bias[e] += (float)acc;
+}
+
+// k_grad_dense and the dense part of k_bias_grad in one sweep over Z (a warp = one entity, looping over slots):
+// G[sl][e][b] = coef_b * exp(z - max_b) is written and summed into grad_bias[e] on the way.
+#define BIAS_SLOT_SPLIT 4
+__global__ void __launch_bounds__(WARPS_PER_BLOCK * 32)
+k_grad_dense_bias(int N, int S, const float *__restrict__ Z, const float *__restrict__ stats,
+                  const float *__restrict__ slot_scale, float *__restrict__ G, float *__restrict__ grad_bias)
+{
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int e = blockIdx.x * WARPS_PER_BLOCK + warp;
+    if (e >= N) return;
+    double acc = 0.0;
+#pragma unroll 8
+    for (int sl = blockIdx.y; sl < S; sl += BIAS_SLOT_SPLIT) {
+        const float4 st = __ldg(reinterpret_cast<const float4 *>(stats) + (size_t)sl * 32 + lane);
+        const size_t at = ((size_t)sl * N + e) * RL_LANES + lane;
+        const float z = Z[at];
+        const float gval = (st.w != 0.f && z != -INFINITY) ? expf(z - st.x) * st.w : 0.f;
+        G[at] = gval;
+        acc += (double)gval * (double)(slot_scale ? slot_scale[sl] : 1.f);
+    }
+    acc = warp_sum(acc);
+    if (lane == 0) atomicAdd(grad_bias + e, (float)acc);
 }
 
 // ------------------------------------------------------------------------------------------
@@ -921,14 +1073,15 @@ int rl_device_count(void)
 }
 
 int rl_prepare_slots(const rl_graph *g, int32_t S, const int32_t *slot_head, const int32_t *q_off,
-                     const int64_t *all_h, const int64_t *all_t, const int64_t *etr, int32_t *lane_h,
-                     int32_t *lane_t, int32_t *lane_eh, int32_t *lane_et, void *stream)
+                     const int64_t *all_h, const int64_t *all_t, const int64_t *etr, int32_t remove_query_edges,
+                     int32_t *lane_h, int32_t *lane_t, int32_t *lane_eh, int32_t *lane_et, void *stream)
 {
     if (!g || !slot_head || !q_off || !all_h || !lane_h || !lane_t || !lane_eh || !lane_et || S <= 0)
         return fail(RL_ERR_ARG, "rl_prepare_slots: bad argument");
     const int n = S * RL_LANES;
+    if (remove_query_edges && !all_t) return fail(RL_ERR_ARG, "rl_prepare_slots: remove_query_edges needs all_t");
     k_prepare_slots<<<(n + 255) / 256, 256, 0, (cudaStream_t)stream>>>(*g, S, slot_head, q_off, all_h, all_t, etr,
-                                                                        lane_h, lane_t, lane_eh, lane_et);
+                                                                        remove_query_edges, lane_h, lane_t, lane_eh, lane_et);
     CHECK_LAUNCH("k_prepare_slots");
     return RL_OK;
 }
@@ -998,30 +1151,62 @@ int rl_sort_items(const rl_graph *g, const rl_slots *s, const rl_frontier *fr, v
     if (check_frontier(fr, "rl_sort_items: incomplete rl_frontier") != RL_OK) return RL_ERR_ARG;
     if (check_items(fr, "rl_sort_items: the frontier was expanded without an item list") != RL_OK) return RL_ERR_ARG;
     if (s->num_slots <= 0) return RL_OK;
-    k_items_sort<<<s->num_slots, 512, 0, (cudaStream_t)stream>>>(g->rank_words, *fr);
-    CHECK_LAUNCH("k_items_sort");
-    return RL_OK;
+    return launch_items_sort(g, s, fr, (cudaStream_t)stream);
+}
+
+// warps per k_predictor_scores block (tail-bound kernel: hub words make long warps; swept on the B200)
+static int score_warps()
+{
+    static int v = 0;
+    if (!v) {
+        const char *e = getenv("RL_SCORE_WARPS");
+        v = e ? atoi(e) : 8;
+        if (v < 1 || v > SCORE_WARPS_MAX) v = 8;
+    }
+    return v;
 }
 
 int rl_predictor_scores(const rl_graph *g, const rl_rules *r, const rl_slots *s, const rl_frontier *fr,
                         const float *w, const float *bias, int32_t fill_neg_inf, float *Z, uint32_t *nzmask,
-                        void *stream)
+                        float *partial, void *stream)
 {
     if (!g || !r || !s || !w || !Z || !nzmask) return fail(RL_ERR_ARG, "rl_predictor_scores: null argument");
     if (check_frontier(fr, "rl_predictor_scores: incomplete rl_frontier") != RL_OK) return RL_ERR_ARG;
     if (check_items(fr, "rl_predictor_scores: the frontier was expanded without an item list") != RL_OK) return RL_ERR_ARG;
     if (s->num_slots <= 0) return RL_OK;
     cudaStream_t st = (cudaStream_t)stream;
-    k_items_sort<<<s->num_slots, 512, 0, st>>>(g->rank_words, *fr);
-    CHECK_LAUNCH("k_items_sort");
-    dim3 grid((g->rank_words + WARPS_PER_BLOCK - 1) / WARPS_PER_BLOCK, s->num_slots);
-    if (fr->count_bits == 32) k_predictor_scores<uint32_t><<<grid, WARPS_PER_BLOCK * 32, 0, st>>>(*g, *r, *s, *fr, w, bias, fill_neg_inf, Z, nzmask);
-    else k_predictor_scores<unsigned long long><<<grid, WARPS_PER_BLOCK * 32, 0, st>>>(*g, *r, *s, *fr, w, bias, fill_neg_inf, Z, nzmask);
+    if (launch_items_sort(g, s, fr, st) != RL_OK) return RL_ERR_CUDA;
+    const int sw = score_warps();
+    dim3 grid((g->rank_words + sw - 1) / sw, s->num_slots);           // one block = one softmax partial
+    if (fr->count_bits == 32) k_predictor_scores<uint32_t><<<grid, sw * 32, 0, st>>>(*g, *r, *s, *fr, w, bias, fill_neg_inf, Z, nzmask, partial);
+    else k_predictor_scores<unsigned long long><<<grid, sw * 32, 0, st>>>(*g, *r, *s, *fr, w, bias, fill_neg_inf, Z, nzmask, partial);
     CHECK_LAUNCH("k_predictor_scores");
     return RL_OK;
 }
 
-int rl_softmax_blocks(int32_t N) { return (N + SM_ROWS_PER_BLOCK - 1) / SM_ROWS_PER_BLOCK; }
+static int sweep_blocks(int N) { return (N + SM_ROWS_PER_BLOCK - 1) / SM_ROWS_PER_BLOCK; }
+static int score_blocks(int N) { const int W = (N + 31) / 32, sw = score_warps(); return (W + sw - 1) / sw; }
+// scratch sizing: partials come either from k_softmax_partial or from k_predictor_scores
+int rl_softmax_blocks(int32_t N) { return sweep_blocks(N) > score_blocks(N) ? sweep_blocks(N) : score_blocks(N); }
+
+// loss half shared by rl_softmax_ce and rl_predictor_ce_backward
+static int ce_forward(const rl_graph *g, const rl_slots *s, const rl_answers *ans, float smoothing, int32_t use_mask,
+                      const float *Z, const uint32_t *nzmask, int32_t n_groups, const int32_t *group_ptr, float *partial,
+                      int partial_ready, float *stats, float *slot_sums, float *group_loss, float *group_tsum, cudaStream_t st)
+{
+    const int S = s->num_slots, N = g->num_entities;
+    const int nblk = partial_ready ? score_blocks(N) : sweep_blocks(N);
+    float *slot_lsum = slot_sums, *slot_tsum = slot_sums + S, *slot_invT = slot_sums + 2 * (size_t)S;
+    if (!partial_ready) {
+        k_softmax_partial<<<dim3(nblk, S), WARPS_PER_BLOCK * 32, 0, st>>>(N, Z, partial, nblk);
+        CHECK_LAUNCH("k_softmax_partial");
+    }
+    k_ce_finalize<<<S, CE_WARPS * 32, 0, st>>>(*g, *s, *ans, smoothing, use_mask, Z, nzmask, partial, nblk, stats, slot_lsum, slot_tsum);
+    CHECK_LAUNCH("k_ce_finalize");
+    k_group_reduce<<<n_groups, 32, 0, st>>>(n_groups, group_ptr, slot_lsum, slot_tsum, group_loss, group_tsum, slot_invT, stats);
+    CHECK_LAUNCH("k_group_reduce");
+    return RL_OK;
+}
 
 int rl_softmax_ce(const rl_graph *g, const rl_slots *s, const rl_answers *ans, float smoothing, int32_t use_mask,
                   const float *Z, const uint32_t *nzmask, int32_t n_groups, const int32_t *group_ptr,
@@ -1033,23 +1218,61 @@ int rl_softmax_ce(const rl_graph *g, const rl_slots *s, const rl_answers *ans, f
     const int S = s->num_slots, N = g->num_entities;
     if (S <= 0) return RL_OK;
     if (n_groups <= 0 || n_groups > S || (!group_ptr && n_groups != S)) return fail(RL_ERR_ARG, "rl_softmax_ce: bad group table");
-    const int nblk = rl_softmax_blocks(N);
     cudaStream_t st = (cudaStream_t)stream;
-    float *slot_lsum = slot_sums, *slot_tsum = slot_sums + S, *slot_invT = slot_sums + 2 * (size_t)S;
-    k_softmax_partial<<<dim3(nblk, S), WARPS_PER_BLOCK * 32, 0, st>>>(N, Z, partial, nblk);
-    CHECK_LAUNCH("k_softmax_partial");
-    k_ce_finalize<<<S, WARPS_PER_BLOCK * 32, 0, st>>>(*g, *s, *ans, smoothing, use_mask, Z, nzmask, partial, nblk, stats, slot_lsum, slot_tsum);
-    CHECK_LAUNCH("k_ce_finalize");
-    k_group_reduce<<<n_groups, 32, 0, st>>>(n_groups, group_ptr, slot_lsum, slot_tsum, group_loss, group_tsum, slot_invT, stats);
-    CHECK_LAUNCH("k_group_reduce");
+    float *slot_invT = slot_sums + 2 * (size_t)S;
+    const int rc = ce_forward(g, s, ans, smoothing, use_mask, Z, nzmask, n_groups, group_ptr, partial, 0, stats, slot_sums,
+                              group_loss, group_tsum, st);
+    if (rc != RL_OK) return rc;
     if (G) {
         const size_t n = (size_t)N * RL_LANES;
         k_grad_dense<<<dim3((unsigned)((n + 255) / 256), S), 256, 0, st>>>(N, Z, stats, slot_invT, G);
         CHECK_LAUNCH("k_grad_dense");
-        k_grad_sparse<<<S, WARPS_PER_BLOCK * 32, 0, st>>>(*g, *s, *ans, smoothing, use_mask, Z, nzmask, stats, slot_invT, G);
+        k_grad_sparse<<<S, CE_WARPS * 32, 0, st>>>(*g, *s, *ans, smoothing, use_mask, Z, nzmask, stats, slot_invT, G, nullptr, nullptr);
         CHECK_LAUNCH("k_grad_sparse");
     }
     return RL_OK;
+}
+
+static int launch_bwd_items(const rl_graph *g, const rl_rules *r, const rl_slots *s, const rl_frontier *fr, const float *G,
+                            const float *slot_scale, float *grad_w, int sorted, cudaStream_t st)
+{
+    const dim3 grid(ITEM_BLOCKS, s->num_slots);
+    if (fr->count_bits == 32) k_predictor_bwd_items<uint32_t><<<grid, WARPS_PER_BLOCK * 32, 0, st>>>(*g, *r, *s, *fr, G, slot_scale, grad_w, sorted);
+    else k_predictor_bwd_items<unsigned long long><<<grid, WARPS_PER_BLOCK * 32, 0, st>>>(*g, *r, *s, *fr, G, slot_scale, grad_w, sorted);
+    CHECK_LAUNCH("k_predictor_bwd_items");
+    return RL_OK;
+}
+
+int rl_predictor_ce_backward(const rl_graph *g, const rl_rules *r, const rl_slots *s, const rl_frontier *fr,
+                             const rl_answers *ans, float smoothing, int32_t use_mask, const float *Z,
+                             const uint32_t *nzmask, int32_t n_groups, const int32_t *group_ptr, float *partial,
+                             int32_t partial_ready, float *stats, float *slot_sums, float *group_loss, float *group_tsum,
+                             float *G, const float *slot_scale, float *grad_w, float *grad_bias, void *stream)
+{
+    if (!g || !r || !s || !ans || !Z || !nzmask || !partial || !stats || !slot_sums || !group_loss || !group_tsum || !G || !grad_w)
+        return fail(RL_ERR_ARG, "rl_predictor_ce_backward: null argument");
+    if (check_frontier(fr, "rl_predictor_ce_backward: incomplete rl_frontier") != RL_OK) return RL_ERR_ARG;
+    if (check_items(fr, "rl_predictor_ce_backward: the frontier was expanded without an item list") != RL_OK) return RL_ERR_ARG;
+    const int S = s->num_slots, N = g->num_entities;
+    if (S <= 0) return RL_OK;
+    if (n_groups <= 0 || n_groups > S || (!group_ptr && n_groups != S)) return fail(RL_ERR_ARG, "rl_predictor_ce_backward: bad group table");
+    cudaStream_t st = (cudaStream_t)stream;
+    float *slot_invT = slot_sums + 2 * (size_t)S;
+    int rc = ce_forward(g, s, ans, smoothing, use_mask, Z, nzmask, n_groups, group_ptr, partial, partial_ready, stats,
+                        slot_sums, group_loss, group_tsum, st);
+    if (rc != RL_OK) return rc;
+    if (grad_bias) {
+        k_grad_dense_bias<<<dim3((N + WARPS_PER_BLOCK - 1) / WARPS_PER_BLOCK, BIAS_SLOT_SPLIT), WARPS_PER_BLOCK * 32, 0, st>>>(
+            N, S, Z, stats, slot_scale, G, grad_bias);
+        CHECK_LAUNCH("k_grad_dense_bias");
+    } else {
+        const size_t n = (size_t)N * RL_LANES;
+        k_grad_dense<<<dim3((unsigned)((n + 255) / 256), S), 256, 0, st>>>(N, Z, stats, slot_invT, G);
+        CHECK_LAUNCH("k_grad_dense");
+    }
+    k_grad_sparse<<<S, CE_WARPS * 32, 0, st>>>(*g, *s, *ans, smoothing, use_mask, Z, nzmask, stats, slot_invT, G, slot_scale, grad_bias);
+    CHECK_LAUNCH("k_grad_sparse");
+    return launch_bwd_items(g, r, s, fr, G, slot_scale, grad_w, 1, st);
 }
 
 int rl_predictor_backward(const rl_graph *g, const rl_rules *r, const rl_slots *s, const rl_frontier *fr,
@@ -1061,10 +1284,8 @@ int rl_predictor_backward(const rl_graph *g, const rl_rules *r, const rl_slots *
     const int S = s->num_slots, N = g->num_entities;
     if (S <= 0) return RL_OK;
     cudaStream_t st = (cudaStream_t)stream;
-    dim3 gi(ITEM_BLOCKS, S);
-    if (fr->count_bits == 32) k_predictor_bwd_items<uint32_t><<<gi, WARPS_PER_BLOCK * 32, 0, st>>>(*g, *r, *s, *fr, G, slot_scale, grad_w);
-    else k_predictor_bwd_items<unsigned long long><<<gi, WARPS_PER_BLOCK * 32, 0, st>>>(*g, *r, *s, *fr, G, slot_scale, grad_w);
-    CHECK_LAUNCH("k_predictor_bwd_items");
+    const int rc = launch_bwd_items(g, r, s, fr, G, slot_scale, grad_w, 0, st);
+    if (rc != RL_OK) return rc;
     if (grad_bias) {
         k_bias_grad<<<(N + WARPS_PER_BLOCK - 1) / WARPS_PER_BLOCK, WARPS_PER_BLOCK * 32, 0, st>>>(N, S, G, slot_scale, grad_bias);
         CHECK_LAUNCH("k_bias_grad");
@@ -1081,7 +1302,7 @@ int rl_filtered_rank(const rl_graph *g, const rl_slots *s, const rl_answers *kno
     cudaStream_t st = (cudaStream_t)stream;
     cudaError_t e = cudaMemsetAsync(counters, 0, (size_t)S * 64 * sizeof(int32_t), st);
     if (e != cudaSuccess) return fail(RL_ERR_CUDA, "rl_filtered_rank: memset", e);
-    k_rank_count<<<dim3(rl_softmax_blocks(N), S), WARPS_PER_BLOCK * 32, 0, st>>>(N, *s, Z, counters);
+    k_rank_count<<<dim3(sweep_blocks(N), S), WARPS_PER_BLOCK * 32, 0, st>>>(N, *s, Z, counters);
     CHECK_LAUNCH("k_rank_count");
     k_rank_finalize<<<S, WARPS_PER_BLOCK * 32, 0, st>>>(*g, *s, *known, use_mask, Z, nzmask, counters, LH);
     CHECK_LAUNCH("k_rank_finalize");

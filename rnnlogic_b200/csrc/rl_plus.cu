@@ -226,11 +226,11 @@ k_plus_backward(rl_graph g, rl_rules r, rl_slots s, rl_frontier fr, const uint32
     const CT *arena = reinterpret_cast<const CT *>(fr.arena) + (size_t)s.arena_off[slot] * RL_LANES;
     const int4 *it = reinterpret_cast<const int4 *>(fr.items) + fr.item_off[slot];
     for (int i = blockIdx.x * WARPS_PER_BLOCK + warp; i < n; i += PLUS_ITEM_BLOCKS * WARPS_PER_BLOCK) {
-        const int4 rec = __ldg(it + i);                            // {row, node, entity, -}
+        const int4 rec = __ldg(it + i);                            // {row, first rule end, entity, rule ends}
         const float cf = (float)arena[(size_t)rec.x * RL_LANES + lane];
         const uint32_t bits = ms[rec.z];
         const long long base = co[rec.z];
-        for (int t = r.node_term_ptr[rec.y]; t < r.node_term_ptr[rec.y + 1]; ++t) contribute(cf, r.node_term_rule[t], bits, base);
+        for (int t = rec.y; t < rec.y + rec.w; ++t) contribute(cf, r.node_term_rule[t], bits, base);
     }
 }
 
@@ -258,7 +258,7 @@ k_rule_stats(rl_graph g, rl_rules r, rl_slots s, rl_frontier fr, int max_terms, 
         const int4 rec = __ldg(it + i);
         const CT c = arena[(size_t)rec.x * RL_LANES + lane];
         if (c == 0) continue;
-        for (int t = r.node_term_ptr[rec.y]; t < r.node_term_ptr[rec.y + 1]; ++t) {
+        for (int t = rec.y; t < rec.y + rec.w; ++t) {
             atomicAdd(sums + (size_t)(t - t_first) * RL_LANES + lane, (double)c);
             if (rec.z == ans) poss[(size_t)(t - t_first) * RL_LANES + lane] = (double)c;
         }

@@ -19,14 +19,18 @@ LANES = _lib.LANES
 
 
 def _stream():
-    return C.c_void_p(torch.cuda.current_stream().cuda_stream)
+    return C.c_void_p(torch._C._cuda_getCurrentRawStream(torch.cuda.current_device()))
 
 
 class Slots:
     """Device-side description of one call (rl_slots) + its frontier arena."""
 
     def __init__(self, dg, cr: CompiledRules, heads: np.ndarray, q_off: np.ndarray,
-                 all_h: torch.Tensor, all_t: Optional[torch.Tensor], etr: Optional[torch.Tensor]):
+                 all_h: Optional[torch.Tensor], all_t: Optional[torch.Tensor], etr: Optional[torch.Tensor],
+                 host_queries: Optional[np.ndarray] = None, remove_query_edges: bool = False,
+                 group_ptr: Optional[np.ndarray] = None):
+        """all_h / all_t / etr: int64 CUDA tensors -- or host_queries int64[k, Q] (rows h, t[, etr]), which
+        then travel with the slot descriptors in ONE pinned host->device copy."""
         dev = dg.device
         S = int(heads.shape[0])
         self.S, self.heads, self.q_off = S, heads, q_off
@@ -41,20 +45,38 @@ class Slots:
         np.cumsum(cr.head_item_cap[heads], out=item_off[1:])
         self.arena_rows, self.nz_total, self.mask_words = int(arena_off[-1]), int(nz_off[-1]), int(mask_off[-1])
         self.item_cap = int(item_off[-1])
-        # one packed H2D copy for the slot descriptors
-        pack = np.concatenate([heads.astype(np.int64), q_off.astype(np.int64), nz_off[:-1], arena_off[:-1],
-                               mask_off[:-1], item_off])
+        # one packed H2D copy: int64 sections first, the int32 tables behind them
+        k, Q = (0, 0) if host_queries is None else host_queries.shape
+        ng1 = 0 if group_ptr is None else int(group_ptr.shape[0])
+        n64 = k * Q + 3 * S + 1
+        n32 = 3 * S + 1 + ng1
+        pack = np.empty(n64 + (n32 + 1) // 2, dtype=np.int64)
+        if k:
+            pack[:k * Q] = host_queries.reshape(-1)
+        o = k * Q
+        pack[o:o + S] = arena_off[:-1]
+        pack[o + S:o + 2 * S] = mask_off[:-1]
+        pack[o + 2 * S:o + 3 * S + 1] = item_off
+        p32 = pack[n64:].view(np.int32)
+        p32[:S] = heads
+        p32[S:2 * S + 1] = q_off
+        p32[2 * S + 1:3 * S + 1] = nz_off[:-1]
+        if ng1:
+            p32[3 * S + 1:3 * S + 1 + ng1] = group_ptr
         d = torch.from_numpy(pack).pin_memory().to(dev, non_blocking=True)      # pinned staging, async copy
-        self.slot_head = d[:S].to(torch.int32)
-        self.q_off_dev = d[S:2 * S + 1].to(torch.int32)
-        self.nz_off = d[2 * S + 1:3 * S + 1].to(torch.int32)
-        self.arena_off = d[3 * S + 1:4 * S + 1].contiguous()
-        self.mask_off = d[4 * S + 1:5 * S + 1].contiguous()
-        self.item_off = d[5 * S + 1:6 * S + 2].contiguous()
+        self.h2d_bytes = int(pack.nbytes)
+        if k:
+            all_h, all_t = d[:Q], d[Q:2 * Q]
+            etr = d[2 * Q:3 * Q] if k > 2 else None
+        self.arena_off, self.mask_off, self.item_off = d[o:o + S], d[o + S:o + 2 * S], d[o + 2 * S:o + 3 * S + 1]
+        d32 = d[n64:].view(torch.int32)
+        self.slot_head, self.q_off_dev, self.nz_off = d32[:S], d32[S:2 * S + 1], d32[2 * S + 1:3 * S + 1]
+        self.group_ptr_dev = d32[3 * S + 1:3 * S + 1 + ng1] if ng1 else None
         self.lane = torch.empty(4, S * LANES, dtype=torch.int32, device=dev)
         _lib.check(_lib.lib().rl_prepare_slots(
             dg.ref(), S, self.slot_head.data_ptr(), self.q_off_dev.data_ptr(), all_h.data_ptr(),
             all_t.data_ptr() if all_t is not None else None, etr.data_ptr() if etr is not None else None,
+            int(remove_query_edges and etr is None),
             self.lane[0].data_ptr(), self.lane[1].data_ptr(), self.lane[2].data_ptr(), self.lane[3].data_ptr(),
             _stream()), "rl_prepare_slots")
         self.struct = _lib.RlSlots(S, self.slot_head.data_ptr(), self.lane[0].data_ptr(), self.lane[1].data_ptr(),
@@ -92,6 +114,20 @@ class Grounder:
         self._ws_items = None
         self.level_events = None      # bench.py: list collecting (depth, start, end) CUDA events
 
+    @staticmethod
+    def _split(heads, sizes):
+        """Cut single-relation groups into slots of <= 32 queries -> (slot heads, query offsets, group slot ranges)."""
+        sh, qo, gp, pos = [], [0], [0], 0
+        for hd, n in zip(heads, sizes):
+            for k in range(0, int(n), LANES):
+                sh.append(int(hd))
+                qo.append(pos + min(int(n), k + LANES))
+            pos += int(n)
+            gp.append(len(sh))
+        if not sh:
+            raise ValueError("empty batch")
+        return np.array(sh, dtype=np.int64), np.array(qo, dtype=np.int64), np.array(gp, dtype=np.int32), pos
+
     def make_slots(self, heads: Sequence[int], sizes: Sequence[int], all_h, all_t=None, etr=None) -> Slots:
         """heads[i] / sizes[i]: head relation and number of queries of the i-th single-relation
         group; queries are consecutive in all_h / all_t / etr (int64 CUDA tensors).  Groups larger
@@ -99,25 +135,20 @@ class Grounder:
         for name, t in (("all_h", all_h), ("all_t", all_t), ("edges_to_remove", etr)):
             if t is not None:
                 _lib.require_cuda(t, name)
-        sh, qo, pos = [], [0], 0
-        for hd, n in zip(heads, sizes):
-            for k in range(0, int(n), LANES):
-                sh.append(int(hd))
-                qo.append(pos + min(int(n), k + LANES))
-            pos += int(n)
-        if not sh:
-            raise ValueError("empty batch")
+        sh, qo, gp, pos = self._split(heads, sizes)
         for name, t in (("all_h", all_h), ("all_t", all_t), ("edges_to_remove", etr)):
             if t is not None and int(t.numel()) != pos:
                 raise ValueError("%s has %d entries for %d queries" % (name, int(t.numel()), pos))
-        return Slots(self.dg, self.cr, np.array(sh, dtype=np.int64), np.array(qo, dtype=np.int64),
-                     all_h.contiguous(), None if all_t is None else all_t.contiguous(),
-                     None if etr is None else etr.contiguous())
+        sl = Slots(self.dg, self.cr, sh, qo, all_h.contiguous(), None if all_t is None else all_t.contiguous(),
+                   None if etr is None else etr.contiguous(), group_ptr=gp if len(sh) != len(sizes) else None)
+        sl.group_sizes = list(sizes)
+        return sl
 
     def make_slots_host(self, batches, with_etr: bool, etr_lists=None) -> Slots:
         """Slots for a list of single-relation batches given as host lists of (h, r, t) triples
-        (what the datasets hold).  One packed host->device copy carries h, t and the removed-edge
-        indices; with_etr looks the indices up in the graph's train-edge table (data.py:214-216)."""
+        (what the datasets hold).  ONE packed host->device copy carries h, t and the slot tables.
+        with_etr: every query's own train edge is masked out (data.py:214-216); the edge is found on
+        the device unless etr_lists gives the reference's per-relation edge indices explicitly."""
         if isinstance(batches[0], np.ndarray):                  # int arrays [n,3]: no per-triple Python work
             flat = np.concatenate(batches).astype(np.int64, copy=False).reshape(-1, 3)
             heads = [int(b[0, 1]) for b in batches]
@@ -126,16 +157,13 @@ class Grounder:
             heads = [b[0][1] for b in batches]
         sizes = [len(b) for b in batches]
         rows = [flat[:, 0], flat[:, 2]]
-        if with_etr:
-            if etr_lists is not None:
-                rows.append(np.array([e for l in etr_lists for e in l], dtype=np.int64))
-            else:
-                rows.append(self.graph.edge_index_of(flat))
-        d = torch.from_numpy(np.ascontiguousarray(np.stack(rows))).pin_memory().to(self.device, non_blocking=True)
-        sl = self.make_slots(heads, sizes, d[0], d[1], d[2] if with_etr else None)
+        if with_etr and etr_lists is not None:
+            rows.append(np.array([e for l in etr_lists for e in l], dtype=np.int64))
+        sh, qo, gp, pos = self._split(heads, sizes)
+        sl = Slots(self.dg, self.cr, sh, qo, None, None, None, host_queries=np.stack(rows),
+                   remove_query_edges=with_etr, group_ptr=gp if len(sh) != len(sizes) else None)
         sl.use_workspace = True
         sl.group_sizes = sizes
-        sl.h2d_bytes = int(d.numel() * 8)
         return sl
 
     def _run(self, sl: Slots, bits: int):
@@ -144,8 +172,9 @@ class Grounder:
         W = self.graph.rank_words
         n_mask, n_cnt = sl.mask_words + 1, sl.nz_total + 1
         n_arena = max(1, sl.arena_rows) * LANES * (1 if bits == 32 else 2)
-        n_bkt, n_boff = sl.S * W, sl.S * (W + 1)
-        n_state = n_mask + n_cnt + sl.S + n_bkt + 1                    # zeroed: row bitmaps | node counts | item counts | buckets | overflow
+        n_bkt = n_boff = sl.S * (W * 32 + 32)                          # per-entity item counts / offsets (RL_BUCKET_STRIDE)
+        n_pad = -(n_mask + n_cnt + sl.S) % 4                           # the bucket table is read with 16-byte loads
+        n_state = n_mask + n_cnt + sl.S + n_pad + n_bkt + 1            # zeroed: row bitmaps | node counts | item counts | buckets | overflow
         n_items = 4 * max(1, sl.item_cap)                              # int32x4 records, exact upper bound (cannot overflow)
         n_scratch = 2 * n_items + n_boff
         if getattr(sl, "use_workspace", False):
@@ -170,7 +199,7 @@ class Grounder:
         sl.overflow = sl.state[-1:]
         base = sl.state.data_ptr()
         o_cnt = n_mask
-        o_icnt, o_bkt = o_cnt + n_cnt, o_cnt + n_cnt + sl.S
+        o_icnt, o_bkt = o_cnt + n_cnt, o_cnt + n_cnt + sl.S + n_pad
         sb = scratch.data_ptr()
         sl.frontier = _lib.RlFrontier(bits, sl.arena.data_ptr(), base, base + 4 * o_cnt,
                                       sl.overflow.data_ptr(), sb, sb + 4 * n_items, sl.item_off.data_ptr(),
@@ -197,8 +226,8 @@ class Grounder:
         step of a steady-state loop triggers a cudaMalloc."""
         W = self.graph.rank_words
         n_arena = max(max(1, sl.arena_rows) * LANES for sl in slots_list)
-        n_state = max(sl.mask_words + 1 + sl.nz_total + 1 + sl.S * W + sl.S + 1 for sl in slots_list)
-        n_scratch = max(8 * max(1, sl.item_cap) + sl.S * (W + 1) for sl in slots_list)
+        n_state = max(sl.mask_words + 1 + sl.nz_total + 1 + sl.S + 3 + sl.S * (W * 32 + 32) + 1 for sl in slots_list)
+        n_scratch = max(8 * max(1, sl.item_cap) + sl.S * (W * 32 + 32) for sl in slots_list)
         for name, n in (("_ws_arena", n_arena), ("_ws_state", n_state), ("_ws_items", n_scratch)):
             cur = getattr(self, name)
             if cur is None or cur.numel() < n:

@@ -24,16 +24,51 @@ class ScoreKernels:
         self.N = grounder.graph.entity_size
         self.device = grounder.device
         self.nblk = _lib.lib().rl_softmax_blocks(self.N)
+        self._scales = {}
+
+    def slot_scale(self, S: int, value: float) -> Optional[torch.Tensor]:
+        """float32[S] filled with ``value`` (None for 1.0); cached -- the same few shapes recur every step."""
+        if value == 1.0:
+            return None
+        key = (int(S), float(value))
+        t = self._scales.get(key)
+        if t is None:
+            if len(self._scales) > 64:
+                self._scales.clear()
+            t = self._scales[key] = torch.full((S,), float(value), dtype=torch.float32, device=self.device)
+        return t
 
     # ---- kernel (2a) -------------------------------------------------------------------------
-    def predictor_scores(self, sl: Slots, w: torch.Tensor, bias: Optional[torch.Tensor], fill_neg_inf: bool):
+    def predictor_scores(self, sl: Slots, w: torch.Tensor, bias: Optional[torch.Tensor], fill_neg_inf: bool,
+                         partial: Optional[torch.Tensor] = None):
+        """partial (S*nblk*64 floats): also leave the softmax partials of every query there."""
         Z = torch.empty(sl.S, self.N, LANES, dtype=torch.float32, device=self.device)
         nzmask = torch.empty(sl.S, self.N, dtype=torch.int32, device=self.device)
         _lib.check(_lib.lib().rl_predictor_scores(
             self.dg.ref(), self.dr.ref(), sl.ref(), sl.fref(), w.data_ptr(),
             bias.data_ptr() if bias is not None else None, int(fill_neg_inf), Z.data_ptr(), nzmask.data_ptr(),
-            _stream()), "rl_predictor_scores")
+            partial.data_ptr() if partial is not None else None, _stream()), "rl_predictor_scores")
         return Z, nzmask
+
+    def predictor_train_tail(self, sl: Slots, w, bias, smoothing: float, group_ptr, n_groups: int,
+                             slot_scale: Optional[torch.Tensor], grad_w, grad_bias):
+        """aggregate -> CE -> backward of Predictor with the passes fused (rl_predictor_scores with
+        softmax partials + rl_predictor_ce_backward).  -> (group_loss, group_tsum, nzmask)."""
+        dev, S = self.device, sl.S
+        use_mask = bias is None
+        partial = torch.empty(S * self.nblk * 64, dtype=torch.float32, device=dev)
+        Z, nzmask = self.predictor_scores(sl, w, bias, use_mask, partial)
+        stats = torch.empty(S * LANES * 4, dtype=torch.float32, device=dev)
+        slot_sums = torch.empty(3 * S, dtype=torch.float32, device=dev)
+        out = torch.empty(2, n_groups, dtype=torch.float32, device=dev)
+        ans, _keep = self.dg.answers["hr2o"]
+        _lib.check(_lib.lib().rl_predictor_ce_backward(
+            self.dg.ref(), self.dr.ref(), sl.ref(), sl.fref(), C.byref(ans), float(smoothing), int(use_mask),
+            Z.data_ptr(), nzmask.data_ptr(), int(n_groups), group_ptr.data_ptr() if group_ptr is not None else None,
+            partial.data_ptr(), 1, stats.data_ptr(), slot_sums.data_ptr(), out[0].data_ptr(), out[1].data_ptr(),
+            torch.empty_like(Z).data_ptr(), slot_scale.data_ptr() if slot_scale is not None else None, grad_w.data_ptr(),
+            grad_bias.data_ptr() if grad_bias is not None else None, _stream()), "rl_predictor_ce_backward")
+        return out[0], out[1], nzmask
 
     # ---- kernel (2b) -------------------------------------------------------------------------
     def softmax_ce(self, sl: Slots, Z, nzmask, smoothing: float, use_mask: bool,

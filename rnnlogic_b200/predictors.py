@@ -163,13 +163,8 @@ class Predictor(_RuleModel):
 # ------------------------------------------------------------------------------------------------
 def _group_ptr(sl, device):
     """DEVICE int32[n_groups+1] slot ranges of the reference batches, or None when every batch fits
-    one slot (then slot == group)."""
-    sizes = sl.group_sizes
-    if all(n <= LANES for n in sizes):
-        return None, len(sizes)
-    ptr = np.zeros(len(sizes) + 1, dtype=np.int32)
-    np.cumsum([(n + LANES - 1) // LANES for n in sizes], out=ptr[1:])
-    return torch.from_numpy(ptr).to(device), len(sizes)
+    one slot (then slot == group).  The table travels with the slot descriptors (engine.Slots)."""
+    return sl.group_ptr_dev, len(sl.group_sizes)
 
 
 _POP8 = torch.tensor([bin(i).count("1") for i in range(256)], dtype=torch.float32)
@@ -194,15 +189,11 @@ def _predictor_step_on_slots(self, sk, sl, smoothing, grad_scale=1.0, bits=32, e
     gptr, ng = _group_ptr(sl, device)
     if not expanded:
         sk.gr._run(sl, bits)
-    Z, nzmask = sk.predictor_scores(sl, self.rule_weights.detach(), self.bias.detach() if use_bias else None,
-                                    not use_bias)
-    loss, tsum, G = sk.softmax_ce(sl, Z, nzmask, smoothing, not use_bias, gptr, ng, want_grad=True)
     gw = torch.zeros_like(self.rule_weights)
     gb = torch.zeros_like(self.bias) if use_bias else None
-    scale = None
-    if grad_scale != 1.0:
-        scale = torch.full((sl.S,), float(grad_scale), dtype=torch.float32, device=device)
-    sk.predictor_backward(sl, G, scale, gw, gb)
+    scale = sk.slot_scale(sl.S, grad_scale)
+    loss, tsum, nzmask = sk.predictor_train_tail(sl, self.rule_weights.detach(), self.bias.detach() if use_bias else None,
+                                                 smoothing, gptr, ng, scale, gw, gb)
     msum = None if use_bias else _group_mask_sum(sl, nzmask, ng)
     return loss, tsum, msum, gw, gb
 

@@ -15,7 +15,6 @@ sk.gr.ground(sl)
 state = sl.state.cpu().numpy()
 n_mask, n_cnt = sl.mask_words + 1, sl.nz_total + 1
 masks = state[:n_mask].view(np.uint32); cnt = state[n_mask:n_mask + n_cnt]
-ent = state[n_mask + n_cnt:n_mask + n_cnt + sl.S * kg.rank_words].view(np.uint32)
 pop = np.bitwise_count(masks)
 tot_nodes = np.zeros(4); nz_nodes = np.zeros(4); rows = np.zeros(4); vrows = np.zeros(4); chunks = np.zeros(4); nzchunks = np.zeros(4); maxrows=np.zeros(4)
 moff = 0; noff = 0
@@ -37,4 +36,3 @@ for s, q in enumerate(sl.heads):
 for d in (1, 2, 3):
     print("depth %d: nodes %d nonzero %d | rows %d valid %d (%.3f%%) max/node %d | chunks %d nonzero %d (%.2f%%)" % (
         d, tot_nodes[d], nz_nodes[d], rows[d], vrows[d], 100 * vrows[d] / max(1, rows[d]), maxrows[d], chunks[d], nzchunks[d], 100 * nzchunks[d] / max(1, chunks[d])))
-print("candidate entities per slot: mean %.1f" % (np.bitwise_count(ent).sum() / sl.S))

@@ -1,0 +1,39 @@
+"""cProfile of the host side of the pipelined end-to-end train loop (submit_train_step / ticket.result())."""
+import cProfile, pstats, sys, time, torch
+sys.path.insert(0, '/root/repo')
+import bench
+from rnnlogic_b200 import KnowledgeGraph
+from rnnlogic_b200.predictors import Predictor
+from rnnlogic_b200.optim import Adam
+shape, N, R, train, valid, test, rules = bench.build_workload()
+batches = bench.make_batches(train, R, seed=1)
+kg = KnowledgeGraph(entity_size=N, relation_size=R, train=train, valid=valid, test=test)
+m = Predictor(kg, "bias"); m.set_rules([[h] + list(b) for h, b in rules]); m = m.cuda()
+opt = Adam(m.parameters(), lr=0.005)
+per, steps = 64, 40
+lists = [batches[i * per:(i + 1) * per] for i in range(steps + 4)]
+def step(gw, gb):
+    m.rule_weights.grad, m.bias.grad = gw, gb
+    opt.step()
+def loop(n0, n1):
+    ticket = m.submit_train_step(lists[n0], 0.2, grad_scale=1.0 / per)
+    for s in range(n0, n1):
+        step(ticket.gw, ticket.gb)
+        nxt = m.submit_train_step(lists[s + 1], 0.2, grad_scale=1.0 / per)
+        ticket.result()
+        ticket = nxt
+    torch.cuda.synchronize()
+loop(0, 3)
+t0 = time.perf_counter(); loop(3, steps); t1 = time.perf_counter()
+print("wall per step %.3f ms" % ((t1 - t0) / (steps - 3) * 1e3))
+# host-only cost: the same loop without waiting for results
+def submit_only(n0, n1):
+    for s in range(n0, n1):
+        t = m.submit_train_step(lists[s], 0.2, grad_scale=1.0 / per)
+        step(t.gw, t.gb)
+torch.cuda.synchronize()
+t0 = time.perf_counter(); submit_only(3, steps); t1 = time.perf_counter()
+torch.cuda.synchronize()
+print("host enqueue per step %.3f ms" % ((t1 - t0) / (steps - 3) * 1e3))
+pr = cProfile.Profile(); pr.enable(); submit_only(3, steps); pr.disable(); torch.cuda.synchronize()
+pstats.Stats(pr).sort_stats("cumulative").print_stats(28)
