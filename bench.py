@@ -434,10 +434,10 @@ def main():
     if world > 1:
         torch.distributed.barrier()
     h2d = d2h = 0
-    for s in range(args.warmup):
-        opt.zero_grad(set_to_none=True)
-        model.fused_train_step(step_lists[s], 0.2, grad_scale=1.0 / per)
-        allreduce_and_step(model.rule_weights.grad, model.bias.grad)
+    for s in range(args.warmup):            # same pipelined API as the timed loop: warms its pinned staging buffers too
+        tk = model.submit_train_step(step_lists[s], 0.2, grad_scale=1.0 / per)
+        allreduce_and_step(tk.gw, tk.gb)
+        tk.result()
     torch.cuda.synchronize()
     if world > 1:
         torch.distributed.barrier()

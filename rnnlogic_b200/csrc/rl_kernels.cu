@@ -445,7 +445,7 @@ k_items_scan(int W, rl_frontier fr)
     if (tid == 0) fr.bucket_off[(size_t)slot * RL_BUCKET_STRIDE(W) + (size_t)W * 32] = carry;
 }
 
-#define SCATTER_BLOCKS 8
+#define SCATTER_BLOCKS 16
 __global__ void __launch_bounds__(256)
 k_items_scatter(int W, rl_frontier fr)
 {
@@ -836,6 +836,61 @@ k_predictor_bwd_items(rl_graph g, rl_rules r, rl_slots s, rl_frontier fr, const 
     }
 }
 
+// The same backward over the entity-grouped list (after rl_sort_items): one warp per 32 entities streams
+// the word's items four at a time (count row + G row of each in flight together; items of one entity hit
+// the same G row), fp32 products as the reference's x.float() * grad, one warp reduction per item.
+template <typename CT>
+__global__ void __launch_bounds__(WARPS_PER_BLOCK * 32)
+k_predictor_bwd_stream(rl_graph g, rl_rules r, rl_slots s, rl_frontier fr, const float *__restrict__ G,
+                       const float *__restrict__ slot_scale, float *__restrict__ grad_w)
+{
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int slot = blockIdx.y;
+    const int ew = blockIdx.x * WARPS_PER_BLOCK + warp;
+    const int N = g.num_entities, W = g.rank_words;
+    const int q = s.slot_head[slot];
+    const float scale = slot_scale ? slot_scale[slot] : 1.f;
+    const float *Gs = G + (size_t)slot * N * RL_LANES;
+    const int z0 = r.zr_ptr[q], z1 = r.zr_ptr[q + 1];
+    if (blockIdx.x == 0 && warp == 0 && z1 > z0) {                 // empty-body rules: count = one_hot(h)
+        const int h = s.lane_h[slot * RL_LANES + lane];
+        double v = h >= 0 ? (double)Gs[(size_t)h * RL_LANES + lane] : 0.0;
+        v = warp_sum(v);
+        if (lane == 0)
+            for (int t = z0; t < z1; ++t) atomicAdd(grad_w + r.zr_rule[t], (float)v * scale);
+    }
+    if (ew >= W) return;
+    const CT *arena = reinterpret_cast<const CT *>(fr.arena) + (size_t)s.arena_off[slot] * RL_LANES;
+    WordItems wi = load_word_items(fr, s, W, slot, ew);
+    const int B0 = __shfl_sync(FULL, wi.b0, 0), B1 = wi.wend;
+    for (int c0 = B0; c0 < B1; c0 += 32) {
+        if (c0 != wi.wbase) word_items_window(wi, c0);
+        const int cnt = min(32, B1 - c0);
+        for (int j0 = 0; j0 < cnt; j0 += 4) {
+            float pv[4];
+#pragma unroll
+            for (int u = 0; u < 4; ++u) {
+                const int src = (j0 + u) & 31;
+                const int a = __shfl_sync(FULL, wi.win.x, src);
+                const int e = __shfl_sync(FULL, wi.win.z, src);
+                const bool ok = j0 + u < cnt;
+                const CT c = ok ? arena[(size_t)a * RL_LANES + lane] : (CT)0;
+                const float gq = ok ? Gs[(size_t)e * RL_LANES + lane] : 0.f;
+                pv[u] = c != 0 ? (float)c * gq : 0.f;             // skips NaN*0 of masked cells
+            }
+#pragma unroll
+            for (int u = 0; u < 4; ++u) {
+                if (j0 + u >= cnt) break;
+                const float v = warp_sumf(pv[u]);
+                const int src = (j0 + u) & 31;
+                const int t0 = __shfl_sync(FULL, wi.win.y, src), nt = __shfl_sync(FULL, wi.win.w, src);
+                if (lane == 0 && v != 0.f)
+                    for (int t = t0; t < t0 + nt; ++t) atomicAdd(grad_w + r.node_term_rule[t], v * scale);
+            }
+        }
+    }
+}
+
 __global__ void __launch_bounds__(WARPS_PER_BLOCK * 32)
 k_bias_grad(int N, int S, const float *__restrict__ G, const float *__restrict__ slot_scale,
             float *__restrict__ grad_bias)
@@ -854,8 +909,9 @@ k_bias_grad(int N, int S, const float *__restrict__ G, const float *__restrict__
 // G[sl][e][b] = coef_b * exp(z - max_b) is written and summed into grad_bias[e] on the way.
 #define BIAS_SLOT_SPLIT 4
 __global__ void __launch_bounds__(WARPS_PER_BLOCK * 32)
-k_grad_dense_bias(int N, int S, const float *__restrict__ Z, const float *__restrict__ stats,
-                  const float *__restrict__ slot_scale, float *__restrict__ G, float *__restrict__ grad_bias)
+k_grad_dense_bias(int N, int S, const float *__restrict__ Z, const uint32_t *__restrict__ nzmask,
+                  const float *__restrict__ stats, const float *__restrict__ slot_scale, float *__restrict__ G,
+                  float *__restrict__ grad_bias)
 {
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const int e = blockIdx.x * WARPS_PER_BLOCK + warp;
@@ -867,7 +923,7 @@ k_grad_dense_bias(int N, int S, const float *__restrict__ Z, const float *__rest
         const size_t at = ((size_t)sl * N + e) * RL_LANES + lane;
         const float z = Z[at];
         const float gval = (st.w != 0.f && z != -INFINITY) ? expf(z - st.x) * st.w : 0.f;
-        G[at] = gval;
+        if (__ldg(nzmask + (size_t)sl * N + e)) G[at] = gval;      // rows without a candidate have no item: nobody reads them
         acc += (double)gval * (double)(slot_scale ? slot_scale[sl] : 1.f);
     }
     acc = warp_sum(acc);
@@ -1236,9 +1292,16 @@ int rl_softmax_ce(const rl_graph *g, const rl_slots *s, const rl_answers *ans, f
 static int launch_bwd_items(const rl_graph *g, const rl_rules *r, const rl_slots *s, const rl_frontier *fr, const float *G,
                             const float *slot_scale, float *grad_w, int sorted, cudaStream_t st)
 {
+    if (sorted) {
+        const dim3 grid((g->rank_words + WARPS_PER_BLOCK - 1) / WARPS_PER_BLOCK, s->num_slots);
+        if (fr->count_bits == 32) k_predictor_bwd_stream<uint32_t><<<grid, WARPS_PER_BLOCK * 32, 0, st>>>(*g, *r, *s, *fr, G, slot_scale, grad_w);
+        else k_predictor_bwd_stream<unsigned long long><<<grid, WARPS_PER_BLOCK * 32, 0, st>>>(*g, *r, *s, *fr, G, slot_scale, grad_w);
+        CHECK_LAUNCH("k_predictor_bwd_stream");
+        return RL_OK;
+    }
     const dim3 grid(ITEM_BLOCKS, s->num_slots);
-    if (fr->count_bits == 32) k_predictor_bwd_items<uint32_t><<<grid, WARPS_PER_BLOCK * 32, 0, st>>>(*g, *r, *s, *fr, G, slot_scale, grad_w, sorted);
-    else k_predictor_bwd_items<unsigned long long><<<grid, WARPS_PER_BLOCK * 32, 0, st>>>(*g, *r, *s, *fr, G, slot_scale, grad_w, sorted);
+    if (fr->count_bits == 32) k_predictor_bwd_items<uint32_t><<<grid, WARPS_PER_BLOCK * 32, 0, st>>>(*g, *r, *s, *fr, G, slot_scale, grad_w, 0);
+    else k_predictor_bwd_items<unsigned long long><<<grid, WARPS_PER_BLOCK * 32, 0, st>>>(*g, *r, *s, *fr, G, slot_scale, grad_w, 0);
     CHECK_LAUNCH("k_predictor_bwd_items");
     return RL_OK;
 }
@@ -1263,7 +1326,7 @@ int rl_predictor_ce_backward(const rl_graph *g, const rl_rules *r, const rl_slot
     if (rc != RL_OK) return rc;
     if (grad_bias) {
         k_grad_dense_bias<<<dim3((N + WARPS_PER_BLOCK - 1) / WARPS_PER_BLOCK, BIAS_SLOT_SPLIT), WARPS_PER_BLOCK * 32, 0, st>>>(
-            N, S, Z, stats, slot_scale, G, grad_bias);
+            N, S, Z, nzmask, stats, slot_scale, G, grad_bias);
         CHECK_LAUNCH("k_grad_dense_bias");
     } else {
         const size_t n = (size_t)N * RL_LANES;

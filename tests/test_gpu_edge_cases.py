@@ -116,3 +116,75 @@ def test_wrong_inputs_raise(world):
         PredictorPlus(kg, type="transformer")
     with pytest.raises(NotImplementedError):
         PredictorPlus(kg, aggregator="mean")
+
+
+def test_device_lookup_of_the_removed_query_edge(world):
+    """rl_prepare_slots(remove_query_edges): the query's own triple is masked iff it is a train edge -- same
+    lanes as the host look-up of its per-relation index (data.py:214-216); triples that are not in train
+    (and duplicates of a train triple) behave like the reference's index path."""
+    from rnnlogic_b200.predictors import Predictor
+    kg, okg, rules, tri = world
+    m = Predictor(kg, "bias")
+    m.set_rules(rules)
+    m = m.cuda()
+    sk = m._driver(torch.device(DEV))
+    rng = np.random.default_rng(11)
+    train_set = set(map(tuple, tri.tolist()))
+    for q in range(5):
+        own = tri[tri[:, 1] == q][:20]
+        fake = np.stack([rng.integers(kg.entity_size, size=32 - len(own)), np.full(32 - len(own), q),
+                         rng.integers(kg.entity_size, size=32 - len(own))], 1)
+        batch = np.concatenate([own, fake]).astype(np.int64)              # 32 queries: train triples and random ones
+        in_train = np.array([tuple(t) in train_set for t in batch.tolist()])
+        assert in_train[:len(own)].all()
+        idx = np.full(len(batch), -1, dtype=np.int64)                     # -1: no edge removed (not a train triple)
+        idx[in_train] = kg.edge_index_of(batch[in_train])
+        a = sk.gr.make_slots_host([batch], with_etr=True)                 # device look-up
+        b = sk.gr.make_slots_host([batch], with_etr=True, etr_lists=[idx.tolist()])   # explicit reference indices
+        assert torch.equal(a.lane.cpu(), b.lane.cpu()), q
+    # end to end: the fused step equals the step driven by explicit indices
+    batch = tri[tri[:, 1] == 0][:32].astype(np.int64)
+    sl = sk.gr.make_slots_host([batch], with_etr=True)
+    sk.gr.ground(sl)
+    Za, _ = sk.predictor_scores(sl, m.rule_weights.detach(), m.bias.detach(), False)
+    Za = Za.clone()
+    sl2 = sk.gr.make_slots_host([batch], with_etr=True, etr_lists=[kg.edge_index_of(batch).tolist()])
+    sk.gr.ground(sl2)
+    Zb, _ = sk.predictor_scores(sl2, m.rule_weights.detach(), m.bias.detach(), False)
+    assert torch.equal(Za, Zb)
+
+
+@pytest.mark.parametrize("ef", ["bias", "none"])
+def test_fused_ce_backward_equals_separate_calls(world, ef):
+    """rl_predictor_ce_backward (partials from the scores kernel, gradient + bias sweep fused) against
+    rl_softmax_ce + rl_predictor_backward on the same frontier."""
+    from rnnlogic_b200.predictors import Predictor, _group_ptr
+    kg, okg, rules, tri = world
+    torch.manual_seed(5)
+    m = Predictor(kg, ef)
+    m.set_rules(rules)
+    with torch.no_grad():
+        m.rule_weights.copy_(torch.randn(len(rules)) * 0.3)
+        if ef == "bias":
+            m.bias.copy_(torch.randn(kg.entity_size) * 0.3)
+    m = m.cuda()
+    sk = m._driver(torch.device(DEV))
+    batches = [tri[tri[:, 1] == q][:40].astype(np.int64) for q in range(5)]      # 40 > 32: groups of two slots
+    sl = sk.gr.make_slots_host(batches, with_etr=True)
+    sk.gr.ground(sl)
+    gptr, ng = _group_ptr(sl, sk.device)
+    w = m.rule_weights.detach()
+    b = m.bias.detach() if ef == "bias" else None
+    scale = sk.slot_scale(sl.S, 0.25)
+    gw1, gb1 = torch.zeros_like(w), (torch.zeros_like(b) if b is not None else None)
+    loss1, tsum1, _ = sk.predictor_train_tail(sl, w, b, 0.2, gptr, ng, scale, gw1, gb1)
+    loss1, tsum1 = loss1.clone(), tsum1.clone()
+    Z, nz = sk.predictor_scores(sl, w, b, b is None)
+    loss2, tsum2, G = sk.softmax_ce(sl, Z, nz, 0.2, b is None, gptr, ng, want_grad=True)
+    gw2, gb2 = torch.zeros_like(w), (torch.zeros_like(b) if b is not None else None)
+    sk.predictor_backward(sl, G, scale, gw2, gb2)
+    np.testing.assert_allclose(loss1.cpu().numpy(), loss2.cpu().numpy(), rtol=1e-6, atol=1e-7)
+    np.testing.assert_array_equal(tsum1.cpu().numpy(), tsum2.cpu().numpy())
+    np.testing.assert_allclose(gw1.cpu().numpy(), gw2.cpu().numpy(), rtol=1e-5, atol=1e-7)
+    if b is not None:
+        np.testing.assert_allclose(gb1.cpu().numpy(), gb2.cpu().numpy(), rtol=1e-5, atol=1e-7)
