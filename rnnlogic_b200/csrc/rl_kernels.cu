@@ -905,29 +905,42 @@ k_bias_grad(int N, int S, const float *__restrict__ G, const float *__restrict__
     if (lane == 0) grad_bias[e] += (float)acc;
 }
 
-// k_grad_dense and the dense part of k_bias_grad in one sweep over Z (a warp = one entity, looping over slots):
-// G[sl][e][b] = coef_b * exp(z - max_b) is written and summed into grad_bias[e] on the way.
-#define BIAS_SLOT_SPLIT 4
+// k_grad_dense and the dense part of k_bias_grad in one sweep over Z: a warp owns BIAS_ROWS consecutive
+// entities (1 KB of contiguous logits per slot) and loops over slots, so the per-query (max, coefficient)
+// pair is loaded once per slot and warp instead of once per row; G[sl][e][b] = coef_b * exp(z - max_b) is
+// written and summed into grad_bias[e] on the way.
+#define BIAS_SLOT_SPLIT 16
+#define BIAS_ROWS 8
 __global__ void __launch_bounds__(WARPS_PER_BLOCK * 32)
-k_grad_dense_bias(int N, int S, const float *__restrict__ Z, const uint32_t *__restrict__ nzmask,
-                  const float *__restrict__ stats, const float *__restrict__ slot_scale, float *__restrict__ G,
-                  float *__restrict__ grad_bias)
+k_grad_dense_bias(int N, int S, const float *__restrict__ Z, const float *__restrict__ stats,
+                  const float *__restrict__ slot_scale, float *__restrict__ G, float *__restrict__ grad_bias)
 {
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    const int e = blockIdx.x * WARPS_PER_BLOCK + warp;
-    if (e >= N) return;
-    double acc = 0.0;
-#pragma unroll 8
+    const int e0 = (blockIdx.x * WARPS_PER_BLOCK + warp) * BIAS_ROWS;
+    if (e0 >= N) return;
+    const int ne = min(BIAS_ROWS, N - e0);
+    double acc[BIAS_ROWS];
+#pragma unroll
+    for (int u = 0; u < BIAS_ROWS; ++u) acc[u] = 0.0;
     for (int sl = blockIdx.y; sl < S; sl += BIAS_SLOT_SPLIT) {
         const float4 st = __ldg(reinterpret_cast<const float4 *>(stats) + (size_t)sl * 32 + lane);
-        const size_t at = ((size_t)sl * N + e) * RL_LANES + lane;
-        const float z = Z[at];
-        const float gval = (st.w != 0.f && z != -INFINITY) ? expf(z - st.x) * st.w : 0.f;
-        if (__ldg(nzmask + (size_t)sl * N + e)) G[at] = gval;      // rows without a candidate have no item: nobody reads them
-        acc += (double)gval * (double)(slot_scale ? slot_scale[sl] : 1.f);
+        const float sc = slot_scale ? slot_scale[sl] : 1.f;
+        const size_t at = ((size_t)sl * N + e0) * RL_LANES + lane;
+        float z[BIAS_ROWS];
+#pragma unroll
+        for (int u = 0; u < BIAS_ROWS; ++u) z[u] = u < ne ? Z[at + (size_t)u * RL_LANES] : -INFINITY;
+#pragma unroll
+        for (int u = 0; u < BIAS_ROWS; ++u) {
+            const float gval = (st.w != 0.f && z[u] != -INFINITY) ? expf(z[u] - st.x) * st.w : 0.f;
+            if (u < ne) G[at + (size_t)u * RL_LANES] = gval;
+            acc[u] += (double)(gval * sc);
+        }
     }
-    acc = warp_sum(acc);
-    if (lane == 0) atomicAdd(grad_bias + e, (float)acc);
+#pragma unroll
+    for (int u = 0; u < BIAS_ROWS; ++u) {
+        const double v = warp_sum(acc[u]);
+        if (lane == 0 && u < ne) atomicAdd(grad_bias + e0 + u, (float)v);
+    }
 }
 
 // ------------------------------------------------------------------------------------------
@@ -1325,8 +1338,9 @@ int rl_predictor_ce_backward(const rl_graph *g, const rl_rules *r, const rl_slot
                         slot_sums, group_loss, group_tsum, st);
     if (rc != RL_OK) return rc;
     if (grad_bias) {
-        k_grad_dense_bias<<<dim3((N + WARPS_PER_BLOCK - 1) / WARPS_PER_BLOCK, BIAS_SLOT_SPLIT), WARPS_PER_BLOCK * 32, 0, st>>>(
-            N, S, Z, nzmask, stats, slot_scale, G, grad_bias);
+        const int rows_per_block = WARPS_PER_BLOCK * BIAS_ROWS;
+        k_grad_dense_bias<<<dim3((N + rows_per_block - 1) / rows_per_block, BIAS_SLOT_SPLIT), WARPS_PER_BLOCK * 32, 0, st>>>(
+            N, S, Z, stats, slot_scale, G, grad_bias);
         CHECK_LAUNCH("k_grad_dense_bias");
     } else {
         const size_t n = (size_t)N * RL_LANES;
