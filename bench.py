@@ -443,12 +443,15 @@ def main():
         torch.distributed.barrier()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     e0.record()
-    # software pipeline: step k+1 is packed / copied / enqueued while step k runs; every step still
-    # does its own H2D of the queries and its own D2H read of the losses
+    # software pipeline: step k+1 is packed / copied / grounded while step k's gradients are exchanged (grounding
+    # does not depend on the parameters); every step still does its own H2D of the queries and its own D2H
+    # read of the losses
     ticket = model.submit_train_step(step_lists[args.warmup], 0.2, grad_scale=1.0 / per)
     for s in range(args.warmup, n_steps):
-        allreduce_and_step(ticket.gw, ticket.gb)
-        nxt = model.submit_train_step(step_lists[s + 1], 0.2, grad_scale=1.0 / per) if s + 1 < n_steps else None
+        pending = start_allreduce(ticket.gw, ticket.gb)
+        prep = model.prepare_train_step(step_lists[s + 1]) if s + 1 < n_steps else None
+        finish_step(pending)
+        nxt = prep.finish(0.2, grad_scale=1.0 / per) if prep is not None else None
         loss, tsum = ticket.result()
         assert torch.isfinite(loss).all()
         h2d += ticket.h2d_bytes

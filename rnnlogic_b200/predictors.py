@@ -224,17 +224,39 @@ class _StepTicket:
         return host[:ng], host[ng:2 * ng]
 
 
+class _PreparedStep:
+    """The parameter-independent half of a fused train step, already enqueued: host pack -> one H2D ->
+    slot preparation -> frontier expansion.  ``finish()`` enqueues the parameter-dependent half."""
+
+    def __init__(self, model, sk, sl, batches, bits):
+        self.model, self.sk, self.sl, self.batches, self.bits = model, sk, sl, batches, bits
+
+    def finish(self, smoothing, grad_scale=1.0):
+        """aggregate -> CE -> backward -> async D2H of the losses; returns the step's ticket."""
+        model, sk, sl = self.model, self.sk, self.sl
+        use_bias = model.entity_feature == "bias"
+        loss, tsum, msum, gw, gb = _predictor_step_on_slots(model, sk, sl, smoothing, grad_scale, self.bits, expanded=True)
+        parts = [loss, tsum] + ([msum] if msum is not None else [])
+        pack = torch.cat(parts + [sl.overflow.float()])
+        return _StepTicket(model, sk, sl, self.batches, smoothing, grad_scale, pack, gw, gb, len(self.batches), use_bias)
+
+
+def _predictor_prepare_train(self, batches):
+    """Enqueue everything of a fused train step that does not depend on the parameters (grounding) and
+    return a handle; ``handle.finish(smoothing, grad_scale)`` enqueues the rest.  A data-parallel loop calls
+    this for step k+1 while the gradient all-reduce of step k is in flight."""
+    device = self.rule_weights.device
+    sk = self._driver(device)
+    sl = sk.gr.make_slots_host(batches, with_etr=True)
+    bits = sk.gr.force_bits or 32
+    sk.gr._run(sl, bits)
+    return _PreparedStep(self, sk, sl, batches, bits)
+
+
 def _predictor_submit_train(self, batches, smoothing, grad_scale=1.0):
     """Enqueue one fused train step (host pack -> H2D -> kernels -> async D2H) and return a ticket; the
     gradients are in ticket.gw / ticket.gb (device).  Lets the host prepare step k+1 while step k runs."""
-    device = self.rule_weights.device
-    sk = self._driver(device)
-    use_bias = self.entity_feature == "bias"
-    sl = sk.gr.make_slots_host(batches, with_etr=True)
-    loss, tsum, msum, gw, gb = _predictor_step_on_slots(self, sk, sl, smoothing, grad_scale, sk.gr.force_bits or 32)
-    parts = [loss, tsum] + ([msum] if msum is not None else [])
-    pack = torch.cat(parts + [sl.overflow.float()])
-    return _StepTicket(self, sk, sl, batches, smoothing, grad_scale, pack, gw, gb, len(batches), use_bias)
+    return _predictor_prepare_train(self, batches).finish(smoothing, grad_scale)
 
 
 def _predictor_fused_train(self, batches, smoothing, grad_scale=1.0):
@@ -287,6 +309,7 @@ def _valid_lanes(sl, LH):
 
 Predictor.fused_train_step = _predictor_fused_train
 Predictor.submit_train_step = _predictor_submit_train
+Predictor.prepare_train_step = _predictor_prepare_train
 Predictor.step_on_slots = _predictor_step_on_slots
 Predictor.fused_rank = _predictor_fused_rank
 

@@ -176,3 +176,24 @@ def test_adam_kernel_matches_torch():
             ob.step()
         for x, y in zip(a, b):
             np.testing.assert_allclose(x.detach().cpu().numpy(), y.detach().cpu().numpy(), rtol=2e-6, atol=2e-7)
+
+
+@pytest.mark.parametrize("ef", ["bias", "none"])
+def test_pipelined_step_api_matches_reference(ds, ef):
+    """prepare_train_step (grounding enqueued ahead) + finish + ticket.result(), two steps in flight,
+    against the reference's per-batch loss and gradients."""
+    name, fx, kg = ds
+    m = make_predictor(fx, kg, ef)
+    js = [j for j in range(5) if "pred_%s_tb%d_loss" % (ef, j) in fx][:2]
+    if len(js) < 2:
+        pytest.skip("fixture holds fewer than two train batches")
+    batches = [np.asarray(G.train_batch_inputs(fx, j)[0], dtype=np.int64) for j in js]
+    t0 = m.submit_train_step([batches[0]], 0.2)
+    p1 = m.prepare_train_step([batches[1]])              # grounding of step 1 enqueued before step 0 is read back
+    t1 = p1.finish(0.2)
+    for t, j in ((t0, js[0]), (t1, js[1])):
+        loss, tsum = t.result()
+        np.testing.assert_allclose(loss[0].item(), fx["pred_%s_tb%d_loss" % (ef, j)], rtol=1e-5)
+        np.testing.assert_allclose(t.gw.cpu().numpy(), fx["pred_%s_tb%d_gw" % (ef, j)], rtol=1e-4, atol=1e-6)
+        if ef == "bias":
+            np.testing.assert_allclose(t.gb.cpu().numpy(), fx["pred_bias_tb%d_gb" % j], rtol=1e-4, atol=1e-7)
