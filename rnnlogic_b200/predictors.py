@@ -219,7 +219,8 @@ class _StepTicket:
         ng = self.ng
         if host[-1].item() != 0:
             raise _lib.RlError("a path count overflowed 32 bits inside an enqueued step; rerun the step with "
-                               "model.fused_train_step (it falls back to exact 64-bit rows)")
+                               "model.fused_train_step (it falls back to exact 64-bit rows; TrainerPredictor: "
+                               "set trainer.pipelined = False)")
         self.model.last_mask_sum = None if self.use_bias else host[2 * ng:3 * ng].tolist()
         return host[:ng], host[ng:2 * ng]
 

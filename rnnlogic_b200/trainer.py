@@ -57,6 +57,8 @@ def allreduce_mean_grads(params, world_size):
 
 class TrainerPredictor(object):
     slots_per_step = 1      # train batches per optimizer step (1 = the reference's schedule)
+    pipelined = True        # Predictor(bias): enqueue step i+1 before reading step i back (a 32-bit count overflow
+                            # then aborts with RlError instead of falling back to 64-bit rows; set False to get the fallback)
     eval_batches_per_call = 64
 
     def __init__(self, model, train_set, valid_set, test_set, optimizer, scheduler=None, gpus=None, num_worker=0):
@@ -107,15 +109,32 @@ class TrainerPredictor(object):
         use_mask = getattr(model, "entity_feature", "bias") not in ("bias", "RotatE")
         N = self.train_set.graph.entity_size
         done = 0
-        for s0 in range(0, len(order), k):
-            batches = [self.train_set.batch_arrays[i] for i in order[s0:s0 + k]]
+        steps = [[self.train_set.batch_arrays[i] for i in order[s0:s0 + k]] for s0 in range(0, len(order), k)]
+        # Predictor with a bias feature: software pipeline.  The grounding of step i+1 (parameter-independent)
+        # is enqueued before the gradient exchange of step i, and the host reads step i's losses only after
+        # step i+1 is on the stream.  (In mask mode the optimizer step depends on a host-side candidate count,
+        # trainer.py:87, so those models take the synchronous path.)
+        pipelined = self.pipelined and hasattr(model, "prepare_train_step") and not use_mask
+        ticket = None
+        if pipelined and steps:
+            ticket = model.prepare_train_step(steps[0]).finish(smoothing, grad_scale=1.0 / len(steps[0]))
+        for si, batches in enumerate(steps):
             self.optimizer.zero_grad(set_to_none=True)
-            loss, tsum = model.fused_train_step(batches, smoothing, grad_scale=1.0 / len(batches))
-            cand = getattr(model, "last_mask_sum", None)          # per-batch mask.sum() in mask mode
-            skip = use_mask and cand is not None and all(c == 0 for c in cand)
-            self._allreduce_grads()
-            if not skip:                                          # trainer.py:87: no candidates -> no step
+            if pipelined:
+                prep = model.prepare_train_step(steps[si + 1]) if si + 1 < len(steps) else None
+                model.rule_weights.grad, model.bias.grad = ticket.gw, ticket.gb
+                self._allreduce_grads()
                 self.optimizer.step()
+                nxt = prep.finish(smoothing, grad_scale=1.0 / len(steps[si + 1])) if prep is not None else None
+                loss, tsum = ticket.result()
+                ticket, cand = nxt, None
+            else:
+                loss, tsum = model.fused_train_step(batches, smoothing, grad_scale=1.0 / len(batches))
+                cand = getattr(model, "last_mask_sum", None)          # per-batch mask.sum() in mask mode
+                skip = use_mask and cand is not None and all(c == 0 for c in cand)
+                self._allreduce_grads()
+                if not skip:                                          # trainer.py:87: no candidates -> no step
+                    self.optimizer.step()
             self.optimizer.zero_grad(set_to_none=True)
             for j, b in enumerate(batches):
                 msum = float(cand[j]) if (use_mask and cand is not None) else float(len(b) * N)
