@@ -102,3 +102,32 @@ predictor:
     assert dict(cfg.predictor.optimizer) == {"lr": 0.005, "weight_decay": 0}
     save_config(cfg, str(tmp_path))
     assert os.path.exists(tmp_path / "config.yaml")
+
+
+@gpu
+@pytest.mark.parametrize("per_step", [1, 3])
+def test_pipelined_train_loop_equals_synchronous(per_step, tmp_path):
+    """TrainerPredictor.train for Predictor(bias): the software-pipelined loop (next step grounded before the
+    gradient exchange, losses read one step late) ends with the same parameters as the step-by-step loop."""
+    from rnnlogic_b200.data import KnowledgeGraph, TrainDataset, ValidDataset, TestDataset
+    from rnnlogic_b200.predictors import Predictor
+    from rnnlogic_b200.trainer import TrainerPredictor
+    from rnnlogic_b200.utils import set_seed
+    fx = G.load("umls")
+    d = str(tmp_path / "umls")
+    write_dataset_dir(d, fx)
+    out = []
+    for pipelined in (True, False):
+        set_seed(3)
+        graph = KnowledgeGraph(d)
+        sets = TrainDataset(graph, 32), ValidDataset(graph, 32), TestDataset(graph, 32)
+        model = Predictor(graph, entity_feature="bias")
+        model.set_rules(G.rules_of(fx))
+        optim = torch.optim.Adam(model.parameters(), lr=0.01)
+        solver = TrainerPredictor(model, *sets, optim, gpus=[0])
+        solver.pipelined, solver.slots_per_step = pipelined, per_step
+        solver.train(batch_per_epoch=14, smoothing=0.2, print_every=5)
+        out.append({k: v.detach().cpu().numpy().copy() for k, v in model.state_dict().items()})
+    for k in out[0]:
+        assert np.abs(out[0][k]).max() > 0
+        np.testing.assert_allclose(out[0][k], out[1][k], rtol=1e-4, atol=1e-6, err_msg=k)
