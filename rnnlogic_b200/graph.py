@@ -11,6 +11,7 @@ from __future__ import annotations
 
 import ctypes as C
 import os
+import zlib
 from collections import OrderedDict
 from typing import Dict, List, Optional, Sequence
 
@@ -83,12 +84,19 @@ class DeviceGraph:
 
 
 class KnowledgeGraph(object):
+    _CACHE_VERSION = 1
+    _FILES = ("entities.dict", "relations.dict", "train.txt", "valid.txt", "test.txt")
+
     def __init__(self, data_path: Optional[str] = None, *, entity_size: Optional[int] = None,
-                 relation_size: Optional[int] = None, train=None, valid=None, test=None):
+                 relation_size: Optional[int] = None, train=None, valid=None, test=None, cache: Optional[str] = None):
         """``KnowledgeGraph(data_path)`` reads entities.dict / relations.dict / {train,valid,test}.txt
         exactly like src/data.py:10-108.  The keyword form builds the same object from integer
-        id arrays [E,3] of (h, r, t) (synthetic graphs, tests)."""
+        id arrays [E,3] of (h, r, t) (synthetic graphs, tests).
+        cache (or $RNNLOGIC_B200_KG_CACHE): a directory for a binary image of the parsed triples and the
+        device tables (DCSR, rank tables), keyed by the dataset files' sizes and mtimes -- a second
+        construction then skips the text parse and every sort."""
         self.data_path = data_path
+        self._cache_dir = cache or os.environ.get("RNNLOGIC_B200_KG_CACHE") or None
         self.entity2id, self.relation2id, self.id2entity, self.id2relation = {}, {}, {}, {}
         if data_path is not None:
             with open(os.path.join(data_path, "entities.dict")) as fi:
@@ -103,8 +111,13 @@ class KnowledgeGraph(object):
                     self.id2relation[int(i)] = name
             self.entity_size = len(self.entity2id)
             self.relation_size = len(self.relation2id)
-            train, valid, test = _load_triples_native(data_path, self.entity_size, self.relation_size)
+            cached = self._cache_load()
+            if cached is None:
+                train, valid, test = _load_triples_native(data_path, self.entity_size, self.relation_size)
+            else:
+                train, valid, test = cached["train"], cached["valid"], cached["test"]
         else:
+            cached = None
             self.entity_size = int(entity_size)
             self.relation_size = int(relation_size)
             train = np.asarray(train, dtype=np.int64).reshape(-1, 3)
@@ -117,9 +130,55 @@ class KnowledgeGraph(object):
         self._ht2index = None
         self._devices: Dict[str, DeviceGraph] = {}
         self._chains: "OrderedDict[tuple, object]" = OrderedDict()
-        self._build_host()
+        if cached is None:
+            self._build_host()
+            self._cache_store()
+        else:
+            self._adopt_host(cached)
         if data_path is not None:
             print("Data loading | DONE!")
+
+    # ---- binary image of a parsed dataset ----
+    def _cache_key(self):
+        st = [os.stat(os.path.join(self.data_path, f)) for f in self._FILES]
+        return np.array([self._CACHE_VERSION, self.entity_size, self.relation_size]
+                        + [v for x in st for v in (x.st_size, x.st_mtime_ns)], dtype=np.int64)
+
+    def _cache_path(self):
+        tag = "%08x" % (zlib.crc32(os.path.abspath(self.data_path).encode()) & 0xFFFFFFFF)
+        return os.path.join(self._cache_dir, "kg_%s_%s.npz" % (os.path.basename(os.path.normpath(self.data_path)), tag))
+
+    def _cache_load(self):
+        if not self._cache_dir or self.data_path is None:
+            return None
+        try:
+            with np.load(self._cache_path()) as z:
+                if not np.array_equal(z["key"], self._cache_key()):
+                    return None                                  # a dataset file changed: rebuild
+                return {k: z[k] for k in z.files}
+        except (OSError, KeyError, ValueError):
+            return None
+
+    def _cache_store(self):
+        if not self._cache_dir or self.data_path is None:
+            return
+        blob = {"key": self._cache_key(), "train": self.train_array, "valid": self.valid_array, "test": self.test_array,
+                "train_edge_index": self.train_edge_index, "rel_edges": self.rel_edges, "rel_rows": self.rel_rows,
+                "rel_sources": self.rel_sources}
+        blob.update({"host_" + k: v for k, v in self.host.items()})
+        try:
+            os.makedirs(self._cache_dir, exist_ok=True)
+            tmp = self._cache_path() + ".tmp%d.npz" % os.getpid()
+            np.savez(tmp, **blob)
+            os.replace(tmp, self._cache_path())                  # atomic: concurrent ranks never see a partial file
+        except OSError:
+            pass                                                 # read-only location: the cache is optional
+
+    def _adopt_host(self, z):
+        self.train_edge_index = z["train_edge_index"]
+        self.rel_edges, self.rel_rows, self.rel_sources = z["rel_edges"], z["rel_rows"], z["rel_sources"]
+        self.rank_words = (self.entity_size + 31) // 32
+        self.host = {k[len("host_"):]: z[k] for k in z if k.startswith("host_")}
 
     # ---- reference-compatible attributes (lazy: Python lists/dicts are slow at 2e7 edges) ----
     def _facts(self, name):

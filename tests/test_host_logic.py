@@ -284,3 +284,44 @@ def test_native_dataset_loader(tmp_path):
     dt = time.perf_counter() - t0
     assert np.array_equal(train, tri) and valid.shape == (0, 3)
     assert dt < 5.0, dt
+
+
+def test_binary_kg_cache(tmp_path, monkeypatch):
+    """KnowledgeGraph(data_path, cache=dir): the second construction adopts the binary image (no parse, no
+    sort) and is identical; touching a dataset file invalidates it; a read-only location is ignored."""
+    from rnnlogic_b200 import KnowledgeGraph
+    from rnnlogic_b200 import graph as graph_mod
+    fx = G.load("syn")
+    N, R = int(fx["N"]), int(fx["R"])
+    d = tmp_path / "ds"
+    d.mkdir()
+    (d / "entities.dict").write_text("".join("%d\te%d\n" % (i, i) for i in range(N)))
+    (d / "relations.dict").write_text("".join("%d\tr%d\n" % (i, i) for i in range(R)))
+    for split in ("train", "valid", "test"):
+        (d / (split + ".txt")).write_text("".join("e%d\tr%d\te%d\n" % tuple(x) for x in fx[split].tolist()))
+    cache = tmp_path / "cache"
+    a = KnowledgeGraph(str(d), cache=str(cache))
+    files = list(cache.glob("kg_*.npz"))
+    assert len(files) == 1
+    calls = {"n": 0}
+    real = graph_mod._load_triples_native
+    monkeypatch.setattr(graph_mod, "_load_triples_native", lambda *x: (calls.__setitem__("n", calls["n"] + 1), real(*x))[1])
+    monkeypatch.setattr(KnowledgeGraph, "_build_host", lambda self: (_ for _ in ()).throw(AssertionError("rebuilt")))
+    b = KnowledgeGraph(str(d), cache=str(cache))                       # adopted: neither parsed nor rebuilt
+    assert calls["n"] == 0
+    for k in a.host:
+        assert a.host[k].dtype == b.host[k].dtype and np.array_equal(a.host[k], b.host[k]), k
+    for attr in ("train_array", "valid_array", "test_array", "train_edge_index", "rel_edges", "rel_rows", "rel_sources"):
+        assert np.array_equal(getattr(a, attr), getattr(b, attr)), attr
+    assert b.rank_words == a.rank_words and b.entity2id["e3"] == 3 and b.hr2o == a.hr2o
+    assert np.array_equal(b.edge_index_of(fx["train"][:50]), a.edge_index_of(fx["train"][:50]))
+    monkeypatch.undo()
+    # one more train triple -> the key changes -> rebuilt and re-stored
+    with open(d / "train.txt", "a") as f:
+        f.write("e0\tr0\te%d\n" % (N - 1))
+    c = KnowledgeGraph(str(d), cache=str(cache))
+    assert c.train_array.shape[0] == a.train_array.shape[0] + 1
+    # environment variable form
+    monkeypatch.setenv("RNNLOGIC_B200_KG_CACHE", str(tmp_path / "cache2"))
+    KnowledgeGraph(str(d))
+    assert len(list((tmp_path / "cache2").glob("kg_*.npz"))) == 1
