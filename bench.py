@@ -220,6 +220,7 @@ def main():
     ap.add_argument("--steps", type=int, default=100)
     ap.add_argument("--warmup", type=int, default=5)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--trace-e2e", action="store_true", help="print the host-side time of every end-to-end step to stderr")
     ap.add_argument("--batches", type=int, default=256, help="reference batches (of <=32 queries) per step per GPU")
     ap.add_argument("--dense", action="store_true", help="expand every row of every trie node (dense SpMM; roofline mode)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
@@ -447,12 +448,16 @@ def main():
     # does not depend on the parameters); every step still does its own H2D of the queries and its own D2H
     # read of the losses
     ticket = model.submit_train_step(step_lists[args.warmup], 0.2, grad_scale=1.0 / per)
+    trace = []                                      # --trace-e2e: host wall time of (enqueue, wait) per step
     for s in range(args.warmup, n_steps):
+        t_a = time.perf_counter()
         pending = start_allreduce(ticket.gw, ticket.gb)
         prep = model.prepare_train_step(step_lists[s + 1]) if s + 1 < n_steps else None
         finish_step(pending)
         nxt = prep.finish(0.2, grad_scale=1.0 / per) if prep is not None else None
+        t_b = time.perf_counter()
         loss, tsum = ticket.result()
+        trace.append((t_b - t_a, time.perf_counter() - t_b))
         assert torch.isfinite(loss).all()
         h2d += ticket.h2d_bytes
         d2h += ticket.d2h_bytes
@@ -464,6 +469,8 @@ def main():
     if world > 1:
         torch.distributed.all_reduce(te, op=torch.distributed.ReduceOp.MAX)
     e2e_value = float(qt.item()) / (float(te.item()) / 1e3)
+    if args.trace_e2e and rank == 0:
+        print("e2e per step, host enqueue/wait ms: " + " ".join("%.2f/%.2f" % (a * 1e3, b * 1e3) for a, b in trace), file=sys.stderr)
 
     clk = clocks.stop() if rank == 0 else None      # sampled over all timed regions (value, dense roofline, e2e)
     if world > 1:

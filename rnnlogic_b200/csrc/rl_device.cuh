@@ -17,6 +17,9 @@
 #ifndef SCORE_ROWS
 #define SCORE_ROWS 4            // count rows a k_predictor_scores warp keeps in flight (8 spills at 64 registers)
 #endif
+#ifndef BWD_ROWS
+#define BWD_ROWS 8               // (count row, G row) pairs a k_predictor_bwd_stream warp keeps in flight
+#endif
 #define CE_WARPS 32             // k_ce_finalize / k_grad_sparse: one warp per query lane of the slot
 
 // error state + launch counter live in rl_kernels.cu

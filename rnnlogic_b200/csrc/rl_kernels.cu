@@ -477,13 +477,13 @@ k_predictor_scores(rl_graph g, rl_rules r, rl_slots s, rl_frontier fr, const flo
                    uint32_t *__restrict__ nzmask, float *__restrict__ partial)
 {
     __shared__ float sm_m[SCORE_WARPS_MAX][32];
-    __shared__ double sm_s[SCORE_WARPS_MAX][32];
+    __shared__ float sm_s[SCORE_WARPS_MAX][32];
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nwarps = blockDim.x >> 5;
     const int slot = blockIdx.y;
     const int ew = blockIdx.x * nwarps + warp;                    // entity word
     const int N = g.num_entities, W = g.rank_words;
     float run_m = -INFINITY;                                      // online softmax of the lane's query over the warp's rows
-    double run_s = 0.0;
+    float run_s = 0.f;
     if (ew < W) {
     const int q = s.slot_head[slot];
     const CT *arena = reinterpret_cast<const CT *>(fr.arena) + (size_t)s.arena_off[slot] * RL_LANES;
@@ -505,8 +505,9 @@ k_predictor_scores(rl_graph g, rl_rules r, rl_slots s, rl_frontier fr, const flo
         const uint32_t bits = __ballot_sync(FULL, any);
         if (lane == i) my_bits = bits;
         if (partial && z != -INFINITY) {
-            if (z > run_m) { run_s = run_s * (double)expf(run_m - z) + 1.0; run_m = z; }
-            else run_s += (double)expf(z - run_m);
+            const float mn = fmaxf(run_m, z);                     // branch-free online softmax (<= 32 rows per warp, fp32)
+            run_s = run_s * expf(run_m - mn) + expf(z - mn);
+            run_m = mn;
         }
     };
     WordItems wi = load_word_items(fr, s, W, slot, ew);
@@ -524,7 +525,7 @@ k_predictor_scores(rl_graph g, rl_rules r, rl_slots s, rl_frontier fr, const flo
     if (partial && !fill_neg_inf && fast) {
         const bool mine = (fast >> lane) & 1u;
         run_m = warp_maxf(mine ? bias_l : -INFINITY);
-        run_s = (double)warp_sumf(mine ? expf(bias_l - run_m) : 0.f);
+        run_s = warp_sumf(mine ? expf(bias_l - run_m) : 0.f);
     }
     // The word's items are one contiguous, entity-grouped range: stream it SCORE_ROWS rows at a time (the
     // count rows and rule weights of a group are all in flight together, whatever entities they belong
@@ -866,10 +867,10 @@ k_predictor_bwd_stream(rl_graph g, rl_rules r, rl_slots s, rl_frontier fr, const
     for (int c0 = B0; c0 < B1; c0 += 32) {
         if (c0 != wi.wbase) word_items_window(wi, c0);
         const int cnt = min(32, B1 - c0);
-        for (int j0 = 0; j0 < cnt; j0 += 4) {
-            float pv[4];
+        for (int j0 = 0; j0 < cnt; j0 += BWD_ROWS) {
+            float pv[BWD_ROWS];
 #pragma unroll
-            for (int u = 0; u < 4; ++u) {
+            for (int u = 0; u < BWD_ROWS; ++u) {
                 const int src = (j0 + u) & 31;
                 const int a = __shfl_sync(FULL, wi.win.x, src);
                 const int e = __shfl_sync(FULL, wi.win.z, src);
@@ -879,7 +880,7 @@ k_predictor_bwd_stream(rl_graph g, rl_rules r, rl_slots s, rl_frontier fr, const
                 pv[u] = c != 0 ? (float)c * gq : 0.f;             // skips NaN*0 of masked cells
             }
 #pragma unroll
-            for (int u = 0; u < 4; ++u) {
+            for (int u = 0; u < BWD_ROWS; ++u) {
                 if (j0 + u >= cnt) break;
                 const float v = warp_sumf(pv[u]);
                 const int src = (j0 + u) & 31;
@@ -1178,7 +1179,7 @@ int rl_expand_level(const rl_graph *g, const rl_rules *r, const rl_slots *s, int
     CHECK_LAUNCH("k_symbolic");
     // chunks per warp: many when most chunks are empty (one coalesced read of their bitmap words),
     // few when every chunk is expanded (more warps in flight to hide the look-up latency)
-    int cpw = force_dense ? 4 : 8;
+    int cpw = force_dense ? 4 : 16;
     if (const char *e = getenv("RL_CPW")) { int v = atoi(e); if (v >= 1 && v <= 32) cpw = v; }
     dim3 grid((grid_chunks + WARPS_PER_BLOCK * cpw - 1) / (WARPS_PER_BLOCK * cpw), s->num_slots);
     // force_dense: plain dense SpMM -- every row of every node is written (zeros included) and read
@@ -1229,8 +1230,8 @@ static int score_warps()
     static int v = 0;
     if (!v) {
         const char *e = getenv("RL_SCORE_WARPS");
-        v = e ? atoi(e) : 8;
-        if (v < 1 || v > SCORE_WARPS_MAX) v = 8;
+        v = e ? atoi(e) : 4;                                   // 4 beat 8 by 2 % (shorter block tails)
+        if (v < 1 || v > SCORE_WARPS_MAX) v = 4;
     }
     return v;
 }
