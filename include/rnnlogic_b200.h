@@ -295,6 +295,28 @@ int rl_plus_backward(const rl_graph *g, const rl_rules *r, const rl_slots *s, co
 int rl_rule_stats(const rl_graph *g, const rl_rules *r, const rl_slots *s, const rl_frontier *fr,
                   int32_t max_terms, double *sum_cnt, double *pos_cnt, void *stream);
 
+/* LSTM rule encoder of PredictorPlus (src/predictors.py:141,201-208: torch.nn.LSTM(H, H, L, batch_first=True)
+ * over the embedded [head, body..., pad] tokens, output of the last non-pad position).  x[n][T][H] embedded
+ * tokens, len[n] (>= 1) non-pad tokens per rule, weights = HOST array of 4*L device pointers
+ * (weight_ih, weight_hh, bias_ih, bias_hh per layer; torch layout [4H][H], gate order i, f, g, o).
+ * H in {16, 32}, L <= RL_RNN_MAX_LAYERS.  Forward: out[n][H]; acts[n][L][T][5][H] (i, f, g, o, c) and
+ * ih[L][n][T][2H] ([input of layer l at step t | its hidden state of step t-1]) are kept for the backward --
+ * zero-filled by the caller, steps behind len stay zero.
+ * Backward: dG[L][n][T][4H] (pre-activation gate gradients) and dX[n][T][H], zero-filled by the caller; the
+ * weight gradients are the reductions [dW_ih[l] | dW_hh[l]] = dG[l]^T ih[l], db[l] = sum dG[l], left to the
+ * caller's (batched) GEMM. */
+#define RL_RNN_MAX_LAYERS 4
+int rl_lstm_encode_forward(int32_t n, int32_t T, int32_t H, int32_t L, const float *x, const int32_t *len,
+                           const float *const *weights, float *acts, float *ih, float *out, void *stream);
+int rl_lstm_encode_backward(int32_t n, int32_t T, int32_t H, int32_t L, const int32_t *len,
+                            const float *const *weights, const float *acts, const float *dout, float *dG,
+                            float *dX, void *stream);
+/* The weight-gradient reductions of the encoder: dW[L][4H][2H] += dG[l]^T ih[l] over the M = n*T rows,
+ * db[L][4H] += column sums of dG[l] (both zero-filled by the caller; K ~ 1e5 with 64 x 32 outputs is no shape
+ * for a library GEMM). */
+int rl_lstm_encode_wgrad(int64_t M, int32_t H, int32_t L, const float *dG, const float *ih, float *dW,
+                         float *db, void *stream);
+
 /* Fused dense tail of PredictorPlus with the `sum` aggregator, one thread per candidate cell
  * (src/layers.py:73-75: Linear(H,H) -> LayerNorm -> ReLU; src/predictors.py:253-255: concat with
  * relation_emb[head], Linear(2H,J) -> ReLU -> Linear(J,1)).  F[C][H] from rl_plus_features,

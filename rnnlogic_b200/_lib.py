@@ -12,7 +12,7 @@ import subprocess
 _HERE = os.path.dirname(os.path.abspath(__file__))
 ROOT = os.path.dirname(_HERE)
 LIB_PATH = os.environ.get("RNNLOGIC_B200_LIB") or os.path.join(_HERE, "lib", "librnnlogic_b200.so")   # env override: A/B builds
-SOURCES = [os.path.join(_HERE, "csrc", f) for f in ("rl_kernels.cu", "rl_plus.cu", "rl_rotate.cu", "rl_tail.cu")]
+SOURCES = [os.path.join(_HERE, "csrc", f) for f in ("rl_kernels.cu", "rl_plus.cu", "rl_rotate.cu", "rl_tail.cu", "rl_rnn.cu")]
 HEADER = os.path.join(ROOT, "include", "rnnlogic_b200.h")
 
 LANES = 32
@@ -145,6 +145,9 @@ _PROTOS = {
                                      vp, vp, vp]),
     "rl_adam_step": (C.c_int, [C.c_int64, vp, vp, vp, vp, C.c_float, C.c_float, C.c_float, C.c_float, C.c_float,
                                C.c_int64, vp]),
+    "rl_lstm_encode_forward": (C.c_int, [C.c_int32, C.c_int32, C.c_int32, C.c_int32, vp, vp, vp, vp, vp, vp, vp]),
+    "rl_lstm_encode_backward": (C.c_int, [C.c_int32, C.c_int32, C.c_int32, C.c_int32, vp, vp, vp, vp, vp, vp, vp]),
+    "rl_lstm_encode_wgrad": (C.c_int, [C.c_int64, C.c_int32, C.c_int32, vp, vp, vp, vp, vp]),
     "rl_slot_to_dense": (C.c_int, [C.c_int32, C.c_int32, vp, vp, C.c_int64, vp]),
     "rl_mask_to_dense": (C.c_int, [C.c_int32, C.c_int32, vp, vp, C.c_int64, vp]),
 }

@@ -6,6 +6,7 @@ edges_to_remove) -> (score fp32[B,N], mask bool[B,N])``, ``compute_H`` and the r
 ``state_dict`` keys.  They are CUDA-only: a CPU tensor raises (no fallback)."""
 from __future__ import annotations
 
+import ctypes as C
 import logging
 import math
 from typing import List, Optional
@@ -483,8 +484,53 @@ class _ToDenseFn(torch.autograd.Function):
         return ctx.sk.from_dense(ctx.sl, gscore.contiguous()), None, None, None
 
 
+class _LstmEncodeFn(torch.autograd.Function):
+    """torch.nn.LSTM(H, H, L, batch_first=True)(x)[0] gathered at the last non-pad step, on the hand-written
+    kernels of rl_rnn.cu (the sequential part) + one GEMM per weight gradient."""
+
+    @staticmethod
+    def forward(ctx, x, lens, L, *weights):
+        n, T, H = x.shape
+        x = x.contiguous().float()
+        weights = [w.detach().contiguous().float() for w in weights]
+        dev = x.device
+        acts = torch.zeros(n, L, T, 5, H, dtype=torch.float32, device=dev)
+        ih = torch.zeros(L, n, T, 2 * H, dtype=torch.float32, device=dev)
+        out = torch.empty(n, H, dtype=torch.float32, device=dev)
+        ptrs = (C.c_void_p * (4 * L))(*[w.data_ptr() for w in weights])
+        _lib.check(_lib.lib().rl_lstm_encode_forward(n, T, H, L, x.data_ptr(), lens.data_ptr(), ptrs, acts.data_ptr(),
+                                                     ih.data_ptr(), out.data_ptr(), _stream()), "rl_lstm_encode_forward")
+        ctx.save_for_backward(lens, acts, ih, *weights)
+        ctx.shape = (n, T, H)
+        ctx.L = L
+        return out
+
+    @staticmethod
+    def backward(ctx, dout):
+        lens, acts, ih, *weights = ctx.saved_tensors
+        L = ctx.L
+        n, T, H = ctx.shape
+        dev = acts.device
+        dG = torch.zeros(L, n, T, 4 * H, dtype=torch.float32, device=dev)
+        dX = torch.zeros(n, T, H, dtype=torch.float32, device=dev)
+        ptrs = (C.c_void_p * (4 * L))(*[w.data_ptr() for w in weights])
+        _lib.check(_lib.lib().rl_lstm_encode_backward(n, T, H, L, lens.data_ptr(), ptrs, acts.data_ptr(),
+                                                      dout.contiguous().float().data_ptr(), dG.data_ptr(), dX.data_ptr(),
+                                                      _stream()), "rl_lstm_encode_backward")
+        # plain reductions over (rule, step): [dW_ih | dW_hh] = dG^T ih and the bias sums, one kernel for all layers
+        dW = torch.zeros(L, 4 * H, 2 * H, dtype=torch.float32, device=dev)
+        db = torch.zeros(L, 4 * H, dtype=torch.float32, device=dev)
+        _lib.check(_lib.lib().rl_lstm_encode_wgrad(n * T, H, L, dG.data_ptr(), ih.data_ptr(), dW.data_ptr(), db.data_ptr(),
+                                                   _stream()), "rl_lstm_encode_wgrad")
+        grads = []
+        for l in range(L):
+            grads += [dW[l, :, :H], dW[l, :, H:], db[l], db[l]]
+        return (dX, None, None) + tuple(grads)
+
+
 class PredictorPlus(_RuleModel):
     fused_tail = True         # `sum` aggregator: run the dense tail in the fused CUDA kernels (rl_tail.cu)
+    fused_rnn = True          # `lstm` rule encoder with hidden_dim 16 / 32: rl_rnn.cu instead of cuDNN
 
     def __init__(self, graph, type='emb', num_layers=3, hidden_dim=16, entity_feature='bias', aggregator='sum',
                  embedding_path=None):
@@ -542,6 +588,11 @@ class PredictorPlus(_RuleModel):
         """predictors.py:201-208: embed [head, body..., pad], run the RNN, take the last non-pad output."""
         rule_masks = rule_features != self.num_relations
         x = self.vocab_emb(rule_features)
+        if (self.fused_rnn and self.type == 'lstm' and x.is_cuda and self.hidden_dim in (16, 32)
+                and 1 <= self.num_layers <= 4 and x.shape[0] > 0):
+            ws = [getattr(self.rnn, "%s_l%d" % (nm, l)) for l in range(self.num_layers)
+                  for nm in ("weight_ih", "weight_hh", "bias_ih", "bias_hh")]
+            return _LstmEncodeFn.apply(x, rule_masks.sum(-1).to(torch.int32), self.num_layers, *ws)
         output, hidden = self.rnn(x)
         idx = (rule_masks.sum(-1) - 1).long()
         idx = idx.unsqueeze(-1).unsqueeze(-1).expand(-1, -1, self.hidden_dim)

@@ -13,6 +13,7 @@ kw = dict(type="lstm", num_layers=3, hidden_dim=16, entity_feature="bias", aggre
      dict(type="emb", hidden_dim=16, entity_feature="bias", aggregator="pna")
 torch.manual_seed(0)
 pm = PredictorPlus(kg, **kw); pm.set_rules([[h] + list(b) for h, b in rules]); pm = pm.cuda()
+pm.fused_rnn = "--cudnn" not in sys.argv
 opt = torch.optim.Adam(pm.parameters(), lr=0.005)
 per = 64
 def step(i):

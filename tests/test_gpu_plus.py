@@ -179,3 +179,42 @@ def test_rotate_module_forward_and_grad(tmp_path):
     for mine, ref in ((mod.eemb.grad, e.grad), (mod.remb.grad, r.grad)):
         scale = ref.abs().max().item()
         np.testing.assert_allclose(mine.cpu().numpy(), ref.numpy(), rtol=1e-3, atol=2e-4 * scale)
+
+
+@pytest.mark.parametrize("H,L", [(16, 3), (32, 2), (16, 1)])
+def test_lstm_rule_encoder_matches_torch(H, L):
+    """rl_rnn.cu (forward + backward of the LSTM rule encoder) against torch.nn.LSTM in fp32: outputs at the
+    last non-pad token and the gradients of every weight and of the token embeddings."""
+    from rnnlogic_b200.predictors import _LstmEncodeFn
+    torch.manual_seed(7)
+    n, T, V = 777, 5, 23
+    prev = torch.backends.cudnn.allow_tf32
+    torch.backends.cudnn.allow_tf32 = False
+    try:
+        emb = torch.nn.Embedding(V + 1, H, padding_idx=V).cuda()
+        rnn = torch.nn.LSTM(H, H, L, batch_first=True).cuda()
+        lens = torch.randint(1, T + 1, (n,), device=DEV)
+        tok = torch.randint(0, V, (n, T), device=DEV)
+        tok[torch.arange(T, device=DEV)[None, :] >= lens[:, None]] = V              # pad behind the last token
+        proj = torch.randn(n, H, device=DEV)
+
+        def run(fused):
+            for p in list(emb.parameters()) + list(rnn.parameters()):
+                p.grad = None
+            x = emb(tok)
+            if fused:
+                ws = [getattr(rnn, "%s_l%d" % (nm, l)) for l in range(L) for nm in ("weight_ih", "weight_hh", "bias_ih", "bias_hh")]
+                out = _LstmEncodeFn.apply(x, lens.to(torch.int32), L, *ws)
+            else:
+                o, _ = rnn(x)
+                out = torch.gather(o, 1, (lens - 1).view(-1, 1, 1).expand(-1, -1, H)).squeeze(1)
+            (out * proj).sum().backward()
+            return out.detach().cpu().numpy(), [p.grad.detach().cpu().numpy().copy() for p in list(emb.parameters()) + list(rnn.parameters())]
+
+        o1, g1 = run(True)
+        o0, g0 = run(False)
+    finally:
+        torch.backends.cudnn.allow_tf32 = prev
+    np.testing.assert_allclose(o1, o0, rtol=1e-5, atol=2e-5)          # fp32, different summation order than cuDNN
+    for a, b in zip(g1, g0):
+        np.testing.assert_allclose(a, b, rtol=1e-4, atol=1e-5 * max(1.0, float(np.abs(b).max())))
