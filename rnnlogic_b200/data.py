@@ -91,3 +91,50 @@ class ValidDataset(_EvalDataset):
 class TestDataset(_EvalDataset):
     split = "test"
     answers = "hr2ooo"
+
+
+class StepPrefetcher(object):
+    """Runs ``pack_fn`` (e.g. ``model.pack_train_step``) over an iterable of steps on a loader thread, ``depth``
+    steps ahead of the consumer -- the host-side packing of step k+2 then overlaps the enqueue of step k+1 and
+    the wait for step k.  Iterating yields the packed steps in order; an exception in the thread is re-raised."""
+
+    _END = object()
+
+    def __init__(self, pack_fn, steps, depth=2):
+        import queue
+        import threading
+        self._q = queue.Queue(maxsize=max(1, int(depth)))
+        self._stop = threading.Event()
+
+        def work():
+            try:
+                for st in steps:
+                    item = pack_fn(st)
+                    while not self._stop.is_set():
+                        try:
+                            self._q.put(item, timeout=0.1)
+                            break
+                        except queue.Full:
+                            continue
+                    if self._stop.is_set():
+                        return
+                self._q.put(self._END)
+            except BaseException as e:                      # surfaces in the consumer
+                self._q.put(e)
+
+        self._thread = threading.Thread(target=work, daemon=True)
+        self._thread.start()
+
+    def __iter__(self):
+        return self
+
+    def __next__(self):
+        item = self._q.get()
+        if item is self._END:
+            raise StopIteration
+        if isinstance(item, BaseException):
+            raise item
+        return item
+
+    def close(self):
+        self._stop.set()

@@ -22,19 +22,17 @@ def _stream():
     return C.c_void_p(torch._C._cuda_getCurrentRawStream(torch.cuda.current_device()))
 
 
-class Slots:
-    """Device-side description of one call (rl_slots) + its frontier arena."""
+class HostStep:
+    """The host half of a call: slot tables (and, for host batches, the queries) packed for ONE host->device
+    copy.  Building it needs no CUDA work, so a loader thread can prepare steps ahead (data.StepPrefetcher)."""
 
-    def __init__(self, dg, cr: CompiledRules, heads: np.ndarray, q_off: np.ndarray,
-                 all_h: Optional[torch.Tensor], all_t: Optional[torch.Tensor], etr: Optional[torch.Tensor],
-                 host_queries: Optional[np.ndarray] = None, remove_query_edges: bool = False,
-                 group_ptr: Optional[np.ndarray] = None):
-        """all_h / all_t / etr: int64 CUDA tensors -- or host_queries int64[k, Q] (rows h, t[, etr]), which
-        then travel with the slot descriptors in ONE pinned host->device copy."""
-        dev = dg.device
+    def __init__(self, cr: CompiledRules, heads: np.ndarray, q_off: np.ndarray, host_queries: Optional[np.ndarray] = None,
+                 group_ptr: Optional[np.ndarray] = None, group_sizes=None, remove_query_edges: bool = False, pin: bool = True):
         S = int(heads.shape[0])
         self.S, self.heads, self.q_off = S, heads, q_off
         self.nq = np.diff(q_off)
+        self.group_sizes = group_sizes
+        self.remove_query_edges = bool(remove_query_edges)
         arena_off = np.zeros(S + 1, dtype=np.int64)
         np.cumsum(cr.head_rows[heads], out=arena_off[1:])
         nz_off = np.zeros(S + 1, dtype=np.int64)
@@ -45,10 +43,11 @@ class Slots:
         np.cumsum(cr.head_item_cap[heads], out=item_off[1:])
         self.arena_rows, self.nz_total, self.mask_words = int(arena_off[-1]), int(nz_off[-1]), int(mask_off[-1])
         self.item_cap = int(item_off[-1])
-        # one packed H2D copy: int64 sections first, the int32 tables behind them
-        k, Q = (0, 0) if host_queries is None else host_queries.shape
-        ng1 = 0 if group_ptr is None else int(group_ptr.shape[0])
-        n64 = k * Q + 3 * S + 1
+        # int64 sections first, the int32 tables behind them
+        self.k, self.Q = (0, 0) if host_queries is None else host_queries.shape
+        self.ng1 = 0 if group_ptr is None else int(group_ptr.shape[0])
+        k, Q, ng1 = self.k, self.Q, self.ng1
+        self.n64 = n64 = k * Q + 3 * S + 1
         n32 = 3 * S + 1 + ng1
         pack = np.empty(n64 + (n32 + 1) // 2, dtype=np.int64)
         if k:
@@ -63,11 +62,30 @@ class Slots:
         p32[2 * S + 1:3 * S + 1] = nz_off[:-1]
         if ng1:
             p32[3 * S + 1:3 * S + 1 + ng1] = group_ptr
-        d = torch.from_numpy(pack).pin_memory().to(dev, non_blocking=True)      # pinned staging, async copy
-        self.h2d_bytes = int(pack.nbytes)
+        self.nbytes = int(pack.nbytes)
+        self.staged = torch.from_numpy(pack)
+        if pin:
+            self.staged = self.staged.pin_memory()               # pinned staging for the async copy
+
+
+class Slots:
+    """Device-side description of one call (rl_slots) + its frontier arena."""
+
+    def __init__(self, dg, host: HostStep, all_h: Optional[torch.Tensor] = None, all_t: Optional[torch.Tensor] = None,
+                 etr: Optional[torch.Tensor] = None):
+        """all_h / all_t / etr: int64 CUDA tensors -- or, when the HostStep carries the queries (rows h, t[, etr]),
+        they travel with the slot descriptors in ONE pinned host->device copy."""
+        dev = dg.device
+        S, k, Q, ng1, n64 = host.S, host.k, host.Q, host.ng1, host.n64
+        self.S, self.heads, self.q_off, self.nq = S, host.heads, host.q_off, host.nq
+        self.arena_rows, self.nz_total, self.mask_words, self.item_cap = host.arena_rows, host.nz_total, host.mask_words, host.item_cap
+        self.group_sizes = host.group_sizes
+        d = host.staged.to(dev, non_blocking=True)
+        self.h2d_bytes = host.nbytes
         if k:
             all_h, all_t = d[:Q], d[Q:2 * Q]
             etr = d[2 * Q:3 * Q] if k > 2 else None
+        o = k * Q
         self.arena_off, self.mask_off, self.item_off = d[o:o + S], d[o + S:o + 2 * S], d[o + 2 * S:o + 3 * S + 1]
         d32 = d[n64:].view(torch.int32)
         self.slot_head, self.q_off_dev, self.nz_off = d32[:S], d32[S:2 * S + 1], d32[2 * S + 1:3 * S + 1]
@@ -76,13 +94,13 @@ class Slots:
         _lib.check(_lib.lib().rl_prepare_slots(
             dg.ref(), S, self.slot_head.data_ptr(), self.q_off_dev.data_ptr(), all_h.data_ptr(),
             all_t.data_ptr() if all_t is not None else None, etr.data_ptr() if etr is not None else None,
-            int(remove_query_edges and etr is None),
+            int(host.remove_query_edges and etr is None),
             self.lane[0].data_ptr(), self.lane[1].data_ptr(), self.lane[2].data_ptr(), self.lane[3].data_ptr(),
             _stream()), "rl_prepare_slots")
         self.struct = _lib.RlSlots(S, self.slot_head.data_ptr(), self.lane[0].data_ptr(), self.lane[1].data_ptr(),
                                    self.lane[2].data_ptr(), self.lane[3].data_ptr(), self.arena_off.data_ptr(),
                                    self.nz_off.data_ptr(), self.mask_off.data_ptr())
-        self._keep = (all_h, all_t, etr, d)
+        self._keep = (all_h, all_t, etr, d, host.staged)
         self.arena = None
         self.state = None         # int32 buffer: row_mask | node_cnt | item_cnt | bucket_cnt | overflow
         self.overflow = None
@@ -139,16 +157,12 @@ class Grounder:
         for name, t in (("all_h", all_h), ("all_t", all_t), ("edges_to_remove", etr)):
             if t is not None and int(t.numel()) != pos:
                 raise ValueError("%s has %d entries for %d queries" % (name, int(t.numel()), pos))
-        sl = Slots(self.dg, self.cr, sh, qo, all_h.contiguous(), None if all_t is None else all_t.contiguous(),
-                   None if etr is None else etr.contiguous(), group_ptr=gp if len(sh) != len(sizes) else None)
-        sl.group_sizes = list(sizes)
-        return sl
+        host = HostStep(self.cr, sh, qo, group_ptr=gp if len(sh) != len(sizes) else None, group_sizes=list(sizes))
+        return Slots(self.dg, host, all_h.contiguous(), None if all_t is None else all_t.contiguous(),
+                     None if etr is None else etr.contiguous())
 
-    def make_slots_host(self, batches, with_etr: bool, etr_lists=None) -> Slots:
-        """Slots for a list of single-relation batches given as host lists of (h, r, t) triples
-        (what the datasets hold).  ONE packed host->device copy carries h, t and the slot tables.
-        with_etr: every query's own train edge is masked out (data.py:214-216); the edge is found on
-        the device unless etr_lists gives the reference's per-relation edge indices explicitly."""
+    def pack_host(self, batches, with_etr: bool, etr_lists=None) -> HostStep:
+        """The CUDA-free half of make_slots_host (thread-safe: a loader thread may run it ahead of the step)."""
         if isinstance(batches[0], np.ndarray):                  # int arrays [n,3]: no per-triple Python work
             flat = np.concatenate(batches).astype(np.int64, copy=False).reshape(-1, 3)
             heads = [int(b[0, 1]) for b in batches]
@@ -160,10 +174,18 @@ class Grounder:
         if with_etr and etr_lists is not None:
             rows.append(np.array([e for l in etr_lists for e in l], dtype=np.int64))
         sh, qo, gp, pos = self._split(heads, sizes)
-        sl = Slots(self.dg, self.cr, sh, qo, None, None, None, host_queries=np.stack(rows),
-                   remove_query_edges=with_etr, group_ptr=gp if len(sh) != len(sizes) else None)
+        return HostStep(self.cr, sh, qo, host_queries=np.stack(rows), group_ptr=gp if len(sh) != len(sizes) else None,
+                        group_sizes=sizes, remove_query_edges=with_etr)
+
+    def make_slots_host(self, batches, with_etr: bool, etr_lists=None) -> Slots:
+        """Slots for a list of single-relation batches given as host lists of (h, r, t) triples
+        (what the datasets hold) -- or for a HostStep packed ahead by pack_host.  ONE packed host->device copy
+        carries h, t and the slot tables.  with_etr: every query's own train edge is masked out
+        (data.py:214-216); the edge is found on the device unless etr_lists gives the reference's
+        per-relation edge indices explicitly."""
+        host = batches if isinstance(batches, HostStep) else self.pack_host(batches, with_etr, etr_lists)
+        sl = Slots(self.dg, host)
         sl.use_workspace = True
-        sl.group_sizes = sizes
         return sl
 
     def _run(self, sl: Slots, bits: int):

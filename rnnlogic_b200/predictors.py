@@ -240,13 +240,21 @@ class _PreparedStep:
         loss, tsum, msum, gw, gb = _predictor_step_on_slots(model, sk, sl, smoothing, grad_scale, self.bits, expanded=True)
         parts = [loss, tsum] + ([msum] if msum is not None else [])
         pack = torch.cat(parts + [sl.overflow.float()])
-        return _StepTicket(model, sk, sl, self.batches, smoothing, grad_scale, pack, gw, gb, len(self.batches), use_bias)
+        return _StepTicket(model, sk, sl, self.batches, smoothing, grad_scale, pack, gw, gb, len(sl.group_sizes), use_bias)
+
+
+def _predictor_pack_train(self, batches):
+    """The CUDA-free part of a fused train step (queries and slot tables packed into pinned memory for one
+    copy).  Thread-safe once the model sits on its device: a loader thread can pack steps ahead
+    (data.StepPrefetcher) and hand the result to prepare_train_step / submit_train_step."""
+    return self._driver(self.rule_weights.device).gr.pack_host(batches, with_etr=True)
 
 
 def _predictor_prepare_train(self, batches):
     """Enqueue everything of a fused train step that does not depend on the parameters (grounding) and
     return a handle; ``handle.finish(smoothing, grad_scale)`` enqueues the rest.  A data-parallel loop calls
-    this for step k+1 while the gradient all-reduce of step k is in flight."""
+    this for step k+1 while the gradient all-reduce of step k is in flight.  ``batches``: a list of
+    single-relation batches or a step packed ahead by pack_train_step."""
     device = self.rule_weights.device
     sk = self._driver(device)
     sl = sk.gr.make_slots_host(batches, with_etr=True)
@@ -312,6 +320,7 @@ def _valid_lanes(sl, LH):
 Predictor.fused_train_step = _predictor_fused_train
 Predictor.submit_train_step = _predictor_submit_train
 Predictor.prepare_train_step = _predictor_prepare_train
+Predictor.pack_train_step = _predictor_pack_train
 Predictor.step_on_slots = _predictor_step_on_slots
 Predictor.fused_rank = _predictor_fused_rank
 

@@ -117,11 +117,13 @@ class TrainerPredictor(object):
         pipelined = self.pipelined and hasattr(model, "prepare_train_step") and not use_mask
         ticket = None
         if pipelined and steps:
-            ticket = model.prepare_train_step(steps[0]).finish(smoothing, grad_scale=1.0 / len(steps[0]))
+            from .data import StepPrefetcher
+            packed = StepPrefetcher(model.pack_train_step, steps, depth=2)      # host packing on a loader thread
+            ticket = model.prepare_train_step(next(packed)).finish(smoothing, grad_scale=1.0 / len(steps[0]))
         for si, batches in enumerate(steps):
             self.optimizer.zero_grad(set_to_none=True)
             if pipelined:
-                prep = model.prepare_train_step(steps[si + 1]) if si + 1 < len(steps) else None
+                prep = model.prepare_train_step(next(packed)) if si + 1 < len(steps) else None
                 model.rule_weights.grad, model.bias.grad = ticket.gw, ticket.gb
                 self._allreduce_grads()
                 self.optimizer.step()

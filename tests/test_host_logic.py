@@ -325,3 +325,36 @@ def test_binary_kg_cache(tmp_path, monkeypatch):
     monkeypatch.setenv("RNNLOGIC_B200_KG_CACHE", str(tmp_path / "cache2"))
     KnowledgeGraph(str(d))
     assert len(list((tmp_path / "cache2").glob("kg_*.npz"))) == 1
+
+
+def test_step_prefetcher_order_errors_and_close():
+    """data.StepPrefetcher: packed steps arrive in order from the loader thread, at most `depth` ahead; an
+    exception in pack_fn surfaces in the consumer; close() releases a blocked producer."""
+    import threading
+    import time
+    from rnnlogic_b200.data import StepPrefetcher
+    seen = []
+
+    def pack(x):
+        seen.append(x)
+        return x * 10
+
+    pf = StepPrefetcher(pack, range(7), depth=2)
+    time.sleep(0.3)
+    assert len(seen) <= 3                                   # depth 2 in the queue + one being offered
+    assert list(pf) == [0, 10, 20, 30, 40, 50, 60]
+
+    def bad(x):
+        if x == 2:
+            raise KeyError("boom")
+        return x
+
+    pf = StepPrefetcher(bad, range(5), depth=1)
+    assert next(pf) == 0 and next(pf) == 1
+    with pytest.raises(KeyError):
+        next(pf)
+    pf = StepPrefetcher(lambda x: x, range(100), depth=1)
+    assert next(pf) == 0
+    pf.close()
+    pf._thread.join(timeout=2.0)
+    assert not pf._thread.is_alive()
