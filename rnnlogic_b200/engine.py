@@ -64,7 +64,7 @@ class HostStep:
             p32[3 * S + 1:3 * S + 1 + ng1] = group_ptr
         self.nbytes = int(pack.nbytes)
         self.staged = torch.from_numpy(pack)
-        if pin:
+        if pin and torch.cuda.is_available():
             self.staged = self.staged.pin_memory()               # pinned staging for the async copy
 
 

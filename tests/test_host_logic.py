@@ -358,3 +358,43 @@ def test_step_prefetcher_order_errors_and_close():
     pf.close()
     pf._thread.join(timeout=2.0)
     assert not pf._thread.is_alive()
+
+
+def test_host_step_pack_layout():
+    """engine.HostStep: the one-copy layout [h | t | arena_off | mask_off | item_off | int32: slot_head, q_off,
+    nz_off, group_ptr] that Slots slices on the device; groups larger than 32 queries split into slots."""
+    from rnnlogic_b200 import KnowledgeGraph, CompiledRules, parse_rules
+    from rnnlogic_b200.engine import Grounder, HostStep
+    fx = G.load("umls")
+    kg = KnowledgeGraph(entity_size=int(fx["N"]), relation_size=int(fx["R"]), train=fx["train"])
+    cr = CompiledRules(kg, parse_rules(G.rules_of(fx)))
+    tri = fx["train"].astype(np.int64)
+    batches = [tri[tri[:, 1] == q][:n] for q, n in ((3, 40), (5, 7), (3, 32), (8, 65)) if (tri[:, 1] == q).sum() >= n]
+    assert len(batches) >= 3
+    g = Grounder.__new__(Grounder)                     # pack_host touches no CUDA state
+    g.cr = cr
+    host = g.pack_host(batches, with_etr=True)
+    sizes = [len(b) for b in batches]
+    S = sum((n + 31) // 32 for n in sizes)
+    Q = sum(sizes)
+    assert (host.S, host.Q, host.k) == (S, Q, 2) and host.remove_query_edges and host.group_sizes == sizes
+    pack = host.staged.numpy() if not host.staged.is_pinned() else host.staged.numpy()
+    flat = np.concatenate(batches)
+    assert np.array_equal(pack[:Q], flat[:, 0]) and np.array_equal(pack[Q:2 * Q], flat[:, 2])
+    heads = np.concatenate([[int(b[0, 1])] * ((len(b) + 31) // 32) for b in batches])
+    o = 2 * Q
+    assert np.array_equal(pack[o:o + S], np.concatenate([[0], np.cumsum(cr.head_rows[heads])[:-1]]))
+    assert np.array_equal(pack[o + S:o + 2 * S], np.concatenate([[0], np.cumsum(cr.head_chunks[heads])[:-1]]))
+    assert np.array_equal(pack[o + 2 * S:o + 3 * S + 1], np.concatenate([[0], np.cumsum(cr.head_item_cap[heads])]))
+    p32 = pack[host.n64:].view(np.int32)
+    assert np.array_equal(p32[:S], heads)
+    q_off = p32[S:2 * S + 1]
+    assert q_off[0] == 0 and q_off[-1] == Q and (np.diff(q_off) <= 32).all() and (np.diff(q_off) > 0).all()
+    gp = p32[3 * S + 1:3 * S + 1 + len(sizes) + 1]
+    assert np.array_equal(np.diff(gp), [(n + 31) // 32 for n in sizes])
+    assert host.nbytes == pack.nbytes and host.arena_rows == int(cr.head_rows[heads].sum())
+    # single-slot groups carry no group table
+    small = g.pack_host([b[:5] for b in batches], with_etr=False)
+    assert small.ng1 == 0 and not small.remove_query_edges
+    with pytest.raises(ValueError):
+        Grounder._split([], [])
