@@ -259,6 +259,7 @@ def main():
     from rnnlogic_b200 import KnowledgeGraph, _lib
     from rnnlogic_b200.predictors import Predictor
     from rnnlogic_b200 import comm
+    from rnnlogic_b200.trainer import snake_deal
     dev = torch.device("cuda", local_rank)
     torch.cuda.set_device(dev)
     if world > 1:
@@ -286,8 +287,7 @@ def main():
     step_batches = []
     for s in range(n_steps):
         glob = [batches[(s * per * world + j) % len(batches)] for j in range(per * world)]
-        order = sorted(range(len(glob)), key=lambda j: -int(cr.head_rows[int(glob[j][0, 1])]))
-        mine = [glob[j] for k, j in enumerate(order) if (k % (2 * world) == rank or k % (2 * world) == 2 * world - 1 - rank)]
+        mine = [glob[j] for j in snake_deal([int(cr.head_rows[int(b[0, 1])]) for b in glob], world, rank)]
         step_batches.append(mine)
     step_lists = step_batches            # int arrays [n,3] per batch, what the datasets hold (batch_arrays)
     queries_per_step = [sum(len(b) for b in sb) for sb in step_batches]

@@ -55,6 +55,17 @@ def allreduce_mean_grads(params, world_size):
         off += n
 
 
+def snake_deal(costs, world_size, rank):
+    """Indices of the items one rank takes when ``costs`` are dealt largest-first in snake order
+    (0,1,..,W-1,W-1,..,1,0,0,1,..): the ranks' shares are disjoint, cover everything, have the same size when
+    len(costs) is a multiple of the world size, and nearly equal total cost -- so a per-step gradient
+    exchange does not wait for one unlucky rank.  (A throughput-mode helper; the reference's own schedule is
+    shard_indices.)"""
+    order = sorted(range(len(costs)), key=lambda j: (-costs[j], j))
+    period = 2 * world_size
+    return [j for k, j in enumerate(order) if k % period == rank or k % period == period - 1 - rank]
+
+
 class TrainerPredictor(object):
     slots_per_step = 1      # train batches per optimizer step (1 = the reference's schedule)
     pipelined = True        # Predictor(bias): enqueue step i+1 before reading step i back (a 32-bit count overflow

@@ -398,3 +398,23 @@ def test_host_step_pack_layout():
     assert small.ng1 == 0 and not small.remove_query_edges
     with pytest.raises(ValueError):
         Grounder._split([], [])
+
+
+def test_snake_deal_partitions_and_balances():
+    """trainer.snake_deal (bench.py's per-step dealing of batches to ranks): disjoint cover, equal counts,
+    near-equal cost -- and identical to the largest-first snake order written out by hand."""
+    from rnnlogic_b200.trainer import snake_deal
+    rng = np.random.default_rng(4)
+    for world in (1, 2, 4, 8):
+        costs = (rng.pareto(1.2, size=64 * world) * 1000).astype(int).tolist()
+        shares = [snake_deal(costs, world, r) for r in range(world)]
+        flat = sorted(j for s in shares for j in s)
+        assert flat == list(range(len(costs)))
+        assert all(len(s) == 64 for s in shares)
+        tot = [sum(costs[j] for j in s) for s in shares]
+        assert max(tot) - min(tot) <= max(costs)                 # never further apart than one item
+        order = sorted(range(len(costs)), key=lambda j: -costs[j])
+        for r in range(world):
+            want = [j for k, j in enumerate(order) if k % (2 * world) in (r, 2 * world - 1 - r)]
+            assert shares[r] == want
+    assert snake_deal([], 2, 0) == [] and snake_deal([5, 5, 5], 2, 0) == [0] and snake_deal([5, 5, 5], 2, 1) == [1, 2]
