@@ -4,18 +4,21 @@
     python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference]
     torchrun --nnodes=1 --nproc-per-node N ... bench.py --gpus N ...
 
-A step = one pass of the hot path (ground every rule of the head -> rule-weight aggregation ->
-log(softmax+1e-8) CE -> backward into rule weights/bias -> Adam) over ``--batches`` reference
-batches (single-relation groups of <= 32 train queries, src/data.py:186-196) per GPU.  Batches
-are sharded over ranks (KG + rules replicated, one flat gradient all-reduce per step): weak
-scaling.  ``value`` is timed with the step's queries already in HBM; ``e2e`` goes through the
-public fused API from HOST lists (pack + H2D + kernels + D2H of the losses) every step.
-``--impl reference`` times the CPU oracle port of the reference path (oracle/) on host cores."""
+A step = one pass of the hot path (ground every rule of the head -> candidate cells -> rule-weight aggregation ->
+log(softmax+1e-8) CE -> backward into rule weights/bias -> Adam) over ``--batches`` reference batches
+(single-relation groups of <= 32 train queries, src/data.py:186-196) per GPU.  Batches are sharded over ranks
+(KG + rules replicated, one flat gradient all-reduce per step): weak scaling.  ``value`` is timed with the
+step's queries already in HBM; ``e2e`` goes through the public fused API from HOST arrays (pack + H2D + kernels +
+D2H of the losses) every step.  ``configs`` holds the same end-to-end measurement for the other configurations
+BASELINE.json names (PredictorPlus as shipped for FB15k-237, with a RotatE-shaped entity feature, the WN18RR
+config), for a TYPED synthetic graph whose rule bodies compose, and for the reference's own schedule (one
+32-query batch per optimizer step).  ``--impl reference`` times the CPU oracle port of the reference path."""
 import argparse
 import json
 import os
 import subprocess
 import sys
+import tempfile
 import threading
 import time
 
@@ -30,11 +33,15 @@ UNIT = "queries/s"
 B = 32
 
 
-def build_workload(name="fb15k237", scale=1.0):
+def build_workload(name="fb15k237", typed=False):
     from rnnlogic_b200 import synth
     shape = synth.load_shape(name)
-    N, R, train, valid, test = synth.synthetic_kg(shape, scale=scale)
-    rules = synth.synthetic_rules(shape)
+    if typed:
+        N, R, train, valid, test, meta = synth.typed_kg(shape)
+        rules = synth.typed_rules(shape, meta)
+    else:
+        N, R, train, valid, test = synth.synthetic_kg(shape)
+        rules = synth.synthetic_rules(shape)
     return shape, N, R, train, valid, test, rules
 
 
@@ -102,8 +109,10 @@ class ClockSampler:
                 "samples": len(sm), "reasons": sorted(reasons)}
 
 
-def cpu_reference_run(N, R, train, valid, test, rules, batches, steps, warmup, budget_s=20.0):
-    """Oracle port of the reference Predictor train step on host cores (bounded sample)."""
+def cpu_reference_run(N, R, train, valid, test, rules, batches, steps, warmup, per, sample=8, budget_s=20.0):
+    """Oracle port of the reference Predictor train step on host cores.  A step of the GPU arm is ``per`` batches with
+    one optimizer step; the CPU arm times a BOUNDED SAMPLE of such a step: ``sample`` of its batches (gradients of
+    loss / per accumulated) and the optimizer step."""
     from oracle import rnnlogic_oracle as O
     torch.set_num_threads(os.cpu_count() or 1)
     kg = O.OracleKG(N, R, train, valid, test)
@@ -112,106 +121,254 @@ def cpu_reference_run(N, R, train, valid, test, rules, batches, steps, warmup, b
     w = (torch.randn(len(rules), generator=g) * 0.1).requires_grad_()
     bias = torch.zeros(N, requires_grad=True)
     opt = torch.optim.Adam([w, bias], lr=0.005)
+    sample = max(1, min(sample, per))
     times, nq = [], 0
+    cursor = [0]
 
-    def one(batch):
-        data = [tuple(int(v) for v in row) for row in batch]
-        all_h, all_r, all_t, target, etr = O.train_batch(kg, data)
-        q = int(all_r[0])
-        score, mask = O.predictor_forward(kg, table[q], w, bias, all_h, etr.numpy(), q)
-        loss = O.ce_loss(score, mask, O.smoothed_target(target, all_t, 0.2))
+    def one_step():
         opt.zero_grad()
-        loss.backward()
+        q_done = 0
+        for _ in range(sample):
+            batch = batches[cursor[0] % len(batches)]
+            cursor[0] += 1
+            data = [tuple(int(v) for v in row) for row in batch]
+            all_h, all_r, all_t, target, etr = O.train_batch(kg, data)
+            q = int(all_r[0])
+            score, mask = O.predictor_forward(kg, table[q], w, bias, all_h, etr.numpy(), q)
+            loss = O.ce_loss(score, mask, O.smoothed_target(target, all_t, 0.2))
+            (loss / per).backward()
+            q_done += len(data)
         opt.step()
-        return len(data)
+        return q_done
 
-    i = 0
     for _ in range(warmup):
-        one(batches[i % len(batches)])
-        i += 1
+        one_step()
     t_all = time.perf_counter()
     for _ in range(steps):
         t0 = time.perf_counter()
-        nq += one(batches[i % len(batches)])
-        i += 1
+        nq += one_step()
         times.append(time.perf_counter() - t0)
         if time.perf_counter() - t_all > budget_s and len(times) >= 1:
             break
     total = sum(times)
     return {"value": nq / total, "unit": UNIT, "cores": torch.get_num_threads(), "kind": "port",
-            "sample": "%d train batches of <=32 queries (%d queries), oracle port: C grounding per rule (1 thread) + "
-                      "torch-CPU aggregation/CE/backward/Adam (%d threads)" % (len(times), nq, torch.get_num_threads()),
+            "sample": "%d steps, each %d of the step's %d train batches of <=32 queries (%d queries in all) + the optimizer "
+                      "step; oracle port: C grounding per rule (1 thread) + torch-CPU aggregation/CE/backward/Adam (%d threads)"
+                      % (len(times), sample, per, nq, torch.get_num_threads()),
             "steps_done": len(times), "ms_per_step": 1e3 * total / len(times)}
 
 
-def _timed(fn, n_warm, n):
-    for _ in range(n_warm):
-        fn()
+class Runner:
+    """One model + optimizer on this rank with its dealt steps: device-resident and end-to-end loops."""
+
+    def __init__(self, model, step_lists, per, world, dev, lr=0.005):
+        from rnnlogic_b200.optim import Adam
+        from rnnlogic_b200 import cellpath
+        self.model, self.steps, self.per, self.world, self.dev = model, step_lists, per, world, dev
+        self.cellpath = cellpath
+        self.params = model.fused_params()
+        self.opt = Adam(self.params, lr=lr)          # torch.optim.Adam semantics, one element per thread (rl_adam_step)
+        self.sk = model._driver(dev)
+        self.queries = [sum(len(b) for b in sb) for sb in step_lists]
+
+    def start_allreduce(self, gbuf):
+        if self.world == 1:
+            return None
+        return torch.distributed.all_reduce(gbuf.flat, op=torch.distributed.ReduceOp.SUM, async_op=True)
+
+    def finish_step(self, work, gbuf):
+        if work is not None:
+            work.wait()
+            gbuf.flat.div_(self.world)
+        gbuf.assign()
+        self.opt.step()
+
+    def size_cells(self):
+        """One synchronous pass over the distinct steps so that the per-cell arrays fit every step (no overflow and
+        no cudaMalloc inside a timed loop)."""
+        from rnnlogic_b200.predictors import RlStepOverflow
+        for sb in self.steps:
+            for _ in range(3):
+                tk = self.model.submit_train_step(sb, 0.2, grad_scale=1.0 / self.per)
+                try:
+                    tk.result()
+                    break
+                except RlStepOverflow as e:
+                    if tk.pinned[-1].item() != 0:
+                        raise AssertionError("32-bit count overflow on the bench workload: " + str(e))
+        torch.cuda.synchronize()
+
+    def device_loop(self, warmup, steps, level_events=False):
+        """Queries already in HBM.  -> (ms, queries, launches, flags, level events)."""
+        from rnnlogic_b200 import _lib
+        model, sk, per = self.model, self.sk, self.per
+        n_steps = warmup + steps
+        slots = [sk.gr.make_slots_host(self.steps[s % len(self.steps)], with_etr=True) for s in range(n_steps)]
+        sk.gr.reserve(slots)
+        self.slots = slots
+        torch.cuda.synchronize()
+        if self.world > 1:
+            torch.distributed.barrier()
+        flags_acc = torch.zeros(9, dtype=torch.int32, device=self.dev)
+        for s in range(warmup):
+            gbuf = self.cellpath.GradBuffer(self.params)
+            model.step_on_slots(sk, slots[s], 0.2, 1.0 / per, gbuf)
+            self.finish_step(self.start_allreduce(gbuf), gbuf)
+        torch.cuda.synchronize()
+        if self.world > 1:
+            torch.distributed.barrier()
+        torch.cuda.synchronize()
+        launches0 = _lib.lib().rl_launch_count()
+        sk.gr.level_events = [] if level_events else None
+        ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        ev0.record()
+        losses = []
+        sk.gr._run(slots[warmup], 32)
+        for s in range(warmup, n_steps):
+            gbuf = self.cellpath.GradBuffer(self.params)
+            loss, tsum = model.step_on_slots(sk, slots[s], 0.2, 1.0 / per, gbuf, expanded=True)
+            flags_acc += slots[s].flags                  # the workspace is reused by the next step
+            pending = self.start_allreduce(gbuf)
+            if s + 1 < n_steps:                          # grounding is parameter-independent: enqueue it before the exchange
+                sk.gr._run(slots[s + 1], 32)
+            self.finish_step(pending, gbuf)
+            losses.append(loss)
+        ev1.record()
+        torch.cuda.synchronize()
+        if self.world > 1:
+            torch.distributed.barrier()
+        ms = ev0.elapsed_time(ev1)
+        launches = _lib.lib().rl_launch_count() - launches0
+        events, sk.gr.level_events = sk.gr.level_events, None
+        flags = flags_acc.cpu().numpy()
+        assert flags[8] == 0, "32-bit count overflow inside the timed region"
+        assert flags[1] == 0, "cell arrays overflowed inside the timed region"
+        assert all(torch.isfinite(l).all().item() for l in losses)
+        return ms, sum(self.queries[s % len(self.steps)] for s in range(warmup, n_steps)), launches, events
+
+    def e2e_loop(self, warmup, steps, trace=None):
+        """Host int arrays in, losses out, through submit / prepare / finish / result (software-pipelined by one
+        step; every step does its own packed H2D copy and its own D2H read).  -> (ms, queries, h2d, d2h)."""
+        from rnnlogic_b200.data import StepPrefetcher
+        model, per = self.model, self.per
+        n_steps = warmup + steps
+        seq = [self.steps[s % len(self.steps)] for s in range(n_steps)]
+        torch.cuda.synchronize()
+        if self.world > 1:
+            torch.distributed.barrier()
+        for s in range(warmup):
+            tk = model.submit_train_step(seq[s], 0.2, grad_scale=1.0 / per)
+            self.finish_step(self.start_allreduce(tk.gbuf), tk.gbuf)
+            tk.result()
+        torch.cuda.synchronize()
+        if self.world > 1:
+            torch.distributed.barrier()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        packed = StepPrefetcher(model.pack_train_step, seq[warmup:], depth=2)        # loader thread, inside the timed region
+        ticket = model.submit_train_step(next(packed), 0.2, grad_scale=1.0 / per)
+        h2d = d2h = 0
+        for s in range(warmup, n_steps):
+            t_a = time.perf_counter()
+            pending = self.start_allreduce(ticket.gbuf)
+            prep = model.prepare_train_step(next(packed)) if s + 1 < n_steps else None
+            self.finish_step(pending, ticket.gbuf)
+            nxt = prep.finish(0.2, grad_scale=1.0 / per) if prep is not None else None
+            t_b = time.perf_counter()
+            loss, tsum = ticket.result()
+            if trace is not None:
+                trace.append((t_b - t_a, time.perf_counter() - t_b))
+            assert torch.isfinite(loss).all()
+            h2d += ticket.h2d_bytes
+            d2h += ticket.d2h_bytes
+            ticket = nxt
+        e1.record()
+        torch.cuda.synchronize()
+        return e0.elapsed_time(e1), sum(self.queries[s % len(self.steps)] for s in range(warmup, n_steps)), h2d, d2h
+
+
+def reduce_max_sum(ms, q, dev, world):
+    t = torch.tensor([ms], dtype=torch.float64, device=dev)
+    n = torch.tensor([q], dtype=torch.float64, device=dev)
+    if world > 1:
+        torch.distributed.all_reduce(t, op=torch.distributed.ReduceOp.MAX)
+        torch.distributed.all_reduce(n)
+    return float(t.item()), float(n.item())
+
+
+def deal_steps(batches, cr, per, n_distinct, world, rank, offset=0):
+    """Every global step takes world*per batches and deals them to the ranks largest-first in snake order of
+    their grounding cost (rows of the head's trie), so that the per-step all-reduce does not wait for one rank."""
+    from rnnlogic_b200.trainer import snake_deal
+    out = []
+    for s in range(n_distinct):
+        glob = [batches[(offset + s * per * world + j) % len(batches)] for j in range(per * world)]
+        out.append([glob[j] for j in snake_deal([int(cr.head_rows[int(b[0, 1])]) for b in glob], world, rank)])
+    return out
+
+
+def rotate_dir(N, R, D=1000, gamma=9.0, seed=237):
+    """BASELINE config 4: RotatE-shaped random entity features (hidden_dim 1000 -> eemb [N,2000], remb [R/2,1000])."""
+    d = tempfile.mkdtemp(prefix="rotate_")
+    rng = np.random.default_rng(seed)
+    rr = (gamma + 2.0) / D
+    np.save(os.path.join(d, "entity_embedding.npy"), rng.uniform(-rr, rr, size=(N, 2 * D)).astype(np.float32))
+    np.save(os.path.join(d, "relation_embedding.npy"), rng.uniform(-rr, rr, size=(R // 2, D)).astype(np.float32))
+    with open(os.path.join(d, "config.json"), "w") as f:
+        json.dump({"hidden_dim": D, "gamma": gamma, "nentity": N}, f)
+    return d
+
+
+def side_config(tag, kg, rules, batches, kw, per, steps, world, rank, dev, plus=True, trace=False):
+    """End-to-end train throughput of one more configuration (same loop as the headline's e2e)."""
+    from rnnlogic_b200.predictors import Predictor, PredictorPlus
+    torch.manual_seed(0)
+    model = PredictorPlus(kg, **kw) if plus else Predictor(kg, **kw)
+    model.set_rules([[h] + list(b) for h, b in rules])
+    if not plus:
+        g = torch.Generator().manual_seed(0)
+        with torch.no_grad():
+            model.rule_weights.copy_(torch.randn(model.num_rules, generator=g) * 0.1)
+    model = model.cuda(dev)
+    if plus and not model.supports_pipeline:
+        return side_config_autograd(model, batches, per, steps, dev)
+    run = Runner(model, deal_steps(batches, model.compiled, per, 4, world, rank), per, world, dev)
+    run.size_cells()
+    ms, q, h2d, d2h = run.e2e_loop(3, steps)
+    ms, q = reduce_max_sum(ms, q, dev, world)
+    out = {"e2e_queries_per_sec": q / (ms / 1e3), "ms_per_step": ms / steps, "steps": steps, "batches_per_step_per_gpu": per,
+           "queries_per_step_per_gpu": int(np.mean(run.queries)), "h2d_bytes_per_step": h2d // steps, "d2h_bytes_per_step": d2h // steps}
+    del run, model
+    torch.cuda.empty_cache()
+    return out
+
+
+def side_config_autograd(model, batches, per, steps, dev):
+    """Configurations whose tail is not on the cell path yet (PNA aggregator): fused_train_step + torch optimizer."""
+    popt = torch.optim.Adam(model.parameters(), lr=0.005)
+    cycle = [[batches[(c * per + j) % len(batches)] for j in range(per)] for c in range(4)]
+    st = {"i": 0}
+
+    def step():
+        sb = cycle[st["i"] % 4]
+        st["i"] += 1
+        popt.zero_grad(set_to_none=True)
+        model.fused_train_step(sb, 0.2, grad_scale=1.0 / per)
+        popt.step()
+
+    for _ in range(4):
+        step()
     torch.cuda.synchronize()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     e0.record()
-    for _ in range(n):
-        fn()
+    for _ in range(steps):
+        step()
     e1.record()
     torch.cuda.synchronize()
-    return e0.elapsed_time(e1) / n
-
-
-def extras(args, kg, model, rules, batches, test, valid, dev):
-    """Side measurements on the same workload (short loops, end to end from host batches):
-    eval mode (ground -> aggregate -> filtered rank) and PredictorPlus train steps (the reference's
-    FB15k-237 config: lstm / sum / bias, and the RotatE entity feature of BASELINE config 4)."""
-    from rnnlogic_b200.predictors import PredictorPlus
-    out = {}
-    per = min(args.batches, 64)             # side measurements keep the 64-batch step of the earlier profiles
-    R = kg.relation_size
-    tb = make_batches(test, R, seed=2)
-    state = {"i": 0}
-
-    def eval_step():
-        sb = [tb[(state["i"] * per + j) % len(tb)] for j in range(per)]
-        state["i"] += 1
-        model.fused_rank(sb, "test")
-        state["q"] = sum(len(b) for b in sb)
-
-    ms = _timed(eval_step, 3, 10)
-    out["eval_filtered_rank_queries_per_sec"] = state["q"] / (ms / 1e3)
-    rule_lists = [[h] + list(b) for h, b in rules]
-    # BASELINE config 4: RotatE-shaped random entity features (hidden_dim 1000 -> eemb [N,2000], remb [R/2,1000])
-    import tempfile
-    rot_dir = tempfile.mkdtemp(prefix="rotate_")
-    rng = np.random.default_rng(237)
-    D, gamma = 1000, 9.0
-    rr = (gamma + 2.0) / D
-    np.save(os.path.join(rot_dir, "entity_embedding.npy"), rng.uniform(-rr, rr, size=(kg.entity_size, 2 * D)).astype(np.float32))
-    np.save(os.path.join(rot_dir, "relation_embedding.npy"), rng.uniform(-rr, rr, size=(R // 2, D)).astype(np.float32))
-    with open(os.path.join(rot_dir, "config.json"), "w") as f:
-        json.dump({"hidden_dim": D, "gamma": gamma, "nentity": kg.entity_size}, f)
-    for tag, kw in (("plus_lstm_sum_bias", dict(type="lstm", num_layers=3, hidden_dim=16, entity_feature="bias", aggregator="sum")),
-                    ("plus_emb_pna_bias", dict(type="emb", hidden_dim=16, entity_feature="bias", aggregator="pna")),
-                    ("plus_lstm_sum_rotate1000", dict(type="lstm", num_layers=3, hidden_dim=16, entity_feature="RotatE",
-                                                      aggregator="sum", embedding_path=rot_dir))):
-        torch.manual_seed(0)
-        pm = PredictorPlus(kg, **kw)
-        pm.set_rules(rule_lists)
-        pm = pm.cuda(dev)
-        popt = torch.optim.Adam(pm.parameters(), lr=0.005)
-        st = {"i": 0}
-        cycle = [[batches[(c * per + j) % len(batches)] for j in range(per)] for c in range(4)]
-        q_mean = sum(len(b) for sb in cycle for b in sb) / 4.0
-
-        def plus_step():            # cycles over 4 distinct steps: the warm-up sizes every workspace, no cudaMalloc is timed
-            sb = cycle[st["i"] % 4]
-            st["i"] += 1
-            popt.zero_grad(set_to_none=True)
-            pm.fused_train_step(sb, 0.2, grad_scale=1.0 / per)
-            popt.step()
-
-        ms = _timed(plus_step, 4, 4 if "rotate" in tag else 8)
-        out[tag + "_train_queries_per_sec"] = q_mean / (ms / 1e3)
-        del pm, popt
-        torch.cuda.empty_cache()
-    return out
+    ms = e0.elapsed_time(e1)
+    q = sum(len(b) for sb in cycle for b in sb) / 4.0 * steps
+    return {"e2e_queries_per_sec": q / (ms / 1e3), "ms_per_step": ms / steps, "steps": steps, "batches_per_step_per_gpu": per,
+            "path": "autograd tail (PNA aggregator), host-synchronous"}
 
 
 def main():
@@ -223,8 +380,11 @@ def main():
     ap.add_argument("--trace-e2e", action="store_true", help="print the host-side time of every end-to-end step to stderr")
     ap.add_argument("--batches", type=int, default=256, help="reference batches (of <=32 queries) per step per GPU")
     ap.add_argument("--dense", action="store_true", help="expand every row of every trie node (dense SpMM; roofline mode)")
+    ap.add_argument("--dense-tail", action="store_true", help="round-1 tail (dense [S][N][32] logit / gradient matrices) for A/B")
     ap.add_argument("--no-cpu-baseline", action="store_true")
-    ap.add_argument("--no-extras", action="store_true", help="skip the eval-mode / PredictorPlus side measurements")
+    ap.add_argument("--no-extras", action="store_true", help="skip the side configurations (configs / extras)")
+    ap.add_argument("--only", default="", help="comma-separated side configurations to run (default: all)")
+    ap.add_argument("--typed", action="store_true", help="headline on the typed synthetic graph instead of the i.i.d. one")
     ap.add_argument("--shape", default="fb15k237", choices=["fb15k237", "wn18rr"],
                     help="synthetic workload shape (the headline metric is quoted on fb15k237)")
     args = ap.parse_args()
@@ -237,18 +397,19 @@ def main():
 
     if args.impl == "reference" and rank != 0:
         return                                   # the CPU arm runs on rank 0 only; other ranks exit 0 without work
-    shape, N, R, train, valid, test, rules = build_workload(args.shape)
+    shape, N, R, train, valid, test, rules = build_workload(args.shape, typed=args.typed)
     batches = make_batches(train, R, seed=1)
-    workload = (shape["name"] + "-shape synthetic KG (N=%d, R=%d, E=%d train triples incl. inverses), %d synthetic rules "
-                "of the reference rule file's shape (L<=%d), Predictor(bias) train step, B=32 per batch, %d batches/step/GPU"
-                % (N, R, train.shape[0], len(rules), shape["max_len"], args.batches))
+    per = args.batches
+    workload = (shape["name"] + "-shape %s synthetic KG (N=%d, R=%d, E=%d train triples incl. inverses), %d synthetic rules "
+                "of the reference rule file's shape (L<=%d), Predictor(bias) train step, B=32 per batch, %d batches per optimizer step per GPU"
+                % ("typed" if args.typed else "i.i.d.", N, R, train.shape[0], len(rules), shape["max_len"], per))
 
     if args.impl == "reference":
-        res = cpu_reference_run(N, R, train, valid, test, rules, batches, args.steps, args.warmup, budget_s=120.0)
+        res = cpu_reference_run(N, R, train, valid, test, rules, batches, args.steps, args.warmup, per, budget_s=120.0)
         line = {"impl": "reference", "metric": METRIC, "value": res["value"], "unit": UNIT, "n_gpus": args.gpus,
                 "steps": res["steps_done"], "warmup": args.warmup, "ms_per_step": res["ms_per_step"],
                 "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "int64/f32",
-                "data": "synthetic", "config": {"workload": workload.replace("%d batches/step/GPU" % args.batches, "1 batch/step")},
+                "data": "synthetic", "config": {"workload": workload},
                 "cpu_baseline": {k: res[k] for k in ("value", "unit", "cores", "kind", "sample")},
                 "e2e": {"value": res["value"], "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
                 "gpu_launches": 0}
@@ -256,10 +417,9 @@ def main():
         return
 
     assert torch.cuda.is_available(), "bench.py needs a CUDA device (no CPU fallback)"
-    from rnnlogic_b200 import KnowledgeGraph, _lib
+    from rnnlogic_b200 import KnowledgeGraph
     from rnnlogic_b200.predictors import Predictor
     from rnnlogic_b200 import comm
-    from rnnlogic_b200.trainer import snake_deal
     dev = torch.device("cuda", local_rank)
     torch.cuda.set_device(dev)
     if world > 1:
@@ -274,96 +434,28 @@ def main():
     with torch.no_grad():
         model.rule_weights.copy_(torch.randn(model.num_rules, generator=g) * 0.1)
     model = model.cuda(dev)
-    from rnnlogic_b200.optim import Adam
-    opt = Adam(model.parameters(), lr=0.005)          # torch.optim.Adam semantics, one element per thread (rl_adam_step)
-    sk = model._driver(dev)
     cr = model.compiled
+    n_distinct = args.warmup + args.steps
+    run = Runner(model, deal_steps(batches, cr, per, n_distinct, world, rank), per, world, dev)
+    sk = run.sk
+    if args.dense_tail:                          # A/B: the round-1 dense tail behind the same loop
+        def dense_step(sk_, sl, smoothing, scale, gbuf, bits=32, expanded=False):
+            loss, tsum, _, gw, gb = model.step_on_slots_dense(sk_, sl, smoothing, scale, bits, expanded)
+            gbuf.view(model.rule_weights).copy_(gw)
+            gbuf.view(model.bias).copy_(gb)
+            return loss, tsum
+        model.step_on_slots = dense_step
+    run.size_cells()
 
-    per = args.batches
-    n_steps = args.warmup + args.steps
-    # query-batch sharding: every global step takes world*per batches and deals them to the ranks
-    # largest-first in snake order of their grounding cost (rows of the head's trie), so that the
-    # per-step all-reduce does not wait for one unlucky rank
-    step_batches = []
-    for s in range(n_steps):
-        glob = [batches[(s * per * world + j) % len(batches)] for j in range(per * world)]
-        mine = [glob[j] for j in snake_deal([int(cr.head_rows[int(b[0, 1])]) for b in glob], world, rank)]
-        step_batches.append(mine)
-    step_lists = step_batches            # int arrays [n,3] per batch, what the datasets hold (batch_arrays)
-    queries_per_step = [sum(len(b) for b in sb) for sb in step_batches]
-
-    def start_allreduce(gw, gb):
-        """One flat all-reduce of the gradients, asynchronous w.r.t. the compute stream."""
-        if world == 1:
-            return (gw, gb, None, None)
-        flat = torch.cat([gw, gb])
-        work = torch.distributed.all_reduce(flat, op=torch.distributed.ReduceOp.SUM, async_op=True)
-        return (gw, gb, flat, work)
-
-    def finish_step(pending):
-        gw, gb, flat, work = pending
-        if work is not None:
-            work.wait()
-            flat /= world
-            gw, gb = flat[:gw.numel()], flat[gw.numel():]
-        model.rule_weights.grad, model.bias.grad = gw, gb
-        opt.step()
-
-    def allreduce_and_step(gw, gb):
-        finish_step(start_allreduce(gw, gb))
-
-    # ---------------- device-resident timing (`value`) ----------------
-    slots = [sk.gr.make_slots_host(sl, with_etr=True) for sl in step_lists]       # inputs now in HBM
-    sk.gr.reserve(slots)                                                            # no cudaMalloc inside the timed loops
-    torch.cuda.synchronize()
-    if world > 1:
-        torch.distributed.barrier()
-    ovf_acc = torch.zeros(1, dtype=torch.int32, device=dev)
-    for s in range(args.warmup):
-        loss, tsum, _, gw, gb = model.step_on_slots(sk, slots[s], 0.2, 1.0 / per)
-        ovf_acc += slots[s].overflow
-        allreduce_and_step(gw, gb)
-    torch.cuda.synchronize()
-    assert int(ovf_acc.item()) == 0, "32-bit count overflow in warmup"
     clocks = ClockSampler(local_rank)
     if rank == 0:
         clocks.start()
-    if world > 1:
-        torch.distributed.barrier()
-    torch.cuda.synchronize()
-    launches0 = _lib.lib().rl_launch_count()
-    sk.gr.level_events = []
-    ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    ev0.record()
-    losses = []
-    sk.gr._run(slots[args.warmup], 32)
-    for s in range(args.warmup, n_steps):
-        ovf_acc += slots[s].overflow   # the frontier workspace is reused by the next step
-        loss, tsum, _, gw, gb = model.step_on_slots(sk, slots[s], 0.2, 1.0 / per, expanded=True)
-        pending = start_allreduce(gw, gb)
-        if s + 1 < n_steps:            # grounding is parameter-independent: run it under the all-reduce
-            sk.gr._run(slots[s + 1], 32)
-        finish_step(pending)
-        losses.append(loss)
-    ev1.record()
-    torch.cuda.synchronize()
-    if world > 1:
-        torch.distributed.barrier()
-    elapsed_ms = ev0.elapsed_time(ev1)
-    launches = _lib.lib().rl_launch_count() - launches0
-    level_events, sk.gr.level_events = sk.gr.level_events, None
-    ovf = int(ovf_acc.item())
-    assert ovf == 0, "32-bit count overflow inside the timed region (rerun needed in 64-bit)"
-    assert all(torch.isfinite(l).all().item() for l in losses)
-    t = torch.tensor([elapsed_ms], dtype=torch.float64, device=dev)
-    if world > 1:
-        torch.distributed.all_reduce(t, op=torch.distributed.ReduceOp.MAX)
-    elapsed_ms = float(t.item())
-    q_timed = sum(queries_per_step[args.warmup:])
-    qt = torch.tensor([q_timed], dtype=torch.float64, device=dev)
-    if world > 1:
-        torch.distributed.all_reduce(qt)
-    value = float(qt.item()) / (elapsed_ms / 1e3)
+    # ---------------- device-resident timing (`value`) ----------------
+    elapsed_ms, q_timed, launches, level_events = run.device_loop(args.warmup, args.steps, level_events=True)
+    step_ms_local = elapsed_ms
+    elapsed_ms, q_total = reduce_max_sum(elapsed_ms, q_timed, dev, world)
+    value = q_total / (elapsed_ms / 1e3)
+    slots = run.slots
 
     # roofline of the dominant kernel (frontier expansion = k_symbolic + k_numeric per depth):
     # algorithmic bytes of SURVEY 8d for the timed heads / CUDA-event time of the expansion launches
@@ -374,13 +466,6 @@ def main():
     except OSError:
         pass
     peak = float(peaks.get("hbm_gbs", 6650.0))
-
-    traffic = None
-    try:      # DRAM bytes of the expansion launches from the committed ncu capture (dense mode; made for a given --batches)
-        with open(os.path.join(ROOT, "profiles", "r1_traffic.json")) as f:
-            traffic = json.load(f)
-    except OSError:
-        pass
 
     def roofline_of(events, heads, step_ms, mode, note):
         exp_ms = {}
@@ -397,25 +482,27 @@ def main():
                 "ms_by_depth": {str(k): v for k, v in sorted(exp_ms.items())}, "share_of_step": tot / step_ms,
                 "note": note}
 
+    n_steps = args.warmup + args.steps
     heads_timed = np.concatenate([slots[s].heads for s in range(args.warmup, n_steps)])
     roofline_product = roofline_of(
-        level_events, heads_timed, ev0.elapsed_time(ev1), "dense SpMM" if model.force_dense else "sparse-aware (product path)",
+        level_events, heads_timed, step_ms_local, "dense SpMM" if model.force_dense else "sparse-aware (product path)",
         "rows that are provably all-zero are neither written nor read (exact); a fraction above 1 is sparsity "
-        "exploitation on the i.i.d. synthetic graph, not bandwidth" if not model.force_dense else "every algorithmic byte is moved")
+        "exploitation, not bandwidth" if not model.force_dense else "every algorithmic byte is moved")
     roofline = roofline_product
     if not model.force_dense:
         # the same kernel as a plain dense SpMM on the same workload (every row of every trie node is
         # written and read, zeros included): the figure that says how close the kernel is to HBM
         sk.gr.force_dense = True
         nd = min(args.steps, 5)
+        torch.cuda.synchronize()
         for s in range(3):
-            model.step_on_slots(sk, slots[s], 0.2, 1.0 / per)
+            sk.gr._run(slots[s], 32)
         torch.cuda.synchronize()
         sk.gr.level_events = []
         d0, d1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         d0.record()
         for s in range(args.warmup, args.warmup + nd):
-            model.step_on_slots(sk, slots[s], 0.2, 1.0 / per)
+            sk.gr._run(slots[s], 32)
         d1.record()
         torch.cuda.synchronize()
         dense_events, sk.gr.level_events = sk.gr.level_events, None
@@ -423,79 +510,113 @@ def main():
         heads_d = np.concatenate([slots[s].heads for s in range(args.warmup, args.warmup + nd)])
         roofline = roofline_of(dense_events, heads_d, d0.elapsed_time(d1), "dense expansion (force_dense), same kernel + workload",
                                "every row of every trie node is expanded (all in-edges examined); rows that are zero for "
-                               "EVERY query (no in-edge from the parent relation's tails) and L2 hits keep DRAM traffic "
-                               "below the algorithmic bytes; timed in a second region right after the product loop "
-                               "(%d steps)" % nd)
-        if traffic is not None and per == traffic.get("batches_per_step", 64):
-            roofline["traffic"] = traffic["dram_bytes_per_launch"]
-            roofline["traffic_source"] = traffic["source"]
+                               "EVERY query and L2 hits keep DRAM traffic below the algorithmic bytes; the expansion alone, "
+                               "timed in a second region right after the product loop (%d steps)" % nd)
 
-    # ---------------- end-to-end through the public fused API (host lists in, losses out) --------
-    torch.cuda.synchronize()
-    if world > 1:
-        torch.distributed.barrier()
-    h2d = d2h = 0
-    for s in range(args.warmup):            # same pipelined API as the timed loop: warms its pinned staging buffers too
-        tk = model.submit_train_step(step_lists[s], 0.2, grad_scale=1.0 / per)
-        allreduce_and_step(tk.gw, tk.gb)
-        tk.result()
-    torch.cuda.synchronize()
-    if world > 1:
-        torch.distributed.barrier()
-    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    e0.record()
-    # software pipeline: a loader thread packs the host batches two steps ahead; step k+1 is copied / grounded
-    # while step k's gradients are exchanged (grounding does not depend on the parameters); every step still
-    # does its own H2D of the queries and its own D2H read of the losses
-    from rnnlogic_b200.data import StepPrefetcher
-    packed = StepPrefetcher(model.pack_train_step, step_lists[args.warmup:n_steps], depth=2)   # loader thread, inside the timed region
-    ticket = model.submit_train_step(next(packed), 0.2, grad_scale=1.0 / per)
-    trace = []                                      # --trace-e2e: host wall time of (enqueue, wait) per step
-    for s in range(args.warmup, n_steps):
-        t_a = time.perf_counter()
-        pending = start_allreduce(ticket.gw, ticket.gb)
-        prep = model.prepare_train_step(next(packed)) if s + 1 < n_steps else None
-        finish_step(pending)
-        nxt = prep.finish(0.2, grad_scale=1.0 / per) if prep is not None else None
-        t_b = time.perf_counter()
-        loss, tsum = ticket.result()
-        trace.append((t_b - t_a, time.perf_counter() - t_b))
-        assert torch.isfinite(loss).all()
-        h2d += ticket.h2d_bytes
-        d2h += ticket.d2h_bytes
-        ticket = nxt
-    e1.record()
-    torch.cuda.synchronize()
-    e2e_ms = e0.elapsed_time(e1)
-    te = torch.tensor([e2e_ms], dtype=torch.float64, device=dev)
-    if world > 1:
-        torch.distributed.all_reduce(te, op=torch.distributed.ReduceOp.MAX)
-    e2e_value = float(qt.item()) / (float(te.item()) / 1e3)
+    # ---------------- end-to-end through the public fused API (host arrays in, losses out) --------
+    trace = [] if args.trace_e2e else None
+    e2e_ms, q_e2e, h2d, d2h = run.e2e_loop(args.warmup, args.steps, trace)
+    e2e_ms, q_e2e = reduce_max_sum(e2e_ms, q_e2e, dev, world)
+    e2e_value = q_e2e / (e2e_ms / 1e3)
     if args.trace_e2e and rank == 0:
         print("e2e per step, host enqueue/wait ms: " + " ".join("%.2f/%.2f" % (a * 1e3, b * 1e3) for a, b in trace), file=sys.stderr)
 
-    clk = clocks.stop() if rank == 0 else None      # sampled over all timed regions (value, dense roofline, e2e)
+    line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
+            "ms_per_step": elapsed_ms / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+            "dtype": "u32/f32", "data": "synthetic",
+            "config": {"workload": workload, "queries_per_step_per_gpu": int(np.mean(run.queries)),
+                       "l2_policy": "per-step working set (frontier arena %.1f GB) is larger than the 126 MB L2"
+                                    % (float(cr.head_rows[heads_timed].sum()) * 128 / args.steps / 1e9),
+                       "parallelism": "dp%d (queries sharded, KG replicated)" % world,
+                       "dense_expansion": bool(model.force_dense), "tail": "dense Z/G matrices" if args.dense_tail else "candidate cells"},
+            "roofline": roofline, "roofline_product": roofline_product,
+            "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d // args.steps,
+                    "d2h_bytes_per_step": d2h // args.steps},
+            "gpu_launches": int(launches)}
+
+    # ---------------- the other configurations BASELINE.json names, same end-to-end loop ----------------
+    if not args.no_extras:
+        only = set(x for x in args.only.split(",") if x)
+        want = lambda t: not only or t in only
+        cfgs = {}
+        side_steps = max(20, min(args.steps, 30))
+        fb_plus = dict(type="lstm", num_layers=3, hidden_dim=16, entity_feature="bias", aggregator="sum")
+        if want("reference_schedule_b1"):        # the reference's own schedule: ONE 32-query batch per optimizer step
+            cfgs["reference_schedule_b1"] = side_config("b1", kg, rules, batches, dict(entity_feature="bias"), 1, 200, world, rank, dev, plus=False)
+            cfgs["reference_schedule_b1"]["model"] = "Predictor(bias), 1 batch of <=32 queries per optimizer step (src/trainer.py:68-95)"
+        if want("eval_filtered_rank"):
+            tb = make_batches(test, R, seed=2)
+            pe = min(per, 64)
+            st = {"i": 0}
+
+            def eval_step():
+                sb = [tb[(st["i"] * pe + j) % len(tb)] for j in range(pe)]
+                st["i"] += 1
+                model.fused_rank(sb, "test")
+                st["q"] = sum(len(b) for b in sb)
+
+            for _ in range(3):
+                eval_step()
+            torch.cuda.synchronize()
+            a0, a1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            a0.record()
+            for _ in range(10):
+                eval_step()
+            a1.record()
+            torch.cuda.synchronize()
+            cfgs["eval_filtered_rank"] = {"e2e_queries_per_sec": st["q"] * 10 / (a0.elapsed_time(a1) / 1e3), "batches_per_call": pe,
+                                          "model": "Predictor(bias): ground -> cells -> filtered rank (L,H)"}
+        if want("fb15k237_plus_lstm_sum_bias"):  # config/FB15k-237_predictorplus.yaml
+            cfgs["fb15k237_plus_lstm_sum_bias"] = side_config("plus", kg, rules, batches, fb_plus, per, side_steps, world, rank, dev)
+            cfgs["fb15k237_plus_lstm_sum_bias"]["model"] = "PredictorPlus(lstm x3, sum, bias, H=16): the reference's shipped FB15k-237 config"
+        if want("fb15k237_plus_lstm_sum_rotate1000"):   # BASELINE config 4
+            kw = dict(fb_plus, entity_feature="RotatE", embedding_path=rotate_dir(N, R))
+            p4 = min(per, 64)
+            cfgs["fb15k237_plus_lstm_sum_rotate1000"] = side_config("rot", kg, rules, batches, kw, p4, side_steps, world, rank, dev)
+            c4 = cfgs["fb15k237_plus_lstm_sum_rotate1000"]
+            c4["model"] = "PredictorPlus(lstm, sum) + RotatE-shaped random entity feature D=1000 (BASELINE config 4)"
+            flop = 13.0 * 32 * N * 1000 * 2.5                    # forward 13 B N D + backward ~1.5x, per 32-query batch
+            c4["fp32_fraction"] = {"flop_per_batch": flop, "achieved_tflops": flop * p4 / (c4["ms_per_step"] / 1e3) / 1e12,
+                                   "peak_tflops": 148 * 128 * 2 * 1.965e-3, "note": "RotatE epilogue is FP32/MUFU work: "
+                                   "13*B*N*D flop forward (SURVEY 8d), ~1.5x that backward; peak = 148 SMs x 128 FMA lanes x 2 x 1.965 GHz"}
+            c4["fp32_fraction"]["frac"] = c4["fp32_fraction"]["achieved_tflops"] / c4["fp32_fraction"]["peak_tflops"]
+        del model, run
+        torch.cuda.empty_cache()
+        if want("fb15k237_typed_predictor_bias"):        # same sizes, rule bodies that compose
+            _, tN, tR, ttrain, tvalid, ttest, trules = build_workload("fb15k237", typed=True)
+            tkg = KnowledgeGraph(entity_size=tN, relation_size=tR, train=ttrain, valid=tvalid, test=ttest)
+            tb_ = make_batches(ttrain, tR, seed=1)
+            pt = min(per, 64)
+            cfgs["fb15k237_typed_predictor_bias"] = side_config("typed", tkg, trules, tb_, dict(entity_feature="bias"), pt, side_steps, world, rank, dev, plus=False)
+            cfgs["fb15k237_typed_predictor_bias"]["model"] = ("Predictor(bias) on a TYPED graph of the same sizes (12 entity types, every relation "
+                                                             "has a domain/range, rule bodies are type-compatible chains): frontiers stay alive")
+            if want("fb15k237_typed_plus_lstm_sum_bias"):
+                cfgs["fb15k237_typed_plus_lstm_sum_bias"] = side_config("typedp", tkg, trules, tb_, fb_plus, pt, side_steps, world, rank, dev)
+                cfgs["fb15k237_typed_plus_lstm_sum_bias"]["model"] = "PredictorPlus(lstm, sum, bias) on the typed graph"
+            del tkg
+        if want("wn18rr_plus_emb_pna_bias"):             # BASELINE config 3: config/wn18rr_predictorplus.yaml
+            _, wN, wR, wtrain, wvalid, wtest, wrules = build_workload("wn18rr")
+            wkg = KnowledgeGraph(entity_size=wN, relation_size=wR, train=wtrain, valid=wvalid, test=wtest)
+            wb = make_batches(wtrain, wR, seed=1)
+            pw = min(per, 64)
+            cfgs["wn18rr_plus_emb_pna_bias"] = side_config("wn", wkg, wrules, wb, dict(type="emb", hidden_dim=16, entity_feature="bias", aggregator="pna"),
+                                                           pw, side_steps, world, rank, dev)
+            cfgs["wn18rr_plus_emb_pna_bias"]["model"] = "PredictorPlus(emb, pna, bias) on the WN18RR shape (BASELINE config 3)"
+            if want("wn18rr_predictor_bias"):
+                cfgs["wn18rr_predictor_bias"] = side_config("wnp", wkg, wrules, wb, dict(entity_feature="bias"), pw, side_steps, world, rank, dev, plus=False)
+                cfgs["wn18rr_predictor_bias"]["model"] = "Predictor(bias) on the WN18RR shape (L<=5)"
+            del wkg
+        line["configs"] = cfgs
+
+    clk = clocks.stop() if rank == 0 else None      # sampled over all timed regions
+    line["clocks"] = clk
     if world > 1:
         torch.distributed.barrier()
         torch.distributed.destroy_process_group()
     if rank != 0:
         return
-    line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
-            "ms_per_step": elapsed_ms / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
-            "dtype": "u32/f32", "data": "synthetic",
-            "config": {"workload": workload, "queries_per_step_per_gpu": int(np.mean(queries_per_step)),
-                       "l2_policy": "per-step working set (frontier arena %.1f GB) is larger than the 126 MB L2"
-                                    % (float(cr.head_rows[heads_timed].sum()) * 128 / args.steps / 1e9),
-                       "parallelism": "dp%d (queries sharded, KG replicated)" % world,
-                       "dense_expansion": bool(model.force_dense)},
-            "roofline": roofline, "roofline_product": roofline_product,
-            "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d // args.steps,
-                    "d2h_bytes_per_step": d2h // args.steps},
-            "gpu_launches": int(launches), "clocks": clk}
-    if world == 1 and not args.no_extras:
-        line["extras"] = extras(args, kg, model, rules, batches, test, valid, dev)
     if world == 1 and not args.no_cpu_baseline:
-        res = cpu_reference_run(N, R, train, valid, test, rules, batches, 1000, 1, budget_s=15.0)
+        res = cpu_reference_run(N, R, train, valid, test, rules, batches, 1000, 1, per, budget_s=15.0)
         line["cpu_baseline"] = {k: res[k] for k in ("value", "unit", "cores", "kind", "sample")}
     print(json.dumps(line))
 

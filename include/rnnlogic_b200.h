@@ -29,7 +29,7 @@ extern "C" {
 #endif
 
 #define RL_LANES 32
-#define RL_ABI_VERSION 1
+#define RL_ABI_VERSION 2
 
 enum rl_status {
     RL_OK = 0,
@@ -131,6 +131,13 @@ typedef struct rl_frontier {
     int32_t *item_cnt;
     int32_t *bucket_cnt;
     int32_t *bucket_off;
+    /* Lane mask of every item (bit b: the count of query b in that row is non-zero), written by k_numeric
+     * next to the item and carried through the sort.  The OR of an entity's item masks is its candidate
+     * word nzmask[slot][entity] (predictors.py:224-225,239: a cell is a candidate iff its total count is
+     * non-zero); rl_sort_items accumulates it when nzmask != NULL ([S][N], zeroed by the caller). */
+    uint32_t *item_mask;
+    uint32_t *item_mask_sorted;
+    uint32_t *nzmask;
 } rl_frontier;
 
 /* Known-answer lists, replaces KnowledgeGraph.hr2o / hr2oo / hr2ooo (src/data.py:36-38,49-61,
@@ -142,6 +149,21 @@ typedef struct rl_answers {
     const int32_t *ptr;   /* [num_keys+1] */
     const int32_t *ent;   /* [ptr[num_keys]] */
 } rl_answers;
+
+/* Candidate cells of a call (rl_cells.cu).  A cell is a (query, entity) pair with a non-zero total path
+ * count (src/predictors.py:224-225,239: mask != 0 -> candidate_set).  Cells are numbered slot by slot,
+ * entity-major, lane-minor; the cells of entity e of slot s are cand_off[s*N+e] .. + popc(nzmask[s*N+e]).
+ * All DEVICE memory owned by the caller; counters must be zero before rl_cells_build.  When the call has
+ * more cells than `cap`, counters[1] is set, cells beyond cap are skipped by every kernel, and the caller
+ * redoes the call with larger per-cell arrays. */
+typedef struct rl_cells {
+    int32_t cap;          /* capacity of the per-cell arrays */
+    int32_t *counters;    /* [8]: [0] number of cells, [1] != 0: cap exceeded */
+    uint32_t *nzmask;     /* [S][N] candidate word per entity (= rl_frontier.nzmask) */
+    int32_t *cand_off;    /* [S][N] first cell of the entity */
+    int32_t *cell_key;    /* [cap] slot*32 + lane of the cell */
+    int32_t *slot_ncell;  /* [S] cells per slot (= mask.sum() of the batch without an entity feature, trainer.py:96) */
+} rl_cells;
 
 int rl_abi_version(void);
 const char *rl_last_error(void);
@@ -182,6 +204,13 @@ int rl_sort_items(const rl_graph *g, const rl_slots *s, const rl_frontier *fr, v
  * return value of KnowledgeGraph.grounding (src/data.py:147). */
 int rl_node_counts_dense(const rl_graph *g, const rl_rules *r, const rl_slots *s, int32_t slot,
                          int32_t node, const rl_frontier *fr, int64_t *out, void *stream);
+
+/* One hop from an arbitrary dense frontier: KnowledgeGraph.propagate (src/data.py:149-173).  x / out are
+ * the reference's int64 [N][B] (its [N,B,1] tensor); etr (may be NULL) holds one index per query into the
+ * relation's train-order edge list whose message is dropped for that query (data.py:164-170).  int64
+ * arithmetic, wraps like the reference. */
+int rl_propagate_dense(const rl_graph *g, int32_t relation, int32_t B, const int64_t *x, const int64_t *etr,
+                       int64_t *out, void *stream);
 
 /* Kernel (2a): rule-weight aggregation, replaces the loop of Predictor.forward
  * (src/predictors.py:58-65,73-78).  Z[S][N][32] fp32 = sum_rule w_rule * fp32(count) (+ bias[e]
@@ -358,6 +387,75 @@ int rl_slot_to_dense(int32_t N, int32_t nq, const float *Z_slot, float *out, int
                      void *stream);
 int rl_mask_to_dense(int32_t N, int32_t nq, const uint32_t *nzmask_slot, uint8_t *out,
                      int64_t out_stride, void *stream);
+
+/* ---- the scoring half on candidate cells (rl_cells.cu, rl_tail2.cu): no [S][N][32] matrix ---- */
+
+/* Group the frontier's items by entity (rl_sort_items, which also ORs the items' lane masks into nzmask) and
+ * number the cells: cand_off, cell_key, slot_ncell, counters[0..1].  Replaces torch.nonzero(mask)
+ * (src/predictors.py:239) without a host sync. */
+int rl_cells_build(const rl_graph *g, const rl_rules *r, const rl_slots *s, const rl_frontier *fr,
+                   const rl_cells *c, void *stream);
+
+/* acc[0] = max_e bias[e], acc[1] = sum_e exp(bias[e] - acc[0]) (doubles, DEVICE); acc[2] is scratch of
+ * rl_cells_softmax_ce.  Once per parameter update. */
+int rl_bias_stats(int32_t N, const float *bias, double *acc, void *stream);
+
+/* Predictor (src/predictors.py:58-65): zc[cell] = sum_rule w_rule * fp32(count), without the bias. */
+int rl_predictor_cell_scores(const rl_graph *g, const rl_rules *r, const rl_slots *s, const rl_frontier *fr,
+                             const rl_cells *c, const float *w, float *zc, void *stream);
+
+/* Floats of `partial` scratch per slot for rl_cells_softmax_ce. */
+int rl_cells_partial_floats(void);
+
+/* log(softmax + 1e-8) cross-entropy against the smoothed multi-hot target (src/trainer.py:84,88-89) with the
+ * logits given as cell scores zc plus bias[e] for EVERY entity (bias != NULL; predictors.py:257-262), or as
+ * the cell scores alone with -inf elsewhere (bias == NULL; predictors.py:267-269).  Same outputs as
+ * rl_softmax_ce (group_loss, group_tsum; stats [S][32][4], slot_sums [3*S], partial
+ * [S*rl_cells_partial_floats()] are scratch).  Gc != NULL: Gc[cell] = grad_scale * dloss/dlogit and, with a
+ * bias, grad_bias[N] += grad_scale * dloss/dbias (rank-one term + cell and target corrections). */
+int rl_cells_softmax_ce(const rl_graph *g, const rl_slots *s, const rl_cells *c, const rl_answers *ans,
+                        float smoothing, const float *bias, double *acc, const float *zc, int32_t n_groups,
+                        const int32_t *group_ptr, float grad_scale, float *partial, float *stats,
+                        float *slot_sums, float *group_loss, float *group_tsum, float *Gc, float *grad_bias,
+                        void *stream);
+
+/* Predictor backward: grad_w[rule] += sum over the rule's non-zero rows of <Gc[cells], fp32(counts)>. */
+int rl_predictor_cell_backward(const rl_graph *g, const rl_rules *r, const rl_slots *s, const rl_frontier *fr,
+                               const rl_cells *c, const float *Gc, float *grad_w, void *stream);
+
+/* Filtered rank (src/trainer.py:189-201) from cell scores: (L,H) int64[S*32][2].  With a bias the entities
+ * outside a query's cells are counted by binary search in sorted_bias (bias sorted ascending);
+ * counters int32[S*64] is scratch. */
+int rl_cells_rank(const rl_graph *g, const rl_slots *s, const rl_cells *c, const rl_answers *known,
+                  const float *bias, const float *sorted_bias, const float *zc, int32_t *counters, int64_t *LH,
+                  void *stream);
+
+/* Z[S][N][32] += zc at the cells / Gc = G at the cells (dense entity features such as RotatE, API forward). */
+int rl_cells_add_to_dense(const rl_graph *g, const rl_slots *s, const rl_cells *c, const float *zc, float *Z, void *stream);
+int rl_cells_gather_dense(const rl_graph *g, const rl_slots *s, const rl_cells *c, const float *G, float *Gc, void *stream);
+
+/* PredictorPlus aggregates per cell (src/layers.py:68-72 / 92-99), hidden_dim 16, emb[num_rules][16] indexed by
+ * the global rule id: out_sum[cell][16]; PNA also out_sq, out_min, out_max, arg_min, arg_max, degree[cell]. */
+int rl_plus_cell_features(const rl_graph *g, const rl_rules *r, const rl_slots *s, const rl_frontier *fr,
+                          const rl_cells *c, const float *emb, int32_t H, int32_t pna, float *out_sum, float *out_sq,
+                          float *out_min, float *out_max, int32_t *arg_min, int32_t *arg_max, float *degree, void *stream);
+
+/* grad_emb[rule][16] += sum over the rule's non-zero (row, query) pairs of fp32(count) * dF[cell][16]. */
+int rl_plus_cell_backward(const rl_graph *g, const rl_rules *r, const rl_slots *s, const rl_frontier *fr,
+                          const rl_cells *c, int32_t H, const float *dF, float *grad_emb, void *stream);
+
+/* Dense tail of PredictorPlus with the sum aggregator on the cells (src/layers.py:73-75,
+ * src/predictors.py:253-255), H = 16, J = 128: zc[cell] = W2 . relu(W1 [relu(LN(W0 F + b0)), rel[head]] + b1) + b2.
+ * The backward ACCUMULATES every weight gradient in-kernel (layouts of the parameters), writes dF[cell][16]
+ * and needs d1sum[R][128] scratch. */
+int rl_tail_forward(const rl_cells *c, const int32_t *slot_head, int32_t H, int32_t J, const float *F, const float *W0,
+                    const float *b0, const float *gamma, const float *beta, const float *W1, const float *b1,
+                    const float *W2, const float *b2, const float *rel_emb, float *zc, void *stream);
+int rl_tail_backward(const rl_cells *c, const int32_t *slot_head, int32_t R, int32_t H, int32_t J, const float *F,
+                     const float *W0, const float *b0, const float *gamma, const float *beta, const float *W1,
+                     const float *b1, const float *W2, const float *b2, const float *rel_emb, const float *Gc,
+                     float *dF, float *gW0, float *gb0, float *ggamma, float *gbeta, float *gW1, float *gb1,
+                     float *gW2, float *gb2, float *grel, float *d1sum, void *stream);
 
 #ifdef __cplusplus
 }

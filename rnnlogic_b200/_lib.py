@@ -12,7 +12,7 @@ import subprocess
 _HERE = os.path.dirname(os.path.abspath(__file__))
 ROOT = os.path.dirname(_HERE)
 LIB_PATH = os.environ.get("RNNLOGIC_B200_LIB") or os.path.join(_HERE, "lib", "librnnlogic_b200.so")   # env override: A/B builds
-SOURCES = [os.path.join(_HERE, "csrc", f) for f in ("rl_kernels.cu", "rl_plus.cu", "rl_rotate.cu", "rl_tail.cu", "rl_rnn.cu")]
+SOURCES = [os.path.join(_HERE, "csrc", f) for f in ("rl_kernels.cu", "rl_cells.cu", "rl_plus.cu", "rl_rotate.cu", "rl_tail.cu", "rl_tail2.cu", "rl_rnn.cu")]
 HEADER = os.path.join(ROOT, "include", "rnnlogic_b200.h")
 
 LANES = 32
@@ -44,7 +44,13 @@ class RlSlots(C.Structure):
 class RlFrontier(C.Structure):
     _fields_ = [("count_bits", C.c_int32), ("arena", vp), ("row_mask", vp), ("node_cnt", vp),
                 ("overflow", vp), ("items", vp), ("items_sorted", vp), ("item_off", vp),
-                ("item_cnt", vp), ("bucket_cnt", vp), ("bucket_off", vp)]
+                ("item_cnt", vp), ("bucket_cnt", vp), ("bucket_off", vp),
+                ("item_mask", vp), ("item_mask_sorted", vp), ("nzmask", vp)]
+
+
+class RlCells(C.Structure):
+    _fields_ = [("cap", C.c_int32), ("counters", vp), ("nzmask", vp), ("cand_off", vp), ("cell_key", vp),
+                ("slot_ncell", vp)]
 
 
 class RlAnswers(C.Structure):
@@ -115,6 +121,7 @@ _PROTOS = {
     "rl_sort_items": (C.c_int, [C.POINTER(RlGraph), C.POINTER(RlSlots), C.POINTER(RlFrontier), vp]),
     "rl_node_counts_dense": (C.c_int, [C.POINTER(RlGraph), C.POINTER(RlRules), C.POINTER(RlSlots), C.c_int32,
                                        C.c_int32, C.POINTER(RlFrontier), vp, vp]),
+    "rl_propagate_dense": (C.c_int, [C.POINTER(RlGraph), C.c_int32, C.c_int32, vp, vp, vp, vp]),
     "rl_predictor_scores": (C.c_int, [C.POINTER(RlGraph), C.POINTER(RlRules), C.POINTER(RlSlots),
                                       C.POINTER(RlFrontier), vp, vp, C.c_int32, vp, vp, vp, vp]),
     "rl_predictor_ce_backward": (C.c_int, [C.POINTER(RlGraph), C.POINTER(RlRules), C.POINTER(RlSlots),
@@ -143,6 +150,26 @@ _PROTOS = {
     "rl_rotate_scores": (C.c_int, [C.POINTER(RlGraph), C.POINTER(RlSlots), C.c_int32, C.c_float, vp, vp, vp, vp, vp]),
     "rl_rotate_backward": (C.c_int, [C.POINTER(RlGraph), C.POINTER(RlSlots), C.c_int32, C.c_float, vp, vp, vp, vp, vp,
                                      vp, vp, vp]),
+    "rl_cells_build": (C.c_int, [C.POINTER(RlGraph), C.POINTER(RlRules), C.POINTER(RlSlots), C.POINTER(RlFrontier),
+                                 C.POINTER(RlCells), vp]),
+    "rl_bias_stats": (C.c_int, [C.c_int32, vp, vp, vp]),
+    "rl_predictor_cell_scores": (C.c_int, [C.POINTER(RlGraph), C.POINTER(RlRules), C.POINTER(RlSlots),
+                                           C.POINTER(RlFrontier), C.POINTER(RlCells), vp, vp, vp]),
+    "rl_cells_partial_floats": (C.c_int, []),
+    "rl_cells_softmax_ce": (C.c_int, [C.POINTER(RlGraph), C.POINTER(RlSlots), C.POINTER(RlCells), C.POINTER(RlAnswers),
+                                      C.c_float, vp, vp, vp, C.c_int32, vp, C.c_float, vp, vp, vp, vp, vp, vp, vp, vp]),
+    "rl_predictor_cell_backward": (C.c_int, [C.POINTER(RlGraph), C.POINTER(RlRules), C.POINTER(RlSlots),
+                                             C.POINTER(RlFrontier), C.POINTER(RlCells), vp, vp, vp]),
+    "rl_cells_rank": (C.c_int, [C.POINTER(RlGraph), C.POINTER(RlSlots), C.POINTER(RlCells), C.POINTER(RlAnswers),
+                                vp, vp, vp, vp, vp, vp]),
+    "rl_cells_add_to_dense": (C.c_int, [C.POINTER(RlGraph), C.POINTER(RlSlots), C.POINTER(RlCells), vp, vp, vp]),
+    "rl_cells_gather_dense": (C.c_int, [C.POINTER(RlGraph), C.POINTER(RlSlots), C.POINTER(RlCells), vp, vp, vp]),
+    "rl_plus_cell_features": (C.c_int, [C.POINTER(RlGraph), C.POINTER(RlRules), C.POINTER(RlSlots), C.POINTER(RlFrontier),
+                                        C.POINTER(RlCells), vp, C.c_int32, C.c_int32, vp, vp, vp, vp, vp, vp, vp, vp]),
+    "rl_plus_cell_backward": (C.c_int, [C.POINTER(RlGraph), C.POINTER(RlRules), C.POINTER(RlSlots), C.POINTER(RlFrontier),
+                                        C.POINTER(RlCells), C.c_int32, vp, vp, vp]),
+    "rl_tail_forward": (C.c_int, [C.POINTER(RlCells), vp, C.c_int32, C.c_int32] + [vp] * 12),
+    "rl_tail_backward": (C.c_int, [C.POINTER(RlCells), vp, C.c_int32, C.c_int32, C.c_int32] + [vp] * 23),
     "rl_adam_step": (C.c_int, [C.c_int64, vp, vp, vp, vp, C.c_float, C.c_float, C.c_float, C.c_float, C.c_float,
                                C.c_int64, vp]),
     "rl_lstm_encode_forward": (C.c_int, [C.c_int32, C.c_int32, C.c_int32, C.c_int32, vp, vp, vp, vp, vp, vp, vp]),

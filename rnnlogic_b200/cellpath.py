@@ -1,0 +1,296 @@
+"""Fused train / eval steps on candidate cells (csrc/rl_cells.cu, rl_tail2.cu): what TrainerPredictor and
+bench.py run.  Nothing of size [B,N] is built; no host synchronisation happens inside a step -- the
+candidate count stays on the device (the reference syncs on it four times per batch,
+src/predictors.py:211,230,239, src/layers.py:65) and comes back with the losses in the step's one D2H read.
+
+Reference semantics: Predictor.forward / PredictorPlus.forward (src/predictors.py:53-80, 210-271) +
+the loss of TrainerPredictor.train (src/trainer.py:84-93) + the rank of evaluate (src/trainer.py:189-201)."""
+from __future__ import annotations
+
+import ctypes as C
+from typing import List, Optional
+
+import numpy as np
+import torch
+
+from . import _lib
+from .engine import _stream
+
+LANES = _lib.LANES
+_L = _lib.lib
+
+
+def _ptr(t: Optional[torch.Tensor]):
+    return None if t is None else t.data_ptr()
+
+
+class GradBuffer:
+    """One flat fp32 gradient buffer with a view per parameter: kernels accumulate into the views, the
+    data-parallel exchange all-reduces ``flat`` directly (no torch.cat per step)."""
+
+    def __init__(self, params: List[torch.nn.Parameter]):
+        self.params = list(params)
+        sizes = [p.numel() for p in self.params]
+        offs = np.concatenate([[0], np.cumsum([(n + 3) // 4 * 4 for n in sizes])])     # 16-byte aligned views
+        dev = self.params[0].device
+        self.flat = torch.zeros(int(offs[-1]), dtype=torch.float32, device=dev)
+        self.views = [self.flat[int(o):int(o) + n].view_as(p) for o, n, p in zip(offs[:-1], sizes, self.params)]
+        self.of = {id(p): v for p, v in zip(self.params, self.views)}
+
+    def view(self, p):
+        return self.of[id(p)]
+
+    def assign(self, used=None):
+        """p.grad = its view (parameters not in ``used`` keep grad None: DDP find_unused_parameters semantics)."""
+        for p, v in zip(self.params, self.views):
+            p.grad = v if (used is None or id(p) in used) else None
+
+
+class CellKernels:
+    """ctypes drivers of the cell kernels for one ScoreKernels (= one device)."""
+
+    def __init__(self, sk):
+        self.sk = sk
+        self.gr, self.dg, self.dr = sk.gr, sk.dg, sk.dr
+        self.N, self.device = sk.N, sk.device
+        self.acc = torch.zeros(4, dtype=torch.float64, device=self.device)       # Mg, Sg, K
+        self.pf = _L().rl_cells_partial_floats()
+        self._bias_version = None
+
+    def bias_stats(self, bias: torch.Tensor):
+        _lib.check(_L().rl_bias_stats(self.N, bias.data_ptr(), self.acc.data_ptr(), _stream()), "rl_bias_stats")
+
+    def predictor_scores(self, sl, w, zc):
+        _lib.check(_L().rl_predictor_cell_scores(self.dg.ref(), self.dr.ref(), sl.ref(), sl.fref(), C.byref(sl.cells),
+                                                 w.data_ptr(), zc.data_ptr(), _stream()), "rl_predictor_cell_scores")
+
+    def softmax_ce(self, sl, bias, zc, smoothing, group_ptr, n_groups, grad_scale, Gc, grad_bias):
+        """-> (group_loss, group_tsum) device tensors; Gc / grad_bias filled when Gc is given."""
+        dev, S = self.device, sl.S
+        scr = torch.empty(S * (self.pf + LANES * 4 + 3) + 2 * n_groups, dtype=torch.float32, device=dev)
+        partial, stats = scr[:S * self.pf], scr[S * self.pf:S * (self.pf + LANES * 4)]
+        slot_sums = scr[S * (self.pf + LANES * 4):S * (self.pf + LANES * 4 + 3)]
+        out = scr[S * (self.pf + LANES * 4 + 3):].view(2, n_groups)
+        ans, _keep = self.dg.answers["hr2o"]
+        _lib.check(_L().rl_cells_softmax_ce(
+            self.dg.ref(), sl.ref(), C.byref(sl.cells), C.byref(ans), float(smoothing), _ptr(bias), self.acc.data_ptr(),
+            zc.data_ptr(), int(n_groups), _ptr(group_ptr), float(grad_scale), partial.data_ptr(), stats.data_ptr(),
+            slot_sums.data_ptr(), out[0].data_ptr(), out[1].data_ptr(), _ptr(Gc), _ptr(grad_bias), _stream()),
+            "rl_cells_softmax_ce")
+        return out[0], out[1]
+
+    def predictor_backward(self, sl, Gc, grad_w):
+        _lib.check(_L().rl_predictor_cell_backward(self.dg.ref(), self.dr.ref(), sl.ref(), sl.fref(), C.byref(sl.cells),
+                                                   Gc.data_ptr(), grad_w.data_ptr(), _stream()), "rl_predictor_cell_backward")
+
+    def rank(self, sl, bias, sorted_bias, zc, which):
+        counters = torch.empty(sl.S * 64, dtype=torch.int32, device=self.device)
+        LH = torch.empty(sl.S * LANES, 2, dtype=torch.int64, device=self.device)
+        known, _keep = self.dg.answers[which]
+        _lib.check(_L().rl_cells_rank(self.dg.ref(), sl.ref(), C.byref(sl.cells), C.byref(known), _ptr(bias),
+                                      _ptr(sorted_bias), zc.data_ptr(), counters.data_ptr(), LH.data_ptr(), _stream()),
+                   "rl_cells_rank")
+        return LH
+
+    def add_to_dense(self, sl, zc, Z):
+        _lib.check(_L().rl_cells_add_to_dense(self.dg.ref(), sl.ref(), C.byref(sl.cells), zc.data_ptr(), Z.data_ptr(),
+                                              _stream()), "rl_cells_add_to_dense")
+
+    def gather_dense(self, sl, G, Gc):
+        _lib.check(_L().rl_cells_gather_dense(self.dg.ref(), sl.ref(), C.byref(sl.cells), G.data_ptr(), Gc.data_ptr(),
+                                              _stream()), "rl_cells_gather_dense")
+
+    def plus_features(self, sl, emb, F):
+        _lib.check(_L().rl_plus_cell_features(self.dg.ref(), self.dr.ref(), sl.ref(), sl.fref(), C.byref(sl.cells),
+                                              emb.data_ptr(), 16, 0, F.data_ptr(), None, None, None, None, None, None,
+                                              _stream()), "rl_plus_cell_features")
+
+    def plus_backward(self, sl, dF, grad_emb):
+        _lib.check(_L().rl_plus_cell_backward(self.dg.ref(), self.dr.ref(), sl.ref(), sl.fref(), C.byref(sl.cells), 16,
+                                              dF.data_ptr(), grad_emb.data_ptr(), _stream()), "rl_plus_cell_backward")
+
+    def tail_forward(self, sl, F, wts, zc):
+        _lib.check(_L().rl_tail_forward(C.byref(sl.cells), sl.slot_head.data_ptr(), 16, 128, F.data_ptr(),
+                                        *[t.data_ptr() for t in wts], zc.data_ptr(), _stream()), "rl_tail_forward")
+
+    def tail_backward(self, sl, R, F, wts, Gc, dF, grads, d1sum):
+        _lib.check(_L().rl_tail_backward(C.byref(sl.cells), sl.slot_head.data_ptr(), int(R), 16, 128, F.data_ptr(),
+                                         *[t.data_ptr() for t in wts], Gc.data_ptr(), dF.data_ptr(),
+                                         *[t.data_ptr() for t in grads], d1sum.data_ptr(), _stream()), "rl_tail_backward")
+
+
+def cell_kernels(sk) -> CellKernels:
+    ck = getattr(sk, "_cells", None)
+    if ck is None:
+        ck = sk._cells = CellKernels(sk)
+    return ck
+
+
+# ================================================================================================
+# Predictor (src/predictors.py:17-80)
+# ================================================================================================
+def predictor_step(model, sk, sl, smoothing, grad_scale, gw, gb, expanded=False, bits=32):
+    """Enqueue ground -> cells -> scores -> CE -> backward for prepared slots; no host sync.
+    gw / gb: zeroed gradient tensors (gb None without a bias).  -> (loss[ng], tsum[ng]) device tensors."""
+    ck = cell_kernels(sk)
+    if not expanded:
+        sk.gr._run(sl, bits)
+    _, (zc, Gc) = sk.gr.build_cells(sl, 2)
+    bias = model.bias.detach() if model.entity_feature == "bias" else None
+    if bias is not None:
+        ck.bias_stats(bias)
+    ck.predictor_scores(sl, model.rule_weights.detach(), zc)
+    loss, tsum = ck.softmax_ce(sl, bias, zc, smoothing, sl.group_ptr_dev, len(sl.group_sizes), grad_scale, Gc, gb)
+    ck.predictor_backward(sl, Gc, gw)
+    return loss, tsum
+
+
+@torch.no_grad()
+def predictor_rank(model, sk, sl, split, bits=32, expanded=False):
+    """(L,H) int64[S*32,2] of prepared eval slots (trainer.py:173,189-201)."""
+    ck = cell_kernels(sk)
+    if not expanded:
+        sk.gr.ground(sl)
+    _, (zc,) = sk.gr.build_cells(sl, 1)
+    bias = model.bias.detach() if model.entity_feature == "bias" else None
+    ck.predictor_scores(sl, model.rule_weights.detach(), zc)
+    sorted_bias = torch.sort(bias)[0] if bias is not None else None
+    return ck.rank(sl, bias, sorted_bias, zc, "hr2oo" if split == "valid" else "hr2ooo")
+
+
+# ================================================================================================
+# PredictorPlus with the sum aggregator, hidden_dim 16, MLP(2H,[128,1]) (every shipped config but WN18RR's pna)
+# ================================================================================================
+def plus_cells_supported(model) -> bool:
+    sm = model.score_model
+    return (model.aggregator == "sum" and model.hidden_dim == 16 and len(sm.layers) == 2
+            and sm.layers[0].out_features == 128 and sm.layers[1].out_features == 1 and sm.batch_norms is None
+            and not sm.short_cut and sm.dropout is None)
+
+
+def _tail_weights(model):
+    r2e, sm = model.rule_to_entity, model.score_model
+    lin0 = r2e.add_model.layers[0]
+    return [lin0.weight, lin0.bias, r2e.layer_norm.weight, r2e.layer_norm.bias, sm.layers[0].weight, sm.layers[0].bias,
+            sm.layers[1].weight, sm.layers[1].bias, model.relation_emb.weight]
+
+
+def _step_rule_ids(model, sl, device):
+    """Global ids of the rules of the heads present in this call (host-known: no sync)."""
+    heads = np.unique(sl.heads)
+    ids = np.concatenate([model.compiled.head_rule_array[int(q)] for q in heads]) if len(heads) else np.zeros(0, np.int64)
+    return torch.from_numpy(ids).to(device, non_blocking=True)
+
+
+def _rule_embeddings(model, sl, device):
+    """-> (emb [num_rules,16] fp32 indexed by global rule id, backward closure(grad_emb) or None)."""
+    if model.type == "emb":
+        return model.rule_emb.detach(), None
+    ids = _step_rule_ids(model, sl, device)
+    if model.rule_features.device != device:
+        model.rule_features = model.rule_features.to(device)
+    full = model._emb_scratch(device)
+    if ids.numel() == 0:
+        return full, None
+    with torch.enable_grad():
+        sub = model.encode_rules(model.rule_features[ids])                    # rule encoder: small autograd graph
+    full.index_copy_(0, ids, sub.detach().float())
+    return full, (ids, sub)
+
+
+def plus_step(model, sk, sl, smoothing, grad_scale, gbuf: GradBuffer, expanded=False, bits=32, want_grad=True):
+    """ground -> cells -> aggregate -> fused tail -> CE -> hand-written backward into every parameter of
+    PredictorPlus (gradients accumulate into ``gbuf``'s views, zeroed by the caller).  No host sync.
+    -> (loss[ng], tsum[ng]) device tensors."""
+    ck = cell_kernels(sk)
+    dev = sk.device
+    if not expanded:
+        sk.gr._run(sl, bits)
+    _, planes = sk.gr.build_cells(sl, 2 + 16 + 16)
+    zc, Gc = planes[0], planes[1]
+    cap = sl.cell_cap
+    F = sk.gr._ws_cells[3 * sk.gr._ws_cells_cap:(3 + 16) * sk.gr._ws_cells_cap]         # [cap][16], contiguous planes
+    dF = sk.gr._ws_cells[(3 + 16) * sk.gr._ws_cells_cap:(3 + 32) * sk.gr._ws_cells_cap]
+    emb, enc = _rule_embeddings(model, sl, dev)
+    wts = [t.detach() for t in _tail_weights(model)]
+    ck.plus_features(sl, emb, F)
+    ck.tail_forward(sl, F, wts, zc)
+    ef = model.entity_feature
+    ng = len(sl.group_sizes)
+    extra = None
+    if ef == "RotatE":
+        with torch.enable_grad():
+            extra = model.RotatE.slot_scores(sk, sl)                               # dense by nature: [S][N][32]
+        Z = extra.detach()
+        ck.add_to_dense(sl, zc, Z)
+        loss, tsum, G = sk.softmax_ce(sl, Z, sl_dummy_mask(sl, sk), smoothing, False, sl.group_ptr_dev, ng, want_grad=want_grad)
+        if want_grad:
+            if grad_scale != 1.0:
+                G.mul_(grad_scale)
+            ck.gather_dense(sl, G, Gc)
+    else:
+        bias = model.bias.detach() if ef == "bias" else None
+        if bias is not None:
+            ck.bias_stats(bias)
+        loss, tsum = ck.softmax_ce(sl, bias, zc, smoothing, sl.group_ptr_dev, ng, grad_scale, Gc if want_grad else None,
+                                   gbuf.view(model.bias) if (bias is not None and want_grad) else None)
+    if not want_grad:
+        return loss, tsum
+    grads = [gbuf.view(p) for p in _tail_weights(model)]
+    d1sum = model._d1sum_scratch(dev)
+    ck.tail_backward(sl, model.num_relations, F, wts, Gc, dF, grads, d1sum)
+    if model.type == "emb":
+        ck.plus_backward(sl, dF, gbuf.view(model.rule_emb))
+    elif enc is not None:
+        ids, sub = enc
+        gfull = model._emb_scratch(dev, grad=True).zero_()
+        ck.plus_backward(sl, dF, gfull)
+        enc_params = [model.vocab_emb.weight] + [p for p in model.rnn.parameters()]
+        gs = torch.autograd.grad(sub, enc_params, gfull[ids].to(sub.dtype), allow_unused=True)
+        for p, g_ in zip(enc_params, gs):
+            if g_ is not None:
+                gbuf.view(p).add_(g_)
+    if extra is not None:
+        rp = [model.RotatE.eemb, model.RotatE.remb]
+        gs = torch.autograd.grad(extra, rp, G, allow_unused=True)
+        for p, g_ in zip(rp, gs):
+            if g_ is not None:
+                gbuf.view(p).add_(g_)
+    return loss, tsum
+
+
+def sl_dummy_mask(sl, sk):
+    """The dense CE kernels take a candidate-word table; with a dense entity feature the mask is all-true and
+    the table is never read (use_mask = 0) -- hand them the cells' own table."""
+    return _NzView(sl)
+
+
+class _NzView:
+    def __init__(self, sl):
+        self._p = sl.cells_tables[1]
+
+    def data_ptr(self):
+        return self._p
+
+
+@torch.no_grad()
+def plus_rank(model, sk, sl, split):
+    ck = cell_kernels(sk)
+    dev = sk.device
+    sk.gr.ground(sl)
+    _, planes = sk.gr.build_cells(sl, 2 + 16 + 16)
+    zc = planes[0]
+    F = sk.gr._ws_cells[3 * sk.gr._ws_cells_cap:(3 + 16) * sk.gr._ws_cells_cap]
+    emb, _ = _rule_embeddings(model, sl, dev)
+    wts = [t.detach() for t in _tail_weights(model)]
+    ck.plus_features(sl, emb, F)
+    ck.tail_forward(sl, F, wts, zc)
+    which = "hr2oo" if split == "valid" else "hr2ooo"
+    ef = model.entity_feature
+    if ef == "RotatE":
+        Z = model.RotatE.slot_scores(sk, sl).detach()
+        ck.add_to_dense(sl, zc, Z)
+        return sk.filtered_rank(sl, Z, _NzView(sl), which, False)
+    bias = model.bias.detach() if ef == "bias" else None
+    sorted_bias = torch.sort(bias)[0] if bias is not None else None
+    return ck.rank(sl, bias, sorted_bias, zc, which)

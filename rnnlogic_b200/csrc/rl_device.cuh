@@ -81,6 +81,29 @@ __device__ __forceinline__ bool row_valid(const int32_t *__restrict__ node_chunk
     return (mbase[node_chunk0[v] - hc0 + (row >> 5)] >> (row & 31)) & 1u;
 }
 
+// per group (= one reference batch, possibly several slots): loss = -sum lp*tgt / max(sum tgt, 1)
+// (trainer.py:89); slot_invT[s] = 1 / max(T_group, 1)
+static __global__ void k_group_reduce(int n_groups, const int32_t *__restrict__ group_ptr, const float *__restrict__ slot_lsum,
+                               const float *__restrict__ slot_tsum, float *__restrict__ group_loss,
+                               float *__restrict__ group_tsum, float *__restrict__ slot_invT, float *__restrict__ stats)
+{
+    const int gi = blockIdx.x, lane = threadIdx.x;               // one warp per group, lane = query lane
+    if (gi >= n_groups) return;
+    const int s0 = group_ptr ? group_ptr[gi] : gi, s1 = group_ptr ? group_ptr[gi + 1] : gi + 1;
+    double L = 0.0, T = 0.0;
+    for (int k = s0; k < s1; ++k) { L += (double)slot_lsum[k]; T += (double)slot_tsum[k]; }
+    const float Tf = fmaxf((float)T, 1.f);
+    if (lane == 0) {
+        group_tsum[gi] = (float)T;
+        group_loss[gi] = (float)L / Tf;
+    }
+    for (int k = s0; k < s1; ++k) {
+        if (lane == 0) slot_invT[k] = 1.f / Tf;
+        float *st = stats + ((size_t)k * 32 + lane) * 4;          // stats[.][3]: valid flag -> softmax-gradient coefficient
+        st[3] = st[3] != 0.f ? st[2] / st[1] / Tf : 0.f;          // S_b / sum-exp / T'
+    }
+}
+
 // ---- item list helpers -------------------------------------------------------------------------
 // k_numeric appends one item {row (slot-relative), t0, entity, n} per NON-ZERO row of every rule-end node
 // (the rules ending there are node_term_rule[t0 .. t0 + n)) and counts it in bucket_cnt[slot][entity]; rl_sort_items (k_items_scan + k_items_scatter) turns the
@@ -90,6 +113,8 @@ __device__ __forceinline__ bool row_valid(const int32_t *__restrict__ node_chunk
 
 struct WordItems {
     const int4 *its;      // the slot's items, grouped by entity
+    const uint32_t *masks; // lane mask of every item (same order), or nullptr
+    uint32_t wmask;       // window: lane mask of item wbase + lane (all lanes set when masks == nullptr)
     int b0, b1;           // item range of the lane's entity (entity = word * 32 + lane)
     int wbase, wend;      // window: lane holds item wbase + lane (the word's items are one contiguous range ending at wend)
     int4 win;
@@ -100,7 +125,9 @@ __device__ __forceinline__ void word_items_window(WordItems &wi, int at)
 {
     const int lane = threadIdx.x & 31;
     wi.wbase = at;
-    wi.win = at + lane < wi.wend ? __ldg(wi.its + at + lane) : make_int4(0, 0, -1, 0);
+    const bool in = at + lane < wi.wend;
+    wi.win = in ? __ldg(wi.its + at + lane) : make_int4(0, 0, -1, 0);
+    wi.wmask = wi.masks ? (in ? __ldg(wi.masks + at + lane) : 0u) : FULL;
 }
 
 __device__ __forceinline__ WordItems load_word_items(const rl_frontier &fr, const rl_slots &s, int W, int slot, int ew)
@@ -111,6 +138,7 @@ __device__ __forceinline__ WordItems load_word_items(const rl_frontier &fr, cons
     wi.b0 = off[lane];                                       // padding entities of the last word: empty ranges
     wi.b1 = off[lane + 1];
     wi.its = reinterpret_cast<const int4 *>(fr.items_sorted) + fr.item_off[slot];
+    wi.masks = fr.item_mask_sorted ? fr.item_mask_sorted + fr.item_off[slot] : nullptr;
     wi.present = __ballot_sync(FULL, wi.b1 > wi.b0);
     wi.wend = __shfl_sync(FULL, wi.b1, 31);
     word_items_window(wi, __shfl_sync(FULL, wi.b0, 0));      // most words fit one window: one item load per word

@@ -212,6 +212,7 @@ __device__ __forceinline__ uint32_t numeric_rows(const rl_graph &g, const rl_rul
     int cur = -1;
     unsigned long long acc = 0;
     uint32_t nzrows = 0;
+    uint32_t my_lanes = 0;                                   // lane j: which queries of row j are non-zero
     auto flush = [&](int j) {
         const int d = __shfl_sync(FULL, my_dst, j);
         if (eh >= 0 && et == d) {                            // data.py:164-170: drop the query's own edge
@@ -225,9 +226,11 @@ __device__ __forceinline__ uint32_t numeric_rows(const rl_graph &g, const rl_rul
             acc -= sub;
         }
         if (sizeof(CT) == 4 && (acc >> 32)) ovf = true;
-        if (!PRUNE || __any_sync(FULL, acc != 0)) {          // all-zero rows are dropped from the bitmap
+        const uint32_t nzl = __ballot_sync(FULL, acc != 0);
+        if (!PRUNE || nzl) {                                 // all-zero rows are dropped from the bitmap
             Y[(size_t)__shfl_sync(FULL, myrow, j) * RL_LANES + lane] = (CT)acc;
             nzrows |= 1u << j;
+            if (lane == j) my_lanes = nzl;
         }
         acc = 0;
     };
@@ -287,6 +290,7 @@ __device__ __forceinline__ uint32_t numeric_rows(const rl_graph &g, const rl_rul
             if (mine) {
                 const long long pos = fr.item_off[slot] + base + __popc(nzrows & ((1u << lane) - 1u));
                 reinterpret_cast<int4 *>(fr.items)[pos] = make_int4((int)(r.node_row_off[v] + myrow), term0, my_dst, nterm);
+                if (fr.item_mask) fr.item_mask[pos] = my_lanes;
                 atomicAdd(fr.bucket_cnt + (size_t)slot * RL_BUCKET_STRIDE(g.rank_words) + my_dst, 1);
             }
         }
@@ -353,6 +357,34 @@ k_numeric(rl_graph g, rl_rules r, rl_slots s, int depth, rl_frontier fr, int cpw
         }
     }
     if (__any_sync(FULL, ovf) && lane == 0) *fr.overflow = 1;
+}
+
+// One hop from an ARBITRARY dense frontier (KnowledgeGraph.propagate, src/data.py:149-173):
+// out[t][b] = sum over the relation's edges (s -> t) of x[s][b], minus x[h_k][b] at t_k for the edge
+// k = edges_to_remove[b] of query b (data.py:164-170 zeroes message[k][b]).  x / out are the reference's
+// int64 [N][B] (entity-major already); one warp per entity, lanes stride over the B queries.
+__global__ void __launch_bounds__(WARPS_PER_BLOCK * 32)
+k_propagate_dense(rl_graph g, int rel, int B, const int64_t *__restrict__ x, const int64_t *__restrict__ etr,
+                  int64_t *__restrict__ out)
+{
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int e = blockIdx.x * WARPS_PER_BLOCK + warp;
+    if (e >= g.num_entities) return;
+    const int row = rank_row(g, rel, e);
+    const long long o0 = g.ord_ptr[rel], n_ord = g.ord_ptr[rel + 1] - o0;
+    for (int b = lane; b < B; b += 32) {
+        unsigned long long acc = 0;                          // wraps exactly like the reference's int64
+        if (row >= 0) {
+            const long long grow = g.dst_ptr[rel] + row;
+            for (int k = g.row_start[grow]; k < g.row_start[grow + 1]; ++k)
+                acc += (unsigned long long)x[(size_t)g.edge_src[k] * B + b];
+            if (etr) {
+                const long long k = etr[b];
+                if (k >= 0 && k < n_ord && g.ord_t[o0 + k] == e) acc -= (unsigned long long)x[(size_t)g.ord_h[o0 + k] * B + b];
+            }
+        }
+        out[(size_t)e * B + b] = (int64_t)acc;
+    }
 }
 
 // dense int64 [32][N] view of one node (debug / KnowledgeGraph.grounding return value)
@@ -447,7 +479,7 @@ k_items_scan(int W, rl_frontier fr)
 
 #define SCATTER_BLOCKS 16
 __global__ void __launch_bounds__(256)
-k_items_scatter(int W, rl_frontier fr)
+k_items_scatter(int N, int W, rl_frontier fr)
 {
     const int slot = blockIdx.y;
     int *cnt = fr.bucket_cnt + (size_t)slot * RL_BUCKET_STRIDE(W);
@@ -455,9 +487,18 @@ k_items_scatter(int W, rl_frontier fr)
     const int n = fr.item_cnt[slot];
     const int4 *in = reinterpret_cast<const int4 *>(fr.items) + fr.item_off[slot];
     int4 *out = reinterpret_cast<int4 *>(fr.items_sorted) + fr.item_off[slot];
+    const uint32_t *min_ = fr.item_mask ? fr.item_mask + fr.item_off[slot] : nullptr;
+    uint32_t *mout = fr.item_mask_sorted ? fr.item_mask_sorted + fr.item_off[slot] : nullptr;
+    uint32_t *nz = fr.nzmask ? fr.nzmask + (size_t)slot * N : nullptr;
     for (int i = blockIdx.x * 256 + threadIdx.x; i < n; i += SCATTER_BLOCKS * 256) {
         const int4 it = in[i];
-        out[off[it.z] + atomicAdd(cnt + it.z, 1)] = it;           // cnt ends as the per-entity item counts again
+        const int pos = off[it.z] + atomicAdd(cnt + it.z, 1);     // cnt ends as the per-entity item counts again
+        out[pos] = it;
+        if (min_ && mout) {
+            const uint32_t m = min_[i];
+            mout[pos] = m;
+            if (nz && m) atomicOr(nz + it.z, m);                  // candidate word of the entity
+        }
     }
 }
 
@@ -465,7 +506,7 @@ static int launch_items_sort(const rl_graph *g, const rl_slots *s, const rl_fron
 {
     k_items_scan<<<s->num_slots, 512, 0, st>>>(g->rank_words, *fr);
     CHECK_LAUNCH("k_items_scan");
-    k_items_scatter<<<dim3(SCATTER_BLOCKS, s->num_slots), 256, 0, st>>>(g->rank_words, *fr);
+    k_items_scatter<<<dim3(SCATTER_BLOCKS, s->num_slots), 256, 0, st>>>(g->num_entities, g->rank_words, *fr);
     CHECK_LAUNCH("k_items_scatter");
     return RL_OK;
 }
@@ -701,29 +742,6 @@ k_ce_finalize(rl_graph g, rl_slots s, rl_answers ans, float smoothing, int use_m
         for (int k = 0; k < CE_WARPS; ++k) { L += red_l[k]; T += red_t[k]; }
         slot_tsum[slot] = (float)T;
         slot_lsum[slot] = (float)(-L);
-    }
-}
-
-// per group (= one reference batch, possibly several slots): loss = -sum lp*tgt / max(sum tgt, 1)
-// (trainer.py:89); slot_invT[s] = 1 / max(T_group, 1)
-__global__ void k_group_reduce(int n_groups, const int32_t *__restrict__ group_ptr, const float *__restrict__ slot_lsum,
-                               const float *__restrict__ slot_tsum, float *__restrict__ group_loss,
-                               float *__restrict__ group_tsum, float *__restrict__ slot_invT, float *__restrict__ stats)
-{
-    const int gi = blockIdx.x, lane = threadIdx.x;               // one warp per group, lane = query lane
-    if (gi >= n_groups) return;
-    const int s0 = group_ptr ? group_ptr[gi] : gi, s1 = group_ptr ? group_ptr[gi + 1] : gi + 1;
-    double L = 0.0, T = 0.0;
-    for (int k = s0; k < s1; ++k) { L += (double)slot_lsum[k]; T += (double)slot_tsum[k]; }
-    const float Tf = fmaxf((float)T, 1.f);
-    if (lane == 0) {
-        group_tsum[gi] = (float)T;
-        group_loss[gi] = (float)L / Tf;
-    }
-    for (int k = s0; k < s1; ++k) {
-        if (lane == 0) slot_invT[k] = 1.f / Tf;
-        float *st = stats + ((size_t)k * 32 + lane) * 4;          // stats[.][3]: valid flag -> softmax-gradient coefficient
-        st[3] = st[3] != 0.f ? st[2] / st[1] / Tf : 0.f;          // S_b / sum-exp / T'
     }
 }
 
@@ -1179,8 +1197,8 @@ int rl_expand_level(const rl_graph *g, const rl_rules *r, const rl_slots *s, int
     CHECK_LAUNCH("k_symbolic");
     // chunks per warp: many when most chunks are empty (one coalesced read of their bitmap words),
     // few when every chunk is expanded (more warps in flight to hide the look-up latency)
-    int cpw = force_dense ? 4 : 16;
-    if (const char *e = getenv("RL_CPW")) { int v = atoi(e); if (v >= 1 && v <= 32) cpw = v; }
+    static const int cpw_env = []() { const char *e = getenv("RL_CPW"); const int v = e ? atoi(e) : 0; return (v >= 1 && v <= 32) ? v : 0; }();
+    const int cpw = cpw_env ? cpw_env : (force_dense ? 4 : 16);
     dim3 grid((grid_chunks + WARPS_PER_BLOCK * cpw - 1) / (WARPS_PER_BLOCK * cpw), s->num_slots);
     // force_dense: plain dense SpMM -- every row of every node is written (zeros included) and read
 #define LAUNCH_NUM(CT, ROOT, PRUNE) k_numeric<CT, ROOT, PRUNE><<<grid, WARPS_PER_BLOCK * 32, 0, st>>>(*g, *r, *s, depth, *fr, cpw)
@@ -1206,6 +1224,18 @@ int rl_node_counts_dense(const rl_graph *g, const rl_rules *r, const rl_slots *s
     if (fr->count_bits == 32) k_node_dense<uint32_t><<<grid, 1024, 0, (cudaStream_t)stream>>>(*g, *r, *s, slot, node, *fr, out);
     else k_node_dense<unsigned long long><<<grid, 1024, 0, (cudaStream_t)stream>>>(*g, *r, *s, slot, node, *fr, out);
     CHECK_LAUNCH("k_node_dense");
+    return RL_OK;
+}
+
+int rl_propagate_dense(const rl_graph *g, int32_t relation, int32_t B, const int64_t *x, const int64_t *etr,
+                       int64_t *out, void *stream)
+{
+    if (!g || !x || !out) return fail(RL_ERR_ARG, "rl_propagate_dense: null argument");
+    if (relation < 0 || relation >= g->num_relations) return fail(RL_ERR_ARG, "rl_propagate_dense: relation out of range");
+    if (B <= 0 || g->num_entities <= 0) return RL_OK;
+    k_propagate_dense<<<(g->num_entities + WARPS_PER_BLOCK - 1) / WARPS_PER_BLOCK, WARPS_PER_BLOCK * 32, 0, (cudaStream_t)stream>>>(
+        *g, relation, B, x, etr, out);
+    CHECK_LAUNCH("k_propagate_dense");
     return RL_OK;
 }
 

@@ -130,6 +130,9 @@ class Grounder:
         self._ws_arena = None
         self._ws_state = None
         self._ws_items = None
+        self._ws_cells = None
+        self._ws_cells_cap = 0
+        self.cell_cap = 0
         self.level_events = None      # bench.py: list collecting (depth, start, end) CUDA events
 
     @staticmethod
@@ -188,17 +191,30 @@ class Grounder:
         sl.use_workspace = True
         return sl
 
+    def _layout(self, sl: "Slots | HostStep", bits: int = 32):
+        """Sizes (in int32 words) of the three per-call buffers: arena | zeroed state | scratch."""
+        W, N, S = self.graph.rank_words, self.graph.entity_size, sl.S
+        n_mask, n_cnt = sl.mask_words + 1, sl.nz_total + 1
+        n_bkt = S * (W * 32 + 32)                                        # per-entity item counts / offsets (RL_BUCKET_STRIDE)
+        n_pad = -(n_mask + n_cnt + S) % 4                                # the bucket table is read with 16-byte loads
+        cap = max(1, sl.item_cap)
+        return {
+            "arena": max(1, sl.arena_rows) * LANES * (1 if bits == 32 else 2),
+            # zeroed: row bitmaps | node counts | item counts | pad | buckets | candidate words | cell counters[8] | overflow
+            "o_cnt": n_mask, "o_icnt": n_mask + n_cnt, "o_bkt": n_mask + n_cnt + S + n_pad,
+            "o_nz": n_mask + n_cnt + S + n_pad + n_bkt, "o_ctr": n_mask + n_cnt + S + n_pad + n_bkt + S * N,
+            "state": n_mask + n_cnt + S + n_pad + n_bkt + S * N + 8 + 1,
+            # scratch: items | items_sorted (int32x4 records, exact upper bound) | bucket offsets | item lane masks (x2) |
+            # first cell per (slot, entity) | cells per slot
+            "n_items": 4 * cap, "o_boff": 8 * cap, "o_im": 8 * cap + n_bkt, "o_ims": 9 * cap + n_bkt,
+            "o_coff": 10 * cap + n_bkt, "o_ncell": 10 * cap + n_bkt + S * N, "scratch": 10 * cap + n_bkt + S * N + S,
+        }
+
     def _run(self, sl: Slots, bits: int):
         dev = self.device
         sl.count_bits = bits
-        W = self.graph.rank_words
-        n_mask, n_cnt = sl.mask_words + 1, sl.nz_total + 1
-        n_arena = max(1, sl.arena_rows) * LANES * (1 if bits == 32 else 2)
-        n_bkt = n_boff = sl.S * (W * 32 + 32)                          # per-entity item counts / offsets (RL_BUCKET_STRIDE)
-        n_pad = -(n_mask + n_cnt + sl.S) % 4                           # the bucket table is read with 16-byte loads
-        n_state = n_mask + n_cnt + sl.S + n_pad + n_bkt + 1            # zeroed: row bitmaps | node counts | item counts | buckets | overflow
-        n_items = 4 * max(1, sl.item_cap)                              # int32x4 records, exact upper bound (cannot overflow)
-        n_scratch = 2 * n_items + n_boff
+        lay = self._layout(sl, bits)
+        n_arena, n_state, n_scratch = lay["arena"], lay["state"], lay["scratch"]
         if getattr(sl, "use_workspace", False):
             # fused paths consume the frontier inside the call: reuse grow-only buffers (no cudaMalloc in
             # steady state; the arena needs no clearing, rows outside the bitmap are never read)
@@ -219,13 +235,16 @@ class Grounder:
             scratch = torch.empty(n_scratch, dtype=torch.int32, device=dev)
         sl.scratch = scratch
         sl.overflow = sl.state[-1:]
-        base = sl.state.data_ptr()
-        o_cnt = n_mask
-        o_icnt, o_bkt = o_cnt + n_cnt, o_cnt + n_cnt + sl.S + n_pad
-        sb = scratch.data_ptr()
-        sl.frontier = _lib.RlFrontier(bits, sl.arena.data_ptr(), base, base + 4 * o_cnt,
-                                      sl.overflow.data_ptr(), sb, sb + 4 * n_items, sl.item_off.data_ptr(),
-                                      base + 4 * o_icnt, base + 4 * o_bkt, sb + 8 * n_items)
+        sl.cell_counters = sl.state[lay["o_ctr"]:lay["o_ctr"] + 8]
+        sl.slot_ncell = scratch[lay["o_ncell"]:lay["o_ncell"] + sl.S]
+        sl.flags = sl.state[lay["o_ctr"]:]                               # cell counters[8] | count overflow: one D2H read
+        base, sb = sl.state.data_ptr(), scratch.data_ptr()
+        sl.frontier = _lib.RlFrontier(bits, sl.arena.data_ptr(), base, base + 4 * lay["o_cnt"],
+                                      sl.overflow.data_ptr(), sb, sb + 4 * lay["n_items"], sl.item_off.data_ptr(),
+                                      base + 4 * lay["o_icnt"], base + 4 * lay["o_bkt"], sb + 4 * lay["o_boff"],
+                                      sb + 4 * lay["o_im"], sb + 4 * lay["o_ims"], base + 4 * lay["o_nz"])
+        sl.cells_tables = (base + 4 * lay["o_ctr"], base + 4 * lay["o_nz"], sb + 4 * lay["o_coff"], sb + 4 * lay["o_ncell"])
+        sl.cells = None
         L = _lib.lib()
         lc = self.cr.level_chunks[sl.heads]                               # [S, max_len]
         ln = self.cr.level_sym_items[sl.heads]
@@ -243,14 +262,41 @@ class Grounder:
                 e1.record()
                 self.level_events.append((depth, e0, e1))
 
+    # ---- candidate cells (rl_cells) ------------------------------------------------------------
+    cells_per_slot_hint = 24576       # first guess of the per-cell capacity; grows on demand (see ensure_cell_cap)
+
+    def cell_arrays(self, sl: Slots, floats_per_cell: int):
+        """Grow-only per-cell workspace: int32 keys [cap] + ``floats_per_cell`` fp32 planes [cap] each."""
+        want = max(self.cell_cap, self.cells_per_slot_hint * sl.S)
+        n = want * (1 + floats_per_cell)
+        if self._ws_cells is None or self._ws_cells.numel() < n or self._ws_cells_cap < want:
+            self._ws_cells = None
+            self._ws_cells = torch.empty(n, dtype=torch.float32, device=self.device)
+            self._ws_cells_cap = want
+        cap = self._ws_cells_cap
+        planes = [self._ws_cells[(1 + i) * cap:(2 + i) * cap] for i in range(floats_per_cell)]
+        return cap, self._ws_cells[:cap].view(torch.int32), planes
+
+    def build_cells(self, sl: Slots, floats_per_cell: int):
+        """rl_cells_build for an expanded frontier -> (RlCells, fp32 planes [cap] each)."""
+        cap, keys, planes = self.cell_arrays(sl, floats_per_cell)
+        ctr, nz, coff, ncell = sl.cells_tables
+        sl.cells = _lib.RlCells(cap, ctr, nz, coff, keys.data_ptr(), ncell)
+        sl.cell_cap = cap
+        _lib.check(_lib.lib().rl_cells_build(self.dg.ref(), self.dr.ref(), sl.ref(), sl.fref(), C.byref(sl.cells), _stream()),
+                   "rl_cells_build")
+        return sl.cells, planes
+
+    def note_cell_count(self, n_cells: int):
+        """Remember the largest cell count seen so that later calls size their arrays for it (x1.25)."""
+        self.cell_cap = max(self.cell_cap, int(n_cells * 1.25) + 1024)
+
     def reserve(self, slots_list):
         """Size the reusable frontier workspace for the largest of the given calls up front, so that no
         step of a steady-state loop triggers a cudaMalloc."""
-        W = self.graph.rank_words
-        n_arena = max(max(1, sl.arena_rows) * LANES for sl in slots_list)
-        n_state = max(sl.mask_words + 1 + sl.nz_total + 1 + sl.S + 3 + sl.S * (W * 32 + 32) + 1 for sl in slots_list)
-        n_scratch = max(8 * max(1, sl.item_cap) + sl.S * (W * 32 + 32) for sl in slots_list)
-        for name, n in (("_ws_arena", n_arena), ("_ws_state", n_state), ("_ws_items", n_scratch)):
+        lays = [self._layout(sl) for sl in slots_list]
+        for name, key in (("_ws_arena", "arena"), ("_ws_state", "state"), ("_ws_items", "scratch")):
+            n = max(l[key] for l in lays)
             cur = getattr(self, name)
             if cur is None or cur.numel() < n:
                 setattr(self, name, None)
@@ -262,7 +308,7 @@ class Grounder:
         sl.overflow = sl.state[-1:]
         p = sl.state.data_ptr()
         sl.frontier = _lib.RlFrontier(32, sl.arena.data_ptr(), p, p + 4, sl.overflow.data_ptr(),
-                                      None, None, None, None, None, None)
+                                      None, None, None, None, None, None, None, None, None)
 
     def ground(self, sl: Slots, check_overflow: bool = True) -> Slots:
         """Run all depths.  Counts are kept in 32-bit rows; if any count does not fit (host sync on

@@ -351,6 +351,26 @@ class KnowledgeGraph(object):
         return ground_chain(self, h, int(r), [int(x) for x in rule], edges_to_remove)
 
     def propagate(self, x, relation, edges_to_remove=None):
-        raise NotImplementedError(
-            "rnnlogic_b200 fuses propagate (src/data.py:149-173) into the frontier-expansion kernel; "
-            "call grounding(h, r, rule, edges_to_remove) instead")
+        """One hop from an arbitrary frontier (src/data.py:149-173): x int64[N,B,D] -> int64[N,B,D] with
+        out[t] = sum over relation edges (s -> t) of x[s]; ``edges_to_remove[b]`` (index into the relation's
+        train-order edge list) drops that edge's message for query b.  CUDA tensors only, bit-exact."""
+        from .engine import _stream
+        _lib.require_cuda(x, "x")
+        if x.dim() != 3 or x.shape[0] != self.entity_size:
+            raise ValueError("propagate expects x of shape [num_entities, B, D]")
+        N, B, D = x.shape
+        dg = self.device_graph(x.device)
+        xi = x.to(torch.int64).contiguous()
+        etr = None
+        if edges_to_remove is not None:
+            etr = edges_to_remove.to(x.device, torch.int64).contiguous()
+            if etr.numel() != B:
+                raise ValueError("edges_to_remove has %d entries for %d queries" % (etr.numel(), B))
+            if D != 1:                                        # data.py:165-169 indexes message.view(-1, D) rows
+                etr = etr.repeat_interleave(D)
+        out = torch.empty_like(xi)
+        with torch.cuda.device(x.device):
+            _lib.check(_lib.lib().rl_propagate_dense(dg.ref(), int(relation), int(B * D), xi.data_ptr(),
+                                                     etr.data_ptr() if etr is not None else None, out.data_ptr(),
+                                                     _stream()), "rl_propagate_dense")
+        return out.to(x.dtype)

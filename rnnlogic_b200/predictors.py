@@ -180,11 +180,9 @@ def _group_mask_sum(sl, nzmask, ng):
     return torch.zeros(ng, dtype=torch.float32, device=nzmask.device).index_add_(0, gid, per_slot)
 
 
-def _predictor_step_on_slots(self, sk, sl, smoothing, grad_scale=1.0, bits=32, expanded=False):
-    """Enqueue ground -> aggregate -> CE -> backward for prepared slots (no host sync).
-    Returns the device tensors (loss[ng], tsum[ng], mask_sum[ng] | None, grad_w, grad_b).
-    expanded=True: the frontier of ``sl`` was already expanded (sk.gr._run) -- grounding does not
-    depend on the parameters, so a caller may run it ahead of the previous step's gradient exchange."""
+def _predictor_step_on_slots_dense(self, sk, sl, smoothing, grad_scale=1.0, bits=32, expanded=False):
+    """Round-1 tail kept for A/B measurements (bench.py --dense-tail): dense entity-major Z / G matrices
+    [S][N][32] (rl_predictor_scores + rl_predictor_ce_backward).  Same results as the cell path."""
     device = sk.device
     use_bias = self.entity_feature == "bias"
     gptr, ng = _group_ptr(sl, device)
@@ -199,31 +197,99 @@ def _predictor_step_on_slots(self, sk, sl, smoothing, grad_scale=1.0, bits=32, e
     return loss, tsum, msum, gw, gb
 
 
+# ---- fused steps on candidate cells (cellpath.py): shared by Predictor and PredictorPlus -------------------
+from . import cellpath  # noqa: E402
+
+
+class RlStepOverflow(_lib.RlError):
+    """An enqueued step must be redone: a path count did not fit 32 bits (redo with 64-bit rows) or the step had
+    more candidate cells than its arrays hold (redo with larger arrays).  ``model.fused_train_step`` does both."""
+
+
+def _fused_params(self):
+    """Parameters the fused step writes gradients for, in a fixed order (= layout of the flat gradient buffer)."""
+    return [p for p in self.parameters() if p.requires_grad]
+
+
+def _step_on_slots(self, sk, sl, smoothing, grad_scale, gbuf, bits=32, expanded=False):
+    """Enqueue one fused train step for prepared slots (no host sync); gradients accumulate into ``gbuf``.
+    -> (loss[ng], tsum[ng]) device tensors."""
+    if isinstance(self, Predictor):
+        gb = gbuf.view(self.bias) if self.entity_feature == "bias" else None
+        return cellpath.predictor_step(self, sk, sl, smoothing, grad_scale, gbuf.view(self.rule_weights), gb,
+                                       expanded=expanded, bits=bits)
+    return cellpath.plus_step(self, sk, sl, smoothing, grad_scale, gbuf, expanded=expanded, bits=bits)
+
+
+def _dense_feature_params(self):
+    if self.entity_feature == "bias":
+        return [self.bias]
+    if self.entity_feature == "RotatE":
+        return [self.RotatE.eemb, self.RotatE.remb]
+    return []
+
+
+def _used_params(self, total_cells):
+    """ids of the parameters that take part in a step (the others keep grad None, as under DDP's
+    find_unused_parameters=True, trainer.py:60): without any candidate only the entity feature has a gradient
+    (predictors.py:67-71, 230-237)."""
+    if total_cells > 0:
+        if isinstance(self, PredictorPlus):
+            skip = [self.vocab_emb.weight] if self.type == "emb" else []
+            return {id(p) for p in _fused_params(self) if all(p is not q for q in skip)}
+        return {id(p) for p in _fused_params(self)}
+    return {id(p) for p in _dense_feature_params(self)}
+
+
 class _StepTicket:
     """Handle of an enqueued fused train step: everything is on the stream, nothing was synchronised.
-    ``result()`` does the step's one device->host read (losses, target sums, overflow flag)."""
+    ``result()`` does the step's one device->host read (losses, target sums, cells per slot, flags)."""
 
-    def __init__(self, model, sk, sl, batches, smoothing, grad_scale, pack, gw, gb, ng, use_bias):
+    def __init__(self, model, sk, sl, batches, smoothing, grad_scale, loss, tsum, gbuf):
         self.model, self.sk, self.sl, self.batches = model, sk, sl, batches
-        self.smoothing, self.grad_scale = smoothing, grad_scale
-        self.gw, self.gb, self.ng, self.use_bias = gw, gb, ng, use_bias
+        self.smoothing, self.grad_scale, self.gbuf = smoothing, grad_scale, gbuf
+        self.ng = len(sl.group_sizes)
+        pack = torch.cat([loss, tsum, sl.slot_ncell.float(), sl.flags.float()])
         self.pinned = torch.empty(pack.numel(), dtype=torch.float32, pin_memory=True)
         self.pinned.copy_(pack, non_blocking=True)
         self.event = torch.cuda.Event()
         self.event.record()
         self.h2d_bytes = sl.h2d_bytes
         self.d2h_bytes = int(pack.numel() * 4)
+        self._done = None
+
+    # gradients of the step (device), for loops that drive the optimizer themselves
+    @property
+    def gw(self):
+        return self.gbuf.view(self.model.rule_weights)
+
+    @property
+    def gb(self):
+        return self.gbuf.view(self.model.bias)
 
     def result(self):
+        """(loss[n_batches], target_sum[n_batches]) host tensors.  Raises RlStepOverflow when the step has to be redone."""
+        if self._done is not None:
+            return self._done
         self.event.synchronize()
-        host = self.pinned
-        ng = self.ng
-        if host[-1].item() != 0:
-            raise _lib.RlError("a path count overflowed 32 bits inside an enqueued step; rerun the step with "
-                               "model.fused_train_step (it falls back to exact 64-bit rows; TrainerPredictor: "
-                               "set trainer.pipelined = False)")
-        self.model.last_mask_sum = None if self.use_bias else host[2 * ng:3 * ng].tolist()
-        return host[:ng], host[ng:2 * ng]
+        host, ng, S = self.pinned, self.ng, self.sl.S
+        flags = host[2 * ng + S:]
+        self.total_cells = int(flags[0].item())
+        self.sk.gr.note_cell_count(self.total_cells)
+        if flags[8].item() != 0:
+            raise RlStepOverflow("a path count overflowed 32 bits inside an enqueued step; redo it with "
+                                 "model.fused_train_step (exact 64-bit rows)")
+        if flags[1].item() != 0:
+            raise RlStepOverflow("the step has %d candidate cells, more than its arrays hold; redo it with "
+                                 "model.fused_train_step (the arrays grow)" % self.total_cells)
+        ncell = host[2 * ng:2 * ng + S].numpy()
+        gslots = [(n + LANES - 1) // LANES for n in self.sl.group_sizes]
+        self.mask_sum = np.add.reduceat(ncell, np.concatenate([[0], np.cumsum(gslots)[:-1]])).tolist() if S else []
+        dense_feature = self.model.entity_feature in ("bias", "RotatE")
+        self.model.last_mask_sum = None if dense_feature else self.mask_sum
+        self.used = _used_params(self.model, self.total_cells)
+        self._done = (host[:ng], host[ng:2 * ng])
+        return self._done
 
 
 class _PreparedStep:
@@ -234,81 +300,82 @@ class _PreparedStep:
         self.model, self.sk, self.sl, self.batches, self.bits = model, sk, sl, batches, bits
 
     def finish(self, smoothing, grad_scale=1.0):
-        """aggregate -> CE -> backward -> async D2H of the losses; returns the step's ticket."""
+        """cells -> scores -> CE -> backward -> async D2H of the losses; returns the step's ticket."""
         model, sk, sl = self.model, self.sk, self.sl
-        use_bias = model.entity_feature == "bias"
-        loss, tsum, msum, gw, gb = _predictor_step_on_slots(model, sk, sl, smoothing, grad_scale, self.bits, expanded=True)
-        parts = [loss, tsum] + ([msum] if msum is not None else [])
-        pack = torch.cat(parts + [sl.overflow.float()])
-        return _StepTicket(model, sk, sl, self.batches, smoothing, grad_scale, pack, gw, gb, len(sl.group_sizes), use_bias)
+        gbuf = cellpath.GradBuffer(_fused_params(model))
+        loss, tsum = _step_on_slots(model, sk, sl, smoothing, grad_scale, gbuf, self.bits, expanded=True)
+        return _StepTicket(model, sk, sl, self.batches, smoothing, grad_scale, loss, tsum, gbuf)
 
 
-def _predictor_pack_train(self, batches):
+def _model_device(self):
+    return next(self.parameters()).device
+
+
+def _pack_train(self, batches):
     """The CUDA-free part of a fused train step (queries and slot tables packed into pinned memory for one
     copy).  Thread-safe once the model sits on its device: a loader thread can pack steps ahead
     (data.StepPrefetcher) and hand the result to prepare_train_step / submit_train_step."""
-    return self._driver(self.rule_weights.device).gr.pack_host(batches, with_etr=True)
+    return self._driver(_model_device(self)).gr.pack_host(batches, with_etr=True)
 
 
-def _predictor_prepare_train(self, batches):
+def _prepare_train(self, batches):
     """Enqueue everything of a fused train step that does not depend on the parameters (grounding) and
     return a handle; ``handle.finish(smoothing, grad_scale)`` enqueues the rest.  A data-parallel loop calls
     this for step k+1 while the gradient all-reduce of step k is in flight.  ``batches``: a list of
     single-relation batches or a step packed ahead by pack_train_step."""
-    device = self.rule_weights.device
-    sk = self._driver(device)
+    sk = self._driver(_model_device(self))
     sl = sk.gr.make_slots_host(batches, with_etr=True)
     bits = sk.gr.force_bits or 32
     sk.gr._run(sl, bits)
     return _PreparedStep(self, sk, sl, batches, bits)
 
 
-def _predictor_submit_train(self, batches, smoothing, grad_scale=1.0):
+def _submit_train(self, batches, smoothing, grad_scale=1.0):
     """Enqueue one fused train step (host pack -> H2D -> kernels -> async D2H) and return a ticket; the
-    gradients are in ticket.gw / ticket.gb (device).  Lets the host prepare step k+1 while step k runs."""
-    return _predictor_prepare_train(self, batches).finish(smoothing, grad_scale)
+    gradients are in ticket.gbuf (device).  Lets the host prepare step k+1 while step k runs."""
+    return _prepare_train(self, batches).finish(smoothing, grad_scale)
 
 
-def _predictor_fused_train(self, batches, smoothing, grad_scale=1.0):
+def _fused_train(self, batches, smoothing, grad_scale=1.0):
     """One fused step over a list of single-relation train batches (trainer.py:68-93 for each):
-    ground -> aggregate -> log(softmax+1e-8) CE -> backward.  Gradients of ``grad_scale * sum of
-    the batch losses`` are ACCUMULATED into .grad.  Returns (loss[n_batches], target_sum[n_batches])
-    as host float tensors -- one device->host read per step."""
-    device = self.rule_weights.device
-    sk = self._driver(device)
-    use_bias = self.entity_feature == "bias"
-    sl = sk.gr.make_slots_host(batches, with_etr=True)
-    ng = len(batches)
-    for bits in ((sk.gr.force_bits,) if sk.gr.force_bits else (32, 64)):
-        loss, tsum, msum, gw, gb = _predictor_step_on_slots(self, sk, sl, smoothing, grad_scale, bits)
-        parts = [loss, tsum] + ([msum] if msum is not None else [])
-        host = torch.cat(parts + [sl.overflow.float()]).cpu()            # the step's one sync
-        if host[-1].item() == 0 or bits == 64:
+    ground -> cells -> scores -> log(softmax+1e-8) CE -> backward.  Gradients of ``grad_scale * sum of
+    the batch losses`` are ACCUMULATED into .grad (parameters that did not take part keep None).  Returns
+    (loss[n_batches], target_sum[n_batches]) as host float tensors -- one device->host read per step.
+    A 32-bit count overflow redoes the step with 64-bit rows, a cell-array overflow with larger arrays."""
+    sk = self._driver(_model_device(self))
+    host = batches if not isinstance(batches, list) else sk.gr.pack_host(batches, with_etr=True)
+    bits = sk.gr.force_bits or 32
+    for _attempt in range(4):
+        sl = sk.gr.make_slots_host(host, with_etr=True)
+        sk.gr._run(sl, bits)
+        ticket = _PreparedStep(self, sk, sl, batches, bits).finish(smoothing, grad_scale)
+        try:
+            loss, tsum = ticket.result()
             break
-    for p, g in ((self.rule_weights, gw), (self.bias if use_bias else None, gb)):
-        if p is not None:
+        except RlStepOverflow:
+            if ticket.pinned[-1].item() != 0:              # count overflow: exact 64-bit rows (they wrap like the reference's int64)
+                bits = 64
+    else:
+        raise _lib.RlError("fused_train_step: the cell arrays kept overflowing")
+    for p in _fused_params(self):
+        if id(p) in ticket.used:
+            g = ticket.gbuf.view(p)
             p.grad = g if p.grad is None else p.grad.add_(g)
     self.last_h2d_bytes = sl.h2d_bytes
-    self.last_d2h_bytes = int(host.numel() * 4)
-    self.last_mask_sum = None if use_bias else host[2 * ng:3 * ng].tolist()
-    return host[:ng], host[ng:2 * ng]
+    self.last_d2h_bytes = ticket.d2h_bytes
+    self.last_ticket = ticket
+    return loss, tsum
 
 
 @torch.no_grad()
-def _predictor_fused_rank(self, batches, split):
+def _fused_rank(self, batches, split):
     """(L,H) int64[Q,2] of a list of single-relation eval batches (trainer.py:173,189-201)."""
-    device = self.rule_weights.device
-    sk = self._driver(device)
-    use_bias = self.entity_feature == "bias"
+    sk = self._driver(_model_device(self))
     sl = sk.gr.make_slots_host(batches, with_etr=False)
-    sk.gr.ground(sl)
-    Z, nzmask = sk.predictor_scores(sl, self.rule_weights.detach(), self.bias.detach() if use_bias else None,
-                                    not use_bias)
-    LH = sk.filtered_rank(sl, Z, nzmask, "hr2oo" if split == "valid" else "hr2ooo", not use_bias)
-    if not use_bias:
-        # predictors.py:67-71 quirk: a batch with no candidate at all returns +inf logits and an
-        # all-False mask -> every query of it ranks (1, N+1); nzmask already yields exactly that.
-        pass
+    if isinstance(self, Predictor):
+        LH = cellpath.predictor_rank(self, sk, sl, split)
+    else:
+        LH = cellpath.plus_rank(self, sk, sl, split)
     return _valid_lanes(sl, LH)
 
 
@@ -317,12 +384,18 @@ def _valid_lanes(sl, LH):
     return LH[torch.from_numpy(idx).to(LH.device)]
 
 
-Predictor.fused_train_step = _predictor_fused_train
-Predictor.submit_train_step = _predictor_submit_train
-Predictor.prepare_train_step = _predictor_prepare_train
-Predictor.pack_train_step = _predictor_pack_train
-Predictor.step_on_slots = _predictor_step_on_slots
-Predictor.fused_rank = _predictor_fused_rank
+def _install_fused(cls):
+    cls.fused_train_step = _fused_train
+    cls.submit_train_step = _submit_train
+    cls.prepare_train_step = _prepare_train
+    cls.pack_train_step = _pack_train
+    cls.step_on_slots = _step_on_slots
+    cls.fused_rank = _fused_rank
+    cls.fused_params = _fused_params
+
+
+_install_fused(Predictor)
+Predictor.step_on_slots_dense = _predictor_step_on_slots_dense
 
 
 # ================================================================================================
@@ -554,6 +627,7 @@ class PredictorPlus(_RuleModel):
         self.num_entities = graph.entity_size
         self.num_relations = graph.relation_size
         self.padding_index = graph.relation_size
+        self._scratch = {}
         self.vocab_emb = torch.nn.Embedding(self.num_relations + 1, self.hidden_dim, padding_idx=self.num_relations)
         if self.type in ('lstm', 'gru', 'rnn'):
             # cuDNN RNNs default to TF32 matmuls (forward AND backward); the rule encoder must stay in
@@ -592,6 +666,21 @@ class PredictorPlus(_RuleModel):
             dev = self.relation_emb.weight.device
             self.rule_emb = nn.parameter.Parameter(torch.zeros(self.num_rules, self.hidden_dim, device=dev))
             nn.init.kaiming_uniform_(self.rule_emb, a=math.sqrt(5), mode="fan_in")
+
+    def _emb_scratch(self, device, grad=False):
+        """[num_rules, H] fp32 scratch indexed by the global rule id (rule embeddings of a step / their gradient)."""
+        key = ("g" if grad else "e") + str(device)
+        t = self._scratch.get(key)
+        if t is None or t.shape[0] != self.num_rules:
+            t = self._scratch[key] = torch.zeros(self.num_rules, self.hidden_dim, dtype=torch.float32, device=device)
+        return t
+
+    def _d1sum_scratch(self, device):
+        key = "d" + str(device)
+        t = self._scratch.get(key)
+        if t is None:
+            t = self._scratch[key] = torch.empty(self.num_relations * 128, dtype=torch.float32, device=device)
+        return t
 
     def encode_rules(self, rule_features):
         """predictors.py:201-208: embed [head, body..., pad], run the RNN, take the last non-pad output."""
@@ -701,5 +790,24 @@ def _plus_fused_rank(self, batches, split):
     return _valid_lanes(sl, LH)
 
 
-PredictorPlus.fused_train_step = _plus_fused_train
-PredictorPlus.fused_rank = _plus_fused_rank
+_install_fused(PredictorPlus)
+
+
+def _plus_train_dispatch(self, batches, smoothing, grad_scale=1.0):
+    """Cell path (hand-written backward, no host sync) for the sum aggregator at hidden_dim 16; the PNA aggregator
+    and other widths take the autograd path above."""
+    if cellpath.plus_cells_supported(self):
+        return _fused_train(self, batches, smoothing, grad_scale)
+    return _plus_fused_train(self, batches, smoothing, grad_scale)
+
+
+def _plus_rank_dispatch(self, batches, split):
+    if cellpath.plus_cells_supported(self):
+        return _fused_rank(self, batches, split)
+    return _plus_fused_rank(self, batches, split)
+
+
+PredictorPlus.fused_train_step = _plus_train_dispatch
+PredictorPlus.fused_rank = _plus_rank_dispatch
+Predictor.supports_pipeline = property(lambda self: True)
+PredictorPlus.supports_pipeline = property(lambda self: cellpath.plus_cells_supported(self))

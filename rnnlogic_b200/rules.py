@@ -136,6 +136,7 @@ class CompiledRules:
         self.head_rules: List[List[int]] = [[] for _ in range(R)]
         for idx, (head, _) in enumerate(rules):
             self.head_rules[head].append(idx)
+        self.head_rule_array = [np.asarray(v, dtype=np.int64) for v in self.head_rules]
         # algorithmic bytes per head for a 32-lane slot: c = i = 4 bytes
         E, D, U = graph.rel_edges, graph.rel_rows, graph.rel_sources
         per_node = 4 * E[node_rel] + 8 * D[node_rel] + 4 * LANES * ((node_depth > 1) * U[node_rel] + D[node_rel]) \

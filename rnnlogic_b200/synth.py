@@ -145,3 +145,105 @@ def scaled_rules(R=1000, n_rules=10_000, length=3, seed=5):
     heads = rng.integers(R, size=n_rules)
     bodies = rng.integers(R, size=(n_rules, length))
     return [(int(h), [int(b) for b in body]) for h, body in zip(heads, bodies)]
+
+
+# ------------------------------------------------------------------------------------------------
+# A TYPED synthetic graph: the i.i.d. recipe above draws heads and tails independently of the relation, so a
+# hop rho' -> rho almost never composes (the tails of rho' are rarely heads of rho) and frontiers die after one
+# hop.  Real KGs are typed: every relation has a domain and a range, and mined rule bodies chain relations whose
+# range / domain agree -- which is why they were mined.  Same sizes as the shape, same Zipf popularity, but every
+# entity has a type, every base relation a (domain, range) pair, and rule bodies are type-compatible chains that
+# start in the head's domain and end in its range.
+# ------------------------------------------------------------------------------------------------
+def typed_kg(shape: dict, n_types: int = 12, seed: int = None):
+    """(N, R, train, valid, test, meta) with meta = {"etype": [N], "domain": [R], "range": [R]}."""
+    seed = shape["seed"] if seed is None else seed
+    rng = np.random.default_rng(seed + 7)
+    N, R = shape["num_entities"], shape["num_relations"]
+    half = R // 2
+    tw = (np.arange(n_types) + 1.0) ** -0.5
+    tw /= tw.sum()
+    etype = rng.choice(n_types, size=N, p=tw)
+    members = [np.flatnonzero(etype == t) for t in range(n_types)]
+    for t in range(n_types):                                    # no empty type
+        if members[t].shape[0] == 0:
+            etype[t] = t
+    members = [np.flatnonzero(etype == t) for t in range(n_types)]
+    pop = []                                                    # Zipf popularity inside a type
+    for t in range(n_types):
+        w = (np.arange(members[t].shape[0]) + 1.0) ** (-shape["entity_zipf"])
+        pop.append(np.cumsum(w / w.sum()))
+    dom = rng.choice(n_types, size=half, p=tw)
+    ran = rng.choice(n_types, size=half, p=tw)
+    rw = np.asarray(shape["eval_count_per_base_relation"], dtype=np.float64) + 1.0
+    rw /= rw.sum()
+    cdf_r = np.cumsum(rw)
+    taken = np.zeros(0, dtype=np.int64)
+
+    def draw(n_target):
+        nonlocal taken
+        out = np.zeros(0, dtype=np.int64)
+        while out.shape[0] < n_target:
+            k = int((n_target - out.shape[0]) * 1.3) + 64
+            r = np.minimum(np.searchsorted(cdf_r, rng.random(k)), half - 1).astype(np.int64)
+            u, v = rng.random(k), rng.random(k)
+            h = np.empty(k, dtype=np.int64)
+            t = np.empty(k, dtype=np.int64)
+            for ty in range(n_types):
+                sel = dom[r] == ty
+                if sel.any():
+                    h[sel] = members[ty][np.minimum(np.searchsorted(pop[ty], u[sel]), members[ty].shape[0] - 1)]
+                sel = ran[r] == ty
+                if sel.any():
+                    t[sel] = members[ty][np.minimum(np.searchsorted(pop[ty], v[sel]), members[ty].shape[0] - 1)]
+            key = (r * N + h) * N + t
+            ok = h != t
+            _, first = np.unique(key, return_index=True)
+            uniq = np.zeros(k, dtype=bool)
+            uniq[first] = True
+            ok &= uniq
+            for prev in (taken, out):
+                if prev.shape[0]:
+                    srt = np.sort(prev)
+                    pos = np.minimum(np.searchsorted(srt, key), srt.shape[0] - 1)
+                    ok &= srt[pos] != key
+            out = np.concatenate([out, key[ok][: n_target - out.shape[0]]])
+        taken = np.concatenate([taken, out])
+        return np.stack([(out // N) % N, out // (N * N), out % N], 1)
+
+    valid = draw(shape["valid_triples"] // 2)
+    test = draw(shape["test_triples"] // 2)
+    train = draw(shape["train_base_triples"])
+    train = train[np.lexsort((train[:, 2], train[:, 1], train[:, 0]))]
+    meta = {"etype": etype, "domain": np.concatenate([dom, ran]), "range": np.concatenate([ran, dom])}
+    return N, R, _with_inverses(train, half), _with_inverses(valid, half), _with_inverses(test, half), meta
+
+
+def typed_rules(shape: dict, meta: dict, seed: int = None) -> List[Tuple[int, List[int]]]:
+    """Per head the shape's number of rules of each body length; bodies are type-compatible chains from the head's
+    domain to its range (the last constraint is dropped when no chain of that length satisfies it)."""
+    seed = shape["seed"] if seed is None else seed
+    rng = np.random.default_rng(seed + 11)
+    R, lmax = shape["num_relations"], shape["max_len"]
+    dom, ran = meta["domain"], meta["range"]
+    n_types = int(max(dom.max(), ran.max())) + 1
+    by_dom = [np.flatnonzero(dom == t) for t in range(n_types)]
+    by_pair = {(a, b): np.flatnonzero((dom == a) & (ran == b)) for a in range(n_types) for b in range(n_types)}
+    rules: List[Tuple[int, List[int]]] = []
+    for q in range(R):
+        n_len = shape["rules_per_head_by_len"][q]
+        rules += [(q, [])] * n_len[0]
+        for L in range(1, lmax + 1):
+            for _ in range(n_len[L]):
+                body, cur = [], int(dom[q])
+                for pos in range(L):
+                    last = pos == L - 1
+                    cand = by_pair[(cur, int(ran[q]))] if last else by_dom[cur]
+                    if cand.shape[0] == 0:
+                        cand = by_dom[cur] if by_dom[cur].shape[0] else np.arange(R)
+                    rel = int(cand[rng.integers(cand.shape[0])])
+                    body.append(rel)
+                    cur = int(ran[rel])
+                rules.append((q, body))
+    order = rng.permutation(len(rules))
+    return [rules[i] for i in order]

@@ -8,7 +8,9 @@ Differences that do not change results at world size 1:
   * evaluate() ranks each batch as it is scored instead of keeping the split's [Q,N] logits.
 Multi-GPU: one process per GPU, batches sharded by DistributedSampler (as the reference), the KG
 and rules replicated, ONE all-reduce per step of the flattened gradients (DDP-mean semantics,
-trainer.py:56-60), and one gather of the (h,r,t,L,H) rows at the end of evaluate()."""
+trainer.py:56-60), and one gather of the (h,r,t,L,H) rows at the end of evaluate().  The exchange of step i
+runs after the grounding of step i+1 was enqueued (same stream: it does not overlap it; the point of the
+early enqueue is that the GPU is never idle while the host reads step i back)."""
 import logging
 import os
 from itertools import islice
@@ -33,26 +35,30 @@ def shard_indices(n_items, world_size, rank, shuffle=True, seed=0, epoch=0):
     return list(iter(sampler))
 
 
-def allreduce_mean_grads(params, world_size):
+def allreduce_mean_grads(params, world_size, local_step=True):
     """The path's one collective: a single flat all-reduce of every gradient, then / world_size
     (DDP mean semantics, trainer.py:56-60).  A usage flag per parameter rides along so that a
-    parameter no rank used keeps grad=None (find_unused_parameters=True behaviour)."""
+    parameter no rank used keeps grad=None (find_unused_parameters=True behaviour), and so does this rank's
+    "my batch had candidates" flag: the return value says whether ANY rank wants an optimizer step, so that
+    every rank takes the same decision and the replicas never diverge (the reference skips the step per rank,
+    trainer.py:87, and would dead-lock DDP there)."""
     if world_size == 1 or not params:
-        return
+        return bool(local_step)
     device = params[0].device
-    used = torch.tensor([0.0 if p.grad is None else 1.0 for p in params], device=device)
+    used = torch.tensor([0.0 if p.grad is None else 1.0 for p in params] + [1.0 if local_step else 0.0], device=device)
     flat = torch.cat([(p.grad if p.grad is not None else torch.zeros_like(p)).reshape(-1).float() for p in params]
                      + [used])
     comm.all_reduce_sum_(flat)
     n_par = len(params)
-    flat[:-n_par] /= world_size
-    used = flat[-n_par:].cpu().tolist()
+    flat[:-(n_par + 1)] /= world_size
+    used = flat[-(n_par + 1):].cpu().tolist()
     off = 0
-    for p, u in zip(params, used):
+    for p, u in zip(params, used[:-1]):
         n = p.numel()
         if u > 0:
             p.grad = flat[off:off + n].view_as(p).clone()
         off += n
+    return used[-1] > 0
 
 
 def snake_deal(costs, world_size, rank):
@@ -68,8 +74,8 @@ def snake_deal(costs, world_size, rank):
 
 class TrainerPredictor(object):
     slots_per_step = 1      # train batches per optimizer step (1 = the reference's schedule)
-    pipelined = True        # Predictor(bias): enqueue step i+1 before reading step i back (a 32-bit count overflow
-                            # then aborts with RlError instead of falling back to 64-bit rows; set False to get the fallback)
+    pipelined = True        # enqueue the grounding of step i+1 before reading step i back (flags are checked before
+                            # every optimizer step; an overflowed step is redone with 64-bit rows / larger arrays)
     eval_batches_per_call = 64
 
     def __init__(self, model, train_set, valid_set, test_set, optimizer, scheduler=None, gpus=None, num_worker=0):
@@ -103,8 +109,8 @@ class TrainerPredictor(object):
         self.optimizer = optimizer
         self.scheduler = scheduler
 
-    def _allreduce_grads(self):
-        allreduce_mean_grads([p for p in self.model.parameters() if p.requires_grad], self.world_size)
+    def _allreduce_grads(self, local_step=True):
+        return allreduce_mean_grads([p for p in self.model.parameters() if p.requires_grad], self.world_size, local_step)
 
     def train(self, batch_per_epoch, smoothing, print_every):
         if comm.get_rank() == 0:
@@ -121,11 +127,12 @@ class TrainerPredictor(object):
         N = self.train_set.graph.entity_size
         done = 0
         steps = [[self.train_set.batch_arrays[i] for i in order[s0:s0 + k]] for s0 in range(0, len(order), k)]
-        # Predictor with a bias feature: software pipeline.  The grounding of step i+1 (parameter-independent)
-        # is enqueued before the gradient exchange of step i, and the host reads step i's losses only after
-        # step i+1 is on the stream.  (In mask mode the optimizer step depends on a host-side candidate count,
-        # trainer.py:87, so those models take the synchronous path.)
-        pipelined = self.pipelined and hasattr(model, "prepare_train_step") and not use_mask
+        # Software pipeline: the grounding of step i+1 (parameter-independent) is enqueued BEFORE the host waits
+        # for step i's losses and flags, so the GPU has work queued while the host reads step i back, exchanges
+        # its gradients and steps the optimizer.  The flags are always checked before the optimizer step: a step
+        # whose 32-bit counts overflowed (or whose cell arrays were too small) is redone synchronously first.
+        from .predictors import RlStepOverflow
+        pipelined = bool(self.pipelined and getattr(model, "supports_pipeline", False))
         ticket = None
         if pipelined and steps:
             from .data import StepPrefetcher
@@ -135,19 +142,23 @@ class TrainerPredictor(object):
             self.optimizer.zero_grad(set_to_none=True)
             if pipelined:
                 prep = model.prepare_train_step(next(packed)) if si + 1 < len(steps) else None
-                model.rule_weights.grad, model.bias.grad = ticket.gw, ticket.gb
-                self._allreduce_grads()
-                self.optimizer.step()
-                nxt = prep.finish(smoothing, grad_scale=1.0 / len(steps[si + 1])) if prep is not None else None
-                loss, tsum = ticket.result()
-                ticket, cand = nxt, None
+                try:
+                    loss, tsum = ticket.result()
+                    ticket.gbuf.assign(ticket.used)
+                    cand = ticket.mask_sum
+                except RlStepOverflow:
+                    loss, tsum = model.fused_train_step(batches, smoothing, grad_scale=1.0 / len(batches))
+                    cand = model.last_ticket.mask_sum
+                    if prep is not None:                               # the redo used the shared frontier workspace
+                        prep = model.prepare_train_step(prep.batches)
             else:
                 loss, tsum = model.fused_train_step(batches, smoothing, grad_scale=1.0 / len(batches))
                 cand = getattr(model, "last_mask_sum", None)          # per-batch mask.sum() in mask mode
-                skip = use_mask and cand is not None and all(c == 0 for c in cand)
-                self._allreduce_grads()
-                if not skip:                                          # trainer.py:87: no candidates -> no step
-                    self.optimizer.step()
+            local_step = not (use_mask and cand is not None and all(c == 0 for c in cand))
+            if self._allreduce_grads(local_step):                     # trainer.py:87: no candidates anywhere -> no step
+                self.optimizer.step()
+            if pipelined:
+                ticket = prep.finish(smoothing, grad_scale=1.0 / len(steps[si + 1])) if prep is not None else None
             self.optimizer.zero_grad(set_to_none=True)
             for j, b in enumerate(batches):
                 msum = float(cand[j]) if (use_mask and cand is not None) else float(len(b) * N)

@@ -1,6 +1,6 @@
 """Config / logging / seeding helpers with the reference's names (src/utils.py:12-70).  YAML files
-of the reference load unchanged; ``easydict`` is not a dependency (a small attribute-dict is
-used when it is absent)."""
+of the reference load unchanged; ``easydict`` is not a dependency (a small attribute-dict of the same
+behaviour is defined here)."""
 import logging
 import os
 import random
@@ -9,29 +9,29 @@ import numpy as np
 import torch
 import yaml
 
-try:
-    from easydict import EasyDict
-except ImportError:
-    class EasyDict(dict):
-        def __init__(self, d=None, **kwargs):
-            super().__init__()
-            for k, v in dict(d or {}, **kwargs).items():
-                self[k] = v
+class EasyDict(dict):
+    """Attribute-access dict (what the third-party ``easydict`` package provides; not a dependency here --
+    compat/easydict.py re-exports this class for the reference's ``from easydict import EasyDict``)."""
 
-        def __setitem__(self, k, v):
-            if isinstance(v, dict) and not isinstance(v, EasyDict):
-                v = EasyDict(v)
-            elif isinstance(v, (list, tuple)):
-                v = type(v)(EasyDict(x) if isinstance(x, dict) else x for x in v)
-            super().__setitem__(k, v)
+    def __init__(self, d=None, **kwargs):
+        super().__init__()
+        for k, v in dict(d or {}, **kwargs).items():
+            self[k] = v
 
-        def __getattr__(self, k):
-            try:
-                return self[k]
-            except KeyError:
-                raise AttributeError(k)
+    def __setitem__(self, k, v):
+        if isinstance(v, dict) and not isinstance(v, EasyDict):
+            v = EasyDict(v)
+        elif isinstance(v, (list, tuple)):
+            v = type(v)(EasyDict(x) if isinstance(x, dict) else x for x in v)
+        super().__setitem__(k, v)
 
-        __setattr__ = __setitem__
+    def __getattr__(self, k):
+        try:
+            return self[k]
+        except KeyError:
+            raise AttributeError(k)
+
+    __setattr__ = __setitem__
 
 
 def load_config(cfg_file):
