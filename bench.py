@@ -213,7 +213,9 @@ class Runner:
         for s in range(warmup):
             gbuf = self.cellpath.GradBuffer(self.params)
             model.step_on_slots(sk, slots[s], 0.2, 1.0 / per, gbuf)
+            flags_acc += slots[s].flags                  # (also warms the op: its first call loads a module, ~17 ms)
             self.finish_step(self.start_allreduce(gbuf), gbuf)
+        flags_acc.zero_()
         torch.cuda.synchronize()
         if self.world > 1:
             torch.distributed.barrier()
@@ -224,15 +226,26 @@ class Runner:
         ev0.record()
         losses = []
         sk.gr._run(slots[warmup], 32)
+        dbg = os.environ.get("RL_BENCH_TRACE")
         for s in range(warmup, n_steps):
+            t0 = time.perf_counter()
             gbuf = self.cellpath.GradBuffer(self.params)
+            t1 = time.perf_counter()
             loss, tsum = model.step_on_slots(sk, slots[s], 0.2, 1.0 / per, gbuf, expanded=True)
+            t2 = time.perf_counter()
             flags_acc += slots[s].flags                  # the workspace is reused by the next step
+            t2b = time.perf_counter()
             pending = self.start_allreduce(gbuf)
             if s + 1 < n_steps:                          # grounding is parameter-independent: enqueue it before the exchange
                 sk.gr._run(slots[s + 1], 32)
+            t3 = time.perf_counter()
+            if dbg and s < warmup + 3:
+                print("[trace] flags %.2f ms" % ((t2b - t2) * 1e3), file=sys.stderr)
             self.finish_step(pending, gbuf)
             losses.append(loss)
+            if dbg and s < warmup + 6:
+                print("[trace] gbuf %.2f step %.2f run %.2f finish %.2f ms" % ((t1 - t0) * 1e3, (t2 - t1) * 1e3, (t3 - t2) * 1e3,
+                                                                              (time.perf_counter() - t3) * 1e3), file=sys.stderr)
         ev1.record()
         torch.cuda.synchronize()
         if self.world > 1:
@@ -242,7 +255,7 @@ class Runner:
         events, sk.gr.level_events = sk.gr.level_events, None
         flags = flags_acc.cpu().numpy()
         assert flags[8] == 0, "32-bit count overflow inside the timed region"
-        assert flags[1] == 0, "cell arrays overflowed inside the timed region"
+        assert flags[1] == 0 and flags[3] == 0, "cell arrays overflowed inside the timed region"
         assert all(torch.isfinite(l).all().item() for l in losses)
         return ms, sum(self.queries[s % len(self.steps)] for s in range(warmup, n_steps)), launches, events
 
@@ -338,6 +351,8 @@ def side_config(tag, kg, rules, batches, kw, per, steps, world, rank, dev, plus=
     ms, q = reduce_max_sum(ms, q, dev, world)
     out = {"e2e_queries_per_sec": q / (ms / 1e3), "ms_per_step": ms / steps, "steps": steps, "batches_per_step_per_gpu": per,
            "queries_per_step_per_gpu": int(np.mean(run.queries)), "h2d_bytes_per_step": h2d // steps, "d2h_bytes_per_step": d2h // steps}
+    if rank == 0:
+        print("[bench] %s: %.0f q/s e2e, %.3f ms/step" % (tag, out["e2e_queries_per_sec"], out["ms_per_step"]), file=sys.stderr)
     del run, model
     torch.cuda.empty_cache()
     return out
@@ -518,6 +533,9 @@ def main():
     e2e_ms, q_e2e, h2d, d2h = run.e2e_loop(args.warmup, args.steps, trace)
     e2e_ms, q_e2e = reduce_max_sum(e2e_ms, q_e2e, dev, world)
     e2e_value = q_e2e / (e2e_ms / 1e3)
+    if rank == 0:
+        print("[bench] headline: value %.0f q/s (%.3f ms/step), e2e %.0f q/s, dense-mode roofline frac %.3f, expansion share %.2f"
+              % (value, elapsed_ms / args.steps, e2e_value, roofline["frac"], roofline_product["share_of_step"]), file=sys.stderr)
     if args.trace_e2e and rank == 0:
         print("e2e per step, host enqueue/wait ms: " + " ".join("%.2f/%.2f" % (a * 1e3, b * 1e3) for a, b in trace), file=sys.stderr)
 

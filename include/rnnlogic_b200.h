@@ -163,6 +163,16 @@ typedef struct rl_cells {
     int32_t *cand_off;    /* [S][N] first cell of the entity */
     int32_t *cell_key;    /* [cap] slot*32 + lane of the cell */
     int32_t *slot_ncell;  /* [S] cells per slot (= mask.sum() of the batch without an entity feature, trainer.py:96) */
+    /* Non-zero (rule end, query, entity) counts of the call in coordinate form (optional: nnz_cap == 0 switches it
+     * off).  nnz_off[i] = first non-zero of the i-th entity-grouped item (rl_cells_build: prefix of the items' lane
+     * mask populations); rl_predictor_cell_scores fills nz_val (fp32(count), predictors.py:64), nz_cell (its cell)
+     * and nz_item (its item) while it reads the count rows, so the backward never touches them again.
+     * counters[2] = number of non-zeros, counters[3] != 0: nnz_cap exceeded. */
+    int32_t nnz_cap;
+    int32_t *nnz_off;     /* [item capacity of the call] */
+    float *nz_val;        /* [nnz_cap] */
+    int32_t *nz_cell;     /* [nnz_cap] */
+    int32_t *nz_item;     /* [nnz_cap] index into items_sorted (global) */
 } rl_cells;
 
 int rl_abi_version(void);
@@ -422,6 +432,9 @@ int rl_cells_softmax_ce(const rl_graph *g, const rl_slots *s, const rl_cells *c,
 /* Predictor backward: grad_w[rule] += sum over the rule's non-zero rows of <Gc[cells], fp32(counts)>. */
 int rl_predictor_cell_backward(const rl_graph *g, const rl_rules *r, const rl_slots *s, const rl_frontier *fr,
                                const rl_cells *c, const float *Gc, float *grad_w, void *stream);
+/* The same from the coordinate list rl_predictor_cell_scores left (c->nnz_cap > 0): one thread per non-zero. */
+int rl_predictor_nnz_backward(const rl_graph *g, const rl_rules *r, const rl_slots *s, const rl_frontier *fr,
+                              const rl_cells *c, const float *Gc, float *grad_w, void *stream);
 
 /* Filtered rank (src/trainer.py:189-201) from cell scores: (L,H) int64[S*32][2].  With a bias the entities
  * outside a query's cells are counted by binary search in sorted_bias (bias sorted ascending);
@@ -446,16 +459,21 @@ int rl_plus_cell_backward(const rl_graph *g, const rl_rules *r, const rl_slots *
 
 /* Dense tail of PredictorPlus with the sum aggregator on the cells (src/layers.py:73-75,
  * src/predictors.py:253-255), H = 16, J = 128: zc[cell] = W2 . relu(W1 [relu(LN(W0 F + b0)), rel[head]] + b1) + b2.
- * The backward ACCUMULATES every weight gradient in-kernel (layouts of the parameters), writes dF[cell][16]
- * and needs d1sum[R][128] scratch. */
+ * The forward also leaves O[cell][16] (the front's output) and relu_bits[cell][4] (which hidden units are active);
+ * the backward uses them instead of recomputing the hidden layer, ACCUMULATES every weight gradient in-kernel
+ * (layouts of the parameters), writes dF[cell][16] (and dY[cell][16], scratch) and needs
+ * rl_tail_scratch_floats(R) floats of scratch. */
+int64_t rl_tail_scratch_floats(int32_t R);
 int rl_tail_forward(const rl_cells *c, const int32_t *slot_head, int32_t H, int32_t J, const float *F, const float *W0,
                     const float *b0, const float *gamma, const float *beta, const float *W1, const float *b1,
-                    const float *W2, const float *b2, const float *rel_emb, float *zc, void *stream);
+                    const float *W2, const float *b2, const float *rel_emb, float *zc, float *O, uint32_t *relu_bits,
+                    void *stream);
 int rl_tail_backward(const rl_cells *c, const int32_t *slot_head, int32_t R, int32_t H, int32_t J, const float *F,
                      const float *W0, const float *b0, const float *gamma, const float *beta, const float *W1,
                      const float *b1, const float *W2, const float *b2, const float *rel_emb, const float *Gc,
-                     float *dF, float *gW0, float *gb0, float *ggamma, float *gbeta, float *gW1, float *gb1,
-                     float *gW2, float *gb2, float *grel, float *d1sum, void *stream);
+                     const float *O, const uint32_t *relu_bits, float *dF, float *dY, float *gW0, float *gb0,
+                     float *ggamma, float *gbeta, float *gW1, float *gb1, float *gW2, float *gb2, float *grel,
+                     float *scratch, void *stream);
 
 #ifdef __cplusplus
 }

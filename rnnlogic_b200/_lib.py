@@ -50,7 +50,8 @@ class RlFrontier(C.Structure):
 
 class RlCells(C.Structure):
     _fields_ = [("cap", C.c_int32), ("counters", vp), ("nzmask", vp), ("cand_off", vp), ("cell_key", vp),
-                ("slot_ncell", vp)]
+                ("slot_ncell", vp), ("nnz_cap", C.c_int32), ("nnz_off", vp), ("nz_val", vp), ("nz_cell", vp),
+                ("nz_item", vp)]
 
 
 class RlAnswers(C.Structure):
@@ -160,6 +161,8 @@ _PROTOS = {
                                       C.c_float, vp, vp, vp, C.c_int32, vp, C.c_float, vp, vp, vp, vp, vp, vp, vp, vp]),
     "rl_predictor_cell_backward": (C.c_int, [C.POINTER(RlGraph), C.POINTER(RlRules), C.POINTER(RlSlots),
                                              C.POINTER(RlFrontier), C.POINTER(RlCells), vp, vp, vp]),
+    "rl_predictor_nnz_backward": (C.c_int, [C.POINTER(RlGraph), C.POINTER(RlRules), C.POINTER(RlSlots),
+                                            C.POINTER(RlFrontier), C.POINTER(RlCells), vp, vp, vp]),
     "rl_cells_rank": (C.c_int, [C.POINTER(RlGraph), C.POINTER(RlSlots), C.POINTER(RlCells), C.POINTER(RlAnswers),
                                 vp, vp, vp, vp, vp, vp]),
     "rl_cells_add_to_dense": (C.c_int, [C.POINTER(RlGraph), C.POINTER(RlSlots), C.POINTER(RlCells), vp, vp, vp]),
@@ -168,8 +171,9 @@ _PROTOS = {
                                         C.POINTER(RlCells), vp, C.c_int32, C.c_int32, vp, vp, vp, vp, vp, vp, vp, vp]),
     "rl_plus_cell_backward": (C.c_int, [C.POINTER(RlGraph), C.POINTER(RlRules), C.POINTER(RlSlots), C.POINTER(RlFrontier),
                                         C.POINTER(RlCells), C.c_int32, vp, vp, vp]),
-    "rl_tail_forward": (C.c_int, [C.POINTER(RlCells), vp, C.c_int32, C.c_int32] + [vp] * 12),
-    "rl_tail_backward": (C.c_int, [C.POINTER(RlCells), vp, C.c_int32, C.c_int32, C.c_int32] + [vp] * 23),
+    "rl_tail_scratch_floats": (C.c_int64, [C.c_int32]),
+    "rl_tail_forward": (C.c_int, [C.POINTER(RlCells), vp, C.c_int32, C.c_int32] + [vp] * 14),
+    "rl_tail_backward": (C.c_int, [C.POINTER(RlCells), vp, C.c_int32, C.c_int32, C.c_int32] + [vp] * 26),
     "rl_adam_step": (C.c_int, [C.c_int64, vp, vp, vp, vp, C.c_float, C.c_float, C.c_float, C.c_float, C.c_float,
                                C.c_int64, vp]),
     "rl_lstm_encode_forward": (C.c_int, [C.c_int32, C.c_int32, C.c_int32, C.c_int32, vp, vp, vp, vp, vp, vp, vp]),

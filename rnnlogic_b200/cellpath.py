@@ -83,6 +83,10 @@ class CellKernels:
         _lib.check(_L().rl_predictor_cell_backward(self.dg.ref(), self.dr.ref(), sl.ref(), sl.fref(), C.byref(sl.cells),
                                                    Gc.data_ptr(), grad_w.data_ptr(), _stream()), "rl_predictor_cell_backward")
 
+    def predictor_nnz_backward(self, sl, Gc, grad_w):
+        _lib.check(_L().rl_predictor_nnz_backward(self.dg.ref(), self.dr.ref(), sl.ref(), sl.fref(), C.byref(sl.cells),
+                                                  Gc.data_ptr(), grad_w.data_ptr(), _stream()), "rl_predictor_nnz_backward")
+
     def rank(self, sl, bias, sorted_bias, zc, which):
         counters = torch.empty(sl.S * 64, dtype=torch.int32, device=self.device)
         LH = torch.empty(sl.S * LANES, 2, dtype=torch.int64, device=self.device)
@@ -109,14 +113,16 @@ class CellKernels:
         _lib.check(_L().rl_plus_cell_backward(self.dg.ref(), self.dr.ref(), sl.ref(), sl.fref(), C.byref(sl.cells), 16,
                                               dF.data_ptr(), grad_emb.data_ptr(), _stream()), "rl_plus_cell_backward")
 
-    def tail_forward(self, sl, F, wts, zc):
+    def tail_forward(self, sl, F, wts, zc, O, bits):
         _lib.check(_L().rl_tail_forward(C.byref(sl.cells), sl.slot_head.data_ptr(), 16, 128, F.data_ptr(),
-                                        *[t.data_ptr() for t in wts], zc.data_ptr(), _stream()), "rl_tail_forward")
+                                        *[t.data_ptr() for t in wts], zc.data_ptr(), O.data_ptr(), bits.data_ptr(),
+                                        _stream()), "rl_tail_forward")
 
-    def tail_backward(self, sl, R, F, wts, Gc, dF, grads, d1sum):
+    def tail_backward(self, sl, R, F, wts, Gc, O, bits, dF, dY, grads, scratch):
         _lib.check(_L().rl_tail_backward(C.byref(sl.cells), sl.slot_head.data_ptr(), int(R), 16, 128, F.data_ptr(),
-                                         *[t.data_ptr() for t in wts], Gc.data_ptr(), dF.data_ptr(),
-                                         *[t.data_ptr() for t in grads], d1sum.data_ptr(), _stream()), "rl_tail_backward")
+                                         *[t.data_ptr() for t in wts], Gc.data_ptr(), O.data_ptr(), bits.data_ptr(),
+                                         dF.data_ptr(), dY.data_ptr(), *[t.data_ptr() for t in grads], scratch.data_ptr(),
+                                         _stream()), "rl_tail_backward")
 
 
 def cell_kernels(sk) -> CellKernels:
@@ -135,13 +141,13 @@ def predictor_step(model, sk, sl, smoothing, grad_scale, gw, gb, expanded=False,
     ck = cell_kernels(sk)
     if not expanded:
         sk.gr._run(sl, bits)
-    _, (zc, Gc) = sk.gr.build_cells(sl, 2)
+    _, (zc, Gc) = sk.gr.build_cells(sl, 2, coo=True)
     bias = model.bias.detach() if model.entity_feature == "bias" else None
     if bias is not None:
         ck.bias_stats(bias)
-    ck.predictor_scores(sl, model.rule_weights.detach(), zc)
+    ck.predictor_scores(sl, model.rule_weights.detach(), zc)          # also leaves the non-zero counts in coordinate form
     loss, tsum = ck.softmax_ce(sl, bias, zc, smoothing, sl.group_ptr_dev, len(sl.group_sizes), grad_scale, Gc, gb)
-    ck.predictor_backward(sl, Gc, gw)
+    ck.predictor_nnz_backward(sl, Gc, gw)
     return loss, tsum
 
 
@@ -166,6 +172,17 @@ def plus_cells_supported(model) -> bool:
     return (model.aggregator == "sum" and model.hidden_dim == 16 and len(sm.layers) == 2
             and sm.layers[0].out_features == 128 and sm.layers[1].out_features == 1 and sm.batch_norms is None
             and not sm.short_cut and sm.dropout is None)
+
+
+PLUS_PLANES = 2 + 4 * 16 + 4          # zc, Gc | F, dF, O, dY [16 each] | ReLU bits [4 words]
+
+
+def _plus_planes(gr):
+    """Per-cell arrays of the PredictorPlus step inside the grounder's cell workspace (contiguous [cap][16] blocks)."""
+    cap, ws = gr._ws_cells_cap, gr._ws_cells
+    blk = lambda i0, n: ws[(1 + i0) * cap:(1 + i0 + n) * cap]
+    return {"zc": blk(0, 1), "Gc": blk(1, 1), "F": blk(2, 16), "dF": blk(18, 16), "O": blk(34, 16), "dY": blk(50, 16),
+            "bits": blk(66, 4)}
 
 
 def _tail_weights(model):
@@ -206,15 +223,13 @@ def plus_step(model, sk, sl, smoothing, grad_scale, gbuf: GradBuffer, expanded=F
     dev = sk.device
     if not expanded:
         sk.gr._run(sl, bits)
-    _, planes = sk.gr.build_cells(sl, 2 + 16 + 16)
-    zc, Gc = planes[0], planes[1]
-    cap = sl.cell_cap
-    F = sk.gr._ws_cells[3 * sk.gr._ws_cells_cap:(3 + 16) * sk.gr._ws_cells_cap]         # [cap][16], contiguous planes
-    dF = sk.gr._ws_cells[(3 + 16) * sk.gr._ws_cells_cap:(3 + 32) * sk.gr._ws_cells_cap]
+    sk.gr.build_cells(sl, PLUS_PLANES)
+    pl = _plus_planes(sk.gr)
+    zc, Gc, F, dF = pl["zc"], pl["Gc"], pl["F"], pl["dF"]
     emb, enc = _rule_embeddings(model, sl, dev)
     wts = [t.detach() for t in _tail_weights(model)]
     ck.plus_features(sl, emb, F)
-    ck.tail_forward(sl, F, wts, zc)
+    ck.tail_forward(sl, F, wts, zc, pl["O"], pl["bits"])
     ef = model.entity_feature
     ng = len(sl.group_sizes)
     extra = None
@@ -237,8 +252,7 @@ def plus_step(model, sk, sl, smoothing, grad_scale, gbuf: GradBuffer, expanded=F
     if not want_grad:
         return loss, tsum
     grads = [gbuf.view(p) for p in _tail_weights(model)]
-    d1sum = model._d1sum_scratch(dev)
-    ck.tail_backward(sl, model.num_relations, F, wts, Gc, dF, grads, d1sum)
+    ck.tail_backward(sl, model.num_relations, F, wts, Gc, pl["O"], pl["bits"], dF, pl["dY"], grads, model._d1sum_scratch(dev))
     if model.type == "emb":
         ck.plus_backward(sl, dF, gbuf.view(model.rule_emb))
     elif enc is not None:
@@ -278,13 +292,13 @@ def plus_rank(model, sk, sl, split):
     ck = cell_kernels(sk)
     dev = sk.device
     sk.gr.ground(sl)
-    _, planes = sk.gr.build_cells(sl, 2 + 16 + 16)
-    zc = planes[0]
-    F = sk.gr._ws_cells[3 * sk.gr._ws_cells_cap:(3 + 16) * sk.gr._ws_cells_cap]
+    sk.gr.build_cells(sl, PLUS_PLANES)
+    pl = _plus_planes(sk.gr)
+    zc, F = pl["zc"], pl["F"]
     emb, _ = _rule_embeddings(model, sl, dev)
     wts = [t.detach() for t in _tail_weights(model)]
     ck.plus_features(sl, emb, F)
-    ck.tail_forward(sl, F, wts, zc)
+    ck.tail_forward(sl, F, wts, zc, pl["O"], pl["bits"])
     which = "hr2oo" if split == "valid" else "hr2ooo"
     ef = model.entity_feature
     if ef == "RotatE":

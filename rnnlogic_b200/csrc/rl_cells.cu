@@ -36,7 +36,7 @@ __device__ __forceinline__ uint32_t lanemask_lt()
 // slot -- the order between slots is arbitrary and internal), entity-major, lane-minor.
 // ------------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(512)
-k_cell_scan(rl_graph g, rl_rules r, rl_slots s, rl_cells c)
+k_cell_scan(rl_graph g, rl_rules r, rl_slots s, rl_frontier fr, rl_cells c)
 {
     __shared__ int wsum[16];
     __shared__ int s_base;
@@ -91,6 +91,46 @@ k_cell_scan(rl_graph g, rl_rules r, rl_slots s, rl_cells c)
             if (idx < c.cap) c.cell_key[idx] = slot * RL_LANES + b;
             ++idx;
         }
+        carry += total;
+        __syncthreads();
+    }
+    if (c.nnz_cap <= 0) return;
+    // first non-zero of every entity-grouped item: prefix of the items' lane-mask populations
+    const int n = fr.item_cnt[slot];
+    const long long ibase = fr.item_off[slot];
+    const uint32_t *im = fr.item_mask_sorted + ibase;
+    tot = 0;
+    for (int i = tid; i < n; i += 512) tot += __popc(im[i]);
+    tot = warp_sumi(tot);
+    if (lane == 0) wsum[warp] = tot;
+    __syncthreads();
+    if (tid == 0) {
+        int t = 0;
+        for (int k = 0; k < 16; ++k) t += wsum[k];
+        s_base = atomicAdd(c.counters + 2, t);
+        if ((long long)s_base + t > (long long)c.nnz_cap) c.counters[3] = 1;
+    }
+    __syncthreads();
+    carry = s_base;
+    for (int i0 = 0; i0 < n; i0 += 512) {
+        const int i = i0 + tid;
+        const int v = i < n ? __popc(im[i]) : 0;
+        int incl = v;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) {
+            const int t = __shfl_up_sync(FULL, incl, o);
+            if (lane >= o) incl += t;
+        }
+        if (lane == 31) wsum[warp] = incl;
+        __syncthreads();
+        int wbase = 0, total = 0;
+#pragma unroll
+        for (int k = 0; k < 16; ++k) {
+            const int t = wsum[k];
+            if (k < warp) wbase += t;
+            total += t;
+        }
+        if (i < n) c.nnz_off[ibase + i] = carry + wbase + incl - v;
         carry += total;
         __syncthreads();
     }
@@ -162,10 +202,13 @@ k_pred_cells(rl_graph g, rl_rules r, rl_slots s, rl_frontier fr, rl_cells c, con
     WordItems wi = load_word_items(fr, s, W, slot, ew);
     int cur = -1;
     double acc = 0.0;
+    const bool coo = c.nnz_cap > 0;
+    const long long ibase = fr.item_off[slot];
     const int B0 = __shfl_sync(FULL, wi.b0, 0), B1 = wi.wend;
     for (int c0 = B0; c0 < B1; c0 += 32) {
         if (c0 != wi.wbase) word_items_window(wi, c0);
         const int cnt = min(32, B1 - c0);
+        const int my_n0 = (coo && lane < cnt) ? c.nnz_off[ibase + c0 + lane] : 0;
         for (int j0 = 0; j0 < cnt; j0 += PC_ROWS) {
             CT cv[PC_ROWS];
             float wv[PC_ROWS];
@@ -178,6 +221,20 @@ k_pred_cells(rl_graph g, rl_rules r, rl_slots s, rl_frontier fr, rl_cells c, con
                 const bool ok = j0 + u < cnt;
                 cv[u] = (ok && ((m >> lane) & 1u)) ? arena[(size_t)a * RL_LANES + lane] : (CT)0;
                 wv[u] = ok ? __ldg(w + __ldg(r.node_term_rule + t0)) : 0.f;
+                if (coo) {                                           // coordinate list for the backward: (cell, item, fp32 count)
+                    const int n0 = __shfl_sync(FULL, my_n0, src);
+                    const int ie = __shfl_sync(FULL, wi.win.z, src) & 31;
+                    const uint32_t bits = __shfl_sync(FULL, my_bits, ie);
+                    const int off = __shfl_sync(FULL, my_off, ie);
+                    if (ok && ((m >> lane) & 1u)) {
+                        const int pos = n0 + __popc(m & lt);
+                        if (pos < c.nnz_cap) {
+                            c.nz_val[pos] = (float)cv[u];
+                            c.nz_cell[pos] = off + __popc(bits & lt);
+                            c.nz_item[pos] = (int)(ibase + c0 + j0 + u);
+                        }
+                    }
+                }
             }
 #pragma unroll
             for (int u = 0; u < PC_ROWS; ++u) {
@@ -204,62 +261,6 @@ k_pred_cells(rl_graph g, rl_rules r, rl_slots s, rl_frontier fr, rl_cells c, con
     for (uint32_t todo = present & ~wi.present; todo; todo &= todo - 1) finish(__ffs(todo) - 1, 0.0);   // cells of empty-body rules only
 }
 
-// ------------------------------------------------------------------------------------------
-// per-query online softmax over the cells: partial[slot][blk] = {max[32], sumexp[32], a[32]} with
-// a = sum over the lane's cells of exp(bias[e] - Mg) (the share of those entities in Sg)
-// ------------------------------------------------------------------------------------------
-__global__ void __launch_bounds__(WARPS_PER_BLOCK * 32)
-k_cell_stats(rl_graph g, rl_cells c, const float *__restrict__ bias, const double *__restrict__ acc,
-             const float *__restrict__ zc, float *__restrict__ partial)
-{
-    __shared__ float sm_m[WARPS_PER_BLOCK][32], sm_s[WARPS_PER_BLOCK][32], sm_a[WARPS_PER_BLOCK][32];
-    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    const int slot = blockIdx.y;
-    const int N = g.num_entities, W = g.rank_words;
-    const float Mg = bias ? (float)acc[0] : 0.f;
-    const uint32_t lt = lanemask_lt();
-    float m = -INFINITY, sum = 0.f, a = 0.f;
-    for (int ew = blockIdx.x * WARPS_PER_BLOCK + warp; ew < W; ew += CELL_BLOCKS * WARPS_PER_BLOCK) {
-        const int e_lane = ew * 32 + lane;
-        const uint32_t my_bits = e_lane < N ? c.nzmask[(size_t)slot * N + e_lane] : 0u;
-        uint32_t present = __ballot_sync(FULL, my_bits != 0u);
-        if (!present) continue;
-        const int my_off = c.cand_off[(size_t)slot * N + min(e_lane, N - 1)];
-        const float bias_l = (bias && e_lane < N) ? bias[e_lane] : 0.f;
-        for (; present; present &= present - 1) {
-            const int i = __ffs(present) - 1;
-            const uint32_t bits = __shfl_sync(FULL, my_bits, i);
-            const int off = __shfl_sync(FULL, my_off, i);
-            const float bl = __shfl_sync(FULL, bias_l, i);
-            if ((bits >> lane) & 1u) {
-                const int idx = off + __popc(bits & lt);
-                const float l = bl + (idx < c.cap ? zc[idx] : 0.f);
-                const float mn = fmaxf(m, l);
-                sum = sum * expf(m - mn) + expf(l - mn);
-                m = mn;
-                if (bias) a += expf(bl - Mg);
-            }
-        }
-    }
-    sm_m[warp][lane] = m;
-    sm_s[warp][lane] = sum;
-    sm_a[warp][lane] = a;
-    __syncthreads();
-    if (warp == 0) {
-        float M = -INFINITY;
-        for (int k = 0; k < WARPS_PER_BLOCK; ++k) M = fmaxf(M, sm_m[k][lane]);
-        double S = 0.0, A = 0.0;
-        for (int k = 0; k < WARPS_PER_BLOCK; ++k) {
-            if (sm_m[k][lane] != -INFINITY) S += (double)sm_s[k][lane] * (double)expf(sm_m[k][lane] - M);
-            A += (double)sm_a[k][lane];
-        }
-        float *p = partial + ((size_t)slot * CELL_BLOCKS + blockIdx.x) * 96;
-        p[lane] = M;
-        p[32 + lane] = (float)S;
-        p[64 + lane] = (float)A;
-    }
-}
-
 // logit of (query b of the slot, entity e): bias[e] + cell score, or "no logit" (mask mode, not a cell)
 __device__ __forceinline__ bool cell_logit(const rl_cells &c, const float *__restrict__ bias, const float *__restrict__ zc,
                                            size_t srow, int e, int b, float &l, int &idx)
@@ -275,43 +276,88 @@ __device__ __forceinline__ bool cell_logit(const rl_cells &c, const float *__res
     return bias != nullptr;
 }
 
-// one block per slot, one warp per query lane: combine the partials into (M_b, S_b), then the sparse smoothed
-// target of the query (data.py:207-212, trainer.py:84) -> loss sums.  stats[slot][lane] = (M, S, S_b, valid)
+// order-preserving float <-> unsigned key (atomicMax on floats of either sign)
+__device__ __forceinline__ unsigned fkey(float v)
+{
+    const unsigned b = __float_as_uint(v);
+    return (b & 0x80000000u) ? ~b : (b | 0x80000000u);
+}
+__device__ __forceinline__ float fkey_inv(unsigned k)
+{
+    return __uint_as_float((k & 0x80000000u) ? (k & 0x7fffffffu) : ~k);
+}
+
+// One block per slot.  Threads first own ENTITIES (each walks the cells of its entities: 32 entities of a warp in
+// flight instead of one): per-query max of the cell logits, then per-query sum of exp(l - M) - exp(bias - M) (the
+// correction of the all-entity sum Sg), both through a few replicated shared-memory atomics.  Then one warp per
+// query lane walks the sparse smoothed target of its query (data.py:207-212, trainer.py:84) -> loss sums.
+// stats[slot][lane] = (M, S, S_b, valid)
+#define CE_COPIES 8
 __global__ void __launch_bounds__(CE_WARPS * 32)
 k_ce_cells(rl_graph g, rl_slots s, rl_cells c, rl_answers ans, float smoothing, const float *__restrict__ bias,
-           const double *__restrict__ acc, const float *__restrict__ zc, const float *__restrict__ partial,
-           float *__restrict__ stats, float *__restrict__ slot_lsum, float *__restrict__ slot_tsum)
+           const double *__restrict__ acc, const float *__restrict__ zc, float *__restrict__ stats,
+           float *__restrict__ slot_lsum, float *__restrict__ slot_tsum)
 {
+    __shared__ unsigned sm_max[CE_COPIES][32];
+    __shared__ float sm_sum[CE_COPIES][32];
+    __shared__ float sm_M[32], sm_S[32];
     __shared__ double red_l[CE_WARPS], red_t[CE_WARPS];
-    const int lane = threadIdx.x & 31, b = threadIdx.x >> 5;
+    const int tid = threadIdx.x, lane = tid & 31, b = tid >> 5;
     const int slot = blockIdx.x;
     const int N = g.num_entities;
     const int q = s.slot_head[slot];
-    const float *pp = partial + (size_t)slot * CELL_BLOCKS * 96;
-    float Mc = -INFINITY;
-#pragma unroll
-    for (int k = 0; k < CELL_BLOCKS; ++k) Mc = fmaxf(Mc, pp[k * 96 + b]);
-    double Sc = 0.0, A = 0.0;
-#pragma unroll
-    for (int k = 0; k < CELL_BLOCKS; ++k) {
-        const float mk = pp[k * 96 + b];
-        if (mk != -INFINITY) Sc += (double)pp[k * 96 + 32 + b] * (double)expf(mk - Mc);
-        A += (double)pp[k * 96 + 64 + b];
+    const size_t srow = (size_t)slot * N;
+    const float Mg = bias ? (float)acc[0] : 0.f;
+    if (tid < CE_COPIES * 32) {
+        (&sm_max[0][0])[tid] = fkey(-INFINITY);
+        (&sm_sum[0][0])[tid] = 0.f;
     }
-    float M, S;
-    if (bias) {
-        const float Mg = (float)acc[0];
-        M = fmaxf(Mg, Mc);
-        double Sd = fmax(acc[1] - A, 0.0) * (double)expf(Mg - M);
-        if (Mc != -INFINITY) Sd += Sc * (double)expf(Mc - M);
-        S = (float)Sd;
-    } else {
-        M = Mc;
-        S = (float)Sc;
+    __syncthreads();
+    const int cp = b & (CE_COPIES - 1);
+    for (int e = tid; e < N; e += CE_WARPS * 32) {              // pass 1: max
+        uint32_t bits = c.nzmask[srow + e];
+        if (!bits) continue;
+        int idx = c.cand_off[srow + e];
+        const float bl = bias ? bias[e] : 0.f;
+        for (; bits; bits &= bits - 1, ++idx) {
+            const float l = bl + (idx < c.cap ? zc[idx] : 0.f);
+            atomicMax(&sm_max[cp][__ffs(bits) - 1], fkey(l));
+        }
     }
+    __syncthreads();
+    if (tid < 32) {
+        unsigned k = sm_max[0][tid];
+#pragma unroll
+        for (int i = 1; i < CE_COPIES; ++i) k = max(k, sm_max[i][tid]);
+        const float Mc = fkey_inv(k);
+        sm_M[tid] = bias ? fmaxf(Mg, Mc) : Mc;
+    }
+    __syncthreads();
+    for (int e = tid; e < N; e += CE_WARPS * 32) {              // pass 2: sum of the corrections
+        uint32_t bits = c.nzmask[srow + e];
+        if (!bits) continue;
+        int idx = c.cand_off[srow + e];
+        const float bl = bias ? bias[e] : 0.f;
+        for (; bits; bits &= bits - 1, ++idx) {
+            const int qb = __ffs(bits) - 1;
+            const float M = sm_M[qb];
+            const float l = bl + (idx < c.cap ? zc[idx] : 0.f);
+            const float v = expf(l - M) - (bias ? expf(bl - M) : 0.f);
+            if (v != 0.f) atomicAdd(&sm_sum[cp][qb], v);
+        }
+    }
+    __syncthreads();
+    if (tid < 32) {
+        double Sd = 0.0;
+#pragma unroll
+        for (int i = 0; i < CE_COPIES; ++i) Sd += (double)sm_sum[i][tid];
+        if (bias) Sd += acc[1] * (double)expf(Mg - sm_M[tid]);
+        sm_S[tid] = (float)Sd;
+    }
+    __syncthreads();
+    const float M = sm_M[b], S = sm_S[b];
     const int h = s.lane_h[slot * RL_LANES + b];
     const int t = s.lane_t[slot * RL_LANES + b];
-    const size_t srow = (size_t)slot * N;
     float lsum = 0.f, tacc = 0.f, sb = 0.f;
     bool saw_t = false;
     const bool valid = h >= 0 && M != -INFINITY;
@@ -356,51 +402,44 @@ k_ce_cells(rl_graph g, rl_slots s, rl_cells c, rl_answers ans, float smoothing, 
 
 // Gc[cell] = scale * softmax * S_b / T'  (dense part of dloss/dlogit at the cells), and the bias gradient's
 // correction at the cells: what the cell's logit contributes beyond the rank-one term exp(bias - M_b) * coef.
-// After k_group_reduce: stats[.][3] = S_b / sum-exp / T'.
-__global__ void __launch_bounds__(WARPS_PER_BLOCK * 32)
+// After k_group_reduce: stats[.][3] = S_b / sum-exp / T'.  Threads own entities (one atomic per entity with cells).
+__global__ void __launch_bounds__(256)
 k_grad_cells(rl_graph g, rl_cells c, const float *__restrict__ bias, double *__restrict__ acc,
              const float *__restrict__ zc, const float *__restrict__ stats, float scale, float *__restrict__ Gc,
              float *__restrict__ grad_bias)
 {
-    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    __shared__ float sM[32], sC[32];
+    const int tid = threadIdx.x;
     const int slot = blockIdx.y;
-    const int N = g.num_entities, W = g.rank_words;
-    const float4 st = __ldg(reinterpret_cast<const float4 *>(stats) + (size_t)slot * 32 + lane);
-    const float coef = st.w * scale;
-    if (bias && blockIdx.x == 0 && warp == 0) {               // K = sum over queries of coef * exp(Mg - M_b)
-        double v = coef != 0.f ? (double)coef * (double)expf((float)acc[0] - st.x) : 0.0;
-        v = warp_sum(v);
-        if (lane == 0 && v != 0.0) atomicAdd(acc + 2, v);
-    }
-    const uint32_t lt = lanemask_lt();
-    for (int ew = blockIdx.x * WARPS_PER_BLOCK + warp; ew < W; ew += CELL_BLOCKS * WARPS_PER_BLOCK) {
-        const int e_lane = ew * 32 + lane;
-        const uint32_t my_bits = e_lane < N ? c.nzmask[(size_t)slot * N + e_lane] : 0u;
-        uint32_t present = __ballot_sync(FULL, my_bits != 0u);
-        if (!present) continue;
-        const int my_off = c.cand_off[(size_t)slot * N + min(e_lane, N - 1)];
-        const float bias_l = (bias && e_lane < N) ? bias[e_lane] : 0.f;
-        float my_corr = 0.f;                                   // lane i: correction of entity i of the word
-        for (; present; present &= present - 1) {
-            const int i = __ffs(present) - 1;
-            const uint32_t bits = __shfl_sync(FULL, my_bits, i);
-            const int off = __shfl_sync(FULL, my_off, i);
-            const float bl = __shfl_sync(FULL, bias_l, i);
-            float corr = 0.f;
-            if ((bits >> lane) & 1u) {
-                const int idx = off + __popc(bits & lt);
-                if (idx < c.cap) {
-                    const float gq = coef != 0.f ? expf(bl + zc[idx] - st.x) * coef : 0.f;
-                    Gc[idx] = gq;
-                    if (bias) corr = gq - (coef != 0.f ? expf(bl - st.x) * coef : 0.f);
-                }
-            }
-            if (bias) {
-                corr = warp_sumf(corr);
-                if (lane == i) my_corr = corr;
-            }
+    const int N = g.num_entities;
+    const size_t srow = (size_t)slot * N;
+    if (tid < 32) {
+        const float4 st = __ldg(reinterpret_cast<const float4 *>(stats) + (size_t)slot * 32 + tid);
+        const float coef = st.w * scale;
+        sM[tid] = st.x;
+        sC[tid] = coef;
+        if (bias && blockIdx.x == 0) {                          // K = sum over queries of coef * exp(Mg - M_b)
+            double v = coef != 0.f ? (double)coef * (double)expf((float)acc[0] - st.x) : 0.0;
+            v = warp_sum(v);
+            if (tid == 0 && v != 0.0) atomicAdd(acc + 2, v);
         }
-        if (bias && my_corr != 0.f) atomicAdd(grad_bias + e_lane, my_corr);
+    }
+    __syncthreads();
+    for (int e = blockIdx.x * 256 + tid; e < N; e += gridDim.x * 256) {
+        uint32_t bits = c.nzmask[srow + e];
+        if (!bits) continue;
+        int idx = c.cand_off[srow + e];
+        const float bl = bias ? bias[e] : 0.f;
+        float corr = 0.f;
+        for (; bits; bits &= bits - 1, ++idx) {
+            if (idx >= c.cap) break;
+            const int qb = __ffs(bits) - 1;
+            const float coef = sC[qb], M = sM[qb];
+            const float gq = coef != 0.f ? expf(bl + zc[idx] - M) * coef : 0.f;
+            Gc[idx] = gq;
+            if (bias && coef != 0.f) corr += gq - expf(bl - M) * coef;
+        }
+        if (bias && corr != 0.f) atomicAdd(grad_bias + e, corr);
     }
 }
 
@@ -519,6 +558,43 @@ k_pred_cells_bwd(rl_graph g, rl_rules r, rl_slots s, rl_frontier fr, rl_cells c,
             }
         }
     }
+}
+
+// The same backward from the coordinate list: one thread per non-zero count, no count row is read again.
+__global__ void __launch_bounds__(256)
+k_pred_nnz_bwd(rl_rules r, rl_frontier fr, rl_cells c, const float *__restrict__ Gc, float *__restrict__ grad_w)
+{
+    const int n = min(c.counters[2], c.nnz_cap);
+    const int4 *items = reinterpret_cast<const int4 *>(fr.items_sorted);
+    for (int p = blockIdx.x * 256 + threadIdx.x; p < n; p += gridDim.x * 256) {
+        const int cell = c.nz_cell[p];
+        if (cell >= c.cap) continue;
+        const float v = c.nz_val[p] * Gc[cell];
+        if (v == 0.f) continue;
+        const int4 it = __ldg(items + c.nz_item[p]);              // {row, first rule end, entity, rule ends}
+        for (int t = it.y; t < it.y + it.w; ++t) atomicAdd(grad_w + __ldg(r.node_term_rule + t), v);
+    }
+}
+
+// empty-body rules: count = one_hot(h) -> grad_w[rule] += sum over the slot's queries of Gc[cell(h_b, b)]
+__global__ void __launch_bounds__(32)
+k_pred_zr_bwd(rl_graph g, rl_rules r, rl_slots s, rl_cells c, const float *__restrict__ Gc, float *__restrict__ grad_w)
+{
+    const int lane = threadIdx.x, slot = blockIdx.x;
+    const int q = s.slot_head[slot];
+    const int z0 = r.zr_ptr[q], z1 = r.zr_ptr[q + 1];
+    if (z1 <= z0) return;
+    const size_t srow = (size_t)slot * g.num_entities;
+    const int h = s.lane_h[slot * RL_LANES + lane];
+    double v = 0.0;
+    if (h >= 0) {
+        const uint32_t bits = c.nzmask[srow + h];
+        const int idx = c.cand_off[srow + h] + __popc(bits & ((1u << lane) - 1u));
+        if (((bits >> lane) & 1u) && idx < c.cap) v = (double)Gc[idx];
+    }
+    v = warp_sum(v);
+    if (lane == 0 && v != 0.0)
+        for (int t = z0; t < z1; ++t) atomicAdd(grad_w + r.zr_rule[t], (float)v);
 }
 
 // ------------------------------------------------------------------------------------------
@@ -668,7 +744,9 @@ int rl_cells_build(const rl_graph *g, const rl_rules *r, const rl_slots *s, cons
     if (s->num_slots <= 0) return RL_OK;
     const int rc = rl_sort_items(g, s, fr, stream);               // groups items by entity, ORs their lane masks into nzmask
     if (rc != RL_OK) return rc;
-    k_cell_scan<<<s->num_slots, 512, 0, (cudaStream_t)stream>>>(*g, *r, *s, *c);
+    if (c->nnz_cap > 0 && (!c->nnz_off || !c->nz_val || !c->nz_cell || !c->nz_item))
+        return rl_fail(RL_ERR_ARG, "rl_cells_build: nnz_cap > 0 needs the coordinate arrays");
+    k_cell_scan<<<s->num_slots, 512, 0, (cudaStream_t)stream>>>(*g, *r, *s, *fr, *c);
     CHECK_LAUNCH("k_cell_scan");
     return RL_OK;
 }
@@ -710,9 +788,7 @@ int rl_cells_softmax_ce(const rl_graph *g, const rl_slots *s, const rl_cells *c,
     if (n_groups <= 0 || n_groups > S || (!group_ptr && n_groups != S)) return rl_fail(RL_ERR_ARG, "rl_cells_softmax_ce: bad group table");
     cudaStream_t st = (cudaStream_t)stream;
     float *slot_lsum = slot_sums, *slot_tsum = slot_sums + S, *slot_invT = slot_sums + 2 * (size_t)S;
-    k_cell_stats<<<dim3(CELL_BLOCKS, S), WARPS_PER_BLOCK * 32, 0, st>>>(*g, *c, bias, acc, zc, partial);
-    CHECK_LAUNCH("k_cell_stats");
-    k_ce_cells<<<S, CE_WARPS * 32, 0, st>>>(*g, *s, *c, *ans, smoothing, bias, acc, zc, partial, stats, slot_lsum, slot_tsum);
+    k_ce_cells<<<S, CE_WARPS * 32, 0, st>>>(*g, *s, *c, *ans, smoothing, bias, acc, zc, stats, slot_lsum, slot_tsum);
     CHECK_LAUNCH("k_ce_cells");
     k_group_reduce<<<n_groups, 32, 0, st>>>(n_groups, group_ptr, slot_lsum, slot_tsum, group_loss, group_tsum, slot_invT, stats);
     CHECK_LAUNCH("k_group_reduce");
@@ -721,7 +797,7 @@ int rl_cells_softmax_ce(const rl_graph *g, const rl_slots *s, const rl_cells *c,
         cudaError_t e = cudaMemsetAsync(acc + 2, 0, sizeof(double), st);
         if (e != cudaSuccess) return rl_fail(RL_ERR_CUDA, "rl_cells_softmax_ce: memset", e);
     }
-    k_grad_cells<<<dim3(CELL_BLOCKS, S), WARPS_PER_BLOCK * 32, 0, st>>>(*g, *c, bias, acc, zc, stats, grad_scale, Gc, grad_bias);
+    k_grad_cells<<<dim3(CELL_BLOCKS, S), 256, 0, st>>>(*g, *c, bias, acc, zc, stats, grad_scale, Gc, grad_bias);
     CHECK_LAUNCH("k_grad_cells");
     k_grad_targets<<<S, CE_WARPS * 32, 0, st>>>(*g, *s, *c, *ans, smoothing, bias, zc, stats, slot_invT, grad_scale, Gc,
                                                  bias ? grad_bias : nullptr);
@@ -743,6 +819,20 @@ int rl_predictor_cell_backward(const rl_graph *g, const rl_rules *r, const rl_sl
     if (fr->count_bits == 32) k_pred_cells_bwd<uint32_t><<<grid, WARPS_PER_BLOCK * 32, 0, st>>>(*g, *r, *s, *fr, *c, Gc, grad_w);
     else k_pred_cells_bwd<unsigned long long><<<grid, WARPS_PER_BLOCK * 32, 0, st>>>(*g, *r, *s, *fr, *c, Gc, grad_w);
     CHECK_LAUNCH("k_pred_cells_bwd");
+    return RL_OK;
+}
+
+int rl_predictor_nnz_backward(const rl_graph *g, const rl_rules *r, const rl_slots *s, const rl_frontier *fr,
+                              const rl_cells *c, const float *Gc, float *grad_w, void *stream)
+{
+    if (!g || !r || !s || !Gc || !grad_w || bad_cells(c) || bad_item_frontier(fr)) return rl_fail(RL_ERR_ARG, "rl_predictor_nnz_backward: bad argument");
+    if (c->nnz_cap <= 0 || !c->nz_val || !c->nz_cell || !c->nz_item) return rl_fail(RL_ERR_ARG, "rl_predictor_nnz_backward: no coordinate list");
+    if (s->num_slots <= 0) return RL_OK;
+    cudaStream_t st = (cudaStream_t)stream;
+    k_pred_nnz_bwd<<<148 * 8, 256, 0, st>>>(*r, *fr, *c, Gc, grad_w);
+    CHECK_LAUNCH("k_pred_nnz_bwd");
+    k_pred_zr_bwd<<<s->num_slots, 32, 0, st>>>(*g, *r, *s, *c, Gc, grad_w);
+    CHECK_LAUNCH("k_pred_zr_bwd");
     return RL_OK;
 }
 

@@ -132,7 +132,9 @@ class Grounder:
         self._ws_items = None
         self._ws_cells = None
         self._ws_cells_cap = 0
+        self._ws_nnz = None
         self.cell_cap = 0
+        self.nnz_cap = 0
         self.level_events = None      # bench.py: list collecting (depth, start, end) CUDA events
 
     @staticmethod
@@ -207,7 +209,8 @@ class Grounder:
             # scratch: items | items_sorted (int32x4 records, exact upper bound) | bucket offsets | item lane masks (x2) |
             # first cell per (slot, entity) | cells per slot
             "n_items": 4 * cap, "o_boff": 8 * cap, "o_im": 8 * cap + n_bkt, "o_ims": 9 * cap + n_bkt,
-            "o_coff": 10 * cap + n_bkt, "o_ncell": 10 * cap + n_bkt + S * N, "scratch": 10 * cap + n_bkt + S * N + S,
+            "o_coff": 10 * cap + n_bkt, "o_ncell": 10 * cap + n_bkt + S * N, "o_nnzoff": 10 * cap + n_bkt + S * N + S,
+            "scratch": 11 * cap + n_bkt + S * N + S,
         }
 
     def _run(self, sl: Slots, bits: int):
@@ -243,7 +246,8 @@ class Grounder:
                                       sl.overflow.data_ptr(), sb, sb + 4 * lay["n_items"], sl.item_off.data_ptr(),
                                       base + 4 * lay["o_icnt"], base + 4 * lay["o_bkt"], sb + 4 * lay["o_boff"],
                                       sb + 4 * lay["o_im"], sb + 4 * lay["o_ims"], base + 4 * lay["o_nz"])
-        sl.cells_tables = (base + 4 * lay["o_ctr"], base + 4 * lay["o_nz"], sb + 4 * lay["o_coff"], sb + 4 * lay["o_ncell"])
+        sl.cells_tables = (base + 4 * lay["o_ctr"], base + 4 * lay["o_nz"], sb + 4 * lay["o_coff"], sb + 4 * lay["o_ncell"],
+                           sb + 4 * lay["o_nnzoff"])
         sl.cells = None
         L = _lib.lib()
         lc = self.cr.level_chunks[sl.heads]                               # [S, max_len]
@@ -267,7 +271,7 @@ class Grounder:
 
     def cell_arrays(self, sl: Slots, floats_per_cell: int):
         """Grow-only per-cell workspace: int32 keys [cap] + ``floats_per_cell`` fp32 planes [cap] each."""
-        want = max(self.cell_cap, self.cells_per_slot_hint * sl.S)
+        want = (max(self.cell_cap, self.cells_per_slot_hint * sl.S) + 63) // 64 * 64       # planes stay 16-byte aligned
         n = want * (1 + floats_per_cell)
         if self._ws_cells is None or self._ws_cells.numel() < n or self._ws_cells_cap < want:
             self._ws_cells = None
@@ -277,19 +281,30 @@ class Grounder:
         planes = [self._ws_cells[(1 + i) * cap:(2 + i) * cap] for i in range(floats_per_cell)]
         return cap, self._ws_cells[:cap].view(torch.int32), planes
 
-    def build_cells(self, sl: Slots, floats_per_cell: int):
-        """rl_cells_build for an expanded frontier -> (RlCells, fp32 planes [cap] each)."""
+    def build_cells(self, sl: Slots, floats_per_cell: int, coo: bool = False):
+        """rl_cells_build for an expanded frontier -> (RlCells, fp32 planes [cap] each).  coo: also reserve the
+        coordinate list of the non-zero counts (value, cell, item) that rl_predictor_cell_scores fills."""
         cap, keys, planes = self.cell_arrays(sl, floats_per_cell)
-        ctr, nz, coff, ncell = sl.cells_tables
-        sl.cells = _lib.RlCells(cap, ctr, nz, coff, keys.data_ptr(), ncell)
+        ctr, nz, coff, ncell, nnzoff = sl.cells_tables
+        nnz_cap, nzp = 0, (None, None, None)
+        if coo:
+            nnz_cap = (max(self.nnz_cap, 2 * cap) + 63) // 64 * 64
+            if self._ws_nnz is None or self._ws_nnz.numel() < 3 * nnz_cap:
+                self._ws_nnz = None
+                self._ws_nnz = torch.empty(3 * nnz_cap, dtype=torch.int32, device=self.device)
+            nnz_cap = self._ws_nnz.numel() // 3
+            b0 = self._ws_nnz.data_ptr()
+            nzp = (b0, b0 + 4 * nnz_cap, b0 + 8 * nnz_cap)
+        sl.cells = _lib.RlCells(cap, ctr, nz, coff, keys.data_ptr(), ncell, nnz_cap, nnzoff, nzp[0], nzp[1], nzp[2])
         sl.cell_cap = cap
         _lib.check(_lib.lib().rl_cells_build(self.dg.ref(), self.dr.ref(), sl.ref(), sl.fref(), C.byref(sl.cells), _stream()),
                    "rl_cells_build")
         return sl.cells, planes
 
-    def note_cell_count(self, n_cells: int):
-        """Remember the largest cell count seen so that later calls size their arrays for it (x1.25)."""
+    def note_cell_count(self, n_cells: int, n_nnz: int = 0):
+        """Remember the largest cell / non-zero counts seen so that later calls size their arrays for them (x1.25)."""
         self.cell_cap = max(self.cell_cap, int(n_cells * 1.25) + 1024)
+        self.nnz_cap = max(self.nnz_cap, int(n_nnz * 1.25) + 1024)
 
     def reserve(self, slots_list):
         """Size the reusable frontier workspace for the largest of the given calls up front, so that no

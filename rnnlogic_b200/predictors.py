@@ -275,13 +275,13 @@ class _StepTicket:
         host, ng, S = self.pinned, self.ng, self.sl.S
         flags = host[2 * ng + S:]
         self.total_cells = int(flags[0].item())
-        self.sk.gr.note_cell_count(self.total_cells)
+        self.sk.gr.note_cell_count(self.total_cells, int(flags[2].item()))
         if flags[8].item() != 0:
             raise RlStepOverflow("a path count overflowed 32 bits inside an enqueued step; redo it with "
                                  "model.fused_train_step (exact 64-bit rows)")
-        if flags[1].item() != 0:
-            raise RlStepOverflow("the step has %d candidate cells, more than its arrays hold; redo it with "
-                                 "model.fused_train_step (the arrays grow)" % self.total_cells)
+        if flags[1].item() != 0 or flags[3].item() != 0:
+            raise RlStepOverflow("the step has %d candidate cells / %d non-zero counts, more than its arrays hold; redo it "
+                                 "with model.fused_train_step (the arrays grow)" % (self.total_cells, int(flags[2].item())))
         ncell = host[2 * ng:2 * ng + S].numpy()
         gslots = [(n + LANES - 1) // LANES for n in self.sl.group_sizes]
         self.mask_sum = np.add.reduceat(ncell, np.concatenate([[0], np.cumsum(gslots)[:-1]])).tolist() if S else []
@@ -679,7 +679,8 @@ class PredictorPlus(_RuleModel):
         key = "d" + str(device)
         t = self._scratch.get(key)
         if t is None:
-            t = self._scratch[key] = torch.empty(self.num_relations * 128, dtype=torch.float32, device=device)
+            n = int(_lib.lib().rl_tail_scratch_floats(self.num_relations))
+            t = self._scratch[key] = torch.empty(n, dtype=torch.float32, device=device)
         return t
 
     def encode_rules(self, rule_features):
