@@ -71,7 +71,7 @@ typedef struct rl_graph {
  * the chunk range of depth d+1 of head q.  node_term_* lists the rules ending at each node; zr_* the
  * rules with an empty body. */
 typedef struct rl_rules {
-    int32_t num_nodes, num_rules, max_len, num_chunks, num_terms;
+    int32_t num_nodes, num_rules, max_len, num_chunks, num_terms, num_zero_rules;
     const int32_t *node_rel;      /* [num_nodes] */
     const int64_t *node_row_off;  /* [num_nodes] */
     const int32_t *head_node_ptr; /* [R+1] */
@@ -134,7 +134,9 @@ typedef struct rl_frontier {
     /* Lane mask of every item (bit b: the count of query b in that row is non-zero), written by k_numeric
      * next to the item and carried through the sort.  The OR of an entity's item masks is its candidate
      * word nzmask[slot][entity] (predictors.py:224-225,239: a cell is a candidate iff its total count is
-     * non-zero); rl_sort_items accumulates it when nzmask != NULL ([S][N], zeroed by the caller). */
+     * non-zero).  nzmask ([S][N], zeroed by the caller) is accumulated by k_numeric itself when the frontier has
+     * no sort buffers (bucket_cnt == NULL: the cell kernels walk the items in the order they were appended),
+     * else by rl_sort_items. */
     uint32_t *item_mask;
     uint32_t *item_mask_sorted;
     uint32_t *nzmask;
@@ -162,17 +164,10 @@ typedef struct rl_cells {
     uint32_t *nzmask;     /* [S][N] candidate word per entity (= rl_frontier.nzmask) */
     int32_t *cand_off;    /* [S][N] first cell of the entity */
     int32_t *cell_key;    /* [cap] slot*32 + lane of the cell */
+    int32_t *cell_ent;    /* [cap] entity of the cell */
     int32_t *slot_ncell;  /* [S] cells per slot (= mask.sum() of the batch without an entity feature, trainer.py:96) */
-    /* Non-zero (rule end, query, entity) counts of the call in coordinate form (optional: nnz_cap == 0 switches it
-     * off).  nnz_off[i] = first non-zero of the i-th entity-grouped item (rl_cells_build: prefix of the items' lane
-     * mask populations); rl_predictor_cell_scores fills nz_val (fp32(count), predictors.py:64), nz_cell (its cell)
-     * and nz_item (its item) while it reads the count rows, so the backward never touches them again.
-     * counters[2] = number of non-zeros, counters[3] != 0: nnz_cap exceeded. */
-    int32_t nnz_cap;
-    int32_t *nnz_off;     /* [item capacity of the call] */
-    float *nz_val;        /* [nnz_cap] */
-    int32_t *nz_cell;     /* [nnz_cap] */
-    int32_t *nz_item;     /* [nnz_cap] index into items_sorted (global) */
+    uint32_t *qmax;       /* [S*32] scratch: per-query max of the cell logits (order-preserving key) */
+    float *qsum;          /* [S*32] scratch: per-query sum of the softmax corrections */
 } rl_cells;
 
 int rl_abi_version(void);
@@ -400,9 +395,9 @@ int rl_mask_to_dense(int32_t N, int32_t nq, const uint32_t *nzmask_slot, uint8_t
 
 /* ---- the scoring half on candidate cells (rl_cells.cu, rl_tail2.cu): no [S][N][32] matrix ---- */
 
-/* Group the frontier's items by entity (rl_sort_items, which also ORs the items' lane masks into nzmask) and
- * number the cells: cand_off, cell_key, slot_ncell, counters[0..1].  Replaces torch.nonzero(mask)
- * (src/predictors.py:239) without a host sync. */
+/* Number the cells: cand_off, cell_key, cell_ent, slot_ncell, counters[0..1] from the candidate words nzmask.  When
+ * the frontier carries sort buffers the items are grouped by entity first (rl_sort_items, which ORs their lane
+ * masks into nzmask).  Replaces torch.nonzero(mask) (src/predictors.py:239) without a host sync. */
 int rl_cells_build(const rl_graph *g, const rl_rules *r, const rl_slots *s, const rl_frontier *fr,
                    const rl_cells *c, void *stream);
 
@@ -410,31 +405,33 @@ int rl_cells_build(const rl_graph *g, const rl_rules *r, const rl_slots *s, cons
  * rl_cells_softmax_ce.  Once per parameter update. */
 int rl_bias_stats(int32_t N, const float *bias, double *acc, void *stream);
 
-/* Predictor (src/predictors.py:58-65): zc[cell] = sum_rule w_rule * fp32(count), without the bias. */
+/* Predictor (src/predictors.py:58-65): zc[cell] = sum_rule w_rule * fp32(count), without the bias.
+ * _item_: one THREAD per item (non-zero row of a rule-end node) in the order k_numeric appended them: it reads the
+ *         counts of the queries in the item's lane mask and adds w * fp32(count) to their cells (zc[cap] is cleared
+ *         first); no sort, no per-warp walk of ragged lists;
+ * _cell_: one warp per 32 entities over the entity-grouped items (frontier with sort buffers; deterministic sums). */
+int rl_predictor_item_scores(const rl_graph *g, const rl_rules *r, const rl_slots *s, const rl_frontier *fr,
+                            const rl_cells *c, const float *w, float *zc, void *stream);
 int rl_predictor_cell_scores(const rl_graph *g, const rl_rules *r, const rl_slots *s, const rl_frontier *fr,
                              const rl_cells *c, const float *w, float *zc, void *stream);
-
-/* Floats of `partial` scratch per slot for rl_cells_softmax_ce. */
-int rl_cells_partial_floats(void);
 
 /* log(softmax + 1e-8) cross-entropy against the smoothed multi-hot target (src/trainer.py:84,88-89) with the
  * logits given as cell scores zc plus bias[e] for EVERY entity (bias != NULL; predictors.py:257-262), or as
  * the cell scores alone with -inf elsewhere (bias == NULL; predictors.py:267-269).  Same outputs as
- * rl_softmax_ce (group_loss, group_tsum; stats [S][32][4], slot_sums [3*S], partial
- * [S*rl_cells_partial_floats()] are scratch).  Gc != NULL: Gc[cell] = grad_scale * dloss/dlogit and, with a
- * bias, grad_bias[N] += grad_scale * dloss/dbias (rank-one term + cell and target corrections). */
+ * rl_softmax_ce (group_loss, group_tsum; stats [S][32][4] and slot_sums [3*S] are scratch).  Gc != NULL:
+ * Gc[cell] = grad_scale * dloss/dlogit and, with a bias, grad_bias[N] += grad_scale * dloss/dbias
+ * (rank-one term + cell and target corrections). */
 int rl_cells_softmax_ce(const rl_graph *g, const rl_slots *s, const rl_cells *c, const rl_answers *ans,
                         float smoothing, const float *bias, double *acc, const float *zc, int32_t n_groups,
-                        const int32_t *group_ptr, float grad_scale, float *partial, float *stats,
-                        float *slot_sums, float *group_loss, float *group_tsum, float *Gc, float *grad_bias,
-                        void *stream);
+                        const int32_t *group_ptr, float grad_scale, float *stats, float *slot_sums,
+                        float *group_loss, float *group_tsum, float *Gc, float *grad_bias, void *stream);
 
-/* Predictor backward: grad_w[rule] += sum over the rule's non-zero rows of <Gc[cells], fp32(counts)>. */
+/* Predictor backward: grad_w[rule] += sum over the rule's non-zero counts of Gc[cell] * fp32(count) (one atomic per
+ * item and rule). */
+int rl_predictor_item_backward(const rl_graph *g, const rl_rules *r, const rl_slots *s, const rl_frontier *fr,
+                              const rl_cells *c, const float *Gc, float *grad_w, void *stream);
 int rl_predictor_cell_backward(const rl_graph *g, const rl_rules *r, const rl_slots *s, const rl_frontier *fr,
                                const rl_cells *c, const float *Gc, float *grad_w, void *stream);
-/* The same from the coordinate list rl_predictor_cell_scores left (c->nnz_cap > 0): one thread per non-zero. */
-int rl_predictor_nnz_backward(const rl_graph *g, const rl_rules *r, const rl_slots *s, const rl_frontier *fr,
-                              const rl_cells *c, const float *Gc, float *grad_w, void *stream);
 
 /* Filtered rank (src/trainer.py:189-201) from cell scores: (L,H) int64[S*32][2].  With a bias the entities
  * outside a query's cells are counted by binary search in sorted_bias (bias sorted ascending);
@@ -448,12 +445,18 @@ int rl_cells_add_to_dense(const rl_graph *g, const rl_slots *s, const rl_cells *
 int rl_cells_gather_dense(const rl_graph *g, const rl_slots *s, const rl_cells *c, const float *G, float *Gc, void *stream);
 
 /* PredictorPlus aggregates per cell (src/layers.py:68-72 / 92-99), hidden_dim 16, emb[num_rules][16] indexed by
- * the global rule id: out_sum[cell][16]; PNA also out_sq, out_min, out_max, arg_min, arg_max, degree[cell]. */
+ * the global rule id.  _item_: F[cell][16] = sum fp32(count) * emb[rule], one thread per (item, quarter of the
+ * hidden vector), 16-byte vector atomics (F[cap][16] is cleared first).  _cell_: from the entity-grouped items (also the PNA statistics
+ * out_sq, out_min, out_max, arg_min, arg_max, degree[cell]). */
+int rl_plus_item_features(const rl_graph *g, const rl_rules *r, const rl_slots *s, const rl_frontier *fr,
+                         const rl_cells *c, const float *emb, int32_t H, float *F, void *stream);
 int rl_plus_cell_features(const rl_graph *g, const rl_rules *r, const rl_slots *s, const rl_frontier *fr,
                           const rl_cells *c, const float *emb, int32_t H, int32_t pna, float *out_sum, float *out_sq,
                           float *out_min, float *out_max, int32_t *arg_min, int32_t *arg_max, float *degree, void *stream);
 
-/* grad_emb[rule][16] += sum over the rule's non-zero (row, query) pairs of fp32(count) * dF[cell][16]. */
+/* grad_emb[rule][16] += sum over the rule's non-zero counts of fp32(count) * dF[cell][16]. */
+int rl_plus_item_backward(const rl_graph *g, const rl_rules *r, const rl_slots *s, const rl_frontier *fr,
+                         const rl_cells *c, int32_t H, const float *dF, float *grad_emb, void *stream);
 int rl_plus_cell_backward(const rl_graph *g, const rl_rules *r, const rl_slots *s, const rl_frontier *fr,
                           const rl_cells *c, int32_t H, const float *dF, float *grad_emb, void *stream);
 

@@ -29,7 +29,7 @@ class RlGraph(C.Structure):
 
 class RlRules(C.Structure):
     _fields_ = [("num_nodes", C.c_int32), ("num_rules", C.c_int32), ("max_len", C.c_int32),
-                ("num_chunks", C.c_int32), ("num_terms", C.c_int32),
+                ("num_chunks", C.c_int32), ("num_terms", C.c_int32), ("num_zero_rules", C.c_int32),
                 ("node_rel", vp), ("node_row_off", vp), ("head_node_ptr", vp),
                 ("lvl_ptr", vp), ("chunk_node", vp), ("chunk_row0", vp), ("zr_ptr", vp), ("zr_rule", vp),
                 ("node_chunk0", vp), ("node_rec", vp), ("node_prow_off", vp),
@@ -50,8 +50,7 @@ class RlFrontier(C.Structure):
 
 class RlCells(C.Structure):
     _fields_ = [("cap", C.c_int32), ("counters", vp), ("nzmask", vp), ("cand_off", vp), ("cell_key", vp),
-                ("slot_ncell", vp), ("nnz_cap", C.c_int32), ("nnz_off", vp), ("nz_val", vp), ("nz_cell", vp),
-                ("nz_item", vp)]
+                ("cell_ent", vp), ("slot_ncell", vp), ("qmax", vp), ("qsum", vp)]
 
 
 class RlAnswers(C.Structure):
@@ -156,12 +155,17 @@ _PROTOS = {
     "rl_bias_stats": (C.c_int, [C.c_int32, vp, vp, vp]),
     "rl_predictor_cell_scores": (C.c_int, [C.POINTER(RlGraph), C.POINTER(RlRules), C.POINTER(RlSlots),
                                            C.POINTER(RlFrontier), C.POINTER(RlCells), vp, vp, vp]),
-    "rl_cells_partial_floats": (C.c_int, []),
+    "rl_predictor_item_scores": (C.c_int, [C.POINTER(RlGraph), C.POINTER(RlRules), C.POINTER(RlSlots),
+                                          C.POINTER(RlFrontier), C.POINTER(RlCells), vp, vp, vp]),
     "rl_cells_softmax_ce": (C.c_int, [C.POINTER(RlGraph), C.POINTER(RlSlots), C.POINTER(RlCells), C.POINTER(RlAnswers),
-                                      C.c_float, vp, vp, vp, C.c_int32, vp, C.c_float, vp, vp, vp, vp, vp, vp, vp, vp]),
+                                      C.c_float, vp, vp, vp, C.c_int32, vp, C.c_float, vp, vp, vp, vp, vp, vp, vp]),
+    "rl_plus_item_features": (C.c_int, [C.POINTER(RlGraph), C.POINTER(RlRules), C.POINTER(RlSlots), C.POINTER(RlFrontier),
+                                       C.POINTER(RlCells), vp, C.c_int32, vp, vp]),
+    "rl_plus_item_backward": (C.c_int, [C.POINTER(RlGraph), C.POINTER(RlRules), C.POINTER(RlSlots), C.POINTER(RlFrontier),
+                                       C.POINTER(RlCells), C.c_int32, vp, vp, vp]),
     "rl_predictor_cell_backward": (C.c_int, [C.POINTER(RlGraph), C.POINTER(RlRules), C.POINTER(RlSlots),
                                              C.POINTER(RlFrontier), C.POINTER(RlCells), vp, vp, vp]),
-    "rl_predictor_nnz_backward": (C.c_int, [C.POINTER(RlGraph), C.POINTER(RlRules), C.POINTER(RlSlots),
+    "rl_predictor_item_backward": (C.c_int, [C.POINTER(RlGraph), C.POINTER(RlRules), C.POINTER(RlSlots),
                                             C.POINTER(RlFrontier), C.POINTER(RlCells), vp, vp, vp]),
     "rl_cells_rank": (C.c_int, [C.POINTER(RlGraph), C.POINTER(RlSlots), C.POINTER(RlCells), C.POINTER(RlAnswers),
                                 vp, vp, vp, vp, vp, vp]),

@@ -54,38 +54,32 @@ class CellKernels:
         self.gr, self.dg, self.dr = sk.gr, sk.dg, sk.dr
         self.N, self.device = sk.N, sk.device
         self.acc = torch.zeros(4, dtype=torch.float64, device=self.device)       # Mg, Sg, K
-        self.pf = _L().rl_cells_partial_floats()
-        self._bias_version = None
 
     def bias_stats(self, bias: torch.Tensor):
         _lib.check(_L().rl_bias_stats(self.N, bias.data_ptr(), self.acc.data_ptr(), _stream()), "rl_bias_stats")
 
     def predictor_scores(self, sl, w, zc):
-        _lib.check(_L().rl_predictor_cell_scores(self.dg.ref(), self.dr.ref(), sl.ref(), sl.fref(), C.byref(sl.cells),
-                                                 w.data_ptr(), zc.data_ptr(), _stream()), "rl_predictor_cell_scores")
+        _lib.check(_L().rl_predictor_item_scores(self.dg.ref(), self.dr.ref(), sl.ref(), sl.fref(), C.byref(sl.cells),
+                                                w.data_ptr(), zc.data_ptr(), _stream()), "rl_predictor_item_scores")
 
     def softmax_ce(self, sl, bias, zc, smoothing, group_ptr, n_groups, grad_scale, Gc, grad_bias):
         """-> (group_loss, group_tsum) device tensors; Gc / grad_bias filled when Gc is given."""
         dev, S = self.device, sl.S
-        scr = torch.empty(S * (self.pf + LANES * 4 + 3) + 2 * n_groups, dtype=torch.float32, device=dev)
-        partial, stats = scr[:S * self.pf], scr[S * self.pf:S * (self.pf + LANES * 4)]
-        slot_sums = scr[S * (self.pf + LANES * 4):S * (self.pf + LANES * 4 + 3)]
-        out = scr[S * (self.pf + LANES * 4 + 3):].view(2, n_groups)
+        scr = torch.empty(S * (LANES * 4 + 3) + 2 * n_groups, dtype=torch.float32, device=dev)
+        stats = scr[:S * LANES * 4]
+        slot_sums = scr[S * LANES * 4:S * (LANES * 4 + 3)]
+        out = scr[S * (LANES * 4 + 3):].view(2, n_groups)
         ans, _keep = self.dg.answers["hr2o"]
         _lib.check(_L().rl_cells_softmax_ce(
             self.dg.ref(), sl.ref(), C.byref(sl.cells), C.byref(ans), float(smoothing), _ptr(bias), self.acc.data_ptr(),
-            zc.data_ptr(), int(n_groups), _ptr(group_ptr), float(grad_scale), partial.data_ptr(), stats.data_ptr(),
+            zc.data_ptr(), int(n_groups), _ptr(group_ptr), float(grad_scale), stats.data_ptr(),
             slot_sums.data_ptr(), out[0].data_ptr(), out[1].data_ptr(), _ptr(Gc), _ptr(grad_bias), _stream()),
             "rl_cells_softmax_ce")
         return out[0], out[1]
 
     def predictor_backward(self, sl, Gc, grad_w):
-        _lib.check(_L().rl_predictor_cell_backward(self.dg.ref(), self.dr.ref(), sl.ref(), sl.fref(), C.byref(sl.cells),
-                                                   Gc.data_ptr(), grad_w.data_ptr(), _stream()), "rl_predictor_cell_backward")
-
-    def predictor_nnz_backward(self, sl, Gc, grad_w):
-        _lib.check(_L().rl_predictor_nnz_backward(self.dg.ref(), self.dr.ref(), sl.ref(), sl.fref(), C.byref(sl.cells),
-                                                  Gc.data_ptr(), grad_w.data_ptr(), _stream()), "rl_predictor_nnz_backward")
+        _lib.check(_L().rl_predictor_item_backward(self.dg.ref(), self.dr.ref(), sl.ref(), sl.fref(), C.byref(sl.cells),
+                                                  Gc.data_ptr(), grad_w.data_ptr(), _stream()), "rl_predictor_item_backward")
 
     def rank(self, sl, bias, sorted_bias, zc, which):
         counters = torch.empty(sl.S * 64, dtype=torch.int32, device=self.device)
@@ -105,13 +99,12 @@ class CellKernels:
                                               _stream()), "rl_cells_gather_dense")
 
     def plus_features(self, sl, emb, F):
-        _lib.check(_L().rl_plus_cell_features(self.dg.ref(), self.dr.ref(), sl.ref(), sl.fref(), C.byref(sl.cells),
-                                              emb.data_ptr(), 16, 0, F.data_ptr(), None, None, None, None, None, None,
-                                              _stream()), "rl_plus_cell_features")
+        _lib.check(_L().rl_plus_item_features(self.dg.ref(), self.dr.ref(), sl.ref(), sl.fref(), C.byref(sl.cells),
+                                             emb.data_ptr(), 16, F.data_ptr(), _stream()), "rl_plus_item_features")
 
     def plus_backward(self, sl, dF, grad_emb):
-        _lib.check(_L().rl_plus_cell_backward(self.dg.ref(), self.dr.ref(), sl.ref(), sl.fref(), C.byref(sl.cells), 16,
-                                              dF.data_ptr(), grad_emb.data_ptr(), _stream()), "rl_plus_cell_backward")
+        _lib.check(_L().rl_plus_item_backward(self.dg.ref(), self.dr.ref(), sl.ref(), sl.fref(), C.byref(sl.cells), 16,
+                                             dF.data_ptr(), grad_emb.data_ptr(), _stream()), "rl_plus_item_backward")
 
     def tail_forward(self, sl, F, wts, zc, O, bits):
         _lib.check(_L().rl_tail_forward(C.byref(sl.cells), sl.slot_head.data_ptr(), 16, 128, F.data_ptr(),
@@ -141,13 +134,13 @@ def predictor_step(model, sk, sl, smoothing, grad_scale, gw, gb, expanded=False,
     ck = cell_kernels(sk)
     if not expanded:
         sk.gr._run(sl, bits)
-    _, (zc, Gc) = sk.gr.build_cells(sl, 2, coo=True)
+    _, (zc, Gc) = sk.gr.build_cells(sl, 2)
     bias = model.bias.detach() if model.entity_feature == "bias" else None
     if bias is not None:
         ck.bias_stats(bias)
     ck.predictor_scores(sl, model.rule_weights.detach(), zc)          # also leaves the non-zero counts in coordinate form
     loss, tsum = ck.softmax_ce(sl, bias, zc, smoothing, sl.group_ptr_dev, len(sl.group_sizes), grad_scale, Gc, gb)
-    ck.predictor_nnz_backward(sl, Gc, gw)
+    ck.predictor_backward(sl, Gc, gw)
     return loss, tsum
 
 
@@ -180,7 +173,7 @@ PLUS_PLANES = 2 + 4 * 16 + 4          # zc, Gc | F, dF, O, dY [16 each] | ReLU b
 def _plus_planes(gr):
     """Per-cell arrays of the PredictorPlus step inside the grounder's cell workspace (contiguous [cap][16] blocks)."""
     cap, ws = gr._ws_cells_cap, gr._ws_cells
-    blk = lambda i0, n: ws[(1 + i0) * cap:(1 + i0 + n) * cap]
+    blk = lambda i0, n: ws[(2 + i0) * cap:(2 + i0 + n) * cap]          # plane 0: cell keys, plane 1: cell entities
     return {"zc": blk(0, 1), "Gc": blk(1, 1), "F": blk(2, 16), "dF": blk(18, 16), "O": blk(34, 16), "dY": blk(50, 16),
             "bits": blk(66, 4)}
 
@@ -281,7 +274,7 @@ def sl_dummy_mask(sl, sk):
 
 class _NzView:
     def __init__(self, sl):
-        self._p = sl.cells_tables[1]
+        self._p = sl.cells_tables["nzmask"]
 
     def data_ptr(self):
         return self._p

@@ -291,7 +291,8 @@ __device__ __forceinline__ uint32_t numeric_rows(const rl_graph &g, const rl_rul
                 const long long pos = fr.item_off[slot] + base + __popc(nzrows & ((1u << lane) - 1u));
                 reinterpret_cast<int4 *>(fr.items)[pos] = make_int4((int)(r.node_row_off[v] + myrow), term0, my_dst, nterm);
                 if (fr.item_mask) fr.item_mask[pos] = my_lanes;
-                atomicAdd(fr.bucket_cnt + (size_t)slot * RL_BUCKET_STRIDE(g.rank_words) + my_dst, 1);
+                if (fr.bucket_cnt) atomicAdd(fr.bucket_cnt + (size_t)slot * RL_BUCKET_STRIDE(g.rank_words) + my_dst, 1);
+                else if (fr.nzmask && my_lanes) atomicOr(fr.nzmask + (size_t)slot * g.num_entities + my_dst, my_lanes);
             }
         }
     }
@@ -356,7 +357,7 @@ k_numeric(rl_graph g, rl_rules r, rl_slots s, int depth, rl_frontier fr, int cpw
             if (lane == 0 && nz) atomicAdd(fr.node_cnt + nzb + v, __popc(nz));
         }
     }
-    if (__any_sync(FULL, ovf) && lane == 0) *fr.overflow = 1;
+    if (__any_sync(FULL, ovf) && lane == 0) fr.overflow[0] = 1;
 }
 
 // One hop from an ARBITRARY dense frontier (KnowledgeGraph.propagate, src/data.py:149-173):

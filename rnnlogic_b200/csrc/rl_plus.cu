@@ -488,6 +488,119 @@ k_plus_cells_bwd(rl_graph g, rl_rules r, rl_slots s, rl_frontier fr, rl_cells c,
     }
 }
 
+// ---- PredictorPlus on the item list as k_numeric appended it: one thread per (item, quarter of the hidden vector) ----
+#define PN_BLOCKS 16
+// F[cell][16] += fp32(count) * emb[rule][16] (layers.py:68-72) with 16-byte vector atomics
+template <typename CT>
+__global__ void __launch_bounds__(256)
+k_plus_item_features(rl_graph g, rl_rules r, rl_slots s, rl_frontier fr, rl_cells c, const float *__restrict__ emb,
+                     float *__restrict__ F)
+{
+    const int slot = blockIdx.y;
+    const int n = fr.item_cnt[slot];
+    const long long ib = fr.item_off[slot];
+    const int4 *items = reinterpret_cast<const int4 *>(fr.items) + ib;
+    const uint32_t *masks = fr.item_mask + ib;
+    const CT *arena = reinterpret_cast<const CT *>(fr.arena) + (size_t)s.arena_off[slot] * RL_LANES;
+    const size_t srow = (size_t)slot * g.num_entities;
+    const int part = threadIdx.x & 3;
+    for (int i = (blockIdx.x * 256 + threadIdx.x) >> 2; i < n; i += PN_BLOCKS * 64) {
+        uint32_t m = __ldg(masks + i);
+        if (!m) continue;
+        const int4 it = __ldg(items + i);                         // {row, first rule end, entity, rule ends}
+        float4 e4 = __ldg(reinterpret_cast<const float4 *>(emb + (size_t)__ldg(r.node_term_rule + it.y) * CH) + part);
+        for (int t = it.y + 1; t < it.y + it.w; ++t) {            // duplicate rules: their embeddings add up
+            const float4 x = __ldg(reinterpret_cast<const float4 *>(emb + (size_t)__ldg(r.node_term_rule + t) * CH) + part);
+            e4.x += x.x; e4.y += x.y; e4.z += x.z; e4.w += x.w;
+        }
+        const uint32_t bits = c.nzmask[srow + it.z];
+        const int off = c.cand_off[srow + it.z];
+        const CT *row = arena + (size_t)it.x * RL_LANES;
+        for (; m; m &= m - 1) {
+            const int b = __ffs(m) - 1;
+            const int cell = off + __popc(bits & ((1u << b) - 1u));
+            if (cell >= c.cap) continue;
+            const float v = (float)row[b];
+            atomicAdd(reinterpret_cast<float4 *>(F + (size_t)cell * CH) + part, make_float4(v * e4.x, v * e4.y, v * e4.z, v * e4.w));
+        }
+    }
+}
+
+// empty-body rules: count = one_hot(h) -> the cell (h_b, b) gets the sum of their embeddings
+__global__ void __launch_bounds__(128)
+k_plus_zr_features(rl_graph g, rl_rules r, rl_slots s, rl_cells c, const float *__restrict__ emb, float *__restrict__ F)
+{
+    const int slot = blockIdx.x, b = threadIdx.x >> 2, part = threadIdx.x & 3;
+    const int q = s.slot_head[slot];
+    const int z0 = r.zr_ptr[q], z1 = r.zr_ptr[q + 1];
+    if (z1 <= z0) return;
+    const int h = s.lane_h[slot * RL_LANES + b];
+    if (h < 0) return;
+    const size_t srow = (size_t)slot * g.num_entities;
+    const uint32_t bits = c.nzmask[srow + h];
+    const int cell = c.cand_off[srow + h] + __popc(bits & ((1u << b) - 1u));
+    if (cell >= c.cap) return;
+    float4 a = make_float4(0.f, 0.f, 0.f, 0.f);
+    for (int t = z0; t < z1; ++t) {
+        const float4 e4 = __ldg(reinterpret_cast<const float4 *>(emb + (size_t)r.zr_rule[t] * CH) + part);
+        a.x += e4.x; a.y += e4.y; a.z += e4.z; a.w += e4.w;
+    }
+    atomicAdd(reinterpret_cast<float4 *>(F + (size_t)cell * CH) + part, a);
+}
+
+// gEmb[rule][16] += sum over the item's non-zero queries of fp32(count) * dF[cell][16]: one vector atomic per
+// (item, rule, quarter)
+template <typename CT>
+__global__ void __launch_bounds__(256)
+k_plus_item_bwd(rl_graph g, rl_rules r, rl_slots s, rl_frontier fr, rl_cells c, const float *__restrict__ dF,
+                float *__restrict__ gEmb)
+{
+    const int slot = blockIdx.y;
+    const int n = fr.item_cnt[slot];
+    const long long ib = fr.item_off[slot];
+    const int4 *items = reinterpret_cast<const int4 *>(fr.items) + ib;
+    const uint32_t *masks = fr.item_mask + ib;
+    const CT *arena = reinterpret_cast<const CT *>(fr.arena) + (size_t)s.arena_off[slot] * RL_LANES;
+    const size_t srow = (size_t)slot * g.num_entities;
+    const int part = threadIdx.x & 3;
+    for (int i = (blockIdx.x * 256 + threadIdx.x) >> 2; i < n; i += PN_BLOCKS * 64) {
+        uint32_t m = __ldg(masks + i);
+        if (!m) continue;
+        const int4 it = __ldg(items + i);
+        const uint32_t bits = c.nzmask[srow + it.z];
+        const int off = c.cand_off[srow + it.z];
+        const CT *row = arena + (size_t)it.x * RL_LANES;
+        float4 a = make_float4(0.f, 0.f, 0.f, 0.f);
+        for (; m; m &= m - 1) {
+            const int b = __ffs(m) - 1;
+            const int cell = off + __popc(bits & ((1u << b) - 1u));
+            if (cell >= c.cap) continue;
+            const float v = (float)row[b];
+            const float4 d4 = __ldg(reinterpret_cast<const float4 *>(dF + (size_t)cell * CH) + part);
+            a.x = fmaf(v, d4.x, a.x); a.y = fmaf(v, d4.y, a.y); a.z = fmaf(v, d4.z, a.z); a.w = fmaf(v, d4.w, a.w);
+        }
+        for (int t = it.y; t < it.y + it.w; ++t)
+            atomicAdd(reinterpret_cast<float4 *>(gEmb + (size_t)__ldg(r.node_term_rule + t) * CH) + part, a);
+    }
+}
+
+__global__ void __launch_bounds__(128)
+k_plus_zr_bwd(rl_graph g, rl_rules r, rl_slots s, rl_cells c, const float *__restrict__ dF, float *__restrict__ gEmb)
+{
+    const int slot = blockIdx.x, b = threadIdx.x >> 2, part = threadIdx.x & 3;
+    const int q = s.slot_head[slot];
+    const int z0 = r.zr_ptr[q], z1 = r.zr_ptr[q + 1];
+    if (z1 <= z0) return;
+    const int h = s.lane_h[slot * RL_LANES + b];
+    if (h < 0) return;
+    const size_t srow = (size_t)slot * g.num_entities;
+    const uint32_t bits = c.nzmask[srow + h];
+    const int cell = c.cand_off[srow + h] + __popc(bits & ((1u << b) - 1u));
+    if (cell >= c.cap) return;
+    const float4 d4 = __ldg(reinterpret_cast<const float4 *>(dF + (size_t)cell * CH) + part);
+    for (int t = z0; t < z1; ++t) atomicAdd(reinterpret_cast<float4 *>(gEmb + (size_t)r.zr_rule[t] * CH) + part, d4);
+}
+
 // ------------------------------------------------------------------------------------------
 // C-ABI
 // ------------------------------------------------------------------------------------------
@@ -609,6 +722,49 @@ int rl_plus_cell_backward(const rl_graph *g, const rl_rules *r, const rl_slots *
     if (fr->count_bits == 32) k_plus_cells_bwd<uint32_t><<<grid, WARPS_PER_BLOCK * 32, 0, st>>>(*g, *r, *s, *fr, *c, dF, grad_emb);
     else k_plus_cells_bwd<unsigned long long><<<grid, WARPS_PER_BLOCK * 32, 0, st>>>(*g, *r, *s, *fr, *c, dF, grad_emb);
     CHECK_LAUNCH("k_plus_cells_bwd");
+    return RL_OK;
+}
+
+static int no_item_arg(const rl_frontier *fr)
+{
+    return !fr || !fr->arena || !fr->items || !fr->item_off || !fr->item_cnt || !fr->item_mask ||
+           (fr->count_bits != 32 && fr->count_bits != 64);
+}
+
+/* F must hold cap*16 floats; it is cleared here */
+int rl_plus_item_features(const rl_graph *g, const rl_rules *r, const rl_slots *s, const rl_frontier *fr,
+                         const rl_cells *c, const float *emb, int32_t H, float *F, void *stream)
+{
+    if (!g || !r || !s || !emb || !F || bad_cells_arg(c) || no_item_arg(fr)) return rl_fail(RL_ERR_ARG, "rl_plus_item_features: bad argument");
+    if (H != CH) return rl_fail(RL_ERR_ARG, "rl_plus_item_features: built for hidden_dim 16");
+    if (s->num_slots <= 0) return RL_OK;
+    cudaStream_t st = (cudaStream_t)stream;
+    cudaError_t e = cudaMemsetAsync(F, 0, (size_t)c->cap * CH * sizeof(float), st);
+    if (e != cudaSuccess) return rl_fail(RL_ERR_CUDA, "rl_plus_item_features: memset", e);
+    if (fr->count_bits == 32) k_plus_item_features<uint32_t><<<dim3(PN_BLOCKS, s->num_slots), 256, 0, st>>>(*g, *r, *s, *fr, *c, emb, F);
+    else k_plus_item_features<unsigned long long><<<dim3(PN_BLOCKS, s->num_slots), 256, 0, st>>>(*g, *r, *s, *fr, *c, emb, F);
+    CHECK_LAUNCH("k_plus_item_features");
+    if (r->num_zero_rules > 0) {
+        k_plus_zr_features<<<s->num_slots, 128, 0, st>>>(*g, *r, *s, *c, emb, F);
+        CHECK_LAUNCH("k_plus_zr_features");
+    }
+    return RL_OK;
+}
+
+int rl_plus_item_backward(const rl_graph *g, const rl_rules *r, const rl_slots *s, const rl_frontier *fr,
+                         const rl_cells *c, int32_t H, const float *dF, float *grad_emb, void *stream)
+{
+    if (!g || !r || !s || !dF || !grad_emb || bad_cells_arg(c) || no_item_arg(fr)) return rl_fail(RL_ERR_ARG, "rl_plus_item_backward: bad argument");
+    if (H != CH) return rl_fail(RL_ERR_ARG, "rl_plus_item_backward: built for hidden_dim 16");
+    if (s->num_slots <= 0) return RL_OK;
+    cudaStream_t st = (cudaStream_t)stream;
+    if (fr->count_bits == 32) k_plus_item_bwd<uint32_t><<<dim3(PN_BLOCKS, s->num_slots), 256, 0, st>>>(*g, *r, *s, *fr, *c, dF, grad_emb);
+    else k_plus_item_bwd<unsigned long long><<<dim3(PN_BLOCKS, s->num_slots), 256, 0, st>>>(*g, *r, *s, *fr, *c, dF, grad_emb);
+    CHECK_LAUNCH("k_plus_item_bwd");
+    if (r->num_zero_rules > 0) {
+        k_plus_zr_bwd<<<s->num_slots, 128, 0, st>>>(*g, *r, *s, *c, dF, grad_emb);
+        CHECK_LAUNCH("k_plus_zr_bwd");
+    }
     return RL_OK;
 }
 

@@ -132,9 +132,7 @@ class Grounder:
         self._ws_items = None
         self._ws_cells = None
         self._ws_cells_cap = 0
-        self._ws_nnz = None
         self.cell_cap = 0
-        self.nnz_cap = 0
         self.level_events = None      # bench.py: list collecting (depth, start, end) CUDA events
 
     @staticmethod
@@ -182,7 +180,7 @@ class Grounder:
         return HostStep(self.cr, sh, qo, host_queries=np.stack(rows), group_ptr=gp if len(sh) != len(sizes) else None,
                         group_sizes=sizes, remove_query_edges=with_etr)
 
-    def make_slots_host(self, batches, with_etr: bool, etr_lists=None) -> Slots:
+    def make_slots_host(self, batches, with_etr: bool, etr_lists=None, coo_only: bool = False) -> Slots:
         """Slots for a list of single-relation batches given as host lists of (h, r, t) triples
         (what the datasets hold) -- or for a HostStep packed ahead by pack_host.  ONE packed host->device copy
         carries h, t and the slot tables.  with_etr: every query's own train edge is masked out
@@ -191,6 +189,7 @@ class Grounder:
         host = batches if isinstance(batches, HostStep) else self.pack_host(batches, with_etr, etr_lists)
         sl = Slots(self.dg, host)
         sl.use_workspace = True
+        sl.coo_only = bool(coo_only)      # cell paths walk the items as appended: no entity-grouped copy, no bucket tables
         return sl
 
     def _layout(self, sl: "Slots | HostStep", bits: int = 32):
@@ -200,17 +199,18 @@ class Grounder:
         n_bkt = S * (W * 32 + 32)                                        # per-entity item counts / offsets (RL_BUCKET_STRIDE)
         n_pad = -(n_mask + n_cnt + S) % 4                                # the bucket table is read with 16-byte loads
         cap = max(1, sl.item_cap)
+        o_nz = n_mask + n_cnt + S + n_pad + n_bkt
+        o_sc = 10 * cap + n_bkt
         return {
             "arena": max(1, sl.arena_rows) * LANES * (1 if bits == 32 else 2),
             # zeroed: row bitmaps | node counts | item counts | pad | buckets | candidate words | cell counters[8] | overflow
             "o_cnt": n_mask, "o_icnt": n_mask + n_cnt, "o_bkt": n_mask + n_cnt + S + n_pad,
-            "o_nz": n_mask + n_cnt + S + n_pad + n_bkt, "o_ctr": n_mask + n_cnt + S + n_pad + n_bkt + S * N,
-            "state": n_mask + n_cnt + S + n_pad + n_bkt + S * N + 8 + 1,
+            "o_nz": o_nz, "o_ctr": o_nz + S * N, "state": o_nz + S * N + 8 + 1,
             # scratch: items | items_sorted (int32x4 records, exact upper bound) | bucket offsets | item lane masks (x2) |
-            # first cell per (slot, entity) | cells per slot
+            # first cell per (slot, entity) | cells per slot | per-query CE statistics (x2)
             "n_items": 4 * cap, "o_boff": 8 * cap, "o_im": 8 * cap + n_bkt, "o_ims": 9 * cap + n_bkt,
-            "o_coff": 10 * cap + n_bkt, "o_ncell": 10 * cap + n_bkt + S * N, "o_nnzoff": 10 * cap + n_bkt + S * N + S,
-            "scratch": 11 * cap + n_bkt + S * N + S,
+            "o_coff": o_sc, "o_ncell": o_sc + S * N, "o_qmax": o_sc + S * N + S, "o_qsum": o_sc + S * N + S + S * LANES,
+            "scratch": o_sc + S * N + S + 2 * S * LANES,
         }
 
     def _run(self, sl: Slots, bits: int):
@@ -242,12 +242,13 @@ class Grounder:
         sl.slot_ncell = scratch[lay["o_ncell"]:lay["o_ncell"] + sl.S]
         sl.flags = sl.state[lay["o_ctr"]:]                               # cell counters[8] | count overflow: one D2H read
         base, sb = sl.state.data_ptr(), scratch.data_ptr()
+        coo_only = bool(getattr(sl, "coo_only", False))                  # cell paths: no entity-grouped copy of the items
         sl.frontier = _lib.RlFrontier(bits, sl.arena.data_ptr(), base, base + 4 * lay["o_cnt"],
                                       sl.overflow.data_ptr(), sb, sb + 4 * lay["n_items"], sl.item_off.data_ptr(),
-                                      base + 4 * lay["o_icnt"], base + 4 * lay["o_bkt"], sb + 4 * lay["o_boff"],
-                                      sb + 4 * lay["o_im"], sb + 4 * lay["o_ims"], base + 4 * lay["o_nz"])
-        sl.cells_tables = (base + 4 * lay["o_ctr"], base + 4 * lay["o_nz"], sb + 4 * lay["o_coff"], sb + 4 * lay["o_ncell"],
-                           sb + 4 * lay["o_nnzoff"])
+                                      base + 4 * lay["o_icnt"], None if coo_only else base + 4 * lay["o_bkt"],
+                                      sb + 4 * lay["o_boff"], sb + 4 * lay["o_im"], sb + 4 * lay["o_ims"], base + 4 * lay["o_nz"])
+        sl.cells_tables = {"counters": base + 4 * lay["o_ctr"], "nzmask": base + 4 * lay["o_nz"], "cand_off": sb + 4 * lay["o_coff"],
+                           "slot_ncell": sb + 4 * lay["o_ncell"], "qmax": sb + 4 * lay["o_qmax"], "qsum": sb + 4 * lay["o_qsum"]}
         sl.cells = None
         L = _lib.lib()
         lc = self.cr.level_chunks[sl.heads]                               # [S, max_len]
@@ -281,30 +282,20 @@ class Grounder:
         planes = [self._ws_cells[(1 + i) * cap:(2 + i) * cap] for i in range(floats_per_cell)]
         return cap, self._ws_cells[:cap].view(torch.int32), planes
 
-    def build_cells(self, sl: Slots, floats_per_cell: int, coo: bool = False):
-        """rl_cells_build for an expanded frontier -> (RlCells, fp32 planes [cap] each).  coo: also reserve the
-        coordinate list of the non-zero counts (value, cell, item) that rl_predictor_cell_scores fills."""
-        cap, keys, planes = self.cell_arrays(sl, floats_per_cell)
-        ctr, nz, coff, ncell, nnzoff = sl.cells_tables
-        nnz_cap, nzp = 0, (None, None, None)
-        if coo:
-            nnz_cap = (max(self.nnz_cap, 2 * cap) + 63) // 64 * 64
-            if self._ws_nnz is None or self._ws_nnz.numel() < 3 * nnz_cap:
-                self._ws_nnz = None
-                self._ws_nnz = torch.empty(3 * nnz_cap, dtype=torch.int32, device=self.device)
-            nnz_cap = self._ws_nnz.numel() // 3
-            b0 = self._ws_nnz.data_ptr()
-            nzp = (b0, b0 + 4 * nnz_cap, b0 + 8 * nnz_cap)
-        sl.cells = _lib.RlCells(cap, ctr, nz, coff, keys.data_ptr(), ncell, nnz_cap, nnzoff, nzp[0], nzp[1], nzp[2])
+    def build_cells(self, sl: Slots, floats_per_cell: int):
+        """rl_cells_build for an expanded frontier -> (RlCells, fp32 planes [cap] each)."""
+        cap, keys, planes = self.cell_arrays(sl, 1 + floats_per_cell)      # plane 0: the cells' entities
+        t = sl.cells_tables
+        sl.cells = _lib.RlCells(cap, t["counters"], t["nzmask"], t["cand_off"], keys.data_ptr(), planes[0].data_ptr(),
+                                t["slot_ncell"], t["qmax"], t["qsum"])
         sl.cell_cap = cap
         _lib.check(_lib.lib().rl_cells_build(self.dg.ref(), self.dr.ref(), sl.ref(), sl.fref(), C.byref(sl.cells), _stream()),
                    "rl_cells_build")
-        return sl.cells, planes
+        return sl.cells, planes[1:]
 
-    def note_cell_count(self, n_cells: int, n_nnz: int = 0):
-        """Remember the largest cell / non-zero counts seen so that later calls size their arrays for them (x1.25)."""
+    def note_cell_count(self, n_cells: int):
+        """Remember the largest cell count seen so that later calls size their arrays for it (x1.25)."""
         self.cell_cap = max(self.cell_cap, int(n_cells * 1.25) + 1024)
-        self.nnz_cap = max(self.nnz_cap, int(n_nnz * 1.25) + 1024)
 
     def reserve(self, slots_list):
         """Size the reusable frontier workspace for the largest of the given calls up front, so that no

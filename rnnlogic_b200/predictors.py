@@ -273,15 +273,16 @@ class _StepTicket:
             return self._done
         self.event.synchronize()
         host, ng, S = self.pinned, self.ng, self.sl.S
-        flags = host[2 * ng + S:]
+        flags = host[2 * ng + S:]                           # cell counters[8] | count overflow
         self.total_cells = int(flags[0].item())
-        self.sk.gr.note_cell_count(self.total_cells, int(flags[2].item()))
-        if flags[8].item() != 0:
+        self.sk.gr.note_cell_count(self.total_cells)
+        self.count_overflow = flags[8].item() != 0
+        if self.count_overflow:
             raise RlStepOverflow("a path count overflowed 32 bits inside an enqueued step; redo it with "
                                  "model.fused_train_step (exact 64-bit rows)")
-        if flags[1].item() != 0 or flags[3].item() != 0:
-            raise RlStepOverflow("the step has %d candidate cells / %d non-zero counts, more than its arrays hold; redo it "
-                                 "with model.fused_train_step (the arrays grow)" % (self.total_cells, int(flags[2].item())))
+        if flags[1].item() != 0:
+            raise RlStepOverflow("the step has %d candidate cells, more than its arrays hold; redo it with "
+                                 "model.fused_train_step (the arrays grow)" % self.total_cells)
         ncell = host[2 * ng:2 * ng + S].numpy()
         gslots = [(n + LANES - 1) // LANES for n in self.sl.group_sizes]
         self.mask_sum = np.add.reduceat(ncell, np.concatenate([[0], np.cumsum(gslots)[:-1]])).tolist() if S else []
@@ -324,7 +325,7 @@ def _prepare_train(self, batches):
     this for step k+1 while the gradient all-reduce of step k is in flight.  ``batches``: a list of
     single-relation batches or a step packed ahead by pack_train_step."""
     sk = self._driver(_model_device(self))
-    sl = sk.gr.make_slots_host(batches, with_etr=True)
+    sl = sk.gr.make_slots_host(batches, with_etr=True, coo_only=True)
     bits = sk.gr.force_bits or 32
     sk.gr._run(sl, bits)
     return _PreparedStep(self, sk, sl, batches, bits)
@@ -345,15 +346,15 @@ def _fused_train(self, batches, smoothing, grad_scale=1.0):
     sk = self._driver(_model_device(self))
     host = batches if not isinstance(batches, list) else sk.gr.pack_host(batches, with_etr=True)
     bits = sk.gr.force_bits or 32
-    for _attempt in range(4):
-        sl = sk.gr.make_slots_host(host, with_etr=True)
+    for _attempt in range(10):
+        sl = sk.gr.make_slots_host(host, with_etr=True, coo_only=True)
         sk.gr._run(sl, bits)
         ticket = _PreparedStep(self, sk, sl, batches, bits).finish(smoothing, grad_scale)
         try:
             loss, tsum = ticket.result()
             break
         except RlStepOverflow:
-            if ticket.pinned[-1].item() != 0:              # count overflow: exact 64-bit rows (they wrap like the reference's int64)
+            if ticket.count_overflow:                      # exact 64-bit rows (they wrap like the reference's int64)
                 bits = 64
     else:
         raise _lib.RlError("fused_train_step: the cell arrays kept overflowing")
@@ -371,7 +372,7 @@ def _fused_train(self, batches, smoothing, grad_scale=1.0):
 def _fused_rank(self, batches, split):
     """(L,H) int64[Q,2] of a list of single-relation eval batches (trainer.py:173,189-201)."""
     sk = self._driver(_model_device(self))
-    sl = sk.gr.make_slots_host(batches, with_etr=False)
+    sl = sk.gr.make_slots_host(batches, with_etr=False, coo_only=True)
     if isinstance(self, Predictor):
         LH = cellpath.predictor_rank(self, sk, sl, split)
     else:

@@ -177,6 +177,8 @@ class CompiledRules:
         i32 = lambda a: np.ascontiguousarray(a, dtype=np.int32)
         if self.num_chunks >= 2 ** 31 or self.num_nodes >= 2 ** 31:
             raise ValueError("rule set too large for 32-bit work tables")
+        if self.num_nodes and int(self.head_item_cap.max()) >= 2 ** 26:
+            raise ValueError("a head's rule-end nodes have >= 2^26 rows: item indices no longer fit the coordinate keys")
         self.host = {
             "node_rel": i32(node_rel), "node_parent": i32(node_parent),
             "node_row_off": np.ascontiguousarray(node_row_off, dtype=np.int64),
@@ -203,7 +205,7 @@ class DeviceRules:
         self.t = {k: torch.from_numpy(v if v.shape[0] else np.zeros(1, v.dtype)).to(device) for k, v in cr.host.items()}
         t = self.t
         self.struct = _lib.RlRules(
-            cr.num_nodes, cr.num_rules, cr.max_len, cr.num_chunks, cr.num_terms,
+            cr.num_nodes, cr.num_rules, cr.max_len, cr.num_chunks, cr.num_terms, int(cr.host["zr_rule"].shape[0]),
             t["node_rel"].data_ptr(), t["node_row_off"].data_ptr(),
             t["head_node_ptr"].data_ptr(), t["lvl_ptr"].data_ptr(), t["chunk_node"].data_ptr(),
             t["chunk_row0"].data_ptr(), t["zr_ptr"].data_ptr(), t["zr_rule"].data_ptr(),
