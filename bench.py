@@ -259,6 +259,34 @@ class Runner:
         assert all(torch.isfinite(l).all().item() for l in losses)
         return ms, sum(self.queries[s % len(self.steps)] for s in range(warmup, n_steps)), launches, events
 
+    def graph_loop(self, warmup, steps):
+        """The reference's schedule (one batch per optimizer step) through the per-head CUDA graphs: host arrays in, loss
+        out, one replay + one sync per step.  -> (ms, queries)"""
+        from rnnlogic_b200 import cellpath
+        from rnnlogic_b200.predictors import _used_params
+        model = self.model
+        seq = [self.steps[s % len(self.steps)][0] for s in range(warmup + steps)]
+        for b in seq:                                            # capture the graphs of the heads of this run (one each)
+            cellpath.graph_train_step(model, b, 0.2)
+        torch.cuda.synchronize()
+        nq = 0
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        for s, b in enumerate(seq):
+            if s == warmup:
+                e0.record()
+            res = cellpath.graph_train_step(model, b, 0.2)
+            if res is None:
+                loss, _ = model.fused_train_step([b], 0.2)
+            else:
+                res[3].assign(_used_params(model, res[2]))
+                assert np.isfinite(res[0])
+            self.opt.step()
+            if s >= warmup:
+                nq += len(b)
+        e1.record()
+        torch.cuda.synchronize()
+        return e0.elapsed_time(e1), nq
+
     def e2e_loop(self, warmup, steps, trace=None):
         """Host int arrays in, losses out, through submit / prepare / finish / result (software-pipelined by one
         step; every step does its own packed H2D copy and its own D2H read).  -> (ms, queries, h2d, d2h)."""
@@ -298,6 +326,41 @@ class Runner:
         e1.record()
         torch.cuda.synchronize()
         return e0.elapsed_time(e1), sum(self.queries[s % len(self.steps)] for s in range(warmup, n_steps)), h2d, d2h
+
+
+def dense_expansion_traffic(kg, cr, heads):
+    """Bytes the expansion kernels MOVE in dense mode for the given slot heads -- a model of the kernel's own behaviour,
+    counted from the graph (not the algorithmic figure): per trie node it reads the relation's rows / edge list, looks every
+    source up in the parent relation's rank table, pulls a parent row (128 B) only for the in-edges whose source is a
+    tail of the parent relation, and writes a row (128 B) only when at least one of its in-edges was pulled.  Both are
+    static statistics of the (parent relation, relation) pair."""
+    N, R = kg.entity_size, kg.relation_size
+    h = kg.host
+    dst_ptr, row_start, edge_src, row_dst = h["dst_ptr"], h["row_start"], h["edge_src"], h["row_dst"]
+    is_tail = np.zeros((R, N), dtype=bool)
+    for rho in range(R):
+        is_tail[rho, row_dst[dst_ptr[rho]:dst_ptr[rho + 1]]] = True
+    pulled = np.zeros((R, R), dtype=np.int64)           # [parent relation][relation]
+    rows_w = np.zeros((R, R), dtype=np.int64)
+    for rho in range(R):
+        r0, r1 = int(dst_ptr[rho]), int(dst_ptr[rho + 1])
+        if r1 == r0:
+            continue
+        e0, e1 = int(row_start[r0]), int(row_start[r1])
+        M = is_tail[:, edge_src[e0:e1]]                 # [R, E_rho]
+        pulled[:, rho] = M.sum(1)
+        rows_w[:, rho] = np.logical_or.reduceat(M, (row_start[r0:r1] - e0).astype(np.int64), axis=1).sum(1)
+    E, D = kg.rel_edges, kg.rel_rows
+    node_rel, node_depth, node_head = cr.node_rel_host, cr.node_depth, cr.node_head
+    prel = np.where(cr.host["node_parent"] >= 0, node_rel[np.maximum(cr.host["node_parent"], 0)], 0)
+    root = node_depth == 1
+    per_node = 4 * E[node_rel] + 8 * D[node_rel] + np.where(
+        root, 128 * D[node_rel],                                                  # depth 1: compares, every row written
+        8 * E[node_rel] + 128 * pulled[prel, node_rel] + 128 * rows_w[prel, node_rel])
+    nb = np.zeros(cr.num_nodes + 1, dtype=np.int64)
+    np.cumsum(per_node, out=nb[1:])
+    head_bytes = nb[cr.head_node_ptr[1:]] - nb[cr.head_node_ptr[:-1]]
+    return float(head_bytes[heads].sum())
 
 
 def reduce_max_sum(ms, q, dev, world):
@@ -345,6 +408,15 @@ def side_config(tag, kg, rules, batches, kw, per, steps, world, rank, dev, plus=
     model = model.cuda(dev)
     if plus and not model.supports_pipeline:
         return side_config_autograd(model, batches, per, steps, dev)
+    if per == 1 and world == 1:                      # reference schedule: per-head CUDA graphs
+        run = Runner(model, deal_steps(batches, model.compiled, 1, 64, world, rank), 1, world, dev)
+        ms, q = run.graph_loop(8, steps)
+        out = {"e2e_queries_per_sec": q / (ms / 1e3), "ms_per_step": ms / steps, "steps": steps, "batches_per_step_per_gpu": 1,
+               "path": "one CUDA graph replay + one sync per step (graph captured once per head relation)"}
+        print("[bench] %s: %.0f q/s e2e, %.3f ms/step" % (tag, out["e2e_queries_per_sec"], out["ms_per_step"]), file=sys.stderr)
+        del run, model
+        torch.cuda.empty_cache()
+        return out
     run = Runner(model, deal_steps(batches, model.compiled, per, 4, world, rank), per, world, dev)
     run.size_cells()
     ms, q, h2d, d2h = run.e2e_loop(3, steps)
@@ -528,6 +600,14 @@ def main():
                                "every row of every trie node is expanded (all in-edges examined); rows that are zero for "
                                "EVERY query and L2 hits keep DRAM traffic below the algorithmic bytes; the expansion alone, "
                                "timed in a second region right after the product loop (%d steps)" % nd)
+        if rank == 0:
+            # what the kernel itself moves in this mode (a parent row is pulled / a row written only where an in-edge starts at a
+            # tail of the parent relation): the bandwidth figure; `frac` above credits the algorithmic bytes of SURVEY 8d
+            moved = dense_expansion_traffic(kg, cr, heads_d)
+            tot_ms = sum(float(v) for v in roofline["ms_by_depth"].values())
+            roofline["moved_bytes_per_launch"] = moved / max(1, roofline["launches"])
+            roofline["moved_bytes_source"] = "counted from the graph for this kernel's access pattern (bench.py: dense_expansion_traffic), not ncu"
+            roofline["dram_frac"] = moved / (tot_ms / 1e3) / 1e9 / peak if tot_ms > 0 else None
 
     # ---------------- end-to-end through the public fused API (host arrays in, losses out) --------
     trace = [] if args.trace_e2e else None

@@ -301,3 +301,88 @@ def plus_rank(model, sk, sl, split):
     bias = model.bias.detach() if ef == "bias" else None
     sorted_bias = torch.sort(bias)[0] if bias is not None else None
     return ck.rank(sl, bias, sorted_bias, zc, which)
+
+
+# ================================================================================================
+# The reference's own schedule -- ONE batch of <= 32 queries per optimizer step (src/trainer.py:68-95) -- is launch
+# bound: ~25 small kernels, a memset, two copies and the Python around them per 32 queries.  Every size of such a
+# step depends only on the batch's head relation, so the whole step (H2D of the queries -> slot preparation ->
+# expansion -> cells -> scores -> CE -> backward -> D2H of loss / flags) is captured ONCE per head relation as a CUDA
+# graph and replayed with new queries written into its pinned staging buffer.
+# ================================================================================================
+class GraphTrainStep:
+    """Captured fused train step of ``model`` for batches of one head relation (one slot)."""
+
+    def __init__(self, model, head: int, smoothing: float):
+        from .engine import HostStep, Slots
+        self.model, self.head, self.smoothing = model, int(head), float(smoothing)
+        dev = next(model.parameters()).device
+        self.sk = sk = model._driver(dev)
+        gr = sk.gr
+        self.params = model.fused_params()
+        # static host staging: 32 query columns (padding = -1), rows h, t
+        q = np.full((2, LANES), -1, dtype=np.int64)
+        self.host = HostStep(gr.cr, np.array([self.head], dtype=np.int64), np.array([0, 0], dtype=np.int64), host_queries=q,
+                             group_sizes=[0], remove_query_edges=True)
+        self._pack = self.host.staged.numpy()
+        self._q = self._pack[:2 * LANES].reshape(2, LANES)
+        self._qoff = self._pack[self.host.n64:].view(np.int32)[1:3]           # q_off = [0, n] behind the slot head
+        self.generation = gr.generation
+
+        def run():
+            sl = Slots(gr.dg, self.host)
+            sl.use_workspace, sl.coo_only = True, True
+            gr._run(sl, 32)
+            gbuf = GradBuffer(self.params)
+            loss, tsum = model.step_on_slots(sk, sl, self.smoothing, 1.0, gbuf, 32, expanded=True)
+            pack = torch.cat([loss, tsum, sl.slot_ncell.float(), sl.flags.float()])
+            return sl, gbuf, pack
+
+        self._fill(np.zeros((1, 3), dtype=np.int64) + np.array([[0, self.head, 0]]))
+        sl, gbuf, pack = run()                                               # eager warm-up: sizes every workspace
+        self.pinned = torch.empty(pack.numel(), dtype=torch.float32, pin_memory=True)
+        torch.cuda.synchronize()
+        self.generation = gr.generation
+        self.graph = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(self.graph):
+            self.sl, self.gbuf, pack = run()
+            self.pinned.copy_(pack, non_blocking=True)
+        if gr.generation != self.generation:
+            raise _lib.RlError("a workspace was reallocated during graph capture")
+
+    def _fill(self, batch: np.ndarray):
+        n = int(batch.shape[0])
+        self._q[:, :] = -1
+        self._q[0, :n] = batch[:, 0]
+        self._q[1, :n] = batch[:, 2]
+        self._qoff[0], self._qoff[1] = 0, n
+        self.n = n
+
+    def __call__(self, batch: np.ndarray):
+        """Replay for one batch [n,3] of this head.  -> (loss, target_sum, cells, flags) after the step's one sync;
+        the gradients are in self.gbuf."""
+        self._fill(batch)
+        self.graph.replay()
+        torch.cuda.current_stream().synchronize()
+        host = self.pinned
+        flags = host[3:]
+        return float(host[0]), float(host[1]), int(host[2]), flags
+
+
+def graph_train_step(model, batch: np.ndarray, smoothing: float):
+    """One reference-schedule train step through the per-head CUDA graph.  Returns (loss, tsum, cells, gbuf) or None
+    when the step has to take the eager path (count overflow, cell arrays too small, unsupported model)."""
+    if len(batch) > LANES or not getattr(model, "supports_pipeline", False):
+        return None
+    head = int(batch[0][1])
+    cache = model.__dict__.setdefault("_graph_steps", {})
+    gs = cache.get((head, float(smoothing)))
+    gr = model._driver(next(model.parameters()).device).gr
+    if gs is None or gs.generation != gr.generation:
+        gr.reserve_single_slot()
+        gs = cache[(head, float(smoothing))] = GraphTrainStep(model, head, smoothing)
+    loss, tsum, cells, flags = gs(np.asarray(batch, dtype=np.int64).reshape(-1, 3))
+    if flags[8] != 0 or flags[1] != 0:
+        gr.note_cell_count(cells)
+        return None
+    return loss, tsum, cells, gs.gbuf

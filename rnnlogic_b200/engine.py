@@ -133,6 +133,7 @@ class Grounder:
         self._ws_cells = None
         self._ws_cells_cap = 0
         self.cell_cap = 0
+        self.generation = 0           # bumped whenever a workspace is reallocated (captured CUDA graphs hold its pointers)
         self.level_events = None      # bench.py: list collecting (depth, start, end) CUDA events
 
     @staticmethod
@@ -224,11 +225,14 @@ class Grounder:
             if self._ws_arena is None or self._ws_arena.numel() < n_arena:
                 self._ws_arena = None
                 self._ws_arena = torch.empty(int(n_arena * 1.25), dtype=torch.int32, device=dev)
+                self.generation += 1
             if self._ws_state is None or self._ws_state.numel() < n_state:
                 self._ws_state = torch.empty(int(n_state * 1.25), dtype=torch.int32, device=dev)
+                self.generation += 1
             if self._ws_items is None or self._ws_items.numel() < n_scratch:
                 self._ws_items = None
                 self._ws_items = torch.empty(int(n_scratch * 1.25), dtype=torch.int32, device=dev)
+                self.generation += 1
             sl.arena = self._ws_arena[:n_arena]
             sl.state = self._ws_state[:n_state].zero_()
             scratch = self._ws_items[:n_scratch]
@@ -278,6 +282,7 @@ class Grounder:
             self._ws_cells = None
             self._ws_cells = torch.empty(n, dtype=torch.float32, device=self.device)
             self._ws_cells_cap = want
+            self.generation += 1
         cap = self._ws_cells_cap
         planes = [self._ws_cells[(1 + i) * cap:(2 + i) * cap] for i in range(floats_per_cell)]
         return cap, self._ws_cells[:cap].view(torch.int32), planes
@@ -307,6 +312,27 @@ class Grounder:
             if cur is None or cur.numel() < n:
                 setattr(self, name, None)
                 setattr(self, name, torch.empty(n, dtype=torch.int32, device=self.device))
+                self.generation += 1
+
+    def reserve_single_slot(self):
+        """Size the frontier workspace for one slot of the LARGEST head, so that per-head CUDA graphs of the reference
+        schedule (one batch per step) never see a reallocation."""
+        cr = self.cr
+        if not len(cr.head_rows):
+            return
+
+        class _One:                                              # what _layout reads of a call
+            S = 1
+        one = _One()
+        one.arena_rows, one.nz_total = int(cr.head_rows.max()), int(cr.head_nodes.max())
+        one.mask_words, one.item_cap = int(cr.head_chunks.max()), int(cr.head_item_cap.max())
+        lay = self._layout(one)
+        for name, key in (("_ws_arena", "arena"), ("_ws_state", "state"), ("_ws_items", "scratch")):
+            cur = getattr(self, name)
+            if cur is None or cur.numel() < lay[key]:
+                setattr(self, name, None)
+                setattr(self, name, torch.empty(lay[key], dtype=torch.int32, device=self.device))
+                self.generation += 1
 
     def _run_empty(self, sl: Slots):
         sl.arena = torch.zeros(LANES, dtype=torch.int32, device=self.device)

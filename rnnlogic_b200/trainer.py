@@ -77,6 +77,7 @@ class TrainerPredictor(object):
     pipelined = True        # enqueue the grounding of step i+1 before reading step i back (flags are checked before
                             # every optimizer step; an overflowed step is redone with 64-bit rows / larger arrays)
     eval_batches_per_call = 64
+    use_graphs = True       # slots_per_step == 1: replay one captured CUDA graph per head relation for the whole fused step
 
     def __init__(self, model, train_set, valid_set, test_set, optimizer, scheduler=None, gpus=None, num_worker=0):
         self.rank = comm.get_rank()
@@ -132,7 +133,10 @@ class TrainerPredictor(object):
         # its gradients and steps the optimizer.  The flags are always checked before the optimizer step: a step
         # whose 32-bit counts overflowed (or whose cell arrays were too small) is redone synchronously first.
         from .predictors import RlStepOverflow
-        pipelined = bool(self.pipelined and getattr(model, "supports_pipeline", False))
+        from .predictors import _used_params
+        from . import cellpath
+        graphs = bool(self.use_graphs and k == 1 and getattr(model, "supports_pipeline", False))
+        pipelined = bool(self.pipelined and getattr(model, "supports_pipeline", False)) and not graphs
         ticket = None
         if pipelined and steps:
             from .data import StepPrefetcher
@@ -140,7 +144,11 @@ class TrainerPredictor(object):
             ticket = model.prepare_train_step(next(packed)).finish(smoothing, grad_scale=1.0 / len(steps[0]))
         for si, batches in enumerate(steps):
             self.optimizer.zero_grad(set_to_none=True)
-            if pipelined:
+            res = cellpath.graph_train_step(model, batches[0], smoothing) if (graphs and len(batches[0]) <= 32) else None
+            if res is not None:                                        # the whole step was one graph replay + one sync
+                loss, tsum, cand = [res[0]], [res[1]], [res[2]]
+                res[3].assign(_used_params(model, res[2]))
+            elif pipelined:
                 prep = model.prepare_train_step(next(packed)) if si + 1 < len(steps) else None
                 try:
                     loss, tsum = ticket.result()
