@@ -467,16 +467,40 @@ int rl_plus_cell_backward(const rl_graph *g, const rl_rules *r, const rl_slots *
  * (layouts of the parameters), writes dF[cell][16] (and dY[cell][16], scratch) and needs
  * rl_tail_scratch_floats(R) floats of scratch. */
 int64_t rl_tail_scratch_floats(int32_t R);
+/* front_done != 0: F already holds the aggregator's Linear output y (the PNA front, rl_pna_front_forward); then W0 is
+ * not used, the backward produces dY only (no dF, no gW0) and gb0 still receives sum dy (the Linear's bias). */
 int rl_tail_forward(const rl_cells *c, const int32_t *slot_head, int32_t H, int32_t J, const float *F, const float *W0,
                     const float *b0, const float *gamma, const float *beta, const float *W1, const float *b1,
                     const float *W2, const float *b2, const float *rel_emb, float *zc, float *O, uint32_t *relu_bits,
-                    void *stream);
+                    int32_t front_done, void *stream);
 int rl_tail_backward(const rl_cells *c, const int32_t *slot_head, int32_t R, int32_t H, int32_t J, const float *F,
                      const float *W0, const float *b0, const float *gamma, const float *beta, const float *W1,
                      const float *b1, const float *W2, const float *b2, const float *rel_emb, const float *Gc,
                      const float *O, const uint32_t *relu_bits, float *dF, float *dY, float *gW0, float *gb0,
                      float *ggamma, float *gbeta, float *gW1, float *gb1, float *gW2, float *gb2, float *grel,
-                     float *scratch, void *stream);
+                     float *scratch, int32_t front_done, void *stream);
+
+/* ---- PNA aggregator (FuncToNode, src/layers.py:89-126) on the cells, hidden_dim 16 (rl_pna.cu) ---- */
+typedef struct rl_pna {                 /* per-cell statistics, arrays of rl_cells.cap cells (DEVICE) */
+    float *s1;                          /* [cap][16] sum count * emb      (layers.py:94) */
+    float *s2;                          /* [cap][16] sum count * emb^2    (layers.py:95) */
+    float *deg;                         /* [cap]     sum count (the reference's degree is this + 1, layers.py:92) */
+    unsigned long long *mnk;            /* [cap][16] min over rules with count != 0: order key of emb << 32 | rule */
+    unsigned long long *mxk;            /* [cap][16] max ...:                        order key of emb << 32 | ~rule */
+} rl_pna;
+/* statistics from the item list (arrays are initialised here) */
+int rl_pna_item_stats(const rl_graph *g, const rl_rules *r, const rl_slots *s, const rl_frontier *fr, const rl_cells *c,
+                      const float *emb, const rl_pna *p, void *stream);
+/* Y[cell][16] = Linear(12H,H)([mean, min, max, std] (x) [1, s, 1/s]) (layers.py:100-124; W [16][192], b [16]);
+ * FEAT[cap][64] and SC[cap] are kept for the backward; qscr = 2*S*32 floats of scratch. */
+int rl_pna_front_forward(const rl_slots *s, const rl_cells *c, const rl_pna *p, const float *W, const float *b, float *qscr,
+                         float *Y, float *FEAT, float *SC, void *stream);
+/* dY[cell][16] -> dstat[cell][64] = [dS1 | dS2 | dMin | dMax]; gW[16][192] += dY^T update */
+int rl_pna_front_backward(const rl_cells *c, const rl_pna *p, const float *W, const float *dY, const float *FEAT,
+                          const float *SC, float *dstat, float *gW, void *stream);
+/* grad_emb[rule][16] += count * dS1 + 2 count emb dS2 (+ dMin / dMax at the arg rules: first rule in file order on ties) */
+int rl_pna_item_backward(const rl_graph *g, const rl_rules *r, const rl_slots *s, const rl_frontier *fr, const rl_cells *c,
+                         const float *emb, const rl_pna *p, const float *dstat, float *grad_emb, void *stream);
 
 #ifdef __cplusplus
 }

@@ -12,7 +12,7 @@ import subprocess
 _HERE = os.path.dirname(os.path.abspath(__file__))
 ROOT = os.path.dirname(_HERE)
 LIB_PATH = os.environ.get("RNNLOGIC_B200_LIB") or os.path.join(_HERE, "lib", "librnnlogic_b200.so")   # env override: A/B builds
-SOURCES = [os.path.join(_HERE, "csrc", f) for f in ("rl_kernels.cu", "rl_cells.cu", "rl_plus.cu", "rl_rotate.cu", "rl_tail.cu", "rl_tail2.cu", "rl_rnn.cu")]
+SOURCES = [os.path.join(_HERE, "csrc", f) for f in ("rl_kernels.cu", "rl_cells.cu", "rl_plus.cu", "rl_rotate.cu", "rl_tail.cu", "rl_tail2.cu", "rl_pna.cu", "rl_rnn.cu")]
 HEADER = os.path.join(ROOT, "include", "rnnlogic_b200.h")
 
 LANES = 32
@@ -51,6 +51,10 @@ class RlFrontier(C.Structure):
 class RlCells(C.Structure):
     _fields_ = [("cap", C.c_int32), ("counters", vp), ("nzmask", vp), ("cand_off", vp), ("cell_key", vp),
                 ("cell_ent", vp), ("slot_ncell", vp), ("qmax", vp), ("qsum", vp)]
+
+
+class RlPna(C.Structure):
+    _fields_ = [("s1", vp), ("s2", vp), ("deg", vp), ("mnk", vp), ("mxk", vp)]
 
 
 class RlAnswers(C.Structure):
@@ -176,8 +180,14 @@ _PROTOS = {
     "rl_plus_cell_backward": (C.c_int, [C.POINTER(RlGraph), C.POINTER(RlRules), C.POINTER(RlSlots), C.POINTER(RlFrontier),
                                         C.POINTER(RlCells), C.c_int32, vp, vp, vp]),
     "rl_tail_scratch_floats": (C.c_int64, [C.c_int32]),
-    "rl_tail_forward": (C.c_int, [C.POINTER(RlCells), vp, C.c_int32, C.c_int32] + [vp] * 14),
-    "rl_tail_backward": (C.c_int, [C.POINTER(RlCells), vp, C.c_int32, C.c_int32, C.c_int32] + [vp] * 26),
+    "rl_tail_forward": (C.c_int, [C.POINTER(RlCells), vp, C.c_int32, C.c_int32] + [vp] * 13 + [C.c_int32, vp]),
+    "rl_tail_backward": (C.c_int, [C.POINTER(RlCells), vp, C.c_int32, C.c_int32, C.c_int32] + [vp] * 25 + [C.c_int32, vp]),
+    "rl_pna_item_stats": (C.c_int, [C.POINTER(RlGraph), C.POINTER(RlRules), C.POINTER(RlSlots), C.POINTER(RlFrontier),
+                                    C.POINTER(RlCells), vp, C.POINTER(RlPna), vp]),
+    "rl_pna_front_forward": (C.c_int, [C.POINTER(RlSlots), C.POINTER(RlCells), C.POINTER(RlPna), vp, vp, vp, vp, vp, vp, vp]),
+    "rl_pna_front_backward": (C.c_int, [C.POINTER(RlCells), C.POINTER(RlPna), vp, vp, vp, vp, vp, vp, vp]),
+    "rl_pna_item_backward": (C.c_int, [C.POINTER(RlGraph), C.POINTER(RlRules), C.POINTER(RlSlots), C.POINTER(RlFrontier),
+                                       C.POINTER(RlCells), vp, C.POINTER(RlPna), vp, vp, vp]),
     "rl_adam_step": (C.c_int, [C.c_int64, vp, vp, vp, vp, C.c_float, C.c_float, C.c_float, C.c_float, C.c_float,
                                C.c_int64, vp]),
     "rl_lstm_encode_forward": (C.c_int, [C.c_int32, C.c_int32, C.c_int32, C.c_int32, vp, vp, vp, vp, vp, vp, vp]),

@@ -106,16 +106,34 @@ class CellKernels:
         _lib.check(_L().rl_plus_item_backward(self.dg.ref(), self.dr.ref(), sl.ref(), sl.fref(), C.byref(sl.cells), 16,
                                              dF.data_ptr(), grad_emb.data_ptr(), _stream()), "rl_plus_item_backward")
 
-    def tail_forward(self, sl, F, wts, zc, O, bits):
+    def tail_forward(self, sl, F, wts, zc, O, bits, front_done=False):
         _lib.check(_L().rl_tail_forward(C.byref(sl.cells), sl.slot_head.data_ptr(), 16, 128, F.data_ptr(),
                                         *[t.data_ptr() for t in wts], zc.data_ptr(), O.data_ptr(), bits.data_ptr(),
-                                        _stream()), "rl_tail_forward")
+                                        int(front_done), _stream()), "rl_tail_forward")
 
-    def tail_backward(self, sl, R, F, wts, Gc, O, bits, dF, dY, grads, scratch):
+    def tail_backward(self, sl, R, F, wts, Gc, O, bits, dF, dY, grads, scratch, front_done=False):
         _lib.check(_L().rl_tail_backward(C.byref(sl.cells), sl.slot_head.data_ptr(), int(R), 16, 128, F.data_ptr(),
                                          *[t.data_ptr() for t in wts], Gc.data_ptr(), O.data_ptr(), bits.data_ptr(),
                                          dF.data_ptr(), dY.data_ptr(), *[t.data_ptr() for t in grads], scratch.data_ptr(),
-                                         _stream()), "rl_tail_backward")
+                                         int(front_done), _stream()), "rl_tail_backward")
+
+    # ---- PNA aggregator (rl_pna.cu) ----
+    def pna_stats(self, sl, emb, pna):
+        _lib.check(_L().rl_pna_item_stats(self.dg.ref(), self.dr.ref(), sl.ref(), sl.fref(), C.byref(sl.cells), emb.data_ptr(),
+                                          C.byref(pna), _stream()), "rl_pna_item_stats")
+
+    def pna_front_forward(self, sl, pna, W, b, Y, FEAT, SC):
+        qscr = torch.empty(2 * sl.S * LANES, dtype=torch.float32, device=self.device)
+        _lib.check(_L().rl_pna_front_forward(sl.ref(), C.byref(sl.cells), C.byref(pna), W.data_ptr(), b.data_ptr(), qscr.data_ptr(),
+                                             Y.data_ptr(), FEAT.data_ptr(), SC.data_ptr(), _stream()), "rl_pna_front_forward")
+
+    def pna_front_backward(self, sl, pna, W, dY, FEAT, SC, dstat, gW):
+        _lib.check(_L().rl_pna_front_backward(C.byref(sl.cells), C.byref(pna), W.data_ptr(), dY.data_ptr(), FEAT.data_ptr(),
+                                              SC.data_ptr(), dstat.data_ptr(), gW.data_ptr(), _stream()), "rl_pna_front_backward")
+
+    def pna_backward(self, sl, emb, pna, dstat, grad_emb):
+        _lib.check(_L().rl_pna_item_backward(self.dg.ref(), self.dr.ref(), sl.ref(), sl.fref(), C.byref(sl.cells), emb.data_ptr(),
+                                             C.byref(pna), dstat.data_ptr(), grad_emb.data_ptr(), _stream()), "rl_pna_item_backward")
 
 
 def cell_kernels(sk) -> CellKernels:
@@ -162,20 +180,27 @@ def predictor_rank(model, sk, sl, split, bits=32, expanded=False):
 # ================================================================================================
 def plus_cells_supported(model) -> bool:
     sm = model.score_model
-    return (model.aggregator == "sum" and model.hidden_dim == 16 and len(sm.layers) == 2
+    return (model.aggregator in ("sum", "pna") and model.hidden_dim == 16 and len(sm.layers) == 2
             and sm.layers[0].out_features == 128 and sm.layers[1].out_features == 1 and sm.batch_norms is None
             and not sm.short_cut and sm.dropout is None)
 
 
 PLUS_PLANES = 2 + 4 * 16 + 4          # zc, Gc | F, dF, O, dY [16 each] | ReLU bits [4 words]
+PNA_PLANES = PLUS_PLANES + 16 + 16 + 32 + 32 + 64 + 64 + 2    # + s1, s2 | min keys, max keys (u64 x 16) | FEAT | dstat | deg, SC
 
 
-def _plus_planes(gr):
+def _plus_planes(gr, pna=False):
     """Per-cell arrays of the PredictorPlus step inside the grounder's cell workspace (contiguous [cap][16] blocks)."""
     cap, ws = gr._ws_cells_cap, gr._ws_cells
     blk = lambda i0, n: ws[(2 + i0) * cap:(2 + i0 + n) * cap]          # plane 0: cell keys, plane 1: cell entities
-    return {"zc": blk(0, 1), "Gc": blk(1, 1), "F": blk(2, 16), "dF": blk(18, 16), "O": blk(34, 16), "dY": blk(50, 16),
-            "bits": blk(66, 4)}
+    pl = {"zc": blk(0, 1), "Gc": blk(1, 1), "F": blk(2, 16), "dF": blk(18, 16), "O": blk(34, 16), "dY": blk(50, 16),
+          "bits": blk(66, 4)}
+    if pna:
+        pl.update({"s1": blk(70, 16), "s2": blk(86, 16), "mnk": blk(102, 32), "mxk": blk(134, 32), "FEAT": blk(166, 64),
+                   "dstat": blk(230, 64), "deg": blk(294, 1), "SC": blk(295, 1)})
+        pl["pna"] = _lib.RlPna(pl["s1"].data_ptr(), pl["s2"].data_ptr(), pl["deg"].data_ptr(), pl["mnk"].data_ptr(),
+                               pl["mxk"].data_ptr())
+    return pl
 
 
 def _tail_weights(model):
@@ -216,13 +241,18 @@ def plus_step(model, sk, sl, smoothing, grad_scale, gbuf: GradBuffer, expanded=F
     dev = sk.device
     if not expanded:
         sk.gr._run(sl, bits)
-    sk.gr.build_cells(sl, PLUS_PLANES)
-    pl = _plus_planes(sk.gr)
+    pna = model.aggregator == "pna"
+    sk.gr.build_cells(sl, PNA_PLANES if pna else PLUS_PLANES)
+    pl = _plus_planes(sk.gr, pna)
     zc, Gc, F, dF = pl["zc"], pl["Gc"], pl["F"], pl["dF"]
     emb, enc = _rule_embeddings(model, sl, dev)
     wts = [t.detach() for t in _tail_weights(model)]
-    ck.plus_features(sl, emb, F)
-    ck.tail_forward(sl, F, wts, zc, pl["O"], pl["bits"])
+    if pna:                                                              # statistics -> scalers + Linear(12H,H) -> F holds y
+        ck.pna_stats(sl, emb, pl["pna"])
+        ck.pna_front_forward(sl, pl["pna"], wts[0], wts[1], F, pl["FEAT"], pl["SC"])
+    else:
+        ck.plus_features(sl, emb, F)
+    ck.tail_forward(sl, F, wts, zc, pl["O"], pl["bits"], front_done=pna)
     ef = model.entity_feature
     ng = len(sl.group_sizes)
     extra = None
@@ -245,13 +275,22 @@ def plus_step(model, sk, sl, smoothing, grad_scale, gbuf: GradBuffer, expanded=F
     if not want_grad:
         return loss, tsum
     grads = [gbuf.view(p) for p in _tail_weights(model)]
-    ck.tail_backward(sl, model.num_relations, F, wts, Gc, pl["O"], pl["bits"], dF, pl["dY"], grads, model._d1sum_scratch(dev))
+    ck.tail_backward(sl, model.num_relations, F, wts, Gc, pl["O"], pl["bits"], dF, pl["dY"], grads, model._d1sum_scratch(dev),
+                     front_done=pna)
+
+    def emb_backward(grad_emb):
+        if pna:
+            ck.pna_front_backward(sl, pl["pna"], wts[0], pl["dY"], pl["FEAT"], pl["SC"], pl["dstat"], grads[0])
+            ck.pna_backward(sl, emb, pl["pna"], pl["dstat"], grad_emb)
+        else:
+            ck.plus_backward(sl, dF, grad_emb)
+
     if model.type == "emb":
-        ck.plus_backward(sl, dF, gbuf.view(model.rule_emb))
+        emb_backward(gbuf.view(model.rule_emb))
     elif enc is not None:
         ids, sub = enc
         gfull = model._emb_scratch(dev, grad=True).zero_()
-        ck.plus_backward(sl, dF, gfull)
+        emb_backward(gfull)
         enc_params = [model.vocab_emb.weight] + [p for p in model.rnn.parameters()]
         gs = torch.autograd.grad(sub, enc_params, gfull[ids].to(sub.dtype), allow_unused=True)
         for p, g_ in zip(enc_params, gs):
@@ -285,13 +324,18 @@ def plus_rank(model, sk, sl, split):
     ck = cell_kernels(sk)
     dev = sk.device
     sk.gr.ground(sl)
-    sk.gr.build_cells(sl, PLUS_PLANES)
-    pl = _plus_planes(sk.gr)
+    pna = model.aggregator == "pna"
+    sk.gr.build_cells(sl, PNA_PLANES if pna else PLUS_PLANES)
+    pl = _plus_planes(sk.gr, pna)
     zc, F = pl["zc"], pl["F"]
     emb, _ = _rule_embeddings(model, sl, dev)
     wts = [t.detach() for t in _tail_weights(model)]
-    ck.plus_features(sl, emb, F)
-    ck.tail_forward(sl, F, wts, zc, pl["O"], pl["bits"])
+    if pna:
+        ck.pna_stats(sl, emb, pl["pna"])
+        ck.pna_front_forward(sl, pl["pna"], wts[0], wts[1], F, pl["FEAT"], pl["SC"])
+    else:
+        ck.plus_features(sl, emb, F)
+    ck.tail_forward(sl, F, wts, zc, pl["O"], pl["bits"], front_done=pna)
     which = "hr2oo" if split == "valid" else "hr2ooo"
     ef = model.entity_feature
     if ef == "RotatE":

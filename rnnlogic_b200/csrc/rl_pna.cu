@@ -1,0 +1,437 @@
+// rnnlogic_b200 -- the PNA aggregator of PredictorPlus (FuncToNode, src/layers.py:89-126; the shipped WN18RR config)
+// on candidate cells: per-cell statistics from the item list, the scaler / Linear(12H,H) front, and their backward
+// into the rule embeddings and the 16 x 192 weight.  H = 16.  The LayerNorm -> ReLU -> MLP tail is rl_tail2.cu with
+// front_done = 1.
+//
+//   degree = sum_rule count + 1                                   (layers.py:92)
+//   mean = S1 / degree, S1 = sum count * emb;  sq_mean = S2 / degree, S2 = sum count * emb^2
+//   mn / mx = min / max of emb over the rules with count != 0     (layers.py:96-99)
+//   std = sqrt(clamp(sq_mean - mean^2, 1e-6))
+//   s = log(degree) / mean over the query's cells of log(degree);  scalers = [1, s, 1/clamp(s)]   (layers.py:109-116)
+//   y = W [mean, mn, mx, std] (x) scalers + b                     (layers.py:118-124: Linear(12H, H))
+//
+// The statistics are accumulated by one thread per (item, quarter of the hidden vector) with vector atomics; min / max
+// carry the rule in the low word of a 64-bit key (order-preserving float key << 32 | rule tag), so the arg rule of the
+// backward -- the FIRST rule in rule-file order on ties, like torch.min / max -- falls out of the same atomic.
+#include "rl_device.cuh"
+
+#define PH 16                 // hidden_dim
+#define PF 64                 // features per cell: mean | min | max | std
+#define PU 192                // inputs of the Linear: feature f, scaler t -> f*3 + t
+#define PNA_BLOCKS 16
+
+__device__ __forceinline__ unsigned pkey(float v)
+{
+    const unsigned b = __float_as_uint(v);
+    return (b & 0x80000000u) ? ~b : (b | 0x80000000u);
+}
+__device__ __forceinline__ float pkey_inv(unsigned k)
+{
+    return __uint_as_float((k & 0x80000000u) ? (k & 0x7fffffffu) : ~k);
+}
+
+__device__ __forceinline__ void pna_add(const rl_pna &p, long long cell, int part, float v, const float4 e4, int rule)
+{
+    atomicAdd(reinterpret_cast<float4 *>(p.s1 + cell * PH) + part, make_float4(v * e4.x, v * e4.y, v * e4.z, v * e4.w));
+    atomicAdd(reinterpret_cast<float4 *>(p.s2 + cell * PH) + part,
+              make_float4(v * (e4.x * e4.x), v * (e4.y * e4.y), v * (e4.z * e4.z), v * (e4.w * e4.w)));
+    if (part == 0) atomicAdd(p.deg + cell, v);
+    const float ev[4] = {e4.x, e4.y, e4.z, e4.w};
+    const unsigned long long lo_min = (unsigned)rule, lo_max = 0xffffffffu - (unsigned)rule;   // ties: the first rule wins both
+#pragma unroll
+    for (int u = 0; u < 4; ++u) {
+        const unsigned long long k = (unsigned long long)pkey(ev[u]) << 32;
+        atomicMin(p.mnk + cell * PH + part * 4 + u, k | lo_min);
+        atomicMax(p.mxk + cell * PH + part * 4 + u, k | lo_max);
+    }
+}
+
+template <typename CT>
+__global__ void __launch_bounds__(256)
+k_pna_item_stats(rl_graph g, rl_rules r, rl_slots s, rl_frontier fr, rl_cells c, const float *__restrict__ emb, rl_pna p)
+{
+    const int slot = blockIdx.y;
+    const int n = fr.item_cnt[slot];
+    const long long ib = fr.item_off[slot];
+    const int4 *items = reinterpret_cast<const int4 *>(fr.items) + ib;
+    const uint32_t *masks = fr.item_mask + ib;
+    const CT *arena = reinterpret_cast<const CT *>(fr.arena) + (size_t)s.arena_off[slot] * RL_LANES;
+    const size_t srow = (size_t)slot * g.num_entities;
+    const int part = threadIdx.x & 3;
+    for (int i = (blockIdx.x * 256 + threadIdx.x) >> 2; i < n; i += PNA_BLOCKS * 64) {
+        const uint32_t m0 = __ldg(masks + i);
+        if (!m0) continue;
+        const int4 it = __ldg(items + i);                         // {row, first rule end, entity, rule ends}
+        const uint32_t bits = c.nzmask[srow + it.z];
+        const int off = c.cand_off[srow + it.z];
+        const CT *row = arena + (size_t)it.x * RL_LANES;
+        for (int t = it.y; t < it.y + it.w; ++t) {
+            const int rule = __ldg(r.node_term_rule + t);
+            const float4 e4 = __ldg(reinterpret_cast<const float4 *>(emb + (size_t)rule * PH) + part);
+            for (uint32_t m = m0; m; m &= m - 1) {
+                const int b = __ffs(m) - 1;
+                const long long cell = off + __popc(bits & ((1u << b) - 1u));
+                if (cell < c.cap) pna_add(p, cell, part, (float)row[b], e4, rule);
+            }
+        }
+    }
+}
+
+// empty-body rules: count = one_hot(h) at the cell (h_b, b)
+__global__ void __launch_bounds__(128)
+k_pna_zr_stats(rl_graph g, rl_rules r, rl_slots s, rl_cells c, const float *__restrict__ emb, rl_pna p)
+{
+    const int slot = blockIdx.x, b = threadIdx.x >> 2, part = threadIdx.x & 3;
+    const int q = s.slot_head[slot];
+    const int z0 = r.zr_ptr[q], z1 = r.zr_ptr[q + 1];
+    if (z1 <= z0) return;
+    const int h = s.lane_h[slot * RL_LANES + b];
+    if (h < 0) return;
+    const size_t srow = (size_t)slot * g.num_entities;
+    const uint32_t bits = c.nzmask[srow + h];
+    const long long cell = c.cand_off[srow + h] + __popc(bits & ((1u << b) - 1u));
+    if (cell >= c.cap) return;
+    for (int t = z0; t < z1; ++t) {
+        const int rule = r.zr_rule[t];
+        pna_add(p, cell, part, 1.f, __ldg(reinterpret_cast<const float4 *>(emb + (size_t)rule * PH) + part), rule);
+    }
+}
+
+// per-query sum and count of log(degree) over the query's cells (layers.py:109-113)
+__global__ void __launch_bounds__(256)
+k_pna_qscale(rl_cells c, rl_pna p, float *__restrict__ qlog, float *__restrict__ qn)
+{
+    const int n = min(c.counters[0], c.cap);
+    for (int i = blockIdx.x * 256 + threadIdx.x; i < n; i += gridDim.x * 256) {
+        const int key = c.cell_key[i];
+        atomicAdd(qlog + key, logf(p.deg[i] + 1.f));
+        atomicAdd(qn + key, 1.f);
+    }
+}
+
+// shared-memory weight layout of the front kernels: Wt[f][t][i] so that the 16 outputs of (f, t) are one 64-byte run
+__device__ __forceinline__ void stage_pna_w(float *sm, const float *__restrict__ W, int tid, int nthreads)
+{
+    for (int x = tid; x < PH * PU; x += nthreads) {               // W[i][f*3+t] row-major [16][192]
+        const int i = x / PU, ft = x % PU;
+        sm[ft * PH + i] = W[x];
+    }
+}
+
+// features of one cell into registers; returns the scaler s
+__device__ __forceinline__ float pna_features(const rl_cells &c, const rl_pna &p, long long cell, const float *__restrict__ qlog,
+                                              const float *__restrict__ qn, float (&feat)[PF])
+{
+    const float deg1 = p.deg[cell] + 1.f;
+    const float dcl = fmaxf(deg1, 1e-6f);
+#pragma unroll
+    for (int h = 0; h < PH; ++h) {
+        const float mean = p.s1[cell * PH + h] / dcl;
+        const float sqm = p.s2[cell * PH + h] / dcl;
+        feat[h] = mean;
+        feat[PH + h] = pkey_inv((unsigned)(p.mnk[cell * PH + h] >> 32));
+        feat[2 * PH + h] = pkey_inv((unsigned)(p.mxk[cell * PH + h] >> 32));
+        feat[3 * PH + h] = sqrtf(fmaxf(sqm - mean * mean, 1e-6f));
+    }
+    const int key = c.cell_key[cell];
+    const float msc = qlog[key] / fmaxf(qn[key], 1e-6f);
+    return logf(deg1) / fmaxf(msc, 1e-6f);
+}
+
+__global__ void __launch_bounds__(256)
+k_pna_front_fwd(rl_cells c, rl_pna p, const float *__restrict__ qlog, const float *__restrict__ qn,
+                const float *__restrict__ W, const float *__restrict__ bvec, float *__restrict__ Y,
+                float *__restrict__ FEAT, float *__restrict__ SC)
+{
+    extern __shared__ __align__(16) float sm[];
+    const long long C = min(c.counters[0], c.cap);
+    if ((long long)blockIdx.x * 256 >= C) return;
+    stage_pna_w(sm, W, threadIdx.x, 256);
+    __syncthreads();
+    for (long long cell = (long long)blockIdx.x * 256 + threadIdx.x; cell < C; cell += (long long)gridDim.x * 256) {
+        float feat[PF];
+        const float sc = pna_features(c, p, cell, qlog, qn, feat);
+        const float isc = 1.f / fmaxf(sc, 1e-6f);
+        float y[PH];
+#pragma unroll
+        for (int i = 0; i < PH; ++i) y[i] = __ldg(bvec + i);
+#pragma unroll 4
+        for (int f = 0; f < PF; ++f) {
+            const float fa = feat[f], fb = feat[f] * sc, fc = feat[f] * isc;
+            const float4 *w0 = reinterpret_cast<const float4 *>(sm + (f * 3) * PH);
+#pragma unroll
+            for (int i4 = 0; i4 < PH / 4; ++i4) {
+                const float4 a = w0[i4], b = w0[PH / 4 + i4], d = w0[2 * (PH / 4) + i4];
+                y[4 * i4] = fmaf(fc, d.x, fmaf(fb, b.x, fmaf(fa, a.x, y[4 * i4])));
+                y[4 * i4 + 1] = fmaf(fc, d.y, fmaf(fb, b.y, fmaf(fa, a.y, y[4 * i4 + 1])));
+                y[4 * i4 + 2] = fmaf(fc, d.z, fmaf(fb, b.z, fmaf(fa, a.z, y[4 * i4 + 2])));
+                y[4 * i4 + 3] = fmaf(fc, d.w, fmaf(fb, b.w, fmaf(fa, a.w, y[4 * i4 + 3])));
+            }
+        }
+        float4 *yo = reinterpret_cast<float4 *>(Y + cell * PH);
+#pragma unroll
+        for (int i4 = 0; i4 < PH / 4; ++i4) yo[i4] = make_float4(y[4 * i4], y[4 * i4 + 1], y[4 * i4 + 2], y[4 * i4 + 3]);
+        float4 *fo = reinterpret_cast<float4 *>(FEAT + cell * PF);
+#pragma unroll
+        for (int f4 = 0; f4 < PF / 4; ++f4) fo[f4] = make_float4(feat[4 * f4], feat[4 * f4 + 1], feat[4 * f4 + 2], feat[4 * f4 + 3]);
+        SC[cell] = sc;
+    }
+}
+
+// dstat[cell] = [dS1 16 | dS2 16 | dMN 16 | dMX 16] from dy = dloss/dy
+__global__ void __launch_bounds__(256)
+k_pna_front_bwd(rl_cells c, rl_pna p, const float *__restrict__ W, const float *__restrict__ dY,
+                const float *__restrict__ FEAT, const float *__restrict__ SC, float *__restrict__ dstat)
+{
+    extern __shared__ __align__(16) float sm[];
+    const long long C = min(c.counters[0], c.cap);
+    if ((long long)blockIdx.x * 256 >= C) return;
+    stage_pna_w(sm, W, threadIdx.x, 256);
+    __syncthreads();
+    for (long long cell = (long long)blockIdx.x * 256 + threadIdx.x; cell < C; cell += (long long)gridDim.x * 256) {
+        float dy[PH];
+        const float4 *dp = reinterpret_cast<const float4 *>(dY + cell * PH);
+#pragma unroll
+        for (int i4 = 0; i4 < PH / 4; ++i4) {
+            const float4 v = __ldg(dp + i4);
+            dy[4 * i4] = v.x; dy[4 * i4 + 1] = v.y; dy[4 * i4 + 2] = v.z; dy[4 * i4 + 3] = v.w;
+        }
+        const float sc = SC[cell], isc = 1.f / fmaxf(sc, 1e-6f);
+        const float deg1 = fmaxf(p.deg[cell] + 1.f, 1e-6f);
+        float *out = dstat + cell * PF;
+        for (int h = 0; h < PH; ++h) {
+            float df[4];                                         // gradient of feature (kind k, unit h), k = mean | min | max | std
+#pragma unroll
+            for (int k = 0; k < 4; ++k) {
+                const int f = k * PH + h;
+                const float4 *w0 = reinterpret_cast<const float4 *>(sm + (f * 3) * PH);
+                float a = 0.f, b = 0.f, d = 0.f;
+#pragma unroll
+                for (int i4 = 0; i4 < PH / 4; ++i4) {
+                    const float4 wa = w0[i4], wb = w0[PH / 4 + i4], wd = w0[2 * (PH / 4) + i4];
+                    a = fmaf(dy[4 * i4], wa.x, a); a = fmaf(dy[4 * i4 + 1], wa.y, a); a = fmaf(dy[4 * i4 + 2], wa.z, a); a = fmaf(dy[4 * i4 + 3], wa.w, a);
+                    b = fmaf(dy[4 * i4], wb.x, b); b = fmaf(dy[4 * i4 + 1], wb.y, b); b = fmaf(dy[4 * i4 + 2], wb.z, b); b = fmaf(dy[4 * i4 + 3], wb.w, b);
+                    d = fmaf(dy[4 * i4], wd.x, d); d = fmaf(dy[4 * i4 + 1], wd.y, d); d = fmaf(dy[4 * i4 + 2], wd.z, d); d = fmaf(dy[4 * i4 + 3], wd.w, d);
+                }
+                df[k] = a + sc * b + isc * d;
+            }
+            const float mean = FEAT[cell * PF + h], stdv = FEAT[cell * PF + 3 * PH + h];
+            const float var = p.s2[cell * PH + h] / deg1 - mean * mean;              // the forward's expression, bit for bit
+            const float dv = var >= 1e-6f ? df[3] / (2.f * stdv) : 0.f;              // clamp(min=1e-6) passes the gradient where v >= 1e-6
+            out[h] = (df[0] - 2.f * mean * dv) / deg1;            // dS1
+            out[PH + h] = dv / deg1;                              // dS2
+            out[2 * PH + h] = df[1];                              // dMN
+            out[3 * PH + h] = df[2];                              // dMX
+        }
+    }
+}
+
+// gW[i][f*3+t] += sum_cells dy_i * feat_f * scaler_t: thread = (unit i, group of 4 features), 12 accumulators in registers
+__global__ void __launch_bounds__(256)
+k_pna_w_grad(rl_cells c, const float *__restrict__ dY, const float *__restrict__ FEAT, const float *__restrict__ SC,
+             float *__restrict__ gW)
+{
+    __shared__ __align__(16) float s_dy[32][PH];
+    __shared__ __align__(16) float s_ft[32][PF];
+    __shared__ float s_sc[32], s_isc[32];
+    const long long C = min(c.counters[0], c.cap);
+    const int tid = threadIdx.x, i = tid & 15, fg = tid >> 4;    // features 4*fg .. 4*fg+3
+    float acc[12];
+#pragma unroll
+    for (int k = 0; k < 12; ++k) acc[k] = 0.f;
+    for (long long base = (long long)blockIdx.x * 32; base < C; base += (long long)gridDim.x * 32) {
+        const int nc = (int)min(32LL, C - base);
+        __syncthreads();
+        for (int x = tid; x < 32 * PH / 4; x += 256)
+            reinterpret_cast<float4 *>(&s_dy[0][0])[x] = (x >> 2) < nc ? __ldg(reinterpret_cast<const float4 *>(dY + base * PH) + x)
+                                                                      : make_float4(0.f, 0.f, 0.f, 0.f);
+        for (int x = tid; x < 32 * PF / 4; x += 256)
+            reinterpret_cast<float4 *>(&s_ft[0][0])[x] = (x >> 4) < nc ? __ldg(reinterpret_cast<const float4 *>(FEAT + base * PF) + x)
+                                                                      : make_float4(0.f, 0.f, 0.f, 0.f);
+        if (tid < 32) {
+            const float sc = tid < nc ? SC[base + tid] : 0.f;
+            s_sc[tid] = sc;
+            s_isc[tid] = tid < nc ? 1.f / fmaxf(sc, 1e-6f) : 0.f;
+        }
+        __syncthreads();
+        for (int cl = 0; cl < nc; ++cl) {
+            const float d = s_dy[cl][i], sc = s_sc[cl], isc = s_isc[cl];
+            const float4 f4 = *reinterpret_cast<const float4 *>(&s_ft[cl][4 * fg]);
+            const float fv[4] = {f4.x, f4.y, f4.z, f4.w};
+#pragma unroll
+            for (int u = 0; u < 4; ++u) {
+                const float df = d * fv[u];
+                acc[3 * u] += df;
+                acc[3 * u + 1] = fmaf(df, sc, acc[3 * u + 1]);
+                acc[3 * u + 2] = fmaf(df, isc, acc[3 * u + 2]);
+            }
+        }
+    }
+#pragma unroll
+    for (int k = 0; k < 12; ++k)
+        if (acc[k] != 0.f) atomicAdd(gW + i * PU + (4 * fg) * 3 + k, acc[k]);
+}
+
+// backward into the rule embeddings: gEmb[rule] += count * dS1 + 2 count emb * dS2 (+ dMN / dMX at the arg rules)
+template <typename CT>
+__global__ void __launch_bounds__(256)
+k_pna_item_bwd(rl_graph g, rl_rules r, rl_slots s, rl_frontier fr, rl_cells c, const float *__restrict__ emb, rl_pna p,
+               const float *__restrict__ dstat, float *__restrict__ gEmb)
+{
+    const int slot = blockIdx.y;
+    const int n = fr.item_cnt[slot];
+    const long long ib = fr.item_off[slot];
+    const int4 *items = reinterpret_cast<const int4 *>(fr.items) + ib;
+    const uint32_t *masks = fr.item_mask + ib;
+    const CT *arena = reinterpret_cast<const CT *>(fr.arena) + (size_t)s.arena_off[slot] * RL_LANES;
+    const size_t srow = (size_t)slot * g.num_entities;
+    const int part = threadIdx.x & 3;
+    for (int i = (blockIdx.x * 256 + threadIdx.x) >> 2; i < n; i += PNA_BLOCKS * 64) {
+        const uint32_t m0 = __ldg(masks + i);
+        if (!m0) continue;
+        const int4 it = __ldg(items + i);
+        const uint32_t bits = c.nzmask[srow + it.z];
+        const int off = c.cand_off[srow + it.z];
+        const CT *row = arena + (size_t)it.x * RL_LANES;
+        for (int t = it.y; t < it.y + it.w; ++t) {
+            const int rule = __ldg(r.node_term_rule + t);
+            const float4 e4 = __ldg(reinterpret_cast<const float4 *>(emb + (size_t)rule * PH) + part);
+            const float ev[4] = {e4.x, e4.y, e4.z, e4.w};
+            float a[4] = {0.f, 0.f, 0.f, 0.f};
+            for (uint32_t m = m0; m; m &= m - 1) {
+                const int b = __ffs(m) - 1;
+                const long long cell = off + __popc(bits & ((1u << b) - 1u));
+                if (cell >= c.cap) continue;
+                const float v = (float)row[b];
+                const float *ds = dstat + cell * PF + part * 4;
+#pragma unroll
+                for (int u = 0; u < 4; ++u) {
+                    a[u] += v * ds[u] + 2.f * v * ev[u] * ds[PH + u];
+                    if ((unsigned)p.mnk[cell * PH + part * 4 + u] == (unsigned)rule) a[u] += ds[2 * PH + u];
+                    if ((unsigned)p.mxk[cell * PH + part * 4 + u] == 0xffffffffu - (unsigned)rule) a[u] += ds[3 * PH + u];
+                }
+            }
+            atomicAdd(reinterpret_cast<float4 *>(gEmb + (size_t)rule * PH) + part, make_float4(a[0], a[1], a[2], a[3]));
+        }
+    }
+}
+
+__global__ void __launch_bounds__(128)
+k_pna_zr_bwd(rl_graph g, rl_rules r, rl_slots s, rl_cells c, const float *__restrict__ emb, rl_pna p,
+             const float *__restrict__ dstat, float *__restrict__ gEmb)
+{
+    const int slot = blockIdx.x, b = threadIdx.x >> 2, part = threadIdx.x & 3;
+    const int q = s.slot_head[slot];
+    const int z0 = r.zr_ptr[q], z1 = r.zr_ptr[q + 1];
+    if (z1 <= z0) return;
+    const int h = s.lane_h[slot * RL_LANES + b];
+    if (h < 0) return;
+    const size_t srow = (size_t)slot * g.num_entities;
+    const uint32_t bits = c.nzmask[srow + h];
+    const long long cell = c.cand_off[srow + h] + __popc(bits & ((1u << b) - 1u));
+    if (cell >= c.cap) return;
+    const float *ds = dstat + cell * PF + part * 4;
+    for (int t = z0; t < z1; ++t) {
+        const int rule = r.zr_rule[t];
+        const float4 e4 = __ldg(reinterpret_cast<const float4 *>(emb + (size_t)rule * PH) + part);
+        const float ev[4] = {e4.x, e4.y, e4.z, e4.w};
+        float a[4];
+#pragma unroll
+        for (int u = 0; u < 4; ++u) {
+            a[u] = ds[u] + 2.f * ev[u] * ds[PH + u];
+            if ((unsigned)p.mnk[cell * PH + part * 4 + u] == (unsigned)rule) a[u] += ds[2 * PH + u];
+            if ((unsigned)p.mxk[cell * PH + part * 4 + u] == 0xffffffffu - (unsigned)rule) a[u] += ds[3 * PH + u];
+        }
+        atomicAdd(reinterpret_cast<float4 *>(gEmb + (size_t)rule * PH) + part, make_float4(a[0], a[1], a[2], a[3]));
+    }
+}
+
+static int bad_pna(const rl_cells *c, const rl_pna *p)
+{
+    return !c || !c->counters || !c->nzmask || !c->cand_off || !c->cell_key || c->cap <= 0 || !p || !p->s1 || !p->s2 || !p->deg ||
+           !p->mnk || !p->mxk;
+}
+static int bad_items(const rl_frontier *fr)
+{
+    return !fr || !fr->arena || !fr->items || !fr->item_off || !fr->item_cnt || !fr->item_mask ||
+           (fr->count_bits != 32 && fr->count_bits != 64);
+}
+static int cell_grid(const rl_cells *c)
+{
+    const long long b = ((long long)c->cap + 255) / 256;
+    return (int)(b < 148 * 8 ? b : 148 * 8);
+}
+
+extern "C" {
+
+int rl_pna_item_stats(const rl_graph *g, const rl_rules *r, const rl_slots *s, const rl_frontier *fr, const rl_cells *c,
+                      const float *emb, const rl_pna *p, void *stream)
+{
+    if (!g || !r || !s || !emb || bad_pna(c, p) || bad_items(fr)) return rl_fail(RL_ERR_ARG, "rl_pna_item_stats: bad argument");
+    if (s->num_slots <= 0) return RL_OK;
+    cudaStream_t st = (cudaStream_t)stream;
+    const size_t n = (size_t)c->cap;
+    if (cudaMemsetAsync(p->s1, 0, n * PH * 4, st) != cudaSuccess || cudaMemsetAsync(p->s2, 0, n * PH * 4, st) != cudaSuccess ||
+        cudaMemsetAsync(p->deg, 0, n * 4, st) != cudaSuccess || cudaMemsetAsync(p->mnk, 0xff, n * PH * 8, st) != cudaSuccess ||
+        cudaMemsetAsync(p->mxk, 0, n * PH * 8, st) != cudaSuccess)
+        return rl_fail(RL_ERR_CUDA, "rl_pna_item_stats: memset", cudaGetLastError());
+    const dim3 grid(PNA_BLOCKS, s->num_slots);
+    if (fr->count_bits == 32) k_pna_item_stats<uint32_t><<<grid, 256, 0, st>>>(*g, *r, *s, *fr, *c, emb, *p);
+    else k_pna_item_stats<unsigned long long><<<grid, 256, 0, st>>>(*g, *r, *s, *fr, *c, emb, *p);
+    CHECK_LAUNCH("k_pna_item_stats");
+    if (r->num_zero_rules > 0) {
+        k_pna_zr_stats<<<s->num_slots, 128, 0, st>>>(*g, *r, *s, *c, emb, *p);
+        CHECK_LAUNCH("k_pna_zr_stats");
+    }
+    return RL_OK;
+}
+
+/* qscr: 2 * S * 32 floats of scratch; Y[cap][16] = Linear(12H,H) output (before LayerNorm), FEAT[cap][64], SC[cap] */
+int rl_pna_front_forward(const rl_slots *s, const rl_cells *c, const rl_pna *p, const float *W, const float *b, float *qscr,
+                         float *Y, float *FEAT, float *SC, void *stream)
+{
+    if (!s || bad_pna(c, p) || !W || !b || !qscr || !Y || !FEAT || !SC) return rl_fail(RL_ERR_ARG, "rl_pna_front_forward: bad argument");
+    if (s->num_slots <= 0) return RL_OK;
+    cudaStream_t st = (cudaStream_t)stream;
+    const size_t nq = (size_t)s->num_slots * RL_LANES;
+    if (cudaMemsetAsync(qscr, 0, 2 * nq * sizeof(float), st) != cudaSuccess) return rl_fail(RL_ERR_CUDA, "rl_pna_front_forward: memset", cudaGetLastError());
+    k_pna_qscale<<<cell_grid(c), 256, 0, st>>>(*c, *p, qscr, qscr + nq);
+    CHECK_LAUNCH("k_pna_qscale");
+    const size_t smem = (size_t)PH * PU * sizeof(float);
+    k_pna_front_fwd<<<cell_grid(c), 256, smem, st>>>(*c, *p, qscr, qscr + nq, W, b, Y, FEAT, SC);
+    CHECK_LAUNCH("k_pna_front_fwd");
+    return RL_OK;
+}
+
+/* dstat[cap][64] scratch; gW[16][192] is ACCUMULATED (the bias gradient comes from rl_tail_backward's gb0) */
+int rl_pna_front_backward(const rl_cells *c, const rl_pna *p, const float *W, const float *dY, const float *FEAT,
+                          const float *SC, float *dstat, float *gW, void *stream)
+{
+    if (bad_pna(c, p) || !W || !dY || !FEAT || !SC || !dstat || !gW) return rl_fail(RL_ERR_ARG, "rl_pna_front_backward: bad argument");
+    cudaStream_t st = (cudaStream_t)stream;
+    const size_t smem = (size_t)PH * PU * sizeof(float);
+    k_pna_front_bwd<<<cell_grid(c), 256, smem, st>>>(*c, *p, W, dY, FEAT, SC, dstat);
+    CHECK_LAUNCH("k_pna_front_bwd");
+    k_pna_w_grad<<<148 * 2, 256, 0, st>>>(*c, dY, FEAT, SC, gW);
+    CHECK_LAUNCH("k_pna_w_grad");
+    return RL_OK;
+}
+
+int rl_pna_item_backward(const rl_graph *g, const rl_rules *r, const rl_slots *s, const rl_frontier *fr, const rl_cells *c,
+                         const float *emb, const rl_pna *p, const float *dstat, float *grad_emb, void *stream)
+{
+    if (!g || !r || !s || !emb || !dstat || !grad_emb || bad_pna(c, p) || bad_items(fr)) return rl_fail(RL_ERR_ARG, "rl_pna_item_backward: bad argument");
+    if (s->num_slots <= 0) return RL_OK;
+    cudaStream_t st = (cudaStream_t)stream;
+    const dim3 grid(PNA_BLOCKS, s->num_slots);
+    if (fr->count_bits == 32) k_pna_item_bwd<uint32_t><<<grid, 256, 0, st>>>(*g, *r, *s, *fr, *c, emb, *p, dstat, grad_emb);
+    else k_pna_item_bwd<unsigned long long><<<grid, 256, 0, st>>>(*g, *r, *s, *fr, *c, emb, *p, dstat, grad_emb);
+    CHECK_LAUNCH("k_pna_item_bwd");
+    if (r->num_zero_rules > 0) {
+        k_pna_zr_bwd<<<s->num_slots, 128, 0, st>>>(*g, *r, *s, *c, emb, *p, dstat, grad_emb);
+        CHECK_LAUNCH("k_pna_zr_bwd");
+    }
+    return RL_OK;
+}
+
+}  // extern "C"

@@ -44,11 +44,17 @@ struct TailP { const float *W0, *b0, *gamma, *beta, *W1, *b1, *W2, *b2, *rel; };
 #define SC_END (SC_ACC + 3 * TH + 4)
 
 // front of one cell in registers: y = W0 f + b0, LayerNorm statistics; returns 1/std, fills nrm[]
+template <bool PRE>
 __device__ __forceinline__ float cell_front(const float *sm, const float (&f)[TH], float (&nrm)[TH])
 {
     float mean = 0.f;
 #pragma unroll
     for (int i = 0; i < TH; ++i) {
+        if (PRE) {                                               // the aggregator's Linear was applied by its own front kernel (PNA)
+            nrm[i] = f[i];
+            mean += f[i];
+            continue;
+        }
         float a = sm[SC_B0 + i];
         const float4 *wr = reinterpret_cast<const float4 *>(sm + SC_W0 + i * TH);
 #pragma unroll
@@ -81,6 +87,7 @@ __device__ __forceinline__ void load_row16(const float *__restrict__ p, float (&
     }
 }
 
+template <bool PRE>
 __global__ void __launch_bounds__(256, 2)
 k_tailc_fwd(const int32_t *__restrict__ counters, int cap, const float *__restrict__ F, const int32_t *__restrict__ cell_key,
             const int32_t *__restrict__ slot_head, TailP w, float *__restrict__ zc, float *__restrict__ O,
@@ -98,7 +105,7 @@ k_tailc_fwd(const int32_t *__restrict__ counters, int cap, const float *__restri
     for (long long cell = (long long)blockIdx.x * 256 + threadIdx.x; cell < C; cell += (long long)gridDim.x * 256) {
         float f[TH], nrm[TH], u[TK];
         load_row16(F + cell * TH, f);
-        cell_front(sm, f, nrm);
+        cell_front<PRE>(sm, f, nrm);
 #pragma unroll
         for (int i = 0; i < TH; ++i) u[i] = fmaxf(fmaf(sm[SC_GA + i], nrm[i], sm[SC_BE + i]), 0.f);
         float4 *op = reinterpret_cast<float4 *>(O + cell * TH);
@@ -142,6 +149,7 @@ k_tailc_fwd(const int32_t *__restrict__ counters, int cap, const float *__restri
     }
 }
 
+template <bool PRE>
 __global__ void __launch_bounds__(256, 2)
 k_tailc_bwd_cells(const int32_t *__restrict__ counters, int cap, const float *__restrict__ F, TailP w,
                   const float *__restrict__ Gc, const uint4 *__restrict__ bits, float *__restrict__ dF,
@@ -170,7 +178,7 @@ k_tailc_bwd_cells(const int32_t *__restrict__ counters, int cap, const float *__
 #pragma unroll
             for (int k = 0; k < TH; ++k) f[k] = 0.f;
         }
-        const float rstd = cell_front(sm, f, nrm);
+        const float rstd = cell_front<PRE>(sm, f, nrm);
         const float gq = live ? Gc[cell] : 0.f;
         const uint4 bw = live ? bits[cell] : make_uint4(0u, 0u, 0u, 0u);
         const uint32_t word[4] = {bw.x, bw.y, bw.z, bw.w};
@@ -232,7 +240,7 @@ k_tailc_bwd_cells(const int32_t *__restrict__ counters, int cap, const float *__
             float4 *o1 = reinterpret_cast<float4 *>(dF + cell * TH), *o2 = reinterpret_cast<float4 *>(dY + cell * TH);
 #pragma unroll
             for (int k4 = 0; k4 < TH / 4; ++k4) {
-                o1[k4] = make_float4(dx[4 * k4], dx[4 * k4 + 1], dx[4 * k4 + 2], dx[4 * k4 + 3]);
+                if (!PRE) o1[k4] = make_float4(dx[4 * k4], dx[4 * k4 + 1], dx[4 * k4 + 2], dx[4 * k4 + 3]);
                 o2[k4] = make_float4(dn[4 * k4], dn[4 * k4 + 1], dn[4 * k4 + 2], dn[4 * k4 + 3]);
             }
         }
@@ -379,7 +387,8 @@ k_tailc_bwd_weights(const int32_t *__restrict__ counters, int cap, const float *
         if (v != 0.f) atomicAdd(Vg + (4 * l + jj) * TK + k, v);
     }
     for (int i = threadIdx.x; i < TJ; i += TW * 32) if (sm[SW_P + i] != 0.f) atomicAdd(Pg + i, sm[SW_P + i]);
-    for (int i = threadIdx.x; i < TH * TH; i += TW * 32) if (sm[SW_W0 + i] != 0.f) atomicAdd(gW0 + i, sm[SW_W0 + i]);
+    if (gW0)
+        for (int i = threadIdx.x; i < TH * TH; i += TW * 32) if (sm[SW_W0 + i] != 0.f) atomicAdd(gW0 + i, sm[SW_W0 + i]);
 }
 
 // dW1, db1, dW2 from V and P (one block, thread j)
@@ -432,7 +441,7 @@ int64_t rl_tail_scratch_floats(int32_t R) { return (int64_t)TK * TJ + TJ + (int6
 int rl_tail_forward(const rl_cells *c, const int32_t *slot_head, int32_t H, int32_t J, const float *F, const float *W0,
                     const float *b0, const float *gamma, const float *beta, const float *W1, const float *b1,
                     const float *W2, const float *b2, const float *rel_emb, float *zc, float *O, uint32_t *relu_bits,
-                    void *stream)
+                    int32_t front_done, void *stream)
 {
     if (!c || !c->counters || !c->cell_key || !slot_head || !F || !W0 || !b0 || !gamma || !beta || !W1 || !b1 || !W2 || !b2 ||
         !rel_emb || !zc || !O || !relu_bits)
@@ -441,11 +450,17 @@ int rl_tail_forward(const rl_cells *c, const int32_t *slot_head, int32_t H, int3
     TailP w{W0, b0, gamma, beta, W1, b1, W2, b2, rel_emb};
     const size_t smem = (size_t)SC_END * sizeof(float);
     static bool attr = false;
-    if (!attr) { cudaFuncSetAttribute(k_tailc_fwd, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem); attr = true; }
+    if (!attr) {
+        cudaFuncSetAttribute(k_tailc_fwd<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        cudaFuncSetAttribute(k_tailc_fwd<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        attr = true;
+    }
     const long long want = ((long long)c->cap + 255) / 256;
     const int grid = (int)(want < 4LL * sm_count() ? want : 4LL * sm_count());
-    k_tailc_fwd<<<grid, 256, smem, (cudaStream_t)stream>>>(c->counters, c->cap, F, c->cell_key, slot_head, w, zc, O,
-                                                          reinterpret_cast<uint4 *>(relu_bits));
+    if (front_done) k_tailc_fwd<true><<<grid, 256, smem, (cudaStream_t)stream>>>(c->counters, c->cap, F, c->cell_key, slot_head, w, zc, O,
+                                                                                 reinterpret_cast<uint4 *>(relu_bits));
+    else k_tailc_fwd<false><<<grid, 256, smem, (cudaStream_t)stream>>>(c->counters, c->cap, F, c->cell_key, slot_head, w, zc, O,
+                                                                       reinterpret_cast<uint4 *>(relu_bits));
     CHECK_LAUNCH("k_tailc_fwd");
     return RL_OK;
 }
@@ -456,10 +471,10 @@ int rl_tail_backward(const rl_cells *c, const int32_t *slot_head, int32_t R, int
                      const float *b1, const float *W2, const float *b2, const float *rel_emb, const float *Gc,
                      const float *O, const uint32_t *relu_bits, float *dF, float *dY, float *gW0, float *gb0,
                      float *ggamma, float *gbeta, float *gW1, float *gb1, float *gW2, float *gb2, float *grel,
-                     float *scratch, void *stream)
+                     float *scratch, int32_t front_done, void *stream)
 {
     if (!c || !c->counters || !c->cell_key || !slot_head || !F || !W0 || !b0 || !gamma || !beta || !W1 || !b1 || !W2 || !b2 || !rel_emb ||
-        !Gc || !O || !relu_bits || !dF || !dY || !gW0 || !gb0 || !ggamma || !gbeta || !gW1 || !gb1 || !gW2 || !gb2 || !grel || !scratch || R <= 0)
+        !Gc || !O || !relu_bits || (!front_done && (!dF || !gW0)) || !dY || !gb0 || !ggamma || !gbeta || !gW1 || !gb1 || !gW2 || !gb2 || !grel || !scratch || R <= 0)
         return rl_fail(RL_ERR_ARG, "rl_tail_backward: null argument");
     if (H != TH || J != TJ) return rl_fail(RL_ERR_ARG, "rl_tail_backward: built for hidden_dim 16 and a 128-wide score MLP");
     cudaStream_t st = (cudaStream_t)stream;
@@ -472,16 +487,18 @@ int rl_tail_backward(const rl_cells *c, const int32_t *slot_head, int32_t R, int
     const size_t smem_b = (size_t)(SW_END + TW * WS_END) * sizeof(float);
     static bool attr = false;
     if (!attr) {
-        cudaFuncSetAttribute(k_tailc_bwd_cells, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_a);
+        cudaFuncSetAttribute(k_tailc_bwd_cells<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_a);
+        cudaFuncSetAttribute(k_tailc_bwd_cells<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_a);
         cudaFuncSetAttribute(k_tailc_bwd_weights, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_b);
         attr = true;
     }
     const long long want = ((long long)c->cap + 255) / 256;
     const int grid = (int)(want < 4LL * sm_count() ? want : 4LL * sm_count());
-    k_tailc_bwd_cells<<<grid, 256, smem_a, st>>>(c->counters, c->cap, F, w, Gc, bits4, dF, dY, gb0, ggamma, gbeta, gb2);
+    if (front_done) k_tailc_bwd_cells<true><<<grid, 256, smem_a, st>>>(c->counters, c->cap, F, w, Gc, bits4, dY, dY, gb0, ggamma, gbeta, gb2);
+    else k_tailc_bwd_cells<false><<<grid, 256, smem_a, st>>>(c->counters, c->cap, F, w, Gc, bits4, dF, dY, gb0, ggamma, gbeta, gb2);
     CHECK_LAUNCH("k_tailc_bwd_cells");
     k_tailc_bwd_weights<<<sm_count(), TW * 32, smem_b, st>>>(c->counters, c->cap, F, O, dY, Gc, bits4, c->cell_key, slot_head,
-                                                              rel_emb, Vg, Pg, Phg, gW0);
+                                                              rel_emb, Vg, Pg, Phg, front_done ? nullptr : gW0);
     CHECK_LAUNCH("k_tailc_bwd_weights");
     k_tailc_finish<<<1, TJ, 0, st>>>(W1, b1, W2, Vg, Pg, gW1, gb1, gW2);
     CHECK_LAUNCH("k_tailc_finish");

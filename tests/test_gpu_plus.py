@@ -1,6 +1,6 @@
 """GPU parity of PredictorPlus (emb/lstm/gru/rnn x sum/pna x bias/none/RotatE) against the
 reference's golden outputs: scores rtol 1e-4 (the reference itself sums [C,R_q,H] broadcasts in a
-different order), loss rtol 1e-5, every parameter gradient rtol 1e-3 (atol 3e-4 of the tensor's max)."""
+different order), loss rtol 1e-5, every parameter gradient within 1e-4 of the tensor's scale (+ rtol 1e-3)."""
 import numpy as np
 import pytest
 import torch
@@ -54,7 +54,9 @@ def check_grads(m, fx, tag, j, name):
     # 'emb' variants reproduce the reference to ~1e-7.  RNN rule encoders differ by ~1e-6 between cuDNN
     # and the CPU reference, enough to flip one ReLU of one candidate (of thousands) per batch now and
     # then, which perturbs every upstream gradient by ~1e-3 of its scale.
-    base, frac = (3e-4, 0.99) if cfg["type"] == "emb" else (5e-3, 0.85)
+    # measured margins of the cell path (scripts/parity_margins.py -> profiles/r2_parity_margins.txt): every element within
+    # 2e-5 of the tensor's scale for emb / lstm x sum / pna x bias / RotatE; gru / rnn encoders run on cuDNN
+    base, frac = (1e-4, 1.0) if cfg["type"] in ("emb", "lstm") else (1e-3, 0.99)
     for pn, par in m.named_parameters():
         key = "%s_tb%d_g_%s" % (tag, j, pn)
         if key in fx:
