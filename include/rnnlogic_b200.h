@@ -393,7 +393,7 @@ int rl_slot_to_dense(int32_t N, int32_t nq, const float *Z_slot, float *out, int
 int rl_mask_to_dense(int32_t N, int32_t nq, const uint32_t *nzmask_slot, uint8_t *out,
                      int64_t out_stride, void *stream);
 
-/* ---- the scoring half on candidate cells (rl_cells.cu, rl_tail2.cu): no [S][N][32] matrix ---- */
+/* ---- the scoring half on candidate cells (rl_cells.cu, rl_tail_tc.cu): no [S][N][32] matrix ---- */
 
 /* Number the cells: cand_off, cell_key, cell_ent, slot_ncell, counters[0..1] from the candidate words nzmask.  When
  * the frontier carries sort buffers the items are grouped by entity first (rl_sort_items, which ORs their lane
@@ -460,23 +460,24 @@ int rl_plus_item_backward(const rl_graph *g, const rl_rules *r, const rl_slots *
 int rl_plus_cell_backward(const rl_graph *g, const rl_rules *r, const rl_slots *s, const rl_frontier *fr,
                           const rl_cells *c, int32_t H, const float *dF, float *grad_emb, void *stream);
 
-/* Dense tail of PredictorPlus with the sum aggregator on the cells (src/layers.py:73-75,
- * src/predictors.py:253-255), H = 16, J = 128: zc[cell] = W2 . relu(W1 [relu(LN(W0 F + b0)), rel[head]] + b1) + b2.
- * The forward also leaves O[cell][16] (the front's output) and relu_bits[cell][4] (which hidden units are active);
- * the backward uses them instead of recomputing the hidden layer, ACCUMULATES every weight gradient in-kernel
- * (layouts of the parameters), writes dF[cell][16] (and dY[cell][16], scratch) and needs
- * rl_tail_scratch_floats(R) floats of scratch. */
+/* Dense tail of PredictorPlus on the cells (src/layers.py:73-75, src/predictors.py:253-255), H = 16, J = 128:
+ * zc[cell] = W2 . relu(W1 [relu(LN(W0 F + b0)), rel[head]] + b1) + b2  (rl_tail_tc.cu).  The Linear(2H,128) of the
+ * score MLP and both of its backward products run on the tensor cores (tcgen05.mma, fp32 accumulators in TMEM) with
+ * split operands (3xTF32 forward; exact bf16 x 3 against the 0/1 ReLU-bit matrix backward), so the logits keep the
+ * 1e-5 bar.  The forward leaves relu_bits[cell][4] (which hidden units are active); the backward uses them instead of
+ * recomputing the hidden layer, ACCUMULATES every weight gradient in-kernel (layouts of the parameters), writes
+ * dF[cell][16] and needs rl_tail_scratch_floats(R) floats of scratch. */
 int64_t rl_tail_scratch_floats(int32_t R);
 /* front_done != 0: F already holds the aggregator's Linear output y (the PNA front, rl_pna_front_forward); then W0 is
- * not used, the backward produces dY only (no dF, no gW0) and gb0 still receives sum dy (the Linear's bias). */
+ * not used, the backward writes dY[cell][16] instead of dF (and no gW0); gb0 still receives sum dy (the Linear's bias). */
 int rl_tail_forward(const rl_cells *c, const int32_t *slot_head, int32_t H, int32_t J, const float *F, const float *W0,
                     const float *b0, const float *gamma, const float *beta, const float *W1, const float *b1,
-                    const float *W2, const float *b2, const float *rel_emb, float *zc, float *O, uint32_t *relu_bits,
+                    const float *W2, const float *b2, const float *rel_emb, float *zc, uint32_t *relu_bits,
                     int32_t front_done, void *stream);
 int rl_tail_backward(const rl_cells *c, const int32_t *slot_head, int32_t R, int32_t H, int32_t J, const float *F,
                      const float *W0, const float *b0, const float *gamma, const float *beta, const float *W1,
                      const float *b1, const float *W2, const float *b2, const float *rel_emb, const float *Gc,
-                     const float *O, const uint32_t *relu_bits, float *dF, float *dY, float *gW0, float *gb0,
+                     const uint32_t *relu_bits, float *dF, float *dY, float *gW0, float *gb0,
                      float *ggamma, float *gbeta, float *gW1, float *gb1, float *gW2, float *gb2, float *grel,
                      float *scratch, int32_t front_done, void *stream);
 

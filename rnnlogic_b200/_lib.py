@@ -12,7 +12,7 @@ import subprocess
 _HERE = os.path.dirname(os.path.abspath(__file__))
 ROOT = os.path.dirname(_HERE)
 LIB_PATH = os.environ.get("RNNLOGIC_B200_LIB") or os.path.join(_HERE, "lib", "librnnlogic_b200.so")   # env override: A/B builds
-SOURCES = [os.path.join(_HERE, "csrc", f) for f in ("rl_kernels.cu", "rl_cells.cu", "rl_plus.cu", "rl_rotate.cu", "rl_tail.cu", "rl_tail2.cu", "rl_pna.cu", "rl_rnn.cu")]
+SOURCES = [os.path.join(_HERE, "csrc", f) for f in ("rl_kernels.cu", "rl_cells.cu", "rl_plus.cu", "rl_rotate.cu", "rl_tail.cu", "rl_tail_tc.cu", "rl_pna.cu", "rl_rnn.cu")]
 HEADER = os.path.join(ROOT, "include", "rnnlogic_b200.h")
 
 LANES = 32
@@ -70,7 +70,7 @@ def nvcc_command(out=LIB_PATH):
 def build(force: bool = False) -> str:
     """Compile csrc/*.cu for sm_100a into rnnlogic_b200/lib/ (cross-compiles without a GPU)."""
     os.makedirs(os.path.dirname(LIB_PATH), exist_ok=True)
-    deps = [s for s in SOURCES if os.path.exists(s)] + [HEADER, os.path.join(_HERE, "csrc", "rl_device.cuh")]
+    deps = [s for s in SOURCES if os.path.exists(s)] + [HEADER, os.path.join(_HERE, "csrc", "rl_device.cuh"), os.path.join(_HERE, "csrc", "rl_umma.cuh")]
     stale = force or not os.path.exists(LIB_PATH) or any(
         os.path.getmtime(d) > os.path.getmtime(LIB_PATH) for d in deps)
     if stale:
@@ -180,8 +180,8 @@ _PROTOS = {
     "rl_plus_cell_backward": (C.c_int, [C.POINTER(RlGraph), C.POINTER(RlRules), C.POINTER(RlSlots), C.POINTER(RlFrontier),
                                         C.POINTER(RlCells), C.c_int32, vp, vp, vp]),
     "rl_tail_scratch_floats": (C.c_int64, [C.c_int32]),
-    "rl_tail_forward": (C.c_int, [C.POINTER(RlCells), vp, C.c_int32, C.c_int32] + [vp] * 13 + [C.c_int32, vp]),
-    "rl_tail_backward": (C.c_int, [C.POINTER(RlCells), vp, C.c_int32, C.c_int32, C.c_int32] + [vp] * 25 + [C.c_int32, vp]),
+    "rl_tail_forward": (C.c_int, [C.POINTER(RlCells), vp, C.c_int32, C.c_int32] + [vp] * 12 + [C.c_int32, vp]),
+    "rl_tail_backward": (C.c_int, [C.POINTER(RlCells), vp, C.c_int32, C.c_int32, C.c_int32] + [vp] * 24 + [C.c_int32, vp]),
     "rl_pna_item_stats": (C.c_int, [C.POINTER(RlGraph), C.POINTER(RlRules), C.POINTER(RlSlots), C.POINTER(RlFrontier),
                                     C.POINTER(RlCells), vp, C.POINTER(RlPna), vp]),
     "rl_pna_front_forward": (C.c_int, [C.POINTER(RlSlots), C.POINTER(RlCells), C.POINTER(RlPna), vp, vp, vp, vp, vp, vp, vp]),

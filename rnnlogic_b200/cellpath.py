@@ -1,4 +1,4 @@
-"""Fused train / eval steps on candidate cells (csrc/rl_cells.cu, rl_tail2.cu): what TrainerPredictor and
+"""Fused train / eval steps on candidate cells (csrc/rl_cells.cu, rl_tail_tc.cu): what TrainerPredictor and
 bench.py run.  Nothing of size [B,N] is built; no host synchronisation happens inside a step -- the
 candidate count stays on the device (the reference syncs on it four times per batch,
 src/predictors.py:211,230,239, src/layers.py:65) and comes back with the losses in the step's one D2H read.
@@ -106,14 +106,14 @@ class CellKernels:
         _lib.check(_L().rl_plus_item_backward(self.dg.ref(), self.dr.ref(), sl.ref(), sl.fref(), C.byref(sl.cells), 16,
                                              dF.data_ptr(), grad_emb.data_ptr(), _stream()), "rl_plus_item_backward")
 
-    def tail_forward(self, sl, F, wts, zc, O, bits, front_done=False):
+    def tail_forward(self, sl, F, wts, zc, bits, front_done=False):
         _lib.check(_L().rl_tail_forward(C.byref(sl.cells), sl.slot_head.data_ptr(), 16, 128, F.data_ptr(),
-                                        *[t.data_ptr() for t in wts], zc.data_ptr(), O.data_ptr(), bits.data_ptr(),
+                                        *[t.data_ptr() for t in wts], zc.data_ptr(), bits.data_ptr(),
                                         int(front_done), _stream()), "rl_tail_forward")
 
-    def tail_backward(self, sl, R, F, wts, Gc, O, bits, dF, dY, grads, scratch, front_done=False):
+    def tail_backward(self, sl, R, F, wts, Gc, bits, dF, dY, grads, scratch, front_done=False):
         _lib.check(_L().rl_tail_backward(C.byref(sl.cells), sl.slot_head.data_ptr(), int(R), 16, 128, F.data_ptr(),
-                                         *[t.data_ptr() for t in wts], Gc.data_ptr(), O.data_ptr(), bits.data_ptr(),
+                                         *[t.data_ptr() for t in wts], Gc.data_ptr(), bits.data_ptr(),
                                          dF.data_ptr(), dY.data_ptr(), *[t.data_ptr() for t in grads], scratch.data_ptr(),
                                          int(front_done), _stream()), "rl_tail_backward")
 
@@ -252,7 +252,7 @@ def plus_step(model, sk, sl, smoothing, grad_scale, gbuf: GradBuffer, expanded=F
         ck.pna_front_forward(sl, pl["pna"], wts[0], wts[1], F, pl["FEAT"], pl["SC"])
     else:
         ck.plus_features(sl, emb, F)
-    ck.tail_forward(sl, F, wts, zc, pl["O"], pl["bits"], front_done=pna)
+    ck.tail_forward(sl, F, wts, zc, pl["bits"], front_done=pna)
     ef = model.entity_feature
     ng = len(sl.group_sizes)
     extra = None
@@ -275,7 +275,7 @@ def plus_step(model, sk, sl, smoothing, grad_scale, gbuf: GradBuffer, expanded=F
     if not want_grad:
         return loss, tsum
     grads = [gbuf.view(p) for p in _tail_weights(model)]
-    ck.tail_backward(sl, model.num_relations, F, wts, Gc, pl["O"], pl["bits"], dF, pl["dY"], grads, model._d1sum_scratch(dev),
+    ck.tail_backward(sl, model.num_relations, F, wts, Gc, pl["bits"], dF, pl["dY"], grads, model._d1sum_scratch(dev),
                      front_done=pna)
 
     def emb_backward(grad_emb):
@@ -335,7 +335,7 @@ def plus_rank(model, sk, sl, split):
         ck.pna_front_forward(sl, pl["pna"], wts[0], wts[1], F, pl["FEAT"], pl["SC"])
     else:
         ck.plus_features(sl, emb, F)
-    ck.tail_forward(sl, F, wts, zc, pl["O"], pl["bits"], front_done=pna)
+    ck.tail_forward(sl, F, wts, zc, pl["bits"], front_done=pna)
     which = "hr2oo" if split == "valid" else "hr2ooo"
     ef = model.entity_feature
     if ef == "RotatE":
