@@ -29,7 +29,7 @@ extern "C" {
 #endif
 
 #define RL_LANES 32
-#define RL_ABI_VERSION 2
+#define RL_ABI_VERSION 3
 
 enum rl_status {
     RL_OK = 0,
@@ -93,6 +93,11 @@ typedef struct rl_rules {
     /* rules ending at a node: node_term_rule[node_term_ptr[v] .. node_term_ptr[v+1]) */
     const int32_t *node_term_ptr;  /* [num_nodes+1] */
     const int32_t *node_term_rule; /* [num_terms] */
+    /* pair tables (rl_pair_table): for a node v of depth > 1 and its destination row d, the parent rows that have an
+     * edge into d are pair_ent[pair_ptr[node_pair_off[v] + d] .. pair_ptr[node_pair_off[v] + d + 1]) */
+    const int64_t *node_pair_off;  /* [num_nodes] first pair_ptr entry of the node's (parent relation, relation) pair */
+    const int32_t *pair_ptr;       /* [sum over pairs of rows(rel) + 1] */
+    const int32_t *pair_ent;       /* parent row indices */
 } rl_rules;
 
 /* One call's queries, cut into slots (<= 32 queries of one head relation each). */
@@ -187,6 +192,13 @@ int rl_prepare_slots(const rl_graph *g, int32_t num_slots, const int32_t *slot_h
                      const int32_t *q_off, const int64_t *all_h, const int64_t *all_t,
                      const int64_t *edges_to_remove, int32_t remove_query_edges, int32_t *lane_h,
                      int32_t *lane_t, int32_t *lane_eh, int32_t *lane_et, void *stream);
+
+/* Pair tables of a rule set (rl_rules.pair_ptr / pair_ent): pair p = (pair_prel[p], pair_rel[p]) owns the entries
+ * [pair_base[p], pair_base[p] + rows(pair_rel[p]) + 1) of the pointer array.  Call once with ptr == NULL: out = per-row
+ * entry counts (int32, same indexing, a zero closes each pair); the caller turns them into exclusive prefix sums; call
+ * again with ptr = the sums: out = pair_ent. */
+int rl_pair_table(const rl_graph *g, int32_t n_pairs, const int32_t *pair_prel, const int32_t *pair_rel,
+                  const int64_t *pair_base, const int32_t *ptr, int32_t *out, void *stream);
 
 /* Kernel (1): frontier expansion of one trie depth for every slot, replaces
  * KnowledgeGraph.propagate (src/data.py:149-173) for all rules of the head at once.  Two

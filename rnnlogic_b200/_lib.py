@@ -33,7 +33,8 @@ class RlRules(C.Structure):
                 ("node_rel", vp), ("node_row_off", vp), ("head_node_ptr", vp),
                 ("lvl_ptr", vp), ("chunk_node", vp), ("chunk_row0", vp), ("zr_ptr", vp), ("zr_rule", vp),
                 ("node_chunk0", vp), ("node_rec", vp), ("node_prow_off", vp),
-                ("lvl_sym_ptr", vp), ("sym_node", vp), ("sym_w0", vp), ("node_term_ptr", vp), ("node_term_rule", vp)]
+                ("lvl_sym_ptr", vp), ("sym_node", vp), ("sym_w0", vp), ("node_term_ptr", vp), ("node_term_rule", vp),
+                ("node_pair_off", vp), ("pair_ptr", vp), ("pair_ent", vp)]
 
 
 class RlSlots(C.Structure):
@@ -179,6 +180,7 @@ _PROTOS = {
                                         C.POINTER(RlCells), vp, C.c_int32, C.c_int32, vp, vp, vp, vp, vp, vp, vp, vp]),
     "rl_plus_cell_backward": (C.c_int, [C.POINTER(RlGraph), C.POINTER(RlRules), C.POINTER(RlSlots), C.POINTER(RlFrontier),
                                         C.POINTER(RlCells), C.c_int32, vp, vp, vp]),
+    "rl_pair_table": (C.c_int, [C.POINTER(RlGraph), C.c_int32, vp, vp, vp, vp, vp, vp]),
     "rl_tail_scratch_floats": (C.c_int64, [C.c_int32]),
     "rl_tail_forward": (C.c_int, [C.POINTER(RlCells), vp, C.c_int32, C.c_int32] + [vp] * 12 + [C.c_int32, vp]),
     "rl_tail_backward": (C.c_int, [C.POINTER(RlCells), vp, C.c_int32, C.c_int32, C.c_int32] + [vp] * 24 + [C.c_int32, vp]),

@@ -193,8 +193,11 @@ __device__ __forceinline__ uint32_t numeric_rows(const rl_graph &g, const rl_rul
     CT *__restrict__ Y = arena + (abase + (size_t)r.node_row_off[v]) * RL_LANES;
     const bool active = myrow >= 0;
     const int grow = ra.w + max(myrow, 0);                   // global row (dst_ptr[rel] + row)
-    const int my_rs = active ? g.row_start[grow] : 0;
-    const int my_re = active ? g.row_start[grow + 1] : 0;
+    // depth 1: the row's in-edges; deeper: the row's entries of the (parent relation, relation) pair table --
+    // only the in-edges whose source is a tail of the parent relation, already resolved to parent rows
+    const int32_t *__restrict__ rs = ROOT ? g.row_start + grow : r.pair_ptr + (r.node_pair_off[v] + max(myrow, 0));
+    const int my_rs = active ? rs[0] : 0;
+    const int my_re = active ? rs[1] : 0;
     const int my_dst = active ? g.row_dst[grow] : -1;
     const int deg = my_re - my_rs;
     int P = deg;                                            // inclusive scan of deg over lanes
@@ -243,12 +246,9 @@ __device__ __forceinline__ uint32_t numeric_rows(const rl_graph &g, const rl_rul
         for (int step = 16; step > 0; step >>= 1)
             if (__shfl_sync(FULL, P, row + step - 1) <= k) row += step;
         const int e = __shfl_sync(FULL, my_rs, row) + (k - __shfl_sync(FULL, my_first, row));
-        const int src = lane < n ? __ldg(g.edge_src + e) : -1;
+        const int src = lane < n ? __ldg((ROOT ? g.edge_src : r.pair_ent) + e) : -1;     // ROOT: source entity; else: parent row
         int pr = -1;
-        if (!ROOT && src >= 0) {
-            pr = rank_row(g, prel, src);
-            if (pr >= 0 && !((pm[pr >> 5] >> (pr & 31)) & 1u)) pr = -1;
-        }
+        if (!ROOT && src >= 0 && ((pm[src >> 5] >> (src & 31)) & 1u)) pr = src;
         // only edges whose parent row is non-zero are pulled (ROOT: every edge, the value is a compare)
         uint32_t todo = ROOT ? (n == 32 ? FULL : ((1u << n) - 1u)) : __ballot_sync(FULL, pr >= 0);
         while (todo) {
@@ -358,6 +358,36 @@ k_numeric(rl_graph g, rl_rules r, rl_slots s, int depth, rl_frontier fr, int cpw
         }
     }
     if (__any_sync(FULL, ovf) && lane == 0) fr.overflow[0] = 1;
+}
+
+// Pair tables (built once per rule set): for every (parent relation rp, relation rr) that occurs as a hop of some trie and
+// every destination row d of rr, the in-edges of d whose SOURCE is a tail of rp, stored as the source's row index under
+// rp.  That map depends only on the relation pair, not on the query, so k_numeric neither looks sources up in the rank
+// table nor touches the in-edges that can never carry a count.  One block per pair; FILL = false counts
+// (out[base + d]; out[base + D] = 0 closes the pair), FILL = true writes the entries at ptr[base + d].
+template <bool FILL>
+__global__ void __launch_bounds__(128)
+k_pair_table(rl_graph g, const int32_t *__restrict__ pair_prel, const int32_t *__restrict__ pair_rel,
+             const int64_t *__restrict__ pair_base, const int32_t *__restrict__ ptr, int32_t *__restrict__ out)
+{
+    const int p = blockIdx.x;
+    const int rp = pair_prel[p], rr = pair_rel[p];
+    const long long base = pair_base[p];
+    const int row0 = g.dst_ptr[rr], D = g.dst_ptr[rr + 1] - row0;
+    for (int d = threadIdx.x; d < D; d += blockDim.x) {
+        int n = 0;
+        const int pos = FILL ? ptr[base + d] : 0;
+        const int k1 = g.row_start[row0 + d + 1];
+        for (int k = g.row_start[row0 + d]; k < k1; ++k) {
+            const int pr = rank_row(g, rp, __ldg(g.edge_src + k));
+            if (pr >= 0) {
+                if (FILL) out[pos + n] = pr;
+                ++n;
+            }
+        }
+        if (!FILL) out[base + d] = n;
+    }
+    if (!FILL && threadIdx.x == 0) out[base + D] = 0;
 }
 
 // One hop from an ARBITRARY dense frontier (KnowledgeGraph.propagate, src/data.py:149-173):
@@ -1179,6 +1209,17 @@ static int check_frontier(const rl_frontier *fr, const char *who)
 {
     if (!fr || !fr->arena || !fr->row_mask || !fr->node_cnt || !fr->overflow) return fail(RL_ERR_ARG, who);
     if (fr->count_bits != 32 && fr->count_bits != 64) return fail(RL_ERR_ARG, "count_bits must be 32 or 64");
+    return RL_OK;
+}
+
+int rl_pair_table(const rl_graph *g, int32_t n_pairs, const int32_t *pair_prel, const int32_t *pair_rel,
+                  const int64_t *pair_base, const int32_t *ptr, int32_t *out, void *stream)
+{
+    if (!g || !pair_prel || !pair_rel || !pair_base || !out) return fail(RL_ERR_ARG, "rl_pair_table: null argument");
+    if (n_pairs <= 0) return RL_OK;
+    if (ptr) k_pair_table<true><<<n_pairs, 128, 0, (cudaStream_t)stream>>>(*g, pair_prel, pair_rel, pair_base, ptr, out);
+    else k_pair_table<false><<<n_pairs, 128, 0, (cudaStream_t)stream>>>(*g, pair_prel, pair_rel, pair_base, ptr, out);
+    CHECK_LAUNCH("k_pair_table");
     return RL_OK;
 }
 

@@ -161,6 +161,21 @@ class CompiledRules:
             rec[:, 6] = np.where(has_p, cstart[:-1][psafe], 0)
             rec[:, 7] = node_nterm[:self.num_nodes]
         node_prow_off = np.where(has_p, node_row_off[psafe], 0) if self.num_nodes else np.zeros(0, np.int64)
+        # distinct (parent relation, relation) hops: each gets a pair table on the device (DeviceRules)
+        if self.num_nodes and has_p.any():
+            pkey = np.where(has_p, node_rel[psafe] * R + node_rel, -1)
+            ukeys, inv = np.unique(pkey[has_p], return_inverse=True)
+            self.pair_prel, self.pair_rel = ukeys // R, ukeys % R
+            pbase = np.zeros(ukeys.shape[0] + 1, dtype=np.int64)
+            np.cumsum(rel_rows[self.pair_rel] + 1, out=pbase[1:])
+            self.pair_base = pbase
+            node_pair_off = np.full(self.num_nodes, -1, dtype=np.int64)
+            node_pair_off[has_p] = pbase[:-1][inv]
+        else:
+            self.pair_prel = self.pair_rel = np.zeros(0, np.int64)
+            self.pair_base = np.zeros(1, dtype=np.int64)
+            node_pair_off = np.full(max(1, self.num_nodes), -1, dtype=np.int64)
+        self.node_pair_off = node_pair_off
         # symbolic work items: one per 32 parent bitmap words (1024 parent rows); one per node at depth 1
         if self.num_nodes:
             pwords = np.where(has_p, (node_rows[psafe] + 31) // 32, 1)
@@ -188,6 +203,7 @@ class CompiledRules:
             "node_rec": i32(rec.reshape(-1)), "node_prow_off": np.ascontiguousarray(node_prow_off, dtype=np.int64),
             "lvl_sym_ptr": i32(lvl_sym_ptr.reshape(-1)), "sym_node": i32(sym_node), "sym_w0": i32(sym_w0),
             "node_term_ptr": i32(node_term_ptr), "node_term_rule": i32(node_term_rule),
+            "node_pair_off": np.ascontiguousarray(node_pair_off, dtype=np.int64),
         }
         self._devices = {}
 
@@ -204,6 +220,7 @@ class DeviceRules:
         # zero-length arrays still need a valid (non-null) pointer for the arg checks
         self.t = {k: torch.from_numpy(v if v.shape[0] else np.zeros(1, v.dtype)).to(device) for k, v in cr.host.items()}
         t = self.t
+        self._build_pair_tables(cr, device)
         self.struct = _lib.RlRules(
             cr.num_nodes, cr.num_rules, cr.max_len, cr.num_chunks, cr.num_terms, int(cr.host["zr_rule"].shape[0]),
             t["node_rel"].data_ptr(), t["node_row_off"].data_ptr(),
@@ -212,7 +229,39 @@ class DeviceRules:
             t["node_chunk0"].data_ptr(),
             t["node_rec"].data_ptr(), t["node_prow_off"].data_ptr(), t["lvl_sym_ptr"].data_ptr(),
             t["sym_node"].data_ptr(), t["sym_w0"].data_ptr(), t["node_term_ptr"].data_ptr(),
-            t["node_term_rule"].data_ptr())
+            t["node_term_rule"].data_ptr(), t["node_pair_off"].data_ptr(), t["pair_ptr"].data_ptr(), t["pair_ent"].data_ptr())
+
+    def _build_pair_tables(self, cr: CompiledRules, device):
+        """(parent relation, relation) -> per destination row, the parent rows with an edge into it (rl_pair_table):
+        count on the device, prefix-sum, fill.  Query-independent, built once per rule set and device."""
+        from .engine import _stream
+        t = self.t
+        P = int(cr.pair_prel.shape[0])
+        total = int(cr.pair_base[-1])
+        if P == 0 or torch.device(device).type != "cuda":
+            t["pair_ptr"] = torch.zeros(2, dtype=torch.int32, device=device)
+            t["pair_ent"] = torch.zeros(1, dtype=torch.int32, device=device)
+            return
+        dg = cr.graph.device_graph(device)
+        with torch.cuda.device(device):
+            prel = torch.from_numpy(cr.pair_prel.astype(np.int32)).to(device)
+            rel = torch.from_numpy(cr.pair_rel.astype(np.int32)).to(device)
+            base = torch.from_numpy(cr.pair_base).to(device)
+            cnt = torch.empty(total, dtype=torch.int32, device=device)
+            _lib.check(_lib.lib().rl_pair_table(dg.ref(), P, prel.data_ptr(), rel.data_ptr(), base.data_ptr(), None,
+                                                cnt.data_ptr(), _stream()), "rl_pair_table")
+            csum = torch.cumsum(cnt, 0, dtype=torch.int64)
+            n_ent = int(csum[-1].item())
+            if n_ent >= 2 ** 31:
+                raise ValueError("pair tables need %d entries: 32-bit offsets exhausted" % n_ent)
+            ptr = (csum - cnt).to(torch.int32)                      # exclusive prefix sum
+            del csum, cnt
+            ent = torch.empty(max(1, n_ent), dtype=torch.int32, device=device)
+            _lib.check(_lib.lib().rl_pair_table(dg.ref(), P, prel.data_ptr(), rel.data_ptr(), base.data_ptr(), ptr.data_ptr(),
+                                                ent.data_ptr(), _stream()), "rl_pair_table")
+            torch.cuda.current_stream().synchronize()                # prel / rel / base die here
+        t["pair_ptr"], t["pair_ent"] = ptr, ent
+        self.pair_entries = n_ent
 
     def ref(self):
         return C.byref(self.struct)

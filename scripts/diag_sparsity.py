@@ -4,7 +4,7 @@ sys.path.insert(0, '/root/repo')
 import bench
 from rnnlogic_b200 import KnowledgeGraph
 from rnnlogic_b200.predictors import Predictor
-shape, N, R, train, valid, test, rules = bench.build_workload()
+shape, N, R, train, valid, test, rules = bench.build_workload(typed='--typed' in sys.argv)
 batches = bench.make_batches(train, R, seed=1)
 kg = KnowledgeGraph(entity_size=N, relation_size=R, train=train, valid=valid, test=test)
 m = Predictor(kg, "bias"); m.set_rules([[h] + list(b) for h, b in rules]); m = m.cuda()
@@ -34,5 +34,6 @@ for s, q in enumerate(sl.heads):
         maxrows[d]=max(maxrows[d], c[sel].max() if sel.any() else 0)
     moff += cs[-1]; noff += n1 - n0
 for d in (1, 2, 3):
+    print("  depth %d: valid rows per non-empty node %.2f, per non-empty chunk %.2f" % (d, vrows[d] / max(1, nz_nodes[d]), vrows[d] / max(1, nzchunks[d])))
     print("depth %d: nodes %d nonzero %d | rows %d valid %d (%.3f%%) max/node %d | chunks %d nonzero %d (%.2f%%)" % (
         d, tot_nodes[d], nz_nodes[d], rows[d], vrows[d], 100 * vrows[d] / max(1, rows[d]), maxrows[d], chunks[d], nzchunks[d], 100 * nzchunks[d] / max(1, chunks[d])))
