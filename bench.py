@@ -705,6 +705,21 @@ def main():
                 cfgs["wn18rr_predictor_bias"] = side_config("wnp", wkg, wrules, wb, dict(entity_feature="bias"), pw, side_steps, world, rank, dev, plus=False)
                 cfgs["wn18rr_predictor_bias"]["model"] = "Predictor(bias) on the WN18RR shape (L<=5)"
             del wkg
+        if want("scaled_1m_predictor_bias"):             # BASELINE config 5: 1M entities, 1k relations, 20M edges, 10k length-3 rules
+            from rnnlogic_b200 import synth
+            t_build = time.time()
+            sN, sR, strain, svalid, stest = synth.scaled_kg()
+            srules = synth.scaled_rules()
+            skg = KnowledgeGraph(entity_size=sN, relation_size=sR, train=strain, valid=svalid, test=stest)
+            sb = make_batches(strain[:2_000_000], sR, seed=1)    # batches from the first 2M facts (same relation mix)
+            t_build = time.time() - t_build
+            for pb in (64, 8):                                   # 2048 and 256 queries per optimizer step
+                tag = "scaled_1m_predictor_bias" + ("" if pb == 64 else "_b%d" % (pb * 32))
+                cfgs[tag] = side_config("scaled%d" % (pb * 32), skg, srules, sb, dict(entity_feature="bias"), pb, 10, world, rank, dev, plus=False)
+                cfgs[tag]["model"] = ("Predictor(bias) on the scaled synthetic KG of BASELINE config 5 (N=1e6, R=1e3, E=2e7, 1e4 random "
+                                      "length-3 rules), %d queries per optimizer step per GPU" % (pb * 32))
+            cfgs["scaled_1m_predictor_bias"]["host_build_s"] = round(t_build, 1)
+            del skg
         line["configs"] = cfgs
 
     clk = clocks.stop() if rank == 0 else None      # sampled over all timed regions

@@ -217,16 +217,18 @@ __device__ __forceinline__ uint32_t numeric_rows(const rl_graph &g, const rl_rul
     uint32_t nzrows = 0;
     uint32_t my_lanes = 0;                                   // lane j: which queries of row j are non-zero
     auto flush = [&](int j) {
-        const int d = __shfl_sync(FULL, my_dst, j);
-        if (eh >= 0 && et == d) {                            // data.py:164-170: drop the query's own edge
-            unsigned long long sub;
-            if (ROOT) sub = (eh == h) ? 1ull : 0ull;
-            else {
-                int pr = rank_row(g, prel, eh);
-                if (pr >= 0 && !((pm[pr >> 5] >> (pr & 31)) & 1u)) pr = -1;
-                sub = pr >= 0 ? (unsigned long long)X[(size_t)pr * RL_LANES + lane] : 0ull;
+        if (masked) {                                        // warp-uniform: only hops over the head relation cut an edge
+            const int d = __shfl_sync(FULL, my_dst, j);
+            if (eh >= 0 && et == d) {                        // data.py:164-170: drop the query's own edge
+                unsigned long long sub;
+                if (ROOT) sub = (eh == h) ? 1ull : 0ull;
+                else {
+                    int pr = rank_row(g, prel, eh);
+                    if (pr >= 0 && !((pm[pr >> 5] >> (pr & 31)) & 1u)) pr = -1;
+                    sub = pr >= 0 ? (unsigned long long)X[(size_t)pr * RL_LANES + lane] : 0ull;
+                }
+                acc -= sub;
             }
-            acc -= sub;
         }
         if (sizeof(CT) == 4 && (acc >> 32)) ovf = true;
         const uint32_t nzl = __ballot_sync(FULL, acc != 0);

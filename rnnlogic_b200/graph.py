@@ -270,16 +270,16 @@ class KnowledgeGraph(object):
         np.cumsum(rel_sizes, out=ord_ptr[1:])
         self.train_edge_index = np.empty(E, dtype=np.int64)       # index of train fact i inside its relation
         self.train_edge_index[order] = np.arange(E) - ord_ptr[r[order]]
-        # duplicates are an input error in the reference (assert at data.py:67)
-        full_key = (r * N + t) * N + h if N * N * max(R, 1) < 2 ** 62 else None
-        if full_key is not None and np.unique(full_key).shape[0] != E:
-            raise AssertionError("duplicate train triple")
-        # DCSR by destination: sort by (r, t, h)
-        srt = np.lexsort((h, t, r))
+        # DCSR by destination: sort by (r, t, h) -- one sort of a packed key when it fits 63 bits
+        packed = N * N * max(R, 1) < 2 ** 62
+        srt = np.argsort((r * N + t) * N + h, kind="stable") if packed else np.lexsort((h, t, r))
         rs, ts, hs = r[srt], t[srt], h[srt]
         rowkey = rs * N + ts
         new_row = np.ones(E, dtype=bool)
         new_row[1:] = rowkey[1:] != rowkey[:-1]
+        # duplicates are an input error in the reference (assert at data.py:67); after the sort they are neighbours
+        if E > 1 and bool(np.any(~new_row[1:] & (hs[1:] == hs[:-1]))):
+            raise AssertionError("duplicate train triple")
         row_first = np.flatnonzero(new_row)
         TR = row_first.shape[0]
         row_rel = rs[row_first]
@@ -297,7 +297,7 @@ class KnowledgeGraph(object):
         rank_tab[:, 0] = bits
         rank_tab[:, 1] = prefix.reshape(-1).astype(np.uint32)
         # forward DCSR by source: edges sorted by (r, h, t); each out-edge stores the LOCAL row of its tail
-        fs = np.lexsort((t, h, r))
+        fs = np.argsort((r * N + h) * N + t, kind="stable") if packed else np.lexsort((t, h, r))
         rf, hf, tf = r[fs], h[fs], t[fs]
         skey = rf * N + hf
         new_src = np.ones(E, dtype=bool)
@@ -319,8 +319,7 @@ class KnowledgeGraph(object):
         # per-relation statistics (algorithmic-bytes model)
         self.rel_edges = rel_sizes
         self.rel_rows = np.diff(dst_ptr)
-        srckey = np.unique(r * N + h)
-        self.rel_sources = np.bincount(srckey // N, minlength=R).astype(np.int64)
+        self.rel_sources = np.diff(fsrc_ptr)                      # distinct (relation, source) pairs
         self.rank_words = W
         i32 = lambda a: np.ascontiguousarray(a, dtype=np.int32)
         self.host = {
