@@ -260,23 +260,35 @@ class Runner:
         return ms, sum(self.queries[s % len(self.steps)] for s in range(warmup, n_steps)), launches, events
 
     def graph_loop(self, warmup, steps):
-        """The reference's schedule (one batch per optimizer step) through the per-head CUDA graphs: host arrays in, loss
-        out, one replay + one sync per step.  -> (ms, queries)"""
+        """The reference's schedule (one batch per optimizer step) through the per-head CUDA graphs, the way
+        TrainerPredictor.train drives them: host arrays in, loss out; per step two graph replays (grounding of step k+1
+        enqueued behind the scoring of step k), one event wait, one optimizer step.  -> (ms, queries)"""
         from rnnlogic_b200 import cellpath
         from rnnlogic_b200.predictors import _used_params
         model = self.model
-        seq = [self.steps[s % len(self.steps)][0] for s in range(warmup + steps)]
+        seq = [np.asarray(self.steps[s % len(self.steps)][0], dtype=np.int64).reshape(-1, 3) for s in range(warmup + steps)]
         for b in seq:                                            # capture the graphs of the heads of this run (one each)
             cellpath.graph_train_step(model, b, 0.2)
         torch.cuda.synchronize()
         nq = 0
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        gs_next = None
         for s, b in enumerate(seq):
             if s == warmup:
                 e0.record()
-            res = cellpath.graph_train_step(model, b, 0.2)
+            gs, gs_next = gs_next, None
+            if gs is None:
+                gs = cellpath.graph_step_for(model, b, 0.2)
+                gs.launch_ground(b)
+            gs.launch_score()
+            if s + 1 < len(seq):
+                gs_next = cellpath.graph_step_for(model, seq[s + 1], 0.2)
+                gs_next.launch_ground(seq[s + 1])
+            res = cellpath.graph_step_result(model, gs)
             if res is None:
                 loss, _ = model.fused_train_step([b], 0.2)
+                if gs_next is not None:
+                    gs_next.launch_ground(seq[s + 1])
             else:
                 res[3].assign(_used_params(model, res[2]))
                 assert np.isfinite(res[0])
@@ -412,7 +424,7 @@ def side_config(tag, kg, rules, batches, kw, per, steps, world, rank, dev, plus=
         run = Runner(model, deal_steps(batches, model.compiled, 1, 64, world, rank), 1, world, dev)
         ms, q = run.graph_loop(8, steps)
         out = {"e2e_queries_per_sec": q / (ms / 1e3), "ms_per_step": ms / steps, "steps": steps, "batches_per_step_per_gpu": 1,
-               "path": "one CUDA graph replay + one sync per step (graph captured once per head relation)"}
+               "path": "two CUDA graph replays (grounding of step k+1 behind the scoring of step k) + one event wait + one optimizer step per step; graphs captured once per head relation"}
         print("[bench] %s: %.0f q/s e2e, %.3f ms/step" % (tag, out["e2e_queries_per_sec"], out["ms_per_step"]), file=sys.stderr)
         del run, model
         torch.cuda.empty_cache()

@@ -213,6 +213,12 @@ def _tail_weights(model):
 def _step_rule_ids(model, sl, device):
     """Global ids of the rules of the heads present in this call (host-known: no sync)."""
     heads = np.unique(sl.heads)
+    if len(heads) == 1:                                                 # one-batch steps (and their CUDA graphs): device-resident per head
+        cache = model.__dict__.setdefault("_head_rule_ids", {})
+        key = (int(heads[0]), str(device))
+        if key not in cache:
+            cache[key] = torch.from_numpy(model.compiled.head_rule_array[key[0]]).to(device)
+        return cache[key]
     ids = np.concatenate([model.compiled.head_rule_array[int(q)] for q in heads]) if len(heads) else np.zeros(0, np.int64)
     return torch.from_numpy(ids).to(device, non_blocking=True)
 
@@ -355,7 +361,13 @@ def plus_rank(model, sk, sl, split):
 # graph and replayed with new queries written into its pinned staging buffer.
 # ================================================================================================
 class GraphTrainStep:
-    """Captured fused train step of ``model`` for batches of one head relation (one slot)."""
+    """Captured fused train step of ``model`` for batches of one head relation (one slot), as TWO CUDA graphs:
+
+      ground  H2D of the queries -> slot preparation -> frontier expansion          (independent of the parameters)
+      score   cells -> scores -> CE -> backward -> D2H of loss / counts / flags     (reads the current parameters)
+
+    so a trainer can enqueue the grounding of step k+1 behind the scoring of step k and only then wait for step k's
+    result: the GPU expands the next frontier while the host reads the loss, exchanges gradients and steps the optimizer."""
 
     def __init__(self, model, head: int, smoothing: float):
         from .engine import HostStep, Slots
@@ -373,26 +385,33 @@ class GraphTrainStep:
         self._qoff = self._pack[self.host.n64:].view(np.int32)[1:3]           # q_off = [0, n] behind the slot head
         self.generation = gr.generation
 
-        def run():
+        def ground():
             sl = Slots(gr.dg, self.host)
             sl.use_workspace, sl.coo_only = True, True
             gr._run(sl, 32)
+            return sl
+
+        def score(sl):
             gbuf = GradBuffer(self.params)
             loss, tsum = model.step_on_slots(sk, sl, self.smoothing, 1.0, gbuf, 32, expanded=True)
             pack = torch.cat([loss, tsum, sl.slot_ncell.float(), sl.flags.float()])
-            return sl, gbuf, pack
+            return gbuf, pack
 
         self._fill(np.zeros((1, 3), dtype=np.int64) + np.array([[0, self.head, 0]]))
-        sl, gbuf, pack = run()                                               # eager warm-up: sizes every workspace
+        _, pack = score(ground())                                            # eager warm-up: sizes every workspace
         self.pinned = torch.empty(pack.numel(), dtype=torch.float32, pin_memory=True)
         torch.cuda.synchronize()
         self.generation = gr.generation
-        self.graph = torch.cuda.CUDAGraph()
-        with torch.cuda.graph(self.graph):
-            self.sl, self.gbuf, pack = run()
+        self.g_ground, self.g_score = torch.cuda.CUDAGraph(), torch.cuda.CUDAGraph()
+        with torch.cuda.graph(self.g_ground):
+            self.sl = ground()
+        with torch.cuda.graph(self.g_score, pool=self.g_ground.pool()):
+            self.gbuf, pack = score(self.sl)
             self.pinned.copy_(pack, non_blocking=True)
         if gr.generation != self.generation:
             raise _lib.RlError("a workspace was reallocated during graph capture")
+        self.ev_in, self.ev_out = torch.cuda.Event(), torch.cuda.Event()
+        self._in_flight = False
 
     def _fill(self, batch: np.ndarray):
         n = int(batch.shape[0])
@@ -402,21 +421,36 @@ class GraphTrainStep:
         self._qoff[0], self._qoff[1] = 0, n
         self.n = n
 
-    def __call__(self, batch: np.ndarray):
-        """Replay for one batch [n,3] of this head.  -> (loss, target_sum, cells, flags) after the step's one sync;
-        the gradients are in self.gbuf."""
+    def launch_ground(self, batch: np.ndarray):
+        """Enqueue the parameter-independent half for ``batch`` [n,3] (no host wait unless this head's previous
+        queries are still being copied)."""
+        if self._in_flight:
+            self.ev_in.synchronize()                                         # the staging buffer is read by the graph's H2D node
         self._fill(batch)
-        self.graph.replay()
-        torch.cuda.current_stream().synchronize()
+        self.g_ground.replay()
+        self.ev_in.record()
+        self._in_flight = True
+
+    def launch_score(self):
+        self.g_score.replay()
+        self.ev_out.record()
+
+    def result(self):
+        """-> (loss, target_sum, cells, flags) of the last launch_score, after waiting for it; gradients are in self.gbuf."""
+        self.ev_out.synchronize()
         host = self.pinned
-        flags = host[3:]
-        return float(host[0]), float(host[1]), int(host[2]), flags
+        return float(host[0]), float(host[1]), int(host[2]), host[3:]
+
+    def __call__(self, batch: np.ndarray):
+        self.launch_ground(batch)
+        self.launch_score()
+        return self.result()
 
 
-def graph_train_step(model, batch: np.ndarray, smoothing: float):
-    """One reference-schedule train step through the per-head CUDA graph.  Returns (loss, tsum, cells, gbuf) or None
-    when the step has to take the eager path (count overflow, cell arrays too small, unsupported model)."""
-    if len(batch) > LANES or not getattr(model, "supports_pipeline", False):
+def graph_step_for(model, batch, smoothing: float):
+    """The captured step of the batch's head relation (captured on first use), or None when the step has to take the
+    eager path (more than 32 queries, unsupported model, capture not possible)."""
+    if len(batch) > LANES or not getattr(model, "supports_pipeline", False) or model.__dict__.get("_graphs_broken", False):
         return None
     head = int(batch[0][1])
     cache = model.__dict__.setdefault("_graph_steps", {})
@@ -424,9 +458,36 @@ def graph_train_step(model, batch: np.ndarray, smoothing: float):
     gr = model._driver(next(model.parameters()).device).gr
     if gs is None or gs.generation != gr.generation:
         gr.reserve_single_slot()
-        gs = cache[(head, float(smoothing))] = GraphTrainStep(model, head, smoothing)
-    loss, tsum, cells, flags = gs(np.asarray(batch, dtype=np.int64).reshape(-1, 3))
+        try:
+            gs = cache[(head, float(smoothing))] = GraphTrainStep(model, head, smoothing)
+        except _lib.RlError:
+            raise
+        except RuntimeError as e:                                            # an op of this model cannot be captured: eager from now on
+            import logging
+            logging.warning("per-head CUDA graphs disabled for this model: %s", str(e).splitlines()[0])
+            model.__dict__["_graphs_broken"] = True
+            torch.cuda.synchronize()
+            return None
+    return gs
+
+
+def graph_step_result(model, gs: GraphTrainStep):
+    """(loss, tsum, cells, gbuf) of a launched step, or None when it has to be redone eagerly (count overflow, cell
+    arrays too small)."""
+    loss, tsum, cells, flags = gs.result()
     if flags[8] != 0 or flags[1] != 0:
-        gr.note_cell_count(cells)
+        gs.sk.gr.note_cell_count(cells)
         return None
     return loss, tsum, cells, gs.gbuf
+
+
+def graph_train_step(model, batch: np.ndarray, smoothing: float):
+    """One reference-schedule train step through the per-head CUDA graphs, synchronously.  Returns (loss, tsum, cells,
+    gbuf) or None when the step has to take the eager path."""
+    batch = np.asarray(batch, dtype=np.int64).reshape(-1, 3)
+    gs = graph_step_for(model, batch, smoothing)
+    if gs is None:
+        return None
+    gs.launch_ground(batch)
+    gs.launch_score()
+    return graph_step_result(model, gs)

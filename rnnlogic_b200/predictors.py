@@ -39,6 +39,8 @@ class _RuleModel(nn.Module):
             self.relation2rules[rule[0]].append([index, rule])
         self.compiled = CompiledRules(self.graph, self.rules)
         self._drivers = {}
+        self.__dict__.pop("_graph_steps", None)        # captured per-head steps and rule-id tables belong to the old rule set
+        self.__dict__.pop("_head_rule_ids", None)
 
     def _driver(self, device) -> ScoreKernels:
         if device.type != "cuda":

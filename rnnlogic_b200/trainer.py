@@ -142,12 +142,35 @@ class TrainerPredictor(object):
             from .data import StepPrefetcher
             packed = StepPrefetcher(model.pack_train_step, steps, depth=2)      # host packing on a loader thread
             ticket = model.prepare_train_step(next(packed)).finish(smoothing, grad_scale=1.0 / len(steps[0]))
+        gs_next = None                                                 # captured step whose grounding half is already enqueued
+        as_batch = lambda b: np.asarray(b, dtype=np.int64).reshape(-1, 3)
         for si, batches in enumerate(steps):
             self.optimizer.zero_grad(set_to_none=True)
-            res = cellpath.graph_train_step(model, batches[0], smoothing) if (graphs and len(batches[0]) <= 32) else None
-            if res is not None:                                        # the whole step was one graph replay + one sync
+            res = None
+            if graphs:
+                # Reference schedule on per-head CUDA graphs: score step i, enqueue the (parameter-independent) grounding of
+                # step i+1 behind it, and only then wait for step i's loss and flags.
+                gs, gs_next = gs_next, None
+                if gs is None:
+                    gs = cellpath.graph_step_for(model, as_batch(batches[0]), smoothing)
+                    if gs is not None:
+                        gs.launch_ground(as_batch(batches[0]))
+                if gs is not None:
+                    gs.launch_score()
+                    if si + 1 < len(steps):
+                        nb = as_batch(steps[si + 1][0])
+                        gs_next = cellpath.graph_step_for(model, nb, smoothing)
+                        if gs_next is not None:
+                            gs_next.launch_ground(nb)
+                    res = cellpath.graph_step_result(model, gs)
+            if res is not None:                                        # the whole step was two graph replays + one event wait
                 loss, tsum, cand = [res[0]], [res[1]], [res[2]]
                 res[3].assign(_used_params(model, res[2]))
+            elif graphs:                                               # eager redo (overflow / larger cell arrays / no capture)
+                loss, tsum = model.fused_train_step(batches, smoothing, grad_scale=1.0 / len(batches))
+                cand = getattr(model, "last_mask_sum", None)
+                if gs_next is not None:                                # the redo used the shared frontier workspace
+                    gs_next.launch_ground(as_batch(steps[si + 1][0]))
             elif pipelined:
                 prep = model.prepare_train_step(next(packed)) if si + 1 < len(steps) else None
                 try:

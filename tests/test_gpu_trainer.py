@@ -131,3 +131,41 @@ def test_pipelined_train_loop_equals_synchronous(per_step, tmp_path):
     for k in out[0]:
         assert np.abs(out[0][k]).max() > 0
         np.testing.assert_allclose(out[0][k], out[1][k], rtol=1e-4, atol=1e-6, err_msg=k)
+
+
+@gpu
+@pytest.mark.parametrize("kind", ["predictor", "plus_emb", "plus_lstm"])
+def test_graph_schedule_equals_eager(kind, tmp_path):
+    """The reference's schedule (one batch per optimizer step) on the per-head CUDA graphs -- grounding of step k+1
+    enqueued behind the scoring of step k -- ends with the same parameters as the eager step-by-step loop, and a new
+    rule set (set_rules) drops the captured graphs."""
+    from rnnlogic_b200.data import KnowledgeGraph, TrainDataset, ValidDataset, TestDataset
+    from rnnlogic_b200.predictors import Predictor, PredictorPlus
+    from rnnlogic_b200.trainer import TrainerPredictor
+    from rnnlogic_b200.utils import set_seed
+    fx = G.load("umls")
+    d = str(tmp_path / "umls")
+    write_dataset_dir(d, fx)
+    out = []
+    for graphs in (True, False):
+        set_seed(5)
+        graph = KnowledgeGraph(d)
+        sets = TrainDataset(graph, 32), ValidDataset(graph, 32), TestDataset(graph, 32)
+        if kind == "predictor":
+            model = Predictor(graph, entity_feature="bias")
+        else:
+            model = PredictorPlus(graph, type=kind.split("_")[1], num_layers=2, hidden_dim=16, entity_feature="bias", aggregator="sum")
+        model.set_rules(G.rules_of(fx))
+        optim = torch.optim.Adam(model.parameters(), lr=0.01)
+        solver = TrainerPredictor(model, *sets, optim, gpus=[0])
+        solver.use_graphs, solver.pipelined = graphs, False
+        solver.train(batch_per_epoch=16, smoothing=0.2, print_every=5)
+        if graphs:
+            assert len(model.__dict__.get("_graph_steps", {})) > 0 and not model.__dict__.get("_graphs_broken", False)
+        out.append({k: v.detach().cpu().numpy().copy() for k, v in model.state_dict().items()})
+        if graphs:
+            model.set_rules(G.rules_of(fx)[:-1])
+            assert "_graph_steps" not in model.__dict__
+    for k in out[0]:
+        scale = max(1e-6, float(np.abs(out[1][k]).max()))
+        assert np.abs(out[0][k] - out[1][k]).max() <= 2e-4 * scale + 1e-6, k
