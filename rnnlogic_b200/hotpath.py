@@ -62,11 +62,12 @@ class ScoreKernels:
         slot_sums = torch.empty(3 * S, dtype=torch.float32, device=dev)
         out = torch.empty(2, n_groups, dtype=torch.float32, device=dev)
         ans, _keep = self.dg.answers["hr2o"]
+        G = torch.empty_like(Z)                                   # gradient rows: held until the call is enqueued
         _lib.check(_lib.lib().rl_predictor_ce_backward(
             self.dg.ref(), self.dr.ref(), sl.ref(), sl.fref(), C.byref(ans), float(smoothing), int(use_mask),
             Z.data_ptr(), nzmask.data_ptr(), int(n_groups), group_ptr.data_ptr() if group_ptr is not None else None,
             partial.data_ptr(), 1, stats.data_ptr(), slot_sums.data_ptr(), out[0].data_ptr(), out[1].data_ptr(),
-            torch.empty_like(Z).data_ptr(), slot_scale.data_ptr() if slot_scale is not None else None, grad_w.data_ptr(),
+            G.data_ptr(), slot_scale.data_ptr() if slot_scale is not None else None, grad_w.data_ptr(),
             grad_bias.data_ptr() if grad_bias is not None else None, _stream()), "rl_predictor_ce_backward")
         return out[0], out[1], nzmask
 

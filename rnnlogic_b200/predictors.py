@@ -46,6 +46,10 @@ class _RuleModel(nn.Module):
         if device.type != "cuda":
             raise _lib.RlError("rnnlogic_b200 predictors are CUDA-only (sm_100a); got a %s batch. There is no CPU "
                                "fallback: move the model and the batch to a CUDA device." % device)
+        # the C-ABI entry points launch on the CURRENT device's stream: a model that lives on another GPU makes that GPU
+        # current (one process per GPU is the design; this keeps `model.cuda(1); model(h, r, etr)` correct)
+        if device.index is not None and device.index != torch.cuda.current_device():
+            torch.cuda.set_device(device)
         key = str(device)
         if key not in self._drivers:
             self._drivers[key] = ScoreKernels(Grounder(self.graph, self.compiled, device, self.force_dense))
@@ -527,10 +531,12 @@ class _PlusScatterFn(torch.autograd.Function):
         sk, sl = pc.sk, pc.sl
         Z = torch.empty(sl.S, sk.N, LANES, dtype=torch.float32, device=sk.device)
         zcc = zc.detach().contiguous().float() if zc is not None else torch.zeros(1, device=sk.device)
+        bc = bias.detach().contiguous() if bias is not None else None       # held in locals until the call is enqueued
+        ec = extra.detach().contiguous() if extra is not None else None
         _lib.check(_lib.lib().rl_plus_scatter(
             sk.dg.ref(), sl.ref(), pc.nzmask.data_ptr(), pc.cand_off.data_ptr(), zcc.data_ptr(),
-            bias.detach().contiguous().data_ptr() if bias is not None else None,
-            extra.detach().contiguous().data_ptr() if extra is not None else None, int(fill_neg_inf),
+            bc.data_ptr() if bc is not None else None,
+            ec.data_ptr() if ec is not None else None, int(fill_neg_inf),
             Z.data_ptr(), _stream()), "rl_plus_scatter")
         ctx.pc = pc
         ctx.flags = (zc is not None, bias is not None, extra is not None)
