@@ -270,6 +270,8 @@ class Runner:
         for b in seq:                                            # capture the graphs of the heads of this run (one each)
             cellpath.graph_train_step(model, b, 0.2)
         torch.cuda.synchronize()
+        if self.world > 1:
+            torch.distributed.barrier()
         nq = 0
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         gs_next = None
@@ -285,13 +287,11 @@ class Runner:
                 gs_next = cellpath.graph_step_for(model, seq[s + 1], 0.2)
                 gs_next.launch_ground(seq[s + 1])
             res = cellpath.graph_step_result(model, gs)
-            if res is None:
-                loss, _ = model.fused_train_step([b], 0.2)
-                if gs_next is not None:
-                    gs_next.launch_ground(seq[s + 1])
-            else:
-                res[3].assign(_used_params(model, res[2]))
-                assert np.isfinite(res[0])
+            assert res is not None and np.isfinite(res[0]), "a bench batch needed the eager path (count overflow / cell arrays)"
+            if self.world > 1:                                   # the path's one collective: the flat gradient buffer of the graph
+                torch.distributed.all_reduce(res[3].flat, op=torch.distributed.ReduceOp.SUM)
+                res[3].flat.div_(self.world)
+            res[3].assign(_used_params(model, res[2]))
             self.opt.step()
             if s >= warmup:
                 nq += len(b)
@@ -342,9 +342,9 @@ class Runner:
 
 def dense_expansion_traffic(kg, cr, heads):
     """Bytes the expansion kernels MOVE in dense mode for the given slot heads -- a model of the kernel's own behaviour,
-    counted from the graph (not the algorithmic figure): per trie node it reads the relation's rows / edge list, looks every
-    source up in the parent relation's rank table, pulls a parent row (128 B) only for the in-edges whose source is a
-    tail of the parent relation, and writes a row (128 B) only when at least one of its in-edges was pulled.  Both are
+    counted from the graph (not the algorithmic figure): per trie node it reads the rows' pair-table pointers and entries
+    (the in-edges whose source is a tail of the parent relation, as parent rows), pulls a parent row (128 B) per entry,
+    and writes a row (128 B) only when at least one entry was pulled.  Both are
     static statistics of the (parent relation, relation) pair."""
     N, R = kg.entity_size, kg.relation_size
     h = kg.host
@@ -366,9 +366,10 @@ def dense_expansion_traffic(kg, cr, heads):
     node_rel, node_depth, node_head = cr.node_rel_host, cr.node_depth, cr.node_head
     prel = np.where(cr.host["node_parent"] >= 0, node_rel[np.maximum(cr.host["node_parent"], 0)], 0)
     root = node_depth == 1
-    per_node = 4 * E[node_rel] + 8 * D[node_rel] + np.where(
-        root, 128 * D[node_rel],                                                  # depth 1: compares, every row written
-        8 * E[node_rel] + 128 * pulled[prel, node_rel] + 128 * rows_w[prel, node_rel])
+    per_node = np.where(
+        root, 4 * E[node_rel] + 8 * D[node_rel] + 128 * D[node_rel],             # depth 1: in-edges compared with h, every row written
+        12 * D[node_rel] + 8 * pulled[prel, node_rel]                             # pair_ptr + row_dst per row, entry + bitmap word per pair entry
+        + 128 * pulled[prel, node_rel] + 128 * rows_w[prel, node_rel])
     nb = np.zeros(cr.num_nodes + 1, dtype=np.int64)
     np.cumsum(per_node, out=nb[1:])
     head_bytes = nb[cr.head_node_ptr[1:]] - nb[cr.head_node_ptr[:-1]]
@@ -420,12 +421,14 @@ def side_config(tag, kg, rules, batches, kw, per, steps, world, rank, dev, plus=
     model = model.cuda(dev)
     if plus and not model.supports_pipeline:
         return side_config_autograd(model, batches, per, steps, dev)
-    if per == 1 and world == 1:                      # reference schedule: per-head CUDA graphs
+    if per == 1:                                     # reference schedule: per-head CUDA graphs
         run = Runner(model, deal_steps(batches, model.compiled, 1, 64, world, rank), 1, world, dev)
         ms, q = run.graph_loop(8, steps)
+        ms, q = reduce_max_sum(ms, q, dev, world)
         out = {"e2e_queries_per_sec": q / (ms / 1e3), "ms_per_step": ms / steps, "steps": steps, "batches_per_step_per_gpu": 1,
                "path": "two CUDA graph replays (grounding of step k+1 behind the scoring of step k) + one event wait + one optimizer step per step; graphs captured once per head relation"}
-        print("[bench] %s: %.0f q/s e2e, %.3f ms/step" % (tag, out["e2e_queries_per_sec"], out["ms_per_step"]), file=sys.stderr)
+        if rank == 0:
+            print("[bench] %s: %.0f q/s e2e, %.3f ms/step" % (tag, out["e2e_queries_per_sec"], out["ms_per_step"]), file=sys.stderr)
         del run, model
         torch.cuda.empty_cache()
         return out
