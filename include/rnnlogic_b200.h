@@ -493,6 +493,18 @@ int rl_tail_backward(const rl_cells *c, const int32_t *slot_head, int32_t R, int
                      float *ggamma, float *gbeta, float *gW1, float *gb1, float *gW2, float *gb2, float *grel,
                      float *scratch, int32_t front_done, void *stream);
 
+/* ---- rule discovery (rl_miner.cu; miner/rnnlogic.cpp:350-382, 505-589) ----
+ * Every relation path of <= max_len hops from h to its FIRST visit of t, for every triple (h, r, t) of
+ * tri[n_triples][3] with that triple removed from the graph, without the trivial rule r <- r; h == t yields the empty
+ * body.  adj_ptr[N+1] / adj_rel / adj_dst = out-edges by source entity over all relations (DEVICE).  table[cap] (cap a
+ * power of two, filled with 0xFF bytes by the caller) receives the DISTINCT rules as 64-bit keys
+ *     head << (b*max_len+3) | length << (b*max_len) | body[i] << (b*(max_len-1-i)),   b = rel_bits,
+ * whose ascending order is the order of the reference's rule list (head relation, then std::set<Rule> order:
+ * length, body; rnnlogic.cpp:118-133, 575-585).  flags[0] != 0 on return:
+ * the table was too small.  rel_bits * (max_len + 1) + 3 must be <= 63, max_len <= 6. */
+int rl_mine_rules(int32_t n_triples, const int32_t *tri, const int32_t *adj_ptr, const int32_t *adj_rel, const int32_t *adj_dst,
+                  int32_t max_len, int32_t rel_bits, unsigned long long *table, int64_t cap, int32_t *flags, void *stream);
+
 /* ---- PNA aggregator (FuncToNode, src/layers.py:89-126) on the cells, hidden_dim 16 (rl_pna.cu) ---- */
 typedef struct rl_pna {                 /* per-cell statistics, arrays of rl_cells.cap cells (DEVICE) */
     float *s1;                          /* [cap][16] sum count * emb      (layers.py:94) */

@@ -38,3 +38,27 @@ int ref_rule_destination(void *kg, int e, int head, const int *body, int L,
 }
 
 }  // extern "C"
+
+// ---- rule discovery: RuleMiner::search (/root/reference/miner/rnnlogic.cpp:505-589) ----
+// Runs the reference's own miner on the loaded graph and writes the mined rules as consecutive records
+// {head, length, body[0..length)} into out (at most cap ints).  Returns the number of ints of the full list.
+extern "C" long long ref_mine_rules(void *kg, int max_length, int threads, int *out, long long cap)
+{
+    RuleMiner miner;
+    miner.init_knowledge_graph(static_cast<KnowledgeGraph *>(kg));
+    miner.search(max_length, 1.0, threads);
+    std::vector<Rule> *rules = miner.get_logic_rules();
+    const int R = static_cast<KnowledgeGraph *>(kg)->get_relation_size();
+    long long n = 0;
+    for (int r = 0; r < R; ++r)
+        for (size_t i = 0; i < rules[r].size(); ++i) {
+            const Rule &u = rules[r][i];
+            if (n + 2 + (long long)u.r_body.size() <= cap) {
+                out[n] = u.r_head;
+                out[n + 1] = (int)u.r_body.size();
+                for (size_t k = 0; k < u.r_body.size(); ++k) out[n + 2 + k] = u.r_body[k];
+            }
+            n += 2 + (long long)u.r_body.size();
+        }
+    return n;
+}

@@ -12,7 +12,7 @@ import subprocess
 _HERE = os.path.dirname(os.path.abspath(__file__))
 ROOT = os.path.dirname(_HERE)
 LIB_PATH = os.environ.get("RNNLOGIC_B200_LIB") or os.path.join(_HERE, "lib", "librnnlogic_b200.so")   # env override: A/B builds
-SOURCES = [os.path.join(_HERE, "csrc", f) for f in ("rl_kernels.cu", "rl_cells.cu", "rl_plus.cu", "rl_rotate.cu", "rl_tail.cu", "rl_tail_tc.cu", "rl_pna.cu", "rl_rnn.cu")]
+SOURCES = [os.path.join(_HERE, "csrc", f) for f in ("rl_kernels.cu", "rl_cells.cu", "rl_plus.cu", "rl_rotate.cu", "rl_tail.cu", "rl_tail_tc.cu", "rl_pna.cu", "rl_rnn.cu", "rl_miner.cu")]
 HEADER = os.path.join(ROOT, "include", "rnnlogic_b200.h")
 
 LANES = 32
@@ -181,6 +181,7 @@ _PROTOS = {
     "rl_plus_cell_backward": (C.c_int, [C.POINTER(RlGraph), C.POINTER(RlRules), C.POINTER(RlSlots), C.POINTER(RlFrontier),
                                         C.POINTER(RlCells), C.c_int32, vp, vp, vp]),
     "rl_pair_table": (C.c_int, [C.POINTER(RlGraph), C.c_int32, vp, vp, vp, vp, vp, vp]),
+    "rl_mine_rules": (C.c_int, [C.c_int32, vp, vp, vp, vp, C.c_int32, C.c_int32, vp, C.c_int64, vp, vp]),
     "rl_tail_scratch_floats": (C.c_int64, [C.c_int32]),
     "rl_tail_forward": (C.c_int, [C.POINTER(RlCells), vp, C.c_int32, C.c_int32] + [vp] * 12 + [C.c_int32, vp]),
     "rl_tail_backward": (C.c_int, [C.POINTER(RlCells), vp, C.c_int32, C.c_int32, C.c_int32] + [vp] * 24 + [C.c_int32, vp]),

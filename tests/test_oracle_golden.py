@@ -3,6 +3,8 @@ unmodified reference stored in tests/golden/ (made by tests/golden/make_golden.p
 
 Integer results (path counts, (L,H) rank bounds) must be bit-exact; fp32 results are compared
 at rtol 1e-5 (north_star tolerance) with a small atol for values that cancel to ~0."""
+import os
+
 import numpy as np
 import pytest
 import torch
@@ -213,3 +215,32 @@ def test_counts_against_reference_cpp(ds, tmp_path):
                 checked += 1
     lib.ref_kg_free(ref)
     assert checked > 500
+
+
+@pytest.mark.parametrize("name", G.DATASETS)
+def test_oracle_rule_search_matches_the_reference_miner(name):
+    """Row f4: the C restatement of rule_search / RuleMiner::search (oracle_mine_rules) reproduces, rule for rule and in
+    the same order, what the reference's own miner binary code mines (tests/golden/mined_*.npz, made by
+    tests/golden/make_mined_golden.py from oracle/_ref); UMLS / Kinship counts are the survey's 39,283 / 70,229."""
+    fx = G.load(name)
+    gold = dict(np.load(os.path.join(G.GOLDEN, "mined_%s.npz" % name)))
+    want = [[int(v) for v in row if v >= 0] for row in gold["rules"]]
+    got = O.mine_rules(fx["train"], int(fx["N"]), int(fx["R"]), int(gold["max_length"]))
+    assert len(got) == len(want) == {"umls": 39283, "kinship": 70229}.get(name, len(want))
+    assert got == want
+
+
+def test_oracle_rule_search_edge_cases():
+    """h == t gives the empty body; r <- r is dropped; the triple itself is removed wherever it occurs; a path stops
+    at its first visit of t."""
+    #        0 -r0-> 1 -r1-> 2,  0 -r2-> 2,  2 -r0-> 2 (self loop),  2 -r1-> 0
+    train = np.array([[0, 0, 1], [1, 1, 2], [0, 2, 2], [2, 0, 2], [2, 1, 0]])
+    rules = O.mine_rules(train, 3, 3, 3)
+    assert [0] in rules                                   # (2, r0, 2): h == t
+    assert [2, 0, 1] in rules                             # (0, r2, 2) via 0 -r0-> 1 -r1-> 2
+    assert [2, 2] not in rules and [0, 0] not in rules    # trivial rules never appear
+    assert [1, 1] not in rules
+    # (0, r0, 1): 0 -r2-> 2 -r1-> 0 -r0-> 1 would use the removed triple; nothing else reaches 1
+    assert not any(r[0] == 0 and len(r) > 1 for r in rules)
+    # a path does not run THROUGH its goal: (1, r1, 2) has 2 -r0-> 2 behind the goal, never used
+    assert all(r != [1, 1, 0] for r in rules)
