@@ -36,8 +36,9 @@ __device__ __forceinline__ unsigned long long mix64(unsigned long long x)
 
 __device__ __forceinline__ void miner_insert(const MinerArgs &a, unsigned long long key)
 {
+    if (*reinterpret_cast<volatile int32_t *>(a.flags)) return;          // table already reported full: the host reruns with a larger one
     unsigned long long slot = mix64(key) & a.cap_mask;
-    for (int probe = 0; probe < 4096; ++probe) {
+    for (int probe = 0; probe < 256; ++probe) {
         const unsigned long long cur = a.table[slot];
         if (cur == key) return;
         if (cur == MINER_EMPTY) {
@@ -86,18 +87,23 @@ __device__ void miner_dfs(const MinerArgs &a, int h, int r, int t, int e, int de
 __global__ void __launch_bounds__(256)
 k_mine_rules(MinerArgs a)
 {
-    __shared__ int s_first;
+    __shared__ int s_first, s_stop;
     for (int T = blockIdx.x; T < a.n_triples; T += gridDim.x) {
+        if (threadIdx.x == 0) {
+            s_first = 0;
+            s_stop = *reinterpret_cast<volatile int32_t *>(a.flags);        // table reported full: the host reruns with a larger one
+        }
+        __syncthreads();
+        if (s_stop) return;                                      // block-uniform
         const int h = a.tri[3 * T], r = a.tri[3 * T + 1], t = a.tri[3 * T + 2];
-        if (h == t) {                                            // e == goal at depth 0: the empty body (rnnlogic.cpp:352-363)
-            if (threadIdx.x == 0) miner_insert(a, miner_key(a, r, nullptr, 0));
+        if (h == t || a.max_len <= 0) {
+            // e == goal at depth 0: the empty body (rnnlogic.cpp:352-363)
+            if (h == t && threadIdx.x == 0) miner_insert(a, miner_key(a, r, nullptr, 0));
+            __syncthreads();
             continue;
         }
-        if (a.max_len <= 0) continue;
         // level 1: the out-edges of h are drawn from a block-wide work counter; a thread goes on alone below its edge
         const int e0 = a.adj_ptr[h], e1 = a.adj_ptr[h + 1];
-        if (threadIdx.x == 0) s_first = 0;
-        __syncthreads();
         int path[MINER_MAX_LEN];
         for (;;) {
             const int i = atomicAdd(&s_first, 1);

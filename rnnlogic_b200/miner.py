@@ -54,7 +54,7 @@ def mine_rule_keys(train: np.ndarray, N: int, R: int, max_length: int = 3, tripl
             full = int(flags[0].item()) != 0 or keys.numel() * 2 > cap          # keep the load factor below 1/2
             if not full:
                 break
-            table_log2 += 2
+            table_log2 += 3
             del table, keys
         return torch.sort(keys)[0].cpu().numpy()
 

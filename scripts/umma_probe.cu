@@ -124,6 +124,9 @@ int main()
     bad |= run("bf16  A MN-major x B MN-major", 1, true, true, 128, 128);
     bad |= run("bf16  A MN-major x B K-major", 1, true, false, 64, 64);
     bad |= run("tf32  A K-major  x B K-major N=16", 0, false, false, 16, 64);
+    bad |= run("tf32  A MN-major x B MN-major", 0, true, true, 128, 128);
+    bad |= run("tf32  A K-major  x B K-major N=48", 0, false, false, 48, 64);
+    bad |= run("tf32  A K-major  x B K-major N=64 K=48", 0, false, false, 64, 48);
     printf(bad ? "PROBE FAILED\n" : "PROBE OK\n");
     return bad;
 }
