@@ -1,6 +1,6 @@
 // rnnlogic_b200 -- the PNA aggregator of PredictorPlus (FuncToNode, src/layers.py:89-126; the shipped WN18RR config)
 // on candidate cells: per-cell statistics from the item list, the scaler / Linear(12H,H) front, and their backward
-// into the rule embeddings and the 16 x 192 weight.  H = 16.  The LayerNorm -> ReLU -> MLP tail is rl_tail2.cu with
+// into the rule embeddings and the 16 x 192 weight.  H = 16.  The LayerNorm -> ReLU -> MLP tail is rl_tail_tc.cu with
 // front_done = 1.
 //
 //   degree = sum_rule count + 1                                   (layers.py:92)
@@ -14,6 +14,7 @@
 // carry the rule in the low word of a 64-bit key (order-preserving float key << 32 | rule tag), so the arg rule of the
 // backward -- the FIRST rule in rule-file order on ties, like torch.min / max -- falls out of the same atomic.
 #include "rl_device.cuh"
+#include "rl_umma.cuh"
 
 #define PH 16                 // hidden_dim
 #define PF 64                 // features per cell: mean | min | max | std
@@ -109,15 +110,6 @@ k_pna_qscale(rl_cells c, rl_pna p, float *__restrict__ qlog, float *__restrict__
     }
 }
 
-// shared-memory weight layout of the front kernels: Wt[f][t][i] so that the 16 outputs of (f, t) are one 64-byte run
-__device__ __forceinline__ void stage_pna_w(float *sm, const float *__restrict__ W, int tid, int nthreads)
-{
-    for (int x = tid; x < PH * PU; x += nthreads) {               // W[i][f*3+t] row-major [16][192]
-        const int i = x / PU, ft = x % PU;
-        sm[ft * PH + i] = W[x];
-    }
-}
-
 // features of one cell into registers; returns the scaler s
 __device__ __forceinline__ float pna_features(const rl_cells &c, const rl_pna &p, long long cell, const float *__restrict__ qlog,
                                               const float *__restrict__ qn, float (&feat)[PF])
@@ -138,92 +130,228 @@ __device__ __forceinline__ float pna_features(const rl_cells &c, const rl_pna &p
     return logf(deg1) / fmaxf(msc, 1e-6f);
 }
 
-__global__ void __launch_bounds__(256)
+// ---- the Linear(12H,H) front on the tensor cores (tcgen05, TMEM accumulators; helpers in rl_umma.cuh) ----
+// y = b + W [f (x) (1, s, 1/s)]: with W3[t*16+i][f] = W[i][f*3+t] the three scaler blocks are ONE product
+// P[cell][48] = FEAT[cell][64] W3^T and y_i = b_i + P_i + s P_{16+i} + P_{32+i} / s.  A tile is 128 cells = the M of the MMA;
+// both operands are general fp32, so the product is 3xTF32 (hi/lo pieces, fp32 accumulate): 24 MMAs of K = 8, N = 48.
+#define PT 128
+#define PCH (PT * 16)                         // bytes of one 16-byte chunk column of a 128-row tile
+#define PF_AHI 0                              // FEAT hi: 16 chunks of 4 features
+#define PF_ALO (PF_AHI + 16 * PCH)
+#define PF_BHI (PF_ALO + 16 * PCH)            // W3 hi: [48 rows][16 chunks]
+#define PF_BLO (PF_BHI + 16 * 48 * 16)
+#define PF_BAR (PF_BLO + 16 * 48 * 16)
+#define PF_END (PF_BAR + 16)
+
+__global__ void __launch_bounds__(PT, 2)
 k_pna_front_fwd(rl_cells c, rl_pna p, const float *__restrict__ qlog, const float *__restrict__ qn,
                 const float *__restrict__ W, const float *__restrict__ bvec, float *__restrict__ Y,
                 float *__restrict__ FEAT, float *__restrict__ SC)
 {
-    extern __shared__ __align__(16) float sm[];
+    extern __shared__ __align__(128) uint8_t smem[];
     const long long C = min(c.counters[0], c.cap);
-    if ((long long)blockIdx.x * 256 >= C) return;
-    stage_pna_w(sm, W, threadIdx.x, 256);
+    const long long tiles = (C + PT - 1) / PT;
+    if ((long long)blockIdx.x >= tiles) return;
+    const int tid = threadIdx.x, warp = tid >> 5;
+    uint64_t *bar = reinterpret_cast<uint64_t *>(smem + PF_BAR);
+    uint32_t *tslot = reinterpret_cast<uint32_t *>(smem + PF_BAR + 8);
+    for (int x = tid; x < 48 * 16; x += PT) {                    // (row n = t*16+i, chunk of 4 features)
+        const int n = x % 48, ch = x / 48, t = n >> 4, i = n & 15;
+        float4 hi, lo;
+        umma::split_tf32(__ldg(W + i * PU + (4 * ch) * 3 + t), hi.x, lo.x);
+        umma::split_tf32(__ldg(W + i * PU + (4 * ch + 1) * 3 + t), hi.y, lo.y);
+        umma::split_tf32(__ldg(W + i * PU + (4 * ch + 2) * 3 + t), hi.z, lo.z);
+        umma::split_tf32(__ldg(W + i * PU + (4 * ch + 3) * 3 + t), hi.w, lo.w);
+        *reinterpret_cast<float4 *>(smem + PF_BHI + ch * (48 * 16) + n * 16) = hi;
+        *reinterpret_cast<float4 *>(smem + PF_BLO + ch * (48 * 16) + n * 16) = lo;
+    }
+    if (tid == 0) umma::mbar_init(bar, 1);
+    if (warp == 0) umma::tmem_alloc(tslot, 64);
+    umma::fence_before();
     __syncthreads();
-    for (long long cell = (long long)blockIdx.x * 256 + threadIdx.x; cell < C; cell += (long long)gridDim.x * 256) {
-        float feat[PF];
-        const float sc = pna_features(c, p, cell, qlog, qn, feat);
-        const float isc = 1.f / fmaxf(sc, 1e-6f);
-        float y[PH];
+    umma::fence_after();
+    const uint32_t tacc = *tslot, trow = tacc + ((uint32_t)(warp * 32) << 16);
+    const uint32_t s_ahi = umma::smem_u32(smem + PF_AHI), s_alo = umma::smem_u32(smem + PF_ALO);
+    const uint32_t s_bhi = umma::smem_u32(smem + PF_BHI), s_blo = umma::smem_u32(smem + PF_BLO);
+    constexpr uint32_t ID = umma::idesc(UMMA_FMT_TF32, PT, 48, false, false);
+    float bv[PH];
 #pragma unroll
-        for (int i = 0; i < PH; ++i) y[i] = __ldg(bvec + i);
-#pragma unroll 4
-        for (int f = 0; f < PF; ++f) {
-            const float fa = feat[f], fb = feat[f] * sc, fc = feat[f] * isc;
-            const float4 *w0 = reinterpret_cast<const float4 *>(sm + (f * 3) * PH);
+    for (int i = 0; i < PH; ++i) bv[i] = __ldg(bvec + i);
+    uint32_t phase = 0;
+    for (long long tile = blockIdx.x; tile < tiles; tile += gridDim.x) {
+        const long long cell = tile * PT + tid;
+        const bool live = cell < C;
+        float sc = 1.f;
+        {
+            float feat[PF];
+            if (live) sc = pna_features(c, p, cell, qlog, qn, feat);
+            else {
+#pragma unroll
+                for (int f = 0; f < PF; ++f) feat[f] = 0.f;
+            }
+#pragma unroll
+            for (int ch = 0; ch < PF / 4; ++ch) {
+                float4 hi, lo;
+                umma::split_tf32(feat[4 * ch], hi.x, lo.x); umma::split_tf32(feat[4 * ch + 1], hi.y, lo.y);
+                umma::split_tf32(feat[4 * ch + 2], hi.z, lo.z); umma::split_tf32(feat[4 * ch + 3], hi.w, lo.w);
+                *reinterpret_cast<float4 *>(smem + PF_AHI + ch * PCH + tid * 16) = hi;
+                *reinterpret_cast<float4 *>(smem + PF_ALO + ch * PCH + tid * 16) = lo;
+                if (live) reinterpret_cast<float4 *>(FEAT + cell * PF)[ch] = make_float4(feat[4 * ch], feat[4 * ch + 1], feat[4 * ch + 2], feat[4 * ch + 3]);
+            }
+            if (live) SC[cell] = sc;
+        }
+        umma::fence_smem_to_async();
+        umma::fence_before();
+        __syncthreads();
+        if (tid == 0) {
+            umma::fence_after();
+#pragma unroll
+            for (int pr = 0; pr < 3; ++pr) {                     // lo*hi, hi*lo, hi*hi
+                const uint32_t sa = pr == 0 ? s_alo : s_ahi, sb = pr == 1 ? s_blo : s_bhi;
+#pragma unroll
+                for (int k = 0; k < PF / 8; ++k)
+                    umma::mma_tf32(tacc, umma::desc(sa + k * 2 * PCH, PCH, 128), umma::desc(sb + k * 2 * (48 * 16), 48 * 16, 128), ID, (pr | k) != 0);
+            }
+            umma::commit(bar);
+        }
+        umma::mbar_wait(bar, phase);
+        phase ^= 1u;
+        umma::fence_after();
+        float d0[16], d1[16], d2[16];
+        umma::tmem_ld16(trow, d0);
+        umma::tmem_ld16(trow + 16, d1);
+        umma::tmem_ld16(trow + 32, d2);
+        if (live) {
+            const float isc = 1.f / fmaxf(sc, 1e-6f);
+            float4 *yo = reinterpret_cast<float4 *>(Y + cell * PH);
 #pragma unroll
             for (int i4 = 0; i4 < PH / 4; ++i4) {
-                const float4 a = w0[i4], b = w0[PH / 4 + i4], d = w0[2 * (PH / 4) + i4];
-                y[4 * i4] = fmaf(fc, d.x, fmaf(fb, b.x, fmaf(fa, a.x, y[4 * i4])));
-                y[4 * i4 + 1] = fmaf(fc, d.y, fmaf(fb, b.y, fmaf(fa, a.y, y[4 * i4 + 1])));
-                y[4 * i4 + 2] = fmaf(fc, d.z, fmaf(fb, b.z, fmaf(fa, a.z, y[4 * i4 + 2])));
-                y[4 * i4 + 3] = fmaf(fc, d.w, fmaf(fb, b.w, fmaf(fa, a.w, y[4 * i4 + 3])));
+                float y[4];
+#pragma unroll
+                for (int u = 0; u < 4; ++u) {
+                    const int i = 4 * i4 + u;
+                    y[u] = fmaf(isc, d2[i], fmaf(sc, d1[i], d0[i] + bv[i]));
+                }
+                yo[i4] = make_float4(y[0], y[1], y[2], y[3]);
             }
         }
-        float4 *yo = reinterpret_cast<float4 *>(Y + cell * PH);
-#pragma unroll
-        for (int i4 = 0; i4 < PH / 4; ++i4) yo[i4] = make_float4(y[4 * i4], y[4 * i4 + 1], y[4 * i4 + 2], y[4 * i4 + 3]);
-        float4 *fo = reinterpret_cast<float4 *>(FEAT + cell * PF);
-#pragma unroll
-        for (int f4 = 0; f4 < PF / 4; ++f4) fo[f4] = make_float4(feat[4 * f4], feat[4 * f4 + 1], feat[4 * f4 + 2], feat[4 * f4 + 3]);
-        SC[cell] = sc;
     }
+    umma::fence_before();
+    __syncthreads();
+    if (warp == 0) umma::tmem_free(tacc, 64);
 }
 
-// dstat[cell] = [dS1 16 | dS2 16 | dMN 16 | dMX 16] from dy = dloss/dy
-__global__ void __launch_bounds__(256)
+// backward of the front: dfeat[cell][64] = [dy, s dy, dy / s][cell][48] W3, again 3xTF32 (18 MMAs of K = 8, N = 64);
+// then dstat[cell] = [dS1 16 | dS2 16 | dMN 16 | dMX 16] per thread.
+#define PB_AHI 0                              // [dy, s dy, dy/s] hi: 12 chunks of 4
+#define PB_ALO (PB_AHI + 12 * PCH)
+#define PB_BHI (PB_ALO + 12 * PCH)            // W3^T hi: [64 rows f][12 chunks of n]
+#define PB_BLO (PB_BHI + 12 * 64 * 16)
+#define PB_BAR (PB_BLO + 12 * 64 * 16)
+#define PB_END (PB_BAR + 16)
+
+__global__ void __launch_bounds__(PT, 2)
 k_pna_front_bwd(rl_cells c, rl_pna p, const float *__restrict__ W, const float *__restrict__ dY,
                 const float *__restrict__ FEAT, const float *__restrict__ SC, float *__restrict__ dstat)
 {
-    extern __shared__ __align__(16) float sm[];
+    extern __shared__ __align__(128) uint8_t smem[];
     const long long C = min(c.counters[0], c.cap);
-    if ((long long)blockIdx.x * 256 >= C) return;
-    stage_pna_w(sm, W, threadIdx.x, 256);
+    const long long tiles = (C + PT - 1) / PT;
+    if ((long long)blockIdx.x >= tiles) return;
+    const int tid = threadIdx.x, warp = tid >> 5;
+    uint64_t *bar = reinterpret_cast<uint64_t *>(smem + PB_BAR);
+    uint32_t *tslot = reinterpret_cast<uint32_t *>(smem + PB_BAR + 8);
+    for (int x = tid; x < 64 * 12; x += PT) {                    // (row f, chunk of 4 n = t*16+i)
+        const int f = x & 63, ch = x >> 6, t = ch >> 2, i0 = (ch & 3) * 4;
+        float4 hi, lo;
+        umma::split_tf32(__ldg(W + (i0) * PU + f * 3 + t), hi.x, lo.x);
+        umma::split_tf32(__ldg(W + (i0 + 1) * PU + f * 3 + t), hi.y, lo.y);
+        umma::split_tf32(__ldg(W + (i0 + 2) * PU + f * 3 + t), hi.z, lo.z);
+        umma::split_tf32(__ldg(W + (i0 + 3) * PU + f * 3 + t), hi.w, lo.w);
+        *reinterpret_cast<float4 *>(smem + PB_BHI + ch * (64 * 16) + f * 16) = hi;
+        *reinterpret_cast<float4 *>(smem + PB_BLO + ch * (64 * 16) + f * 16) = lo;
+    }
+    if (tid == 0) umma::mbar_init(bar, 1);
+    if (warp == 0) umma::tmem_alloc(tslot, 64);
+    umma::fence_before();
     __syncthreads();
-    for (long long cell = (long long)blockIdx.x * 256 + threadIdx.x; cell < C; cell += (long long)gridDim.x * 256) {
-        float dy[PH];
-        const float4 *dp = reinterpret_cast<const float4 *>(dY + cell * PH);
+    umma::fence_after();
+    const uint32_t tacc = *tslot, trow = tacc + ((uint32_t)(warp * 32) << 16);
+    const uint32_t s_ahi = umma::smem_u32(smem + PB_AHI), s_alo = umma::smem_u32(smem + PB_ALO);
+    const uint32_t s_bhi = umma::smem_u32(smem + PB_BHI), s_blo = umma::smem_u32(smem + PB_BLO);
+    constexpr uint32_t ID = umma::idesc(UMMA_FMT_TF32, PT, 64, false, false);
+    uint32_t phase = 0;
+    for (long long tile = blockIdx.x; tile < tiles; tile += gridDim.x) {
+        const long long cell = tile * PT + tid;
+        const bool live = cell < C;
+        {
+            const float sc = live ? SC[cell] : 1.f, isc = 1.f / fmaxf(sc, 1e-6f);
 #pragma unroll
-        for (int i4 = 0; i4 < PH / 4; ++i4) {
-            const float4 v = __ldg(dp + i4);
-            dy[4 * i4] = v.x; dy[4 * i4 + 1] = v.y; dy[4 * i4 + 2] = v.z; dy[4 * i4 + 3] = v.w;
-        }
-        const float sc = SC[cell], isc = 1.f / fmaxf(sc, 1e-6f);
-        const float deg1 = fmaxf(p.deg[cell] + 1.f, 1e-6f);
-        float *out = dstat + cell * PF;
-        for (int h = 0; h < PH; ++h) {
-            float df[4];                                         // gradient of feature (kind k, unit h), k = mean | min | max | std
+            for (int i4 = 0; i4 < PH / 4; ++i4) {
+                const float4 v = live ? __ldg(reinterpret_cast<const float4 *>(dY + cell * PH) + i4) : make_float4(0.f, 0.f, 0.f, 0.f);
+                const float dv[4] = {v.x, v.y, v.z, v.w};
 #pragma unroll
-            for (int k = 0; k < 4; ++k) {
-                const int f = k * PH + h;
-                const float4 *w0 = reinterpret_cast<const float4 *>(sm + (f * 3) * PH);
-                float a = 0.f, b = 0.f, d = 0.f;
-#pragma unroll
-                for (int i4 = 0; i4 < PH / 4; ++i4) {
-                    const float4 wa = w0[i4], wb = w0[PH / 4 + i4], wd = w0[2 * (PH / 4) + i4];
-                    a = fmaf(dy[4 * i4], wa.x, a); a = fmaf(dy[4 * i4 + 1], wa.y, a); a = fmaf(dy[4 * i4 + 2], wa.z, a); a = fmaf(dy[4 * i4 + 3], wa.w, a);
-                    b = fmaf(dy[4 * i4], wb.x, b); b = fmaf(dy[4 * i4 + 1], wb.y, b); b = fmaf(dy[4 * i4 + 2], wb.z, b); b = fmaf(dy[4 * i4 + 3], wb.w, b);
-                    d = fmaf(dy[4 * i4], wd.x, d); d = fmaf(dy[4 * i4 + 1], wd.y, d); d = fmaf(dy[4 * i4 + 2], wd.z, d); d = fmaf(dy[4 * i4 + 3], wd.w, d);
+                for (int t = 0; t < 3; ++t) {
+                    const float m = t == 0 ? 1.f : (t == 1 ? sc : isc);
+                    float4 hi, lo;
+                    umma::split_tf32(dv[0] * m, hi.x, lo.x); umma::split_tf32(dv[1] * m, hi.y, lo.y);
+                    umma::split_tf32(dv[2] * m, hi.z, lo.z); umma::split_tf32(dv[3] * m, hi.w, lo.w);
+                    *reinterpret_cast<float4 *>(smem + PB_AHI + (t * 4 + i4) * PCH + tid * 16) = hi;
+                    *reinterpret_cast<float4 *>(smem + PB_ALO + (t * 4 + i4) * PCH + tid * 16) = lo;
                 }
-                df[k] = a + sc * b + isc * d;
             }
-            const float mean = FEAT[cell * PF + h], stdv = FEAT[cell * PF + 3 * PH + h];
-            const float var = p.s2[cell * PH + h] / deg1 - mean * mean;              // the forward's expression, bit for bit
-            const float dv = var >= 1e-6f ? df[3] / (2.f * stdv) : 0.f;              // clamp(min=1e-6) passes the gradient where v >= 1e-6
-            out[h] = (df[0] - 2.f * mean * dv) / deg1;            // dS1
-            out[PH + h] = dv / deg1;                              // dS2
-            out[2 * PH + h] = df[1];                              // dMN
-            out[3 * PH + h] = df[2];                              // dMX
+        }
+        umma::fence_smem_to_async();
+        umma::fence_before();
+        __syncthreads();
+        if (tid == 0) {
+            umma::fence_after();
+#pragma unroll
+            for (int pr = 0; pr < 3; ++pr) {
+                const uint32_t sa = pr == 0 ? s_alo : s_ahi, sb = pr == 1 ? s_blo : s_bhi;
+#pragma unroll
+                for (int k = 0; k < 48 / 8; ++k)
+                    umma::mma_tf32(tacc, umma::desc(sa + k * 2 * PCH, PCH, 128), umma::desc(sb + k * 2 * (64 * 16), 64 * 16, 128), ID, (pr | k) != 0);
+            }
+            umma::commit(bar);
+        }
+        umma::mbar_wait(bar, phase);
+        phase ^= 1u;
+        umma::fence_after();
+        float dmean[16], dmn[16], dmx[16], dsd[16];              // gradient of feature (kind, unit h): columns kind*16 + h
+        umma::tmem_ld16(trow, dmean);
+        umma::tmem_ld16(trow + 16, dmn);
+        umma::tmem_ld16(trow + 32, dmx);
+        umma::tmem_ld16(trow + 48, dsd);
+        if (live) {
+            const float deg1 = fmaxf(p.deg[cell] + 1.f, 1e-6f);
+            float4 *out = reinterpret_cast<float4 *>(dstat + cell * PF);
+#pragma unroll
+            for (int h4 = 0; h4 < PH / 4; ++h4) {
+                const float4 mean4 = __ldg(reinterpret_cast<const float4 *>(FEAT + cell * PF) + h4);
+                const float4 std4 = __ldg(reinterpret_cast<const float4 *>(FEAT + cell * PF + 3 * PH) + h4);
+                const float4 s24 = __ldg(reinterpret_cast<const float4 *>(p.s2 + cell * PH) + h4);
+                const float mean[4] = {mean4.x, mean4.y, mean4.z, mean4.w}, stdv[4] = {std4.x, std4.y, std4.z, std4.w},
+                            s2v[4] = {s24.x, s24.y, s24.z, s24.w};
+                float o1[4], o2[4];
+#pragma unroll
+                for (int u = 0; u < 4; ++u) {
+                    const int h = 4 * h4 + u;
+                    const float var = s2v[u] / deg1 - mean[u] * mean[u];             // the forward's expression, bit for bit
+                    const float dv = var >= 1e-6f ? dsd[h] / (2.f * stdv[u]) : 0.f;  // clamp(min=1e-6) passes the gradient where v >= 1e-6
+                    o1[u] = (dmean[h] - 2.f * mean[u] * dv) / deg1;                  // dS1
+                    o2[u] = dv / deg1;                                               // dS2
+                }
+                out[h4] = make_float4(o1[0], o1[1], o1[2], o1[3]);
+                out[PH / 4 + h4] = make_float4(o2[0], o2[1], o2[2], o2[3]);
+                out[2 * (PH / 4) + h4] = make_float4(dmn[4 * h4], dmn[4 * h4 + 1], dmn[4 * h4 + 2], dmn[4 * h4 + 3]);
+                out[3 * (PH / 4) + h4] = make_float4(dmx[4 * h4], dmx[4 * h4 + 1], dmx[4 * h4 + 2], dmx[4 * h4 + 3]);
+            }
         }
     }
+    umma::fence_before();
+    __syncthreads();
+    if (warp == 0) umma::tmem_free(tacc, 64);
 }
 
 // gW[i][f*3+t] += sum_cells dy_i * feat_f * scaler_t: thread = (unit i, group of 4 features), 12 accumulators in registers
@@ -362,6 +490,12 @@ static int cell_grid(const rl_cells *c)
     return (int)(b < 148 * 8 ? b : 148 * 8);
 }
 
+static int tile_grid(const rl_cells *c)
+{
+    const long long b = ((long long)c->cap + PT - 1) / PT;
+    return (int)(b < 148 * 2 ? (b > 0 ? b : 1) : 148 * 2);
+}
+
 extern "C" {
 
 int rl_pna_item_stats(const rl_graph *g, const rl_rules *r, const rl_slots *s, const rl_frontier *fr, const rl_cells *c,
@@ -397,8 +531,9 @@ int rl_pna_front_forward(const rl_slots *s, const rl_cells *c, const rl_pna *p, 
     if (cudaMemsetAsync(qscr, 0, 2 * nq * sizeof(float), st) != cudaSuccess) return rl_fail(RL_ERR_CUDA, "rl_pna_front_forward: memset", cudaGetLastError());
     k_pna_qscale<<<cell_grid(c), 256, 0, st>>>(*c, *p, qscr, qscr + nq);
     CHECK_LAUNCH("k_pna_qscale");
-    const size_t smem = (size_t)PH * PU * sizeof(float);
-    k_pna_front_fwd<<<cell_grid(c), 256, smem, st>>>(*c, *p, qscr, qscr + nq, W, b, Y, FEAT, SC);
+    static bool attr = false;
+    if (!attr) { cudaFuncSetAttribute(k_pna_front_fwd, cudaFuncAttributeMaxDynamicSharedMemorySize, PF_END); attr = true; }
+    k_pna_front_fwd<<<tile_grid(c), PT, PF_END, st>>>(*c, *p, qscr, qscr + nq, W, b, Y, FEAT, SC);
     CHECK_LAUNCH("k_pna_front_fwd");
     return RL_OK;
 }
@@ -409,8 +544,9 @@ int rl_pna_front_backward(const rl_cells *c, const rl_pna *p, const float *W, co
 {
     if (bad_pna(c, p) || !W || !dY || !FEAT || !SC || !dstat || !gW) return rl_fail(RL_ERR_ARG, "rl_pna_front_backward: bad argument");
     cudaStream_t st = (cudaStream_t)stream;
-    const size_t smem = (size_t)PH * PU * sizeof(float);
-    k_pna_front_bwd<<<cell_grid(c), 256, smem, st>>>(*c, *p, W, dY, FEAT, SC, dstat);
+    static bool attr = false;
+    if (!attr) { cudaFuncSetAttribute(k_pna_front_bwd, cudaFuncAttributeMaxDynamicSharedMemorySize, PB_END); attr = true; }
+    k_pna_front_bwd<<<tile_grid(c), PT, PB_END, st>>>(*c, *p, W, dY, FEAT, SC, dstat);
     CHECK_LAUNCH("k_pna_front_bwd");
     k_pna_w_grad<<<148 * 2, 256, 0, st>>>(*c, dY, FEAT, SC, gW);
     CHECK_LAUNCH("k_pna_w_grad");
