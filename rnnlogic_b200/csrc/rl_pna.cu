@@ -39,11 +39,20 @@ __device__ __forceinline__ void pna_add(const rl_pna &p, long long cell, int par
     if (part == 0) atomicAdd(p.deg + cell, v);
     const float ev[4] = {e4.x, e4.y, e4.z, e4.w};
     const unsigned long long lo_min = (unsigned)rule, lo_max = 0xffffffffu - (unsigned)rule;   // ties: the first rule wins both
+    // look before the atomic: a key only ever moves towards its extreme, so a (possibly stale) L2 read that already beats
+    // this rule means the atomic cannot change anything -- most contributions of a well-connected cell skip it
+    unsigned long long cur_mn[4], cur_mx[4];
+#pragma unroll
+    for (int u2 = 0; u2 < 2; ++u2) {
+        const ulonglong2 a = __ldcg(reinterpret_cast<const ulonglong2 *>(p.mnk + cell * PH + part * 4) + u2);
+        const ulonglong2 b = __ldcg(reinterpret_cast<const ulonglong2 *>(p.mxk + cell * PH + part * 4) + u2);
+        cur_mn[2 * u2] = a.x; cur_mn[2 * u2 + 1] = a.y; cur_mx[2 * u2] = b.x; cur_mx[2 * u2 + 1] = b.y;
+    }
 #pragma unroll
     for (int u = 0; u < 4; ++u) {
         const unsigned long long k = (unsigned long long)pkey(ev[u]) << 32;
-        atomicMin(p.mnk + cell * PH + part * 4 + u, k | lo_min);
-        atomicMax(p.mxk + cell * PH + part * 4 + u, k | lo_max);
+        if ((k | lo_min) < cur_mn[u]) atomicMin(p.mnk + cell * PH + part * 4 + u, k | lo_min);
+        if ((k | lo_max) > cur_mx[u]) atomicMax(p.mxk + cell * PH + part * 4 + u, k | lo_max);
     }
 }
 
@@ -116,14 +125,29 @@ __device__ __forceinline__ float pna_features(const rl_cells &c, const rl_pna &p
 {
     const float deg1 = p.deg[cell] + 1.f;
     const float dcl = fmaxf(deg1, 1e-6f);
+    // 16-byte loads: a cell's statistics are 64-byte (sums) and 128-byte (min / max keys) rows
 #pragma unroll
-    for (int h = 0; h < PH; ++h) {
-        const float mean = p.s1[cell * PH + h] / dcl;
-        const float sqm = p.s2[cell * PH + h] / dcl;
-        feat[h] = mean;
-        feat[PH + h] = pkey_inv((unsigned)(p.mnk[cell * PH + h] >> 32));
-        feat[2 * PH + h] = pkey_inv((unsigned)(p.mxk[cell * PH + h] >> 32));
-        feat[3 * PH + h] = sqrtf(fmaxf(sqm - mean * mean, 1e-6f));
+    for (int h4 = 0; h4 < PH / 4; ++h4) {
+        const float4 a = __ldg(reinterpret_cast<const float4 *>(p.s1 + cell * PH) + h4);
+        const float4 b = __ldg(reinterpret_cast<const float4 *>(p.s2 + cell * PH) + h4);
+        const float s1v[4] = {a.x, a.y, a.z, a.w}, s2v[4] = {b.x, b.y, b.z, b.w};
+        unsigned long long mn[4], mx[4];
+#pragma unroll
+        for (int u2 = 0; u2 < 2; ++u2) {
+            const ulonglong2 q = __ldg(reinterpret_cast<const ulonglong2 *>(p.mnk + cell * PH) + 2 * h4 + u2);
+            const ulonglong2 r = __ldg(reinterpret_cast<const ulonglong2 *>(p.mxk + cell * PH) + 2 * h4 + u2);
+            mn[2 * u2] = q.x; mn[2 * u2 + 1] = q.y; mx[2 * u2] = r.x; mx[2 * u2 + 1] = r.y;
+        }
+#pragma unroll
+        for (int u = 0; u < 4; ++u) {
+            const int h = 4 * h4 + u;
+            const float mean = s1v[u] / dcl;
+            const float sqm = s2v[u] / dcl;
+            feat[h] = mean;
+            feat[PH + h] = pkey_inv((unsigned)(mn[u] >> 32));
+            feat[2 * PH + h] = pkey_inv((unsigned)(mx[u] >> 32));
+            feat[3 * PH + h] = sqrtf(fmaxf(sqm - mean * mean, 1e-6f));
+        }
     }
     const int key = c.cell_key[cell];
     const float msc = qlog[key] / fmaxf(qn[key], 1e-6f);
