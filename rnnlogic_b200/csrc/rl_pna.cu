@@ -378,50 +378,114 @@ k_pna_front_bwd(rl_cells c, rl_pna p, const float *__restrict__ W, const float *
     if (warp == 0) umma::tmem_free(tacc, 64);
 }
 
-// gW[i][f*3+t] += sum_cells dy_i * feat_f * scaler_t: thread = (unit i, group of 4 features), 12 accumulators in registers
-__global__ void __launch_bounds__(256)
+// gW[i][f*3+t] += sum_cells dy_i * feat_f * scaler_t  -- a product over the CELLS: gW3[n][f] = sum_c DY3[c][n] FEAT[c][f]
+// (n = t*16+i).  On the tensor cores with K = cells: both operands are K-major tiles whose rows are the n / f indices,
+// so a thread (= cell) writes its values as one 4-byte COLUMN of the tile; a row count of 129 (one pad row) spreads the
+// eight 16-byte chunks of a warp over all 32 banks.  hi / lo pieces are stacked along M and N:
+//     A rows: [DY3 hi 48 | 0 x16 | DY3 lo 48 | 0 x16]      B rows: [FEAT hi 64 | FEAT lo 64]
+// and D[128][128] accumulates in TMEM over the whole kernel; gW3 = D[n][f] + D[n][64+f] + D[64+n][f] (3xTF32).
+#define PW_ROWS 129
+#define PW_CH (PW_ROWS * 16)                  // bytes of one chunk (4 cells) of a tile
+#define PW_A 0
+#define PW_B (PW_A + 32 * PW_CH)
+#define PW_BAR (PW_B + 32 * PW_CH)
+#define PW_END (PW_BAR + 16)
+
+__global__ void __launch_bounds__(PT, 1)
 k_pna_w_grad(rl_cells c, const float *__restrict__ dY, const float *__restrict__ FEAT, const float *__restrict__ SC,
              float *__restrict__ gW)
 {
-    __shared__ __align__(16) float s_dy[32][PH];
-    __shared__ __align__(16) float s_ft[32][PF];
-    __shared__ float s_sc[32], s_isc[32];
+    extern __shared__ __align__(128) uint8_t smem[];
     const long long C = min(c.counters[0], c.cap);
-    const int tid = threadIdx.x, i = tid & 15, fg = tid >> 4;    // features 4*fg .. 4*fg+3
-    float acc[12];
+    const long long tiles = (C + PT - 1) / PT;
+    const long long t0 = tiles * blockIdx.x / gridDim.x, t1 = tiles * (blockIdx.x + 1) / gridDim.x;
+    if (t0 >= t1) return;
+    const int tid = threadIdx.x, warp = tid >> 5;
+    uint64_t *bar = reinterpret_cast<uint64_t *>(smem + PW_BAR);
+    uint32_t *tslot = reinterpret_cast<uint32_t *>(smem + PW_BAR + 8);
+    for (int x = tid; x < 32 * 32; x += PT) {                    // the zero rows of A: 48..63 and 112..127, every chunk
+        const int ch = x >> 5, r = x & 31;
+        const int row = r < 16 ? 48 + r : 96 + r;
+        *reinterpret_cast<float4 *>(smem + PW_A + ch * PW_CH + row * 16) = make_float4(0.f, 0.f, 0.f, 0.f);
+    }
+    if (tid == 0) umma::mbar_init(bar, 1);
+    if (warp == 0) umma::tmem_alloc(tslot, 128);
+    umma::fence_before();
+    __syncthreads();
+    umma::fence_after();
+    const uint32_t tacc = *tslot, trow = tacc + ((uint32_t)(warp * 32) << 16);
+    const uint32_t s_a = umma::smem_u32(smem + PW_A), s_b = umma::smem_u32(smem + PW_B);
+    constexpr uint32_t ID = umma::idesc(UMMA_FMT_TF32, 128, 128, false, false);
+    float *colA = reinterpret_cast<float *>(smem + PW_A + (tid >> 2) * PW_CH + (tid & 3) * 4);     // this cell's column
+    float *colB = reinterpret_cast<float *>(smem + PW_B + (tid >> 2) * PW_CH + (tid & 3) * 4);
+    uint32_t phase = 0;
+    for (long long tile = t0; tile < t1; ++tile) {
+        const long long cell = tile * PT + tid;
+        const bool live = cell < C;
+        const float sc = live ? SC[cell] : 0.f, isc = live ? 1.f / fmaxf(sc, 1e-6f) : 0.f;
 #pragma unroll
-    for (int k = 0; k < 12; ++k) acc[k] = 0.f;
-    for (long long base = (long long)blockIdx.x * 32; base < C; base += (long long)gridDim.x * 32) {
-        const int nc = (int)min(32LL, C - base);
-        __syncthreads();
-        for (int x = tid; x < 32 * PH / 4; x += 256)
-            reinterpret_cast<float4 *>(&s_dy[0][0])[x] = (x >> 2) < nc ? __ldg(reinterpret_cast<const float4 *>(dY + base * PH) + x)
-                                                                      : make_float4(0.f, 0.f, 0.f, 0.f);
-        for (int x = tid; x < 32 * PF / 4; x += 256)
-            reinterpret_cast<float4 *>(&s_ft[0][0])[x] = (x >> 4) < nc ? __ldg(reinterpret_cast<const float4 *>(FEAT + base * PF) + x)
-                                                                      : make_float4(0.f, 0.f, 0.f, 0.f);
-        if (tid < 32) {
-            const float sc = tid < nc ? SC[base + tid] : 0.f;
-            s_sc[tid] = sc;
-            s_isc[tid] = tid < nc ? 1.f / fmaxf(sc, 1e-6f) : 0.f;
-        }
-        __syncthreads();
-        for (int cl = 0; cl < nc; ++cl) {
-            const float d = s_dy[cl][i], sc = s_sc[cl], isc = s_isc[cl];
-            const float4 f4 = *reinterpret_cast<const float4 *>(&s_ft[cl][4 * fg]);
-            const float fv[4] = {f4.x, f4.y, f4.z, f4.w};
+        for (int i4 = 0; i4 < PH / 4; ++i4) {
+            const float4 v = live ? __ldg(reinterpret_cast<const float4 *>(dY + cell * PH) + i4) : make_float4(0.f, 0.f, 0.f, 0.f);
+            const float dv[4] = {v.x, v.y, v.z, v.w};
 #pragma unroll
             for (int u = 0; u < 4; ++u) {
-                const float df = d * fv[u];
-                acc[3 * u] += df;
-                acc[3 * u + 1] = fmaf(df, sc, acc[3 * u + 1]);
-                acc[3 * u + 2] = fmaf(df, isc, acc[3 * u + 2]);
+                const int i = 4 * i4 + u;
+#pragma unroll
+                for (int t = 0; t < 3; ++t) {
+                    float hi, lo;
+                    umma::split_tf32(dv[u] * (t == 0 ? 1.f : (t == 1 ? sc : isc)), hi, lo);
+                    colA[(t * 16 + i) * 4] = hi;                 // row stride 16 bytes = 4 floats
+                    colA[(64 + t * 16 + i) * 4] = lo;
+                }
+            }
+        }
+#pragma unroll
+        for (int f4 = 0; f4 < PF / 4; ++f4) {
+            const float4 v = live ? __ldg(reinterpret_cast<const float4 *>(FEAT + cell * PF) + f4) : make_float4(0.f, 0.f, 0.f, 0.f);
+            const float fv[4] = {v.x, v.y, v.z, v.w};
+#pragma unroll
+            for (int u = 0; u < 4; ++u) {
+                float hi, lo;
+                umma::split_tf32(fv[u], hi, lo);
+                colB[(4 * f4 + u) * 4] = hi;
+                colB[(64 + 4 * f4 + u) * 4] = lo;
+            }
+        }
+        umma::fence_smem_to_async();
+        __syncthreads();
+        if (tid == 0) {
+            umma::fence_after();
+#pragma unroll
+            for (int k = 0; k < PT / 8; ++k)                     // K = 8 cells = two chunks per MMA
+                umma::mma_tf32(tacc, umma::desc(s_a + k * 2 * PW_CH, PW_CH, 128), umma::desc(s_b + k * 2 * PW_CH, PW_CH, 128), ID,
+                               tile != t0 || k != 0);
+            umma::commit(bar);
+        }
+        umma::mbar_wait(bar, phase);                             // the operand tiles are free again
+        phase ^= 1u;
+    }
+    umma::fence_after();
+    {   // lane m of the accumulator: m < 48 -> hi rows (hi*hi + hi*lo), 64 <= m < 112 -> lo rows (lo*hi)
+        const int m = tid;
+        const bool hi_row = m < 48, lo_row = m >= 64 && m < 112;
+        const int n = hi_row ? m : m - 64, t = n >> 4, i = n & 15;
+#pragma unroll
+        for (int q = 0; q < 2; ++q) {
+            float a[32], b[32];
+            umma::tmem_ld32(trow + q * 32, a);                   // columns f = 32q .. (FEAT hi)
+            umma::tmem_ld32(trow + 64 + q * 32, b);              // columns 64 + f  (FEAT lo)
+            if (hi_row || lo_row) {
+#pragma unroll
+                for (int j = 0; j < 32; ++j) {
+                    const float v = hi_row ? a[j] + b[j] : a[j];
+                    if (v != 0.f) atomicAdd(gW + i * PU + (32 * q + j) * 3 + t, v);
+                }
             }
         }
     }
-#pragma unroll
-    for (int k = 0; k < 12; ++k)
-        if (acc[k] != 0.f) atomicAdd(gW + i * PU + (4 * fg) * 3 + k, acc[k]);
+    umma::fence_before();
+    __syncthreads();
+    if (warp == 0) umma::tmem_free(tacc, 128);
 }
 
 // backward into the rule embeddings: gEmb[rule] += count * dS1 + 2 count emb * dS2 (+ dMN / dMX at the arg rules)
@@ -572,7 +636,9 @@ int rl_pna_front_backward(const rl_cells *c, const rl_pna *p, const float *W, co
     if (!attr) { cudaFuncSetAttribute(k_pna_front_bwd, cudaFuncAttributeMaxDynamicSharedMemorySize, PB_END); attr = true; }
     k_pna_front_bwd<<<tile_grid(c), PT, PB_END, st>>>(*c, *p, W, dY, FEAT, SC, dstat);
     CHECK_LAUNCH("k_pna_front_bwd");
-    k_pna_w_grad<<<148 * 2, 256, 0, st>>>(*c, dY, FEAT, SC, gW);
+    static bool attr_w = false;
+    if (!attr_w) { cudaFuncSetAttribute(k_pna_w_grad, cudaFuncAttributeMaxDynamicSharedMemorySize, PW_END); attr_w = true; }
+    k_pna_w_grad<<<148, PT, PW_END, st>>>(*c, dY, FEAT, SC, gW);
     CHECK_LAUNCH("k_pna_w_grad");
     return RL_OK;
 }
