@@ -170,6 +170,9 @@ k_symbolic(rl_graph g, rl_rules r, rl_slots s, int depth, rl_frontier fr, int de
 }
 
 #define EDGE_GROUP 8
+#ifndef NUM_WARPS
+#define NUM_WARPS 4             // warps per k_numeric block (2, 4, 8 measured within 1.5 % of each other)
+#endif
 // Up to 32 valid destination rows of node v, one per lane (myrow = row index inside the node, -1 =
 // none).  Returns the lanes whose row ended up NON-ZERO (exact frontier support).
 template <typename CT, bool ROOT, bool PRUNE>
@@ -305,7 +308,7 @@ __device__ __forceinline__ uint32_t numeric_rows(const rl_graph &g, const rl_rul
 // one coalesced load, then the valid rows of all chunks of the same trie node are merged and expanded
 // 32 at a time (full tiles even when each chunk holds only a few valid rows).
 template <typename CT, bool ROOT, bool PRUNE>
-__global__ void __launch_bounds__(WARPS_PER_BLOCK * 32, 6)     // <= 40 registers: 6 blocks (48 warps) per SM -- latency-bound, swept 4..8
+__global__ void __launch_bounds__(NUM_WARPS * 32, 48 / NUM_WARPS)    // <= 40 registers, 48 warps per SM -- latency-bound; small blocks so a slow warp strands few slots
 k_numeric(rl_graph g, rl_rules r, rl_slots s, int depth, rl_frontier fr, int cpw)
 {
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
@@ -313,7 +316,7 @@ k_numeric(rl_graph g, rl_rules r, rl_slots s, int depth, rl_frontier fr, int cpw
     const int q = s.slot_head[slot];
     const int32_t *lp = r.lvl_ptr + (size_t)q * (r.max_len + 1);
     const int c_end = lp[depth];
-    const int c0 = lp[depth - 1] + (blockIdx.x * WARPS_PER_BLOCK + warp) * cpw;   // cpw (<= 32) chunks per warp
+    const int c0 = lp[depth - 1] + (blockIdx.x * NUM_WARPS + warp) * cpw;   // cpw (<= 32) chunks per warp
     if (c0 >= c_end) return;
     const int hc0 = lp[0];
     uint32_t *mbase = fr.row_mask + (size_t)s.mask_off[slot];
@@ -1243,9 +1246,9 @@ int rl_expand_level(const rl_graph *g, const rl_rules *r, const rl_slots *s, int
     // few when every chunk is expanded (more warps in flight to hide the look-up latency)
     static const int cpw_env = []() { const char *e = getenv("RL_CPW"); const int v = e ? atoi(e) : 0; return (v >= 1 && v <= 32) ? v : 0; }();
     const int cpw = cpw_env ? cpw_env : (force_dense ? 4 : 16);
-    dim3 grid((grid_chunks + WARPS_PER_BLOCK * cpw - 1) / (WARPS_PER_BLOCK * cpw), s->num_slots);
+    dim3 grid((grid_chunks + NUM_WARPS * cpw - 1) / (NUM_WARPS * cpw), s->num_slots);
     // force_dense: plain dense SpMM -- every row of every node is written (zeros included) and read
-#define LAUNCH_NUM(CT, ROOT, PRUNE) k_numeric<CT, ROOT, PRUNE><<<grid, WARPS_PER_BLOCK * 32, 0, st>>>(*g, *r, *s, depth, *fr, cpw)
+#define LAUNCH_NUM(CT, ROOT, PRUNE) k_numeric<CT, ROOT, PRUNE><<<grid, NUM_WARPS * 32, 0, st>>>(*g, *r, *s, depth, *fr, cpw)
     if (fr->count_bits == 32) {
         if (depth == 1) { if (force_dense) LAUNCH_NUM(uint32_t, true, false); else LAUNCH_NUM(uint32_t, true, true); }
         else { if (force_dense) LAUNCH_NUM(uint32_t, false, false); else LAUNCH_NUM(uint32_t, false, true); }
