@@ -391,7 +391,10 @@ def ground_chain(graph, h: torch.Tensor, r: int, body: List[int], etr: Optional[
         cache[key] = cr
         if len(cache) > _CHAIN_CACHE_MAX:
             cache.popitem(last=False)
-    gr = Grounder(graph, cr, h.device)
+    grs = cr.__dict__.setdefault("_grounders", {})               # one driver (and workspace) per cached chain and device
+    gr = grs.get(str(h.device))
+    if gr is None:
+        gr = grs[str(h.device)] = Grounder(graph, cr, h.device)
     B = int(h.shape[0])
     sl = gr.make_slots([r], [B], h.to(torch.int64), None, None if etr is None else etr.to(h.device, torch.int64))
     if len(body):

@@ -638,9 +638,11 @@ class PredictorPlus(_RuleModel):
         self.padding_index = graph.relation_size
         self._scratch = {}
         self.vocab_emb = torch.nn.Embedding(self.num_relations + 1, self.hidden_dim, padding_idx=self.num_relations)
-        if self.type in ('lstm', 'gru', 'rnn'):
-            # cuDNN RNNs default to TF32 matmuls (forward AND backward); the rule encoder must stay in
-            # true fp32 for the 1e-5 parity bar, and the backward runs outside any context manager
+        own_lstm = self.type == 'lstm' and self.fused_rnn and self.hidden_dim in (16, 32) and 1 <= self.num_layers <= 4
+        if self.type in ('lstm', 'gru', 'rnn') and not own_lstm:
+            # Only the encoders that run on cuDNN touch this process-global switch (the shipped lstm configs run on
+            # rl_rnn.cu and leave it alone): cuDNN RNNs default to TF32 matmuls, forward AND backward; the rule encoder
+            # must stay in true fp32 for the 1e-5 parity bar, and the backward runs outside any context manager.
             torch.backends.cudnn.allow_tf32 = False
         if self.type == 'lstm':
             self.rnn = torch.nn.LSTM(self.hidden_dim, self.hidden_dim, self.num_layers, batch_first=True)
