@@ -623,6 +623,15 @@ def main():
             roofline["moved_bytes_per_launch"] = moved / max(1, roofline["launches"])
             roofline["moved_bytes_source"] = "counted from the graph for this kernel's access pattern (bench.py: dense_expansion_traffic), not ncu"
             roofline["dram_frac"] = moved / (tot_ms / 1e3) / 1e9 / peak if tot_ms > 0 else None
+            # measured DRAM bytes per launch of the same kernels in the same mode: one `ncu --set full` capture (profiles/),
+            # valid for the default step size only -- a profiler cannot run inside a timed region
+            tj = os.path.join(os.path.dirname(os.path.abspath(__file__)), "profiles", "r2_traffic.json")
+            if os.path.exists(tj) and args.shape == "fb15k237" and not args.typed:
+                with open(tj) as f:
+                    tr = json.load(f)
+                if int(tr.get("batches_per_step", -1)) == per:
+                    roofline["traffic"] = float(tr["dram_bytes_per_launch"])
+                    roofline["traffic_source"] = tr["source"]
 
     # ---------------- end-to-end through the public fused API (host arrays in, losses out) --------
     trace = [] if args.trace_e2e else None

@@ -143,24 +143,32 @@ k_tail_fwd_tc(const int32_t *__restrict__ counters, int cap, const float *__rest
     const uint32_t s_whi = umma::smem_u32(smem + FS_WHI), s_wlo = umma::smem_u32(smem + FS_WLO);
     constexpr uint32_t ID = umma::idesc(UMMA_FMT_TF32, TILE, TJ, false, false);
     uint32_t phase = 0;
+    // the rows of a tile (F row, relation row of the cell's head) are fetched ONE TILE AHEAD: the dependent chain
+    // cell_key -> slot_head -> rel row and the F row fly while the MMAs of the current tile run and its epilogue is computed
+    float f[TH], r16[TH];
+    auto fetch = [&](long long tile) -> bool {
+        const long long cell = tile * TILE + tid;
+        const bool ok = tile < tiles && cell < C;
+        if (ok) {
+            load_row16(F + cell * TH, f);
+            load_row16(w.rel + (size_t)slot_head[cell_key[cell] >> 5] * TH, r16);
+        } else {
+#pragma unroll
+            for (int k = 0; k < TH; ++k) { f[k] = 0.f; r16[k] = 0.f; }
+        }
+        return ok;
+    };
+    bool live = fetch(blockIdx.x);
     for (long long tile = blockIdx.x; tile < tiles; tile += gridDim.x) {
         const long long cell = tile * TILE + tid;
-        const bool live = cell < C;
         float u[TK];
         {
-            float f[TH], nrm[TH];
-            if (live) load_row16(F + cell * TH, f);
-            else {
-#pragma unroll
-                for (int k = 0; k < TH; ++k) f[k] = 0.f;
-            }
+            float nrm[TH];
             cell_front<PRE>(sp, f, nrm);
 #pragma unroll
             for (int i = 0; i < TH; ++i) u[i] = live ? fmaxf(fmaf(sp[SP_GA + i], nrm[i], sp[SP_BE + i]), 0.f) : 0.f;
-            float r16[TH];
-            if (live) load_row16(w.rel + (size_t)slot_head[cell_key[cell] >> 5] * TH, r16);
 #pragma unroll
-            for (int i = 0; i < TH; ++i) u[TH + i] = live ? r16[i] : 0.f;
+            for (int i = 0; i < TH; ++i) u[TH + i] = r16[i];
         }
 #pragma unroll
         for (int c = 0; c < TK / 4; ++c) {
@@ -186,10 +194,11 @@ k_tail_fwd_tc(const int32_t *__restrict__ counters, int cap, const float *__rest
             }
             umma::commit(bar);
         }
+        const bool live_next = fetch(tile + gridDim.x);          // issued before the wait: in flight during the MMAs and the epilogue
         umma::mbar_wait(bar, phase);
         phase ^= 1u;
         umma::fence_after();
-        float z = b2;
+        float z0 = b2, z1 = 0.f;                                 // two chains: the 128-term dot product is latency-bound otherwise
         uint32_t word[4];
 #pragma unroll
         for (int q = 0; q < 4; ++q) {
@@ -197,17 +206,20 @@ k_tail_fwd_tc(const int32_t *__restrict__ counters, int cap, const float *__rest
             umma::tmem_ld32(trow + q * 32, a);
             uint32_t wb = 0u;
 #pragma unroll
-            for (int i = 0; i < 32; ++i) {
-                const float v = a[i] + sp[SP_B1 + q * 32 + i];
-                z = fmaf(sp[SP_W2 + q * 32 + i], fmaxf(v, 0.f), z);
-                wb |= (v > 0.f ? 1u : 0u) << i;
+            for (int i = 0; i < 32; i += 2) {
+                const float v0 = a[i] + sp[SP_B1 + q * 32 + i], v1 = a[i + 1] + sp[SP_B1 + q * 32 + i + 1];
+                z0 = fmaf(sp[SP_W2 + q * 32 + i], fmaxf(v0, 0.f), z0);
+                z1 = fmaf(sp[SP_W2 + q * 32 + i + 1], fmaxf(v1, 0.f), z1);
+                wb |= (v0 > 0.f ? 1u : 0u) << i;
+                wb |= (v1 > 0.f ? 1u : 0u) << (i + 1);
             }
             word[q] = wb;
         }
         if (live) {
-            zc[cell] = z;
+            zc[cell] = z0 + z1;
             bits[cell] = make_uint4(word[0], word[1], word[2], word[3]);
         }
+        live = live_next;
     }
     umma::fence_before();
     __syncthreads();

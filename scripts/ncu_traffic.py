@@ -1,8 +1,8 @@
-"""profiles/r1_traffic.json from an `ncu --set full` capture of one dense-mode expansion:
+"""profiles/r<N>_traffic.json from an `ncu --set full` capture of one dense-mode expansion:
     ncu --set full --clock-control none --import-source on -k regex:"k_numeric|k_symbolic" -s <skip> -c 6 \\
         -o gpurun_out/expand python bench.py --steps 4 --warmup 3 --dense --no-cpu-baseline --no-extras
     ncu -i gpurun_out/expand.ncu-rep --page raw --csv > profiles/<name>.csv
-    python scripts/ncu_traffic.py profiles/<name>.csv <batches per step> > profiles/r1_traffic.json
+    python scripts/ncu_traffic.py profiles/<name>.csv <batches per step> > profiles/r2_traffic.json
 One expansion = k_symbolic + k_numeric per trie depth; bench.py reports dram bytes per rl_expand_level call."""
 import csv, json, sys
 
