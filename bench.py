@@ -72,7 +72,7 @@ class ClockSampler:
     def start(self):
         try:
             self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.index), "--query-gpu=" + self.QUERY,
-                                          "--format=csv,noheader,nounits", "-lms", "25"],
+                                          "--format=csv,noheader,nounits", "-lms", "100"],
                                          stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
             self.thread = threading.Thread(target=self._read, daemon=True)
             self.thread.start()
@@ -158,6 +158,25 @@ def cpu_reference_run(N, R, train, valid, test, rules, batches, steps, warmup, p
             "steps_done": len(times), "ms_per_step": 1e3 * total / len(times)}
 
 
+class quiet_gc:
+    """Timed regions run with the cyclic garbage collector parked: the rule set alone is ~10^6 small Python objects, and a
+    generation-2 collection in the middle of a loop is a 30-70 ms host stall that drains the GPU queue (and, through the
+    per-step all-reduce, stalls every other rank too)."""
+
+    def __enter__(self):
+        import gc
+        gc.collect()
+        gc.freeze()
+        self.was = gc.isenabled()
+        gc.disable()
+
+    def __exit__(self, *exc):
+        import gc
+        if self.was:
+            gc.enable()
+        gc.unfreeze()
+
+
 class Runner:
     """One model + optimizer on this rank with its dealt steps: device-resident and end-to-end loops."""
 
@@ -198,7 +217,7 @@ class Runner:
                         raise AssertionError("32-bit count overflow on the bench workload: " + str(e))
         torch.cuda.synchronize()
 
-    def device_loop(self, warmup, steps, level_events=False):
+    def _device_loop(self, warmup, steps, level_events=False):
         """Queries already in HBM.  -> (ms, queries, launches, flags, level events)."""
         from rnnlogic_b200 import _lib
         model, sk, per = self.model, self.sk, self.per
@@ -227,7 +246,12 @@ class Runner:
         losses = []
         sk.gr._run(slots[warmup], 32)
         dbg = os.environ.get("RL_BENCH_TRACE")
+        step_ev = []
         for s in range(warmup, n_steps):
+            if dbg:
+                ev = torch.cuda.Event(enable_timing=True)
+                ev.record()
+                step_ev.append(ev)
             t0 = time.perf_counter()
             gbuf = self.cellpath.GradBuffer(self.params)
             t1 = time.perf_counter()
@@ -251,6 +275,9 @@ class Runner:
         if self.world > 1:
             torch.distributed.barrier()
         ms = ev0.elapsed_time(ev1)
+        if dbg and len(step_ev) > 1:
+            per = [step_ev[i].elapsed_time(step_ev[i + 1]) for i in range(len(step_ev) - 1)]
+            print("[trace] device ms per step: " + " ".join("%.2f" % v for v in per), file=sys.stderr)
         launches = _lib.lib().rl_launch_count() - launches0
         events, sk.gr.level_events = sk.gr.level_events, None
         flags = flags_acc.cpu().numpy()
@@ -259,7 +286,7 @@ class Runner:
         assert all(torch.isfinite(l).all().item() for l in losses)
         return ms, sum(self.queries[s % len(self.steps)] for s in range(warmup, n_steps)), launches, events
 
-    def graph_loop(self, warmup, steps):
+    def _graph_loop(self, warmup, steps):
         """The reference's schedule (one batch per optimizer step) through the per-head CUDA graphs, the way
         TrainerPredictor.train drives them: host arrays in, loss out; per step two graph replays (grounding of step k+1
         enqueued behind the scoring of step k), one event wait, one optimizer step.  -> (ms, queries)"""
@@ -299,7 +326,7 @@ class Runner:
         torch.cuda.synchronize()
         return e0.elapsed_time(e1), nq
 
-    def e2e_loop(self, warmup, steps, trace=None):
+    def _e2e_loop(self, warmup, steps, trace=None):
         """Host int arrays in, losses out, through submit / prepare / finish / result (software-pipelined by one
         step; every step does its own packed H2D copy and its own D2H read).  -> (ms, queries, h2d, d2h)."""
         from rnnlogic_b200.data import StepPrefetcher
@@ -318,27 +345,53 @@ class Runner:
             torch.distributed.barrier()
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         e0.record()
+        t_p0 = time.perf_counter()
         packed = StepPrefetcher(model.pack_train_step, seq[warmup:], depth=2)        # loader thread, inside the timed region
         ticket = model.submit_train_step(next(packed), 0.2, grad_scale=1.0 / per)
+        if trace is not None:
+            print("[trace] loader start + first submit: %.2f ms" % ((time.perf_counter() - t_p0) * 1e3), file=sys.stderr)
         h2d = d2h = 0
         for s in range(warmup, n_steps):
             t_a = time.perf_counter()
             pending = self.start_allreduce(ticket.gbuf)
-            prep = model.prepare_train_step(next(packed)) if s + 1 < n_steps else None
+            t_1 = time.perf_counter()
+            nb = next(packed) if s + 1 < n_steps else None
+            t_2 = time.perf_counter()
+            prep = model.prepare_train_step(nb) if nb is not None else None
+            t_3 = time.perf_counter()
             self.finish_step(pending, ticket.gbuf)
+            t_4 = time.perf_counter()
             nxt = prep.finish(0.2, grad_scale=1.0 / per) if prep is not None else None
             t_b = time.perf_counter()
             loss, tsum = ticket.result()
-            if trace is not None:
-                trace.append((t_b - t_a, time.perf_counter() - t_b))
+            t_c = time.perf_counter()
             assert torch.isfinite(loss).all()
             h2d += ticket.h2d_bytes
             d2h += ticket.d2h_bytes
-            ticket = nxt
+            t_d = time.perf_counter()
+            ticket = nxt                                         # drops the finished step (its slots, staging and gradient buffer)
+            if trace is not None:      # all-reduce enqueue | packed batch from the loader thread | prepare | wait + Adam | finish | result wait | check | release
+                trace.append((t_1 - t_a, t_2 - t_1, t_3 - t_2, t_4 - t_3, t_b - t_4, t_c - t_b, t_d - t_c, time.perf_counter() - t_d))
         e1.record()
         torch.cuda.synchronize()
+        if trace is not None:
+            print("[trace] e2e region %.2f ms for %d steps (host wall %.2f ms)" % (e0.elapsed_time(e1), steps, (time.perf_counter() - t_p0) * 1e3),
+                  file=sys.stderr)
         return e0.elapsed_time(e1), sum(self.queries[s % len(self.steps)] for s in range(warmup, n_steps)), h2d, d2h
 
+
+
+    def device_loop(self, *a, **k):
+        with quiet_gc():
+            return self._device_loop(*a, **k)
+
+    def graph_loop(self, *a, **k):
+        with quiet_gc():
+            return self._graph_loop(*a, **k)
+
+    def e2e_loop(self, *a, **k):
+        with quiet_gc():
+            return self._e2e_loop(*a, **k)
 
 def dense_expansion_traffic(kg, cr, heads):
     """Bytes the expansion kernels MOVE in dense mode for the given slot heads -- a model of the kernel's own behaviour,
@@ -642,7 +695,10 @@ def main():
         print("[bench] headline: value %.0f q/s (%.3f ms/step), e2e %.0f q/s, dense-mode roofline frac %.3f, expansion share %.2f"
               % (value, elapsed_ms / args.steps, e2e_value, roofline["frac"], roofline_product["share_of_step"]), file=sys.stderr)
     if args.trace_e2e and rank == 0:
-        print("e2e per step, host enqueue/wait ms: " + " ".join("%.2f/%.2f" % (a * 1e3, b * 1e3) for a, b in trace), file=sys.stderr)
+        tr = np.asarray(trace) * 1e3
+        print("e2e host ms per step [all-reduce enqueue | loader wait | prepare | nccl wait + Adam | finish | result wait | check | release]: median "
+              + " ".join("%.3f" % v for v in np.median(tr, 0)) + " | mean " + " ".join("%.3f" % v for v in tr.mean(0))
+              + " | max " + " ".join("%.3f" % v for v in tr.max(0)), file=sys.stderr)
 
     line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
             "ms_per_step": elapsed_ms / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
