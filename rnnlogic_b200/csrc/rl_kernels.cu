@@ -68,12 +68,14 @@ __global__ void k_prepare_slots(rl_graph g, int S, const int32_t *__restrict__ s
 //              entity up in the relation's forward DCSR and ORs the reached destination rows into
 //              the node's row bitmap (one 32-bit word per 32-row chunk).  A parent with more than
 //              dense_num/dense_den of its rows valid switches the node to "all rows" (plain SpMM).
-//  k_numeric   one warp per chunk of <= 32 destination rows: builds the compact list of in-edges
-//              of the chunk's valid rows (warp scan), fetches the sources 32 at a time (coalesced),
-//              resolves each source's parent-frontier row with one 8-byte rank-table load + one
-//              bitmap word, then pulls the parent rows (128 B each, lane = query, 8 loads in
-//              flight) and reduces them per destination row.  Rows outside the bitmap are never
-//              written or read.  The query's own edge is cut with an exact integer fix-up.
+//  k_numeric   one warp per run of chunks: the valid rows of a trie node are expanded 32 at a time.
+//              Depth > 1: warp-scan compaction of the rows' pair-table entries (the in-edges whose
+//              source is a tail of the parent relation, already resolved to parent rows), coalesced
+//              fetch, one parent-bitmap word per entry, then the live parent rows are pulled (128 B
+//              each, lane = query, 8 loads in flight) and reduced per destination row.
+//              Depth 1: each lane looks the row up in the sorted forward list of its own query entity.
+//              Rows outside the bitmap are never written or read.  The query's own edge is cut with
+//              an exact integer fix-up.
 // ------------------------------------------------------------------------------------------
 __device__ __forceinline__ int srank_row(const rl_graph &g, int rel, int e)
 {
@@ -198,19 +200,7 @@ __device__ __forceinline__ uint32_t numeric_rows(const rl_graph &g, const rl_rul
     const int grow = ra.w + max(myrow, 0);                   // global row (dst_ptr[rel] + row)
     // depth 1: the row's in-edges; deeper: the row's entries of the (parent relation, relation) pair table --
     // only the in-edges whose source is a tail of the parent relation, already resolved to parent rows
-    const int32_t *__restrict__ rs = ROOT ? g.row_start + grow : r.pair_ptr + (r.node_pair_off[v] + max(myrow, 0));
-    const int my_rs = active ? rs[0] : 0;
-    const int my_re = active ? rs[1] : 0;
     const int my_dst = active ? g.row_dst[grow] : -1;
-    const int deg = my_re - my_rs;
-    int P = deg;                                            // inclusive scan of deg over lanes
-#pragma unroll
-    for (int o = 1; o < 32; o <<= 1) {
-        const int t = __shfl_up_sync(FULL, P, o);
-        if (lane >= o) P += t;
-    }
-    const int T = __shfl_sync(FULL, P, 31);
-    const int my_first = P - deg;                            // position of my row's first edge in the list
     const bool masked = (rho == q);
     const int eh = masked ? lane_eh : -1;
     const int et = masked ? lane_et : -1;
@@ -243,6 +233,46 @@ __device__ __forceinline__ uint32_t numeric_rows(const rl_graph &g, const rl_rul
         acc = 0;
     };
 
+    constexpr bool SEARCH = ROOT && PRUNE;                    // dense mode (every row of a node) keeps the streaming in-edge scan
+    if (SEARCH) {
+        // Depth 1: the count of row d for query b is the multiplicity of the edge (h_b -> d).  Each lane searches d in the
+        // SORTED forward list of its own h under this relation (forward DCSR) instead of the warp scanning every in-edge
+        // of d for the 32 sources that matter: log(out-degree of h) steps per row, independent of the row's in-degree.
+        int fs = 0, fe = 0;
+        if (h >= 0) {
+            const int sr = srank_row(g, rho, h);
+            if (sr >= 0) {
+                const int fb = g.fsrc_ptr[rho] + sr;
+                fs = g.frow_start[fb];
+                fe = g.frow_start[fb + 1];
+            }
+        }
+        for (uint32_t act = __ballot_sync(FULL, active); act; act &= act - 1) {
+            const int j = __ffs(act) - 1;
+            const int rj = __shfl_sync(FULL, myrow, j);
+            int lo = fs, hi = fe;
+            while (lo < hi) {
+                const int mid = (lo + hi) >> 1;
+                if (__ldg(g.fedge_dstrow + mid) < rj) lo = mid + 1; else hi = mid;
+            }
+            int cnt = 0;
+            while (lo + cnt < fe && __ldg(g.fedge_dstrow + lo + cnt) == rj) ++cnt;
+            acc = (unsigned long long)cnt;
+            flush(j);
+        }
+    } else {
+    const int32_t *__restrict__ rs = ROOT ? g.row_start + grow : r.pair_ptr + (r.node_pair_off[v] + max(myrow, 0));
+    const int my_rs = active ? rs[0] : 0;
+    const int my_re = active ? rs[1] : 0;
+    const int deg = my_re - my_rs;
+    int P = deg;                                            // inclusive scan of deg over lanes
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+        const int t = __shfl_up_sync(FULL, P, o);
+        if (lane >= o) P += t;
+    }
+    const int T = __shfl_sync(FULL, P, 31);
+    const int my_first = P - deg;                            // position of my row's first entry in the list
     for (int base = 0; base < T; base += 32) {
         const int n = min(32, T - base);
         const int k = min(base + lane, T - 1);
@@ -254,7 +284,7 @@ __device__ __forceinline__ uint32_t numeric_rows(const rl_graph &g, const rl_rul
         const int src = lane < n ? __ldg((ROOT ? g.edge_src : r.pair_ent) + e) : -1;     // ROOT: source entity; else: parent row
         int pr = -1;
         if (!ROOT && src >= 0 && ((pm[src >> 5] >> (src & 31)) & 1u)) pr = src;
-        // only edges whose parent row is non-zero are pulled (ROOT: every edge, the value is a compare)
+        // only entries whose parent row is non-zero are pulled (ROOT: every in-edge, the value is a compare)
         uint32_t todo = ROOT ? (n == 32 ? FULL : ((1u << n) - 1u)) : __ballot_sync(FULL, pr >= 0);
         while (todo) {
             CT vals[EDGE_GROUP];
@@ -285,6 +315,7 @@ __device__ __forceinline__ uint32_t numeric_rows(const rl_graph &g, const rl_rul
         }
     }
     if (cur >= 0) flush(cur);
+    }
     if (nterm > 0 && nzrows) {
         const bool mine = (nzrows >> lane) & 1u;
         if (fr.items) {                                      // {row, first rule end, entity, rule ends} items for the aggregation / backward
