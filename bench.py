@@ -228,11 +228,12 @@ class Runner:
         torch.cuda.synchronize()
         if self.world > 1:
             torch.distributed.barrier()
-        flags_acc = torch.zeros(9, dtype=torch.int32, device=self.dev)
+        flags_acc = torch.zeros(17, dtype=torch.int32, device=self.dev)
         for s in range(warmup):
             gbuf = self.cellpath.GradBuffer(self.params)
             model.step_on_slots(sk, slots[s], 0.2, 1.0 / per, gbuf)
             flags_acc += slots[s].flags                  # (also warms the op: its first call loads a module, ~17 ms)
+            sk.gr.note_level_rows(slots[s], slots[s].flags[9:17].tolist())     # warm-up only: launch-shape feedback (a host read)
             self.finish_step(self.start_allreduce(gbuf), gbuf)
         flags_acc.zero_()
         torch.cuda.synchronize()

@@ -29,7 +29,7 @@ extern "C" {
 #endif
 
 #define RL_LANES 32
-#define RL_ABI_VERSION 3
+#define RL_ABI_VERSION 4
 
 enum rl_status {
     RL_OK = 0,
@@ -121,7 +121,8 @@ typedef struct rl_frontier {
     void *arena;           /* [rows][32] counts */
     uint32_t *row_mask;    /* one word per 32-row chunk */
     int32_t *node_cnt;     /* valid rows per (slot, node) */
-    int32_t *overflow;     /* set to 1 when a 32-bit count overflowed */
+    int32_t *overflow;     /* int32[9], zeroed by the caller: [0] set to 1 when a 32-bit count overflowed; [1 + d] non-zero
+                            * rows produced at depth d (d < 8) over all slots -- feedback for the next call's chunks_per_warp */
     /* Item list (may be all NULL when only rl_expand_level / rl_node_counts_dense are used): one
      * int32x4 record {row (slot-relative), t0, entity, n} per NON-ZERO row of every rule-end node
      * (the rules ending at that node are node_term_rule[t0 .. t0+n)),
@@ -207,10 +208,11 @@ int rl_pair_table(const rl_graph *g, int32_t n_pairs, const int32_t *pair_prel, 
  * grid_nodes / grid_chunks = max over the call's slots of the number of symbolic work items
  * (lvl_sym_ptr) / chunks at this depth.  A node whose parent has more than dense_num/dense_den of its rows valid takes all
  * its rows; force_dense != 0 does that for every node (plain dense SpMM: every algorithmic byte
- * of SURVEY.md 8d is moved -- the mode the roofline figure is quoted on). */
+ * of SURVEY.md 8d is moved -- the mode the roofline figure is quoted on).  chunks_per_warp: consecutive 32-row chunks one k_numeric warp owns (1..32; 0 = default 16, 4 in dense mode): many when
+ * most chunks are empty (one coalesced read of their bitmap words), few when the frontier is dense (finer, balanced work). */
 int rl_expand_level(const rl_graph *g, const rl_rules *r, const rl_slots *s, int32_t depth,
                     int32_t grid_nodes, int32_t grid_chunks, const rl_frontier *fr,
-                    int32_t dense_num, int32_t dense_den, int32_t force_dense, void *stream);
+                    int32_t dense_num, int32_t dense_den, int32_t force_dense, int32_t chunks_per_warp, void *stream);
 
 /* Bucket the frontier's item list by entity word (counting sort, idempotent).  Called by
  * rl_predictor_scores and rl_plus_mask themselves; exported for callers that drive the kernels. */

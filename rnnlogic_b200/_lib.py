@@ -122,7 +122,7 @@ _PROTOS = {
     "rl_launch_count": (C.c_longlong, []),
     "rl_prepare_slots": (C.c_int, [C.POINTER(RlGraph), C.c_int32, vp, vp, vp, vp, vp, C.c_int32, vp, vp, vp, vp, vp]),
     "rl_expand_level": (C.c_int, [C.POINTER(RlGraph), C.POINTER(RlRules), C.POINTER(RlSlots), C.c_int32,
-                                  C.c_int32, C.c_int32, C.POINTER(RlFrontier), C.c_int32, C.c_int32, C.c_int32, vp]),
+                                  C.c_int32, C.c_int32, C.POINTER(RlFrontier), C.c_int32, C.c_int32, C.c_int32, C.c_int32, vp]),
     "rl_sort_items": (C.c_int, [C.POINTER(RlGraph), C.POINTER(RlSlots), C.POINTER(RlFrontier), vp]),
     "rl_node_counts_dense": (C.c_int, [C.POINTER(RlGraph), C.POINTER(RlRules), C.POINTER(RlSlots), C.c_int32,
                                        C.c_int32, C.POINTER(RlFrontier), vp, vp]),

@@ -363,6 +363,7 @@ k_numeric(rl_graph g, rl_rules r, rl_slots s, int depth, rl_frontier fr, int cpw
     const int leh = s.lane_eh[slot * RL_LANES + lane];
     const int let_ = s.lane_et[slot * RL_LANES + lane];
     bool ovf = false;
+    int rows_done = 0;                                           // non-zero rows this warp produced (level statistic)
     while (todo) {
         const int v = __shfl_sync(FULL, my_node, __ffs(todo) - 1);
         const uint32_t seg = __ballot_sync(FULL, my_m != 0u && my_node == v);       // this node's chunks in my range
@@ -391,8 +392,11 @@ k_numeric(rl_graph g, rl_rules r, rl_slots s, int depth, rl_frontier fr, int cpw
             const uint32_t nz = numeric_rows<CT, ROOT, PRUNE>(g, r, s, fr, slot, q, hc0, mbase, v, myrow, h, leh, let_, ovf);
             if (have && !((nz >> lane) & 1u)) atomicAnd(mbase + (c0 + sl - hc0), ~(1u << bit));   // bitmap = exact support
             if (lane == 0 && nz) atomicAdd(fr.node_cnt + nzb + v, __popc(nz));
+            rows_done += __popc(nz);
         }
     }
+    // overflow[1 + depth]: non-zero rows of this depth over the whole call -- the host sizes the next call's launch with it
+    if (lane == 0 && rows_done && depth < 8) atomicAdd(fr.overflow + 1 + depth, rows_done);
     if (__any_sync(FULL, ovf) && lane == 0) fr.overflow[0] = 1;
 }
 
@@ -1261,7 +1265,7 @@ int rl_pair_table(const rl_graph *g, int32_t n_pairs, const int32_t *pair_prel, 
 
 int rl_expand_level(const rl_graph *g, const rl_rules *r, const rl_slots *s, int32_t depth, int32_t grid_nodes,
                     int32_t grid_chunks, const rl_frontier *fr, int32_t dense_num, int32_t dense_den,
-                    int32_t force_dense, void *stream)
+                    int32_t force_dense, int32_t chunks_per_warp, void *stream)
 {
     if (!g || !r || !s) return fail(RL_ERR_ARG, "rl_expand_level: null argument");
     if (check_frontier(fr, "rl_expand_level: incomplete rl_frontier") != RL_OK) return RL_ERR_ARG;
@@ -1276,7 +1280,7 @@ int rl_expand_level(const rl_graph *g, const rl_rules *r, const rl_slots *s, int
     // chunks per warp: many when most chunks are empty (one coalesced read of their bitmap words),
     // few when every chunk is expanded (more warps in flight to hide the look-up latency)
     static const int cpw_env = []() { const char *e = getenv("RL_CPW"); const int v = e ? atoi(e) : 0; return (v >= 1 && v <= 32) ? v : 0; }();
-    const int cpw = cpw_env ? cpw_env : (force_dense ? 4 : 16);
+    const int cpw = cpw_env ? cpw_env : (chunks_per_warp >= 1 && chunks_per_warp <= 32 ? chunks_per_warp : (force_dense ? 4 : 16));
     dim3 grid((grid_chunks + NUM_WARPS * cpw - 1) / (NUM_WARPS * cpw), s->num_slots);
     // force_dense: plain dense SpMM -- every row of every node is written (zeros included) and read
 #define LAUNCH_NUM(CT, ROOT, PRUNE) k_numeric<CT, ROOT, PRUNE><<<grid, NUM_WARPS * 32, 0, st>>>(*g, *r, *s, depth, *fr, cpw)

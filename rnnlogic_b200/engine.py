@@ -134,6 +134,7 @@ class Grounder:
         self._ws_cells_cap = 0
         self.cell_cap = 0
         self.generation = 0           # bumped whenever a workspace is reallocated (captured CUDA graphs hold its pointers)
+        self.level_density = {}       # depth -> non-zero rows per chunk seen by recent calls (see chunks_per_warp)
         self.level_events = None      # bench.py: list collecting (depth, start, end) CUDA events
 
     @staticmethod
@@ -204,9 +205,9 @@ class Grounder:
         o_sc = 10 * cap + n_bkt
         return {
             "arena": max(1, sl.arena_rows) * LANES * (1 if bits == 32 else 2),
-            # zeroed: row bitmaps | node counts | item counts | pad | buckets | candidate words | cell counters[8] | overflow
+            # zeroed: row bitmaps | node counts | item counts | pad | buckets | candidate words | cell counters[8] | overflow | rows per depth[8]
             "o_cnt": n_mask, "o_icnt": n_mask + n_cnt, "o_bkt": n_mask + n_cnt + S + n_pad,
-            "o_nz": o_nz, "o_ctr": o_nz + S * N, "state": o_nz + S * N + 8 + 1,
+            "o_nz": o_nz, "o_ctr": o_nz + S * N, "state": o_nz + S * N + 8 + 1 + 8,
             # scratch: items | items_sorted (int32x4 records, exact upper bound) | bucket offsets | item lane masks (x2) |
             # first cell per (slot, entity) | cells per slot | per-query CE statistics (x2)
             "n_items": 4 * cap, "o_boff": 8 * cap, "o_im": 8 * cap + n_bkt, "o_ims": 9 * cap + n_bkt,
@@ -241,10 +242,10 @@ class Grounder:
             sl.state = torch.zeros(n_state, dtype=torch.int32, device=dev)                    # one memset
             scratch = torch.empty(n_scratch, dtype=torch.int32, device=dev)
         sl.scratch = scratch
-        sl.overflow = sl.state[-1:]
+        sl.overflow = sl.state[lay["o_ctr"] + 8:lay["o_ctr"] + 9]
         sl.cell_counters = sl.state[lay["o_ctr"]:lay["o_ctr"] + 8]
         sl.slot_ncell = scratch[lay["o_ncell"]:lay["o_ncell"] + sl.S]
-        sl.flags = sl.state[lay["o_ctr"]:]                               # cell counters[8] | count overflow: one D2H read
+        sl.flags = sl.state[lay["o_ctr"]:]                 # cell counters[8] | count overflow | non-zero rows per depth[8]: one D2H read
         base, sb = sl.state.data_ptr(), scratch.data_ptr()
         coo_only = bool(getattr(sl, "coo_only", False))                  # cell paths: no entity-grouped copy of the items
         sl.frontier = _lib.RlFrontier(bits, sl.arena.data_ptr(), base, base + 4 * lay["o_cnt"],
@@ -265,11 +266,33 @@ class Grounder:
                 e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
                 e0.record()
             _lib.check(L.rl_expand_level(self.dg.ref(), self.dr.ref(), sl.ref(), depth, gn, gc, sl.fref(),
-                                         self.dense_num, self.dense_den, int(self.force_dense), _stream()),
+                                         self.dense_num, self.dense_den, int(self.force_dense), self.chunks_per_warp(depth), _stream()),
                        "rl_expand_level")
             if self.level_events is not None:
                 e1.record()
                 self.level_events.append((depth, e0, e1))
+
+    # ---- launch-shape feedback -------------------------------------------------------------------
+    # k_numeric gives one warp a run of consecutive 32-row chunks.  Long runs win when most chunks are empty (i.i.d.
+    # graphs: ~1 non-zero row per chunk), short runs when the frontier stays alive (typed graphs: ~9 rows per chunk; a
+    # 16-chunk run is then a warp's worth of thousands of entries and the launch ends on a few stragglers).  The kernel
+    # counts the non-zero rows it produced per depth (rl_frontier.overflow[1 + d]); whoever reads a call's flags back
+    # hands them to note_level_rows and the NEXT call is launched with the run length that density asks for.
+    def chunks_per_warp(self, depth: int) -> int:
+        d = self.level_density.get(depth)
+        if self.force_dense or d is None:
+            return 0                                                     # library default
+        return 16 if d < 2.0 else 8 if d < 4.0 else 4 if d < 6.0 else 2
+
+    def note_level_rows(self, sl, rows) -> None:
+        """rows[d] = non-zero rows the call produced at depth d (flags[9:17] of the call)."""
+        lc = self.cr.level_chunks[sl.heads]
+        for depth in range(1, min(self.cr.max_len, 7) + 1):
+            chunks = float(lc[:, depth - 1].sum())
+            if chunks > 0:
+                dens = float(rows[depth]) / chunks
+                old = self.level_density.get(depth)
+                self.level_density[depth] = dens if old is None else 0.5 * (old + dens)
 
     # ---- candidate cells (rl_cells) ------------------------------------------------------------
     cells_per_slot_hint = 24576       # first guess of the per-cell capacity; grows on demand (see ensure_cell_cap)

@@ -279,9 +279,10 @@ class _StepTicket:
             return self._done
         self.event.synchronize()
         host, ng, S = self.pinned, self.ng, self.sl.S
-        flags = host[2 * ng + S:]                           # cell counters[8] | count overflow
+        flags = host[2 * ng + S:]                           # cell counters[8] | count overflow | non-zero rows per depth[8]
         self.total_cells = int(flags[0].item())
         self.sk.gr.note_cell_count(self.total_cells)
+        self.sk.gr.note_level_rows(self.sl, flags[9:17].tolist())
         self.count_overflow = flags[8].item() != 0
         if self.count_overflow:
             raise RlStepOverflow("a path count overflowed 32 bits inside an enqueued step; redo it with "
