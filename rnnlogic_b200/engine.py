@@ -277,12 +277,13 @@ class Grounder:
     # graphs: ~1 non-zero row per chunk), short runs when the frontier stays alive (typed graphs: ~9 rows per chunk; a
     # 16-chunk run is then a warp's worth of thousands of entries and the launch ends on a few stragglers).  The kernel
     # counts the non-zero rows it produced per depth (rl_frontier.overflow[1 + d]); whoever reads a call's flags back
-    # hands them to note_level_rows and the NEXT call is launched with the run length that density asks for.
+    # hands them to note_level_rows and the NEXT call is launched with the run length that density asks for
+    # (swept on the B200: profiles/README.md).
     def chunks_per_warp(self, depth: int) -> int:
         d = self.level_density.get(depth)
         if self.force_dense or d is None:
             return 0                                                     # library default
-        return 16 if d < 2.0 else 8 if d < 4.0 else 4 if d < 6.0 else 2
+        return 16 if d < 4.0 else 4 if d < 6.0 else 2 if d < 8.0 else 1      # measured: i.i.d. 1.2 -> 16, WN18RR shape ~3 -> 16, typed 6-9 -> 2 / 1
 
     def note_level_rows(self, sl, rows) -> None:
         """rows[d] = non-zero rows the call produced at depth d (flags[9:17] of the call)."""
