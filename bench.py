@@ -492,8 +492,11 @@ def side_config(tag, kg, rules, batches, kw, per, steps, world, rank, dev, plus=
     ms, q = reduce_max_sum(ms, q, dev, world)
     out = {"e2e_queries_per_sec": q / (ms / 1e3), "ms_per_step": ms / steps, "steps": steps, "batches_per_step_per_gpu": per,
            "queries_per_step_per_gpu": int(np.mean(run.queries)), "h2d_bytes_per_step": h2d // steps, "d2h_bytes_per_step": d2h // steps}
+    gr = run.sk.gr
+    out["chunks_per_numeric_warp"] = {str(d): (gr.chunks_per_warp(d) or 16) for d in sorted(gr.level_density)}   # launch-shape feedback
     if rank == 0:
-        print("[bench] %s: %.0f q/s e2e, %.3f ms/step" % (tag, out["e2e_queries_per_sec"], out["ms_per_step"]), file=sys.stderr)
+        print("[bench] %s: %.0f q/s e2e, %.3f ms/step (chunks per k_numeric warp by depth: %s)"
+              % (tag, out["e2e_queries_per_sec"], out["ms_per_step"], out["chunks_per_numeric_warp"]), file=sys.stderr)
     del run, model
     torch.cuda.empty_cache()
     return out
