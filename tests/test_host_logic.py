@@ -418,3 +418,23 @@ def test_snake_deal_partitions_and_balances():
             want = [j for k, j in enumerate(order) if k % (2 * world) in (r, 2 * world - 1 - r)]
             assert shares[r] == want
     assert snake_deal([], 2, 0) == [] and snake_deal([5, 5, 5], 2, 0) == [0] and snake_deal([5, 5, 5], 2, 1) == [1, 2]
+
+
+def test_launch_shape_feedback_host_logic():
+    """Grounder.note_level_rows / chunks_per_warp (no CUDA needed): the density of a depth = non-zero rows the last calls
+    produced per chunk of that depth; sparse frontiers keep long chunk runs per k_numeric warp, dense ones get short runs;
+    dense mode and an unknown density fall back to the library default (0)."""
+    import types
+    import numpy as np
+    from rnnlogic_b200.engine import Grounder
+    gr = Grounder.__new__(Grounder)
+    gr.force_dense, gr.level_density = False, {}
+    gr.cr = types.SimpleNamespace(max_len=3, level_chunks=np.array([[100, 400, 300], [50, 200, 100]]))
+    sl = types.SimpleNamespace(heads=np.array([0, 1, 1]))            # chunks per depth: 200, 800, 500
+    assert [gr.chunks_per_warp(d) for d in (1, 2, 3)] == [0, 0, 0]
+    gr.note_level_rows(sl, [0, 240, 4000, 4600, 0, 0, 0, 0])         # rows[d]: 1.2, 5.0, 9.2 per chunk
+    assert [gr.chunks_per_warp(d) for d in (1, 2, 3)] == [16, 4, 1]
+    gr.note_level_rows(sl, [0, 240, 5600, 2400, 0, 0, 0, 0])         # running mean with the previous call: 1.2, 6.0, 7.0
+    assert abs(gr.level_density[2] - 6.0) < 1e-9 and [gr.chunks_per_warp(d) for d in (1, 2, 3)] == [16, 2, 2]
+    gr.force_dense = True
+    assert gr.chunks_per_warp(2) == 0
