@@ -120,12 +120,15 @@ class TrainerPredictor(object):
         # the graph, the rule set and the batches are ~10^6 long-lived Python objects: keep them out of the cyclic
         # collector's generations for the loop (a generation-2 pass over them is a 30-70 ms host stall per occurrence)
         import gc
-        gc.collect()
-        gc.freeze()
+        freeze = type(self.model).__name__ == "Predictor"        # PredictorPlus steps were bimodal with frozen generations
+        if freeze:
+            gc.collect()
+            gc.freeze()
         try:
             self._train_loop(batch_per_epoch, smoothing, print_every)
         finally:
-            gc.unfreeze()
+            if freeze:
+                gc.unfreeze()
         if self.scheduler:
             self.scheduler.step()
 
