@@ -109,6 +109,8 @@ def host_lib():
         L.rl_kg_triples.restype = C.POINTER(C.c_int64)
         L.rl_kg_triples.argtypes = [C.c_void_p, C.c_int, C.POINTER(C.c_int64)]
         L.rl_kg_free.argtypes = [C.c_void_p]
+        L.rl_compile_tries.restype = C.c_longlong
+        L.rl_compile_tries.argtypes = [C.c_longlong, C.c_longlong] + [C.c_void_p] * 9
         _host = L
     return _host
 

@@ -126,4 +126,63 @@ const int64_t *rl_kg_triples(void *h, int which, int64_t *count)
 }
 void rl_kg_free(void *h) { delete static_cast<Dataset *>(h); }
 
+// ---- rule compiler: rule list -> per-head prefix tries (rules.py: CompiledRules) ----------------------------------
+// Replaces the reference's relation2rules table (src/predictors.py:46-49, 186-189).  Rules are given flattened
+// (head[n], body_ptr[n+1], body[]).  Nodes are numbered by head relation, then depth, then first appearance in the rule
+// list -- the order the Python compiler used, so every table built on top of it is unchanged.  Outputs (caller-allocated,
+// capacity = total body length): node_rel / node_parent (global ids, -1 at depth 1) / node_depth / node_head,
+// head_node_ptr[R+1], rule_node[n] (-1 for an empty body).  Returns the number of nodes, or -1 - i when rule i uses a
+// relation outside [0, R).
+long long rl_compile_tries(long long n_rules, long long R, const long long *head, const long long *body_ptr,
+                           const long long *body, long long *node_rel, long long *node_parent, long long *node_depth,
+                           long long *node_head, long long *head_node_ptr, long long *rule_node)
+{
+    struct Local { long long rel, parent, depth; };                 // parent = local id inside the head's trie, -1 at depth 1
+    std::vector<std::vector<Local>> nodes((size_t)R);
+    std::vector<std::unordered_map<unsigned long long, long long>> index((size_t)R);   // (parent local id + 1) * R + rel -> local id
+    std::vector<long long> leaf_local((size_t)n_rules, -1);
+    for (long long i = 0; i < n_rules; ++i) {
+        const long long q = head[i];
+        if (q < 0 || q >= R) return -1 - i;
+        long long cur = -1;
+        for (long long k = body_ptr[i]; k < body_ptr[i + 1]; ++k) {
+            const long long r = body[k];
+            if (r < 0 || r >= R) return -1 - i;
+            const unsigned long long key = (unsigned long long)(cur + 1) * (unsigned long long)R + (unsigned long long)r;
+            auto it = index[q].find(key);
+            if (it == index[q].end()) {
+                const long long id = (long long)nodes[q].size();
+                nodes[q].push_back({r, cur, k - body_ptr[i] + 1});
+                index[q].emplace(key, id);
+                cur = id;
+            } else cur = it->second;
+        }
+        leaf_local[i] = cur;
+    }
+    long long total = 0;
+    std::vector<std::vector<long long>> gid((size_t)R);
+    for (long long q = 0; q < R; ++q) {
+        head_node_ptr[q] = total;
+        const auto &nd = nodes[q];
+        long long maxd = 0;
+        for (const Local &x : nd) maxd = x.depth > maxd ? x.depth : maxd;
+        std::vector<long long> start((size_t)maxd + 2, 0);          // stable counting sort by depth
+        for (const Local &x : nd) ++start[(size_t)x.depth + 1];
+        for (long long d = 1; d <= maxd + 1; ++d) start[(size_t)d] += start[(size_t)d - 1];
+        gid[q].resize(nd.size());
+        for (size_t j = 0; j < nd.size(); ++j) gid[q][j] = total + start[(size_t)nd[j].depth]++;
+        for (size_t j = 0; j < nd.size(); ++j) {
+            const long long g = gid[q][j];
+            node_rel[g] = nd[j].rel;
+            node_depth[g] = nd[j].depth;
+            node_head[g] = q;
+            node_parent[g] = nd[j].parent < 0 ? -1 : gid[q][(size_t)nd[j].parent];
+        }
+        total += (long long)nd.size();
+    }
+    head_node_ptr[R] = total;
+    for (long long i = 0; i < n_rules; ++i) rule_node[i] = leaf_local[i] < 0 ? -1 : gid[(size_t)head[i]][(size_t)leaf_local[i]];
+    return total;
+}
+
 }  // extern "C"

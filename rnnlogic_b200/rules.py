@@ -41,49 +41,30 @@ class CompiledRules:
         self.num_rules = len(rules)
         self.max_len = max([len(b) for _, b in rules] + [1])
         rel_rows = graph.rel_rows
-        # ---- tries -------------------------------------------------------------------------
-        tries: List[Dict[tuple, int]] = [dict() for _ in range(R)]
-        per_head_nodes: List[List[tuple]] = [[] for _ in range(R)]      # (depth, rel, parent_prefix)
-        rule_leaf: List[tuple] = []
-        zero_rules: List[List[int]] = [[] for _ in range(R)]
-        for idx, (head, body) in enumerate(rules):
-            if not (0 <= head < R) or any(not (0 <= b < R) for b in body):
-                raise ValueError("rule %d uses a relation id outside [0, %d)" % (idx, R))
-            body = tuple(body)
-            if len(body) == 0:
-                zero_rules[head].append(idx)
-                rule_leaf.append(None)
-                continue
-            trie = tries[head]
-            for d in range(1, len(body) + 1):
-                pre = body[:d]
-                if pre not in trie:
-                    trie[pre] = len(per_head_nodes[head])
-                    per_head_nodes[head].append((d, pre[-1], pre[:-1]))
-            rule_leaf.append((head, body))
-        # global node numbering: by head, then depth (stable)
-        node_rel, node_parent, node_depth, node_head = [], [], [], []
+        # ---- tries: native compiler (csrc_host/kg_loader.cpp: rl_compile_tries) ---------------
+        # nodes numbered by head, then depth, then first appearance in the rule list
+        n = self.num_rules
+        heads_a = np.fromiter((int(h) for h, _ in rules), dtype=np.int64, count=n)
+        body_ptr = np.zeros(n + 1, dtype=np.int64)
+        np.cumsum(np.fromiter((len(b) for _, b in rules), dtype=np.int64, count=n), out=body_ptr[1:])
+        total = int(body_ptr[-1])
+        body_a = np.fromiter((int(x) for _, b in rules for x in b), dtype=np.int64, count=total)
+        cap = max(1, total)
+        node_rel, node_parent = np.empty(cap, np.int64), np.empty(cap, np.int64)
+        node_depth, node_head = np.empty(cap, np.int64), np.empty(cap, np.int64)
         head_node_ptr = np.zeros(R + 1, dtype=np.int64)
-        gid: List[Dict[tuple, int]] = [dict() for _ in range(R)]
-        for q in range(R):
-            nodes = per_head_nodes[q]
-            order = sorted(range(len(nodes)), key=lambda i: nodes[i][0])
-            base = len(node_rel)
-            local_pre = {v: k for k, v in tries[q].items()}
-            for new, old in enumerate(order):
-                gid[q][local_pre[old]] = base + new
-            for old in order:
-                d, rel, ppre = nodes[old]
-                node_rel.append(rel)
-                node_depth.append(d)
-                node_head.append(q)
-                node_parent.append(gid[q][ppre] if len(ppre) else -1)
-            head_node_ptr[q + 1] = len(node_rel)
-        self.num_nodes = len(node_rel)
-        node_rel = np.array(node_rel, dtype=np.int64)
-        node_depth = np.array(node_depth, dtype=np.int64)
-        node_head = np.array(node_head, dtype=np.int64)
-        node_parent = np.array(node_parent, dtype=np.int64)
+        rule_node = np.full(max(1, n), -1, dtype=np.int64)
+        vp_ = lambda a: a.ctypes.data_as(C.c_void_p)
+        nn = int(_lib.host_lib().rl_compile_tries(n, R, vp_(heads_a), vp_(body_ptr), vp_(body_a), vp_(node_rel), vp_(node_parent),
+                                                  vp_(node_depth), vp_(node_head), vp_(head_node_ptr), vp_(rule_node)))
+        if nn < 0:
+            raise ValueError("rule %d uses a relation id outside [0, %d)" % (-1 - nn, R))
+        self.num_nodes = nn
+        node_rel, node_parent, node_depth, node_head = node_rel[:nn], node_parent[:nn], node_depth[:nn], node_head[:nn]
+        rule_node = rule_node[:n]
+        zero_rules: List[List[int]] = [[] for _ in range(R)]
+        for idx in np.flatnonzero(rule_node < 0):
+            zero_rules[int(heads_a[idx])].append(int(idx))
         node_rows = rel_rows[node_rel] if self.num_nodes else np.zeros(0, np.int64)
         # arena rows per head and per-node offset inside the head's arena
         csum = np.zeros(self.num_nodes + 1, dtype=np.int64)
@@ -109,8 +90,8 @@ class CompiledRules:
         self.level_nodes = np.diff(first_node.reshape(R, L1), axis=1)  # [R, max_len] nodes per (head, depth)
         self.head_chunks = lvl_ptr[:, -1] - lvl_ptr[:, 0]
         # rule ends: (rule id, node) pairs of the rules with a non-empty body
-        t_rule = np.array([i for i, lf in enumerate(rule_leaf) if lf is not None], dtype=np.int64)
-        t_node = np.array([gid[lf[0]][lf[1]] for lf in rule_leaf if lf is not None], dtype=np.int64)
+        t_rule = np.flatnonzero(rule_node >= 0).astype(np.int64)
+        t_node = rule_node[t_rule]
         self.num_terms = int(t_rule.shape[0])
         self.head_terms = np.bincount(node_head[t_node], minlength=R) if t_rule.shape[0] else np.zeros(R, np.int64)
         self.rule_node = np.full(self.num_rules, -1, dtype=np.int64)
