@@ -395,29 +395,60 @@ k_pred_cells_bwd(rl_graph g, rl_rules r, rl_slots s, rl_frontier fr, rl_cells c,
 // ------------------------------------------------------------------------------------------
 // log(softmax + 1e-8) CE on the cells (trainer.py:84,88-89)
 // ------------------------------------------------------------------------------------------
-// one thread per cell: per-query max of the cell logits, then per-query sum of exp(l - M) - exp(bias - M)
+// one thread per cell: per-query max of the cell logits, then per-query sum of exp(l - M) - exp(bias - M).
+// The cells of a slot are contiguous (slots in the order their blocks numbered them), so the 256 consecutive cells of a
+// block iteration belong to one or two slots -- the first cell's and the last cell's: their per-query partials are combined
+// in shared memory first (2 x 32 entries) and reach the global per-query words with one atomic per touched query instead of
+// one per cell; a cell of any other slot (tiny slots in between) goes to the global word directly.
 __global__ void __launch_bounds__(256)
 k_cell_max(rl_cells c, const float *__restrict__ bias, const float *__restrict__ zc)
 {
+    __shared__ uint32_t sm[64];
     const int n = min(c.counters[0], c.cap);
-    for (int i = blockIdx.x * 256 + threadIdx.x; i < n; i += gridDim.x * 256) {
-        const float l = (bias ? bias[c.cell_ent[i]] : 0.f) + zc[i];
-        atomicMax(c.qmax + c.cell_key[i], fkey(l));
+    for (int base = blockIdx.x * 256; base < n; base += gridDim.x * 256) {
+        if (threadIdx.x < 64) sm[threadIdx.x] = 0u;                // fkey(x) > 0 for every float
+        __syncthreads();
+        const int ka = c.cell_key[base] & ~31, kb = c.cell_key[min(base + 255, n - 1)] & ~31;   // query words of the two slots
+        const int i = base + threadIdx.x;
+        if (i < n) {
+            const float l = (bias ? bias[c.cell_ent[i]] : 0.f) + zc[i];
+            const int key = c.cell_key[i], ks = key & ~31;
+            if (ks == ka) atomicMax(sm + (key & 31), fkey(l));
+            else if (ks == kb) atomicMax(sm + 32 + (key & 31), fkey(l));
+            else atomicMax(c.qmax + key, fkey(l));
+        }
+        __syncthreads();
+        if (threadIdx.x < 64 && sm[threadIdx.x]) atomicMax(c.qmax + (threadIdx.x < 32 ? ka : kb) + (threadIdx.x & 31), sm[threadIdx.x]);
+        __syncthreads();
     }
 }
 
 __global__ void __launch_bounds__(256)
 k_cell_sum(rl_cells c, const float *__restrict__ bias, const double *__restrict__ acc, const float *__restrict__ zc)
 {
+    __shared__ float sm[64];
     const int n = min(c.counters[0], c.cap);
     const float Mg = bias ? (float)acc[0] : 0.f;
-    for (int i = blockIdx.x * 256 + threadIdx.x; i < n; i += gridDim.x * 256) {
-        const int key = c.cell_key[i];
-        const float bl = bias ? bias[c.cell_ent[i]] : 0.f;
-        const float Mc = fkey_inv(c.qmax[key]);
-        const float M = bias ? fmaxf(Mg, Mc) : Mc;
-        const float v = expf(bl + zc[i] - M) - (bias ? expf(bl - M) : 0.f);
-        if (v != 0.f) atomicAdd(c.qsum + key, v);
+    for (int base = blockIdx.x * 256; base < n; base += gridDim.x * 256) {
+        if (threadIdx.x < 64) sm[threadIdx.x] = 0.f;
+        __syncthreads();
+        const int ka = c.cell_key[base] & ~31, kb = c.cell_key[min(base + 255, n - 1)] & ~31;
+        const int i = base + threadIdx.x;
+        if (i < n) {
+            const int key = c.cell_key[i], ks = key & ~31;
+            const float bl = bias ? bias[c.cell_ent[i]] : 0.f;
+            const float Mc = fkey_inv(c.qmax[key]);
+            const float M = bias ? fmaxf(Mg, Mc) : Mc;
+            const float v = expf(bl + zc[i] - M) - (bias ? expf(bl - M) : 0.f);
+            if (v != 0.f) {
+                if (ks == ka) atomicAdd(sm + (key & 31), v);
+                else if (ks == kb) atomicAdd(sm + 32 + (key & 31), v);
+                else atomicAdd(c.qsum + key, v);
+            }
+        }
+        __syncthreads();
+        if (threadIdx.x < 64 && sm[threadIdx.x] != 0.f) atomicAdd(c.qsum + (threadIdx.x < 32 ? ka : kb) + (threadIdx.x & 31), sm[threadIdx.x]);
+        __syncthreads();
     }
 }
 
