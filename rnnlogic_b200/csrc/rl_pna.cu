@@ -107,15 +107,32 @@ k_pna_zr_stats(rl_graph g, rl_rules r, rl_slots s, rl_cells c, const float *__re
     }
 }
 
-// per-query sum and count of log(degree) over the query's cells (layers.py:109-113)
+// per-query sum and count of log(degree) over the query's cells (layers.py:109-113); a block's 256 consecutive cells belong
+// to one or two slots (the first cell's and the last cell's): combined in shared memory first, as in k_cell_sum
 __global__ void __launch_bounds__(256)
 k_pna_qscale(rl_cells c, rl_pna p, float *__restrict__ qlog, float *__restrict__ qn)
 {
+    __shared__ float sl[64], sn[64];
     const int n = min(c.counters[0], c.cap);
-    for (int i = blockIdx.x * 256 + threadIdx.x; i < n; i += gridDim.x * 256) {
-        const int key = c.cell_key[i];
-        atomicAdd(qlog + key, logf(p.deg[i] + 1.f));
-        atomicAdd(qn + key, 1.f);
+    for (int base = blockIdx.x * 256; base < n; base += gridDim.x * 256) {
+        if (threadIdx.x < 64) { sl[threadIdx.x] = 0.f; sn[threadIdx.x] = 0.f; }
+        __syncthreads();
+        const int ka = c.cell_key[base] & ~31, kb = c.cell_key[min(base + 255, n - 1)] & ~31;
+        const int i = base + threadIdx.x;
+        if (i < n) {
+            const int key = c.cell_key[i], ks = key & ~31;
+            const float lg = logf(p.deg[i] + 1.f);
+            if (ks == ka) { atomicAdd(sl + (key & 31), lg); atomicAdd(sn + (key & 31), 1.f); }
+            else if (ks == kb) { atomicAdd(sl + 32 + (key & 31), lg); atomicAdd(sn + 32 + (key & 31), 1.f); }
+            else { atomicAdd(qlog + key, lg); atomicAdd(qn + key, 1.f); }
+        }
+        __syncthreads();
+        if (threadIdx.x < 64 && sn[threadIdx.x] != 0.f) {
+            const int key = (threadIdx.x < 32 ? ka : kb) + (threadIdx.x & 31);
+            atomicAdd(qlog + key, sl[threadIdx.x]);
+            atomicAdd(qn + key, sn[threadIdx.x]);
+        }
+        __syncthreads();
     }
 }
 
