@@ -184,6 +184,7 @@ class quiet_gc:
 
 class Runner:
     """One model + optimizer on this rank with its dealt steps: device-resident and end-to-end loops."""
+    read_late = 2        # e2e: a step's losses are read this many steps behind the enqueue front (absorbs host jitter)
 
     def __init__(self, model, step_lists, per, world, dev, lr=0.005):
         from rnnlogic_b200.optim import Adam
@@ -333,8 +334,9 @@ class Runner:
         return e0.elapsed_time(e1), nq
 
     def _e2e_loop(self, warmup, steps, trace=None):
-        """Host int arrays in, losses out, through submit / prepare / finish / result (software-pipelined by one
-        step; every step does its own packed H2D copy and its own D2H read).  -> (ms, queries, h2d, d2h)."""
+        """Host int arrays in, losses out, through submit / prepare / finish / result (software-pipelined: a
+        step's losses are read ``read_late`` steps behind the enqueue front; every step does its own packed H2D copy and its
+        own D2H read inside the timed region).  -> (ms, queries, h2d, d2h)."""
         from rnnlogic_b200.data import StepPrefetcher
         model, per = self.model, self.per
         n_steps = warmup + steps
@@ -357,6 +359,7 @@ class Runner:
         if trace is not None:
             print("[trace] loader start + first submit: %.2f ms" % ((time.perf_counter() - t_p0) * 1e3), file=sys.stderr)
         h2d = d2h = 0
+        inflight, loss = [], torch.zeros(1)
         for s in range(warmup, n_steps):
             t_a = time.perf_counter()
             pending = self.start_allreduce(ticket.gbuf)
@@ -369,15 +372,23 @@ class Runner:
             t_4 = time.perf_counter()
             nxt = prep.finish(0.2, grad_scale=1.0 / per) if prep is not None else None
             t_b = time.perf_counter()
-            loss, tsum = ticket.result()
+            inflight.append(ticket)
+            if len(inflight) > self.read_late:                   # the step's D2H read, `read_late` steps behind the enqueue front
+                done = inflight.pop(0)
+                loss, tsum = done.result()
+                h2d += done.h2d_bytes
+                d2h += done.d2h_bytes
             t_c = time.perf_counter()
             assert torch.isfinite(loss).all()
-            h2d += ticket.h2d_bytes
-            d2h += ticket.d2h_bytes
             t_d = time.perf_counter()
-            ticket = nxt                                         # drops the finished step (its slots, staging and gradient buffer)
+            ticket = nxt                                         # the finished step goes out of scope (slots, staging, gradient buffer)
             if trace is not None:      # all-reduce enqueue | packed batch from the loader thread | prepare | wait + Adam | finish | result wait | check | release
                 trace.append((t_1 - t_a, t_2 - t_1, t_3 - t_2, t_4 - t_3, t_b - t_4, t_c - t_b, t_d - t_c, time.perf_counter() - t_d))
+        for done in inflight:                                    # drain: every step's result is read inside the timed region
+            loss, tsum = done.result()
+            assert torch.isfinite(loss).all()
+            h2d += done.h2d_bytes
+            d2h += done.d2h_bytes
         e1.record()
         torch.cuda.synchronize()
         if trace is not None:
