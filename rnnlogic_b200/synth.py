@@ -73,7 +73,10 @@ def synthetic_kg(shape: dict, seed: int = None, scale: float = 1.0):
     valid = _draw_triples(rng, int(n_valid * scale), half, N, rw, ew, perm, taken)
     test = _draw_triples(rng, int(n_test * scale), half, N, rw, ew, perm, taken)
     train = _draw_triples(rng, int(shape["train_base_triples"] * scale), half, N, rw, ew, perm, taken)
-    train = train[np.lexsort((train[:, 2], train[:, 1], train[:, 0]))]
+    if N * N * max(R, 1) < 2 ** 62:                              # one sort of a packed (h, r, t) key: same order as the lexsort
+        train = train[np.argsort((train[:, 0] * R + train[:, 1]) * N + train[:, 2], kind="stable")]
+    else:
+        train = train[np.lexsort((train[:, 2], train[:, 1], train[:, 0]))]
     return N, R, _with_inverses(train, half), _with_inverses(valid, half), _with_inverses(test, half)
 
 
@@ -214,7 +217,10 @@ def typed_kg(shape: dict, n_types: int = 12, seed: int = None):
     valid = draw(shape["valid_triples"] // 2)
     test = draw(shape["test_triples"] // 2)
     train = draw(shape["train_base_triples"])
-    train = train[np.lexsort((train[:, 2], train[:, 1], train[:, 0]))]
+    if N * N * max(R, 1) < 2 ** 62:                              # one sort of a packed (h, r, t) key: same order as the lexsort
+        train = train[np.argsort((train[:, 0] * R + train[:, 1]) * N + train[:, 2], kind="stable")]
+    else:
+        train = train[np.lexsort((train[:, 2], train[:, 1], train[:, 0]))]
     meta = {"etype": etype, "domain": np.concatenate([dom, ran]), "range": np.concatenate([ran, dom])}
     return N, R, _with_inverses(train, half), _with_inverses(valid, half), _with_inverses(test, half), meta
 
